@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver for oracle/_ref/librefsoft.so (the unmodified
+reference ref_soft C path compiled by oracle/Makefile).  Only tests/, bench.py's
+cpu_baseline / --impl reference legs and __graft_entry__.smoke() may import this.
+
+The reference keeps all state in globals, so one process = one renderer instance at one
+resolution; use `run_isolated()` / a subprocess for every (asset dir, resolution) pair."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "librefsoft.so")
+
+sys.path.insert(0, os.path.dirname(HERE))
+from tochris_b200.refdef import refdef_t  # noqa: E402
+
+
+class orc_edge_t(C.Structure):
+    _fields_ = [("u", C.c_int), ("u_step", C.c_int), ("v", C.c_int), ("v2", C.c_int),
+                ("surfs", C.c_ushort * 2), ("nearzi", C.c_float), ("owner", C.c_int)]
+
+
+class orc_surf_t(C.Structure):
+    _fields_ = [("key", C.c_int), ("flags", C.c_int), ("insubmodel", C.c_int), ("face", C.c_int),
+                ("nearzi", C.c_float), ("d_ziorigin", C.c_float), ("d_zistepu", C.c_float),
+                ("d_zistepv", C.c_float), ("nspans", C.c_int), ("entity", C.c_int)]
+
+
+class orc_span_t(C.Structure):
+    _fields_ = [("u", C.c_int), ("v", C.c_int), ("count", C.c_int), ("surf", C.c_int)]
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+class RefSoft:
+    def __init__(self, basedir: str, width: int, height: int, heap_mb: int = 64, verbose: int = 0):
+        if not available():
+            raise RuntimeError("oracle/_ref/librefsoft.so missing: run `make -C oracle` where /root/reference exists")
+        self.lib = C.CDLL(LIB)
+        L = self.lib
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_model.restype = C.c_void_p
+        L.orc_load_world.restype = C.c_void_p
+        L.orc_set_cvar.argtypes = [C.c_char_p, C.c_float]
+        L.orc_render.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.c_void_p]
+        L.orc_render_batch.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        self.width, self.height = width, height
+        if L.orc_init(basedir.encode(), width, height, heap_mb, verbose) != 0:
+            raise RuntimeError("orc_init: " + L.orc_last_error().decode())
+
+    def err(self) -> str:
+        return self.lib.orc_last_error().decode()
+
+    def load_world(self, name: str) -> int:
+        p = self.lib.orc_load_world(name.encode())
+        if not p:
+            raise RuntimeError("orc_load_world: " + self.err())
+        return p
+
+    def model(self, name: str) -> int:
+        p = self.lib.orc_model(name.encode())
+        if not p:
+            raise RuntimeError("orc_model: " + self.err())
+        return p
+
+    def set_cvar(self, name: str, value: float):
+        if self.lib.orc_set_cvar(name.encode(), value) != 0:
+            raise KeyError(name)
+
+    def struct_sizes(self):
+        buf = (C.c_int * 16)()
+        n = self.lib.orc_struct_sizes(buf, 16)
+        return list(buf[:n])
+
+    def clear(self, fbval: int = 0, zval: int = 0):
+        self.lib.orc_clear_buffers(fbval, zval)
+
+    def flush_caches(self):
+        self.lib.orc_flush_caches()
+
+    def render(self, rd: refdef_t, want_z: bool = True):
+        fb = np.empty((self.height, self.width), dtype=np.uint8)
+        z = np.empty((self.height, self.width), dtype=np.int16) if want_z else None
+        rc = self.lib.orc_render(C.byref(rd), fb.ctypes.data, z.ctypes.data if want_z else None)
+        if rc != 0:
+            raise RuntimeError("orc_render: " + self.err())
+        return fb, z
+
+    def render_batch(self, rds, want_fb: bool = True, want_z: bool = True):
+        n = len(rds)
+        fb = np.empty((n, self.height, self.width), dtype=np.uint8) if want_fb else None
+        z = np.empty((n, self.height, self.width), dtype=np.int16) if want_z else None
+        secs = C.c_double(0)
+        rc = self.lib.orc_render_batch(rds, n, fb.ctypes.data if want_fb else None,
+                                       z.ctypes.data if want_z else None, C.byref(secs))
+        if rc != 0:
+            raise RuntimeError("orc_render_batch: " + self.err())
+        return fb, z, secs.value
+
+    # ---- stage dumps (edges before the scan, surfaces and spans as drawn) ----
+    def dump_enable(self, on: bool = True, maxedges: int = 20000, maxsurfs: int = 8000, maxspans: int = 400000):
+        self.lib.orc_dump_enable(int(on), maxedges, maxsurfs, maxspans)
+
+    def dump_get(self):
+        pe, ps, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ne, ns, np_ = C.c_int(), C.c_int(), C.c_int()
+        self.lib.orc_dump_get(C.byref(pe), C.byref(ne), C.byref(ps), C.byref(ns), C.byref(pp), C.byref(np_))
+
+        def arr(ptr, n, ty):
+            if n == 0:
+                return np.zeros(0, dtype=np.dtype(ty))
+            a = (ty * n).from_address(ptr.value)
+            return np.frombuffer(a, dtype=np.dtype(ty)).copy()
+        return arr(pe, ne.value, orc_edge_t), arr(ps, ns.value, orc_surf_t), arr(pp, np_.value, orc_span_t)
+
+    def counters(self):
+        a = (C.c_int * 8).in_dll(self.lib, "orc_counters")
+        return dict(outofsurfaces=a[0], outofedges=a[1], nsurfs=a[2], nedges=a[3], c_surf=a[4])
