@@ -1,0 +1,177 @@
+/*
+ * ref_cuda.h -- C-ABI of libref_cuda.so, the B200 drop-in for the ref_soft renderer of
+ * viciious/tochris (ToChriS Quake 1.67).
+ *
+ * The reference has no plugin struct: its renderer boundary is the set of C symbols in
+ * client/render.h:25-53 plus the data structs of client/ref.h:37-108 and the `vid`
+ * global of client/vid.h:34-44.  This header declares
+ *   (1) the same data structs, byte-compatible on LP64 (refdef_t 136 B, entity_t 80 B ...),
+ *   (2) the render.h entry points with identical names and signatures, so engine objects
+ *       link against libref_cuda.so in place of ref_soft/ *.o,
+ *   (3) a batched extension (RC_*) that renders many independent views per call and
+ *       reports errors through return codes instead of Sys_Error/exit,
+ *   (4) a refexport_t-shaped table (GetRefAPI) with BASELINE.json's north_star naming.
+ * Only plain pointers and sizes cross this boundary.
+ */
+#ifndef REF_CUDA_H
+#define REF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ client/ref.h ---- */
+#ifndef RC_NO_REF_TYPES
+typedef float vec_t;
+typedef vec_t vec3_t[3];
+typedef unsigned char byte;
+typedef int qboolean;
+
+#define MAX_LIGHTSTYLES 64          /* common/quakedef.h:105 */
+#define MAX_STYLESTRING 64          /* common/quakedef.h:111 */
+#define MAX_DLIGHTS     32          /* client/ref.h:31 */
+
+#define RF_VIEWERMODEL  1           /* common/quakedef.h:228-234 */
+#define RF_WEAPONMODEL  2
+#define RF_DEPTHSCALE   4
+#define RF_MINLIGHT     8
+#define RF_FULLBRIGHT   16
+#define RF_NOSHADOW     32
+#define RF_CULLVIS      64
+#define RDF_NOWORLDMODEL 1          /* common/quakedef.h:238-239 */
+#define RDF_UNDERWATER   2
+
+typedef struct { vec3_t org; int color; } particle_t;                 /* ref.h:37-41 */
+typedef struct { vec3_t origin; float radius; } dlight_t;             /* ref.h:43-47 */
+typedef struct { int destcolor[3]; int percent; } cshift_t;           /* ref.h:49-53 */
+typedef struct { int length; char map[MAX_STYLESTRING]; } lightstyle_t; /* ref.h:55-59 */
+
+struct model_s;
+typedef struct entity_s {                                             /* ref.h:61-80 */
+    float           framelerp;
+    struct model_s *model;
+    int             number;
+    int             flags;
+    int             skinnum;
+    byte           *colormap;
+    vec3_t          origin;
+    vec3_t          angles;
+    int             frame;
+    int             oldframe;
+    float           syncbase;
+} entity_t;
+
+typedef struct {                                                      /* ref.h:82-107 */
+    int           x, y, width, height;
+    float         time;
+    float         oldtime;
+    int           flags;
+    float         fov_x, fov_y;
+    vec3_t        vieworg;
+    vec3_t        viewangles;
+    lightstyle_t *lightstyles;       /* [MAX_LIGHTSTYLES] */
+    int           num_entities;
+    entity_t     *entities;
+    int           num_dlights;
+    dlight_t     *dlights;
+    int           num_particles;
+    particle_t   *particles;
+    int           num_cshifts;
+    cshift_t     *cshifts;
+} refdef_t;
+#endif /* RC_NO_REF_TYPES */
+
+/* ------------------------------------------------------- client/render.h:25-53 set ---- */
+struct model_s *Mod_ForName (char *name, qboolean crash);      /* render.h:25  r_model.c:339 */
+void  Mod_TouchModel (char *name);                             /* render.h:26 */
+void  R_Init (void);                                           /* render.h:28  r_main.c:185 */
+void  R_RenderView (refdef_t *refdef);                         /* render.h:29  r_main.c:988 */
+void  Mod_Init (void);                                         /* render.h:32 */
+void  Mod_ClearAll (void);                                     /* render.h:33 */
+int   Mod_Flags (struct model_s *model);                       /* render.h:34 */
+void  R_BeginFrame (void);                                     /* render.h:36  r_main.c:951 */
+void  R_EndFrame (void);                                       /* render.h:37  r_main.c:961 */
+void  R_NewMap (struct model_s *worldmodel);                   /* render.h:39  r_main.c:258 */
+void  R_TranslatePlayerSkin (int playernum, struct model_s *model, int skinnum, int top, int bottom); /* render.h:40 (empty in ref_soft, r_misc.c:372) */
+
+/* ---------------------------------------------------------------- batched extension ---- */
+typedef struct {
+    int   width, height;      /* vid.width / vid.height: every view of a batch shares them */
+    int   device;             /* CUDA device ordinal (one process per GPU) */
+    const char *basedir;      /* files are read from <basedir>/id1/<name> like COM_LoadFile */
+    /* cvars that change pixels (r_main.c:108-134, d_init.c:26-28); RC_DefaultConfig fills
+     * the reference defaults */
+    float r_clearcolor, r_fullbright, r_ambient, r_drawentities, r_drawviewmodel, r_waterwarp,
+          r_fastsky, r_skycolor, r_lerpmodels, d_mipcap, d_mipscale, r_maxsurfs, r_maxedges;
+    size_t surfcache_bytes;   /* device surface-cache pool (0: default) */
+    int   max_views_in_flight;/* views processed per pipeline pass (0: derived from memory) */
+} rc_config_t;
+
+void RC_DefaultConfig (rc_config_t *cfg);
+
+/* Creates the renderer (CUDA context, tables, palette/colormap from <basedir>/id1/gfx).
+ * Replaces VID_Init + R_Init (common/host.c:837-841).  Returns RC_OK or a negative RC_ERR_*. */
+int  RC_Init (const rc_config_t *cfg);
+void RC_Shutdown (void);
+const char *RC_LastError (void);
+
+/* Mod_ForName + R_NewMap in one call, with an error code instead of Sys_Error
+ * (client/cl_parse.c:271,294). */
+int  RC_LoadWorld (const char *name);
+
+/* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
+ * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)
+ * n*height*width int16.  Host<->device copies happen inside the call.
+ * Returns RC_OK or RC_ERR_*; *status (may be NULL) receives RC_STAT_* bits. */
+int  RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out, int *status);
+
+/* Same, outputs stay on the device (fb_dev / z_dev are CUDA device pointers owned by the
+ * caller, e.g. torch tensors; z_dev may be 0).  Work is enqueued on `stream`
+ * (a cudaStream_t, 0 = legacy default) and is complete when the stream reaches this point. */
+int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status);
+
+/* Drops every cached surface block (D_FlushCaches, d_surf.c:101). */
+void RC_FlushCaches (void);
+
+/* Counters of the last RC_RenderViews* call: kernels launched, edges, surfs, spans,
+ * 8-pixel blocks, surface-cache texels built, per-stage device milliseconds when
+ * profiling was enabled with RC_SetProfiling(1). */
+typedef struct {
+    int    kernel_launches;
+    long long edges, surfs, spans, blocks, cache_texels, cache_jobs, faces;
+    float  ms_walk, ms_faces, ms_scan, ms_surfprep, ms_cache, ms_draw, ms_total;
+    float  ms_h2d, ms_d2h;
+} rc_stats_t;
+void RC_GetStats (rc_stats_t *out);
+void RC_SetProfiling (int on);
+
+/* Stage readback for tests: copies the last batch's per-view records to the host.
+ * kind: 0 edges (rc_edge_t), 1 surfs (rc_surf_t), 2 spans (rc_span_t, whole batch; view ignored).
+ * Returns the number of records written (<= cap) or a negative error. */
+int  RC_DebugRead (int kind, int view, void *dst, int cap);
+
+/* north_star naming: a refexport_t-style table over the same functions. */
+typedef struct {
+    int   api_version;
+    void (*Init) (void);
+    void (*BeginRegistration) (struct model_s *world);   /* = R_NewMap      */
+    struct model_s *(*RegisterModel) (char *name);        /* = Mod_ForName   */
+    void (*BeginFrame) (void);                            /* = R_BeginFrame  */
+    void (*RenderFrame) (refdef_t *fd);                   /* = R_RenderView  */
+    void (*EndFrame) (void);                              /* = R_EndFrame    */
+    int  (*RenderFrames) (const refdef_t *fds, int n, uint8_t *fb, int16_t *z, int *status); /* = RC_RenderViews */
+} refexport_t;
+refexport_t GetRefAPI (int api_version);
+
+/* The single-view render.h path draws into the engine's `vid.buffer` / `d_pzbuffer`
+ * (client/vid.h:34-44, d_iface.h).  A host engine registers them here once
+ * (the reference's vid driver does the same job in VID_Init, win32/vid_win.c:237-291). */
+void RC_SetVidBuffers (uint8_t *buffer, int rowbytes, int16_t *zbuffer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

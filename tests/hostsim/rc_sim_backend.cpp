@@ -1,0 +1,187 @@
+/*
+ * tests/hostsim/rc_sim_backend.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Implements the rc_gpu_* backend interface (tochris_b200/csrc/rc_host.h) by running the
+ * per-thread kernel bodies of rc_pipeline.h in plain loops on the CPU.  It exists so that
+ * the host logic (loaders, view setup, C-ABI) and the kernel arithmetic can be checked
+ * against the oracle in the GPU-less container (`pytest -m "not gpu"`).  It is built into
+ * tests/hostsim/_build/libref_cuda_sim.so, never into libref_cuda.so: the product has no
+ * CPU path and fails at RC_Init without a CUDA device.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../tochris_b200/csrc/rc_host.h"
+#include "../../tochris_b200/csrc/rc_pipeline.h"
+
+struct rc_gpu_s {
+	int width, height;
+	rc_world_t w;
+	bool haveworld;
+	int maxedges, maxsurfs;
+	std::vector<int> sintable, intsintable;
+	std::vector<unsigned long long> cachekeys;
+	std::vector<int> cachevals;
+	std::vector<uint8_t> cachepool;
+	unsigned long long alloc[4];
+	rc_stats_t stats;
+	// last batch (debug reads)
+	std::vector<rc_edge_t> edges; std::vector<int> nedges; int edgecap;
+	std::vector<rc_surf_t> surfs; int surfcap; std::vector<int> nfaces;
+	std::vector<rc_span_t> spans; int nspans;
+};
+
+extern "C" {
+
+rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen)
+{
+	(void)device; (void)max_views; (void)err; (void)errlen;
+	rc_gpu_t *g = new rc_gpu_s ();
+	g->width = width; g->height = height; g->haveworld = false;
+	g->sintable.resize (RC_SIN_BUFFER_SIZE); g->intsintable.resize (RC_SIN_BUFFER_SIZE);
+	RC_BuildTurbTables (g->sintable.data (), g->intsintable.data (), RC_SIN_BUFFER_SIZE);
+	g->cachekeys.assign (1 << 16, RC_CACHE_EMPTY);
+	g->cachevals.assign (1 << 16, 0);
+	g->cachepool.resize (cache_bytes ? cache_bytes : (size_t)64 << 20);
+	memset (g->alloc, 0, sizeof(g->alloc));
+	memset (&g->stats, 0, sizeof(g->stats));
+	return g;
+}
+
+void rc_gpu_destroy (rc_gpu_t *g) { delete g; }
+
+int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen)
+{
+	(void)err; (void)errlen;
+	g->w = hw->w;
+	g->w.sintable = g->sintable.data ();
+	g->w.intsintable = g->intsintable.data ();
+	g->haveworld = true;
+	g->maxedges = maxedges; g->maxsurfs = maxsurfs;
+	rc_gpu_flush_caches (g);
+	return RC_OK;
+}
+
+void rc_gpu_flush_caches (rc_gpu_t *g)
+{
+	std::fill (g->cachekeys.begin (), g->cachekeys.end (), RC_CACHE_EMPTY);
+	g->alloc[1] = 0;
+}
+
+int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+		   int *status, char *err, size_t errlen)
+{
+	(void)stream;
+	const rc_world_t *w = &g->w;
+	int st = 0;
+	rc_frame_t f;
+	memset (&f, 0, sizeof(f));
+	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
+	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views;
+	f.facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
+	if (f.facecap < 1) f.facecap = 1;
+	std::vector<rc_facerec_t> facelist ((size_t)n * f.facecap);
+	std::vector<int> nfaces (n, 0);
+	std::vector<uint16_t> facepos ((size_t)n * w->numfaces, 0xFFFF);
+	f.facelist = facelist.data (); f.nfaces = nfaces.data (); f.facepos = facepos.data ();
+	f.edgecap = g->maxedges; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
+	g->edges.assign ((size_t)n * f.edgecap, rc_edge_t ());
+	g->nedges.assign (n, 0);
+	f.edges = g->edges.data (); f.nedges = g->nedges.data ();
+	f.surfcap = f.facecap + 2;
+	g->surfs.assign ((size_t)n * f.surfcap, rc_surf_t ());
+	f.surfs = g->surfs.data ();
+	f.spancap = n * g->height * 96;
+	f.blockcap = n * g->height * ((g->width + 7) / 8 + 96);
+	g->spans.assign (f.spancap, rc_span_t ());
+	std::vector<int> blockspan (f.blockcap, -1);
+	f.spans = g->spans.data (); f.blockspan = blockspan.data ();
+	g->alloc[0] = 0; g->alloc[2] = 0;
+	f.alloc = g->alloc;
+	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;
+	f.cachepool = g->cachepool.data (); f.cachecap = (long long)g->cachepool.size ();
+	f.jobcap = n * f.surfcap;
+	std::vector<rc_cachejob_t> jobs (f.jobcap);
+	f.jobs = jobs.data ();
+	f.fb = (uint8_t *)fb_dev; f.zb = (int16_t *)z_dev;
+	f.status = &st;
+
+	for (int vi = 0; vi < n; vi++) rc_walk_view (w, &f, vi);
+	for (int vi = 0; vi < n; vi++)
+		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p);
+	for (int vi = 0; vi < n; vi++)
+		for (int p = 0; p < nfaces[vi]; p++) rc_face_fixup (w, &f, vi, p);
+	for (int vi = 0; vi < n; vi++)
+		for (int line = 0; line < g->height; line++) rc_scan_line (w, &f, vi, line);
+	for (int vi = 0; vi < n; vi++)
+		for (int si = 1; si < nfaces[vi] + 2; si++) rc_surf_prep (w, &f, vi, si);
+	for (int vi = 0; vi < n; vi++)
+		for (int si = 1; si < nfaces[vi] + 2; si++) rc_surf_resolve (&f, vi, si);
+	int njobs = (int)g->alloc[2];
+	if (njobs > f.jobcap) njobs = f.jobcap;
+	long long texels = 0;
+	for (int j = 0; j < njobs; j++)
+	{
+		const rc_cachejob_t *job = &jobs[j];
+		const rc_face_t *fa = &w->faces[job->face];
+		unsigned bl[18 * 18];
+		int size = ((fa->extents[0] >> 4) + 1) * ((fa->extents[1] >> 4) + 1);
+		for (int i = 0; i < size; i++) bl[i] = rc_cache_luxel (w, job, i);
+		for (int y = 0; y < job->height; y++)
+			for (int x = 0; x < job->width; x++)
+				g->cachepool[job->dstofs + y * job->width + x] = rc_cache_texel (w, job, bl, x, y);
+		texels += (long long)job->width * job->height;
+	}
+	int nblocks = (int)(g->alloc[0] >> 32);
+	if (nblocks > f.blockcap) nblocks = f.blockcap;
+	for (int t = 0; t < nblocks; t++) rc_draw_block (w, &f, t);
+
+	g->nspans = (int)(g->alloc[0] & 0xFFFFFFFFu);
+	if (g->nspans > f.spancap) g->nspans = f.spancap;
+	g->edgecap = f.edgecap; g->surfcap = f.surfcap; g->nfaces = nfaces;
+	memset (&g->stats, 0, sizeof(g->stats));
+	g->stats.cache_jobs = njobs; g->stats.cache_texels = texels; g->stats.blocks = nblocks; g->stats.spans = g->nspans;
+	for (int vi = 0; vi < n; vi++) { g->stats.edges += g->nedges[vi]; g->stats.faces += nfaces[vi]; }
+	if (status) *status = st;
+	return RC_OK;
+}
+
+int rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+			int *status, char *err, size_t errlen)
+{
+	size_t px = (size_t)g->width * g->height;
+	memset (fb_out, 0, px * n);
+	std::vector<int16_t> ztmp;
+	if (!z_out) { ztmp.assign (px * n, 0); z_out = ztmp.data (); }
+	else memset (z_out, 0, px * n * 2);
+	return rc_gpu_render (g, views, n, fb_out, z_out, NULL, status, err, errlen);
+}
+
+void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }
+void rc_gpu_set_profiling (rc_gpu_t *g, int on) { (void)g; (void)on; }
+
+int rc_gpu_debug_read (rc_gpu_t *g, int kind, int view, void *dst, int cap)
+{
+	if (kind == 0)
+	{
+		int n = g->nedges[view] < cap ? g->nedges[view] : cap;
+		memcpy (dst, &g->edges[(size_t)view * g->edgecap], sizeof(rc_edge_t) * n);
+		return n;
+	}
+	if (kind == 1)
+	{
+		int n = g->nfaces[view] + 2 < cap ? g->nfaces[view] + 2 : cap;
+		memcpy (dst, &g->surfs[(size_t)view * g->surfcap], sizeof(rc_surf_t) * n);
+		return n;
+	}
+	if (kind == 2)
+	{
+		int n = g->nspans < cap ? g->nspans : cap;
+		memcpy (dst, g->spans.data (), sizeof(rc_span_t) * n);
+		return n;
+	}
+	return RC_ERR_ARG;
+}
+
+} // extern "C"

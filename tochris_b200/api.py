@@ -1,0 +1,148 @@
+"""ctypes binding of libref_cuda.so (include/ref_cuda.h).
+
+The library is the product; this module only marshals arguments.  There is no CPU
+rendering path: if the CUDA library is missing or no device is present, RefCuda() raises.
+`libpath` exists so the test-suite can point the same binding at the host-simulation
+build of the C-ABI (tests/hostsim), which is test infrastructure, not a fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .refdef import refdef_t
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libref_cuda.so")
+
+RC_STAT = {1: "EDGE_OVERFLOW", 2: "SURF_OVERFLOW", 4: "SPAN_POOL", 8: "AET_OVERFLOW", 16: "STACK_OVERFLOW",
+           32: "CACHE_POOL", 64: "STALE_CLIPVERT", 128: "FACELIST"}
+
+
+class rc_config_t(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("device", C.c_int), ("basedir", C.c_char_p),
+                ("r_clearcolor", C.c_float), ("r_fullbright", C.c_float), ("r_ambient", C.c_float),
+                ("r_drawentities", C.c_float), ("r_drawviewmodel", C.c_float), ("r_waterwarp", C.c_float),
+                ("r_fastsky", C.c_float), ("r_skycolor", C.c_float), ("r_lerpmodels", C.c_float),
+                ("d_mipcap", C.c_float), ("d_mipscale", C.c_float), ("r_maxsurfs", C.c_float),
+                ("r_maxedges", C.c_float),
+                ("surfcache_bytes", C.c_size_t), ("max_views_in_flight", C.c_int)]
+
+
+class rc_stats_t(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int),
+                ("edges", C.c_longlong), ("surfs", C.c_longlong), ("spans", C.c_longlong), ("blocks", C.c_longlong),
+                ("cache_texels", C.c_longlong), ("cache_jobs", C.c_longlong), ("faces", C.c_longlong),
+                ("ms_walk", C.c_float), ("ms_faces", C.c_float), ("ms_scan", C.c_float), ("ms_surfprep", C.c_float),
+                ("ms_cache", C.c_float), ("ms_draw", C.c_float), ("ms_total", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
+
+
+class rc_edge_t(C.Structure):
+    _fields_ = [("u", C.c_int), ("u_step", C.c_int), ("v", C.c_short), ("v2", C.c_short),
+                ("surfs", C.c_ushort * 2), ("rank", C.c_uint), ("pad", C.c_int * 3)]
+
+
+class rc_surf_t(C.Structure):
+    _fields_ = [("key", C.c_int), ("flags", C.c_int), ("face", C.c_int), ("insubmodel", C.c_int),
+                ("nearzi", C.c_float), ("d_ziorigin", C.c_float), ("d_zistepu", C.c_float), ("d_zistepv", C.c_float),
+                ("miplevel", C.c_int), ("cacheofs", C.c_int), ("cachewidth", C.c_int), ("hasspans", C.c_int),
+                ("d_sdivzstepu", C.c_float), ("d_tdivzstepu", C.c_float), ("d_sdivzstepv", C.c_float),
+                ("d_tdivzstepv", C.c_float), ("d_sdivzorigin", C.c_float), ("d_tdivzorigin", C.c_float),
+                ("sadjust", C.c_int), ("tadjust", C.c_int), ("bbextents", C.c_int), ("bbextentt", C.c_int),
+                ("entity", C.c_int), ("pad", C.c_int)]
+
+
+class rc_span_t(C.Structure):
+    _fields_ = [("view", C.c_int), ("surf", C.c_ushort), ("v", C.c_short), ("u", C.c_short), ("count", C.c_short),
+                ("firstblock", C.c_int)]
+
+
+def status_names(status: int):
+    return [n for b, n in RC_STAT.items() if status & b]
+
+
+class RefCuda:
+    """One renderer instance per process (the C library keeps one global renderer, as the
+    reference does)."""
+
+    def __init__(self, basedir: str, width: int, height: int, device: int = 0, libpath: str | None = None, **cvars):
+        path = libpath or LIBPATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.RC_LastError.restype = C.c_char_p
+        L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_RenderViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_DebugRead.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.Mod_ForName.restype = C.c_void_p
+        L.Mod_ForName.argtypes = [C.c_char_p, C.c_int]
+        cfg = rc_config_t()
+        L.RC_DefaultConfig(C.byref(cfg))
+        cfg.width, cfg.height, cfg.device = width, height, device
+        self._basedir = basedir.encode()
+        cfg.basedir = self._basedir
+        for k, v in cvars.items():
+            setattr(cfg, k, v)
+        self.width, self.height = width, height
+        rc = L.RC_Init(C.byref(cfg))
+        if rc != 0:
+            raise RuntimeError(f"RC_Init failed ({rc}): {L.RC_LastError().decode()}")
+
+    def err(self) -> str:
+        return self.lib.RC_LastError().decode()
+
+    def load_world(self, name: str):
+        rc = self.lib.RC_LoadWorld(name.encode())
+        if rc != 0:
+            raise RuntimeError(f"RC_LoadWorld({name}) failed ({rc}): {self.err()}")
+
+    def model(self, name: str) -> int:
+        p = self.lib.Mod_ForName(name.encode(), 0)
+        if not p:
+            raise RuntimeError(f"Mod_ForName({name}): {self.err()}")
+        return p
+
+    def render(self, rds, n: int | None = None, want_z: bool = True, fb=None, z=None):
+        """rds: ctypes array of refdef_t.  Returns (fb[n,h,w] uint8, z[n,h,w] int16 | None, status)."""
+        n = len(rds) if n is None else n
+        if fb is None:
+            fb = np.empty((n, self.height, self.width), dtype=np.uint8)
+        if want_z and z is None:
+            z = np.empty((n, self.height, self.width), dtype=np.int16)
+        st = C.c_int(0)
+        rc = self.lib.RC_RenderViews(rds, n, fb.ctypes.data, z.ctypes.data if want_z else None, C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"RC_RenderViews failed ({rc}): {self.err()}")
+        return fb, (z if want_z else None), st.value
+
+    def render_device(self, rds, n: int, fb_ptr: int, z_ptr: int = 0, stream: int = 0) -> int:
+        st = C.c_int(0)
+        rc = self.lib.RC_RenderViewsDevice(rds, n, fb_ptr, z_ptr or None, stream or None, C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"RC_RenderViewsDevice failed ({rc}): {self.err()}")
+        return st.value
+
+    def flush_caches(self):
+        self.lib.RC_FlushCaches()
+
+    def set_profiling(self, on: bool):
+        self.lib.RC_SetProfiling(int(on))
+
+    def stats(self) -> dict:
+        s = rc_stats_t()
+        self.lib.RC_GetStats(C.byref(s))
+        return {k: getattr(s, k) for k, _ in rc_stats_t._fields_}
+
+    def debug_read(self, kind: int, view: int = 0, cap: int = 1 << 20):
+        ty = [rc_edge_t, rc_surf_t, rc_span_t][kind]
+        buf = (ty * cap)()
+        n = self.lib.RC_DebugRead(kind, view, buf, cap)
+        if n < 0:
+            raise RuntimeError("RC_DebugRead failed")
+        return np.frombuffer(buf, dtype=np.dtype(ty))[:n].copy()
+
+    def shutdown(self):
+        self.lib.RC_Shutdown()

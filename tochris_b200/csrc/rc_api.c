@@ -1,0 +1,315 @@
+/*
+ * rc_api.c -- the C-ABI of libref_cuda.so (include/ref_cuda.h): the reference's
+ * client/render.h symbol set, the batched RC_* extension and the refexport_t table.
+ * Host-side only; all rendering is done by the CUDA pipeline behind rc_gpu_*.
+ * There is no CPU rendering path: without a CUDA device RC_Init fails.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "rc_host.h"
+
+#define RC_MAX_MODELS 512
+
+static struct {
+	int          inited;
+	rc_config_t  cfg;
+	char         basedir[512];
+	rc_vidinfo_t vid;
+	rc_cvars_t   cvars;
+	rc_gpu_t    *gpu;
+	uint8_t      palette[768];
+	uint8_t      colormap[256 * 64 + 4];
+	struct model_s *models[RC_MAX_MODELS];
+	int          nummodels;
+	struct model_s *world;
+	char         err[1024];
+	/* single-view path targets (RC_SetVidBuffers) */
+	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
+	rc_view_t   *viewscratch; int viewscratchcap;
+} rc;
+
+static int rc_fail (int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start (ap, fmt);
+	vsnprintf (rc.err, sizeof(rc.err), fmt, ap);
+	va_end (ap);
+	return code;
+}
+
+const char *RC_LastError (void) { return rc.err; }
+
+void RC_DefaultConfig (rc_config_t *c)
+{
+	memset (c, 0, sizeof(*c));
+	c->width = 320; c->height = 200; c->device = 0; c->basedir = ".";
+	/* reference defaults: r_main.c:108-134, d_init.c:26-28, R_Init :223-224 */
+	c->r_clearcolor = 2; c->r_fullbright = 0; c->r_ambient = 0; c->r_drawentities = 1;
+	c->r_drawviewmodel = 1; c->r_waterwarp = 1; c->r_fastsky = 0; c->r_skycolor = 4;
+	c->r_lerpmodels = 1; c->d_mipcap = 0; c->d_mipscale = 1;
+	c->r_maxsurfs = 1000; c->r_maxedges = 2000;
+}
+
+static void *rc_read_file (const char *name, size_t *len)
+{
+	char path[1024];
+	FILE *f;
+	long n;
+	void *buf;
+	snprintf (path, sizeof(path), "%s/id1/%s", rc.basedir, name);
+	f = fopen (path, "rb");
+	if (!f) return NULL;
+	fseek (f, 0, SEEK_END); n = ftell (f); fseek (f, 0, SEEK_SET);
+	buf = malloc (n > 0 ? n : 1);
+	if (buf && fread (buf, 1, n, f) != (size_t)n) { free (buf); buf = NULL; }
+	fclose (f);
+	if (len) *len = n;
+	return buf;
+}
+
+int RC_Init (const rc_config_t *cfg)
+{
+	size_t n;
+	void *p;
+	if (rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init called twice");
+	if (!cfg || cfg->width <= 0 || cfg->height <= 0 || cfg->width > RC_MAXWIDTH || cfg->height > RC_MAXHEIGHT)
+		return rc_fail (RC_ERR_ARG, "bad config (size limit %dx%d)", RC_MAXWIDTH, RC_MAXHEIGHT);
+	rc.cfg = *cfg;
+	snprintf (rc.basedir, sizeof(rc.basedir), "%s", cfg->basedir ? cfg->basedir : ".");
+	rc.cfg.basedir = rc.basedir;
+	/* common/host.c:827-832 */
+	p = rc_read_file ("gfx/palette.lmp", &n);
+	if (!p || n < 768) { free (p); return rc_fail (RC_ERR_FILE, "Couldn't load gfx/palette.lmp"); }
+	memcpy (rc.palette, p, 768); free (p);
+	p = rc_read_file ("gfx/colormap.lmp", &n);
+	if (!p || n < 256 * 64) { free (p); return rc_fail (RC_ERR_FILE, "Couldn't load gfx/colormap.lmp"); }
+	memcpy (rc.colormap, p, 256 * 64); free (p);
+	/* VID_Init equivalent: win32/vid_win.c:1351 */
+	rc.vid.width = cfg->width; rc.vid.height = cfg->height; rc.vid.rowbytes = cfg->width;
+	rc.vid.aspect = ((float)cfg->height / (float)cfg->width) * (320.0 / 240.0);
+	rc.cvars.r_clearcolor = cfg->r_clearcolor; rc.cvars.r_fullbright = cfg->r_fullbright;
+	rc.cvars.r_ambient = cfg->r_ambient; rc.cvars.r_drawentities = cfg->r_drawentities;
+	rc.cvars.r_drawviewmodel = cfg->r_drawviewmodel; rc.cvars.r_waterwarp = cfg->r_waterwarp;
+	rc.cvars.r_fastsky = cfg->r_fastsky; rc.cvars.r_skycolor = cfg->r_skycolor;
+	rc.cvars.r_lerpmodels = cfg->r_lerpmodels; rc.cvars.d_mipcap = cfg->d_mipcap;
+	rc.cvars.d_mipscale = cfg->d_mipscale;
+	rc.cvars.r_maxsurfs = cfg->r_maxsurfs < 1000 ? 1000 : cfg->r_maxsurfs;	/* MINSURFACES, r_main.c:267 */
+	rc.cvars.r_maxedges = cfg->r_maxedges < 2000 ? 2000 : cfg->r_maxedges;	/* MINEDGES, r_main.c:293 */
+	rc.gpu = rc_gpu_create (cfg->device, cfg->width, cfg->height, cfg->surfcache_bytes, cfg->max_views_in_flight,
+				rc.err, sizeof(rc.err));
+	if (!rc.gpu) return RC_ERR_CUDA;
+	rc.inited = 1;
+	return RC_OK;
+}
+
+void RC_Shutdown (void)
+{
+	Mod_ClearAll ();
+	if (rc.gpu) rc_gpu_destroy (rc.gpu);
+	free (rc.viewscratch);
+	memset (&rc, 0, sizeof(rc));
+}
+
+/* ---- models ---------------------------------------------------------------------------- */
+void Mod_Init (void) {}
+
+void Mod_ClearAll (void)
+{
+	int i;
+	for (i = 0; i < rc.nummodels; i++)
+	{
+		struct model_s *m = rc.models[i];
+		if (m->type == rc_mod_brush && m->submodel == 0 && m->world)
+			RC_FreeHostWorld (m->world);
+		free (m->alias);
+		free (m);
+	}
+	rc.nummodels = 0;
+	rc.world = NULL;
+	if (rc.gpu) rc_gpu_flush_caches (rc.gpu);	/* D_FlushCaches, r_model.c:178 */
+}
+
+static struct model_s *rc_find_model (const char *name)
+{
+	int i;
+	for (i = 0; i < rc.nummodels; i++)
+		if (!strcmp (rc.models[i]->name, name))
+			return rc.models[i];
+	return NULL;
+}
+
+static struct model_s *rc_new_model (const char *name)
+{
+	struct model_s *m;
+	if (rc.nummodels >= RC_MAX_MODELS) return NULL;
+	m = (struct model_s *)calloc (1, sizeof(*m));
+	snprintf (m->name, sizeof(m->name), "%s", name);
+	rc.models[rc.nummodels++] = m;
+	return m;
+}
+
+static struct model_s *rc_load_model (const char *name)
+{
+	struct model_s *m = rc_find_model (name);
+	size_t len;
+	void *buf;
+	int i;
+	if (m) return m;
+	buf = rc_read_file (name, &len);
+	if (!buf) { rc_fail (RC_ERR_FILE, "Mod_NumForName: %s not found", name); return NULL; }
+	if (len >= 4 && *(int *)buf == 29)
+	{
+		rc_hostworld_t *hw = RC_LoadBrushModel (buf, len, rc.colormap, rc.err, sizeof(rc.err));
+		free (buf);
+		if (!hw) return NULL;
+		/* r_model.c:1098-1126: model 0 under its file name, submodels as "*1", "*2", ... */
+		for (i = 0; i < hw->numsubmodels; i++)
+		{
+			char sub[16];
+			struct model_s *sm;
+			const rc_submodel_t *bm = &hw->submodels[i];
+			if (i == 0) sm = rc_new_model (name);
+			else { snprintf (sub, sizeof(sub), "*%i", i); sm = rc_find_model (sub); if (!sm) sm = rc_new_model (sub); }
+			if (!sm) { rc_fail (RC_ERR_NOMEM, "too many models"); return NULL; }
+			sm->type = rc_mod_brush; sm->world = hw; sm->submodel = i; sm->numframes = 2; sm->flags = 0;
+			memcpy (sm->mins, bm->mins, sizeof(sm->mins)); memcpy (sm->maxs, bm->maxs, sizeof(sm->maxs));
+			sm->radius = bm->radius;
+			if (i == 0) m = sm;
+		}
+		return m;
+	}
+	free (buf);
+	rc_fail (RC_ERR_FORMAT, "Mod_NumForName: %s has an unsupported format", name);
+	return NULL;
+}
+
+struct model_s *Mod_ForName (char *name, qboolean crash)
+{
+	struct model_s *m = rc_load_model (name);
+	if (!m && crash)
+	{
+		/* the reference calls Sys_Error here (r_model.c:296); a library must not exit() */
+		fprintf (stderr, "ref_cuda: %s\n", rc.err);
+	}
+	return m;
+}
+
+void Mod_TouchModel (char *name) { (void)name; }
+int  Mod_Flags (struct model_s *model) { return model ? model->flags : 0; }
+void R_TranslatePlayerSkin (int playernum, struct model_s *model, int skinnum, int top, int bottom)
+{ (void)playernum; (void)model; (void)skinnum; (void)top; (void)bottom; }
+
+void R_Init (void) {}
+
+void R_NewMap (struct model_s *worldmodel)
+{
+	if (!worldmodel || worldmodel->type != rc_mod_brush || !rc.gpu) return;
+	rc.world = worldmodel;
+	if (rc_gpu_upload_world (rc.gpu, worldmodel->world, (int)rc.cvars.r_maxedges, (int)rc.cvars.r_maxsurfs,
+				 rc.err, sizeof(rc.err)) != RC_OK)
+		rc.world = NULL;
+}
+
+int RC_LoadWorld (const char *name)
+{
+	struct model_s *m;
+	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	Mod_ClearAll ();
+	m = rc_load_model (name);
+	if (!m) return RC_ERR_FILE;
+	if (m->type != rc_mod_brush) return rc_fail (RC_ERR_FORMAT, "%s is not a brush model", name);
+	R_NewMap (m);
+	return rc.world ? RC_OK : RC_ERR_CUDA;
+}
+
+/* ---- rendering --------------------------------------------------------------------------- */
+static int rc_prepare_views (const refdef_t *views, int n)
+{
+	int i, rcode;
+	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
+	if (n > rc.viewscratchcap)
+	{
+		free (rc.viewscratch);
+		rc.viewscratch = (rc_view_t *)malloc (sizeof(rc_view_t) * n);
+		rc.viewscratchcap = rc.viewscratch ? n : 0;
+		if (!rc.viewscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	}
+	for (i = 0; i < n; i++)
+	{
+		if (!rc.world && !(views[i].flags & RDF_NOWORLDMODEL))
+			return rc_fail (RC_ERR_NOWORLD, "R_RenderView: NULL worldmodel");	/* r_main.c:1003 */
+		rcode = RC_SetupView (&views[i], &rc.vid, &rc.cvars, &rc.viewscratch[i]);
+		if (rcode != RC_OK) return rc_fail (rcode, "view %d: bad refdef rectangle", i);
+	}
+	return RC_OK;
+}
+
+int RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out, int *status)
+{
+	int r = rc_prepare_views (views, n);
+	if (r != RC_OK) return r;
+	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
+	return rc_gpu_render_host (rc.gpu, rc.viewscratch, n, fb_out, z_out, status, rc.err, sizeof(rc.err));
+}
+
+int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
+{
+	int r = rc_prepare_views (views, n);
+	if (r != RC_OK) return r;
+	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
+	return rc_gpu_render (rc.gpu, rc.viewscratch, n, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
+}
+
+void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }
+void RC_GetStats (rc_stats_t *out) { if (rc.gpu) rc_gpu_get_stats (rc.gpu, out); else memset (out, 0, sizeof(*out)); }
+void RC_SetProfiling (int on) { if (rc.gpu) rc_gpu_set_profiling (rc.gpu, on); }
+int  RC_DebugRead (int kind, int view, void *dst, int cap) { return rc.gpu ? rc_gpu_debug_read (rc.gpu, kind, view, dst, cap) : RC_ERR_ARG; }
+
+void RC_SetVidBuffers (uint8_t *buffer, int rowbytes, int16_t *zbuffer)
+{
+	rc.vidbuffer = buffer; rc.vidrowbytes = rowbytes; rc.zbuffer = zbuffer;
+}
+
+/* the render.h single-view path: one view through the batched pipeline, copied into the
+ * engine's vid.buffer / d_pzbuffer */
+void R_BeginFrame (void) {}
+void R_EndFrame (void) {}
+
+void R_RenderView (refdef_t *refdef)
+{
+	size_t px = (size_t)rc.vid.width * rc.vid.height;
+	uint8_t *fb;
+	int16_t *zb;
+	int y, status = 0;
+	if (!rc.vidbuffer) { rc_fail (RC_ERR_ARG, "RC_SetVidBuffers first"); return; }
+	fb = (uint8_t *)malloc (px);
+	zb = rc.zbuffer ? (int16_t *)malloc (px * 2) : NULL;
+	if (RC_RenderViews (refdef, 1, fb, zb, &status) == RC_OK)
+	{
+		for (y = 0; y < rc.vid.height; y++)
+			memcpy (rc.vidbuffer + (size_t)y * rc.vidrowbytes, fb + (size_t)y * rc.vid.width, rc.vid.width);
+		if (zb) memcpy (rc.zbuffer, zb, px * 2);
+	}
+	else
+		fprintf (stderr, "ref_cuda: R_RenderView: %s\n", rc.err);
+	free (fb); free (zb);
+}
+
+static struct model_s *rc_register_model (char *name) { return Mod_ForName (name, 0); }
+
+refexport_t GetRefAPI (int api_version)
+{
+	refexport_t re;
+	re.api_version = api_version;
+	re.Init = R_Init;
+	re.BeginRegistration = R_NewMap;
+	re.RegisterModel = rc_register_model;
+	re.BeginFrame = R_BeginFrame;
+	re.RenderFrame = R_RenderView;
+	re.EndFrame = R_EndFrame;
+	re.RenderFrames = RC_RenderViews;
+	return re;
+}

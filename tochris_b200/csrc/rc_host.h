@@ -1,0 +1,97 @@
+/*
+ * rc_host.h -- host-side (plain C) declarations of ref_cuda: model loading, per-view
+ * setup and the GPU pipeline entry points implemented in rc_gpu.cu.
+ */
+#ifndef RC_HOST_H
+#define RC_HOST_H
+
+#include "../../include/ref_cuda.h"
+#include "rc_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_WARP_WIDTH   320    /* ref_soft/d_iface.h:22-23 */
+#define RC_WARP_HEIGHT  200
+#define RC_RDF_NOWORLDMODEL RDF_NOWORLDMODEL
+#define RC_RDF_UNDERWATER   RDF_UNDERWATER
+
+typedef refdef_t     rc_refdef_t;
+typedef lightstyle_t rc_lightstyle_t;
+
+typedef struct { int width, height, rowbytes; float aspect; } rc_vidinfo_t;
+
+typedef struct {
+    float r_clearcolor, r_fullbright, r_ambient, r_drawentities, r_drawviewmodel, r_waterwarp,
+          r_fastsky, r_skycolor, r_lerpmodels, d_mipcap, d_mipscale, r_maxsurfs, r_maxedges;
+} rc_cvars_t;
+
+/* ---- models ------------------------------------------------------------------------- */
+typedef enum { rc_mod_brush, rc_mod_sprite, rc_mod_alias } rc_modtype_t;
+
+typedef struct {               /* mmodel_t, r_model.h:44-50 (+ mins/maxs spread by 1, r_model.c:642) */
+    float mins[3], maxs[3];
+    float radius;
+    int   headnode;
+    int   visleafs;
+    int   firstface, numfaces;
+} rc_submodel_t;
+
+typedef struct rc_hostworld_s {
+    rc_world_t w;              /* HOST pointers */
+    int        numsubmodels;
+    rc_submodel_t *submodels;
+    size_t     texelbytes, lightbytes;
+    int        sintablesize;
+    void      *owned[32];      /* malloc'd blocks to free */
+    int        numowned;
+} rc_hostworld_t;
+
+struct model_s {
+    char          name[64];
+    rc_modtype_t  type;
+    int           flags;
+    int           numframes;
+    float         mins[3], maxs[3], radius;
+    /* brush */
+    rc_hostworld_t *world;     /* shared by the world model and its '*n' submodels */
+    int           submodel;    /* index into world->submodels */
+    /* alias: filled by rc_host_alias.c */
+    void         *alias;
+};
+
+int  RC_SetupView (const rc_refdef_t *rd, const rc_vidinfo_t *vid, const rc_cvars_t *cv, rc_view_t *out);
+void RC_AngleVectors (const float *angles, float *forward, float *right, float *up);
+void RC_ScreenEdges (const rc_view_t *v, float pixelAspect, float fov_x, float screenedge[4][3]);
+void RC_TransformFrustum (const float screenedge[4][3], const float *vright, const float *vup,
+                          const float *vpn, const float *modelorg, float clipnormal[4][3], float *clipdist);
+
+#define RC_SIN_BUFFER_SIZE (RC_MAXWIDTH + RC_CYCLE + 1)   /* r_shared.h:44 with the raised maxima */
+void RC_BuildTurbTables (int *sintable, int *intsintable, int n);
+
+/* BSP29 -> flat arrays.  Mirrors Mod_LoadBrushModel (ref_soft/r_model.c:1062-1127).
+ * Returns NULL and fills err on malformed data (the reference calls Sys_Error). */
+rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *colormap, char *err, size_t errlen);
+void RC_FreeHostWorld (rc_hostworld_t *hw);
+
+/* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
+typedef struct rc_gpu_s rc_gpu_t;
+
+rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen);
+void rc_gpu_destroy (rc_gpu_t *g);
+int  rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen);
+/* renders n prepared views; fb_dev/z_dev are device pointers (z may be NULL) */
+int  rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+                    int *status, char *err, size_t errlen);
+int  rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+                         int *status, char *err, size_t errlen);
+void rc_gpu_flush_caches (rc_gpu_t *g);
+void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out);
+void rc_gpu_set_profiling (rc_gpu_t *g, int on);
+int  rc_gpu_debug_read (rc_gpu_t *g, int kind, int view, void *dst, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

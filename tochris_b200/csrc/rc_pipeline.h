@@ -1,0 +1,1206 @@
+/*
+ * rc_pipeline.h -- the per-thread bodies of the ref_cuda kernels.
+ *
+ * Every function here is the work of ONE CUDA thread (one view, one face, one scanline,
+ * one cache texel, one 8-pixel block ...).  rc_gpu.cu wraps them in __global__ kernels;
+ * tests/hostsim compiles the same bodies with g++ to step through the pipeline on a CPU
+ * while developing (test infrastructure only -- the product never runs them on the host).
+ *
+ * Arithmetic rules: float expressions are written with the
+ * reference's operand types and order; the file is compiled with --fmad=false /
+ * -ffp-contract=off; float->int goes through rc_f2i/rc_d2i, which reproduce x86
+ * cvttss2si/cvttsd2si (0x80000000 when out of range) instead of CUDA's saturation.
+ */
+#ifndef RC_PIPELINE_H
+#define RC_PIPELINE_H
+
+#include "rc_types.h"
+#include <math.h>
+
+#ifdef __CUDACC__
+#define RC_HD __host__ __device__ __forceinline__
+#define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
+#define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
+#define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
+#define RC_ATOMIC_CAS_ULL(p, c, v) atomicCAS ((p), (c), (v))
+#else
+#define RC_HD static inline
+static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline int rc_host_or_i (int *p, int v) { int o = *p; *p = o | v; return o; }
+static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
+#define RC_ATOMIC_ADD_I(p, v)   rc_host_add_i ((p), (v))
+#define RC_ATOMIC_ADD_ULL(p, v) rc_host_add_ull ((p), (v))
+#define RC_ATOMIC_OR_I(p, v)    rc_host_or_i ((p), (v))
+#define RC_ATOMIC_CAS_ULL(p, c, v) rc_host_cas_ull ((p), (c), (v))
+#endif
+
+#define RC_FACEPOS_NONE    0xFFFFu   /* face not marked by any visited leaf */
+#define RC_FACEPOS_MARKED  0xFFFEu   /* marked (surf->visframe == r_framecount), not rendered */
+#define RC_MAX_FACE_EDGES  30        /* per face; slot 31 is the synthetic left-clip edge */
+#define RC_WALK_STACK      512
+#define RC_AET_MAX         320       /* active edges per scanline held by the scan thread */
+#define RC_STACK_MAX       96        /* active surface stack depth held by the scan thread */
+#define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
+
+/* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
+typedef struct {
+    int nviews, width, height;
+    const rc_view_t *views;
+    /* BSP walk */
+    rc_facerec_t *facelist; int facecap; int *nfaces;
+    uint16_t *facepos;            /* [nviews][numfaces] */
+    /* face stage */
+    rc_edge_t *edges; int edgecap; int *nedges;
+    rc_surf_t *surfs; int surfcap; /* [nviews][surfcap]; 0 dummy, 1 background, 2+p face-list slot p */
+    int maxedges, maxsurfs;       /* the reference's r_maxedges / r_maxsurfs (overflow reporting) */
+    /* scan */
+    rc_span_t *spans; int spancap;
+    int *blockspan; int blockcap;
+    unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 blocks used  [1]: cache pool cursor  [2]: jobs */
+    /* surface cache */
+    unsigned long long *cachekeys; int *cachevals; int cachemask;
+    uint8_t *cachepool; long long cachecap;
+    rc_cachejob_t *jobs; int jobcap;
+    /* outputs */
+    uint8_t *fb; int16_t *zb;
+    int *status;
+} rc_frame_t;
+
+/* ------------------------------------------------------------------ scalar helpers ---- */
+RC_HD int rc_f2i (float x)
+{
+	/* cvttss2si: truncation, "integer indefinite" when out of range or NaN */
+	if (x >= 2147483648.0f || x < -2147483648.0f || x != x)
+		return (int)0x80000000;
+	return (int)x;
+}
+RC_HD int rc_d2i (double x)
+{
+	/* cvttsd2si */
+	if (!(x > -2147483649.0 && x < 2147483648.0))
+		return (int)0x80000000;
+	return (int)x;
+}
+RC_HD int rc_sar (int x, int s) { return x >> s; }   /* arithmetic on every target we build for */
+RC_HD int rc_addw (int a, int b) { return (int)((unsigned)a + (unsigned)b); }   /* wrapping add */
+RC_HD int rc_mulw (int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+
+RC_HD float rc_dot3 (const float *x, const float *y) { return x[0]*y[0] + x[1]*y[1] + x[2]*y[2]; }
+
+RC_HD void rc_transform_vector (const rc_view_t *v, const float *in, float *out)
+{	/* TransformVector, r_misc.c:308-313 */
+	out[0] = rc_dot3 (in, v->vright);
+	out[1] = rc_dot3 (in, v->vup);
+	out[2] = rc_dot3 (in, v->vpn);
+}
+
+/* ------------------------------------------------------------------ stage 1: walk ----- */
+RC_HD int rc_visbit (const uint32_t *row, int idx) { return (row[idx >> 5] >> (idx & 31)) & 1; }
+
+/* bbox vs frustum, r_bsp.c:453-491.  Returns 0 when rejected, else 1 with *pclip updated. */
+RC_HD int rc_cull_box (const rc_view_t *v, const int16_t *minmaxs, int *pclip)
+{
+	int clipflags = *pclip;
+	if (clipflags)
+	{
+		for (int i = 0; i < 4; i++)
+		{
+			if (!(clipflags & (1 << i)))
+				continue;
+			const int *pindex = v->frustum_idx[i];
+			float rejectpt[3], acceptpt[3];
+			rejectpt[0] = (float)minmaxs[pindex[0]];
+			rejectpt[1] = (float)minmaxs[pindex[1]];
+			rejectpt[2] = (float)minmaxs[pindex[2]];
+			double d = rc_dot3 (rejectpt, v->clipnormal[i]) - v->clipdist[i];
+			if (d <= 0)
+				return 0;
+			acceptpt[0] = (float)minmaxs[pindex[3+0]];
+			acceptpt[1] = (float)minmaxs[pindex[3+1]];
+			acceptpt[2] = (float)minmaxs[pindex[3+2]];
+			d = rc_dot3 (acceptpt, v->clipnormal[i]) - v->clipdist[i];
+			if (d >= 0)
+				clipflags &= ~(1 << i);
+		}
+	}
+	*pclip = clipflags;
+	return 1;
+}
+
+RC_HD float rc_plane_diff (const float *p, const rc_plane_t *pl)
+{	/* PlaneDiff, common/mathlib.h:46 */
+	return (pl->type < 3 ? p[pl->type] : rc_dot3 (p, pl->normal)) - pl->dist;
+}
+
+/* One thread per view: Mod_PointInLeaf (r_model.c:83) + R_MarkLeaves lookup (precomputed
+ * nodevis row) + R_RecursiveWorldNode (r_bsp.c:436-557) as an explicit-stack DFS.
+ * Emits the ordered list of faces R_RenderFace is called on, with their clipflags. */
+RC_HD void rc_walk_view (const rc_world_t *w, const rc_frame_t *f, int vi)
+{
+	const rc_view_t *v = &f->views[vi];
+	rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	uint16_t *facepos = f->facepos + (size_t)vi * w->numfaces;
+	int nlist = 0, key = 0;
+	int stack_node[RC_WALK_STACK];
+	signed char stack_info[RC_WALK_STACK];	/* bits 0-3 clipflags, bit 4: faces pending (phase 1) */
+	int sp = 0;
+
+	f->nfaces[vi] = 0;
+	{
+		/* surfaces[1]: the background (R_BeginEdgeFrame, r_edge.c:86-106) */
+		rc_surf_t *bg = f->surfs + (size_t)vi * f->surfcap + 1;
+		bg->key = 0x7FFFFFFF; bg->flags = RC_SURF_DRAWBACKGROUND; bg->face = -1; bg->insubmodel = 0;
+		bg->hasspans = 0; bg->entity = -1; bg->nearzi = 0;
+		bg->d_ziorigin = 0; bg->d_zistepu = 0; bg->d_zistepv = 0;
+		f->nedges[vi] = 0;
+	}
+	if (v->rdflags & 1 /* RDF_NOWORLDMODEL */)
+		return;
+
+	/* Mod_PointInLeaf */
+	int n = 0;
+	while (n >= 0)
+	{
+		const rc_node_t *nd = &w->nodes[n];
+		const rc_plane_t *pl = &w->planes[nd->plane];
+		float d = rc_dot3 (v->origin, pl->normal) - pl->dist;
+		n = (d > 0) ? nd->children[0] : nd->children[1];
+	}
+	const uint32_t *vis = w->nodevis + (size_t)(-1 - n) * w->visrowwords;
+
+	stack_node[sp] = 0; stack_info[sp] = 15; sp++;
+	while (sp)
+	{
+		sp--;
+		int node = stack_node[sp];
+		int info = stack_info[sp];
+		int clipflags = info & 15;
+		if (!(info & 16))
+		{
+			if (node < 0)
+			{
+				int li = -1 - node;
+				const rc_leaf_t *lf = &w->leafs[li];
+				if (lf->contents == RC_CONTENTS_SOLID)
+					continue;
+				if (!rc_visbit (vis, w->numnodes + li))
+					continue;
+				if (!rc_cull_box (v, lf->minmaxs, &clipflags))
+					continue;
+				for (int c = 0; c < lf->nummarks; c++)
+				{
+					int fi = w->marksurfaces[lf->firstmark + c];
+					if (facepos[fi] == RC_FACEPOS_NONE)
+						facepos[fi] = RC_FACEPOS_MARKED;
+				}
+				key++;		/* pleaf->key = r_currentkey++ */
+				continue;
+			}
+			const rc_node_t *nd = &w->nodes[node];
+			if (!rc_visbit (vis, node))
+				continue;
+			if (!rc_cull_box (v, nd->minmaxs, &clipflags))
+				continue;
+			float dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
+			int side = (dot < 0);
+			if (sp + 2 > RC_WALK_STACK)
+			{
+				RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
+				break;
+			}
+			stack_node[sp] = node; stack_info[sp] = (signed char)(clipflags | 16); sp++;
+			stack_node[sp] = nd->children[side]; stack_info[sp] = (signed char)clipflags; sp++;
+		}
+		else
+		{
+			const rc_node_t *nd = &w->nodes[node];
+			double dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
+			int side = (dot < 0);
+			int c = nd->numsurfaces;
+			if (c)
+			{
+				int want = -1;
+				if (dot < -RC_BACKFACE_EPSILON) want = RC_SURF_PLANEBACK;
+				else if (dot > RC_BACKFACE_EPSILON) want = 0;
+				if (want >= 0)
+				{
+					for (int s = 0; s < c; s++)
+					{
+						int fi = nd->firstsurface + s;
+						if ((w->faces[fi].flags & RC_SURF_PLANEBACK) == want && facepos[fi] != RC_FACEPOS_NONE)
+						{
+							/* R_RenderFace (surf, clipflags) */
+							if (nlist >= f->facecap || nlist >= (int)RC_FACEPOS_MARKED - 1)
+							{
+								RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
+								continue;
+							}
+							list[nlist].face = fi;
+							list[nlist].clipflags = clipflags;
+							list[nlist].key = key++;
+							list[nlist].pad = 0;
+							facepos[fi] = (uint16_t)nlist;
+							nlist++;
+						}
+					}
+				}
+				key++;		/* all surfaces on the same node share the same sequence number */
+			}
+			stack_node[sp] = nd->children[!side]; stack_info[sp] = (signed char)clipflags; sp++;
+		}
+	}
+	f->nfaces[vi] = nlist;
+}
+
+/* ------------------------------------------------------------- stage 2: face -> edges -- */
+typedef struct {
+	float u, v, lzi;
+	int   ceilv;
+} rc_evert_t;
+
+/* transform and project one end point, r_rast.c:236-262 */
+RC_HD void rc_project (const rc_view_t *vw, const float *world, rc_evert_t *o)
+{
+	float local[3], t[3];
+	local[0] = world[0] - vw->origin[0];
+	local[1] = world[1] - vw->origin[1];
+	local[2] = world[2] - vw->origin[2];
+	rc_transform_vector (vw, local, t);
+	if (t[2] < RC_NEAR_CLIP)
+		t[2] = RC_NEAR_CLIP;
+	float lzi = 1.0 / t[2];
+	float scale = vw->xscale * lzi;
+	float u = (vw->xcenter + scale*t[0]);
+	if (u < vw->fvrectx_adj) u = vw->fvrectx_adj;
+	if (u > vw->fvrectright_adj) u = vw->fvrectright_adj;
+	scale = vw->yscale * lzi;
+	float vv = (vw->ycenter - scale*t[1]);
+	if (vv < vw->fvrecty_adj) vv = vw->fvrecty_adj;
+	if (vv > vw->fvrectbottom_adj) vv = vw->fvrectbottom_adj;
+	o->u = u; o->v = vv; o->lzi = lzi;
+	o->ceilv = rc_d2i (ceil ((double)vv));
+}
+
+#define RC_CLS_PARTIAL   0   /* cacheoffset = 0x7FFFFFFF: clipped, never cached            */
+#define RC_CLS_FULLCLIP  1   /* FULLY_CLIPPED_CACHED: second user skips the edge           */
+#define RC_CLS_CACHED    2   /* emitted unclipped: second user shares the edge_t           */
+
+typedef struct {
+	int   cls;
+	int   emitted;        /* R_EmitEdge reached (r_emitted = 1), even for horizontal: no */
+	int   made_edge;      /* an edge_t was produced */
+	int   trailing;       /* side == 0 */
+	int   u, u_step, v, v2;
+	float nearzi;         /* edge->nearzi (max of the two 1/z), valid when R_EmitEdge ran */
+	int   reached_emit;
+	int   leftclipped, rightclipped;
+	int   have_leftenter, have_leftexit, have_rightenter, have_rightexit;
+	float leftenter[3], leftexit[3], rightenter[3], rightexit[3];
+} rc_clipres_t;
+
+/* R_ClipEdge (r_rast.c:391-485, tail recursion unrolled) followed by R_EmitEdge
+ * (r_rast.c:213-383) for one polygon edge p0->p1 against the planes in `mask`
+ * (bit i = view_clipplanes[i], tested in ascending i).  Pure: returns what the reference
+ * would have written to its globals. */
+RC_HD void rc_clip_emit (const rc_view_t *vw, const float *p0in, const float *p1in, int mask,
+			 int nearzionly, rc_clipres_t *r)
+{
+	float p0[3], p1[3];
+	int clipped = 0;
+	p0[0] = p0in[0]; p0[1] = p0in[1]; p0[2] = p0in[2];
+	p1[0] = p1in[0]; p1[1] = p1in[1]; p1[2] = p1in[2];
+	r->cls = RC_CLS_CACHED;
+	r->emitted = 0; r->made_edge = 0; r->reached_emit = 0; r->nearzi = 0;
+	r->leftclipped = r->rightclipped = 0;
+	r->have_leftenter = r->have_leftexit = r->have_rightenter = r->have_rightexit = 0;
+
+	for (int i = 0; i < 4; i++)
+	{
+		if (!(mask & (1 << i)))
+			continue;
+		const float *nrm = vw->clipnormal[i];
+		float d0 = rc_dot3 (p0, nrm) - vw->clipdist[i];
+		float d1 = rc_dot3 (p1, nrm) - vw->clipdist[i];
+		if (d0 >= 0)
+		{
+			if (d1 >= 0)
+				continue;
+			/* only point 1 is clipped */
+			clipped = 1;
+			float fr = d0 / (d0 - d1);
+			float c[3];
+			c[0] = p0[0] + fr * (p1[0] - p0[0]);
+			c[1] = p0[1] + fr * (p1[1] - p0[1]);
+			c[2] = p0[2] + fr * (p1[2] - p0[2]);
+			if (i == 0) { r->leftclipped = 1; r->have_leftexit = 1; r->leftexit[0] = c[0]; r->leftexit[1] = c[1]; r->leftexit[2] = c[2]; }
+			else if (i == 1) { r->rightclipped = 1; r->have_rightexit = 1; r->rightexit[0] = c[0]; r->rightexit[1] = c[1]; r->rightexit[2] = c[2]; }
+			p1[0] = c[0]; p1[1] = c[1]; p1[2] = c[2];
+		}
+		else
+		{
+			if (d1 < 0)
+			{
+				/* both points are clipped; cached as fully clipped unless the left plane cut it */
+				r->cls = (!r->leftclipped) ? RC_CLS_FULLCLIP : RC_CLS_PARTIAL;
+				return;
+			}
+			clipped = 1;
+			float fr = d0 / (d0 - d1);
+			float c[3];
+			c[0] = p0[0] + fr * (p1[0] - p0[0]);
+			c[1] = p0[1] + fr * (p1[1] - p0[1]);
+			c[2] = p0[2] + fr * (p1[2] - p0[2]);
+			if (i == 0) { r->leftclipped = 1; r->have_leftenter = 1; r->leftenter[0] = c[0]; r->leftenter[1] = c[1]; r->leftenter[2] = c[2]; }
+			else if (i == 1) { r->rightclipped = 1; r->have_rightenter = 1; r->rightenter[0] = c[0]; r->rightenter[1] = c[1]; r->rightenter[2] = c[2]; }
+			p0[0] = c[0]; p0[1] = c[1]; p0[2] = c[2];
+		}
+	}
+	if (clipped)
+		r->cls = RC_CLS_PARTIAL;
+
+	/* R_EmitEdge */
+	rc_evert_t e0, e1;
+	rc_project (vw, p0, &e0);
+	rc_project (vw, p1, &e1);
+	float lzi0 = e0.lzi;
+	if (e1.lzi > lzi0)
+		lzi0 = e1.lzi;
+	r->nearzi = lzi0;
+	r->reached_emit = 1;
+	if (nearzionly)
+		return;
+	r->emitted = 1;
+	if (e0.ceilv == e1.ceilv)
+	{
+		/* horizontal edge: unclipped ones are cached as fully clipped */
+		if (r->cls != RC_CLS_PARTIAL)
+			r->cls = RC_CLS_FULLCLIP;
+		return;
+	}
+	int side = e0.ceilv > e1.ceilv;
+	float u, u_step;
+	r->made_edge = 1;
+	if (side == 0)
+	{
+		r->trailing = 1;
+		r->v = e0.ceilv;
+		r->v2 = e1.ceilv - 1;
+		u_step = ((e1.u - e0.u) / (e1.v - e0.v));
+		u = e0.u + ((float)r->v - e0.v) * u_step;
+	}
+	else
+	{
+		r->trailing = 0;
+		r->v2 = e0.ceilv - 1;
+		r->v = e1.ceilv;
+		u_step = ((e0.u - e1.u) / (e0.v - e1.v));
+		u = e1.u + ((float)r->v - e1.v) * u_step;
+	}
+	r->u_step = rc_f2i (u_step*0x100000);
+	r->u = rc_f2i (u*0x100000 + 0xFFFFF);
+	if (r->u < vw->vrect_x_adj_shift20)
+		r->u = vw->vrect_x_adj_shift20;
+	if (r->u > vw->vrectright_adj_shift20)
+		r->u = vw->vrectright_adj_shift20;
+}
+
+/* One thread per (view, face-list slot): R_RenderFace, r_rast.c:518-716. */
+RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int p)
+{
+	const rc_view_t *vw = &f->views[vi];
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	const uint16_t *facepos = f->facepos + (size_t)vi * w->numfaces;
+	const rc_facerec_t rec = list[p];
+	const rc_face_t *fa = &w->faces[rec.face];
+	rc_surf_t *surf = f->surfs + (size_t)vi * f->surfcap + (p + 2);
+	const int clipflags = rec.clipflags;
+	const int surfidx = p + 2;
+
+	rc_edge_t eb[RC_MAX_FACE_EDGES + 1];
+	int neb = 0;
+	int emitted = 0, makeleft = 0, makeright = 0;
+	float nearzi = 0;
+	float leftenter[3] = {0,0,0}, leftexit[3] = {0,0,0}, rightenter[3] = {0,0,0}, rightexit[3] = {0,0,0};
+	int have_le = 0, have_lx = 0, have_re = 0, have_rx = 0;
+	rc_clipres_t r;
+
+	surf->flags = -1;		/* not posted unless an edge comes out */
+	surf->hasspans = 0;
+	if (fa->numedges > RC_MAX_FACE_EDGES)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
+		return;
+	}
+
+	for (int i = 0; i < fa->numedges; i++)
+	{
+		int lindex = w->surfedges[fa->firstedge + i];
+		int m = lindex > 0 ? lindex : -lindex;
+		const float *va = &w->vertexes[3 * w->edges[2 * m + (lindex > 0 ? 0 : 1)]];
+		const float *vb = &w->vertexes[3 * w->edges[2 * m + (lindex > 0 ? 1 : 0)]];
+		const rc_separtner_t sp = w->separtner[fa->firstedge + i];
+		int q = RC_FACEPOS_NONE;
+		if (sp.partner_face >= 0)
+			q = facepos[sp.partner_face];
+
+		if (q < (int)RC_FACEPOS_MARKED && q < p)
+		{
+			/* the partner face ran first: redo its R_ClipEdge to learn what it left in
+			 * medge_t.cachededgeoffset (r_rast.c:583-603) */
+			const rc_face_t *pf = &w->faces[sp.partner_face];
+			int pl = w->surfedges[pf->firstedge + sp.partner_slot];
+			int pm = pl > 0 ? pl : -pl;
+			const float *pa = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 0 : 1)]];
+			const float *pb = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 1 : 0)]];
+			rc_clip_emit (vw, pa, pb, list[q].clipflags, 0, &r);
+			if (r.cls == RC_CLS_FULLCLIP)
+				continue;
+			if (r.cls == RC_CLS_CACHED)
+			{
+				/* R_EmitCachedEdge: the partner's edge_t carries this surface */
+				if (r.nearzi > nearzi)
+					nearzi = r.nearzi;
+				emitted = 1;
+				continue;
+			}
+		}
+
+		rc_clip_emit (vw, va, vb, clipflags, 0, &r);
+		if (r.have_leftenter) { have_le = 1; leftenter[0] = r.leftenter[0]; leftenter[1] = r.leftenter[1]; leftenter[2] = r.leftenter[2]; }
+		if (r.have_leftexit) { have_lx = 1; leftexit[0] = r.leftexit[0]; leftexit[1] = r.leftexit[1]; leftexit[2] = r.leftexit[2]; }
+		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
+		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
+		if (r.leftclipped) makeleft = 1;
+		if (r.rightclipped) makeright = 1;
+		if (r.reached_emit && r.nearzi > nearzi)
+			nearzi = r.nearzi;
+		if (r.emitted)
+			emitted = 1;
+		if (r.made_edge)
+		{
+			rc_edge_t *e = &eb[neb++];
+			e->u = r.u; e->u_step = r.u_step;
+			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
+			e->surfs[0] = r.trailing ? surfidx : 0;
+			e->surfs[1] = r.trailing ? 0 : surfidx;
+			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)p << 5) | (uint32_t)i;
+			e->pad[0] = e->pad[1] = e->pad[2] = 0;
+			if (r.cls == RC_CLS_CACHED && q < (int)RC_FACEPOS_MARKED && q > p)
+			{
+				/* the partner will find this edge cached and add itself (R_EmitCachedEdge) */
+				if (r.trailing) e->surfs[1] = (uint16_t)(q + 2);
+				else e->surfs[0] = (uint16_t)(q + 2);
+			}
+		}
+	}
+
+	if (makeleft)
+	{
+		/* r_rast.c:661-666: R_ClipEdge (&r_leftexit, &r_leftenter, pclip->next) */
+		int first = 0;
+		while (!(clipflags & (1 << first))) first++;
+		int mask = clipflags & ~((2 << first) - 1);
+		if (!have_le || !have_lx)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_STALE_CLIPVERT);
+		rc_clip_emit (vw, leftexit, leftenter, mask, 0, &r);
+		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
+		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
+		if (r.reached_emit && r.nearzi > nearzi)
+			nearzi = r.nearzi;
+		if (r.emitted)
+			emitted = 1;
+		if (r.made_edge)
+		{
+			rc_edge_t *e = &eb[neb++];
+			e->u = r.u; e->u_step = r.u_step;
+			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
+			e->surfs[0] = r.trailing ? surfidx : 0;
+			e->surfs[1] = r.trailing ? 0 : surfidx;
+			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)p << 5) | 31u;
+			e->pad[0] = e->pad[1] = e->pad[2] = 0;
+		}
+	}
+	/* r_rightenter / r_rightexit are globals in the reference: a face whose own edges wrote
+	 * only one of them (the other crossing edge was skipped as FULLY_CLIPPED_CACHED) reads the
+	 * value an EARLIER face left behind.  Publish what this face wrote; rc_face_fixup resolves
+	 * such reads once every face of the view has run. */
+	surf->d_sdivzstepu = rightenter[0]; surf->d_tdivzstepu = rightenter[1]; surf->d_sdivzstepv = rightenter[2];
+	surf->d_tdivzstepv = rightexit[0]; surf->d_sdivzorigin = rightexit[1]; surf->d_tdivzorigin = rightexit[2];
+	surf->miplevel = have_re | (have_rx << 1);
+	if (makeright)
+	{
+		/* r_rast.c:669-675: only the effect on r_nearzi is wanted; planes after the right one */
+		if (have_re && have_rx)
+		{
+			rc_clip_emit (vw, rightexit, rightenter, clipflags & 0xC, 1, &r);
+			if (r.reached_emit && r.nearzi > nearzi)
+				nearzi = r.nearzi;
+		}
+		else
+			surf->miplevel |= 4;
+	}
+
+	if (neb)
+	{
+		int base = RC_ATOMIC_ADD_I (&f->nedges[vi], neb);
+		if (base + neb > f->edgecap)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
+		else
+		{
+			rc_edge_t *dst = f->edges + (size_t)vi * f->edgecap + base;
+			for (int i = 0; i < neb; i++)
+				dst[i] = eb[i];
+		}
+	}
+	if (!emitted)
+		return;
+
+	/* r_rast.c:693-714 */
+	const rc_plane_t *pplane = &w->planes[fa->plane];
+	float p_normal[3];
+	rc_transform_vector (vw, pplane->normal, p_normal);
+	float distinv = 1.0 / (pplane->dist - rc_dot3 (vw->origin, pplane->normal));
+	surf->key = rec.key;
+	surf->flags = fa->flags;
+	surf->face = rec.face;
+	surf->insubmodel = 0;
+	surf->entity = -1;
+	surf->nearzi = nearzi;
+	surf->d_zistepu = p_normal[0] * vw->xscaleinv * distinv;
+	surf->d_zistepv = -p_normal[1] * vw->yscaleinv * distinv;
+	surf->d_ziorigin = p_normal[2] * distinv - vw->xcenter * surf->d_zistepu - vw->ycenter * surf->d_zistepv;
+}
+
+/* One thread per (view, face-list slot), after rc_render_face: faces that must read an
+ * r_rightenter / r_rightexit written by an earlier face (see above) walk the list backwards
+ * for the most recent writer, then run the r_nearzionly clip of r_rast.c:669-675. */
+RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int p)
+{
+	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
+	rc_surf_t *surf = &surfs[p + 2];
+	if (!(surf->miplevel & 4))
+		return;
+	const rc_view_t *vw = &f->views[vi];
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	float re[3], rx[3];
+	int have_re = surf->miplevel & 1, have_rx = (surf->miplevel >> 1) & 1;
+	re[0] = surf->d_sdivzstepu; re[1] = surf->d_tdivzstepu; re[2] = surf->d_sdivzstepv;
+	rx[0] = surf->d_tdivzstepv; rx[1] = surf->d_sdivzorigin; rx[2] = surf->d_tdivzorigin;
+	for (int q = p - 1; q >= 0 && !(have_re && have_rx); q--)
+	{
+		const rc_surf_t *o = &surfs[q + 2];
+		if (!have_re && (o->miplevel & 1))
+		{ have_re = 1; re[0] = o->d_sdivzstepu; re[1] = o->d_tdivzstepu; re[2] = o->d_sdivzstepv; }
+		if (!have_rx && (o->miplevel & 2))
+		{ have_rx = 1; rx[0] = o->d_tdivzstepv; rx[1] = o->d_sdivzorigin; rx[2] = o->d_tdivzorigin; }
+	}
+	if (!have_re || !have_rx)
+	{
+		/* nothing wrote it this frame: the reference would use last frame's leftovers */
+		RC_ATOMIC_OR_I (f->status, RC_STAT_STALE_CLIPVERT);
+		return;
+	}
+	if (surf->flags == -1)
+		return;
+	rc_clipres_t r;
+	rc_clip_emit (vw, rx, re, list[p].clipflags & 0xC, 1, &r);
+	if (r.reached_emit && r.nearzi > surf->nearzi)
+		surf->nearzi = r.nearzi;
+}
+
+/* ------------------------------------------------------------------ stage 3: scan ------ */
+typedef struct { unsigned long long hi, lo; uint32_t surfs; int iu; } rc_aet_t;
+RC_HD int aet_u_of (const rc_aet_t a) { return (int)((uint32_t)(a.hi >> 32) ^ 0x80000000u); }
+
+typedef struct {
+	int surf, key, state, last_u, insub;
+} rc_stk_t;
+
+/* Emits one span for surface `s` (r_edge.c:268-276,349-357,398-406,505-513) */
+#define RC_EMIT_SPAN(sidx, ustart, uend)                                                      \
+	do {                                                                                  \
+		if (nsp < spanroom) {                                                         \
+			rc_span_t *_s = &f->spans[spanbase + nsp];                            \
+			int _c = (uend) - (ustart);                                           \
+			_s->view = vi; _s->surf = (uint16_t)(sidx); _s->v = (int16_t)line;    \
+			_s->u = (int16_t)(ustart); _s->count = (int16_t)_c;                   \
+			_s->firstblock = blockbase + nblk;                                    \
+			for (int _b = 0; _b < ((_c + 7) >> 3) && nblk < blockroom; _b++)      \
+				f->blockspan[blockbase + nblk++] = spanbase + nsp;            \
+			nsp++;                                                                \
+			surfs[sidx].hasspans = 1;                                             \
+		}                                                                             \
+	} while (0)
+
+/* One thread per (view, scanline).  Rebuilds the active edge table the reference has on
+ * that line -- membership from v..v2, u = u0 + (line-v)*u_step (R_StepActiveU adds
+ * u_step once per line, r_edge.c:195), order from the closed-form comparator derived in
+ * DESIGN.md from R_InsertNewEdges / R_StepActiveU / R_EmitEdge's newedges[] insertion
+ *  -- then runs R_GenerateSpans (r_edge.c:536-563) over it. */
+RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int line)
+{
+	const rc_view_t *vw = &f->views[vi];
+	if (line < vw->vrect_y || line >= vw->vrectbottom)
+		return;
+	const rc_edge_t *edges = f->edges + (size_t)vi * f->edgecap;
+	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
+	int E = f->nedges[vi];
+	if (E > f->edgecap) E = f->edgecap;
+	rc_aet_t aet[RC_AET_MAX];
+	int n = 0;
+
+	for (int e = 0; e < E; e++)
+	{
+		const rc_edge_t ed = edges[e];
+		if (ed.v > line || ed.v2 < line)
+			continue;
+		if (n >= RC_AET_MAX)
+		{
+			RC_ATOMIC_OR_I (f->status, RC_STAT_AET_OVERFLOW);
+			break;
+		}
+		int isold = line > ed.v;
+		int u = rc_addw (ed.u, rc_mulw (line - ed.v, ed.u_step));
+		uint32_t c = 0;
+		if (isold)
+		{
+			c = ~((uint32_t)ed.u_step ^ 0x80000000u);	/* larger step first */
+			if (c == 0) c = 1;
+		}
+		uint32_t em = ed.rank & 0x7FFFFFFFu;
+		uint32_t trailing = ed.rank >> 31;
+		uint32_t fl = trailing ? em : (~em & 0x7FFFFFFFu);	/* leaders newest first, trailers oldest first */
+		rc_aet_t a;
+		a.hi = ((unsigned long long)((uint32_t)u ^ 0x80000000u) << 32) | c;
+		a.lo = ((unsigned long long)(uint16_t)(~ed.v) << 32) | ((unsigned long long)trailing << 31) | fl;
+		a.surfs = (uint32_t)ed.surfs[0] | ((uint32_t)ed.surfs[1] << 16);
+		a.iu = u >> 20;
+		/* insertion sort */
+		int j = n++;
+		while (j > 0 && (aet[j-1].hi > a.hi || (aet[j-1].hi == a.hi && aet[j-1].lo > a.lo)))
+		{
+			aet[j] = aet[j-1];
+			j--;
+		}
+		aet[j] = a;
+	}
+
+	/* output room: at most n+1 spans, (w+7)/8 + n+1 blocks; one allocation per line */
+	int spanroom = n + 1;
+	int blockroom = ((vw->vrect_w + 7) >> 3) + n + 1;
+	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)spanroom | ((unsigned long long)blockroom << 32));
+	int spanbase = (int)(old & 0xFFFFFFFFu), blockbase = (int)(old >> 32);
+	if (spanbase + spanroom > f->spancap || blockbase + blockroom > f->blockcap)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_SPAN_POOL);
+		return;
+	}
+	int nsp = 0, nblk = 0;
+
+	/* R_GenerateSpans */
+	rc_stk_t stk[RC_STACK_MAX];
+	int depth = 1;
+	int nneg = 0;
+	rc_stk_t neg[8];
+	const int edge_head_u = vw->vrect_x;			/* edge_head.u >> 20 */
+	const int edge_tail_u = vw->vrectright;		/* ((vrectright<<20)+0xFFFFF) >> 20 */
+	stk[0].surf = 1; stk[0].key = 0x7FFFFFFF; stk[0].state = 1; stk[0].last_u = edge_head_u; stk[0].insub = 0;
+	const float fv = (float)line;
+
+	for (int k = 0; k < n; k++)
+	{
+		const int iu = aet[k].iu;
+		const int s0 = aet[k].surfs & 0xFFFF, s1 = aet[k].surfs >> 16;
+		if (s0)
+		{
+			/* R_TrailingEdge, r_edge.c:370-407 */
+			int pos = -1;
+			for (int i = 0; i < depth; i++)
+				if (stk[i].surf == s0) { pos = i; break; }
+			if (pos >= 0)
+			{
+				if (--stk[pos].state == 0)
+				{
+					if (pos == 0)
+					{
+						if (iu > stk[0].last_u)
+							RC_EMIT_SPAN (s0, stk[0].last_u, iu);
+						stk[1].last_u = iu;
+					}
+					for (int i = pos; i < depth - 1; i++)
+						stk[i] = stk[i+1];
+					depth--;
+				}
+			}
+			else
+			{
+				/* spanstate goes negative: trailing edge seen before the leading one */
+				int ni = -1;
+				for (int i = 0; i < nneg; i++)
+					if (neg[i].surf == s0) { ni = i; break; }
+				if (ni < 0)
+				{
+					if (nneg < 8) { ni = nneg++; neg[ni].surf = s0; neg[ni].state = 0; }
+					else RC_ATOMIC_OR_I (f->status, RC_STAT_STACK_OVERFLOW);
+				}
+				if (ni >= 0)
+					neg[ni].state--;
+			}
+			if (!s1)
+				continue;
+		}
+		if (s1)
+		{
+			/* R_LeadingEdge, r_edge.c:411-527 */
+			int pos = -1, ni = -1, state;
+			for (int i = 0; i < depth; i++)
+				if (stk[i].surf == s1) { pos = i; break; }
+			if (pos >= 0)
+			{
+				stk[pos].state++;	/* already in a span (state >= 1 -> >= 2): nothing else */
+				continue;
+			}
+			for (int i = 0; i < nneg; i++)
+				if (neg[i].surf == s1) { ni = i; break; }
+			state = (ni >= 0) ? neg[ni].state : 0;
+			state++;
+			if (ni >= 0)
+			{
+				neg[ni].state = state;
+				if (state == 0) { neg[ni] = neg[nneg-1]; nneg--; }
+			}
+			if (state != 1)
+				continue;
+
+			const rc_surf_t *sf = &surfs[s1];
+			const int skey = sf->key, sinsub = sf->insubmodel;
+			int at;			/* insert before stk[at] */
+			int newtop = 0;
+			if (skey < stk[0].key)
+				newtop = 1;
+			else if (sinsub && skey == stk[0].key)
+			{
+				/* two bmodels in the same leaf: sort on 1/z (r_edge.c:436-458) */
+				const rc_surf_t *s2 = &surfs[stk[0].surf];
+				double fu = (float)(aet_u_of (aet[k]) - 0xFFFFF) * (1.0 / 0x100000);
+				double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
+				double newzibottom = newzi * 0.99;
+				double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
+				if (newzibottom >= testzi)
+					newtop = 1;
+				else
+				{
+					double newzitop = newzi * 1.01;
+					if (newzitop >= testzi && sf->d_zistepu >= s2->d_zistepu)
+						newtop = 1;
+				}
+			}
+			if (newtop)
+			{
+				if (iu > stk[0].last_u)
+					RC_EMIT_SPAN (stk[0].surf, stk[0].last_u, iu);
+				at = 0;
+			}
+			else
+			{
+				at = 0;
+				for (;;)
+				{
+					do { at++; } while (skey > stk[at].key);
+					if (skey == stk[at].key)
+					{
+						if (!sinsub)
+							continue;
+						const rc_surf_t *s2 = &surfs[stk[at].surf];
+						double fu = (float)(aet_u_of (aet[k]) - 0xFFFFF) * (1.0 / 0x100000);
+						double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
+						double newzibottom = newzi * 0.99;
+						double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
+						if (newzibottom >= testzi)
+							break;
+						double newzitop = newzi * 1.01;
+						if (newzitop >= testzi && sf->d_zistepu >= s2->d_zistepu)
+							break;
+						continue;
+					}
+					break;
+				}
+			}
+			if (depth >= RC_STACK_MAX)
+			{
+				RC_ATOMIC_OR_I (f->status, RC_STAT_STACK_OVERFLOW);
+				continue;
+			}
+			for (int i = depth; i > at; i--)
+				stk[i] = stk[i-1];
+			depth++;
+			stk[at].surf = s1; stk[at].key = skey; stk[at].state = 1; stk[at].insub = sinsub;
+			stk[at].last_u = newtop ? iu : 0;
+		}
+	}
+	/* R_CleanupSpan, r_edge.c:256-285 */
+	if (edge_tail_u > stk[0].last_u)
+		RC_EMIT_SPAN (stk[0].surf, stk[0].last_u, edge_tail_u);
+	if (nneg)
+		RC_ATOMIC_OR_I (f->status, RC_STAT_STACK_OVERFLOW);	/* spanstate would leak into the next line */
+
+	for (int i = nsp; i < spanroom; i++)
+		f->spans[spanbase + i].count = 0;
+	for (int i = nblk; i < blockroom; i++)
+		f->blockspan[blockbase + i] = -1;
+}
+
+/* ------------------------------------------------------------- stage 4: surface prep --- */
+RC_HD int rc_lightadj_code (int value)
+{
+	/* compact code for an 8.8 light scale ((c-'a')*22, or 256 for an unset style,
+	 * r_light.c:40-48); 254 = not representable -> the block is built privately */
+	if (value == 256) return 255;
+	if (value % 22 == 0) { int c = value / 22 + 128; if (c >= 0 && c <= 253) return c; }
+	return 254;
+}
+
+RC_HD uint32_t rc_hash64 (unsigned long long k)
+{
+	k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+	return (uint32_t)k;
+}
+
+/* D_CalcGradients, d_edge.c:96-157 */
+RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc_face_t *fa, int miplevel, rc_surf_t *s)
+{
+	const rc_texinfo_t *ti = &w->texinfo[fa->texinfo];
+	float mipscale = 1.0 / (float)(1 << miplevel);
+	float p_saxis[3], p_taxis[3], p_temp1[3];
+	float t;
+	rc_transform_vector (vw, ti->vecs[0], p_saxis);
+	rc_transform_vector (vw, ti->vecs[1], p_taxis);
+	t = vw->xscaleinv * mipscale;
+	s->d_sdivzstepu = p_saxis[0] * t;
+	s->d_tdivzstepu = p_taxis[0] * t;
+	t = vw->yscaleinv * mipscale;
+	s->d_sdivzstepv = -p_saxis[1] * t;
+	s->d_tdivzstepv = -p_taxis[1] * t;
+	s->d_sdivzorigin = p_saxis[2] * mipscale - vw->xcenter * s->d_sdivzstepu - vw->ycenter * s->d_sdivzstepv;
+	s->d_tdivzorigin = p_taxis[2] * mipscale - vw->xcenter * s->d_tdivzstepu - vw->ycenter * s->d_tdivzstepv;
+	p_temp1[0] = vw->tmodelorg[0] * mipscale;
+	p_temp1[1] = vw->tmodelorg[1] * mipscale;
+	p_temp1[2] = vw->tmodelorg[2] * mipscale;
+	t = 0x10000*mipscale;
+	s->sadjust = rc_f2i ((float)(rc_d2i (rc_dot3 (p_temp1, p_saxis) * 0x10000 + 0.5) -
+			((fa->texturemins[0] << 16) >> miplevel)) + ti->vecs[0][3]*t);
+	s->tadjust = rc_f2i ((float)(rc_d2i (rc_dot3 (p_temp1, p_taxis) * 0x10000 + 0.5) -
+			((fa->texturemins[1] << 16) >> miplevel)) + ti->vecs[1][3]*t);
+	s->bbextents = ((fa->extents[0] << 16) >> miplevel) - 1;
+	s->bbextentt = ((fa->extents[1] << 16) >> miplevel) - 1;
+}
+
+#define RC_SRC_POOL    0
+#define RC_SRC_TEXELS  1
+#define RC_SRC_SOLID   2    /* background / fast sky: constant colour, z at "infinity" */
+
+/* One thread per (view, surface): the per-surface part of D_DrawSurfaces (d_edge.c:161-340)
+ * for surfaces that own spans: mip selection, D_CacheSurface lookup (d_surf.c:196) against
+ * the shared GPU surface cache, gradients.  surf->pad = texel source. */
+RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int si)
+{
+	const rc_view_t *vw = &f->views[vi];
+	rc_surf_t *s = f->surfs + (size_t)vi * f->surfcap + si;
+	if (!s->hasspans || s->flags == -1)
+		return;
+	s->cacheofs = -1;
+	s->miplevel = -1;		/* reused as the cache-table slot to resolve, -1: none */
+	if (s->flags & (RC_SURF_DRAWBACKGROUND | RC_SURF_DRAWSKY))
+	{
+		/* TODO(sky): scrolling sky; until then sky draws as r_fastsky does */
+		s->pad = RC_SRC_SOLID;
+		s->cachewidth = (s->flags & RC_SURF_DRAWBACKGROUND) ? vw->clearcolor : vw->skycolor;
+		s->d_ziorigin = -0.9; s->d_zistepu = 0; s->d_zistepv = 0;
+		return;
+	}
+	const rc_face_t *fa = &w->faces[s->face];
+	const rc_texinfo_t *ti = &w->texinfo[fa->texinfo];
+	if (s->flags & RC_SURF_DRAWTURB)
+	{
+		s->pad = RC_SRC_TEXELS;
+		s->cacheofs = w->textures[ti->texture].offsets[0];
+		s->cachewidth = 64;
+		rc_calc_gradients (w, vw, fa, 0, s);
+		return;
+	}
+	/* D_MipLevelForScale, d_edge.c:44-63 */
+	float scale = s->nearzi * vw->scale_for_mip * ti->mipadjust;
+	int mip;
+	if (scale >= vw->d_scalemip[0]) mip = 0;
+	else if (scale >= vw->d_scalemip[1]) mip = 1;
+	else if (scale >= vw->d_scalemip[2]) mip = 2;
+	else mip = 3;
+	if (mip < vw->d_minmip) mip = vw->d_minmip;
+
+	/* R_TextureAnimation, r_surf.c:60-87 (world entity: frame 0) */
+	int tex = ti->texture;
+	if (w->textures[tex].anim_total)
+	{
+		int reletive = vw->animtime % w->textures[tex].anim_total;
+		int count = 0;
+		while (w->textures[tex].anim_min > reletive || w->textures[tex].anim_max <= reletive)
+		{
+			tex = w->textures[tex].anim_next;
+			if (tex < 0 || ++count > 100) { tex = ti->texture; break; }
+		}
+	}
+	int la[4], codes[4], cacheable = 1;
+	for (int k = 0; k < 4; k++)
+	{
+		int st = fa->styles[k];
+		la[k] = st < RC_MAX_LIGHTSTYLES ? vw->lightstylevalue[st] : 0;	/* d_lightstylevalue[256]: 64.. never set */
+		codes[k] = rc_lightadj_code (la[k]);
+		if (codes[k] == 254) cacheable = 0;
+	}
+	int bw = fa->extents[0] >> mip, bh = fa->extents[1] >> mip;
+	int bytes = (bw * bh + 15) & ~15;
+	int slot = -1, creator = 0, ofs = -1;
+	if (cacheable)
+	{
+		unsigned long long key = ((unsigned long long)s->face << 44) | ((unsigned long long)mip << 42) |
+			((unsigned long long)tex << 32) | ((unsigned long long)codes[0] << 24) |
+			((unsigned long long)codes[1] << 16) | ((unsigned long long)codes[2] << 8) | (unsigned long long)codes[3];
+		uint32_t h = rc_hash64 (key) & (uint32_t)f->cachemask;
+		for (int probe = 0; probe <= f->cachemask; probe++)
+		{
+			unsigned long long prev = RC_ATOMIC_CAS_ULL (&f->cachekeys[h], RC_CACHE_EMPTY, key);
+			if (prev == RC_CACHE_EMPTY) { slot = (int)h; creator = 1; break; }
+			if (prev == key) { slot = (int)h; break; }
+			h = (h + 1) & (uint32_t)f->cachemask;
+		}
+		if (slot < 0) { RC_ATOMIC_OR_I (f->status, RC_STAT_CACHE_POOL); cacheable = 0; }
+	}
+	if (!cacheable || creator)
+	{
+		unsigned long long o = RC_ATOMIC_ADD_ULL (&f->alloc[1], (unsigned long long)bytes);
+		int j = (int)RC_ATOMIC_ADD_ULL (&f->alloc[2], 1ull);
+		if ((long long)(o + bytes) > f->cachecap || j >= f->jobcap)
+		{
+			RC_ATOMIC_OR_I (f->status, RC_STAT_CACHE_POOL);
+			ofs = 0;
+		}
+		else
+		{
+			rc_cachejob_t *job = &f->jobs[j];
+			ofs = (int)o;
+			job->face = s->face; job->mip = mip; job->texture = tex;
+			job->lightadj[0] = la[0]; job->lightadj[1] = la[1]; job->lightadj[2] = la[2]; job->lightadj[3] = la[3];
+			job->ambient = vw->ambientlight; job->dstofs = ofs; job->width = bw; job->height = bh;
+			job->view = -1; job->pad = vw->fullbright;
+		}
+		if (creator)
+			f->cachevals[slot] = ofs;
+	}
+	s->pad = RC_SRC_POOL;
+	s->cacheofs = ofs;
+	s->miplevel = (cacheable && !creator) ? slot : -1;
+	s->cachewidth = bw;
+	rc_calc_gradients (w, vw, fa, mip, s);
+}
+
+RC_HD void rc_surf_resolve (const rc_frame_t *f, int vi, int si)
+{
+	rc_surf_t *s = f->surfs + (size_t)vi * f->surfcap + si;
+	if (!s->hasspans || s->flags == -1)
+		return;
+	if (s->pad == RC_SRC_POOL && s->miplevel >= 0)
+		s->cacheofs = f->cachevals[s->miplevel];
+}
+
+/* ------------------------------------------------------------- stage 5: cache build ---- */
+/* one lightmap sample of R_BuildLightmap (r_light.c:372-425) */
+RC_HD unsigned rc_cache_luxel (const rc_world_t *w, const rc_cachejob_t *job, int i)
+{
+	const rc_face_t *fa = &w->faces[job->face];
+	int smax = (fa->extents[0] >> 4) + 1, tmax = (fa->extents[1] >> 4) + 1;
+	int size = smax * tmax;
+	if (job->pad /* r_fullbright */ || !w->haslight)
+		return 0;
+	unsigned bl = (unsigned)(job->ambient << 8);
+	if (fa->lightofs != -1)
+	{
+		const uint8_t *lightmap = w->lightdata + fa->lightofs;
+		for (int maps = 0; maps < RC_MAXLIGHTMAPS && fa->styles[maps] != 255; maps++)
+		{
+			unsigned scale = (unsigned)job->lightadj[maps];
+			bl += lightmap[i] * scale;
+			lightmap += size;
+		}
+	}
+	int t = (255*256 - (int)bl) >> (8 - 6);
+	if (t < (1 << 6))
+		t = (1 << 6);
+	return (unsigned)t;
+}
+
+/* one texel of R_DrawSurface + R_DrawSurfaceBlock8_mipN (r_surf.c:95-375), in closed form:
+ * the block drawers step light with wrapping 32-bit adds, so light at (row i, column b) of
+ * a block is lightright + i*rightstep + (bs-1-b)*((lightleft + i*leftstep - that) >> shift). */
+RC_HD uint8_t rc_cache_texel (const rc_world_t *w, const rc_cachejob_t *job, const unsigned *bl, int x, int y)
+{
+	const rc_face_t *fa = &w->faces[job->face];
+	const rc_texture_t *mt = &w->textures[job->texture];
+	const int mip = job->mip;
+	const int shift = 4 - mip, bs = 16 >> mip;
+	const int lw = (fa->extents[0] >> 4) + 1;
+	const int u = x >> shift, b = x & (bs - 1), vb = y >> shift, i = y & (bs - 1);
+	unsigned l00 = bl[vb * lw + u], l01 = bl[vb * lw + u + 1];
+	unsigned l10 = bl[(vb + 1) * lw + u], l11 = bl[(vb + 1) * lw + u + 1];
+	int lightleftstep = (int)((l10 - l00) >> shift);		/* unsigned >> : r_surf.c:202 (H4) */
+	int lightrightstep = (int)((l11 - l01) >> shift);
+	int lightleft = rc_addw ((int)l00, rc_mulw (i, lightleftstep));
+	int lightright = rc_addw ((int)l01, rc_mulw (i, lightrightstep));
+	int lighttemp = (int)((unsigned)lightleft - (unsigned)lightright);
+	int lightstep = lighttemp >> shift;
+	int light = rc_addw (lightright, rc_mulw (bs - 1 - b, lightstep));
+	/* source texel with the reference's tiling (texture sizes and texturemins are multiples
+	 * of the block size, so its "wrap to 0" equals a modulo) */
+	int tw = mt->width >> mip, th = mt->height >> mip;
+	int soffset = ((fa->texturemins[0] >> mip) + (tw << 16)) % tw;
+	int toffset = ((fa->texturemins[1] >> mip) + (th << 16)) % th;
+	int sx = (soffset + u * bs) % tw + b;
+	int sy = (toffset + y) % th;
+	uint8_t pix = w->texels[mt->offsets[mip] + sy * tw + sx];
+	return w->colormap[(light & 0xFF00) + pix];
+}
+
+/* ------------------------------------------------------------------ stage 6: draw ------ */
+/* One thread per 8-pixel block of a span: D_DrawSpans8 (d_scan.c:254-386) /
+ * Turbulent8 (d_scan.c:121-251) / D_DrawSolidSurface (d_edge.c:72-90) fused with
+ * D_DrawZSpans (d_scan.c:388-439).  The s/z, t/z, 1/z accumulators are advanced block by
+ * block exactly as the reference does (k rounded float adds for block k). */
+RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
+{
+	const int si = f->blockspan[t];
+	if (si < 0)
+		return;
+	const rc_span_t sp = f->spans[si];
+	const int k = t - sp.firstblock;
+	const rc_view_t *vw = &f->views[sp.view];
+	const rc_surf_t *s = f->surfs + (size_t)sp.view * f->surfcap + sp.surf;
+	const int first = k << 3;
+	int cnt = sp.count - first;
+	const int last = cnt <= 8;
+	if (cnt > 8) cnt = 8;
+	const size_t viewpix = (size_t)f->width * f->height;
+	uint8_t *pdest = f->fb + viewpix * sp.view + (size_t)vw->screenwidth * sp.v + sp.u + first;
+
+	const float du = (float)sp.u, dv = (float)sp.v;
+
+	/* ---- z (D_DrawZSpans) ---- */
+	if (f->zb)
+	{
+		int izistep = rc_f2i (s->d_zistepu * 0x8000 * 0x10000);
+		double zi = s->d_ziorigin + dv*s->d_zistepv + du*s->d_zistepu;
+		int izi0 = rc_d2i (zi * 0x8000 * 0x10000);
+		size_t zindex = (size_t)vw->zwidth * sp.v + sp.u;
+		int16_t *pz = f->zb + viewpix * sp.view + zindex;
+		const int a0 = (int)(zindex & 1);
+		const int doublecount = (sp.count - a0) >> 1;
+		for (int j = first; j < first + cnt; j++)
+		{
+			int izi = rc_addw (izi0, rc_mulw (j, izistep));
+			unsigned zval = (unsigned)(izi >> 16) & 0xFFFFu;
+			int rel = j - a0;
+			if (rel >= 0 && (rel & 1) && (rel >> 1) < doublecount)
+			{
+				/* second short of a 32-bit store: the first one's sign extension is OR-ed in
+				 * (d_scan.c:421-427: ltemp = izi >> 16 on a signed izi) */
+				int prev = rc_addw (izi0, rc_mulw (j - 1, izistep));
+				if (prev < 0)
+					zval = 0xFFFFu;
+			}
+			pz[j] = (int16_t)zval;
+		}
+	}
+
+	/* ---- colour ---- */
+	if (s->pad == RC_SRC_SOLID)
+	{
+		for (int j = 0; j < cnt; j++)
+			pdest[j] = (uint8_t)s->cachewidth;
+		return;
+	}
+	const int turb = (s->flags & RC_SURF_DRAWTURB) != 0;
+	const uint8_t *pbase = (s->pad == RC_SRC_TEXELS ? w->texels : f->cachepool) + s->cacheofs;
+	const int cachewidth = s->cachewidth;
+	const float sdivz8stepu = s->d_sdivzstepu * 8, tdivz8stepu = s->d_tdivzstepu * 8, zi8stepu = s->d_zistepu * 8;
+	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*s->d_sdivzstepu;
+	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*s->d_tdivzstepu;
+	float zi = s->d_ziorigin + dv*s->d_zistepv + du*s->d_zistepu;
+	for (int j = 0; j < k; j++)
+	{
+		sdivz += sdivz8stepu;
+		tdivz += tdivz8stepu;
+		zi += zi8stepu;
+	}
+	float z = (float)0x10000 / zi;
+	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
+	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
+	const int lo = k ? 8 : 0;	/* block 0 starts from the span start clamp, later blocks from a `snext` clamp */
+	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
+	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
+
+	int snext, tnext, sstep = 0, tstep = 0;
+	if (!last)
+	{
+		sdivz += sdivz8stepu;
+		tdivz += tdivz8stepu;
+		zi += zi8stepu;
+		z = (float)0x10000 / zi;
+		snext = rc_addw (rc_f2i (sdivz * z), s->sadjust);
+		if (snext > s->bbextents) snext = s->bbextents; else if (snext < 8) snext = 8;
+		tnext = rc_addw (rc_f2i (tdivz * z), s->tadjust);
+		if (tnext > s->bbextentt) tnext = s->bbextentt; else if (tnext < 8) tnext = 8;
+		sstep = (snext - ss) >> 3;
+		tstep = (tnext - tt) >> 3;
+	}
+	else
+	{
+		float spancountminus1 = (float)(cnt - 1);
+		sdivz += s->d_sdivzstepu * spancountminus1;
+		tdivz += s->d_tdivzstepu * spancountminus1;
+		zi += s->d_zistepu * spancountminus1;
+		z = (float)0x10000 / zi;
+		snext = rc_addw (rc_f2i (sdivz * z), s->sadjust);
+		if (snext > s->bbextents) snext = s->bbextents; else if (snext < 8) snext = 8;
+		tnext = rc_addw (rc_f2i (tdivz * z), s->tadjust);
+		if (tnext > s->bbextentt) tnext = s->bbextentt; else if (tnext < 8) tnext = 8;
+		if (cnt > 1)
+		{
+			sstep = (snext - ss) / (cnt - 1);
+			tstep = (tnext - tt) / (cnt - 1);
+		}
+	}
+	if (!turb)
+	{
+		for (int j = 0; j < cnt; j++)
+		{
+			pdest[j] = pbase[(ss >> 16) + (tt >> 16) * cachewidth];
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
+		}
+	}
+	else
+	{
+		const int *turbtab = w->sintable + vw->turbphase;
+		ss &= ((RC_CYCLE << 16) - 1);
+		tt &= ((RC_CYCLE << 16) - 1);
+		for (int j = 0; j < cnt; j++)
+		{
+			int sturb = ((ss + turbtab[(tt >> 16) & (RC_CYCLE - 1)]) >> 16) & 63;
+			int tturb = ((tt + turbtab[(ss >> 16) & (RC_CYCLE - 1)]) >> 16) & 63;
+			pdest[j] = pbase[(tturb << 6) + sturb];
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
+		}
+	}
+}
+
+#endif /* RC_PIPELINE_H */

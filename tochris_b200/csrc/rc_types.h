@@ -1,0 +1,234 @@
+/*
+ * rc_types.h -- plain-old-data records shared by the C host side and the CUDA kernels of
+ * ref_cuda.  Everything here is laid out for HBM: flat arrays indexed by int, no pointers
+ * inside records, 16/32-byte records so a lane fetches a record with one or two vector loads.
+ *
+ * Each record names the reference structure it replaces (paths relative to /root/reference).
+ */
+#ifndef RC_TYPES_H
+#define RC_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- limits (ref_soft/r_shared.h:40-41,110-114; raised where the reference needs a
+ *      recompile) ------------------------------------------------- */
+#define RC_MAXWIDTH        2047
+#define RC_MAXHEIGHT       1200
+#define RC_MAX_LIGHTSTYLES 64      /* common/quakedef.h:105 */
+#define RC_MAXLIGHTMAPS    4
+#define RC_MIPLEVELS       4
+#define RC_NEAR_CLIP       0.01    /* r_local.h:205 */
+#define RC_BACKFACE_EPSILON 0.01   /* r_local.h:68 */
+#define RC_CYCLE           128     /* d_iface.h turbulence period */
+#define RC_TURB_SPEED      20      /* r_local.h:242 */
+
+/* surface flags, ref_soft/r_model.h:72-78 */
+#define RC_SURF_PLANEBACK      2
+#define RC_SURF_DRAWSKY        4
+#define RC_SURF_DRAWSPRITE     8
+#define RC_SURF_DRAWTURB       0x10
+#define RC_SURF_DRAWTILED      0x20
+#define RC_SURF_DRAWBACKGROUND 0x40
+#define RC_SURF_DRAWSKYBOX     0x80
+
+#define RC_CONTENTS_SOLID (-2)
+
+/* ---- world model (replaces model_t's brush arrays, ref_soft/r_model.h:290-340) ------ */
+typedef struct {            /* cplane_t, common/mathlib.h */
+    float normal[3];
+    float dist;
+    int   type;
+    int   pad[3];
+} rc_plane_t;               /* 32 B */
+
+typedef struct {            /* mnode_t, r_model.h:118-134.  child >= 0: node, < 0: leaf -1-child */
+    int      plane;
+    int      children[2];
+    int16_t  minmaxs[6];
+    uint16_t firstsurface, numsurfaces;
+    int      parent;        /* node index or -1 */
+} rc_node_t;                /* 32 B */
+
+typedef struct {            /* mleaf_t, r_model.h:138-153 */
+    int     contents;
+    int16_t minmaxs[6];
+    int     firstmark, nummarks;
+    int     parent;
+    int     pad;
+} rc_leaf_t;                /* 32 B */
+
+typedef struct {            /* msurface_t, r_model.h:98-116 (static part) */
+    int      plane;
+    int      flags;
+    int      firstedge, numedges;
+    int16_t  texturemins[2];
+    int16_t  extents[2];
+    int      texinfo;
+    uint8_t  styles[4];
+    int      lightofs;      /* offset into lightdata or -1 */
+    int      node;          /* owning node (load-time derived) */
+    int      pad[2];
+} rc_face_t;                /* 48 B */
+
+typedef struct {            /* mtexinfo_t, r_model.h:90-96 */
+    float vecs[2][4];
+    float mipadjust;
+    int   texture;
+    int   flags;
+    int   pad;
+} rc_texinfo_t;             /* 48 B */
+
+typedef struct {            /* texture_t, r_model.h:63-72; offsets index the shared texel blob */
+    int width, height;
+    int offsets[4];
+    int anim_total, anim_min, anim_max;
+    int anim_next;          /* texture index or -1 */
+    int alternate_anims;    /* texture index or -1 */
+    int pad;
+} rc_texture_t;             /* 48 B */
+
+/* one entry per surfedge: who else uses the same medge_t (r_rast.c:583-603 edge cache) */
+typedef struct {
+    int partner_face;       /* -1: medge used by this face only */
+    int partner_slot;       /* index of the medge inside the partner's surfedge run */
+} rc_separtner_t;
+
+typedef struct {            /* device-resident world; all pointers are device pointers */
+    int numplanes, numnodes, numleafs /* incl. leaf 0 */, numfaces, numsurfedges, numedges,
+        numvertexes, numtexinfo, numtextures, nummarksurfaces, visleafs, haslight;
+    int numworldfaces;      /* faces of model 0 (without skybox faces) */
+    int visrowwords;        /* words per row of nodevis */
+    const rc_plane_t     *planes;
+    const rc_node_t      *nodes;
+    const rc_leaf_t      *leafs;
+    const rc_face_t      *faces;
+    const int            *surfedges;
+    const rc_separtner_t *separtner;
+    const uint16_t       *edges;       /* 2 x uint16 per medge_t */
+    const float          *vertexes;    /* 3 floats per mvertex_t */
+    const rc_texinfo_t   *texinfo;
+    const rc_texture_t   *textures;
+    const uint8_t        *texels;      /* all miptex pixel data */
+    const uint8_t        *lightdata;
+    const int            *marksurfaces;
+    const uint32_t       *nodevis;     /* [numleafs][visrowwords]: bit i<numnodes: node i, else leaf */
+    const uint8_t        *colormap;    /* vid.colormap, 64*256 */
+    const int            *sintable;    /* r_rast.c:45, SIN_BUFFER_SIZE ints */
+    const int            *intsintable;
+} rc_world_t;
+
+/* ---- per-view constants (host computed; replaces the globals written by R_SetupFrame,
+ *      R_ViewChanged, D_ViewChanged, D_SetupFrame, R_TransformFrustum,
+ *      R_SetUpFrustumIndexes, R_AnimateLight; see rc_host_view.c) --------------------- */
+typedef struct {
+    int   vrect_x, vrect_y, vrect_w, vrect_h, vrectright, vrectbottom;
+    float fvrectx_adj, fvrecty_adj, fvrectright_adj, fvrectbottom_adj;
+    int   vrect_x_adj_shift20, vrectright_adj_shift20;
+    float xcenter, ycenter, xscale, yscale, xscaleinv, yscaleinv, xscaleshrink, yscaleshrink;
+    float vpn[3], vright[3], vup[3], origin[3];
+    float tmodelorg[3];            /* TransformVector(modelorg), d_edge.c:173 */
+    float clipnormal[4][3];
+    float clipdist[4];
+    int   frustum_idx[4][6];
+    float scale_for_mip;
+    float d_scalemip[3];
+    int   d_minmip;
+    int   ambientlight;
+    int   animtime;                /* (int)(time*10)   r_surf.c:72 */
+    int   turbphase;               /* (int)(time*SPEED)&(CYCLE-1)  d_scan.c:128 */
+    int   rdflags;
+    int   dowarp;
+    int   clearcolor;              /* (int)r_clearcolor.value & 0xFF */
+    int   fullbright;              /* r_fullbright.value != 0 */
+    int   screenwidth;             /* row pitch of the colour target in bytes */
+    int   zwidth;                  /* d_zwidth (= vid.width) */
+    int   d_pix_min, d_pix_max, d_pix_shift, d_y_aspect_shift;
+    int   d_vrectx, d_vrecty, d_vrectright_particle, d_vrectbottom_particle;
+    float aliasxscale, aliasyscale, aliasxcenter, aliasycenter;
+    int   lightstylevalue[RC_MAX_LIGHTSTYLES];
+    int   skycolor;                /* (int)r_skycolor.value & 0xFF */
+    int   fastsky;                 /* r_fastsky.value != 0 */
+} rc_view_t;
+
+/* ---- per-view transient records ------------------------------------------------------ */
+typedef struct {            /* one rendered face: output of the BSP walk (r_bsp.c:436) */
+    int face;
+    int clipflags;
+    int key;                /* order-isomorphic to r_currentkey (r_rast.c:699) */
+    int pad;
+} rc_facerec_t;             /* 16 B */
+
+/* edge_t replacement (r_shared.h:199-208): 32 B, no pointers.  `rank` reproduces the
+ * newedges[] insertion order (r_rast.c:355-379): bit31 = emitted as trailing edge,
+ * bits 5..30 = emission order of the face (list position), bits 0..4 = slot in face. */
+typedef struct {
+    int      u, u_step;     /* 12.20 */
+    int16_t  v, v2;         /* first / last scanline */
+    uint16_t surfs[2];
+    uint32_t rank;
+    int      pad[3];
+} rc_edge_t;
+
+typedef struct {            /* surf_t replacement (r_shared.h:125-147) + drawing state */
+    int   key;
+    int   flags;
+    int   face;             /* world face index, -1 for the background */
+    int   insubmodel;
+    float nearzi;
+    float d_ziorigin, d_zistepu, d_zistepv;
+    /* filled by the surface-prep kernel for surfaces that own spans (d_edge.c:96-135,307) */
+    int   miplevel;
+    int   cacheofs;         /* byte offset of the texel block (cache pool or texel blob) */
+    int   cachewidth;
+    int   hasspans;
+    float d_sdivzstepu, d_tdivzstepu, d_sdivzstepv, d_tdivzstepv, d_sdivzorigin, d_tdivzorigin;
+    int   sadjust, tadjust, bbextents, bbextentt;
+    int   entity;
+    int   pad;
+} rc_surf_t;                /* 96 B */
+
+typedef struct {            /* espan_t replacement (r_shared.h:117-121), 16 B */
+    int      view;
+    uint16_t surf;
+    int16_t  v;
+    int16_t  u;
+    int16_t  count;
+    int      firstblock;    /* index of this span's first 8-pixel block in the block list */
+} rc_span_t;
+
+/* surface-cache build job (d_surf.c:196 D_CacheSurface miss) */
+typedef struct {
+    int face, mip, texture;
+    int lightadj[4];
+    int ambient;
+    int dstofs;             /* into the cache pool */
+    int width, height;      /* block size in texels */
+    int view;               /* for dynamic lights (-1: none) */
+    int pad;
+} rc_cachejob_t;            /* 48 B */
+
+/* error / status bits returned through the C-ABI */
+#define RC_OK                    0
+#define RC_ERR_CUDA              (-1)
+#define RC_ERR_ARG               (-2)
+#define RC_ERR_NOWORLD           (-3)
+#define RC_ERR_FILE              (-4)
+#define RC_ERR_FORMAT            (-5)
+#define RC_ERR_NOMEM             (-6)
+#define RC_STAT_EDGE_OVERFLOW    1   /* a view produced more edges than r_maxedges: the reference drops faces (r_rast.c:544) */
+#define RC_STAT_SURF_OVERFLOW    2   /* ditto r_maxsurfs (r_rast.c:537) */
+#define RC_STAT_SPAN_POOL        4   /* internal span pool was too small (retried by the host) */
+#define RC_STAT_AET_OVERFLOW     8   /* more active edges on one scanline than the scan kernel holds */
+#define RC_STAT_STACK_OVERFLOW   16  /* active surface stack deeper than the scan kernel holds */
+#define RC_STAT_CACHE_POOL       32  /* surface cache pool too small (retried by the host) */
+#define RC_STAT_STALE_CLIPVERT   64  /* reference would read r_rightenter/r_rightexit left over from an earlier face */
+#define RC_STAT_FACELIST         128 /* face list capacity exceeded */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
