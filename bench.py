@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric for ref_cuda: frames/s of batched ref_soft views.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, libref_cuda.so)
+  python bench.py --impl reference --gpus N ...            the reference's own C renderer on the host cores
+
+A step = one pass of the hot path (R_RenderView semantics per view) over one batch of
+synthetic views.  N=1 workload = BASELINE.json configs[1]: procedural multi-room BSP with
+lightmaps and 4 mip levels, 640x480, batch of 64 views.  N>1: every rank renders its own
+64-view shard (weak scaling) and the finished framebuffers are gathered to rank 0 over NCCL
+inside the timed region -- the only collective on this path.
+
+value  : frames/s, device-timed (CUDA events on the launching stream), world + outputs in HBM
+e2e    : frames/s through RC_RenderViews with HOST buffers (view upload + framebuffer download)
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = "C2: procedural multi-room BSP (4x4 rooms, lightmaps, 4 mips), 640x480, 64 views per GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views", type=int, default=64, help="views per GPU per step")
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--scene", default="multi")
+    ap.add_argument("--keep-cache", action="store_true", help="do not flush the surface cache between steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ scene ----
+def make_scene(args, rank):
+    import rcutil
+    base = tempfile.mkdtemp(prefix=f"rc_bench_{rank}_")
+    rcutil.make_assets(base, names=[args.scene])
+    specs = rcutil.scene_views(args.scene, args.views, start=1 + rank * args.views, time=1.0)
+    return base, specs
+
+
+# -------------------------------------------------------------------- reference on CPU ----
+def _cpu_worker(idx, nworkers, basedir, mapname, w, h, specs, barrier, seconds, passes, q):
+    try:
+        sys.path.insert(0, ROOT)
+        from oracle.refsoft import RefSoft
+        from tochris_b200.scenes.views import build_refdefs
+        mine = specs[idx::nworkers]
+        r = RefSoft(basedir, w, h, heap_mb=64)
+        r.load_world(mapname)
+        rds = build_refdefs(mine, w, h, model_resolver=r.model)
+        r.render_batch(rds, False, False)            # warm-up pass (surface cache, page-in)
+        barrier.wait()
+        t0 = time.perf_counter()
+        done = 0
+        if passes:
+            for _ in range(passes):
+                r.render_batch(rds, False, False)
+                done += 1
+        else:
+            while time.perf_counter() - t0 < seconds:
+                r.render_batch(rds, False, False)
+                done += 1
+        t1 = time.perf_counter()
+        q.put((idx, len(mine) * done, t0, t1))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((idx, -1, 0.0, traceback.format_exc()))
+
+
+def run_reference_cpu(basedir, mapname, w, h, specs, seconds=8.0, passes=0):
+    """The oracle (unmodified ref_soft C path), one engine process per host core over the
+    same view batch (views split evenly), each looping R_RenderView over its slice after one
+    warm-up pass (pattern of R_TimeRefresh_f, ref_soft/r_misc.c:42-58)."""
+    from oracle import refsoft
+    if not refsoft.available():
+        return None
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
+    nworkers = max(1, min(cores, len(specs)))
+    ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(nworkers)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(i, nworkers, basedir, mapname, w, h, specs, barrier, seconds, passes, q))
+             for i in range(nworkers)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for r in res:
+        if r[1] < 0:
+            raise RuntimeError("reference worker failed:\n" + str(r[3]))
+    frames = sum(r[1] for r in res)
+    wall = max(r[3] for r in res) - min(r[2] for r in res)
+    return dict(frames=frames, seconds=wall, fps=frames / wall, cores=nworkers, host_cores=cores)
+
+
+# ------------------------------------------------------------------------------ clocks ----
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop = index, [], False
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------- ours ----
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tochris_b200.api import RefCuda, status_names
+    from tochris_b200.scenes.views import build_refdefs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- ref_cuda has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    base, specs = make_scene(args, rank)
+    W, H, n = args.width, args.height, args.views
+    r = RefCuda(base, W, H, device=local)
+    r.load_world(f"maps/{args.scene}.bsp")
+    rds = build_refdefs(specs, W, H, model_resolver=r.model)
+    dev = torch.device("cuda", local)
+    fb = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+    zb = torch.empty((n, H, W), dtype=torch.int16, device=dev)
+    gather = [torch.empty_like(fb) for _ in range(world)] if (world > 1 and rank == 0) else None
+    l2flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    px = n * W * H
+
+    def step(timed_events=None):
+        if not args.keep_cache:
+            r.flush_caches()               # D_FlushCaches: every step rebuilds its surface blocks
+        l2flush.zero_()                    # evict the previous step's data from the 126 MB L2
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        st = r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(fb, gather, dst=0)
+        if timed_events is not None:
+            timed_events[1].record(stream)
+        return st
+
+    status = 0
+    for _ in range(max(args.warmup, 3)):
+        status |= step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = r.stats()["kernel_launches"]
+    launches = 0
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        status |= step(evs[k])
+        launches += r.stats()["kernel_launches"]
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    sampler.stop = True
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers ----
+    fb_host = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    fb_np = fb_host.numpy()
+    e2e_s = 0.0
+    for k in range(3 + args.steps):
+        if not args.keep_cache:
+            r.flush_caches()
+        l2flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, st = r.render(rds, n, want_z=False, fb=fb_np)
+        dt = time.perf_counter() - t0
+        status |= st
+        if k >= 3:
+            e2e_s += dt
+    # ---- per-kernel times (profiling mode puts events between the kernels) ----
+    r.set_profiling(True)
+    prof = {}
+    for k in range(args.steps):
+        if not args.keep_cache:
+            r.flush_caches()
+        l2flush.zero_()
+        r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        s = r.stats()
+        for key, v in s.items():
+            prof[key] = prof.get(key, 0) + v
+    r.set_profiling(False)
+    torch.cuda.synchronize()
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    frames = n * world * args.steps
+    ms_per_step = dev_ms / args.steps
+    value = frames / (dev_ms / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    draw_ms = prof["ms_draw"] / args.steps
+    alg_bytes = 4.0 * px                      # 1 B texel + 1 B colour + 2 B z per pixel
+    achieved = alg_bytes / (draw_ms * 1e-3) / 1e9 if draw_ms > 0 else 0.0
+    out = {
+        "metric": "frames/s, batched ref_soft views (pixel-exact 8-bit framebuffer + int16 z-buffer)",
+        "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 fixed-point + f32 setup (fmad off)", "data": "synthetic",
+        "config": {"workload": WORKLOAD if (args.scene, W, H, n) == ("multi", 640, 480, 64) else f"{args.scene} {W}x{H} x{n} views per GPU",
+                   "width": W, "height": H, "views_per_gpu": n, "global_batch": n * world, "parallelism": f"dp{world} by view",
+                   "l2": "flushed between steps (256 MiB write)",
+                   "surface_cache": "kept across steps" if args.keep_cache else "flushed before every step (all visible blocks rebuilt inside the timed region)",
+                   "collective": "NCCL gather of framebuffers to rank 0 inside the timed region" if world > 1 else "none"},
+        "mpixel_per_s": round(value * W * H / 1e6, 1),
+        "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),
+        "e2e": {"value": round(n * world * args.steps / e2e_s, 1), "unit": "frames/s",
+                "h2d_bytes_per_step": int(n * 648), "d2h_bytes_per_step": int(px), "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
+                "note": "RC_RenderViews: refdef_t[] in host memory -> 8-bit framebuffers in pinned host memory (z stays on device)"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "status": status_names(status),
+        "roofline": {"bound": "hbm", "kernel": "k_draw (span texture mapping + z-buffer)", "achieved": round(achieved, 1), "peak": peak,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "alg_bytes_per_launch": int(alg_bytes), "kernel_ms": round(draw_ms, 4),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+        "kernel_ms_per_step": {k[3:]: round(v / args.steps, 4) for k, v in prof.items() if k.startswith("ms_") and k not in ("ms_h2d", "ms_d2h")},
+        "per_step_counts": {k: int(prof[k] / args.steps) for k in ("faces", "edges", "spans", "blocks", "cache_jobs", "cache_texels")},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_reference_cpu(base, f"maps/{args.scene}.bsp", W, H, specs, seconds=args.cpu_seconds)
+        if cb:
+            out["cpu_baseline"] = {"value": round(cb["fps"], 1), "unit": "frames/s", "cores": cb["cores"], "kind": "reference",
+                                   "sample": f"the same {n}-view batch split over {cb['cores']} engine processes (host has {cb['host_cores']} cores), looped for {cb['seconds']:.1f} s after a warm-up pass; oracle/_ref = unmodified ref_soft C path, gcc -O2"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, specs = make_scene(args, 0)
+    W, H, n = args.width, args.height, args.views
+    from oracle import refsoft
+    if not refsoft.available():
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        else:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/librefsoft.so missing and /root/reference absent"}))
+            return
+    run_reference_cpu(base, f"maps/{args.scene}.bsp", W, H, specs, passes=max(args.warmup, 1))
+    cb = run_reference_cpu(base, f"maps/{args.scene}.bsp", W, H, specs, passes=args.steps)
+    value = cb["fps"]
+    out = {
+        "impl": "reference",
+        "metric": "frames/s, batched ref_soft views (pixel-exact 8-bit framebuffer + int16 z-buffer)",
+        "value": round(value, 1), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(cb["seconds"] / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 fixed-point + f32 setup", "data": "synthetic",
+        "config": {"workload": WORKLOAD if (args.scene, W, H, n) == ("multi", 640, 480, 64) else f"{args.scene} {W}x{H} x{n} views",
+                   "width": W, "height": H, "views_per_gpu": n, "global_batch": n, "parallelism": f"{cb['cores']} host processes by view"},
+        "mpixel_per_s": round(value * W * H / 1e6, 1),
+        "cpu_baseline": {"value": round(value, 1), "unit": "frames/s", "cores": cb["cores"], "kind": "reference",
+                         "sample": f"{args.steps} passes over the {n}-view batch split over {cb['cores']} engine processes (host has {cb['host_cores']} cores)"},
+        "e2e": {"value": round(value, 1), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,61 @@
+"""TEST INFRASTRUCTURE ONLY: runs the compiled reference (oracle/_ref) in a fresh process.
+ref_soft keeps all state in globals and its buffers are sized at init, so every
+(asset dir, resolution, cvar set) needs its own process."""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat):
+    try:
+        sys.path.insert(0, ROOT)
+        from oracle.refsoft import RefSoft
+        from tochris_b200.scenes.views import build_refdefs
+        import ctypes as C
+        r = RefSoft(basedir, width, height, heap_mb=96)
+        for k, v in (cvars or {}).items():
+            r.set_cvar(k, v)
+        r.load_world(mapname)
+        cm = C.addressof(C.c_char.in_dll(r.lib, "vid")) + 8     # vid.colormap (client/vid.h:36: after `byte *buffer`)
+        rds = build_refdefs(specs, width, height, model_resolver=r.model, colormap_ptr=cm)
+        out = {}
+        if want_dump:
+            r.dump_enable(True)
+            fbs, zs, dumps = [], [], []
+            for i in range(len(specs)):
+                fb, z = r.render(rds[i], True)
+                fbs.append(fb); zs.append(z)
+                e, s, sp = r.dump_get()
+                dumps.append((e, s, sp, r.counters()))
+            out["fb"] = np.stack(fbs); out["z"] = np.stack(zs); out["dumps"] = dumps
+        else:
+            secs = 0.0
+            for _ in range(max(1, repeat)):
+                fb, z, secs = r.render_batch(rds, True, want_z)
+            out["fb"] = fb; out["z"] = z; out["seconds"] = secs
+        q.put(("ok", out))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put(("err", traceback.format_exc()))
+
+
+def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat))
+    p.start()
+    try:
+        kind, payload = q.get(timeout=timeout)
+    finally:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    if kind != "ok":
+        raise RuntimeError("oracle failed:\n" + payload)
+    return payload

@@ -1,0 +1,541 @@
+/*
+ * rc_gpu.cu -- the CUDA (sm_100a) side of ref_cuda: device memory, kernels, launch order.
+ *
+ * Built with  nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
+ * (float results must match the reference's C path bit for bit: no FMA contraction,
+ * IEEE division, see rc_pipeline.h).  Tensor cores are not used: nothing on this path is a
+ * dense contraction (BASELINE.json north_star); the kernels are integer/byte gather-scatter
+ * work bounded by HBM/L2 traffic and by latency in the per-view front end.
+ *
+ * One process drives one GPU.  A batch of views goes through, per chunk of views:
+ *   k_walk      1 thread / view           BSP descent, PVS, frustum cull -> ordered face list
+ *   k_faces     1 thread / (view, face)   clip + project edges, surf_t setup
+ *   k_fixup     1 thread / (view, face)   cross-face r_rightenter/r_rightexit reads
+ *   k_scan      1 thread / (view, line)   active-edge table -> spans + 8-pixel block list
+ *   k_surfprep  1 thread / (view, surf)   mip, gradients, surface-cache lookup -> build jobs
+ *   k_resolve   1 thread / (view, surf)   cache slot -> pool offset
+ *   k_cache     1 CTA    / job (strided)  lightmap + colormap'd texel block
+ *   k_draw      1 thread / 8-pixel block  perspective texture mapping + z-buffer
+ * All launches are asynchronous on one stream; counts produced on the device (jobs, blocks)
+ * are consumed by grid-stride loops, so the host never waits inside a batch.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "rc_host.h"
+#include "rc_pipeline.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
+
+struct rc_gpu_s {
+	int device, width, height, numsms;
+	cudaStream_t stream;
+	/* world */
+	rc_world_t w;			/* device pointers */
+	std::vector<void *> worldallocs;
+	bool haveworld;
+	int maxedges, maxsurfs;
+	int *d_sintable, *d_intsintable;
+	/* surface cache (persists across batches) */
+	unsigned long long *d_cachekeys; int *d_cachevals; int cacheslots;
+	uint8_t *d_cachepool; long long cachecap;
+	/* per-chunk buffers */
+	int chunkcap;			/* views the buffers below are sized for */
+	int maxchunk;			/* largest chunk the memory budget allows */
+	int maxviews;			/* user cap on views in flight (0: auto) */
+	int facecap, edgecap, surfcap, spancap, blockcap, jobcap;
+	int spans_per_line;		/* sizing heuristic, doubled on RC_STAT_SPAN_POOL */
+	rc_view_t *d_views;
+	rc_facerec_t *d_facelist; int *d_nfaces; uint16_t *d_facepos;
+	rc_edge_t *d_edges; int *d_nedges;
+	rc_surf_t *d_surfs;
+	rc_span_t *d_spans; int *d_blockspan;
+	rc_cachejob_t *d_jobs;
+	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
+	int *d_status;
+	/* host-output path */
+	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
+	/* stats */
+	rc_stats_t stats;
+	int profiling;
+	int flush_pending;		/* D_FlushCaches requested: done on the stream of the next render */
+	long long launches_total;
+	cudaEvent_t ev[10];
+	int last_n;
+};
+
+/* ------------------------------------------------------------------------ kernels ----- */
+__global__ void k_walk (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (vi < f.nviews)
+		rc_walk_view (&w, &f, vi);
+}
+
+__global__ void k_faces (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int p = blockIdx.y * blockDim.x + threadIdx.x;
+	if (p < f.nfaces[vi])
+		rc_render_face (&w, &f, vi, p);
+}
+
+__global__ void k_fixup (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int p = blockIdx.y * blockDim.x + threadIdx.x;
+	if (p < f.nfaces[vi])
+		rc_face_fixup (&w, &f, vi, p);
+}
+
+__global__ void k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int line = blockIdx.y * blockDim.x + threadIdx.x;
+	if (line < f.height)
+		rc_scan_line (&w, &f, vi, line);
+}
+
+__global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int si = 1 + blockIdx.y * blockDim.x + threadIdx.x;
+	if (si < f.nfaces[vi] + 2)
+		rc_surf_prep (&w, &f, vi, si);
+}
+
+__global__ void k_resolve (const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int si = 1 + blockIdx.y * blockDim.x + threadIdx.x;
+	if (si < f.nfaces[vi] + 2)
+		rc_surf_resolve (&f, vi, si);
+}
+
+/* One CTA per surface-cache job, strided over the job list the prep kernel produced.
+ * blocklights (<= 17x17 luxels) are built once in shared memory, then every thread shades
+ * texels: 1 B source texel in, 1 B colormap'd texel out. */
+__global__ void k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	__shared__ unsigned bl[18 * 18];
+	unsigned long long nj = f.alloc[2];
+	int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
+	for (int j = blockIdx.x; j < njobs; j += gridDim.x)
+	{
+		const rc_cachejob_t job = f.jobs[j];
+		const rc_face_t *fa = &w.faces[job.face];
+		int size = ((fa->extents[0] >> 4) + 1) * ((fa->extents[1] >> 4) + 1);
+		__syncthreads ();
+		for (int i = threadIdx.x; i < size; i += blockDim.x)
+			bl[i] = rc_cache_luxel (&w, &job, i);
+		__syncthreads ();
+		int total = job.width * job.height;
+		uint8_t *dst = f.cachepool + job.dstofs;
+		for (int t = threadIdx.x; t < total; t += blockDim.x)
+		{
+			int y = t / job.width, x = t - y * job.width;
+			dst[t] = rc_cache_texel (&w, &job, bl, x, y);
+		}
+	}
+}
+
+__global__ void k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	unsigned long long a = f.alloc[0];
+	int nblocks = (int)(a >> 32);
+	if (nblocks > f.blockcap) nblocks = f.blockcap;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nblocks; t += gridDim.x * blockDim.x)
+		rc_draw_block (&w, &f, t);
+}
+
+__global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+
+/* ------------------------------------------------------------------------- host ------- */
+template <typename T>
+static int upload (rc_gpu_t *g, const T *src, size_t count, const T **dst, char *err, size_t errlen)
+{
+	void *d = NULL;
+	size_t bytes = sizeof(T) * (count ? count : 1);
+	CK (cudaMalloc (&d, bytes));
+	g->worldallocs.push_back (d);
+	if (count) CK (cudaMemcpy (d, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+	*dst = (const T *)d;
+	return RC_OK;
+}
+
+extern "C" {
+
+rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen)
+{
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount (&count);
+	if (e != cudaSuccess || count <= 0)
+	{
+		snprintf (err, errlen, "ref_cuda needs a CUDA device: %s (there is no CPU rendering path)",
+			  e != cudaSuccess ? cudaGetErrorString (e) : "no device found");
+		return NULL;
+	}
+	if (device < 0 || device >= count) { snprintf (err, errlen, "device %d out of range (%d devices)", device, count); return NULL; }
+	if (cudaSetDevice (device) != cudaSuccess) { snprintf (err, errlen, "cudaSetDevice(%d) failed", device); return NULL; }
+	rc_gpu_t *g = new rc_gpu_s ();
+	memset (&g->stats, 0, sizeof(g->stats));
+	g->device = device; g->width = width; g->height = height;
+	g->haveworld = false; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
+	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0;
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties (&prop, device);
+	g->numsms = prop.multiProcessorCount;
+	cudaStreamCreateWithFlags (&g->stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
+
+	std::vector<int> st (RC_SIN_BUFFER_SIZE), ist (RC_SIN_BUFFER_SIZE);
+	RC_BuildTurbTables (st.data (), ist.data (), RC_SIN_BUFFER_SIZE);
+	cudaMalloc (&g->d_sintable, sizeof(int) * RC_SIN_BUFFER_SIZE);
+	cudaMalloc (&g->d_intsintable, sizeof(int) * RC_SIN_BUFFER_SIZE);
+	cudaMemcpy (g->d_sintable, st.data (), sizeof(int) * RC_SIN_BUFFER_SIZE, cudaMemcpyHostToDevice);
+	cudaMemcpy (g->d_intsintable, ist.data (), sizeof(int) * RC_SIN_BUFFER_SIZE, cudaMemcpyHostToDevice);
+
+	g->cachecap = cache_bytes ? (long long)cache_bytes : (1ll << 30);
+	if (g->cachecap > 0x7FFF0000ll) g->cachecap = 0x7FFF0000ll;	/* offsets are int */
+	g->cacheslots = 1 << 18;
+	if (cudaMalloc (&g->d_cachepool, g->cachecap) != cudaSuccess ||
+	    cudaMalloc (&g->d_cachekeys, sizeof(unsigned long long) * g->cacheslots) != cudaSuccess ||
+	    cudaMalloc (&g->d_cachevals, sizeof(int) * g->cacheslots) != cudaSuccess ||
+	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 4) != cudaSuccess ||
+	    cudaMalloc (&g->d_status, sizeof(int) * 4) != cudaSuccess)
+	{
+		snprintf (err, errlen, "cudaMalloc (surface cache) failed: %s", cudaGetErrorString (cudaGetLastError ()));
+		delete g;
+		return NULL;
+	}
+	cudaMemset (g->d_alloc, 0, sizeof(unsigned long long) * 4);
+	cudaMemset (g->d_cachekeys, 0xFF, sizeof(unsigned long long) * g->cacheslots);
+	cudaDeviceSynchronize ();
+	return g;
+}
+
+static void free_chunk (rc_gpu_t *g)
+{
+	cudaFree (g->d_views); cudaFree (g->d_facelist); cudaFree (g->d_nfaces); cudaFree (g->d_facepos);
+	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
+	cudaFree (g->d_blockspan); cudaFree (g->d_jobs);
+	g->d_views = NULL; g->chunkcap = 0;
+}
+
+static void free_world (rc_gpu_t *g)
+{
+	for (void *p : g->worldallocs) cudaFree (p);
+	g->worldallocs.clear ();
+	g->haveworld = false;
+}
+
+void rc_gpu_destroy (rc_gpu_t *g)
+{
+	if (!g) return;
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	free_chunk (g); free_world (g);
+	cudaFree (g->d_cachepool); cudaFree (g->d_cachekeys); cudaFree (g->d_cachevals);
+	cudaFree (g->d_alloc); cudaFree (g->d_status); cudaFree (g->d_sintable); cudaFree (g->d_intsintable);
+	cudaFree (g->d_fb); cudaFree (g->d_zb);
+	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
+	cudaStreamDestroy (g->stream);
+	delete g;
+}
+
+int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen)
+{
+	const rc_world_t *h = &hw->w;
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	free_world (g);
+	free_chunk (g);
+	g->w = *h;
+#define UP(field, count) if (upload (g, h->field, (size_t)(count), &g->w.field, err, errlen) != RC_OK) return RC_ERR_CUDA;
+	UP (planes, h->numplanes + 6)
+	UP (nodes, h->numnodes)
+	UP (leafs, h->numleafs)
+	UP (faces, h->numfaces + 6)
+	UP (surfedges, h->numsurfedges + 24)
+	UP (separtner, h->numsurfedges + 1)
+	UP (edges, (size_t)(h->numedges + 13) * 2)
+	UP (vertexes, (size_t)(h->numvertexes + 8) * 3)
+	UP (texinfo, h->numtexinfo + 6)
+	UP (textures, h->numtextures + 1)
+	UP (texels, hw->texelbytes + 16)
+	UP (lightdata, hw->lightbytes + 16)
+	UP (marksurfaces, h->nummarksurfaces + 1)
+	UP (nodevis, (size_t)h->visrowwords * h->numleafs)
+	UP (colormap, 256 * 64)
+#undef UP
+	g->w.sintable = g->d_sintable;
+	g->w.intsintable = g->d_intsintable;
+	g->maxedges = maxedges; g->maxsurfs = maxsurfs;
+	g->haveworld = true;
+	rc_gpu_flush_caches (g);
+	return RC_OK;
+}
+
+void rc_gpu_flush_caches (rc_gpu_t *g)
+{
+	g->flush_pending = 1;
+}
+
+static void do_flush (rc_gpu_t *g, cudaStream_t s)
+{
+	/* only the slots that can be in use are cleared: the table is sized for the pool */
+	k_fill64<<<g->numsms * 4, 256, 0, s>>> (g->d_cachekeys, RC_CACHE_EMPTY, (size_t)g->cacheslots);
+	cudaMemsetAsync (g->d_alloc + 1, 0, sizeof(unsigned long long), s);
+	g->flush_pending = 0;
+}
+
+static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int surfcap, int numfaces)
+{
+	size_t lines = g->height;
+	size_t spans = lines * g->spans_per_line, blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
+	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 2 * (size_t)numfaces + sizeof(rc_edge_t) * edgecap +
+	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
+}
+
+static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
+{
+	const rc_world_t *w = &g->w;
+	int facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
+	if (facecap < 1) facecap = 1;
+	int edgecap = g->maxedges, surfcap = facecap + 2;
+	size_t freeb = 0, totalb = 0;
+	if (g->d_views && g->facecap == facecap && g->edgecap == edgecap && (g->chunkcap >= n || g->chunkcap == g->maxchunk))
+		return RC_OK;
+	cudaMemGetInfo (&freeb, &totalb);
+	size_t pv = per_view_bytes (g, facecap, edgecap, surfcap, w->numfaces);
+	size_t budget = (size_t)(totalb * 0.35);
+	int maxchunk = (int)(budget / pv);
+	if (maxchunk < 1) maxchunk = 1;
+	if (maxchunk > 65535) maxchunk = 65535;		/* one grid dimension per view */
+	if (g->maxviews > 0 && maxchunk > g->maxviews) maxchunk = g->maxviews;
+	int want = n < maxchunk ? n : maxchunk;
+	g->maxchunk = maxchunk;
+	free_chunk (g);
+	g->facecap = facecap; g->edgecap = edgecap; g->surfcap = surfcap;
+	size_t lines = (size_t)g->height * want;
+	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
+	size_t blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
+	g->blockcap = (int)(blocks < 0x7FFFFFFF ? blocks : 0x7FFFFFFF);
+	g->jobcap = want * 8 + 4096;
+	if (g->jobcap > want * surfcap) g->jobcap = want * surfcap;
+	CK (cudaMalloc (&g->d_views, sizeof(rc_view_t) * want));
+	CK (cudaMalloc (&g->d_facelist, sizeof(rc_facerec_t) * (size_t)want * facecap));
+	CK (cudaMalloc (&g->d_nfaces, sizeof(int) * want));
+	CK (cudaMalloc (&g->d_facepos, sizeof(uint16_t) * (size_t)want * w->numfaces));
+	CK (cudaMalloc (&g->d_edges, sizeof(rc_edge_t) * (size_t)want * edgecap));
+	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
+	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
+	CK (cudaMalloc (&g->d_spans, sizeof(rc_span_t) * (size_t)g->spancap));
+	CK (cudaMalloc (&g->d_blockspan, sizeof(int) * (size_t)g->blockcap));
+	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
+	g->chunkcap = want;
+	return RC_OK;
+}
+
+/* one chunk of views, everything asynchronous on `s` */
+static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, int16_t *zb, cudaStream_t s,
+		      bool timed, char *err, size_t errlen)
+{
+	const rc_world_t &w = g->w;
+	rc_frame_t f;
+	memset (&f, 0, sizeof(f));
+	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views;
+	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
+	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
+	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
+	f.spans = g->d_spans; f.spancap = g->spancap; f.blockspan = g->d_blockspan; f.blockcap = g->blockcap;
+	f.alloc = g->d_alloc;
+	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
+	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
+	f.jobs = g->d_jobs; f.jobcap = g->jobcap;
+	f.fb = fb; f.zb = zb; f.status = g->d_status;
+
+	if (timed) cudaEventRecord (g->ev[0], s);
+	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
+	CK (cudaMemsetAsync (g->d_facepos, 0xFF, sizeof(uint16_t) * (size_t)n * w.numfaces, s));
+	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
+	CK (cudaMemsetAsync (g->d_alloc + 2, 0, sizeof(unsigned long long), s));
+	g->stats.kernel_launches += 0;
+
+	k_walk<<<(n + 31) / 32, 32, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[1], s);
+	dim3 gf (n, (g->facecap + 63) / 64);
+	k_faces<<<gf, 64, 0, s>>> (w, f);
+	k_fixup<<<gf, 64, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[2], s);
+	dim3 gs (n, (g->height + 31) / 32);
+	k_scan<<<gs, 32, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[3], s);
+	dim3 gp (n, (g->surfcap + 63) / 64);
+	k_surfprep<<<gp, 64, 0, s>>> (w, f);
+	k_resolve<<<gp, 64, 0, s>>> (f);
+	if (timed) cudaEventRecord (g->ev[4], s);
+	k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[5], s);
+	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[6], s);
+	g->stats.kernel_launches += 8;
+	CK (cudaGetLastError ());
+	return RC_OK;
+}
+
+static void collect_stats (rc_gpu_t *g, int n, bool timed)
+{
+	unsigned long long a[4];
+	cudaMemcpy (a, g->d_alloc, sizeof(a), cudaMemcpyDeviceToHost);
+	g->stats.spans += (long long)(a[0] & 0xFFFFFFFFu);
+	g->stats.blocks += (long long)(a[0] >> 32);
+	g->stats.cache_jobs += (long long)a[2];
+	std::vector<int> ne (n), nf (n);
+	cudaMemcpy (ne.data (), g->d_nedges, sizeof(int) * n, cudaMemcpyDeviceToHost);
+	cudaMemcpy (nf.data (), g->d_nfaces, sizeof(int) * n, cudaMemcpyDeviceToHost);
+	for (int i = 0; i < n; i++) { g->stats.edges += ne[i]; g->stats.faces += nf[i]; }
+	if (g->stats.cache_jobs > 0)
+	{
+		int nj = (int)(a[2] < (unsigned long long)g->jobcap ? a[2] : g->jobcap);
+		std::vector<rc_cachejob_t> jobs (nj);
+		if (nj) cudaMemcpy (jobs.data (), g->d_jobs, sizeof(rc_cachejob_t) * nj, cudaMemcpyDeviceToHost);
+		for (int i = 0; i < nj; i++) g->stats.cache_texels += (long long)jobs[i].width * jobs[i].height;
+	}
+	if (timed)
+	{
+		float ms;
+		cudaEventElapsedTime (&ms, g->ev[0], g->ev[1]); g->stats.ms_walk += ms;
+		cudaEventElapsedTime (&ms, g->ev[1], g->ev[2]); g->stats.ms_faces += ms;
+		cudaEventElapsedTime (&ms, g->ev[2], g->ev[3]); g->stats.ms_scan += ms;
+		cudaEventElapsedTime (&ms, g->ev[3], g->ev[4]); g->stats.ms_surfprep += ms;
+		cudaEventElapsedTime (&ms, g->ev[4], g->ev[5]); g->stats.ms_cache += ms;
+		cudaEventElapsedTime (&ms, g->ev[5], g->ev[6]); g->stats.ms_draw += ms;
+		cudaEventElapsedTime (&ms, g->ev[0], g->ev[6]); g->stats.ms_total += ms;
+	}
+}
+
+int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+		   int *status, char *err, size_t errlen)
+{
+	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	size_t px = (size_t)g->width * g->height;
+	int st = 0;
+	if (!g->haveworld) { snprintf (err, errlen, "no world loaded"); return RC_ERR_NOWORLD; }
+	cudaSetDevice (g->device);
+	memset (&g->stats, 0, sizeof(g->stats));
+	if (g->flush_pending)
+	{
+		do_flush (g, s);
+		g->stats.kernel_launches++;
+	}
+	for (int attempt = 0; attempt < 4; attempt++)
+	{
+		int r = ensure_chunk (g, n, err, errlen);
+		if (r != RC_OK) return r;
+		CK (cudaMemsetAsync (g->d_status, 0, sizeof(int), s));
+		st = 0;
+		for (int first = 0; first < n; first += g->chunkcap)
+		{
+			int cn = n - first < g->chunkcap ? n - first : g->chunkcap;
+			r = run_chunk (g, views + first, cn, (uint8_t *)fb_dev + px * first,
+				       z_dev ? (int16_t *)z_dev + px * first : NULL, s, g->profiling != 0, err, errlen);
+			if (r != RC_OK) return r;
+			if (g->profiling || n > g->chunkcap)
+			{
+				/* d_views is reused by the next chunk and the stats are read here */
+				CK (cudaStreamSynchronize (s));
+				if (g->profiling) collect_stats (g, cn, true);
+			}
+		}
+		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+		CK (cudaStreamSynchronize (s));
+		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL)))
+			break;
+		if (st & RC_STAT_SPAN_POOL)
+		{
+			/* the span / block pool heuristic was too small for this scene: grow and redo */
+			g->spans_per_line *= 2;
+			free_chunk (g);
+		}
+		/* surface-cache pool (or table) exhausted, or entries left half-built: D_FlushCaches and redo */
+		memset (&g->stats, 0, sizeof(g->stats));
+		do_flush (g, s);
+	}
+	g->launches_total += g->stats.kernel_launches;
+	g->last_n = n < g->chunkcap ? n : g->chunkcap;
+	if (status) *status = st;
+	return RC_OK;
+}
+
+int rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+			int *status, char *err, size_t errlen)
+{
+	size_t px = (size_t)g->width * g->height;
+	cudaSetDevice (g->device);
+	if (g->outcap < px * n)
+	{
+		cudaFree (g->d_fb); cudaFree (g->d_zb);
+		g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0;
+		CK (cudaMalloc (&g->d_fb, px * n));
+		CK (cudaMalloc (&g->d_zb, px * n * sizeof(int16_t)));
+		g->outcap = px * n;
+	}
+	/* every pixel of a full-screen view is written by the world spans; views that use a
+	 * sub-rectangle leave the rest as the caller's buffer had it in the reference, here 0 */
+	CK (cudaMemsetAsync (g->d_fb, 0, px * n, g->stream));
+	int r = rc_gpu_render (g, views, n, g->d_fb, g->d_zb, NULL, status, err, errlen);
+	if (r != RC_OK) return r;
+	CK (cudaMemcpyAsync (fb_out, g->d_fb, px * n, cudaMemcpyDeviceToHost, g->stream));
+	if (z_out) CK (cudaMemcpyAsync (z_out, g->d_zb, px * n * sizeof(int16_t), cudaMemcpyDeviceToHost, g->stream));
+	CK (cudaStreamSynchronize (g->stream));
+	return RC_OK;
+}
+
+void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }
+void rc_gpu_set_profiling (rc_gpu_t *g, int on) { g->profiling = on; }
+
+int rc_gpu_debug_read (rc_gpu_t *g, int kind, int view, void *dst, int cap)
+{
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	if (!g->d_views || view < 0 || view >= g->last_n) return RC_ERR_ARG;
+	if (kind == 0)
+	{
+		int n = 0;
+		cudaMemcpy (&n, g->d_nedges + view, sizeof(int), cudaMemcpyDeviceToHost);
+		if (n > g->edgecap) n = g->edgecap;
+		if (n > cap) n = cap;
+		cudaMemcpy (dst, g->d_edges + (size_t)view * g->edgecap, sizeof(rc_edge_t) * n, cudaMemcpyDeviceToHost);
+		return n;
+	}
+	if (kind == 1)
+	{
+		int n = 0;
+		cudaMemcpy (&n, g->d_nfaces + view, sizeof(int), cudaMemcpyDeviceToHost);
+		n += 2;
+		if (n > cap) n = cap;
+		cudaMemcpy (dst, g->d_surfs + (size_t)view * g->surfcap, sizeof(rc_surf_t) * n, cudaMemcpyDeviceToHost);
+		return n;
+	}
+	if (kind == 2)
+	{
+		unsigned long long a = 0;
+		cudaMemcpy (&a, g->d_alloc, sizeof(a), cudaMemcpyDeviceToHost);
+		int n = (int)(a & 0xFFFFFFFFu);
+		if (n > g->spancap) n = g->spancap;
+		if (n > cap) n = cap;
+		cudaMemcpy (dst, g->d_spans, sizeof(rc_span_t) * n, cudaMemcpyDeviceToHost);
+		return n;
+	}
+	return RC_ERR_ARG;
+}
+
+} /* extern "C" */

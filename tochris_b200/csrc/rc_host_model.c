@@ -164,6 +164,14 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 			memcpy (texels + ofs, (const unsigned char *)(mt + 1), pixels);
 			ofs += pixels;
 		}
+		w->skytexofs = -1;
+		for (i = 0; i < nummiptex; i++)
+			if (tx[i].width && !strncmp (texnames[i], "sky", 3))
+			{
+				/* R_InitSky (r_sky.c:53-61) memcpy's 256*128 bytes: every "sky*" texture overwrites skydata */
+				if (tx[i].width != 256 || tx[i].height != 128) FAIL ("sky texture %.16s is not 256x128", texnames[i]);
+				w->skytexofs = tx[i].offsets[0];
+			}
 		hw->texelbytes = total;
 		w->texels = texels;
 		w->textures = tx;

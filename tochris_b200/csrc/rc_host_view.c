@@ -138,6 +138,13 @@ int RC_SetupView (const rc_refdef_t *rd, const rc_vidinfo_t *vid, const rc_cvars
 			v->lightstylevalue[j] = (ls->map[t % ls->length] - 'a') * 22;
 		}
 	}
+	{
+		/* R_SetSkyFrame, r_sky.c:112-130: iskyspeed 8, iskyspeed2 2 -> gcd 2, s1 4, s2 1 */
+		float skyspeed = 8, temp, skytime;
+		temp = 128 * 4 * 1;
+		skytime = rd->time - ((int)(rd->time / temp) * temp);
+		v->skyshift = skytime * skyspeed;
+	}
 	v->animtime = (int)(rd->time*10);
 	v->turbphase = (int)(rd->time*RC_TURB_SPEED) & (RC_CYCLE-1);
 

@@ -18,7 +18,7 @@
 #include <math.h>
 
 #ifdef __CUDACC__
-#define RC_HD __host__ __device__ __forceinline__
+#define RC_HD __device__ __forceinline__
 #define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
@@ -899,6 +899,7 @@ RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc
 #define RC_SRC_POOL    0
 #define RC_SRC_TEXELS  1
 #define RC_SRC_SOLID   2    /* background / fast sky: constant colour, z at "infinity" */
+#define RC_SRC_SKY     3    /* scrolling two-layer sky (d_sky.c) */
 
 /* One thread per (view, surface): the per-surface part of D_DrawSurfaces (d_edge.c:161-340)
  * for surfaces that own spans: mip selection, D_CacheSurface lookup (d_surf.c:196) against
@@ -911,9 +912,13 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		return;
 	s->cacheofs = -1;
 	s->miplevel = -1;		/* reused as the cache-table slot to resolve, -1: none */
+	if ((s->flags & RC_SURF_DRAWSKY) && !vw->fastsky)
+	{
+		s->pad = RC_SRC_SKY;		/* d_edge.c:186-193; z uses the surface's own 1/z plane */
+		return;
+	}
 	if (s->flags & (RC_SURF_DRAWBACKGROUND | RC_SURF_DRAWSKY))
 	{
-		/* TODO(sky): scrolling sky; until then sky draws as r_fastsky does */
 		s->pad = RC_SRC_SOLID;
 		s->cachewidth = (s->flags & RC_SURF_DRAWBACKGROUND) ? vw->clearcolor : vw->skycolor;
 		s->d_ziorigin = -0.9; s->d_zistepu = 0; s->d_zistepv = 0;
@@ -1070,6 +1075,43 @@ RC_HD uint8_t rc_cache_texel (const rc_world_t *w, const rc_cachejob_t *job, con
 	return w->colormap[(light & 0xFF00) + pix];
 }
 
+
+/* D_Sky_uv_To_st, d_sky.c:34-52 */
+RC_HD void rc_sky_uv_to_st (const rc_view_t *vw, int u, int v, int *ps, int *pt)
+{
+	float wu = (u - vw->xcenter) / vw->xscale;
+	float wv = (vw->ycenter - v) / vw->yscale;
+	float end[3];
+	end[0] = vw->vpn[0] + wu*vw->vright[0] + wv*vw->vup[0];
+	end[1] = vw->vpn[1] + wu*vw->vright[1] + wv*vw->vup[1];
+	end[2] = vw->vpn[2] + wu*vw->vright[2] + wv*vw->vup[2];
+	end[2] *= 3;
+	float length = end[0]*end[0] + end[1]*end[1] + end[2]*end[2];
+	if (length)
+	{
+		length = sqrt ((double)length);
+		float ilength = 1/length;
+		end[0] *= ilength;
+		end[1] *= ilength;
+		end[2] *= ilength;
+	}
+	*ps = rc_f2i ((vw->skyshift + 6*(128/2-1)*end[0]) * 0x10000);
+	*pt = rc_f2i ((vw->skyshift + 6*(128/2-1)*end[1]) * 0x10000);
+}
+
+/* one texel of `newsky` as R_MakeSky composes it (r_sky.c:68-105), without materialising it */
+RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int t)
+{
+	const uint8_t *skydata = w->texels + w->skytexofs;
+	int xshift2 = rc_f2i (vw->skyshift), yshift2 = xshift2;
+	int xshift1 = xshift2 >> 1, yshift1 = yshift2 >> 1;
+	int y = (t >> 16) & 127, x = (s >> 16) & 127;
+	uint8_t b1 = skydata[((y + yshift1) & 127) * 256 + ((x + xshift1) & 127)];
+	if (b1)
+		return b1;
+	return skydata[((y + yshift2) & 127) * 256 + 128 + ((x + xshift2) & 127)];
+}
+
 /* ------------------------------------------------------------------ stage 6: draw ------ */
 /* One thread per 8-pixel block of a span: D_DrawSpans8 (d_scan.c:254-386) /
  * Turbulent8 (d_scan.c:121-251) / D_DrawSolidSurface (d_edge.c:72-90) fused with
@@ -1125,6 +1167,42 @@ RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
 	{
 		for (int j = 0; j < cnt; j++)
 			pdest[j] = (uint8_t)s->cachewidth;
+		return;
+	}
+	if (s->pad == RC_SRC_SKY)
+	{
+		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form */
+		const int b32 = first >> 5;			/* which 32-pixel run of the span */
+		const int u0 = sp.u + (b32 << 5);
+		int remaining = sp.count - (b32 << 5);		/* pixels from the start of this run */
+		int spancount = remaining >= 32 ? 32 : remaining;
+		int ss, tt, snext = 0, tnext = 0, sstep = 0, tstep = 0;
+		rc_sky_uv_to_st (vw, u0, sp.v, &ss, &tt);
+		if (remaining - spancount)
+		{
+			rc_sky_uv_to_st (vw, u0 + spancount, sp.v, &snext, &tnext);
+			sstep = (snext - ss) >> 5;
+			tstep = (tnext - tt) >> 5;
+		}
+		else
+		{
+			int spancountminus1 = spancount - 1;
+			if (spancountminus1 > 0)
+			{
+				rc_sky_uv_to_st (vw, u0 + spancountminus1, sp.v, &snext, &tnext);
+				sstep = (snext - ss) / spancountminus1;
+				tstep = (tnext - tt) / spancountminus1;
+			}
+		}
+		const int within = first & 31;
+		ss = rc_addw (ss, rc_mulw (within, sstep));
+		tt = rc_addw (tt, rc_mulw (within, tstep));
+		for (int j = 0; j < cnt; j++)
+		{
+			pdest[j] = rc_sky_texel (w, vw, ss, tt);
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
+		}
 		return;
 	}
 	const int turb = (s->flags & RC_SURF_DRAWTURB) != 0;

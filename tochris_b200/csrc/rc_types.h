@@ -101,6 +101,8 @@ typedef struct {            /* device-resident world; all pointers are device po
     int numplanes, numnodes, numleafs /* incl. leaf 0 */, numfaces, numsurfedges, numedges,
         numvertexes, numtexinfo, numtextures, nummarksurfaces, visleafs, haslight;
     int numworldfaces;      /* faces of model 0 (without skybox faces) */
+    int skytexofs;          /* texel offset of the 256x128 sky texture R_InitSky copied last (r_sky.c:53), -1: none */
+    int pad0;
     int visrowwords;        /* words per row of nodevis */
     const rc_plane_t     *planes;
     const rc_node_t      *nodes;
@@ -152,6 +154,8 @@ typedef struct {
     int   lightstylevalue[RC_MAX_LIGHTSTYLES];
     int   skycolor;                /* (int)r_skycolor.value & 0xFF */
     int   fastsky;                 /* r_fastsky.value != 0 */
+    float skyshift;                /* R_SetSkyFrame, r_sky.c:112-130 */
+    int   pad1;
 } rc_view_t;
 
 /* ---- per-view transient records ------------------------------------------------------ */

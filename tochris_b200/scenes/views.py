@@ -1,13 +1,40 @@
-"""Camera sets for the BASELINE.json configs and asset-directory writer."""
+"""Camera sets for the BASELINE.json configs, asset-directory writer and
+the picklable view description both renderers are driven from."""
 from __future__ import annotations
 
+import ctypes as C
+import math
 import os
-from typing import List, Sequence, Tuple
-
-import numpy as np
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
 
 from . import assets
-from ..refdef import refdef_t, default_lightstyles
+from ..refdef import (refdef_t, entity_t, dlight_t, particle_t, default_lightstyles)
+
+
+@dataclass
+class EntitySpec:
+    model: str
+    origin: Tuple[float, float, float]
+    angles: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    frame: int = 0
+    oldframe: int = 0
+    framelerp: float = 0.0
+    skinnum: int = 0
+    flags: int = 0
+
+
+@dataclass
+class ViewSpec:
+    origin: Tuple[float, float, float]
+    angles: Tuple[float, float, float]
+    time: float = 1.0
+    fov_x: float = 90.0
+    flags: int = 0
+    rect: Optional[Tuple[int, int, int, int]] = None     # x, y, w, h (default: full screen)
+    entities: List[EntitySpec] = field(default_factory=list)
+    dlights: List[Tuple[float, float, float, float]] = field(default_factory=list)   # x, y, z, radius
+    particles: List[Tuple[float, float, float, int]] = field(default_factory=list)   # x, y, z, colour
 
 
 def write_base_assets(basedir: str):
@@ -39,46 +66,91 @@ def halton(i: int, base: int) -> float:
     return r
 
 
-def make_refdefs(n: int, width: int, height: int, cams: Sequence[Tuple[Tuple[float, float, float], Tuple[float, float, float]]],
-                 times: Sequence[float], fov_x: float = 90.0, lightstyles=None):
-    """n refdef_t structs sharing one lightstyle table (the table must outlive the array)."""
+def calc_fov_y(fov_x: float, width: int, height: int) -> float:
+    """client/cl_screen.c CalcFov: fov_y from fov_x and the window shape."""
+    x = width / math.tan(fov_x / 360.0 * math.pi)
+    return math.atan(height / x) * 360.0 / math.pi
+
+
+def build_refdefs(specs: Sequence[ViewSpec], width: int, height: int,
+                  model_resolver: Optional[Callable[[str], int]] = None, colormap_ptr: int = 0,
+                  lightstyles=None):
+    """refdef_t[n] for `specs`.  The returned ctypes array keeps every sub-array alive."""
+    n = len(specs)
     ls = lightstyles if lightstyles is not None else default_lightstyles()
     rds = (refdef_t * n)()
-    import math
-    for i in range(n):
+    keep = [ls]
+    cache = {}
+    for i, sp in enumerate(specs):
         rd = rds[i]
-        rd.x, rd.y, rd.width, rd.height = 0, 0, width, height
-        rd.time = float(times[i]); rd.oldtime = float(times[i])
-        rd.flags = 0
-        rd.fov_x = fov_x
-        # client/cl_screen.c CalcFov: fov_y from fov_x and the window shape
-        x = width / math.tan(fov_x / 360.0 * math.pi)
-        rd.fov_y = math.atan(height / x) * 360.0 / math.pi
-        org, ang = cams[i]
+        x, y, w, h = sp.rect if sp.rect else (0, 0, width, height)
+        rd.x, rd.y, rd.width, rd.height = x, y, w, h
+        rd.time = float(sp.time)
+        rd.oldtime = float(sp.time)
+        rd.flags = sp.flags
+        rd.fov_x = sp.fov_x
+        rd.fov_y = calc_fov_y(sp.fov_x, w, h)
         for k in range(3):
-            rd.vieworg[k] = float(org[k]); rd.viewangles[k] = float(ang[k])
+            rd.vieworg[k] = float(sp.origin[k])
+            rd.viewangles[k] = float(sp.angles[k])
         rd.lightstyles = ls
-    rds._keep = ls
+        if sp.entities:
+            ents = (entity_t * len(sp.entities))()
+            for j, e in enumerate(sp.entities):
+                if e.model not in cache:
+                    cache[e.model] = model_resolver(e.model)
+                ents[j].model = cache[e.model]
+                ents[j].framelerp = e.framelerp
+                ents[j].number = j + 1
+                ents[j].flags = e.flags
+                ents[j].skinnum = e.skinnum
+                ents[j].colormap = colormap_ptr
+                for k in range(3):
+                    ents[j].origin[k] = float(e.origin[k])
+                    ents[j].angles[k] = float(e.angles[k])
+                ents[j].frame = e.frame
+                ents[j].oldframe = e.oldframe
+            rd.num_entities = len(sp.entities)
+            rd.entities = ents
+            keep.append(ents)
+        if sp.dlights:
+            dl = (dlight_t * len(sp.dlights))()
+            for j, d in enumerate(sp.dlights):
+                dl[j].origin[0], dl[j].origin[1], dl[j].origin[2], dl[j].radius = d
+            rd.num_dlights = len(sp.dlights)
+            rd.dlights = dl
+            keep.append(dl)
+        if sp.particles:
+            pt = (particle_t * len(sp.particles))()
+            for j, p in enumerate(sp.particles):
+                pt[j].org[0], pt[j].org[1], pt[j].org[2] = p[0], p[1], p[2]
+                pt[j].color = int(p[3])
+            rd.num_particles = len(sp.particles)
+            rd.particles = pt
+            keep.append(pt)
+    rds._keep = keep
     return rds
 
 
-def timerefresh_cams(origin=(0.0, 0.0, 0.0), frames: int = 128):
+def timerefresh_views(origin=(0.0, 0.0, 0.0), frames: int = 128, time: float = 1.0) -> List[ViewSpec]:
     """The reference's own benchmark path: yaw = i/128*360 (ref_soft/r_misc.c:42-58)."""
-    return [(tuple(origin), (0.0, i / 128.0 * 360.0, 0.0)) for i in range(frames)]
+    return [ViewSpec(tuple(origin), (0.0, i / 128.0 * 360.0, 0.0), time) for i in range(frames)]
 
 
-def halton_cams(info: dict, n: int, start: int = 1):
-    """Halton(2,3,5) positions inside rooms x Halton(7) yaw, pitch in [-20, 20]."""
-    spawn = info["spawn"]; room = info.get("room", 400)
-    cams = []
+def halton_views(info: dict, n: int, start: int = 1, time: float = 1.0, time_step: float = 0.0) -> List[ViewSpec]:
+    """Halton(2,3,5) positions inside rooms x Halton(7) yaw, pitch in [-20, 20];
+    view i is rendered at time + i*time_step (C4: 0.01 s apart)."""
+    spawn = info["spawn"]
+    room = info.get("room", 400)
+    out = []
     for i in range(n):
         k = start + i
-        sx, sy, sz = spawn[k % len(spawn)]
+        sx, sy, _ = spawn[k % len(spawn)]
         r = room * 0.5 - 24.0
         ox = sx + (halton(k, 2) * 2 - 1) * r
         oy = sy + (halton(k, 3) * 2 - 1) * r
         oz = 24.0 + halton(k, 5) * 80.0
         yaw = halton(k, 7) * 360.0
         pitch = (halton(k, 11) * 2 - 1) * 20.0
-        cams.append(((ox, oy, oz), (pitch, yaw, 0.0)))
-    return cams
+        out.append(ViewSpec((ox, oy, oz), (pitch, yaw, 0.0), time + i * time_step))
+    return out
