@@ -107,7 +107,14 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	f.fb = (uint8_t *)fb_dev; f.zb = (int16_t *)z_dev;
 	f.status = &st;
 
-	for (int vi = 0; vi < n; vi++) rc_walk_view (w, &f, vi);
+	std::vector<int> facemark ((size_t)n * w->numfaces, 0x7F7F7F7F), viewleaf (n, 0);
+	std::vector<rc_nodevisit_t> nodevisit ((size_t)n * w->numnodes, rc_nodevisit_t ());
+	f.facemark = facemark.data (); f.viewleaf = viewleaf.data (); f.nodevisit = nodevisit.data ();
+	for (int vi = 0; vi < n; vi++) rc_view_begin (w, &f, vi);
+	for (int vi = 0; vi < n; vi++)
+		for (int x = 0; x < w->numnodes + w->numleafs; x++) rc_visit (w, &f, vi, x);
+	for (int vi = 0; vi < n; vi++)
+		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi);
 	for (int vi = 0; vi < n; vi++)
 		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p);
 	for (int vi = 0; vi < n; vi++)

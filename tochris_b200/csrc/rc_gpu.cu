@@ -8,10 +8,12 @@
  * work bounded by HBM/L2 traffic and by latency in the per-view front end.
  *
  * One process drives one GPU.  A batch of views goes through, per chunk of views:
- *   k_walk      1 thread / view           BSP descent, PVS, frustum cull -> ordered face list
+ *   k_begin     1 thread / view           view leaf, per-view resets
+ *   k_visit     1 thread / (view, node)   root->node replay: PVS, frustum cull, sort keys
+ *   k_listfaces 1 thread / (view, face)   face list R_RenderFace is called on
  *   k_faces     1 thread / (view, face)   clip + project edges, surf_t setup
  *   k_fixup     1 thread / (view, face)   cross-face r_rightenter/r_rightexit reads
- *   k_scan      1 thread / (view, line)   active-edge table -> spans + 8-pixel block list
+ *   k_scan      1 warp   / (view, line)   active-edge table -> spans + 8-pixel block list
  *   k_surfprep  1 thread / (view, surf)   mip, gradients, surface-cache lookup -> build jobs
  *   k_resolve   1 thread / (view, surf)   cache slot -> pool offset
  *   k_cache     1 CTA    / job (strided)  lightmap + colormap'd texel block
@@ -50,6 +52,7 @@ struct rc_gpu_s {
 	int spans_per_line;		/* sizing heuristic, doubled on RC_STAT_SPAN_POOL */
 	rc_view_t *d_views;
 	rc_facerec_t *d_facelist; int *d_nfaces; uint16_t *d_facepos;
+	int *d_facemark; rc_nodevisit_t *d_nodevisit; int *d_viewleaf;
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
 	rc_span_t *d_spans; int *d_blockspan;
@@ -68,11 +71,27 @@ struct rc_gpu_s {
 };
 
 /* ------------------------------------------------------------------------ kernels ----- */
-__global__ void k_walk (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+__global__ void k_begin (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	int vi = blockIdx.x * blockDim.x + threadIdx.x;
 	if (vi < f.nviews)
-		rc_walk_view (&w, &f, vi);
+		rc_view_begin (&w, &f, vi);
+}
+
+__global__ void k_visit (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int x = blockIdx.y * blockDim.x + threadIdx.x;
+	if (x < w.numnodes + w.numleafs)
+		rc_visit (&w, &f, vi, x);
+}
+
+__global__ void k_listfaces (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	int vi = blockIdx.x;
+	int fi = blockIdx.y * blockDim.x + threadIdx.x;
+	if (fi < w.numworldfaces)
+		rc_list_face (&w, &f, vi, fi);
 }
 
 __global__ void k_faces (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -91,12 +110,118 @@ __global__ void k_fixup (const __grid_constant__ rc_world_t w, const __grid_cons
 		rc_face_fixup (&w, &f, vi, p);
 }
 
-__global__ void k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* One WARP per (view, scanline).
+ *   1. the lanes sweep the view's edge records (32 B each, coalesced), keep those with
+ *      v <= line <= v2 and append their sort keys to shared memory (ballot + popc compaction)
+ *   2. rank sort in shared memory: every lane counts, for its elements, how many keys are
+ *      smaller (keys are unique), and scatters the payload to that rank
+ *   3. lane 0 runs R_GenerateSpans over the sorted edges (inherently serial: each edge mutates
+ *      the active surface stack)
+ *   4. the lanes expand the line's spans into the 8-pixel block list the draw kernel consumes
+ * Integer work throughout; per-line state never leaves shared memory / registers. */
+#define SCAN_WARPS 4
+struct rc_aet_shared {
+	const unsigned long long *pl;	/* surfs | iu << 32 */
+	const uint32_t *uu;
+	__device__ __forceinline__ int iu (int k) const { return (int)(pl[k] >> 32); }
+	__device__ __forceinline__ uint32_t surfs (int k) const { return (uint32_t)pl[k]; }
+	__device__ __forceinline__ int u (int k) const { return (int)uu[k]; }
+};
+
+__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	int vi = blockIdx.x;
-	int line = blockIdx.y * blockDim.x + threadIdx.x;
-	if (line < f.height)
-		rc_scan_line (&w, &f, vi, line);
+	__shared__ unsigned long long s_hi[SCAN_WARPS][RC_AET_MAX], s_lo[SCAN_WARPS][RC_AET_MAX], s_pl[SCAN_WARPS][RC_AET_MAX];
+	__shared__ unsigned long long s_spl[SCAN_WARPS][RC_AET_MAX];
+	__shared__ uint32_t s_su[SCAN_WARPS][RC_AET_MAX];
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int vi = blockIdx.x;
+	const int line = blockIdx.y * SCAN_WARPS + wid;
+	if (line >= f.height)
+		return;
+	const rc_view_t *vw = &f.views[vi];
+	if (line < vw->vrect_y || line >= vw->vrectbottom)
+		return;
+	const rc_edge_t *edges = f.edges + (size_t)vi * f.edgecap;
+	rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
+	int E = f.nedges[vi];
+	if (E > f.edgecap) E = f.edgecap;
+	unsigned long long *hi = s_hi[wid], *lo = s_lo[wid], *pl = s_pl[wid];
+
+	/* 1. gather */
+	int n = 0;
+	for (int base = 0; base < E; base += 32)
+	{
+		int e = base + lane;
+		bool act = false;
+		rc_aet_t a;
+		if (e < E)
+		{
+			const rc_edge_t ed = edges[e];
+			if (ed.v <= line && ed.v2 >= line)
+			{
+				act = true;
+				rc_aet_make (&ed, line, &a);
+			}
+		}
+		unsigned m = __ballot_sync (0xFFFFFFFFu, act);
+		int pos = n + __popc (m & ((1u << lane) - 1));
+		if (act && pos < RC_AET_MAX)
+		{
+			hi[pos] = a.hi; lo[pos] = a.lo;
+			pl[pos] = (unsigned long long)a.surfs | ((unsigned long long)(uint32_t)a.iu << 32);
+		}
+		n += __popc (m);
+	}
+	if (n > RC_AET_MAX)
+	{
+		if (lane == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
+		n = RC_AET_MAX;
+	}
+	__syncwarp ();
+	/* 2. rank sort */
+	for (int i = lane; i < n; i += 32)
+	{
+		const unsigned long long h = hi[i], l = lo[i];
+		int rank = 0;
+		for (int j = 0; j < n; j++)
+		{
+			const unsigned long long hj = hi[j];
+			rank += (hj < h || (hj == h && lo[j] < l)) ? 1 : 0;
+		}
+		s_spl[wid][rank] = pl[i];
+		s_su[wid][rank] = (uint32_t)(h >> 32) ^ 0x80000000u;
+	}
+	__syncwarp ();
+	/* 3. span generation */
+	int spanbase = 0, spanroom = 0, blockbase = 0, blockroom = 0, nsp = 0, nblk = 0, ok = 0;
+	if (lane == 0)
+	{
+		ok = rc_scan_alloc (&f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom);
+		if (ok)
+		{
+			rc_aet_shared acc; acc.pl = s_spl[wid]; acc.uu = s_su[wid];
+			nsp = rc_span_walk (&f, vw, surfs, vi, line, acc, n, spanbase, spanroom, blockbase, &nblk);
+		}
+	}
+	ok = __shfl_sync (0xFFFFFFFFu, ok, 0);
+	if (!ok)
+		return;
+	spanbase = __shfl_sync (0xFFFFFFFFu, spanbase, 0); spanroom = __shfl_sync (0xFFFFFFFFu, spanroom, 0);
+	blockbase = __shfl_sync (0xFFFFFFFFu, blockbase, 0); blockroom = __shfl_sync (0xFFFFFFFFu, blockroom, 0);
+	nsp = __shfl_sync (0xFFFFFFFFu, nsp, 0); nblk = __shfl_sync (0xFFFFFFFFu, nblk, 0);
+	__syncwarp ();
+	/* 4. block list */
+	for (int i = lane; i < nsp; i += 32)
+	{
+		const int fbk = f.spans[spanbase + i].firstblock;
+		const int nb = (f.spans[spanbase + i].count + 7) >> 3;
+		for (int b = 0; b < nb; b++)
+			f.blockspan[fbk + b] = spanbase + i;
+	}
+	for (int i = nsp + lane; i < spanroom; i += 32)
+		f.spans[spanbase + i].count = 0;
+	for (int i = nblk + lane; i < blockroom; i += 32)
+		f.blockspan[blockbase + i] = -1;
 }
 
 __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -224,6 +349,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 static void free_chunk (rc_gpu_t *g)
 {
 	cudaFree (g->d_views); cudaFree (g->d_facelist); cudaFree (g->d_nfaces); cudaFree (g->d_facepos);
+	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
 	cudaFree (g->d_blockspan); cudaFree (g->d_jobs);
 	g->d_views = NULL; g->chunkcap = 0;
@@ -274,6 +400,8 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	UP (marksurfaces, h->nummarksurfaces + 1)
 	UP (nodevis, (size_t)h->visrowwords * h->numleafs)
 	UP (colormap, 256 * 64)
+	UP (nodeaux, h->numnodes + 1)
+	UP (leafdfs, h->numleafs + 1)
 #undef UP
 	g->w.sintable = g->d_sintable;
 	g->w.intsintable = g->d_intsintable;
@@ -300,7 +428,7 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 {
 	size_t lines = g->height;
 	size_t spans = lines * g->spans_per_line, blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
-	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 2 * (size_t)numfaces + sizeof(rc_edge_t) * edgecap +
+	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
 	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
@@ -334,6 +462,9 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 	CK (cudaMalloc (&g->d_facelist, sizeof(rc_facerec_t) * (size_t)want * facecap));
 	CK (cudaMalloc (&g->d_nfaces, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_facepos, sizeof(uint16_t) * (size_t)want * w->numfaces));
+	CK (cudaMalloc (&g->d_facemark, sizeof(int) * (size_t)want * w->numfaces));
+	CK (cudaMalloc (&g->d_nodevisit, sizeof(rc_nodevisit_t) * (size_t)want * w->numnodes));
+	CK (cudaMalloc (&g->d_viewleaf, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_edges, sizeof(rc_edge_t) * (size_t)want * edgecap));
 	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
@@ -353,6 +484,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	memset (&f, 0, sizeof(f));
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views;
 	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
+	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
 	f.spans = g->d_spans; f.spancap = g->spancap; f.blockspan = g->d_blockspan; f.blockcap = g->blockcap;
@@ -365,18 +497,24 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
 	CK (cudaMemsetAsync (g->d_facepos, 0xFF, sizeof(uint16_t) * (size_t)n * w.numfaces, s));
+	CK (cudaMemsetAsync (g->d_facemark, 0x7F, sizeof(int) * (size_t)n * w.numfaces, s));
+	CK (cudaMemsetAsync (g->d_nodevisit, 0, sizeof(rc_nodevisit_t) * (size_t)n * w.numnodes, s));
 	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
 	CK (cudaMemsetAsync (g->d_alloc + 2, 0, sizeof(unsigned long long), s));
 	g->stats.kernel_launches += 0;
 
-	k_walk<<<(n + 31) / 32, 32, 0, s>>> (w, f);
+	k_begin<<<(n + 63) / 64, 64, 0, s>>> (w, f);
+	dim3 gv (n, (w.numnodes + w.numleafs + 63) / 64);
+	k_visit<<<gv, 64, 0, s>>> (w, f);
+	dim3 gl (n, (w.numworldfaces + 127) / 128);
+	k_listfaces<<<gl, 128, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[1], s);
 	dim3 gf (n, (g->facecap + 63) / 64);
 	k_faces<<<gf, 64, 0, s>>> (w, f);
 	k_fixup<<<gf, 64, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[2], s);
-	dim3 gs (n, (g->height + 31) / 32);
-	k_scan<<<gs, 32, 0, s>>> (w, f);
+	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
+	k_scan<<<gs, SCAN_WARPS * 32, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
@@ -386,7 +524,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	if (timed) cudaEventRecord (g->ev[5], s);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 8;
+	g->stats.kernel_launches += 10;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }

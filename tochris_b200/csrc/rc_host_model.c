@@ -498,6 +498,49 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 		w->nodevis = nodevis;
 	}
 
+	/* nodeaux / leafdfs: static numbering of the world tree for the parallel walk */
+	{
+		rc_nodeaux_t *aux = (rc_nodeaux_t *)own (hw, sizeof(rc_nodeaux_t) * (w->numnodes + 1));
+		int *leafdfs = (int *)own (hw, sizeof(int) * (w->numleafs + 1));
+		int *stk = (int *)malloc (sizeof(int) * 2 * (w->numnodes + 2));
+		int *order = (int *)malloc (sizeof(int) * (w->numnodes + 2));
+		int *dfs_out = (int *)malloc (sizeof(int) * (w->numnodes + 2));
+		int sp = 0, counter = 0, norder = 0;
+		for (i = 0; i < w->numleafs; i++) leafdfs[i] = -1;
+		/* iterative pre-order from the world head node (model 0) */
+		stk[sp++] = hw->submodels[0].headnode;
+		while (sp)
+		{
+			int n = stk[--sp];
+			if (n < 0)
+			{
+				if (-1 - n != 0) leafdfs[-1 - n] = counter;	/* leaf 0 (solid) is shared: never numbered */
+				counter++;
+				continue;
+			}
+			aux[n].dfs_in = counter++;
+			order[norder++] = n;
+			stk[sp++] = w->nodes[n].children[1];
+			stk[sp++] = w->nodes[n].children[0];
+		}
+		/* dfs_out and slot counts bottom-up (reverse pre-order) */
+		for (i = norder - 1; i >= 0; i--)
+		{
+			int n = order[i], out = aux[n].dfs_in + 1;
+			for (j = 0; j < 2; j++)
+			{
+				int c = w->nodes[n].children[j];
+				if (c < 0) { aux[n].slots[j] = 1; out += 1; }
+				else { aux[n].slots[j] = aux[c].slots[0] + aux[c].slots[1] + w->nodes[c].numsurfaces + 1; out += dfs_out[c] - aux[c].dfs_in; }
+				if (j == 0) aux[n].dfs_mid = out;
+			}
+			dfs_out[n] = out;
+		}
+		free (stk); free (order); free (dfs_out);
+		w->nodeaux = aux;
+		w->leafdfs = leafdfs;
+	}
+
 	/* separtner: world faces sharing a medge_t */
 	{
 		rc_separtner_t *sp = (rc_separtner_t *)own (hw, sizeof(rc_separtner_t) * (w->numsurfedges + 1));

@@ -19,12 +19,15 @@
 
 #ifdef __CUDACC__
 #define RC_HD __device__ __forceinline__
+#define RC_HD2 __device__ __forceinline__
 #define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
+#define RC_ATOMIC_MIN_I(p, v)   atomicMin ((p), (v))
 #define RC_ATOMIC_CAS_ULL(p, c, v) atomicCAS ((p), (c), (v))
 #else
 #define RC_HD static inline
+#define RC_HD2 inline
 static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline int rc_host_or_i (int *p, int v) { int o = *p; *p = o | v; return o; }
@@ -32,6 +35,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_ATOMIC_ADD_I(p, v)   rc_host_add_i ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) rc_host_add_ull ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    rc_host_or_i ((p), (v))
+#define RC_ATOMIC_MIN_I(p, v)   do { if ((v) < *(p)) *(p) = (v); } while (0)
 #define RC_ATOMIC_CAS_ULL(p, c, v) rc_host_cas_ull ((p), (c), (v))
 #endif
 
@@ -39,7 +43,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_FACEPOS_MARKED  0xFFFEu   /* marked (surf->visframe == r_framecount), not rendered */
 #define RC_MAX_FACE_EDGES  30        /* per face; slot 31 is the synthetic left-clip edge */
 #define RC_WALK_STACK      512
-#define RC_AET_MAX         320       /* active edges per scanline held by the scan thread */
+#define RC_AET_MAX         256       /* active edges per scanline the scan kernel holds (shared memory) */
 #define RC_STACK_MAX       96        /* active surface stack depth held by the scan thread */
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
 
@@ -49,7 +53,10 @@ typedef struct {
     const rc_view_t *views;
     /* BSP walk */
     rc_facerec_t *facelist; int facecap; int *nfaces;
-    uint16_t *facepos;            /* [nviews][numfaces] */
+    uint16_t *facepos;            /* [nviews][numfaces]: list position of a rendered face, else RC_FACEPOS_NONE */
+    int *facemark;                /* [nviews][numfaces]: smallest key of a visited leaf that marks the face */
+    rc_nodevisit_t *nodevisit;    /* [nviews][numnodes] */
+    int *viewleaf;                /* [nviews] */
     /* face stage */
     rc_edge_t *edges; int edgecap; int *nedges;
     rc_surf_t *surfs; int surfcap; /* [nviews][surfcap]; 0 dummy, 1 background, 2+p face-list slot p */
@@ -133,32 +140,18 @@ RC_HD float rc_plane_diff (const float *p, const rc_plane_t *pl)
 	return (pl->type < 3 ? p[pl->type] : rc_dot3 (p, pl->normal)) - pl->dist;
 }
 
-/* One thread per view: Mod_PointInLeaf (r_model.c:83) + R_MarkLeaves lookup (precomputed
- * nodevis row) + R_RecursiveWorldNode (r_bsp.c:436-557) as an explicit-stack DFS.
- * Emits the ordered list of faces R_RenderFace is called on, with their clipflags. */
-RC_HD void rc_walk_view (const rc_world_t *w, const rc_frame_t *f, int vi)
+/* One thread per view: Mod_PointInLeaf (r_model.c:83-105) and the per-view resets
+ * R_BeginEdgeFrame does (r_edge.c:81-112). */
+RC_HD void rc_view_begin (const rc_world_t *w, const rc_frame_t *f, int vi)
 {
 	const rc_view_t *v = &f->views[vi];
-	rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
-	uint16_t *facepos = f->facepos + (size_t)vi * w->numfaces;
-	int nlist = 0, key = 0;
-	int stack_node[RC_WALK_STACK];
-	signed char stack_info[RC_WALK_STACK];	/* bits 0-3 clipflags, bit 4: faces pending (phase 1) */
-	int sp = 0;
-
+	rc_surf_t *bg = f->surfs + (size_t)vi * f->surfcap + 1;
+	/* surfaces[1]: the background */
+	bg->key = 0x7FFFFFFF; bg->flags = RC_SURF_DRAWBACKGROUND; bg->face = -1; bg->insubmodel = 0;
+	bg->hasspans = 0; bg->entity = -1; bg->nearzi = 0;
+	bg->d_ziorigin = 0; bg->d_zistepu = 0; bg->d_zistepv = 0;
+	f->nedges[vi] = 0;
 	f->nfaces[vi] = 0;
-	{
-		/* surfaces[1]: the background (R_BeginEdgeFrame, r_edge.c:86-106) */
-		rc_surf_t *bg = f->surfs + (size_t)vi * f->surfcap + 1;
-		bg->key = 0x7FFFFFFF; bg->flags = RC_SURF_DRAWBACKGROUND; bg->face = -1; bg->insubmodel = 0;
-		bg->hasspans = 0; bg->entity = -1; bg->nearzi = 0;
-		bg->d_ziorigin = 0; bg->d_zistepu = 0; bg->d_zistepv = 0;
-		f->nedges[vi] = 0;
-	}
-	if (v->rdflags & 1 /* RDF_NOWORLDMODEL */)
-		return;
-
-	/* Mod_PointInLeaf */
 	int n = 0;
 	while (n >= 0)
 	{
@@ -167,90 +160,100 @@ RC_HD void rc_walk_view (const rc_world_t *w, const rc_frame_t *f, int vi)
 		float d = rc_dot3 (v->origin, pl->normal) - pl->dist;
 		n = (d > 0) ? nd->children[0] : nd->children[1];
 	}
-	const uint32_t *vis = w->nodevis + (size_t)(-1 - n) * w->visrowwords;
+	f->viewleaf[vi] = -1 - n;
+}
 
-	stack_node[sp] = 0; stack_info[sp] = 15; sp++;
-	while (sp)
+/* One thread per (view, node-or-leaf x): decides whether R_RecursiveWorldNode (r_bsp.c:436-557)
+ * reaches x for this view, by replaying the root->x descent: every ancestor must be in the
+ * PVS-marked set (precomputed R_MarkLeaves row) and survive the bbox/frustum test with the
+ * clipflags it inherits.  The BSP sort key is accumulated on the way down from static subtree
+ * slot counts: front subtree first, then the node's faces, then the back subtree -- the same
+ * order in which the reference increments r_currentkey, so keys compare identically.
+ *   visited node -> f->nodevisit[x] (side, clipflags, key of its first face)
+ *   visited leaf -> atomicMin of the leaf's key into f->facemark[] for its marksurfaces
+ *                   (surf->visframe = r_framecount happens when the leaf is reached, so a face
+ *                   is drawn only if some leaf with a SMALLER key marked it). */
+RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
+{
+	const rc_view_t *v = &f->views[vi];
+	if (v->rdflags & 1 /* RDF_NOWORLDMODEL */)
+		return;
+	const int is_leaf = x >= w->numnodes;
+	const int L = x - w->numnodes;
+	int tx;
+	if (is_leaf)
 	{
-		sp--;
-		int node = stack_node[sp];
-		int info = stack_info[sp];
-		int clipflags = info & 15;
-		if (!(info & 16))
-		{
-			if (node < 0)
-			{
-				int li = -1 - node;
-				const rc_leaf_t *lf = &w->leafs[li];
-				if (lf->contents == RC_CONTENTS_SOLID)
-					continue;
-				if (!rc_visbit (vis, w->numnodes + li))
-					continue;
-				if (!rc_cull_box (v, lf->minmaxs, &clipflags))
-					continue;
-				for (int c = 0; c < lf->nummarks; c++)
-				{
-					int fi = w->marksurfaces[lf->firstmark + c];
-					if (facepos[fi] == RC_FACEPOS_NONE)
-						facepos[fi] = RC_FACEPOS_MARKED;
-				}
-				key++;		/* pleaf->key = r_currentkey++ */
-				continue;
-			}
-			const rc_node_t *nd = &w->nodes[node];
-			if (!rc_visbit (vis, node))
-				continue;
-			if (!rc_cull_box (v, nd->minmaxs, &clipflags))
-				continue;
-			float dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
-			int side = (dot < 0);
-			if (sp + 2 > RC_WALK_STACK)
-			{
-				RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
-				break;
-			}
-			stack_node[sp] = node; stack_info[sp] = (signed char)(clipflags | 16); sp++;
-			stack_node[sp] = nd->children[side]; stack_info[sp] = (signed char)clipflags; sp++;
-		}
-		else
-		{
-			const rc_node_t *nd = &w->nodes[node];
-			double dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
-			int side = (dot < 0);
-			int c = nd->numsurfaces;
-			if (c)
-			{
-				int want = -1;
-				if (dot < -RC_BACKFACE_EPSILON) want = RC_SURF_PLANEBACK;
-				else if (dot > RC_BACKFACE_EPSILON) want = 0;
-				if (want >= 0)
-				{
-					for (int s = 0; s < c; s++)
-					{
-						int fi = nd->firstsurface + s;
-						if ((w->faces[fi].flags & RC_SURF_PLANEBACK) == want && facepos[fi] != RC_FACEPOS_NONE)
-						{
-							/* R_RenderFace (surf, clipflags) */
-							if (nlist >= f->facecap || nlist >= (int)RC_FACEPOS_MARKED - 1)
-							{
-								RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
-								continue;
-							}
-							list[nlist].face = fi;
-							list[nlist].clipflags = clipflags;
-							list[nlist].key = key++;
-							list[nlist].pad = 0;
-							facepos[fi] = (uint16_t)nlist;
-							nlist++;
-						}
-					}
-				}
-				key++;		/* all surfaces on the same node share the same sequence number */
-			}
-			stack_node[sp] = nd->children[!side]; stack_info[sp] = (signed char)clipflags; sp++;
-		}
+		if (L == 0 || w->leafs[L].contents == RC_CONTENTS_SOLID)
+			return;
+		tx = w->leafdfs[L];
+		if (tx < 0)
+			return;
 	}
-	f->nfaces[vi] = nlist;
+	else
+		tx = w->nodeaux[x].dfs_in;
+	const uint32_t *vis = w->nodevis + (size_t)f->viewleaf[vi] * w->visrowwords;
+	if (!rc_visbit (vis, x))
+		return;
+	int cur = 0, clipflags = 15, key = 0;
+	for (;;)
+	{
+		const rc_node_t *nd = &w->nodes[cur];
+		if (!rc_cull_box (v, nd->minmaxs, &clipflags))
+			return;
+		double dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
+		const int side = (dot < 0);
+		const rc_nodeaux_t aux = w->nodeaux[cur];
+		if (!is_leaf && cur == x)
+		{
+			rc_nodevisit_t *nv = &f->nodevisit[(size_t)vi * w->numnodes + x];
+			nv->clipflags = (int16_t)clipflags;
+			nv->facekey = key + aux.slots[side];
+			nv->state = (int16_t)(dot > RC_BACKFACE_EPSILON ? 1 : (dot < -RC_BACKFACE_EPSILON ? 2 : 3));
+			return;
+		}
+		const int c = (tx < aux.dfs_mid) ? 0 : 1;
+		if (c != side)
+			key += aux.slots[side] + nd->numsurfaces + 1;
+		const int child = nd->children[c];
+		if (child < 0)
+		{
+			const rc_leaf_t *lf = &w->leafs[L];
+			if (!rc_cull_box (v, lf->minmaxs, &clipflags))
+				return;
+			int *facemark = f->facemark + (size_t)vi * w->numfaces;
+			for (int m = 0; m < lf->nummarks; m++)
+				RC_ATOMIC_MIN_I (&facemark[w->marksurfaces[lf->firstmark + m]], key);
+			return;
+		}
+		cur = child;
+	}
+}
+
+/* One thread per (view, world face): the face loop of R_RecursiveWorldNode (r_bsp.c:520-549):
+ * right side of its node's plane, marked by an earlier leaf -> R_RenderFace is called on it. */
+RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int fi)
+{
+	const rc_face_t *fa = &w->faces[fi];
+	if (fa->node < 0)
+		return;
+	const rc_nodevisit_t nv = f->nodevisit[(size_t)vi * w->numnodes + fa->node];
+	if (nv.state != 1 && nv.state != 2)
+		return;
+	const int want = nv.state == 2 ? RC_SURF_PLANEBACK : 0;
+	if ((fa->flags & RC_SURF_PLANEBACK) != want)
+		return;
+	const int key = nv.facekey + (fi - w->nodes[fa->node].firstsurface);
+	if (!(f->facemark[(size_t)vi * w->numfaces + fi] < key))
+		return;
+	int p = RC_ATOMIC_ADD_I (&f->nfaces[vi], 1);
+	if (p >= f->facecap || p >= (int)RC_FACEPOS_MARKED - 1)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
+		return;
+	}
+	rc_facerec_t *rec = f->facelist + (size_t)vi * f->facecap + p;
+	rec->face = fi; rec->clipflags = nv.clipflags; rec->key = key; rec->pad = 0;
+	f->facepos[(size_t)vi * w->numfaces + fi] = (uint16_t)p;
 }
 
 /* ------------------------------------------------------------- stage 2: face -> edges -- */
@@ -444,7 +447,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 		if (sp.partner_face >= 0)
 			q = facepos[sp.partner_face];
 
-		if (q < (int)RC_FACEPOS_MARKED && q < p)
+		if (q < (int)RC_FACEPOS_MARKED && list[q].key < rec.key)
 		{
 			/* the partner face ran first: redo its R_ClipEdge to learn what it left in
 			 * medge_t.cachededgeoffset (r_rast.c:583-603) */
@@ -484,9 +487,9 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
 			e->surfs[0] = r.trailing ? surfidx : 0;
 			e->surfs[1] = r.trailing ? 0 : surfidx;
-			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)p << 5) | (uint32_t)i;
+			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)rec.key << 5) | (uint32_t)i;
 			e->pad[0] = e->pad[1] = e->pad[2] = 0;
-			if (r.cls == RC_CLS_CACHED && q < (int)RC_FACEPOS_MARKED && q > p)
+			if (r.cls == RC_CLS_CACHED && q < (int)RC_FACEPOS_MARKED && list[q].key > rec.key)
 			{
 				/* the partner will find this edge cached and add itself (R_EmitCachedEdge) */
 				if (r.trailing) e->surfs[1] = (uint16_t)(q + 2);
@@ -517,7 +520,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
 			e->surfs[0] = r.trailing ? surfidx : 0;
 			e->surfs[1] = r.trailing ? 0 : surfidx;
-			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)p << 5) | 31u;
+			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)rec.key << 5) | 31u;
 			e->pad[0] = e->pad[1] = e->pad[2] = 0;
 		}
 	}
@@ -587,13 +590,23 @@ RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int 
 	int have_re = surf->miplevel & 1, have_rx = (surf->miplevel >> 1) & 1;
 	re[0] = surf->d_sdivzstepu; re[1] = surf->d_tdivzstepu; re[2] = surf->d_sdivzstepv;
 	rx[0] = surf->d_tdivzstepv; rx[1] = surf->d_sdivzorigin; rx[2] = surf->d_tdivzorigin;
-	for (int q = p - 1; q >= 0 && !(have_re && have_rx); q--)
 	{
-		const rc_surf_t *o = &surfs[q + 2];
-		if (!have_re && (o->miplevel & 1))
-		{ have_re = 1; re[0] = o->d_sdivzstepu; re[1] = o->d_tdivzstepu; re[2] = o->d_sdivzstepv; }
-		if (!have_rx && (o->miplevel & 2))
-		{ have_rx = 1; rx[0] = o->d_tdivzstepv; rx[1] = o->d_sdivzorigin; rx[2] = o->d_tdivzorigin; }
+		/* the face list is unordered: take, per value, the writer with the largest key below ours */
+		const int mykey = list[p].key, nf = f->nfaces[vi] < f->facecap ? f->nfaces[vi] : f->facecap;
+		int best_re = -1, best_rx = -1, kre = -1, krx = -1;
+		for (int q = 0; q < nf; q++)
+		{
+			const int k = list[q].key;
+			if (k >= mykey)
+				continue;
+			const int m = surfs[q + 2].miplevel;
+			if (!have_re && (m & 1) && k > kre) { kre = k; best_re = q; }
+			if (!have_rx && (m & 2) && k > krx) { krx = k; best_rx = q; }
+		}
+		if (best_re >= 0)
+		{ const rc_surf_t *o = &surfs[best_re + 2]; have_re = 1; re[0] = o->d_sdivzstepu; re[1] = o->d_tdivzstepu; re[2] = o->d_sdivzstepv; }
+		if (best_rx >= 0)
+		{ const rc_surf_t *o = &surfs[best_rx + 2]; have_rx = 1; rx[0] = o->d_tdivzstepv; rx[1] = o->d_sdivzorigin; rx[2] = o->d_tdivzorigin; }
 	}
 	if (!have_re || !have_rx)
 	{
@@ -611,13 +624,47 @@ RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int 
 
 /* ------------------------------------------------------------------ stage 3: scan ------ */
 typedef struct { unsigned long long hi, lo; uint32_t surfs; int iu; } rc_aet_t;
-RC_HD int aet_u_of (const rc_aet_t a) { return (int)((uint32_t)(a.hi >> 32) ^ 0x80000000u); }
 
 typedef struct {
 	int surf, key, state, last_u, insub;
 } rc_stk_t;
 
-/* Emits one span for surface `s` (r_edge.c:268-276,349-357,398-406,505-513) */
+/* Sort key of one active edge on scanline `line` (DESIGN.md "AET order"): the order the
+ * reference's linked list has when R_GenerateSpans walks it, in closed form.
+ *   hi = u (12.20, biased) : then for edges already active on line-1, ~u_step (the edge that was
+ *        further left on the previous line, i.e. the larger step, stays in front:
+ *        R_StepActiveU is a stable insertion sort, r_edge.c:188-249); new edges (c = 0) precede
+ *        old ones with the same u (R_InsertNewEdges inserts before, r_edge.c:127-163)
+ *   lo = later start line first, then newedges[] order: leaders newest-emitted first, trailers
+ *        after leaders and oldest first (u_check = u+1 for trailers, r_rast.c:355-379). */
+RC_HD void rc_aet_make (const rc_edge_t *ed, int line, rc_aet_t *a)
+{
+	int isold = line > ed->v;
+	int u = rc_addw (ed->u, rc_mulw (line - ed->v, ed->u_step));
+	uint32_t c = 0;
+	if (isold)
+	{
+		c = ~((uint32_t)ed->u_step ^ 0x80000000u);
+		if (c == 0) c = 1;
+	}
+	uint32_t em = ed->rank & 0x7FFFFFFFu;
+	uint32_t trailing = ed->rank >> 31;
+	uint32_t fl = trailing ? em : (~em & 0x7FFFFFFFu);
+	a->hi = ((unsigned long long)((uint32_t)u ^ 0x80000000u) << 32) | c;
+	a->lo = ((unsigned long long)(uint16_t)(~ed->v) << 32) | ((unsigned long long)trailing << 31) | fl;
+	a->surfs = (uint32_t)ed->surfs[0] | ((uint32_t)ed->surfs[1] << 16);
+	a->iu = u >> 20;
+}
+
+/* accessors so the span walk can run over an array of rc_aet_t (serial scan, host sim) or over
+ * the split shared-memory arrays of the warp-cooperative kernel */
+struct rc_aet_array {
+	const rc_aet_t *a;
+	RC_HD2 int iu (int k) const { return a[k].iu; }
+	RC_HD2 uint32_t surfs (int k) const { return a[k].surfs; }
+	RC_HD2 int u (int k) const { return (int)((uint32_t)(a[k].hi >> 32) ^ 0x80000000u); }
+};
+
 #define RC_EMIT_SPAN(sidx, ustart, uend)                                                      \
 	do {                                                                                  \
 		if (nsp < spanroom) {                                                         \
@@ -626,79 +673,22 @@ typedef struct {
 			_s->view = vi; _s->surf = (uint16_t)(sidx); _s->v = (int16_t)line;    \
 			_s->u = (int16_t)(ustart); _s->count = (int16_t)_c;                   \
 			_s->firstblock = blockbase + nblk;                                    \
-			for (int _b = 0; _b < ((_c + 7) >> 3) && nblk < blockroom; _b++)      \
-				f->blockspan[blockbase + nblk++] = spanbase + nsp;            \
+			nblk += (_c + 7) >> 3;                                                \
 			nsp++;                                                                \
 			surfs[sidx].hasspans = 1;                                             \
 		}                                                                             \
 	} while (0)
 
-/* One thread per (view, scanline).  Rebuilds the active edge table the reference has on
- * that line -- membership from v..v2, u = u0 + (line-v)*u_step (R_StepActiveU adds
- * u_step once per line, r_edge.c:195), order from the closed-form comparator derived in
- * DESIGN.md from R_InsertNewEdges / R_StepActiveU / R_EmitEdge's newedges[] insertion
- *  -- then runs R_GenerateSpans (r_edge.c:536-563) over it. */
-RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int line)
+/* R_GenerateSpans (r_edge.c:536-563) with R_TrailingEdge (:370-407), R_LeadingEdge (:411-527)
+ * and R_CleanupSpan (:256-285) over the sorted active edges of one scanline.  The active
+ * surface stack is a small array ordered top..background instead of a linked list through
+ * surf_t; spanstate lives in the stack entry (a surface is in the stack iff spanstate >= 1).
+ * Returns spans written; *pnblk = 8-pixel blocks they cover. */
+template <class AET>
+RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *surfs, int vi, int line,
+			const AET aet, int n, int spanbase, int spanroom, int blockbase, int *pnblk)
 {
-	const rc_view_t *vw = &f->views[vi];
-	if (line < vw->vrect_y || line >= vw->vrectbottom)
-		return;
-	const rc_edge_t *edges = f->edges + (size_t)vi * f->edgecap;
-	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
-	int E = f->nedges[vi];
-	if (E > f->edgecap) E = f->edgecap;
-	rc_aet_t aet[RC_AET_MAX];
-	int n = 0;
-
-	for (int e = 0; e < E; e++)
-	{
-		const rc_edge_t ed = edges[e];
-		if (ed.v > line || ed.v2 < line)
-			continue;
-		if (n >= RC_AET_MAX)
-		{
-			RC_ATOMIC_OR_I (f->status, RC_STAT_AET_OVERFLOW);
-			break;
-		}
-		int isold = line > ed.v;
-		int u = rc_addw (ed.u, rc_mulw (line - ed.v, ed.u_step));
-		uint32_t c = 0;
-		if (isold)
-		{
-			c = ~((uint32_t)ed.u_step ^ 0x80000000u);	/* larger step first */
-			if (c == 0) c = 1;
-		}
-		uint32_t em = ed.rank & 0x7FFFFFFFu;
-		uint32_t trailing = ed.rank >> 31;
-		uint32_t fl = trailing ? em : (~em & 0x7FFFFFFFu);	/* leaders newest first, trailers oldest first */
-		rc_aet_t a;
-		a.hi = ((unsigned long long)((uint32_t)u ^ 0x80000000u) << 32) | c;
-		a.lo = ((unsigned long long)(uint16_t)(~ed.v) << 32) | ((unsigned long long)trailing << 31) | fl;
-		a.surfs = (uint32_t)ed.surfs[0] | ((uint32_t)ed.surfs[1] << 16);
-		a.iu = u >> 20;
-		/* insertion sort */
-		int j = n++;
-		while (j > 0 && (aet[j-1].hi > a.hi || (aet[j-1].hi == a.hi && aet[j-1].lo > a.lo)))
-		{
-			aet[j] = aet[j-1];
-			j--;
-		}
-		aet[j] = a;
-	}
-
-	/* output room: at most n+1 spans, (w+7)/8 + n+1 blocks; one allocation per line */
-	int spanroom = n + 1;
-	int blockroom = ((vw->vrect_w + 7) >> 3) + n + 1;
-	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)spanroom | ((unsigned long long)blockroom << 32));
-	int spanbase = (int)(old & 0xFFFFFFFFu), blockbase = (int)(old >> 32);
-	if (spanbase + spanroom > f->spancap || blockbase + blockroom > f->blockcap)
-	{
-		RC_ATOMIC_OR_I (f->status, RC_STAT_SPAN_POOL);
-		return;
-	}
 	int nsp = 0, nblk = 0;
-
-	/* R_GenerateSpans */
 	rc_stk_t stk[RC_STACK_MAX];
 	int depth = 1;
 	int nneg = 0;
@@ -710,11 +700,12 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 
 	for (int k = 0; k < n; k++)
 	{
-		const int iu = aet[k].iu;
-		const int s0 = aet[k].surfs & 0xFFFF, s1 = aet[k].surfs >> 16;
+		const int iu = aet.iu (k);
+		const uint32_t ss = aet.surfs (k);
+		const int s0 = ss & 0xFFFF, s1 = ss >> 16;
 		if (s0)
 		{
-			/* R_TrailingEdge, r_edge.c:370-407 */
+			/* R_TrailingEdge */
 			int pos = -1;
 			for (int i = 0; i < depth; i++)
 				if (stk[i].surf == s0) { pos = i; break; }
@@ -752,13 +743,13 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 		}
 		if (s1)
 		{
-			/* R_LeadingEdge, r_edge.c:411-527 */
+			/* R_LeadingEdge */
 			int pos = -1, ni = -1, state;
 			for (int i = 0; i < depth; i++)
 				if (stk[i].surf == s1) { pos = i; break; }
 			if (pos >= 0)
 			{
-				stk[pos].state++;	/* already in a span (state >= 1 -> >= 2): nothing else */
+				stk[pos].state++;	/* already in a span: ++spanstate != 1 */
 				continue;
 			}
 			for (int i = 0; i < nneg; i++)
@@ -783,7 +774,7 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 			{
 				/* two bmodels in the same leaf: sort on 1/z (r_edge.c:436-458) */
 				const rc_surf_t *s2 = &surfs[stk[0].surf];
-				double fu = (float)(aet_u_of (aet[k]) - 0xFFFFF) * (1.0 / 0x100000);
+				double fu = (float)(aet.u (k) - 0xFFFFF) * (1.0 / 0x100000);
 				double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
 				double newzibottom = newzi * 0.99;
 				double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
@@ -813,7 +804,7 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 						if (!sinsub)
 							continue;
 						const rc_surf_t *s2 = &surfs[stk[at].surf];
-						double fu = (float)(aet_u_of (aet[k]) - 0xFFFFF) * (1.0 / 0x100000);
+						double fu = (float)(aet.u (k) - 0xFFFFF) * (1.0 / 0x100000);
 						double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
 						double newzibottom = newzi * 0.99;
 						double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
@@ -839,12 +830,74 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 			stk[at].last_u = newtop ? iu : 0;
 		}
 	}
-	/* R_CleanupSpan, r_edge.c:256-285 */
+	/* R_CleanupSpan */
 	if (edge_tail_u > stk[0].last_u)
 		RC_EMIT_SPAN (stk[0].surf, stk[0].last_u, edge_tail_u);
 	if (nneg)
 		RC_ATOMIC_OR_I (f->status, RC_STAT_STACK_OVERFLOW);	/* spanstate would leak into the next line */
+	*pnblk = nblk;
+	return nsp;
+}
 
+/* room reserved per scanline: at most n+1 spans, (w+7)/8 + n+1 blocks; one allocation per line */
+RC_HD int rc_scan_alloc (const rc_frame_t *f, const rc_view_t *vw, int n, int *spanbase, int *spanroom, int *blockbase, int *blockroom)
+{
+	*spanroom = n + 1;
+	*blockroom = ((vw->vrect_w + 7) >> 3) + n + 1;
+	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)*spanroom | ((unsigned long long)*blockroom << 32));
+	*spanbase = (int)(old & 0xFFFFFFFFu);
+	*blockbase = (int)(old >> 32);
+	if (*spanbase + *spanroom > f->spancap || *blockbase + *blockroom > f->blockcap)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_SPAN_POOL);
+		return 0;
+	}
+	return 1;
+}
+
+/* One thread per (view, scanline), fully serial: the reference implementation of the scan
+ * stage (host simulation; the GPU runs the warp-cooperative k_scan built from the same parts). */
+RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int line)
+{
+	const rc_view_t *vw = &f->views[vi];
+	if (line < vw->vrect_y || line >= vw->vrectbottom)
+		return;
+	const rc_edge_t *edges = f->edges + (size_t)vi * f->edgecap;
+	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
+	int E = f->nedges[vi];
+	if (E > f->edgecap) E = f->edgecap;
+	rc_aet_t aet[RC_AET_MAX];
+	int n = 0;
+	for (int e = 0; e < E; e++)
+	{
+		if (edges[e].v > line || edges[e].v2 < line)
+			continue;
+		if (n >= RC_AET_MAX)
+		{
+			RC_ATOMIC_OR_I (f->status, RC_STAT_AET_OVERFLOW);
+			break;
+		}
+		rc_aet_t a;
+		rc_aet_make (&edges[e], line, &a);
+		int j = n++;
+		while (j > 0 && (aet[j-1].hi > a.hi || (aet[j-1].hi == a.hi && aet[j-1].lo > a.lo)))
+		{
+			aet[j] = aet[j-1];
+			j--;
+		}
+		aet[j] = a;
+	}
+	int spanbase, spanroom, blockbase, blockroom, nblk = 0;
+	if (!rc_scan_alloc (f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom))
+		return;
+	rc_aet_array acc; acc.a = aet;
+	int nsp = rc_span_walk (f, vw, surfs, vi, line, acc, n, spanbase, spanroom, blockbase, &nblk);
+	for (int i = 0; i < nsp; i++)
+	{
+		const rc_span_t *sp = &f->spans[spanbase + i];
+		for (int b = 0; b < ((sp->count + 7) >> 3); b++)
+			f->blockspan[sp->firstblock + b] = spanbase + i;
+	}
 	for (int i = nsp; i < spanroom; i++)
 		f->spans[spanbase + i].count = 0;
 	for (int i = nblk; i < blockroom; i++)

@@ -91,6 +91,20 @@ typedef struct {            /* texture_t, r_model.h:63-72; offsets index the sha
     int pad;
 } rc_texture_t;             /* 48 B */
 
+/* static per-node data for the parallel BSP walk: a pre-order interval that tells which child
+ * holds a given node/leaf, and the number of sort-key slots in each child's subtree */
+typedef struct {
+    int dfs_in, dfs_mid;    /* pre-order number; numbers < dfs_mid lie under children[0], the rest under children[1] */
+    int slots[2];           /* key slots under children[0] / children[1] */
+} rc_nodeaux_t;             /* 16 B */
+
+/* per-view result of visiting a node (r_bsp.c:436-557), consumed by the face-list kernel */
+typedef struct {
+    int16_t  state;         /* 0: not visited, 1: view in front (dot > eps), 2: behind (dot < -eps), 3: on plane */
+    int16_t  clipflags;
+    int      facekey;       /* sort key of the node's first face */
+} rc_nodevisit_t;           /* 8 B */
+
 /* one entry per surfedge: who else uses the same medge_t (r_rast.c:583-603 edge cache) */
 typedef struct {
     int partner_face;       /* -1: medge used by this face only */
@@ -121,6 +135,8 @@ typedef struct {            /* device-resident world; all pointers are device po
     const uint8_t        *colormap;    /* vid.colormap, 64*256 */
     const int            *sintable;    /* r_rast.c:45, SIN_BUFFER_SIZE ints */
     const int            *intsintable;
+    const rc_nodeaux_t   *nodeaux;     /* [numnodes] */
+    const int            *leafdfs;     /* [numleafs] pre-order number of each leaf (-1: not in the world tree) */
 } rc_world_t;
 
 /* ---- per-view constants (host computed; replaces the globals written by R_SetupFrame,
