@@ -97,6 +97,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	g->spans.assign (f.spancap, rc_span_t ());
 	std::vector<int> blockspan (f.blockcap, -1);
 	f.spans = g->spans.data (); f.blockspan = blockspan.data ();
+	std::vector<float> chk ((size_t)f.blockcap * 4, 0.f);
+	std::vector<int> spanaux ((size_t)f.spancap * 2, 0);
+	f.chk = chk.data (); f.spanaux = spanaux.data ();
 	g->alloc[0] = 0; g->alloc[2] = 0;
 	f.alloc = g->alloc;
 	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;
@@ -142,6 +145,11 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	}
 	int nblocks = (int)(g->alloc[0] >> 32);
 	if (nblocks > f.blockcap) nblocks = f.blockcap;
+	{
+		int ns = (int)(g->alloc[0] & 0xFFFFFFFFu);
+		if (ns > f.spancap) ns = f.spancap;
+		for (int t = 0; t < ns; t++) rc_span_prep (w, &f, t);
+	}
 	for (int t = 0; t < nblocks; t++) rc_draw_block (w, &f, t);
 
 	g->nspans = (int)(g->alloc[0] & 0xFFFFFFFFu);

@@ -13,7 +13,9 @@
  *   k_listfaces 1 thread / (view, face)   face list R_RenderFace is called on
  *   k_faces     1 thread / (view, face)   clip + project edges, surf_t setup
  *   k_fixup     1 thread / (view, face)   cross-face r_rightenter/r_rightexit reads
- *   k_scan      1 warp   / (view, line)   active-edge table -> spans + 8-pixel block list
+ *   k_scan_sort 1 warp   / (view, line)   active edges of the line, sorted -> HBM
+ *   k_scan_walk 1 thread / (view, line)   R_GenerateSpans over the sorted list -> spans
+ *   k_scan_blocks 1 warp / (view, line)   spans -> 8-pixel block list
  *   k_surfprep  1 thread / (view, surf)   mip, gradients, surface-cache lookup -> build jobs
  *   k_resolve   1 thread / (view, surf)   cache slot -> pool offset
  *   k_cache     1 CTA    / job (strided)  lightmap + colormap'd texel block
@@ -31,6 +33,8 @@
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
+
+struct rc_lineinfo { int spanbase, blockbase, n, nsp; };
 
 struct rc_gpu_s {
 	int device, width, height, numsms;
@@ -56,6 +60,8 @@ struct rc_gpu_s {
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
 	rc_span_t *d_spans; int *d_blockspan;
+	rc_lineinfo *d_lineinfo; uint2 *d_aetpool; int walk_lanes;
+	float *d_chk; int *d_spanaux;
 	rc_cachejob_t *d_jobs;
 	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
 	int *d_status;
@@ -110,44 +116,50 @@ __global__ void k_fixup (const __grid_constant__ rc_world_t w, const __grid_cons
 		rc_face_fixup (&w, &f, vi, p);
 }
 
-/* One WARP per (view, scanline).
- *   1. the lanes sweep the view's edge records (32 B each, coalesced), keep those with
- *      v <= line <= v2 and append their sort keys to shared memory (ballot + popc compaction)
- *   2. rank sort in shared memory: every lane counts, for its elements, how many keys are
- *      smaller (keys are unique), and scatters the payload to that rank
- *   3. lane 0 runs R_GenerateSpans over the sorted edges (inherently serial: each edge mutates
- *      the active surface stack)
- *   4. the lanes expand the line's spans into the 8-pixel block list the draw kernel consumes
- * Integer work throughout; per-line state never leaves shared memory / registers. */
-#define SCAN_WARPS 4
-struct rc_aet_shared {
-	const unsigned long long *pl;	/* surfs | iu << 32 */
-	const uint32_t *uu;
-	__device__ __forceinline__ int iu (int k) const { return (int)(pl[k] >> 32); }
-	__device__ __forceinline__ uint32_t surfs (int k) const { return (uint32_t)pl[k]; }
-	__device__ __forceinline__ int u (int k) const { return (int)uu[k]; }
+/* Scan stage, three kernels (R_ScanEdges and friends):
+ *  k_scan_sort   one WARP per (view, scanline): the lanes sweep the view's edge records
+ *                (32 B each, coalesced), keep those with v <= line <= v2 (ballot + popc
+ *                compaction into shared memory), rank-sort their keys (keys are unique: each
+ *                lane counts the smaller keys of its elements) and write the line's sorted
+ *                active-edge list (u, surfs) to HBM.  Also reserves the line's span/block room.
+ *  k_scan_walk   one THREAD per (view, scanline): R_GenerateSpans over the sorted list.  The
+ *                walk is inherently serial per line (every edge mutates the surface stack), so
+ *                the parallelism is 32 scanlines per warp.
+ *  k_scan_blocks one WARP per (view, scanline): expands the line's spans into the 8-pixel
+ *                block list the draw kernel consumes.
+ * Integer work throughout. */
+#define SCAN_WARPS 8
+
+struct rc_aet_global {
+	const uint2 *e;		/* x = u (12.20), y = surfs[0] | surfs[1] << 16 */
+	__device__ __forceinline__ int iu (int k) const { return (int)e[k].x >> 20; }
+	__device__ __forceinline__ uint32_t surfs (int k) const { return e[k].y; }
+	__device__ __forceinline__ int u (int k) const { return (int)e[k].x; }
 };
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_sort (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f,
+								  rc_lineinfo *lineinfo, uint2 *aetpool)
 {
-	__shared__ unsigned long long s_hi[SCAN_WARPS][RC_AET_MAX], s_lo[SCAN_WARPS][RC_AET_MAX], s_pl[SCAN_WARPS][RC_AET_MAX];
-	__shared__ unsigned long long s_spl[SCAN_WARPS][RC_AET_MAX];
-	__shared__ uint32_t s_su[SCAN_WARPS][RC_AET_MAX];
+	__shared__ unsigned long long s_hi[SCAN_WARPS][RC_AET_MAX], s_lo[SCAN_WARPS][RC_AET_MAX];
+	__shared__ uint32_t s_sf[SCAN_WARPS][RC_AET_MAX];
 	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int vi = blockIdx.x;
 	const int line = blockIdx.y * SCAN_WARPS + wid;
 	if (line >= f.height)
 		return;
+	rc_lineinfo *li = &lineinfo[(size_t)vi * f.height + line];
 	const rc_view_t *vw = &f.views[vi];
 	if (line < vw->vrect_y || line >= vw->vrectbottom)
+	{
+		if (lane == 0) li->n = -1;
 		return;
+	}
 	const rc_edge_t *edges = f.edges + (size_t)vi * f.edgecap;
-	rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
 	int E = f.nedges[vi];
 	if (E > f.edgecap) E = f.edgecap;
-	unsigned long long *hi = s_hi[wid], *lo = s_lo[wid], *pl = s_pl[wid];
+	unsigned long long *hi = s_hi[wid], *lo = s_lo[wid];
+	uint32_t *sf = s_sf[wid];
 
-	/* 1. gather */
 	int n = 0;
 	for (int base = 0; base < E; base += 32)
 	{
@@ -156,9 +168,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		rc_aet_t a;
 		if (e < E)
 		{
-			const rc_edge_t ed = edges[e];
-			if (ed.v <= line && ed.v2 >= line)
+			const int4 q = *reinterpret_cast<const int4 *>(&edges[e]);	/* u, u_step, v|v2, surfs */
+			const int v = (int16_t)(q.z & 0xFFFF), v2 = (int16_t)(q.z >> 16);
+			if (v <= line && v2 >= line)
 			{
+				rc_edge_t ed;
+				ed.u = q.x; ed.u_step = q.y; ed.v = (int16_t)v; ed.v2 = (int16_t)v2;
+				ed.surfs[0] = (uint16_t)(q.w & 0xFFFF); ed.surfs[1] = (uint16_t)((unsigned)q.w >> 16);
+				ed.rank = edges[e].rank;
 				act = true;
 				rc_aet_make (&ed, line, &a);
 			}
@@ -167,8 +184,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		int pos = n + __popc (m & ((1u << lane) - 1));
 		if (act && pos < RC_AET_MAX)
 		{
-			hi[pos] = a.hi; lo[pos] = a.lo;
-			pl[pos] = (unsigned long long)a.surfs | ((unsigned long long)(uint32_t)a.iu << 32);
+			hi[pos] = a.hi; lo[pos] = a.lo; sf[pos] = a.surfs;
 		}
 		n += __popc (m);
 	}
@@ -177,8 +193,18 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		if (lane == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
 		n = RC_AET_MAX;
 	}
+	int spanbase = 0, spanroom = 0, blockbase = 0, blockroom = 0, ok = 0;
+	if (lane == 0)
+	{
+		ok = rc_scan_alloc (&f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom);
+		li->spanbase = spanbase; li->blockbase = blockbase; li->n = ok ? n : -1; li->nsp = 0;
+	}
+	ok = __shfl_sync (0xFFFFFFFFu, ok, 0);
+	if (!ok)
+		return;
+	spanbase = __shfl_sync (0xFFFFFFFFu, spanbase, 0);
 	__syncwarp ();
-	/* 2. rank sort */
+	uint2 *out = aetpool + spanbase;		/* the line's span room (n+1 slots) doubles as its AET list */
 	for (int i = lane; i < n; i += 32)
 	{
 		const unsigned long long h = hi[i], l = lo[i];
@@ -188,40 +214,61 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			const unsigned long long hj = hi[j];
 			rank += (hj < h || (hj == h && lo[j] < l)) ? 1 : 0;
 		}
-		s_spl[wid][rank] = pl[i];
-		s_su[wid][rank] = (uint32_t)(h >> 32) ^ 0x80000000u;
+		out[rank] = make_uint2 ((uint32_t)(h >> 32) ^ 0x80000000u, sf[i]);
 	}
-	__syncwarp ();
-	/* 3. span generation */
-	int spanbase = 0, spanroom = 0, blockbase = 0, blockroom = 0, nsp = 0, nblk = 0, ok = 0;
-	if (lane == 0)
-	{
-		ok = rc_scan_alloc (&f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom);
-		if (ok)
-		{
-			rc_aet_shared acc; acc.pl = s_spl[wid]; acc.uu = s_su[wid];
-			nsp = rc_span_walk (&f, vw, surfs, vi, line, acc, n, spanbase, spanroom, blockbase, &nblk);
-		}
-	}
-	ok = __shfl_sync (0xFFFFFFFFu, ok, 0);
-	if (!ok)
+}
+
+__global__ void k_scan_walk (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f,
+			     rc_lineinfo *lineinfo, const uint2 *aetpool, int lanes_per_warp)
+{
+	const int lane = threadIdx.x & 31;
+	if (lane >= lanes_per_warp)
 		return;
-	spanbase = __shfl_sync (0xFFFFFFFFu, spanbase, 0); spanroom = __shfl_sync (0xFFFFFFFFu, spanroom, 0);
-	blockbase = __shfl_sync (0xFFFFFFFFu, blockbase, 0); blockroom = __shfl_sync (0xFFFFFFFFu, blockroom, 0);
-	nsp = __shfl_sync (0xFFFFFFFFu, nsp, 0); nblk = __shfl_sync (0xFFFFFFFFu, nblk, 0);
-	__syncwarp ();
-	/* 4. block list */
-	for (int i = lane; i < nsp; i += 32)
+	const int vi = blockIdx.x;
+	const int line = (blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
+	if (line >= f.height)
+		return;
+	rc_lineinfo *li = &lineinfo[(size_t)vi * f.height + line];
+	const int n = li->n;
+	if (n < 0)
+		return;
+	const rc_view_t *vw = &f.views[vi];
+	rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
+	const int spanbase = li->spanbase, blockbase = li->blockbase;
+	rc_aet_global acc; acc.e = aetpool + spanbase;
+	int nblk = 0;
+	li->nsp = rc_span_walk (&f, vw, surfs, vi, line, acc, n, spanbase, n + 1, blockbase, &nblk);
+}
+
+__global__ void k_scan_blocks (const __grid_constant__ rc_frame_t f, const rc_lineinfo *lineinfo)
+{
+	const int lane = threadIdx.x & 31;
+	const int vi = blockIdx.x;
+	const int line = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (line >= f.height)
+		return;
+	const rc_lineinfo li = lineinfo[(size_t)vi * f.height + line];
+	if (li.n < 0)
+		return;
+	const rc_view_t *vw = &f.views[vi];
+	const int spanroom = li.n + 1, blockroom = ((vw->vrect_w + 7) >> 3) + li.n + 1;
+	int nblk = 0;
+	for (int i = lane; i < li.nsp; i += 32)
 	{
-		const int fbk = f.spans[spanbase + i].firstblock;
-		const int nb = (f.spans[spanbase + i].count + 7) >> 3;
+		const rc_span_t sp = f.spans[li.spanbase + i];
+		const int nb = (sp.count + 7) >> 3;
 		for (int b = 0; b < nb; b++)
-			f.blockspan[fbk + b] = spanbase + i;
+			f.blockspan[sp.firstblock + b] = li.spanbase + i;
+		if (i == li.nsp - 1)
+			nblk = sp.firstblock + nb - li.blockbase;
 	}
-	for (int i = nsp + lane; i < spanroom; i += 32)
-		f.spans[spanbase + i].count = 0;
+	/* the lane that owned the last span knows how many blocks are in use */
+	for (int o = 16; o; o >>= 1)
+		nblk = max (nblk, __shfl_xor_sync (0xFFFFFFFFu, nblk, o));
+	for (int i = li.nsp + lane; i < spanroom; i += 32)
+		f.spans[li.spanbase + i].count = 0;
 	for (int i = nblk + lane; i < blockroom; i += 32)
-		f.blockspan[blockbase + i] = -1;
+		f.blockspan[li.blockbase + i] = -1;
 }
 
 __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -240,31 +287,96 @@ __global__ void k_resolve (const __grid_constant__ rc_frame_t f)
 		rc_surf_resolve (&f, vi, si);
 }
 
-/* One CTA per surface-cache job, strided over the job list the prep kernel produced.
- * blocklights (<= 17x17 luxels) are built once in shared memory, then every thread shades
- * texels: 1 B source texel in, 1 B colormap'd texel out. */
-__global__ void k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* Surface-cache build: R_BuildLightmap + R_DrawSurfaceBlock8_mip0..3 (r_light.c:372,
+ * r_surf.c:187-375).  Persistent CTAs stride over the job list the prep kernel produced.
+ *   - vid.colormap (16 KB) is staged in shared memory once per CTA
+ *   - per job, blocklights (<= 17x17 luxels) are built in shared memory
+ *   - each thread then shades one row segment of one light block (16>>mip texels): one
+ *     vector load of source texels, light stepped right->left with the reference's wrapping
+ *     32-bit adds, one vector store.  1 B in, 1 B out per texel. */
+__global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	__shared__ __align__(16) uint8_t s_cmap[256 * 64];
 	__shared__ unsigned bl[18 * 18];
-	unsigned long long nj = f.alloc[2];
-	int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
+	const unsigned long long nj = f.alloc[2];
+	const int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
+	if ((int)blockIdx.x >= njobs)
+		return;
+	for (int i = threadIdx.x; i < 256 * 64 / 16; i += blockDim.x)
+		reinterpret_cast<uint4 *>(s_cmap)[i] = reinterpret_cast<const uint4 *>(w.colormap)[i];
 	for (int j = blockIdx.x; j < njobs; j += gridDim.x)
 	{
 		const rc_cachejob_t job = f.jobs[j];
 		const rc_face_t *fa = &w.faces[job.face];
-		int size = ((fa->extents[0] >> 4) + 1) * ((fa->extents[1] >> 4) + 1);
+		const rc_texture_t *mt = &w.textures[job.texture];
+		const int lw = (fa->extents[0] >> 4) + 1;
+		const int size = lw * ((fa->extents[1] >> 4) + 1);
 		__syncthreads ();
 		for (int i = threadIdx.x; i < size; i += blockDim.x)
 			bl[i] = rc_cache_luxel (&w, &job, i);
 		__syncthreads ();
-		int total = job.width * job.height;
+		const int mip = job.mip, shift = 4 - mip, bs = 16 >> mip;
+		const int nu = job.width >> shift;		/* light blocks per row */
+		const int nseg = nu * job.height;
+		const int tw = mt->width >> mip, th = mt->height >> mip;
+		const int soffset = ((fa->texturemins[0] >> mip) + (tw << 16)) % tw;
+		const int toffset = ((fa->texturemins[1] >> mip) + (th << 16)) % th;
+		const uint8_t *src = w.texels + mt->offsets[mip];
 		uint8_t *dst = f.cachepool + job.dstofs;
-		for (int t = threadIdx.x; t < total; t += blockDim.x)
+		for (int seg = threadIdx.x; seg < nseg; seg += blockDim.x)
 		{
-			int y = t / job.width, x = t - y * job.width;
-			dst[t] = rc_cache_texel (&w, &job, bl, x, y);
+			const int y = seg / nu, u = seg - y * nu;
+			const int vb = y >> shift, i = y & (bs - 1);
+			const unsigned l00 = bl[vb * lw + u], l01 = bl[vb * lw + u + 1];
+			const unsigned l10 = bl[(vb + 1) * lw + u], l11 = bl[(vb + 1) * lw + u + 1];
+			const int lightleftstep = (int)((l10 - l00) >> shift);
+			const int lightrightstep = (int)((l11 - l01) >> shift);
+			const unsigned lightleft = l00 + (unsigned)i * (unsigned)lightleftstep;
+			const unsigned lightright = l01 + (unsigned)i * (unsigned)lightrightstep;
+			const int lightstep = (int)(lightleft - lightright) >> shift;
+			const int sx = (soffset + u * bs) % tw;
+			const int sy = (toffset + y) % th;
+			const uint8_t *ps = src + sy * tw + sx;
+			uint8_t *pd = dst + y * job.width + u * bs;
+			unsigned light = lightright;		/* column b = bs-1 first */
+			if (mip == 0 && ((((size_t)ps) | ((size_t)pd)) & 15) == 0)
+			{
+				const uint4 sv = *reinterpret_cast<const uint4 *>(ps);
+				const unsigned in[4] = { sv.x, sv.y, sv.z, sv.w };
+				unsigned out[4];
+				#pragma unroll
+				for (int q = 3; q >= 0; q--)
+				{
+					unsigned o = 0;
+					#pragma unroll
+					for (int b = 3; b >= 0; b--)
+					{
+						o |= (unsigned)s_cmap[(light & 0xFF00) + ((in[q] >> (8 * b)) & 0xFF)] << (8 * b);
+						light += (unsigned)lightstep;
+					}
+					out[q] = o;
+				}
+				*reinterpret_cast<uint4 *>(pd) = make_uint4 (out[0], out[1], out[2], out[3]);
+			}
+			else
+			{
+				for (int b = bs - 1; b >= 0; b--)
+				{
+					pd[b] = s_cmap[(light & 0xFF00) + ps[b]];
+					light += (unsigned)lightstep;
+				}
+			}
 		}
 	}
+}
+
+__global__ void k_spanprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	unsigned long long a = f.alloc[0];
+	int nspans = (int)(a & 0xFFFFFFFFu);
+	if (nspans > f.spancap) nspans = f.spancap;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nspans; t += gridDim.x * blockDim.x)
+		rc_span_prep (&w, &f, t);
 }
 
 __global__ void k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -314,6 +426,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->device = device; g->width = width; g->height = height;
 	g->haveworld = false; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0;
+	g->walk_lanes = getenv ("RC_WALK_LANES") ? atoi (getenv ("RC_WALK_LANES")) : 4;
+	if (g->walk_lanes < 1 || g->walk_lanes > 32) g->walk_lanes = 32;
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties (&prop, device);
 	g->numsms = prop.multiProcessorCount;
@@ -351,7 +465,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_views); cudaFree (g->d_facelist); cudaFree (g->d_nfaces); cudaFree (g->d_facepos);
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_blockspan); cudaFree (g->d_jobs);
+	cudaFree (g->d_blockspan); cudaFree (g->d_jobs); cudaFree (g->d_lineinfo); cudaFree (g->d_aetpool); cudaFree (g->d_chk); cudaFree (g->d_spanaux);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -429,7 +543,7 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 	size_t lines = g->height;
 	size_t spans = lines * g->spans_per_line, blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
 	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
-	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
+	       sizeof(rc_surf_t) * surfcap + (sizeof(rc_span_t) + 16) * spans + 16 * lines + 16 * blocks + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
 static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
@@ -470,6 +584,10 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
 	CK (cudaMalloc (&g->d_spans, sizeof(rc_span_t) * (size_t)g->spancap));
 	CK (cudaMalloc (&g->d_blockspan, sizeof(int) * (size_t)g->blockcap));
+	CK (cudaMalloc (&g->d_lineinfo, sizeof(rc_lineinfo) * lines));
+	CK (cudaMalloc (&g->d_aetpool, sizeof(uint2) * (size_t)g->spancap));
+	CK (cudaMalloc (&g->d_chk, sizeof(float) * 4 * (size_t)g->blockcap));
+	CK (cudaMalloc (&g->d_spanaux, sizeof(int) * 2 * (size_t)g->spancap));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
 	g->chunkcap = want;
 	return RC_OK;
@@ -488,6 +606,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
 	f.spans = g->d_spans; f.spancap = g->spancap; f.blockspan = g->d_blockspan; f.blockcap = g->blockcap;
+	f.chk = g->d_chk; f.spanaux = g->d_spanaux;
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
@@ -514,7 +633,13 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	k_fixup<<<gf, 64, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
-	k_scan<<<gs, SCAN_WARPS * 32, 0, s>>> (w, f);
+	k_scan_sort<<<gs, SCAN_WARPS * 32, 0, s>>> (w, f, g->d_lineinfo, g->d_aetpool);
+	{
+		const int lpw = g->walk_lanes, wpb = 2;		/* lines per warp, warps per CTA */
+		dim3 gw (n, (g->height + lpw * wpb - 1) / (lpw * wpb));
+		k_scan_walk<<<gw, wpb * 32, 0, s>>> (w, f, g->d_lineinfo, g->d_aetpool, lpw);
+	}
+	k_scan_blocks<<<gs, SCAN_WARPS * 32, 0, s>>> (f, g->d_lineinfo);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
@@ -522,9 +647,10 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	if (timed) cudaEventRecord (g->ev[4], s);
 	k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[5], s);
+	k_spanprep<<<g->numsms * 8, 128, 0, s>>> (w, f);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 10;
+	g->stats.kernel_launches += 13;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }

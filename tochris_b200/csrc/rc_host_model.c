@@ -139,7 +139,7 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 			if (dataofs[i] < 0 || (size_t)dataofs[i] + sizeof(miptex_t) > (size_t)l->filelen) FAIL ("miptex %d out of lump", i);
 			mt = (const miptex_t *)(base + l->fileofs + dataofs[i]);
 			if ((mt->width & 15) || (mt->height & 15)) FAIL ("Texture %.16s is not 16 aligned", mt->name);
-			total += (size_t)mt->width * mt->height / 64 * 85;
+			total += ((size_t)mt->width * mt->height / 64 * 85 + 15) & ~(size_t)15;	/* 16-byte aligned for vector loads */
 		}
 		texels = (uint8_t *)own (hw, total + 16);
 		for (i = 0; i < nummiptex; i++)
@@ -162,7 +162,7 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 				tx[i].offsets[j] = (int)(ofs + mt->offsets[j] - sizeof(miptex_t));
 			}
 			memcpy (texels + ofs, (const unsigned char *)(mt + 1), pixels);
-			ofs += pixels;
+			ofs += (pixels + 15) & ~(size_t)15;
 		}
 		w->skytexofs = -1;
 		for (i = 0; i < nummiptex; i++)

@@ -20,6 +20,7 @@
 #ifdef __CUDACC__
 #define RC_HD __device__ __forceinline__
 #define RC_HD2 __device__ __forceinline__
+#define RC_LDG(p) __ldg (p)
 #define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
@@ -28,6 +29,7 @@
 #else
 #define RC_HD static inline
 #define RC_HD2 inline
+#define RC_LDG(p) (*(p))
 static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline int rc_host_or_i (int *p, int v) { int o = *p; *p = o | v; return o; }
@@ -64,6 +66,8 @@ typedef struct {
     /* scan */
     rc_span_t *spans; int spancap;
     int *blockspan; int blockcap;
+    float *chk;                   /* [blockcap][4]: s/z, t/z, 1/z checkpoints every 4th subdivision of a span */
+    int *spanaux;                 /* [spancap][2]: izi at span start, izistep */
     unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 blocks used  [1]: cache pool cursor  [2]: jobs */
     /* surface cache */
     unsigned long long *cachekeys; int *cachevals; int cachemask;
@@ -77,10 +81,9 @@ typedef struct {
 /* ------------------------------------------------------------------ scalar helpers ---- */
 RC_HD int rc_f2i (float x)
 {
-	/* cvttss2si: truncation, "integer indefinite" when out of range or NaN */
-	if (x >= 2147483648.0f || x < -2147483648.0f || x != x)
-		return (int)0x80000000;
-	return (int)x;
+	/* cvttss2si: truncation, "integer indefinite" (0x80000000) when out of range or NaN;
+	 * |x| < 2^31 is false for NaN, and x == -2^31 maps to INT_MIN either way */
+	return (fabsf (x) < 2147483648.0f) ? (int)x : (int)0x80000000;
 }
 RC_HD int rc_d2i (double x)
 {
@@ -839,7 +842,7 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *sur
 	return nsp;
 }
 
-/* room reserved per scanline: at most n+1 spans, (w+7)/8 + n+1 blocks; one allocation per line */
+/* room reserved per scanline: at most n+1 spans, (w+15)/16 + n+1 16-pixel chunks; one allocation per line */
 RC_HD int rc_scan_alloc (const rc_frame_t *f, const rc_view_t *vw, int n, int *spanbase, int *spanroom, int *blockbase, int *blockroom)
 {
 	*spanroom = n + 1;
@@ -965,6 +968,8 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		return;
 	s->cacheofs = -1;
 	s->miplevel = -1;		/* reused as the cache-table slot to resolve, -1: none */
+	s->drawflags = s->flags;
+	s->d_zistepu_draw = s->d_zistepu;
 	if ((s->flags & RC_SURF_DRAWSKY) && !vw->fastsky)
 	{
 		s->pad = RC_SRC_SKY;		/* d_edge.c:186-193; z uses the surface's own 1/z plane */
@@ -975,6 +980,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		s->pad = RC_SRC_SOLID;
 		s->cachewidth = (s->flags & RC_SURF_DRAWBACKGROUND) ? vw->clearcolor : vw->skycolor;
 		s->d_ziorigin = -0.9; s->d_zistepu = 0; s->d_zistepv = 0;
+		s->d_zistepu_draw = 0;
 		return;
 	}
 	const rc_face_t *fa = &w->faces[s->face];
@@ -1166,63 +1172,173 @@ RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int
 }
 
 /* ------------------------------------------------------------------ stage 6: draw ------ */
-/* One thread per 8-pixel block of a span: D_DrawSpans8 (d_scan.c:254-386) /
- * Turbulent8 (d_scan.c:121-251) / D_DrawSolidSurface (d_edge.c:72-90) fused with
- * D_DrawZSpans (d_scan.c:388-439).  The s/z, t/z, 1/z accumulators are advanced block by
- * block exactly as the reference does (k rounded float adds for block k). */
-RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
+/* One thread per span, before drawing: the per-span part of D_DrawSpans8 / D_DrawZSpans.
+ *   spanaux[si] = { izi at the span start, izistep }                    (d_scan.c:399-413)
+ *   chk[firstblock + 4j] = (s/z, t/z, 1/z) after 4j subdivision steps    (d_scan.c:278-315)
+ * The float accumulators of D_DrawSpans8 are sequentially rounded sums, so subdivision k needs
+ * k adds; checkpoints every 4 subdivisions bound the replay in the draw kernel to 3 steps. */
+RC_HD void rc_span_prep (const rc_world_t *w, const rc_frame_t *f, int si)
 {
-	const int si = f->blockspan[t];
-	if (si < 0)
-		return;
 	const rc_span_t sp = f->spans[si];
-	const int k = t - sp.firstblock;
+	if (sp.count <= 0)
+		return;
 	const rc_view_t *vw = &f->views[sp.view];
 	const rc_surf_t *s = f->surfs + (size_t)sp.view * f->surfcap + sp.surf;
+	const float du = (float)sp.u, dv = (float)sp.v;
+	const float zistepu = s->d_zistepu, zistepv = s->d_zistepv, ziorigin = s->d_ziorigin;
+	const int izistep = rc_f2i (zistepu * 0x8000 * 0x10000);
+	const double zid = ziorigin + dv*zistepv + du*zistepu;
+	f->spanaux[2 * si + 0] = rc_d2i (zid * 0x8000 * 0x10000);
+	f->spanaux[2 * si + 1] = izistep;
+	if (s->pad != RC_SRC_POOL && s->pad != RC_SRC_TEXELS)
+		return;
+	const float sdivz8stepu = s->d_sdivzstepu * 8, tdivz8stepu = s->d_tdivzstepu * 8, zi8stepu = zistepu * 8;
+	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*s->d_sdivzstepu;
+	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*s->d_tdivzstepu;
+	float zi = ziorigin + dv*zistepv + du*zistepu;
+	const int nblocks = (sp.count + 7) >> 3;
+	float *chk = f->chk + 4 * (size_t)sp.firstblock;
+	for (int j = 0; j < nblocks; j += 4)
+	{
+		chk[4 * j + 0] = sdivz; chk[4 * j + 1] = tdivz; chk[4 * j + 2] = zi; chk[4 * j + 3] = 0;
+		for (int q = 0; q < 4; q++)
+		{
+			sdivz += sdivz8stepu;
+			tdivz += tdivz8stepu;
+			zi += zi8stepu;
+		}
+	}
+}
+
+/* stores `cnt` (1..8) bytes held little-endian in (lo, hi) at p, using the widest aligned
+ * stores the address allows: fewer, fuller L1/L2 sector writes than 8 byte stores */
+RC_HD void rc_store_bytes8 (uint8_t *p, uint32_t lo, uint32_t hi, int cnt)
+{
+	unsigned long long v = (unsigned long long)lo | ((unsigned long long)hi << 32);
+	int head = (int)((4 - ((size_t)p & 3)) & 3);
+	if (head > cnt) head = cnt;
+	for (int i = 0; i < head; i++) { p[i] = (uint8_t)v; v >>= 8; }
+	p += head; cnt -= head;
+	if (cnt >= 4) { *(uint32_t *)p = (uint32_t)v; v >>= 32; p += 4; cnt -= 4; }
+	if (cnt >= 4) { *(uint32_t *)p = (uint32_t)v; v >>= 32; p += 4; cnt -= 4; }
+	for (int i = 0; i < cnt; i++) { p[i] = (uint8_t)v; v >>= 8; }
+}
+
+/* the 48 bytes of rc_surf_t the draw kernel needs, fetched with three 16-byte loads */
+typedef struct {
+	int   cacheofs, cachewidth, srckind, flags;
+	float sdivzstepu, tdivzstepu, zistepu, pad1;
+	int   sadjust, tadjust, bbextents, bbextentt;
+} rc_drawsurf_t;
+
+#ifdef __CUDACC__
+RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
+{
+	const uint4 *q = reinterpret_cast<const uint4 *>(&s->cacheofs);
+	const uint4 a = __ldg (q), b = __ldg (q + 1), c = __ldg (q + 2);
+	rc_drawsurf_t d;
+	d.cacheofs = (int)a.x; d.cachewidth = (int)a.y; d.srckind = (int)a.z; d.flags = (int)a.w;
+	d.sdivzstepu = __uint_as_float (b.x); d.tdivzstepu = __uint_as_float (b.y); d.zistepu = __uint_as_float (b.z); d.pad1 = 0;
+	d.sadjust = (int)c.x; d.tadjust = (int)c.y; d.bbextents = (int)c.z; d.bbextentt = (int)c.w;
+	return d;
+}
+RC_HD rc_span_t rc_load_span (const rc_span_t *p)
+{
+	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p));
+	rc_span_t s;
+	s.view = (int)a.x; s.surf = (uint16_t)(a.y & 0xFFFF); s.v = (int16_t)(a.y >> 16);
+	s.u = (int16_t)(a.z & 0xFFFF); s.count = (int16_t)(a.z >> 16); s.firstblock = (int)a.w;
+	return s;
+}
+RC_HD uint32_t rc_zpair (int a, int b) { return __byte_perm ((uint32_t)a, (uint32_t)b, 0x7632); }
+#else
+RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
+{
+	rc_drawsurf_t d;
+	d.cacheofs = s->cacheofs; d.cachewidth = s->cachewidth; d.srckind = s->pad; d.flags = s->drawflags;
+	d.sdivzstepu = s->d_sdivzstepu; d.tdivzstepu = s->d_tdivzstepu; d.zistepu = s->d_zistepu_draw; d.pad1 = 0;
+	d.sadjust = s->sadjust; d.tadjust = s->tadjust; d.bbextents = s->bbextents; d.bbextentt = s->bbextentt;
+	return d;
+}
+RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
+RC_HD uint32_t rc_zpair (int a, int b) { return (((uint32_t)a >> 16) & 0xFFFFu) | ((uint32_t)b & 0xFFFF0000u); }
+#endif
+
+/* One thread per 8-pixel subdivision of a span: D_DrawSpans8 (d_scan.c:254-386) /
+ * Turbulent8 (d_scan.c:121-251) / D_DrawSkyScans8 (d_sky.c:58) / D_DrawSolidSurface
+ * (d_edge.c:72-90) fused with D_DrawZSpans (d_scan.c:388-439).  Span, surface and checkpoint
+ * records come in as 16-byte loads; the eight texel gathers are issued together, results are
+ * packed in registers and written with aligned word stores. */
+RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
+{
+	const int si = RC_LDG (&f->blockspan[t]);
+	if (si < 0)
+		return;
+	const rc_span_t sp = rc_load_span (&f->spans[si]);
+	const int k = t - sp.firstblock;
+	const rc_view_t *vw = &f->views[sp.view];
+	const rc_drawsurf_t ds = rc_load_drawsurf (f->surfs + (size_t)sp.view * f->surfcap + sp.surf);
 	const int first = k << 3;
-	int cnt = sp.count - first;
-	const int last = cnt <= 8;
-	if (cnt > 8) cnt = 8;
+	const int total = sp.count - first;		/* pixels from this subdivision to the end of the span */
+	const int cnt = total > 8 ? 8 : total;
 	const size_t viewpix = (size_t)f->width * f->height;
 	uint8_t *pdest = f->fb + viewpix * sp.view + (size_t)vw->screenwidth * sp.v + sp.u + first;
-
-	const float du = (float)sp.u, dv = (float)sp.v;
+	const int srckind = ds.srckind;
 
 	/* ---- z (D_DrawZSpans) ---- */
 	if (f->zb)
 	{
-		int izistep = rc_f2i (s->d_zistepu * 0x8000 * 0x10000);
-		double zi = s->d_ziorigin + dv*s->d_zistepv + du*s->d_zistepu;
-		int izi0 = rc_d2i (zi * 0x8000 * 0x10000);
-		size_t zindex = (size_t)vw->zwidth * sp.v + sp.u;
-		int16_t *pz = f->zb + viewpix * sp.view + zindex;
+		const int izi0 = RC_LDG (&f->spanaux[2 * si]), izistep = RC_LDG (&f->spanaux[2 * si + 1]);
+		const size_t zindex = (size_t)vw->zwidth * sp.v + sp.u;
+		int16_t *pz = f->zb + viewpix * sp.view + zindex + first;
 		const int a0 = (int)(zindex & 1);
-		const int doublecount = (sp.count - a0) >> 1;
-		for (int j = first; j < first + cnt; j++)
+		const int izif = rc_addw (izi0, rc_mulw (first, izistep));
+		const int prev0 = rc_addw (izif, -izistep), izil = rc_addw (izif, rc_mulw (7, izistep));
+		if (cnt == 8 && (prev0 | izif | izil) >= 0)
 		{
-			int izi = rc_addw (izi0, rc_mulw (j, izistep));
-			unsigned zval = (unsigned)(izi >> 16) & 0xFFFFu;
-			int rel = j - a0;
-			if (rel >= 0 && (rel & 1) && (rel >> 1) < doublecount)
+			/* no negative 1/z in reach: plain (izi >> 16) for every pixel, two per word */
+			int z0 = izif, z1 = rc_addw (z0, izistep), z2 = rc_addw (z1, izistep), z3 = rc_addw (z2, izistep);
+			int z4 = rc_addw (z3, izistep), z5 = rc_addw (z4, izistep), z6 = rc_addw (z5, izistep), z7 = rc_addw (z6, izistep);
+			if (((size_t)pz & 3) == 0)
 			{
+				uint32_t *pw = (uint32_t *)pz;
+				pw[0] = rc_zpair (z0, z1); pw[1] = rc_zpair (z2, z3); pw[2] = rc_zpair (z4, z5); pw[3] = rc_zpair (z6, z7);
+			}
+			else
+			{
+				uint32_t *pw = (uint32_t *)(pz + 1);
+				pz[0] = (int16_t)(z0 >> 16);
+				pw[0] = rc_zpair (z1, z2); pw[1] = rc_zpair (z3, z4); pw[2] = rc_zpair (z5, z6);
+				pz[7] = (int16_t)(z7 >> 16);
+			}
+		}
+		else
+		{
+			const int doublecount = (sp.count - a0) >> 1;
+			int izi = izif, prev = prev0;
+			for (int j = 0; j < cnt; j++)
+			{
+				uint32_t zval = (uint32_t)(izi >> 16) & 0xFFFFu;
+				const int rel = first + j - a0;
 				/* second short of a 32-bit store: the first one's sign extension is OR-ed in
 				 * (d_scan.c:421-427: ltemp = izi >> 16 on a signed izi) */
-				int prev = rc_addw (izi0, rc_mulw (j - 1, izistep));
-				if (prev < 0)
+				if (prev < 0 && rel >= 0 && (rel & 1) && (rel >> 1) < doublecount)
 					zval = 0xFFFFu;
+				pz[j] = (int16_t)zval;
+				prev = izi;
+				izi = rc_addw (izi, izistep);
 			}
-			pz[j] = (int16_t)zval;
 		}
 	}
 
 	/* ---- colour ---- */
-	if (s->pad == RC_SRC_SOLID)
+	if (srckind == RC_SRC_SOLID)
 	{
-		for (int j = 0; j < cnt; j++)
-			pdest[j] = (uint8_t)s->cachewidth;
+		const uint32_t c = (uint32_t)(ds.cachewidth & 0xFF) * 0x01010101u;
+		rc_store_bytes8 (pdest, c, c, cnt);
 		return;
 	}
-	if (s->pad == RC_SRC_SKY)
+	if (srckind == RC_SRC_SKY)
 	{
 		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form */
 		const int b32 = first >> 5;			/* which 32-pixel run of the span */
@@ -1258,62 +1374,75 @@ RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
 		}
 		return;
 	}
-	const int turb = (s->flags & RC_SURF_DRAWTURB) != 0;
-	const uint8_t *pbase = (s->pad == RC_SRC_TEXELS ? w->texels : f->cachepool) + s->cacheofs;
-	const int cachewidth = s->cachewidth;
-	const float sdivz8stepu = s->d_sdivzstepu * 8, tdivz8stepu = s->d_tdivzstepu * 8, zi8stepu = s->d_zistepu * 8;
-	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*s->d_sdivzstepu;
-	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*s->d_tdivzstepu;
-	float zi = s->d_ziorigin + dv*s->d_zistepv + du*s->d_zistepu;
-	for (int j = 0; j < k; j++)
+	const int turb = (ds.flags & RC_SURF_DRAWTURB) != 0;
+	const uint8_t *pbase = (srckind == RC_SRC_TEXELS ? w->texels : f->cachepool) + ds.cacheofs;
+	const int cachewidth = ds.cachewidth;
+	const float sdivz8stepu = ds.sdivzstepu * 8, tdivz8stepu = ds.tdivzstepu * 8, zi8stepu = ds.zistepu * 8;
+	const float *chk = f->chk + 4 * (size_t)(sp.firstblock + (k & ~3));
+	float sdivz = RC_LDG (&chk[0]), tdivz = RC_LDG (&chk[1]), zi = RC_LDG (&chk[2]);
+	for (int j = 0; j < (k & 3); j++)
 	{
 		sdivz += sdivz8stepu;
 		tdivz += tdivz8stepu;
 		zi += zi8stepu;
 	}
 	float z = (float)0x10000 / zi;
-	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
-	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
-	const int lo = k ? 8 : 0;	/* block 0 starts from the span start clamp, later blocks from a `snext` clamp */
-	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
-	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
+	int ss = rc_addw (rc_f2i (sdivz * z), ds.sadjust);
+	int tt = rc_addw (rc_f2i (tdivz * z), ds.tadjust);
+	const int lo = k ? 8 : 0;	/* subdivision 0 starts from the span-start clamp, later ones from a `snext` clamp */
+	if (ss > ds.bbextents) ss = ds.bbextents; else if (ss < lo) ss = lo;
+	if (tt > ds.bbextentt) tt = ds.bbextentt; else if (tt < lo) tt = lo;
 
 	int snext, tnext, sstep = 0, tstep = 0;
-	if (!last)
+	if (total > 8)
 	{
 		sdivz += sdivz8stepu;
 		tdivz += tdivz8stepu;
 		zi += zi8stepu;
-		z = (float)0x10000 / zi;
-		snext = rc_addw (rc_f2i (sdivz * z), s->sadjust);
-		if (snext > s->bbextents) snext = s->bbextents; else if (snext < 8) snext = 8;
-		tnext = rc_addw (rc_f2i (tdivz * z), s->tadjust);
-		if (tnext > s->bbextentt) tnext = s->bbextentt; else if (tnext < 8) tnext = 8;
-		sstep = (snext - ss) >> 3;
-		tstep = (tnext - tt) >> 3;
 	}
 	else
 	{
 		float spancountminus1 = (float)(cnt - 1);
-		sdivz += s->d_sdivzstepu * spancountminus1;
-		tdivz += s->d_tdivzstepu * spancountminus1;
-		zi += s->d_zistepu * spancountminus1;
-		z = (float)0x10000 / zi;
-		snext = rc_addw (rc_f2i (sdivz * z), s->sadjust);
-		if (snext > s->bbextents) snext = s->bbextents; else if (snext < 8) snext = 8;
-		tnext = rc_addw (rc_f2i (tdivz * z), s->tadjust);
-		if (tnext > s->bbextentt) tnext = s->bbextentt; else if (tnext < 8) tnext = 8;
-		if (cnt > 1)
-		{
-			sstep = (snext - ss) / (cnt - 1);
-			tstep = (tnext - tt) / (cnt - 1);
-		}
+		sdivz += ds.sdivzstepu * spancountminus1;
+		tdivz += ds.tdivzstepu * spancountminus1;
+		zi += ds.zistepu * spancountminus1;
 	}
-	if (!turb)
+	z = (float)0x10000 / zi;
+	snext = rc_addw (rc_f2i (sdivz * z), ds.sadjust);
+	if (snext > ds.bbextents) snext = ds.bbextents; else if (snext < 8) snext = 8;
+	tnext = rc_addw (rc_f2i (tdivz * z), ds.tadjust);
+	if (tnext > ds.bbextentt) tnext = ds.bbextentt; else if (tnext < 8) tnext = 8;
+	if (total > 8)
+	{
+		sstep = (snext - ss) >> 3;
+		tstep = (tnext - tt) >> 3;
+	}
+	else if (cnt > 1)
+	{
+		sstep = (snext - ss) / (cnt - 1);
+		tstep = (tnext - tt) / (cnt - 1);
+	}
+	uint32_t plo = 0, phi = 0;
+	if (!turb && cnt == 8)
+	{
+		/* the common case, fully unrolled: 8 independent gathers, then one packed store */
+		uint32_t px[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+		{
+			px[j] = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
+		}
+		plo = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+		phi = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+	}
+	else if (!turb)
 	{
 		for (int j = 0; j < cnt; j++)
 		{
-			pdest[j] = pbase[(ss >> 16) + (tt >> 16) * cachewidth];
+			const uint32_t px = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
+			if (j < 4) plo |= px << (8 * j); else phi |= px << (8 * (j - 4));
 			ss = rc_addw (ss, sstep);
 			tt = rc_addw (tt, tstep);
 		}
@@ -1325,13 +1454,15 @@ RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
 		tt &= ((RC_CYCLE << 16) - 1);
 		for (int j = 0; j < cnt; j++)
 		{
-			int sturb = ((ss + turbtab[(tt >> 16) & (RC_CYCLE - 1)]) >> 16) & 63;
-			int tturb = ((tt + turbtab[(ss >> 16) & (RC_CYCLE - 1)]) >> 16) & 63;
-			pdest[j] = pbase[(tturb << 6) + sturb];
+			const int sturb = ((ss + RC_LDG (&turbtab[(tt >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
+			const int tturb = ((tt + RC_LDG (&turbtab[(ss >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
+			const uint32_t px = RC_LDG (&pbase[(tturb << 6) + sturb]);
+			if (j < 4) plo |= px << (8 * j); else phi |= px << (8 * (j - 4));
 			ss = rc_addw (ss, sstep);
 			tt = rc_addw (tt, tstep);
 		}
 	}
+	rc_store_bytes8 (pdest, plo, phi, cnt);
 }
 
 #endif /* RC_PIPELINE_H */

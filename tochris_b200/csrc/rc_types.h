@@ -193,23 +193,29 @@ typedef struct {
     int      pad[3];
 } rc_edge_t;
 
-typedef struct {            /* surf_t replacement (r_shared.h:125-147) + drawing state */
+typedef struct {            /* surf_t replacement (r_shared.h:125-147) + drawing state; 128 B */
+    /* -- scan / prep fields (first 64 B) -- */
     int   key;
     int   flags;
     int   face;             /* world face index, -1 for the background */
     int   insubmodel;
     float nearzi;
     float d_ziorigin, d_zistepu, d_zistepv;
-    /* filled by the surface-prep kernel for surfaces that own spans (d_edge.c:96-135,307) */
-    int   miplevel;
-    int   cacheofs;         /* byte offset of the texel block (cache pool or texel blob) */
-    int   cachewidth;
+    int   miplevel;         /* scratch: cache-table slot to resolve / right-clip flags of the face stage */
     int   hasspans;
-    float d_sdivzstepu, d_tdivzstepu, d_sdivzstepv, d_tdivzstepv, d_sdivzorigin, d_tdivzorigin;
-    int   sadjust, tadjust, bbextents, bbextentt;
     int   entity;
-    int   pad;
-} rc_surf_t;                /* 96 B */
+    int   pad0;
+    float d_sdivzstepv, d_tdivzstepv, d_sdivzorigin, d_tdivzorigin;
+    /* -- draw fields: three 16-byte groups the draw kernel fetches with vector loads,
+     *    filled by the surface-prep kernel (d_edge.c:96-135,307) -- */
+    int   cacheofs;         /* byte offset of the texel block (cache pool or texel blob) */
+    int   cachewidth;       /* row pitch of the block; constant colour for RC_SRC_SOLID */
+    int   pad;              /* texel source, RC_SRC_* */
+    int   drawflags;        /* copy of flags */
+    float d_sdivzstepu, d_tdivzstepu, d_zistepu_draw, pad1;
+    int   sadjust, tadjust, bbextents, bbextentt;
+    int   pad2[4];
+} rc_surf_t;                /* 128 B */
 
 typedef struct {            /* espan_t replacement (r_shared.h:117-121), 16 B */
     int      view;
