@@ -69,16 +69,18 @@ void rc_gpu_flush_caches (rc_gpu_t *g)
 	g->alloc[1] = 0;
 }
 
-int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
 		   int *status, char *err, size_t errlen)
 {
 	(void)stream;
+	const rc_view_t *views = batch->views;
+	const int n = batch->n;
 	const rc_world_t *w = &g->w;
 	int st = 0;
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
 	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
-	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views;
+	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views; f.dlights = batch->dlights;
 	f.facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
 	if (f.facecap < 1) f.facecap = 1;
 	std::vector<rc_facerec_t> facelist ((size_t)n * f.facecap);
@@ -108,6 +110,8 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	std::vector<rc_cachejob_t> jobs (f.jobcap);
 	f.jobs = jobs.data ();
 	f.fb = (uint8_t *)fb_dev; f.zb = (int16_t *)z_dev;
+	std::vector<uint8_t> warpbuf ((size_t)(batch->nwarp + 1) * RC_WARP_W * RC_WARP_H, 0);
+	f.warpbuf = warpbuf.data ();
 	f.status = &st;
 
 	std::vector<int> facemark ((size_t)n * w->numfaces, 0x7F7F7F7F), viewleaf (n, 0);
@@ -137,7 +141,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 		const rc_face_t *fa = &w->faces[job->face];
 		unsigned bl[18 * 18];
 		int size = ((fa->extents[0] >> 4) + 1) * ((fa->extents[1] >> 4) + 1);
-		for (int i = 0; i < size; i++) bl[i] = rc_cache_luxel (w, job, i);
+		for (int i = 0; i < size; i++) bl[i] = rc_cache_luxel (w, &f, job, i);
 		for (int y = 0; y < job->height; y++)
 			for (int x = 0; x < job->width; x++)
 				g->cachepool[job->dstofs + y * job->width + x] = rc_cache_texel (w, job, bl, x, y);
@@ -152,6 +156,10 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	}
 	for (int t = 0; t < nblocks; t++) rc_draw_block (w, &f, t);
 
+	for (int vi = 0; vi < n; vi++)
+		if (views[vi].warp_index >= 0)
+			for (int v = 0; v < views[vi].rd_h; v++)
+				for (int u = 0; u < ((views[vi].rd_w + 3) & ~3); u++) rc_warp_pixel (w, &f, vi, u, v);
 	g->nspans = (int)(g->alloc[0] & 0xFFFFFFFFu);
 	if (g->nspans > f.spancap) g->nspans = f.spancap;
 	g->edgecap = f.edgecap; g->surfcap = f.surfcap; g->nfaces = nfaces;
@@ -162,15 +170,16 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	return RC_OK;
 }
 
-int rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
 			int *status, char *err, size_t errlen)
 {
+	const int n = batch->n;
 	size_t px = (size_t)g->width * g->height;
 	memset (fb_out, 0, px * n);
 	std::vector<int16_t> ztmp;
 	if (!z_out) { ztmp.assign (px * n, 0); z_out = ztmp.data (); }
 	else memset (z_out, 0, px * n * 2);
-	return rc_gpu_render (g, views, n, fb_out, z_out, NULL, status, err, errlen);
+	return rc_gpu_render (g, batch, fb_out, z_out, NULL, status, err, errlen);
 }
 
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }

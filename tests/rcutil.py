@@ -43,10 +43,30 @@ def scene_info(name: str) -> dict:
     return _INFO[name]
 
 
-def scene_views(name: str, n: int, **kw):
+def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, **kw):
     if name == "box":
-        return views.timerefresh_views((0, 0, 0), 128)[:n] if n <= 128 else views.timerefresh_views((0, 0, 0), n)
-    return views.halton_views(scene_info(name), n, **kw)
+        vs = views.timerefresh_views((0, 0, 0), 128)[:n] if n <= 128 else views.timerefresh_views((0, 0, 0), n)
+    else:
+        vs = views.halton_views(scene_info(name), n, **kw)
+    if dlights:
+        add_dlights(vs, dlights)
+    if underwater_every:
+        for i, sp in enumerate(vs):
+            if i % underwater_every == 0:
+                sp.flags |= 2          # RDF_UNDERWATER -> r_dowarp (r_misc.c:446)
+    return vs
+
+
+def add_dlights(specs, k: int):
+    """k dynamic lights per view, radius 200-300, scattered around the camera."""
+    for i, sp in enumerate(specs):
+        sp.dlights = []
+        for j in range(k):
+            h = i * 31 + j * 7 + 1
+            ox = (views.halton(h, 2) * 2 - 1) * 260.0
+            oy = (views.halton(h, 3) * 2 - 1) * 260.0
+            oz = (views.halton(h, 5) * 2 - 1) * 60.0
+            sp.dlights.append((sp.origin[0] + ox, sp.origin[1] + oy, sp.origin[2] + oz, 200.0 + 100.0 * views.halton(h, 7)))
 
 
 def sha(a: np.ndarray) -> str:

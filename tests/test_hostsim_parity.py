@@ -1,0 +1,71 @@
+"""Host logic + kernel arithmetic on the CPU: the C-ABI host files linked with a loop over the
+kernel bodies (tests/hostsim, test infrastructure) against the oracle and the golden vectors.
+Sizes are kept small so the whole CPU suite runs in a few minutes."""
+import os
+
+import numpy as np
+import pytest
+
+import rcutil
+from tochris_b200 import api
+
+CASES = [
+    ("box", 320, 200, 24, 1.0, 0.0, {}),
+    ("small", 320, 200, 8, 0.4, 0.31, {}),
+    ("multi", 640, 480, 6, 1.0, 0.0, {}),
+    ("full", 320, 240, 24, 0.37, 0.173, {}),
+    ("multi", 160, 120, 48, 0.0, 0.01, {}),
+    ("multi", 320, 240, 12, 0.2, 0.05, dict(dlights=4)),
+    ("full", 320, 200, 8, 0.9, 0.11, dict(dlights=2, underwater_every=2)),
+]
+
+
+@pytest.mark.parametrize("scene,w,h,n,t0,dt,extra", CASES)
+def test_sim_matches_oracle(assets_dir, sim_lib, oracle_available, scene, w, h, n, t0, dt, extra):
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import run_oracle
+    kw = dict(extra)
+    if scene != "box":
+        kw.update(time=t0, time_step=dt)
+    specs = rcutil.scene_views(scene, n, **kw)
+    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    r = rcutil.render_rc(sim_lib, assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    assert r["status"] == 0, api.status_names(r["status"])
+    assert (o["fb"] == r["fb"]).all()
+    if not extra.get("underwater_every"):
+        assert (o["z"] == r["z"]).all()
+    else:
+        # under water only the 320x200 warp rectangle of the z-buffer is written (r_misc.c:448-454)
+        for i, sp in enumerate(specs):
+            hh, ww = (min(h, 200), min(w, 320)) if sp.flags & 2 else (h, w)
+            assert (o["z"][i, :hh, :ww] == r["z"][i, :hh, :ww]).all()
+
+
+def test_sim_matches_golden(assets_dir, sim_lib):
+    g = np.load(os.path.join(rcutil.ROOT, "tests", "golden", "smoke_small_320x200.npz"))
+    specs = rcutil.scene_views("small", int(g["n"]), time=float(g["t0"]), time_step=float(g["dt"]))
+    r = rcutil.render_rc(sim_lib, assets_dir, "maps/small.bsp", 320, 200, specs)
+    assert rcutil.sha(r["fb"]) == str(g["fb_sha"]) and rcutil.sha(r["z"]) == str(g["z_sha"])
+
+
+def test_stage_dumps_match(assets_dir, sim_lib, oracle_available):
+    """Per-stage differential test: emitted edges and spans, not only pixels."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import run_oracle
+    specs = rcutil.scene_views("multi", 4, time=1.0)
+    o = run_oracle.render(assets_dir, "maps/multi.bsp", 320, 240, specs, want_dump=True)
+    r = rcutil.render_rc(sim_lib, assets_dir, "maps/multi.bsp", 320, 240, specs, want_debug=True)
+    for vi in range(4):
+        oe, os_, osp, cnt = o["dumps"][vi]
+        assert cnt["outofedges"] == 0 and cnt["outofsurfaces"] == 0
+        re = r["edges"][vi]
+        assert len(re) == len(oe)
+        a = sorted((int(e["u"]), int(e["u_step"]), int(e["v"]), int(e["v2"])) for e in oe)
+        b = sorted((int(e["u"]), int(e["u_step"]), int(e["v"]), int(e["v2"])) for e in re)
+        assert a == b
+        rsp = r["spans"][(r["spans"]["view"] == vi) & (r["spans"]["count"] > 0)]
+        a = sorted((int(s["u"]), int(s["v"]), int(s["count"])) for s in osp)
+        b = sorted((int(s["u"]), int(s["v"]), int(s["count"])) for s in rsp)
+        assert a == b

@@ -28,6 +28,8 @@ static struct {
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
 	rc_view_t   *viewscratch; int viewscratchcap;
+	rc_dlight_t *dlscratch; int dlscratchcap;
+	rc_batch_t   batch;
 } rc;
 
 static int rc_fail (int code, const char *fmt, ...)
@@ -109,6 +111,7 @@ void RC_Shutdown (void)
 	Mod_ClearAll ();
 	if (rc.gpu) rc_gpu_destroy (rc.gpu);
 	free (rc.viewscratch);
+	free (rc.dlscratch);
 	memset (&rc, 0, sizeof(rc));
 }
 
@@ -227,7 +230,7 @@ int RC_LoadWorld (const char *name)
 /* ---- rendering --------------------------------------------------------------------------- */
 static int rc_prepare_views (const refdef_t *views, int n)
 {
-	int i, rcode;
+	int i, j, rcode, ndl, nwarp = 0;
 	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
 	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
 	if (n > rc.viewscratchcap)
@@ -237,13 +240,39 @@ static int rc_prepare_views (const refdef_t *views, int n)
 		rc.viewscratchcap = rc.viewscratch ? n : 0;
 		if (!rc.viewscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
 	}
+	ndl = 0;
+	for (i = 0; i < n; i++)
+		ndl += views[i].num_dlights > 0 ? views[i].num_dlights : 0;
+	if (ndl > rc.dlscratchcap)
+	{
+		free (rc.dlscratch);
+		rc.dlscratch = (rc_dlight_t *)malloc (sizeof(rc_dlight_t) * ndl);
+		rc.dlscratchcap = rc.dlscratch ? ndl : 0;
+		if (!rc.dlscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	}
+	ndl = 0;
 	for (i = 0; i < n; i++)
 	{
+		rc_view_t *v = &rc.viewscratch[i];
 		if (!rc.world && !(views[i].flags & RDF_NOWORLDMODEL))
 			return rc_fail (RC_ERR_NOWORLD, "R_RenderView: NULL worldmodel");	/* r_main.c:1003 */
-		rcode = RC_SetupView (&views[i], &rc.vid, &rc.cvars, &rc.viewscratch[i]);
+		rcode = RC_SetupView (&views[i], &rc.vid, &rc.cvars, v);
 		if (rcode != RC_OK) return rc_fail (rcode, "view %d: bad refdef rectangle", i);
+		if (views[i].num_dlights > MAX_DLIGHTS)
+			return rc_fail (RC_ERR_ARG, "view %d: more than %d dlights", i, MAX_DLIGHTS);
+		if (v->dowarp)
+			v->warp_index = nwarp++;
+		v->num_dlights = views[i].num_dlights > 0 ? views[i].num_dlights : 0;
+		v->dlight_ofs = ndl;
+		for (j = 0; j < v->num_dlights; j++, ndl++)
+		{
+			memcpy (rc.dlscratch[ndl].origin, views[i].dlights[j].origin, sizeof(float) * 3);
+			rc.dlscratch[ndl].radius = views[i].dlights[j].radius;
+		}
 	}
+	rc.batch.views = rc.viewscratch; rc.batch.n = n;
+	rc.batch.dlights = rc.dlscratch; rc.batch.ndlights = ndl;
+	rc.batch.nwarp = nwarp;
 	return RC_OK;
 }
 
@@ -252,7 +281,7 @@ int RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_ou
 	int r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
-	return rc_gpu_render_host (rc.gpu, rc.viewscratch, n, fb_out, z_out, status, rc.err, sizeof(rc.err));
+	return rc_gpu_render_host (rc.gpu, &rc.batch, fb_out, z_out, status, rc.err, sizeof(rc.err));
 }
 
 int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
@@ -260,7 +289,7 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 	int r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
-	return rc_gpu_render (rc.gpu, rc.viewscratch, n, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
+	return rc_gpu_render (rc.gpu, &rc.batch, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
 }
 
 void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }

@@ -62,6 +62,8 @@ struct rc_gpu_s {
 	rc_span_t *d_spans; int *d_blockspan;
 	rc_lineinfo *d_lineinfo; uint2 *d_aetpool; int walk_lanes;
 	float *d_chk; int *d_spanaux;
+	rc_dlight_t *d_dlights; int dlightcap;
+	uint8_t *d_warpbuf; int warpcap;
 	rc_cachejob_t *d_jobs;
 	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
 	int *d_status;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
 		const int size = lw * ((fa->extents[1] >> 4) + 1);
 		__syncthreads ();
 		for (int i = threadIdx.x; i < size; i += blockDim.x)
-			bl[i] = rc_cache_luxel (&w, &job, i);
+			bl[i] = rc_cache_luxel (&w, &f, &job, i);
 		__syncthreads ();
 		const int mip = job.mip, shift = 4 - mip, bs = 16 >> mip;
 		const int nu = job.width >> shift;		/* light blocks per row */
@@ -388,6 +390,13 @@ __global__ void k_draw (const __grid_constant__ rc_world_t w, const __grid_const
 		rc_draw_block (&w, &f, t);
 }
 
+__global__ void k_warp (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	const int vi = blockIdx.z;
+	const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+	rc_warp_pixel (&w, &f, vi, u, v);
+}
+
 __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -425,7 +434,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	memset (&g->stats, 0, sizeof(g->stats));
 	g->device = device; g->width = width; g->height = height;
 	g->haveworld = false; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
-	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0;
+	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->walk_lanes = getenv ("RC_WALK_LANES") ? atoi (getenv ("RC_WALK_LANES")) : 4;
 	if (g->walk_lanes < 1 || g->walk_lanes > 32) g->walk_lanes = 32;
 	cudaDeviceProp prop;
@@ -484,7 +493,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	free_chunk (g); free_world (g);
 	cudaFree (g->d_cachepool); cudaFree (g->d_cachekeys); cudaFree (g->d_cachevals);
 	cudaFree (g->d_alloc); cudaFree (g->d_status); cudaFree (g->d_sintable); cudaFree (g->d_intsintable);
-	cudaFree (g->d_fb); cudaFree (g->d_zb);
+	cudaFree (g->d_fb); cudaFree (g->d_zb); cudaFree (g->d_dlights); cudaFree (g->d_warpbuf);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
 	delete g;
@@ -597,10 +606,12 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, int16_t *zb, cudaStream_t s,
 		      bool timed, char *err, size_t errlen)
 {
+	bool anywarp = false;
+	for (int i = 0; i < n; i++) anywarp |= hviews[i].warp_index >= 0;
 	const rc_world_t &w = g->w;
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
-	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views;
+	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views; f.dlights = g->d_dlights;
 	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
@@ -611,7 +622,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
 	f.jobs = g->d_jobs; f.jobcap = g->jobcap;
-	f.fb = fb; f.zb = zb; f.status = g->d_status;
+	f.fb = fb; f.zb = zb; f.status = g->d_status; f.warpbuf = g->d_warpbuf;
 
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
@@ -649,6 +660,12 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	if (timed) cudaEventRecord (g->ev[5], s);
 	k_spanprep<<<g->numsms * 8, 128, 0, s>>> (w, f);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+	if (anywarp)
+	{
+		dim3 gw2 ((g->width + 127) / 128, g->height, n);
+		k_warp<<<gw2, 128, 0, s>>> (w, f);
+		g->stats.kernel_launches++;
+	}
 	if (timed) cudaEventRecord (g->ev[6], s);
 	g->stats.kernel_launches += 13;
 	CK (cudaGetLastError ());
@@ -686,9 +703,11 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 	}
 }
 
-int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
 		   int *status, char *err, size_t errlen)
 {
+	const rc_view_t *views = batch->views;
+	const int n = batch->n;
 	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
 	size_t px = (size_t)g->width * g->height;
 	int st = 0;
@@ -700,6 +719,20 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 		do_flush (g, s);
 		g->stats.kernel_launches++;
 	}
+	if (batch->ndlights > g->dlightcap)
+	{
+		cudaFree (g->d_dlights);
+		g->dlightcap = batch->ndlights + 1024;
+		CK (cudaMalloc (&g->d_dlights, sizeof(rc_dlight_t) * g->dlightcap));
+	}
+	if (batch->nwarp > g->warpcap)
+	{
+		cudaFree (g->d_warpbuf);
+		g->warpcap = batch->nwarp;
+		CK (cudaMalloc (&g->d_warpbuf, (size_t)g->warpcap * RC_WARP_W * RC_WARP_H));
+	}
+	if (batch->ndlights)
+		CK (cudaMemcpyAsync (g->d_dlights, batch->dlights, sizeof(rc_dlight_t) * batch->ndlights, cudaMemcpyHostToDevice, s));
 	for (int attempt = 0; attempt < 4; attempt++)
 	{
 		int r = ensure_chunk (g, n, err, errlen);
@@ -739,9 +772,10 @@ int rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, voi
 	return RC_OK;
 }
 
-int rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
 			int *status, char *err, size_t errlen)
 {
+	const int n = batch->n;
 	size_t px = (size_t)g->width * g->height;
 	cudaSetDevice (g->device);
 	if (g->outcap < px * n)
@@ -755,7 +789,7 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_
 	/* every pixel of a full-screen view is written by the world spans; views that use a
 	 * sub-rectangle leave the rest as the caller's buffer had it in the reference, here 0 */
 	CK (cudaMemsetAsync (g->d_fb, 0, px * n, g->stream));
-	int r = rc_gpu_render (g, views, n, g->d_fb, g->d_zb, NULL, status, err, errlen);
+	int r = rc_gpu_render (g, batch, g->d_fb, g->d_zb, NULL, status, err, errlen);
 	if (r != RC_OK) return r;
 	CK (cudaMemcpyAsync (fb_out, g->d_fb, px * n, cudaMemcpyDeviceToHost, g->stream));
 	if (z_out) CK (cudaMemcpyAsync (z_out, g->d_zb, px * n * sizeof(int16_t), cudaMemcpyDeviceToHost, g->stream));

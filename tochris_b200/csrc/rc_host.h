@@ -78,13 +78,20 @@ void RC_FreeHostWorld (rc_hostworld_t *hw);
 /* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
 typedef struct rc_gpu_s rc_gpu_t;
 
+/* everything one RC_RenderViews call hands to the device, already flattened by rc_api.c */
+typedef struct {
+    const rc_view_t   *views;    int n;
+    const rc_dlight_t *dlights;  int ndlights;
+    int nwarp;                   /* views with r_dowarp (each needs a 320x200 warp buffer) */
+} rc_batch_t;
+
 rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen);
 void rc_gpu_destroy (rc_gpu_t *g);
 int  rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen);
 /* renders n prepared views; fb_dev/z_dev are device pointers (z may be NULL) */
-int  rc_gpu_render (rc_gpu_t *g, const rc_view_t *views, int n, void *fb_dev, void *z_dev, void *stream,
+int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
                     int *status, char *err, size_t errlen);
-int  rc_gpu_render_host (rc_gpu_t *g, const rc_view_t *views, int n, uint8_t *fb_out, int16_t *z_out,
+int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
 void rc_gpu_flush_caches (rc_gpu_t *g);
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out);

@@ -149,6 +149,11 @@ int RC_SetupView (const rc_refdef_t *rd, const rc_vidinfo_t *vid, const rc_cvars
 	v->turbphase = (int)(rd->time*RC_TURB_SPEED) & (RC_CYCLE-1);
 
 	v->dowarp = (cv->r_waterwarp != 0) && (rd->flags & RC_RDF_UNDERWATER);
+	v->warp_index = -1;
+	v->rd_x = rd->x; v->rd_y = rd->y; v->rd_w = rd->width; v->rd_h = rd->height;
+	if (rd->x < 0 || rd->y < 0 || rd->width <= 0 || rd->height <= 0 ||
+	    rd->x + rd->width > vid->width || rd->y + rd->height > vid->height)
+		return RC_ERR_ARG;
 	if (v->dowarp)
 	{	/* r_misc.c:448-454 */
 		v->vrect_x = 0;

@@ -48,11 +48,14 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_AET_MAX         256       /* active edges per scanline the scan kernel holds (shared memory) */
 #define RC_STACK_MAX       96        /* active surface stack depth held by the scan thread */
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
+#define RC_WARP_W          320       /* WARP_WIDTH / WARP_HEIGHT, d_iface.h:22-23 */
+#define RC_WARP_H          200
 
 /* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
 typedef struct {
     int nviews, width, height;
     const rc_view_t *views;
+    const rc_dlight_t *dlights;   /* all views' dynamic lights, indexed from rc_view_t.dlight_ofs */
     /* BSP walk */
     rc_facerec_t *facelist; int facecap; int *nfaces;
     uint16_t *facepos;            /* [nviews][numfaces]: list position of a rendered face, else RC_FACEPOS_NONE */
@@ -75,6 +78,7 @@ typedef struct {
     rc_cachejob_t *jobs; int jobcap;
     /* outputs */
     uint8_t *fb; int16_t *zb;
+    uint8_t *warpbuf;             /* [nwarp][320*200]: r_warpbuffer of the views that render under water */
     int *status;
 } rc_frame_t;
 
@@ -957,6 +961,39 @@ RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc
 #define RC_SRC_SOLID   2    /* background / fast sky: constant colour, z at "infinity" */
 #define RC_SRC_SKY     3    /* scrolling two-layer sky (d_sky.c) */
 
+/* R_PushDlights / R_MarkLights (r_light.c:66-151) for one face: the bit of every dynamic light
+ * whose BSP descent reaches the face's node with |dist| <= radius.  The reference descends
+ * from the root choosing children by plane distance; a node is marked iff no ancestor's
+ * test sends the descent away from it and its own plane is within the radius. */
+RC_HD int rc_dlight_bits (const rc_world_t *w, const rc_frame_t *f, const rc_view_t *vw, int node)
+{
+	int bits = 0;
+	const int tx = w->nodeaux[node].dfs_in;
+	for (int l = 0; l < vw->num_dlights; l++)
+	{
+		const rc_dlight_t *dl = &f->dlights[vw->dlight_ofs + l];
+		int cur = 0;
+		for (;;)
+		{
+			const rc_node_t *nd = &w->nodes[cur];
+			float dist = rc_plane_diff (dl->origin, &w->planes[nd->plane]);
+			if (cur == node)
+			{
+				if (!(dist > dl->radius) && !(dist < -dl->radius))
+					bits |= 1 << l;
+				break;
+			}
+			const int c = (tx < w->nodeaux[cur].dfs_mid) ? 0 : 1;
+			if (dist > dl->radius) { if (c != 0) break; }
+			else if (dist < -dl->radius) { if (c != 1) break; }
+			cur = nd->children[c];
+			if (cur < 0)
+				break;
+		}
+	}
+	return bits;
+}
+
 /* One thread per (view, surface): the per-surface part of D_DrawSurfaces (d_edge.c:161-340)
  * for surfaces that own spans: mip selection, D_CacheSurface lookup (d_surf.c:196) against
  * the shared GPU surface cache, gradients.  surf->pad = texel source. */
@@ -1022,6 +1059,11 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		codes[k] = rc_lightadj_code (la[k]);
 		if (codes[k] == 254) cacheable = 0;
 	}
+	int dlbits = 0;
+	if (vw->num_dlights && fa->node >= 0)
+		dlbits = rc_dlight_bits (w, f, vw, fa->node);
+	if (dlbits)
+		cacheable = 0;		/* cache->dlight: rebuilt every frame (d_surf.c:214-228), private to the view */
 	int bw = fa->extents[0] >> mip, bh = fa->extents[1] >> mip;
 	int bytes = (bw * bh + 15) & ~15;
 	int slot = -1, creator = 0, ofs = -1;
@@ -1056,7 +1098,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 			job->face = s->face; job->mip = mip; job->texture = tex;
 			job->lightadj[0] = la[0]; job->lightadj[1] = la[1]; job->lightadj[2] = la[2]; job->lightadj[3] = la[3];
 			job->ambient = vw->ambientlight; job->dstofs = ofs; job->width = bw; job->height = bh;
-			job->view = -1; job->pad = vw->fullbright;
+			job->view = dlbits ? vi : -1; job->pad = vw->fullbright; job->dlightbits = dlbits;
 		}
 		if (creator)
 			f->cachevals[slot] = ofs;
@@ -1079,7 +1121,7 @@ RC_HD void rc_surf_resolve (const rc_frame_t *f, int vi, int si)
 
 /* ------------------------------------------------------------- stage 5: cache build ---- */
 /* one lightmap sample of R_BuildLightmap (r_light.c:372-425) */
-RC_HD unsigned rc_cache_luxel (const rc_world_t *w, const rc_cachejob_t *job, int i)
+RC_HD unsigned rc_cache_luxel (const rc_world_t *w, const rc_frame_t *f, const rc_cachejob_t *job, int i)
 {
 	const rc_face_t *fa = &w->faces[job->face];
 	int smax = (fa->extents[0] >> 4) + 1, tmax = (fa->extents[1] >> 4) + 1;
@@ -1095,6 +1137,49 @@ RC_HD unsigned rc_cache_luxel (const rc_world_t *w, const rc_cachejob_t *job, in
 			unsigned scale = (unsigned)job->lightadj[maps];
 			bl += lightmap[i] * scale;
 			lightmap += size;
+		}
+	}
+	if (job->dlightbits)
+	{
+		/* R_AddDynamicLights, r_light.c:274-365 (world entity: no rotation, origin 0) */
+		const rc_view_t *vw = &f->views[job->view];
+		const rc_texinfo_t *tex = &w->texinfo[fa->texinfo];
+		const rc_plane_t *plane = &w->planes[fa->plane];
+		const int ls = i % smax, lt = i / smax;
+		for (int lnum = 0; lnum < vw->num_dlights; lnum++)
+		{
+			if (!(job->dlightbits & (1 << lnum)))
+				continue;
+			const rc_dlight_t *l = &f->dlights[vw->dlight_ofs + lnum];
+			float dlorigin[3], impact[3], local[2];
+			dlorigin[0] = l->origin[0] - 0.0f; dlorigin[1] = l->origin[1] - 0.0f; dlorigin[2] = l->origin[2] - 0.0f;
+			float rad = l->radius;
+			float dist = rc_plane_diff (dlorigin, plane);
+			rad -= fabs ((double)dist);
+			if (rad < 0)
+				continue;
+			if (plane->type < 3)
+			{
+				impact[0] = dlorigin[0]; impact[1] = dlorigin[1]; impact[2] = dlorigin[2];
+				impact[plane->type] -= dist;
+			}
+			else
+			{
+				for (int q = 0; q < 3; q++)
+					impact[q] = dlorigin[q] - plane->normal[q]*dist;
+			}
+			local[0] = rc_dot3 (impact, tex->vecs[0]) + tex->vecs[0][3];
+			local[1] = rc_dot3 (impact, tex->vecs[1]) + tex->vecs[1][3];
+			local[0] -= fa->texturemins[0];
+			local[1] -= fa->texturemins[1];
+			int td = rc_f2i (local[1] - lt*16);
+			if (td < 0) td = -td;
+			int sd = rc_f2i (local[0] - ls*16);
+			if (sd < 0) sd = -sd;
+			if (sd > td) dist = sd + (td>>1);
+			else dist = td + (sd>>1);
+			if (dist < rad)
+				bl = (unsigned)(long long)((float)bl + (rad - dist)*256);
 		}
 	}
 	int t = (255*256 - (int)bl) >> (8 - 6);
@@ -1282,7 +1367,8 @@ RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
 	const int total = sp.count - first;		/* pixels from this subdivision to the end of the span */
 	const int cnt = total > 8 ? 8 : total;
 	const size_t viewpix = (size_t)f->width * f->height;
-	uint8_t *pdest = f->fb + viewpix * sp.view + (size_t)vw->screenwidth * sp.v + sp.u + first;
+	uint8_t *pdest = (vw->warp_index < 0 ? f->fb + viewpix * sp.view : f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H)) +
+			 (size_t)vw->screenwidth * sp.v + sp.u + first;
 	const int srckind = ds.srckind;
 
 	/* ---- z (D_DrawZSpans) ---- */
@@ -1463,6 +1549,30 @@ RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
 		}
 	}
 	rc_store_bytes8 (pdest, plo, phi, cnt);
+}
+
+
+/* One thread per output pixel of an underwater view: D_WarpScreen (d_scan.c:43-89).
+ * (u, v) run over the r_refdef rectangle; like the reference's 4-way unrolled loop the
+ * columns are processed up to the next multiple of 4. */
+RC_HD void rc_warp_pixel (const rc_world_t *w, const rc_frame_t *f, int vi, int u, int v)
+{
+	const rc_view_t *vw = &f->views[vi];
+	if (vw->warp_index < 0 || v >= vw->rd_h || u >= ((vw->rd_w + 3) & ~3))
+		return;
+	const int ww = vw->vrect_w, hh = vw->vrect_h;
+	const float wratio = ww / (float)vw->rd_w;
+	const float hratio = hh / (float)vw->rd_h;
+	const int *turb = w->intsintable + vw->turbphase;
+	const int vv = v + turb[u & (RC_CYCLE - 1)];		/* row[turb[u&127]] = rowptr[v + ...] */
+	const int uu = turb[v & (RC_CYCLE - 1)] + u;		/* col[u] = column[turb[v&127] + u] */
+	const int srow = vw->vrect_y + rc_f2i ((float)vv * hratio * hh / (hh + 3 * 2));
+	const int scol = vw->vrect_x + rc_f2i ((float)uu * wratio * ww / (ww + 3 * 2));
+	const uint8_t *src = f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H);
+	const size_t viewpix = (size_t)f->width * f->height;
+	const size_t o = (size_t)(vw->rd_y + v) * f->width + vw->rd_x + u;
+	if (o < viewpix)
+		f->fb[viewpix * vi + o] = src[srow * RC_WARP_W + scol];
 }
 
 #endif /* RC_PIPELINE_H */

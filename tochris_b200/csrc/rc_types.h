@@ -171,8 +171,15 @@ typedef struct {
     int   skycolor;                /* (int)r_skycolor.value & 0xFF */
     int   fastsky;                 /* r_fastsky.value != 0 */
     float skyshift;                /* R_SetSkyFrame, r_sky.c:112-130 */
-    int   pad1;
+    int   num_dlights;             /* refdef.num_dlights (<= 32) */
+    int   dlight_ofs;              /* first entry of this view in the batch's dlight array */
+    int   warp_index;              /* r_dowarp: which 320x200 warp buffer this view renders into, else -1 */
+    int   rd_x, rd_y, rd_w, rd_h;  /* r_refdef rectangle (D_WarpScreen target) */
+    int   pad1[2];
 } rc_view_t;
+
+/* dlight_t (client/ref.h:43-47) */
+typedef struct { float origin[3]; float radius; } rc_dlight_t;
 
 /* ---- per-view transient records ------------------------------------------------------ */
 typedef struct {            /* one rendered face: output of the BSP walk (r_bsp.c:436) */
@@ -234,8 +241,10 @@ typedef struct {
     int dstofs;             /* into the cache pool */
     int width, height;      /* block size in texels */
     int view;               /* for dynamic lights (-1: none) */
-    int pad;
-} rc_cachejob_t;            /* 48 B */
+    int pad;                /* bit 0: r_fullbright */
+    int dlightbits;
+    int pad2[3];
+} rc_cachejob_t;            /* 64 B */
 
 /* error / status bits returned through the C-ABI */
 #define RC_OK                    0
