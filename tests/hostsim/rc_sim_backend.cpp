@@ -30,6 +30,12 @@ struct rc_gpu_s {
 	std::vector<rc_edge_t> edges; std::vector<int> nedges; int edgecap;
 	std::vector<rc_surf_t> surfs; int surfcap; std::vector<int> nfaces;
 	std::vector<rc_span_t> spans; int nspans;
+	// alias model blobs
+	std::vector<rc_aliasmodel_t> amodels;
+	std::vector<int> stverts, atris;
+	std::vector<uint8_t> poseverts, skinpixels;
+	std::vector<float> anormdots;
+	int maxverts, maxtris;
 };
 
 extern "C" {
@@ -63,6 +69,31 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	return RC_OK;
 }
 
+int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const float *anorm_dots, char *err, size_t errlen)
+{
+	(void)err; (void)errlen;
+	g->amodels.clear (); g->stverts.clear (); g->atris.clear (); g->poseverts.clear (); g->skinpixels.clear ();
+	g->anormdots.assign (anorm_dots, anorm_dots + 16 * 256);
+	g->maxverts = g->maxtris = 0;
+	for (int i = 0; i < n; i++)
+	{
+		rc_hostalias_t *a = models[i];
+		rc_aliasmodel_t m;
+		m.numverts = a->numverts; m.numtris = a->numtris; m.skinwidth = a->skinwidth; m.skinheight = a->skinheight;
+		m.stverts_ofs = (int)g->stverts.size () / 4; m.tris_ofs = (int)g->atris.size () / 4;
+		m.poses_ofs = (int)g->poseverts.size () / 4; m.skins_ofs = (int)g->skinpixels.size ();
+		g->stverts.insert (g->stverts.end (), a->stverts, a->stverts + 4 * a->numverts);
+		g->atris.insert (g->atris.end (), a->tris, a->tris + 4 * a->numtris);
+		g->poseverts.insert (g->poseverts.end (), a->poseverts, a->poseverts + 4 * (size_t)a->numposes * a->numverts);
+		g->skinpixels.insert (g->skinpixels.end (), a->skinpixels, a->skinpixels + (size_t)a->numskinpics * a->skinwidth * a->skinheight);
+		g->amodels.push_back (m);
+		a->device_index = i;
+		if (a->numverts > g->maxverts) g->maxverts = a->numverts;
+		if (a->numtris > g->maxtris) g->maxtris = a->numtris;
+	}
+	return RC_OK;
+}
+
 void rc_gpu_flush_caches (rc_gpu_t *g)
 {
 	std::fill (g->cachekeys.begin (), g->cachekeys.end (), RC_CACHE_EMPTY);
@@ -80,7 +111,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
 	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
-	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views; f.dlights = batch->dlights;
+	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views; f.dlights = batch->dlights; f.viewbase = 0;
 	f.facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
 	if (f.facecap < 1) f.facecap = 1;
 	std::vector<rc_facerec_t> facelist ((size_t)n * f.facecap);
@@ -156,6 +187,24 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	}
 	for (int t = 0; t < nblocks; t++) rc_draw_block (w, &f, t);
 
+	/* alias models, particles, z resolve (R_DrawEntitiesOnList, R_DrawParticles) */
+	std::vector<rc_finalvert_t> finalverts ((size_t)batch->nfinalverts + 1);
+	std::vector<unsigned long long> zres ((size_t)(batch->nzres ? batch->nzres : 1) * g->width * g->height, 0ull);
+	f.alias = batch->alias; f.nalias = batch->nalias; f.amodels = g->amodels.data ();
+	f.stverts = g->stverts.data (); f.atris = g->atris.data (); f.poseverts = g->poseverts.data ();
+	f.skinpixels = g->skinpixels.data (); f.anormdots = g->anormdots.data (); f.colormaps = batch->colormaps;
+	f.finalverts = finalverts.data (); f.particles = batch->particles; f.nparticles = batch->nparticles;
+	f.zres = zres.data ();
+	for (int ii = 0; ii < batch->nalias; ii++)
+		for (int v = 0; v < g->amodels[batch->alias[ii].model].numverts; v++) rc_alias_vertex (&f, ii, v);
+	for (int ii = 0; ii < batch->nalias; ii++)
+		for (int t = 0; t < g->amodels[batch->alias[ii].model].numtris; t++) rc_alias_triangle (&f, ii, t);
+	for (int pi = 0; pi < batch->nparticles; pi++) rc_particle (&f, pi);
+	if (batch->nzres)
+		for (int vi = 0; vi < n; vi++)
+			if (views[vi].zres_index >= 0)
+				for (int y = 0; y < g->height; y++)
+					for (int x = 0; x < g->width; x++) rc_zresolve_pixel (&f, vi, x, y);
 	for (int vi = 0; vi < n; vi++)
 		if (views[vi].warp_index >= 0)
 			for (int v = 0; v < views[vi].rd_h; v++)

@@ -27,7 +27,11 @@ def scene_defs():
 
 
 def make_assets(basedir: str, names=None):
+    from tochris_b200.scenes import mdlgen
     views.write_base_assets(basedir)
+    views.write_file(basedir, "progs/ball.mdl", mdlgen.icosphere_mdl())
+    views.write_file(basedir, "progs/blob.mdl", mdlgen.icosphere_mdl(seed=77, subdiv=1, radius=14.0, nframes=2,
+                                                                       frame_group=False, skin_group=True, skin_w=64, skin_h=96))
     for name, fn in scene_defs().items():
         if names and name not in names:
             continue
@@ -43,18 +47,56 @@ def scene_info(name: str) -> dict:
     return _INFO[name]
 
 
-def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, **kw):
+def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, entities: int = 0, particles: int = 0, **kw):
     if name == "box":
         vs = views.timerefresh_views((0, 0, 0), 128)[:n] if n <= 128 else views.timerefresh_views((0, 0, 0), n)
     else:
         vs = views.halton_views(scene_info(name), n, **kw)
     if dlights:
         add_dlights(vs, dlights)
+    if entities:
+        add_entities(vs, entities)
+    if particles:
+        add_particles(vs, particles)
     if underwater_every:
         for i, sp in enumerate(vs):
             if i % underwater_every == 0:
                 sp.flags |= 2          # RDF_UNDERWATER -> r_dowarp (r_misc.c:446)
     return vs
+
+
+def add_entities(specs, k: int, near: float = 40.0):
+    """k alias entities per view on a jittered ring in front of / around the camera."""
+    import math
+    for i, sp in enumerate(specs):
+        sp.entities = []
+        yaw = math.radians(sp.angles[1])
+        for j in range(k):
+            h = i * 53 + j * 11 + 3
+            ang = yaw + (views.halton(h, 2) - 0.5) * 2.2
+            dist = near + views.halton(h, 3) * 260.0
+            ox = sp.origin[0] + math.cos(ang) * dist
+            oy = sp.origin[1] + math.sin(ang) * dist
+            oz = sp.origin[2] - 20.0 + views.halton(h, 5) * 60.0
+            model = "progs/ball.mdl" if j % 3 else "progs/blob.mdl"
+            nfr = 4 if model.endswith("ball.mdl") else 2
+            sp.entities.append(views.EntitySpec(model, (ox, oy, oz), (views.halton(h, 7) * 30 - 15, views.halton(h, 11) * 360, 0.0),
+                                                frame=j % nfr, oldframe=(j + 1) % nfr, framelerp=views.halton(h, 13),
+                                                flags=(8 if j % 5 == 0 else 0) | (16 if j % 7 == 3 else 0)))
+
+
+def add_particles(specs, k: int):
+    """k particles per view, uniform in a cone in front of the camera."""
+    import math
+    for i, sp in enumerate(specs):
+        sp.particles = []
+        yaw = math.radians(sp.angles[1])
+        for j in range(k):
+            h = i * 97 + j + 5
+            ang = yaw + (views.halton(h, 2) - 0.5) * 1.4
+            dist = 12.0 + views.halton(h, 3) * 300.0
+            sp.particles.append((sp.origin[0] + math.cos(ang) * dist, sp.origin[1] + math.sin(ang) * dist,
+                                 sp.origin[2] + (views.halton(h, 5) - 0.5) * 0.8 * dist, int(views.halton(h, 7) * 255)))
 
 
 def add_dlights(specs, k: int):
@@ -111,3 +153,28 @@ def render_rc(libpath, basedir, mapname, width, height, specs, cvars=None, want_
 
 def diff_fraction(a: np.ndarray, b: np.ndarray) -> float:
     return float((a != b).sum()) / a.size
+
+
+RC_STAT_ALIAS_RANGE = 512
+TOLERANCE = 1e-4        # BASELINE.json north_star: differing pixels per frame
+
+
+def assert_parity(o, r, specs, w, h):
+    """Bit-exact colour and z.  Two documented exceptions:
+    - views rendered under water only define the 320x200 warp rectangle of the z-buffer
+      (r_misc.c:448-454); the rest is whatever the previous frame left there in the reference;
+    - when the alias rasteriser reports RC_STAT_ALIAS_RANGE the reference itself read outside the
+      skin / colormap (clipped triangles stepping one texel row off the skin, d_polyse.c:385-447);
+      those pixels are undefined in the reference, so the frame is held to north_star's 1e-4."""
+    from tochris_b200 import api
+    status = r["status"] & ~RC_STAT_ALIAS_RANGE
+    assert status == 0, api.status_names(r["status"])
+    loose = bool(r["status"] & RC_STAT_ALIAS_RANGE)
+    for i, sp in enumerate(specs):
+        hh, ww = (min(h, 200), min(w, 320)) if sp.flags & 2 else (h, w)
+        dz = int((o["z"][i, :hh, :ww] != r["z"][i, :hh, :ww]).sum())
+        dfb = int((o["fb"][i] != r["fb"][i]).sum())
+        if loose:
+            assert dfb <= TOLERANCE * w * h and dz <= TOLERANCE * w * h, (i, dfb, dz)
+        else:
+            assert dfb == 0 and dz == 0, (i, dfb, dz)

@@ -12,29 +12,31 @@ from tochris_b200 import api
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # scene, w, h, views, time, time_step
-    ("box", 320, 200, 128, 1.0, 0.0),          # BASELINE config C1: timerefresh sweep
-    ("small", 320, 200, 16, 0.4, 0.31),
-    ("multi", 640, 480, 64, 1.0, 0.0),         # BASELINE config C2
-    ("full", 320, 240, 64, 0.37, 0.173),       # sky + water + animated textures, time-varying lights
-    ("multi", 160, 120, 512, 0.0, 0.01),       # BASELINE config C4 (sample)
-    ("full", 1280, 720, 6, 2.5, 0.5),          # BASELINE config C3 resolution (world only)
+    # scene, w, h, views, time, time_step, extras
+    ("box", 320, 200, 128, 1.0, 0.0, {}),          # BASELINE config C1: timerefresh sweep
+    ("small", 320, 200, 16, 0.4, 0.31, {}),
+    ("multi", 640, 480, 64, 1.0, 0.0, {}),         # BASELINE config C2
+    ("full", 320, 240, 64, 0.37, 0.173, {}),       # sky + water + animated textures, time-varying lights
+    ("multi", 160, 120, 512, 0.0, 0.01, {}),       # BASELINE config C4 (sample)
+    ("full", 1280, 720, 6, 2.5, 0.5, dict(entities=64, particles=2048)),   # BASELINE config C3 (sample)
+    ("multi", 320, 240, 48, 0.2, 0.05, dict(dlights=6)),                     # dynamic lights
+    ("full", 640, 480, 12, 0.9, 0.11, dict(dlights=2, underwater_every=2, entities=12, particles=200)),  # warp + everything
 ]
 
 
-@pytest.mark.parametrize("scene,w,h,n,t0,dt", CASES)
-def test_matches_oracle(assets_dir, oracle_available, scene, w, h, n, t0, dt):
+@pytest.mark.parametrize("scene,w,h,n,t0,dt,extra", CASES)
+def test_matches_oracle(assets_dir, oracle_available, scene, w, h, n, t0, dt, extra):
     if not oracle_available:
         pytest.skip("oracle/_ref not built")
     from oracle import run_oracle
-    specs = rcutil.scene_views(scene, n, time=t0, time_step=dt) if scene != "box" else rcutil.scene_views(scene, n)
+    kw = dict(extra)
+    if scene != "box":
+        kw.update(time=t0, time_step=dt)
+    specs = rcutil.scene_views(scene, n, **kw)
     o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
-    assert r["status"] == 0, api.status_names(r["status"])
     assert r["stats"]["kernel_launches"] > 0
-    nfb = int((o["fb"] != r["fb"]).sum())
-    nz = int((o["z"] != r["z"]).sum())
-    assert nfb == 0 and nz == 0, f"{nfb} colour / {nz} z pixels differ of {o['fb'].size}"
+    rcutil.assert_parity(o, r, specs, w, h)
 
 
 def test_golden_fixtures(assets_dir):

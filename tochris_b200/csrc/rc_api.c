@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /*
  * rc_api.c -- the C-ABI of libref_cuda.so (include/ref_cuda.h): the reference's
  * client/render.h symbol set, the batched RC_* extension and the refexport_t table.
@@ -8,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <dlfcn.h>
 #include "rc_host.h"
 
 #define RC_MAX_MODELS 512
@@ -25,10 +27,16 @@ static struct {
 	int          nummodels;
 	struct model_s *world;
 	char         err[1024];
+	int          unsupported;
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
 	rc_view_t   *viewscratch; int viewscratchcap;
 	rc_dlight_t *dlscratch; int dlscratchcap;
+	rc_aliasinst_t *aliasscratch; int aliasscratchcap;
+	rc_particle_t *partscratch; int partscratchcap;
+	uint8_t     *cmapscratch; int cmapscratchcap;
+	float        anorm_dots[16 * 256];
+	int          alias_dirty;		/* alias models loaded since the last device upload */
 	rc_batch_t   batch;
 } rc;
 
@@ -99,6 +107,36 @@ int RC_Init (const rc_config_t *cfg)
 	rc.cvars.d_mipscale = cfg->d_mipscale;
 	rc.cvars.r_maxsurfs = cfg->r_maxsurfs < 1000 ? 1000 : cfg->r_maxsurfs;	/* MINSURFACES, r_main.c:267 */
 	rc.cvars.r_maxedges = cfg->r_maxedges < 2000 ? 2000 : cfg->r_maxedges;	/* MINEDGES, r_main.c:293 */
+	{
+		/* r_avertexnormal_dots (r_alias.c:29-31): data/anorm_dots.f32 next to the library */
+		Dl_info di;
+		char path[1024];
+		FILE *f = NULL;
+		if (dladdr ((void *)RC_Init, &di) && di.dli_fname)
+		{
+			char *slash;
+			snprintf (path, sizeof(path) - 32, "%s", di.dli_fname);
+			slash = strrchr (path, '/');
+			if (slash) *slash = 0; else strcpy (path, ".");
+			strcat (path, "/data/anorm_dots.f32");
+			f = fopen (path, "rb");
+			if (!f)
+			{
+				/* the host-sim build lives in tests/hostsim/_build */
+				snprintf (path, sizeof(path) - 64, "%s", di.dli_fname);
+				slash = strrchr (path, '/');
+				if (slash) *slash = 0;
+				strcat (path, "/../../../tochris_b200/data/anorm_dots.f32");
+				f = fopen (path, "rb");
+			}
+		}
+		if (!f || fread (rc.anorm_dots, sizeof(float), 16 * 256, f) != 16 * 256)
+		{
+			if (f) fclose (f);
+			return rc_fail (RC_ERR_FILE, "Couldn't load data/anorm_dots.f32 (alias shading table)");
+		}
+		fclose (f);
+	}
 	rc.gpu = rc_gpu_create (cfg->device, cfg->width, cfg->height, cfg->surfcache_bytes, cfg->max_views_in_flight,
 				rc.err, sizeof(rc.err));
 	if (!rc.gpu) return RC_ERR_CUDA;
@@ -111,7 +149,7 @@ void RC_Shutdown (void)
 	Mod_ClearAll ();
 	if (rc.gpu) rc_gpu_destroy (rc.gpu);
 	free (rc.viewscratch);
-	free (rc.dlscratch);
+	free (rc.dlscratch); free (rc.aliasscratch); free (rc.partscratch); free (rc.cmapscratch);
 	memset (&rc, 0, sizeof(rc));
 }
 
@@ -126,11 +164,12 @@ void Mod_ClearAll (void)
 		struct model_s *m = rc.models[i];
 		if (m->type == rc_mod_brush && m->submodel == 0 && m->world)
 			RC_FreeHostWorld (m->world);
-		free (m->alias);
+		RC_FreeHostAlias (m->alias);
 		free (m);
 	}
 	rc.nummodels = 0;
 	rc.world = NULL;
+	rc.alias_dirty = 1;
 	if (rc.gpu) rc_gpu_flush_caches (rc.gpu);	/* D_FlushCaches, r_model.c:178 */
 }
 
@@ -183,6 +222,18 @@ static struct model_s *rc_load_model (const char *name)
 		}
 		return m;
 	}
+	if (len >= 4 && !memcmp (buf, "IDPO", 4))
+	{
+		rc_hostalias_t *a = RC_LoadAliasModel (buf, len, rc.err, sizeof(rc.err));
+		free (buf);
+		if (!a) return NULL;
+		m = rc_new_model (name);
+		if (!m) { RC_FreeHostAlias (a); rc_fail (RC_ERR_NOMEM, "too many models"); return NULL; }
+		m->type = rc_mod_alias; m->alias = a; m->flags = a->flags; m->numframes = a->numframes; m->synctype = a->synctype;
+		memcpy (m->mins, a->mins, sizeof(m->mins)); memcpy (m->maxs, a->maxs, sizeof(m->maxs));
+		rc.alias_dirty = 1;
+		return m;
+	}
 	free (buf);
 	rc_fail (RC_ERR_FORMAT, "Mod_NumForName: %s has an unsupported format", name);
 	return NULL;
@@ -231,6 +282,7 @@ int RC_LoadWorld (const char *name)
 static int rc_prepare_views (const refdef_t *views, int n)
 {
 	int i, j, rcode, ndl, nwarp = 0;
+	rc.unsupported = 0;
 	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
 	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
 	if (n > rc.viewscratchcap)
@@ -270,6 +322,122 @@ static int rc_prepare_views (const refdef_t *views, int n)
 			rc.dlscratch[ndl].radius = views[i].dlights[j].radius;
 		}
 	}
+	/* ---- entities and particles (R_DrawEntitiesOnList r_main.c:489-533, R_DrawParticles :773) ---- */
+	{
+		int nent = 0, npart = 0, nalias = 0, nverts = 0, ncmap = 1, nzres = 0, maxcmaps = 1;
+		const byte *cmaps[64];
+		rc_hostalias_t *amodels[RC_MAX_MODELS];
+		int namodels = 0;
+		for (i = 0; i < n; i++)
+		{
+			nent += views[i].num_entities > 0 ? views[i].num_entities : 0;
+			npart += views[i].num_particles > 0 ? views[i].num_particles : 0;
+		}
+		if (rc.alias_dirty && nent)
+		{
+			for (i = 0; i < rc.nummodels; i++)
+				if (rc.models[i]->type == rc_mod_alias)
+					amodels[namodels++] = rc.models[i]->alias;
+			if (rc_gpu_upload_alias (rc.gpu, amodels, namodels, rc.anorm_dots, rc.err, sizeof(rc.err)) != RC_OK)
+				return RC_ERR_CUDA;
+			rc.alias_dirty = 0;
+		}
+		if (nent > rc.aliasscratchcap)
+		{
+			free (rc.aliasscratch);
+			rc.aliasscratch = (rc_aliasinst_t *)malloc (sizeof(rc_aliasinst_t) * nent);
+			rc.aliasscratchcap = rc.aliasscratch ? nent : 0;
+			if (!rc.aliasscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+		}
+		if (npart > rc.partscratchcap)
+		{
+			free (rc.partscratch);
+			rc.partscratch = (rc_particle_t *)malloc (sizeof(rc_particle_t) * npart);
+			rc.partscratchcap = rc.partscratch ? npart : 0;
+			if (!rc.partscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+		}
+		(void)maxcmaps;
+		cmaps[0] = NULL;
+		npart = 0;
+		for (i = 0; i < n; i++)
+		{
+			rc_view_t *v = &rc.viewscratch[i];
+			int order = 0, used = 0;
+			v->zres_index = -1;
+			if (rc.cvars.r_drawentities)
+				for (j = 0; j < views[i].num_entities; j++)
+				{
+					const entity_t *e = &views[i].entities[j];
+					const struct model_s *mod = e->model;
+					rc_aliasinst_t *inst;
+					int c;
+					if (!mod) continue;
+					if ((e->flags & RF_WEAPONMODEL) && !rc.cvars.r_drawviewmodel) continue;
+					if (mod->type != rc_mod_alias)
+					{
+						if (mod->type == rc_mod_sprite) rc.unsupported = 1;
+						continue;		/* brush entities are handled with the world (R_DrawBEntitiesOnList) */
+					}
+					if (e->flags & RF_CULLVIS)
+					{
+						float mins[3], maxs[3];
+						for (c = 0; c < 3; c++) { mins[c] = e->origin[c] + mod->mins[c]; maxs[c] = e->origin[c] + mod->maxs[c]; }
+						if (!rc.world || !RC_VisCullEntity (rc.world->world, views[i].vieworg, mins, maxs))
+							continue;
+					}
+					inst = &rc.aliasscratch[nalias];
+					if (!RC_AliasSetup (mod->alias, rc.world ? rc.world->world : NULL, e, &views[i], v, &rc.cvars, inst))
+						continue;
+					inst->view = i;
+					inst->model = mod->alias->device_index;
+					inst->order = ++order;
+					inst->vertbase = nverts;
+					inst->tribase = 0;
+					inst->skin += 0;		/* picture index inside the model; the device table adds the base */
+					/* entity colormap (r_alias.c:770): NULL or the library's own -> vid.colormap */
+					inst->colormap = 0;
+					if (e->colormap && e->colormap != rc.colormap)
+					{
+						for (c = 1; c < ncmap; c++)
+							if (cmaps[c] == e->colormap) break;
+						if (c == ncmap)
+						{
+							if (ncmap >= 64) return rc_fail (RC_ERR_ARG, "more than 63 distinct entity colormaps in a batch");
+							cmaps[ncmap++] = e->colormap;
+						}
+						inst->colormap = c;
+					}
+					nverts += mod->alias->numverts;
+					nalias++;
+					used = 1;
+					if (order >= 32767) return rc_fail (RC_ERR_ARG, "view %d: too many alias entities", i);
+				}
+			for (j = 0; j < views[i].num_particles; j++, npart++)
+			{
+				rc_particle_t *p = &rc.partscratch[npart];
+				memcpy (p->org, views[i].particles[j].org, sizeof(float) * 3);
+				p->color = views[i].particles[j].color;
+				p->view = i; p->order = j; p->pad[0] = p->pad[1] = 0;
+				used = 1;
+			}
+			if (used)
+				v->zres_index = nzres++;
+		}
+		if (ncmap * 16384 > rc.cmapscratchcap)
+		{
+			free (rc.cmapscratch);
+			rc.cmapscratch = (uint8_t *)malloc ((size_t)ncmap * 16384);
+			rc.cmapscratchcap = rc.cmapscratch ? ncmap * 16384 : 0;
+			if (!rc.cmapscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+		}
+		memcpy (rc.cmapscratch, rc.colormap, 16384);
+		for (i = 1; i < ncmap; i++)
+			memcpy (rc.cmapscratch + (size_t)i * 16384, cmaps[i], 16384);
+		rc.batch.alias = rc.aliasscratch; rc.batch.nalias = nalias; rc.batch.nfinalverts = nverts; rc.batch.ntriwork = 0;
+		rc.batch.particles = rc.partscratch; rc.batch.nparticles = npart;
+		rc.batch.colormaps = rc.cmapscratch; rc.batch.ncolormaps = ncmap;
+		rc.batch.nzres = nzres;
+	}
 	rc.batch.views = rc.viewscratch; rc.batch.n = n;
 	rc.batch.dlights = rc.dlscratch; rc.batch.ndlights = ndl;
 	rc.batch.nwarp = nwarp;
@@ -281,7 +449,9 @@ int RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_ou
 	int r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
-	return rc_gpu_render_host (rc.gpu, &rc.batch, fb_out, z_out, status, rc.err, sizeof(rc.err));
+	r = rc_gpu_render_host (rc.gpu, &rc.batch, fb_out, z_out, status, rc.err, sizeof(rc.err));
+	if (status && rc.unsupported) *status |= RC_STAT_UNSUPPORTED_ENT;
+	return r;
 }
 
 int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
@@ -289,7 +459,9 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 	int r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
-	return rc_gpu_render (rc.gpu, &rc.batch, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
+	r = rc_gpu_render (rc.gpu, &rc.batch, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
+	if (status && rc.unsupported) *status |= RC_STAT_UNSUPPORTED_ENT;
+	return r;
 }
 
 void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }

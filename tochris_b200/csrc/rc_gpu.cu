@@ -64,6 +64,15 @@ struct rc_gpu_s {
 	float *d_chk; int *d_spanaux;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
+	/* alias models (uploaded blobs) and per-batch entity buffers */
+	rc_aliasmodel_t *d_amodels; int *d_stverts, *d_atris; uint8_t *d_poseverts, *d_skinpixels; float *d_anormdots;
+	int maxverts, maxtris;
+	rc_aliasinst_t *d_alias; int aliascap;
+	rc_finalvert_t *d_finalverts; int finalvertcap;
+	rc_particle_t *d_particles; int particlecap;
+	uint8_t *d_colormaps; int colormapcap;
+	unsigned long long *d_zres; size_t zrescap;
+	int16_t *d_zscratch; size_t zscratchcap;
 	rc_cachejob_t *d_jobs;
 	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
 	int *d_status;
@@ -76,6 +85,7 @@ struct rc_gpu_s {
 	long long launches_total;
 	cudaEvent_t ev[10];
 	int last_n;
+	const rc_batch_t *cur_batch;
 };
 
 /* ------------------------------------------------------------------------ kernels ----- */
@@ -397,6 +407,28 @@ __global__ void k_warp (const __grid_constant__ rc_world_t w, const __grid_const
 	rc_warp_pixel (&w, &f, vi, u, v);
 }
 
+__global__ void k_alias_verts (const __grid_constant__ rc_frame_t f)
+{
+	rc_alias_vertex (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k_alias_tris (const __grid_constant__ rc_frame_t f)
+{
+	rc_alias_triangle (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void k_particles (const __grid_constant__ rc_frame_t f)
+{
+	int pi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pi < f.nparticles)
+		rc_particle (&f, pi);
+}
+
+__global__ void k_zresolve (const __grid_constant__ rc_frame_t f)
+{
+	rc_zresolve_pixel (&f, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
+}
+
 __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -435,6 +467,9 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->device = device; g->width = width; g->height = height;
 	g->haveworld = false; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
+	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
+	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
+	g->d_particles = NULL; g->particlecap = 0; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->walk_lanes = getenv ("RC_WALK_LANES") ? atoi (getenv ("RC_WALK_LANES")) : 4;
 	if (g->walk_lanes < 1 || g->walk_lanes > 32) g->walk_lanes = 32;
 	cudaDeviceProp prop;
@@ -497,6 +532,51 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
 	delete g;
+}
+
+int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const float *anorm_dots, char *err, size_t errlen)
+{
+	std::vector<rc_aliasmodel_t> am;
+	std::vector<int> stv, tri;
+	std::vector<uint8_t> pose, skin;
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	g->maxverts = g->maxtris = 0;
+	for (int i = 0; i < n; i++)
+	{
+		rc_hostalias_t *a = models[i];
+		rc_aliasmodel_t m;
+		m.numverts = a->numverts; m.numtris = a->numtris; m.skinwidth = a->skinwidth; m.skinheight = a->skinheight;
+		m.stverts_ofs = (int)stv.size () / 4; m.tris_ofs = (int)tri.size () / 4;
+		m.poses_ofs = (int)pose.size () / 4; m.skins_ofs = (int)skin.size ();
+		stv.insert (stv.end (), a->stverts, a->stverts + 4 * a->numverts);
+		tri.insert (tri.end (), a->tris, a->tris + 4 * a->numtris);
+		pose.insert (pose.end (), a->poseverts, a->poseverts + 4 * (size_t)a->numposes * a->numverts);
+		skin.insert (skin.end (), a->skinpixels, a->skinpixels + (size_t)a->numskinpics * a->skinwidth * a->skinheight);
+		am.push_back (m);
+		a->device_index = i;
+		if (a->numverts > g->maxverts) g->maxverts = a->numverts;
+		if (a->numtris > g->maxtris) g->maxtris = a->numtris;
+	}
+	cudaFree (g->d_amodels); cudaFree (g->d_stverts); cudaFree (g->d_atris); cudaFree (g->d_poseverts);
+	cudaFree (g->d_skinpixels); cudaFree (g->d_anormdots);
+	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
+	CK (cudaMalloc (&g->d_amodels, sizeof(rc_aliasmodel_t) * (am.size () + 1)));
+	CK (cudaMalloc (&g->d_stverts, sizeof(int) * (stv.size () + 4)));
+	CK (cudaMalloc (&g->d_atris, sizeof(int) * (tri.size () + 4)));
+	CK (cudaMalloc (&g->d_poseverts, pose.size () + 16));
+	CK (cudaMalloc (&g->d_skinpixels, skin.size () + 16));
+	CK (cudaMalloc (&g->d_anormdots, sizeof(float) * 16 * 256));
+	if (n)
+	{
+		CK (cudaMemcpy (g->d_amodels, am.data (), sizeof(rc_aliasmodel_t) * am.size (), cudaMemcpyHostToDevice));
+		CK (cudaMemcpy (g->d_stverts, stv.data (), sizeof(int) * stv.size (), cudaMemcpyHostToDevice));
+		CK (cudaMemcpy (g->d_atris, tri.data (), sizeof(int) * tri.size (), cudaMemcpyHostToDevice));
+		CK (cudaMemcpy (g->d_poseverts, pose.data (), pose.size (), cudaMemcpyHostToDevice));
+		CK (cudaMemcpy (g->d_skinpixels, skin.data (), skin.size (), cudaMemcpyHostToDevice));
+	}
+	CK (cudaMemcpy (g->d_anormdots, anorm_dots, sizeof(float) * 16 * 256, cudaMemcpyHostToDevice));
+	return RC_OK;
 }
 
 int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen)
@@ -603,7 +683,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 }
 
 /* one chunk of views, everything asynchronous on `s` */
-static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, int16_t *zb, cudaStream_t s,
+static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int n, uint8_t *fb, int16_t *zb, cudaStream_t s,
 		      bool timed, char *err, size_t errlen)
 {
 	bool anywarp = false;
@@ -612,6 +692,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views; f.dlights = g->d_dlights;
+	f.viewbase = first_view;
 	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
@@ -660,6 +741,43 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int n, uint8_t *fb, 
 	if (timed) cudaEventRecord (g->ev[5], s);
 	k_spanprep<<<g->numsms * 8, 128, 0, s>>> (w, f);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+	if (g->cur_batch && g->cur_batch->nzres)
+	{
+		const rc_batch_t *b = g->cur_batch;
+		f.alias = g->d_alias; f.nalias = b->nalias; f.amodels = g->d_amodels; f.stverts = g->d_stverts; f.atris = g->d_atris;
+		f.poseverts = g->d_poseverts; f.skinpixels = g->d_skinpixels; f.anormdots = g->d_anormdots;
+		f.colormaps = g->d_colormaps; f.finalverts = g->d_finalverts; f.particles = g->d_particles; f.nparticles = b->nparticles;
+		f.zres = g->d_zres;
+		/* instances / particles of this chunk's views (both arrays are ordered by view) */
+		int alo = 0, ahi = b->nalias, plo = 0, phi = b->nparticles;
+		while (alo < b->nalias && b->alias[alo].view < first_view) alo++;
+		ahi = alo;
+		while (ahi < b->nalias && b->alias[ahi].view < first_view + n) ahi++;
+		while (plo < b->nparticles && b->particles[plo].view < first_view) plo++;
+		phi = plo;
+		while (phi < b->nparticles && b->particles[phi].view < first_view + n) phi++;
+		for (int first = alo; first < ahi; first += 32768)
+		{
+			/* grid.y = instance: at most 65535 per launch */
+			int cnt = ahi - first < 32768 ? ahi - first : 32768;
+			rc_frame_t f2 = f;
+			f2.alias = g->d_alias + first;
+			dim3 ga ((g->maxverts + 127) / 128, cnt), gt ((g->maxtris + 63) / 64, cnt);
+			k_alias_verts<<<ga, 128, 0, s>>> (f2);
+			k_alias_tris<<<gt, 64, 0, s>>> (f2);
+			g->stats.kernel_launches += 2;
+		}
+		if (phi > plo)
+		{
+			rc_frame_t f3 = f;
+			f3.particles = g->d_particles + plo; f3.nparticles = phi - plo;
+			k_particles<<<(phi - plo + 127) / 128, 128, 0, s>>> (f3);
+			g->stats.kernel_launches++;
+		}
+		dim3 gz ((g->width + 127) / 128, g->height, n);
+		k_zresolve<<<gz, 128, 0, s>>> (f);
+		g->stats.kernel_launches++;
+	}
 	if (anywarp)
 	{
 		dim3 gw2 ((g->width + 127) / 128, g->height, n);
@@ -731,6 +849,50 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		g->warpcap = batch->nwarp;
 		CK (cudaMalloc (&g->d_warpbuf, (size_t)g->warpcap * RC_WARP_W * RC_WARP_H));
 	}
+	if (batch->nalias > g->aliascap)
+	{
+		cudaFree (g->d_alias); g->aliascap = batch->nalias + 256;
+		CK (cudaMalloc (&g->d_alias, sizeof(rc_aliasinst_t) * g->aliascap));
+	}
+	if (batch->nfinalverts > g->finalvertcap)
+	{
+		cudaFree (g->d_finalverts); g->finalvertcap = batch->nfinalverts + 4096;
+		CK (cudaMalloc (&g->d_finalverts, sizeof(rc_finalvert_t) * (size_t)g->finalvertcap));
+	}
+	if (batch->nparticles > g->particlecap)
+	{
+		cudaFree (g->d_particles); g->particlecap = batch->nparticles + 4096;
+		CK (cudaMalloc (&g->d_particles, sizeof(rc_particle_t) * (size_t)g->particlecap));
+	}
+	if (batch->ncolormaps > g->colormapcap)
+	{
+		cudaFree (g->d_colormaps); g->colormapcap = batch->ncolormaps;
+		CK (cudaMalloc (&g->d_colormaps, (size_t)g->colormapcap * 16384));
+	}
+	if ((size_t)batch->nzres * px > g->zrescap)
+	{
+		cudaFree (g->d_zres); g->zrescap = (size_t)batch->nzres * px;
+		CK (cudaMalloc (&g->d_zres, sizeof(unsigned long long) * g->zrescap));
+	}
+	if (batch->nalias)
+		CK (cudaMemcpyAsync (g->d_alias, batch->alias, sizeof(rc_aliasinst_t) * batch->nalias, cudaMemcpyHostToDevice, s));
+	if (batch->nparticles)
+		CK (cudaMemcpyAsync (g->d_particles, batch->particles, sizeof(rc_particle_t) * batch->nparticles, cudaMemcpyHostToDevice, s));
+	if (batch->nzres)
+	{
+		CK (cudaMemcpyAsync (g->d_colormaps, batch->colormaps, (size_t)batch->ncolormaps * 16384, cudaMemcpyHostToDevice, s));
+		CK (cudaMemsetAsync (g->d_zres, 0, sizeof(unsigned long long) * (size_t)batch->nzres * px, s));
+	}
+	g->cur_batch = batch;
+	if (!z_dev && batch->nzres)
+	{
+		if (g->zscratchcap < px * n)
+		{
+			cudaFree (g->d_zscratch); g->zscratchcap = px * n;
+			CK (cudaMalloc (&g->d_zscratch, g->zscratchcap * sizeof(int16_t)));
+		}
+		z_dev = g->d_zscratch;
+	}
 	if (batch->ndlights)
 		CK (cudaMemcpyAsync (g->d_dlights, batch->dlights, sizeof(rc_dlight_t) * batch->ndlights, cudaMemcpyHostToDevice, s));
 	for (int attempt = 0; attempt < 4; attempt++)
@@ -742,7 +904,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		for (int first = 0; first < n; first += g->chunkcap)
 		{
 			int cn = n - first < g->chunkcap ? n - first : g->chunkcap;
-			r = run_chunk (g, views + first, cn, (uint8_t *)fb_dev + px * first,
+			r = run_chunk (g, views + first, first, cn, (uint8_t *)fb_dev + px * first,
 				       z_dev ? (int16_t *)z_dev + px * first : NULL, s, g->profiling != 0, err, errlen);
 			if (r != RC_OK) return r;
 			if (g->profiling || n > g->chunkcap)

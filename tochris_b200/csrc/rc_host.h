@@ -48,6 +48,28 @@ typedef struct rc_hostworld_s {
     int        numowned;
 } rc_hostworld_t;
 
+typedef struct {               /* maliasframedesc_t / maliasskindesc_t + group info, r_model.h:214-252 */
+    int type;                  /* 0 single, 1 group */
+    int first, count;          /* poses (or skin pictures) */
+    int intervals;             /* index into intervals[] for groups, else -1 */
+    unsigned char bboxmin[4], bboxmax[4];
+} rc_aliasframe_t;
+
+typedef struct rc_hostalias_s {  /* aliashdr_t + mdl_t, flattened */
+    int   numskins, skinwidth, skinheight, numverts, numtris, numframes, synctype, flags;
+    float scale[3], scale_origin[3];
+    float mins[3], maxs[3];
+    int   numposes, numskinpics;
+    int  *stverts;             /* [numverts][4]: onseam, s<<16, t<<16, 0 */
+    int  *tris;                /* [numtris][4]: facesfront, v0, v1, v2 */
+    unsigned char *poseverts;  /* [numposes][numverts] trivertx_t */
+    unsigned char *posebbox;   /* [numposes][8] */
+    unsigned char *skinpixels; /* [numskinpics][skinwidth*skinheight] */
+    rc_aliasframe_t *frames, *skins;
+    float *intervals;
+    int   device_index;        /* slot in the device model table, -1 until uploaded */
+} rc_hostalias_t;
+
 struct model_s {
     char          name[64];
     rc_modtype_t  type;
@@ -58,7 +80,8 @@ struct model_s {
     rc_hostworld_t *world;     /* shared by the world model and its '*n' submodels */
     int           submodel;    /* index into world->submodels */
     /* alias: filled by rc_host_alias.c */
-    void         *alias;
+    rc_hostalias_t *alias;
+    int           synctype;
 };
 
 int  RC_SetupView (const rc_refdef_t *rd, const rc_vidinfo_t *vid, const rc_cvars_t *cv, rc_view_t *out);
@@ -75,6 +98,13 @@ void RC_BuildTurbTables (int *sintable, int *intsintable, int n);
 rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *colormap, char *err, size_t errlen);
 void RC_FreeHostWorld (rc_hostworld_t *hw);
 
+rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, char *err, size_t errlen);
+void RC_FreeHostAlias (rc_hostalias_t *a);
+int  RC_LightPoint (const rc_hostworld_t *hw, const int *lightstylevalue, const float *p);
+int  RC_VisCullEntity (const rc_hostworld_t *hw, const float *vieworg, const float *mins, const float *maxs);
+int  RC_AliasSetup (const rc_hostalias_t *a, const rc_hostworld_t *hw, const entity_t *e, const rc_refdef_t *rd,
+                    const rc_view_t *v, const rc_cvars_t *cv, rc_aliasinst_t *out);
+
 /* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
 typedef struct rc_gpu_s rc_gpu_t;
 
@@ -83,10 +113,17 @@ typedef struct {
     const rc_view_t   *views;    int n;
     const rc_dlight_t *dlights;  int ndlights;
     int nwarp;                   /* views with r_dowarp (each needs a 320x200 warp buffer) */
+    const rc_aliasinst_t *alias; int nalias;      /* drawn alias entities, in (view, entity) order */
+    int nfinalverts, ntriwork;   /* totals over the instances */
+    const rc_particle_t *particles; int nparticles;
+    const uint8_t *colormaps;    int ncolormaps;  /* entity colormaps (16 KB each); 0 = vid.colormap */
+    int nzres;                   /* views that need an entity z-resolve plane */
 } rc_batch_t;
 
 rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen);
 void rc_gpu_destroy (rc_gpu_t *g);
+/* (re)uploads every loaded alias model; models[i]->device_index = i */
+int  rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const float *anorm_dots, char *err, size_t errlen);
 int  rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen);
 /* renders n prepared views; fb_dev/z_dev are device pointers (z may be NULL) */
 int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,

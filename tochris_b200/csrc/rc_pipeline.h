@@ -20,15 +20,20 @@
 #ifdef __CUDACC__
 #define RC_HD __device__ __forceinline__
 #define RC_HD2 __device__ __forceinline__
+#define RC_DEBUG_PRINT(...) do { } while (0)
 #define RC_LDG(p) __ldg (p)
 #define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
 #define RC_ATOMIC_MIN_I(p, v)   atomicMin ((p), (v))
+#define RC_ATOMIC_MAX_ULL(p, v) atomicMax ((p), (v))
 #define RC_ATOMIC_CAS_ULL(p, c, v) atomicCAS ((p), (c), (v))
 #else
 #define RC_HD static inline
 #define RC_HD2 inline
+#include <stdio.h>
+#include <stdlib.h>
+#define RC_DEBUG_PRINT(...) do { if (getenv ("RC_DEBUG")) fprintf (stderr, __VA_ARGS__); } while (0)
 #define RC_LDG(p) (*(p))
 static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
@@ -38,6 +43,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_ATOMIC_ADD_ULL(p, v) rc_host_add_ull ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    rc_host_or_i ((p), (v))
 #define RC_ATOMIC_MIN_I(p, v)   do { if ((v) < *(p)) *(p) = (v); } while (0)
+#define RC_ATOMIC_MAX_ULL(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
 #define RC_ATOMIC_CAS_ULL(p, c, v) rc_host_cas_ull ((p), (c), (v))
 #endif
 
@@ -54,6 +60,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 /* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
 typedef struct {
     int nviews, width, height;
+    int viewbase;                 /* batch index of views[0] (entities / particles carry batch view indices) */
     const rc_view_t *views;
     const rc_dlight_t *dlights;   /* all views' dynamic lights, indexed from rc_view_t.dlight_ofs */
     /* BSP walk */
@@ -79,6 +86,18 @@ typedef struct {
     /* outputs */
     uint8_t *fb; int16_t *zb;
     uint8_t *warpbuf;             /* [nwarp][320*200]: r_warpbuffer of the views that render under water */
+    /* alias models and particles */
+    const rc_aliasinst_t *alias; int nalias;
+    const rc_aliasmodel_t *amodels;
+    const int *stverts;           /* [..][4] */
+    const int *atris;             /* [..][4] */
+    const uint8_t *poseverts;     /* trivertx_t */
+    const uint8_t *skinpixels;
+    const float *anormdots;       /* r_avertexnormal_dots[16][256] */
+    const uint8_t *colormaps;     /* [ncolormaps][16384]; 0 = vid.colormap */
+    rc_finalvert_t *finalverts;
+    const rc_particle_t *particles; int nparticles;
+    unsigned long long *zres;     /* [nzres][height*width]: max over fragments of (z, draw order, colour) */
     int *status;
 } rc_frame_t;
 
@@ -1573,6 +1592,635 @@ RC_HD void rc_warp_pixel (const rc_world_t *w, const rc_frame_t *f, int vi, int 
 	const size_t o = (size_t)(vw->rd_y + v) * f->width + vw->rd_x + u;
 	if (o < viewpix)
 		f->fb[viewpix * vi + o] = src[srow * RC_WARP_W + scol];
+}
+
+
+/* ============================================================ alias models & particles ==== */
+#define RC_ALIAS_LEFT_CLIP   0x0001   /* r_shared.h:186-194 */
+#define RC_ALIAS_TOP_CLIP    0x0002
+#define RC_ALIAS_RIGHT_CLIP  0x0004
+#define RC_ALIAS_BOTTOM_CLIP 0x0008
+#define RC_ALIAS_Z_CLIP      0x0010
+#define RC_ALIAS_ONSEAM      0x0020
+#define RC_ALIAS_XY_CLIP_MASK 0x000F
+#define RC_ALIAS_Z_CLIP_PLANE 5
+
+/* One thread per (alias instance, vertex): R_AliasTransformAndProjectFinalVerts
+ * (r_alias.c:453-490) for trivially accepted models, else R_AliasTransformFinalVert +
+ * R_AliasProjectFinalVert + clip flags (r_alias.c:304-338,423-511). */
+RC_HD void rc_alias_vertex (const rc_frame_t *f, int ii, int vi_)
+{
+	const rc_aliasinst_t *in = &f->alias[ii];
+	const rc_aliasmodel_t *m = &f->amodels[in->model];
+	if (vi_ >= m->numverts)
+		return;
+	const rc_view_t *vw = &f->views[in->view - f->viewbase];
+	const uint8_t *pv1 = f->poseverts + 4 * ((size_t)m->poses_ofs + (size_t)in->pose_old * m->numverts + vi_);
+	const uint8_t *pv2 = f->poseverts + 4 * ((size_t)m->poses_ofs + (size_t)in->pose_new * m->numverts + vi_);
+	const int *st = f->stverts + 4 * ((size_t)m->stverts_ofs + vi_);
+	rc_finalvert_t *fv = &f->finalverts[in->vertbase + vi_];
+	const float lerp = in->framelerp;
+	float v[3];
+	v[0] = pv1[0] + lerp * ((float)pv2[0] - (float)pv1[0]);
+	v[1] = pv1[1] + lerp * ((float)pv2[1] - (float)pv1[1]);
+	v[2] = pv1[2] + lerp * ((float)pv2[2] - (float)pv1[2]);
+	const float *dots = f->anormdots + 256 * in->shadequant;
+	const float temp = dots[pv1[3]] + lerp * (dots[pv2[3]] - dots[pv1[3]]);
+	int light = rc_f2i (in->ambientlight - temp * in->shadelight);
+	if (light < 0)
+		light = 0;
+	fv->v[2] = st[1];
+	fv->v[3] = st[2];
+	fv->v[4] = light;
+	fv->flags = st[0];
+	if (in->trivial_accept)
+	{
+		const float zi = 1.0 / (rc_dot3 (v, in->xf[2]) + in->xf[2][3]);
+		fv->v[5] = rc_f2i (zi);
+		fv->v[0] = rc_f2i (((rc_dot3 (v, in->xf[0]) + in->xf[0][3]) * zi) + vw->aliasxcenter);
+		fv->v[1] = rc_f2i (((rc_dot3 (v, in->xf[1]) + in->xf[1][3]) * zi) + vw->aliasycenter);
+		return;
+	}
+	fv->av[0] = rc_dot3 (v, in->xf[0]) + in->xf[0][3];
+	fv->av[1] = rc_dot3 (v, in->xf[1]) + in->xf[1][3];
+	fv->av[2] = rc_dot3 (v, in->xf[2]) + in->xf[2][3];
+	if (fv->av[2] < RC_ALIAS_Z_CLIP_PLANE)
+	{
+		fv->flags |= RC_ALIAS_Z_CLIP;
+		fv->v[0] = fv->v[1] = fv->v[5] = 0;
+	}
+	else
+	{
+		const float zi = 1.0 / fv->av[2];
+		fv->v[5] = rc_f2i (zi * in->ziscale);
+		fv->v[0] = rc_f2i ((fv->av[0] * vw->aliasxscale * zi) + vw->aliasxcenter);
+		fv->v[1] = rc_f2i ((fv->av[1] * vw->aliasyscale * zi) + vw->aliasycenter);
+		if (fv->v[0] < vw->vrect_x) fv->flags |= RC_ALIAS_LEFT_CLIP;
+		if (fv->v[1] < vw->vrect_y) fv->flags |= RC_ALIAS_TOP_CLIP;
+		if (fv->v[0] > vw->vrectright) fv->flags |= RC_ALIAS_RIGHT_CLIP;
+		if (fv->v[1] > vw->vrectbottom) fv->flags |= RC_ALIAS_BOTTOM_CLIP;
+	}
+}
+
+typedef struct {
+	const rc_frame_t *f;
+	const rc_view_t *vw;
+	const uint8_t *skin;
+	const uint8_t *colormap;
+	unsigned long long *zplane;
+	int skinwidth, skinsize, seamfixupX16;
+	unsigned long long orderbits;	/* (order << 8), OR-ed under the z and over the colour */
+} rc_polyctx_t;
+
+/* D_PolysetSetUpForLineScan, d_polyse.c:279-310.  adivtab (ref_soft/adivtab.h) is the table of
+ * floor quotients / remainders for numerators and denominators in [-15,16] ({0,0} for a zero
+ * denominator); FloorDivMod (common/mathlib.c:416-455) handles the rest. */
+RC_HD void rc_line_scan_setup (int su, int sv, int eu, int ev, int *ubasestep, int *errorterm, int *adjup, int *adjdown)
+{
+	const int tm = eu - su, tn = ev - sv;
+	*errorterm = -1;
+	if (((tm <= 16) && (tm >= -15)) && ((tn <= 16) && (tn >= -15)))
+	{
+		int q = 0, r = 0;
+		if (tn != 0)
+		{
+			q = tm / tn; r = tm - q * tn;
+			if (r != 0 && ((r < 0) != (tn < 0))) { q--; r += tn; }	/* floor division */
+		}
+		*ubasestep = q; *adjup = r; *adjdown = tn;
+	}
+	else
+	{
+		const double numer = (double)tm, denom = (double)tn;
+		int q, r;
+		double x;
+		if (numer >= 0.0)
+		{
+			x = floor (numer / denom);
+			q = rc_d2i (x);
+			r = rc_d2i (floor (numer - (x * denom)));
+		}
+		else
+		{
+			x = floor (-numer / denom);
+			q = -rc_d2i (x);
+			r = rc_d2i (floor (-numer - (x * denom)));
+			if (r != 0)
+			{
+				q--;
+				r = rc_d2i (denom) - r;
+			}
+		}
+		*ubasestep = q; *adjup = r; *adjdown = rc_d2i (denom);
+	}
+}
+
+/* the twelve left/right edge orders of d_polyse.c:50-63: {numleft, l0, l1, l2, numright, r0, r1, r2} */
+RC_HD void rc_edge_table (int idx, int *t)
+{
+	const unsigned tab[12] = {
+		/* each entry: nibbles numleft,l0,l1,l2,numright,r0,r1,r2 (3 = unused) */
+		0x10232012u, 0x21021123u, 0x10231123u, 0x11032120u, 0x20211013u, 0x12131203u,
+		0x12132201u, 0x22101203u, 0x11031123u, 0x12131013u, 0x11031203u, 0x10231013u };
+	const unsigned e = tab[idx];
+	for (int i = 0; i < 8; i++)
+		t[i] = (e >> (28 - 4 * i)) & 15;
+}
+
+/* One triangle of D_DrawNonSubdiv (d_polyse.c:139-203): backface test, seam fix-up,
+ * D_PolysetSetEdgeTable (:713-767), D_RasterizeAliasPolySmooth (:454-706) with
+ * D_PolysetCalcGradients (:320-375), D_PolysetScanLeftEdge (:210-271) and
+ * D_PolysetDrawSpans8 (:385-447).  The reference scans the whole left side into span
+ * packages and then walks the right side; the two sides are independent, so here they are
+ * stepped together scanline by scanline.  Each pixel that the reference would z-test becomes
+ * one atomicMax of (z, draw order, colour) into the view's resolve plane. */
+RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, const int *fv1, int fl1,
+				const int *fv2, int fl2, int facesfront, int sub)
+{
+	const rc_frame_t *f = c->f;
+	const int d_xdenom = (fv0[1]-fv1[1]) * (fv0[0]-fv2[0]) - (fv0[0]-fv1[0])*(fv0[1]-fv2[1]);
+	if (d_xdenom >= 0)
+		return;
+	int P[3][6];
+	for (int i = 0; i < 6; i++) { P[0][i] = fv0[i]; P[1][i] = fv1[i]; P[2][i] = fv2[i]; }
+	if (!facesfront)
+	{
+		if (fl0 & RC_ALIAS_ONSEAM) P[0][2] += c->seamfixupX16;
+		if (fl1 & RC_ALIAS_ONSEAM) P[1][2] += c->seamfixupX16;
+		if (fl2 & RC_ALIAS_ONSEAM) P[2][2] += c->seamfixupX16;
+	}
+	/* D_PolysetSetEdgeTable */
+	int eti = 0, done = 0;
+	if (P[0][1] >= P[1][1])
+	{
+		if (P[0][1] == P[1][1]) { eti = (P[0][1] < P[2][1]) ? 2 : 5; done = 1; }
+		else eti = 1;
+	}
+	if (!done)
+	{
+		if (P[0][1] == P[2][1]) { eti = eti ? 8 : 9; done = 1; }
+		else if (P[1][1] == P[2][1]) { eti = eti ? 10 : 11; done = 1; }
+	}
+	if (!done)
+	{
+		if (P[0][1] > P[2][1]) eti += 2;
+		if (P[1][1] > P[2][1]) eti += 4;
+	}
+	int et[8];
+	rc_edge_table (eti, et);
+	const int numleft = et[0], numright = et[4];
+	const int *plefttop = P[et[1]], *pleftbottom = P[et[2]];
+	const int *prighttop = P[et[5]], *prightbottom = P[et[6]];
+	const int initialleftheight = pleftbottom[1] - plefttop[1];
+	const int initialrightheight = prightbottom[1] - prighttop[1];
+	const int skinwidth = c->skinwidth;
+
+	/* D_PolysetCalcGradients */
+	int r_lstepx, r_lstepy, r_sstepx, r_sstepy, r_tstepx, r_tstepy, r_zistepx, r_zistepy;
+	{
+		const float p00_minus_p20 = P[0][0] - P[2][0];
+		const float p01_minus_p21 = P[0][1] - P[2][1];
+		const float p10_minus_p20 = P[1][0] - P[2][0];
+		const float p11_minus_p21 = P[1][1] - P[2][1];
+		const float xstepdenominv = 1.0 / (float)d_xdenom;
+		const float ystepdenominv = -xstepdenominv;
+		float t0, t1;
+		t0 = P[0][4] - P[2][4];
+		t1 = P[1][4] - P[2][4];
+		r_lstepx = rc_d2i (ceil ((double)((t1 * p01_minus_p21 - t0 * p11_minus_p21) * xstepdenominv)));
+		r_lstepy = rc_d2i (ceil ((double)((t1 * p00_minus_p20 - t0 * p10_minus_p20) * ystepdenominv)));
+		t0 = P[0][2] - P[2][2];
+		t1 = P[1][2] - P[2][2];
+		r_sstepx = rc_f2i ((t1 * p01_minus_p21 - t0 * p11_minus_p21) * xstepdenominv);
+		r_sstepy = rc_f2i ((t1 * p00_minus_p20 - t0* p10_minus_p20) * ystepdenominv);
+		t0 = P[0][3] - P[2][3];
+		t1 = P[1][3] - P[2][3];
+		r_tstepx = rc_f2i ((t1 * p01_minus_p21 - t0 * p11_minus_p21) * xstepdenominv);
+		r_tstepy = rc_f2i ((t1 * p00_minus_p20 - t0 * p10_minus_p20) * ystepdenominv);
+		t0 = P[0][5] - P[2][5];
+		t1 = P[1][5] - P[2][5];
+		r_zistepx = rc_f2i ((t1 * p01_minus_p21 - t0 * p11_minus_p21) * xstepdenominv);
+		r_zistepy = rc_f2i ((t1 * p00_minus_p20 - t0 * p10_minus_p20) * ystepdenominv);
+	}
+	const int a_sstepxfrac = r_sstepx & 0xFFFF;
+	const int a_tstepxfrac = r_tstepx & 0xFFFF;
+	const int a_ststepxwhole = rc_addw (rc_mulw (skinwidth, r_tstepx >> 16), r_sstepx >> 16);
+
+	/* ---- left edge state (d_pdest / d_pz kept as x, y) ---- */
+	int lx, ly, l_aspancount, l_ptex, l_sfrac, l_tfrac, l_light, l_zi;
+	int l_ubasestep = 0, l_errorterm = 0, l_adjup = 0, l_adjdown = 0, l_countextrastep = 0;
+	int l_ptexbase = 0, l_ptexextra = 0, l_sfracbase = 0, l_sfracextra = 0, l_tfracbase = 0, l_tfracextra = 0;
+	int l_lightbase = 0, l_lightextra = 0, l_zibase = 0, l_ziextra = 0;
+	int l_remaining, l_segment = 1, l_stepping;
+#define RC_LEFT_SETUP(top, bottom, height)                                                             \
+	do {                                                                                           \
+		l_remaining = (height);                                                                \
+		l_stepping = (height) != 1;                                                            \
+		if (l_stepping) {                                                                      \
+			rc_line_scan_setup ((top)[0], (top)[1], (bottom)[0], (bottom)[1], &l_ubasestep, &l_errorterm, &l_adjup, &l_adjdown); \
+			const int working_lstepx = (l_ubasestep < 0) ? r_lstepx - 1 : r_lstepx;        \
+			l_countextrastep = l_ubasestep + 1;                                            \
+			l_ptexbase = rc_addw ((rc_addw (r_sstepy, rc_mulw (r_sstepx, l_ubasestep))) >> 16, \
+				rc_mulw ((rc_addw (r_tstepy, rc_mulw (r_tstepx, l_ubasestep))) >> 16, skinwidth)); \
+			l_sfracbase = rc_addw (r_sstepy, rc_mulw (r_sstepx, l_ubasestep)) & 0xFFFF;    \
+			l_tfracbase = rc_addw (r_tstepy, rc_mulw (r_tstepx, l_ubasestep)) & 0xFFFF;    \
+			l_lightbase = rc_addw (r_lstepy, rc_mulw (working_lstepx, l_ubasestep));       \
+			l_zibase = rc_addw (r_zistepy, rc_mulw (r_zistepx, l_ubasestep));              \
+			l_ptexextra = rc_addw ((rc_addw (r_sstepy, rc_mulw (r_sstepx, l_countextrastep))) >> 16, \
+				rc_mulw ((rc_addw (r_tstepy, rc_mulw (r_tstepx, l_countextrastep))) >> 16, skinwidth)); \
+			l_sfracextra = rc_addw (r_sstepy, rc_mulw (r_sstepx, l_countextrastep)) & 0xFFFF; \
+			l_tfracextra = rc_addw (r_tstepy, rc_mulw (r_tstepx, l_countextrastep)) & 0xFFFF; \
+			l_lightextra = rc_addw (l_lightbase, working_lstepx);                          \
+			l_ziextra = rc_addw (l_zibase, r_zistepx);                                     \
+		}                                                                                      \
+	} while (0)
+
+	lx = plefttop[0]; ly = plefttop[1];
+	l_aspancount = plefttop[0] - prighttop[0];
+	l_ptex = (plefttop[2] >> 16) + (plefttop[3] >> 16) * skinwidth;
+	l_sfrac = plefttop[2] & 0xFFFF;
+	l_tfrac = plefttop[3] & 0xFFFF;
+	l_light = plefttop[4];
+	l_zi = plefttop[5];
+	RC_LEFT_SETUP (plefttop, pleftbottom, initialleftheight);
+
+	/* ---- right edge state ---- */
+	int r_ubasestep, r_errorterm, r_adjup, r_adjdown, r_countextrastep, r_aspancount = 0;
+	int r_remaining = initialrightheight, r_segment = 1;
+	rc_line_scan_setup (prighttop[0], prighttop[1], prightbottom[0], prightbottom[1], &r_ubasestep, &r_errorterm, &r_adjup, &r_adjdown);
+	r_countextrastep = r_ubasestep + 1;
+	if (initialleftheight <= 0 || initialrightheight <= 0)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		return;
+	}
+	const int W = f->width, H = f->height;
+	int guard = 0;
+	for (;;)
+	{
+		if (r_remaining == 0)
+		{
+			if (r_segment == 1 && numright == 2)
+			{
+				/* d_polyse.c:683-704 */
+				const int *oldtop = prighttop, *oldbottom = prightbottom;
+				r_aspancount = oldbottom[0] - oldtop[0];
+				prighttop = oldbottom;
+				prightbottom = P[et[7]];
+				r_remaining = prightbottom[1] - prighttop[1];
+				rc_line_scan_setup (prighttop[0], prighttop[1], prightbottom[0], prightbottom[1], &r_ubasestep, &r_errorterm, &r_adjup, &r_adjdown);
+				r_countextrastep = r_ubasestep + 1;
+				r_segment = 2;
+				if (r_remaining <= 0)
+					break;
+			}
+			else
+				break;
+		}
+		if (l_remaining == 0)
+		{
+			if (l_segment == 1 && numleft == 2)
+			{
+				/* d_polyse.c:576-664: bottom part of the left edge; sfrac/tfrac restart at 0 (H4) */
+				const int *top = pleftbottom, *bottom = P[et[3]];
+				const int *rt0 = P[et[5]];
+				lx = top[0]; ly = top[1];
+				l_aspancount = top[0] - rt0[0];
+				l_ptex = (top[2] >> 16) + (top[3] >> 16) * skinwidth;
+				l_sfrac = 0;
+				l_tfrac = 0;
+				l_light = top[4];
+				l_zi = top[5];
+				RC_LEFT_SETUP (top, bottom, bottom[1] - top[1]);
+				l_segment = 2;
+				if (l_remaining <= 0)
+				{
+					RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+					break;
+				}
+			}
+			else
+			{
+				/* the reference would read span packages left over from an earlier triangle */
+				RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+				break;
+			}
+		}
+		if (++guard > 4096)
+			break;
+		/* D_PolysetDrawSpans8 for this scanline */
+		const int lcount = r_aspancount - l_aspancount;
+		r_errorterm += r_adjup;
+		if (r_errorterm >= 0)
+		{
+			r_aspancount += r_countextrastep;
+			r_errorterm -= r_adjdown;
+		}
+		else
+			r_aspancount += r_ubasestep;
+		r_remaining--;
+		if (lcount > 0)
+		{
+			int lptex = l_ptex, lsfrac = l_sfrac, ltfrac = l_tfrac, llight = l_light, lzi = l_zi;
+			int x = lx;
+			const int y = ly;
+			for (int n = lcount; n; n--, x++)
+			{
+				if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
+				{
+					int ti = lptex;
+					if ((unsigned)ti >= (unsigned)c->skinsize)
+					{
+						RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+						RC_DEBUG_PRINT ("skin index %d out of %d (sub %d, x %d y %d)\n", ti, c->skinsize, sub, x, y);
+						ti = 0;
+					}
+					int ci = c->skin[ti] + (llight & 0xFF00);
+					if (ci >= 64 * 256)
+					{
+						RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+						RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, llight);
+						ci &= 0x3FFF;
+					}
+					const unsigned long long key = ((unsigned long long)(unsigned)((lzi >> 16) + 32768) << 48) |
+						c->orderbits | ((unsigned long long)sub << 8) | c->colormap[ci];
+					RC_ATOMIC_MAX_ULL (&c->zplane[(size_t)y * W + x], key);
+				}
+				else
+					RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+				lzi = rc_addw (lzi, r_zistepx);
+				llight = rc_addw (llight, r_lstepx);
+				lptex += a_ststepxwhole;
+				lsfrac += a_sstepxfrac;
+				lptex += lsfrac >> 16;
+				lsfrac &= 0xFFFF;
+				ltfrac += a_tstepxfrac;
+				if (ltfrac & 0x10000)
+				{
+					lptex += skinwidth;
+					ltfrac &= 0xFFFF;
+				}
+			}
+		}
+		else if (lcount < 0)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		/* D_PolysetScanLeftEdge step */
+		l_remaining--;
+		if (l_stepping)
+		{
+			l_errorterm += l_adjup;
+			if (l_errorterm >= 0)
+			{
+				lx += l_ubasestep + 1; ly += 1;		/* d_pdestextrastep = screenwidth + ubasestep + 1 */
+				l_aspancount += l_countextrastep;
+				l_ptex += l_ptexextra;
+				l_sfrac += l_sfracextra;
+				l_ptex += l_sfrac >> 16;
+				l_sfrac &= 0xFFFF;
+				l_tfrac += l_tfracextra;
+				if (l_tfrac & 0x10000)
+				{
+					l_ptex += skinwidth;
+					l_tfrac &= 0xFFFF;
+				}
+				l_light = rc_addw (l_light, l_lightextra);
+				l_zi = rc_addw (l_zi, l_ziextra);
+				l_errorterm -= l_adjdown;
+			}
+			else
+			{
+				lx += l_ubasestep; ly += 1;
+				l_aspancount += l_ubasestep;
+				l_ptex += l_ptexbase;
+				l_sfrac += l_sfracbase;
+				l_ptex += l_sfrac >> 16;
+				l_sfrac &= 0xFFFF;
+				l_tfrac += l_tfracbase;
+				if (l_tfrac & 0x10000)
+				{
+					l_ptex += skinwidth;
+					l_tfrac &= 0xFFFF;
+				}
+				l_light = rc_addw (l_light, l_lightbase);
+				l_zi = rc_addw (l_zi, l_zibase);
+			}
+		}
+	}
+#undef RC_LEFT_SETUP
+}
+
+/* R_Alias_clip_{left,right,top,bottom} (r_aclip.c:96-185): edge 0 = left, 1 = right, 2 = top, 3 = bottom */
+RC_HD void rc_alias_clip_xy (const rc_view_t *vw, int which, const rc_finalvert_t *pfv0, const rc_finalvert_t *pfv1, rc_finalvert_t *out)
+{
+	const int comp = which < 2 ? 0 : 1;
+	const int bound = which == 0 ? vw->vrect_x : which == 1 ? vw->vrectright : which == 2 ? vw->vrect_y : vw->vrectbottom;
+	float scale;
+	if (pfv0->v[1] >= pfv1->v[1])
+	{
+		scale = (float)(bound - pfv0->v[comp]) / (pfv1->v[comp] - pfv0->v[comp]);
+		for (int i = 0; i < 6; i++)
+			out->v[i] = rc_d2i (pfv0->v[i] + (pfv1->v[i] - pfv0->v[i])*scale + 0.5);
+	}
+	else
+	{
+		scale = (float)(bound - pfv1->v[comp]) / (pfv0->v[comp] - pfv1->v[comp]);
+		for (int i = 0; i < 6; i++)
+			out->v[i] = rc_d2i (pfv1->v[i] + (pfv0->v[i] - pfv1->v[i])*scale + 0.5);
+	}
+}
+
+/* R_Alias_clip_z (r_aclip.c:46-91): pfv0 / pfv1 carry their auxvert in .av */
+RC_HD void rc_alias_clip_z (const rc_view_t *vw, float ziscale, const rc_finalvert_t *pfv0, const rc_finalvert_t *pfv1, rc_finalvert_t *out)
+{
+	float scale, avout[3];
+	const rc_finalvert_t *a = pfv0, *b = pfv1;
+	if (!(pfv0->v[1] >= pfv1->v[1])) { a = pfv1; b = pfv0; }
+	scale = (RC_ALIAS_Z_CLIP_PLANE - a->av[2]) / (b->av[2] - a->av[2]);
+	avout[0] = a->av[0] + (b->av[0] - a->av[0]) * scale;
+	avout[1] = a->av[1] + (b->av[1] - a->av[1]) * scale;
+	avout[2] = RC_ALIAS_Z_CLIP_PLANE;
+	out->v[2] = rc_f2i (a->v[2] + (b->v[2] - a->v[2]) * scale);
+	out->v[3] = rc_f2i (a->v[3] + (b->v[3] - a->v[3]) * scale);
+	out->v[4] = rc_f2i (a->v[4] + (b->v[4] - a->v[4]) * scale);
+	/* R_AliasProjectFinalVert */
+	const float zi = 1.0 / avout[2];
+	out->v[5] = rc_f2i (zi * ziscale);
+	out->v[0] = rc_f2i ((avout[0] * vw->aliasxscale * zi) + vw->aliasxcenter);
+	out->v[1] = rc_f2i ((avout[1] * vw->aliasyscale * zi) + vw->aliasycenter);
+	out->av[0] = avout[0]; out->av[1] = avout[1]; out->av[2] = avout[2];
+}
+
+/* R_AliasClip, r_aclip.c:190-228.  which: -1 = z plane, 0..3 screen edges */
+RC_HD int rc_alias_clip (const rc_view_t *vw, float ziscale, const rc_finalvert_t *in, rc_finalvert_t *out, int flag, int count, int which)
+{
+	int j = count - 1, k = 0;
+	for (int i = 0; i < count; j = i, i++)
+	{
+		const int oldflags = in[j].flags & flag;
+		const int flags = in[i].flags & flag;
+		if (flags && oldflags)
+			continue;
+		if (oldflags ^ flags)
+		{
+			if (which < 0) rc_alias_clip_z (vw, ziscale, &in[j], &in[i], &out[k]);
+			else rc_alias_clip_xy (vw, which, &in[j], &in[i], &out[k]);
+			out[k].flags = 0;
+			if (out[k].v[0] < vw->vrect_x) out[k].flags |= RC_ALIAS_LEFT_CLIP;
+			if (out[k].v[1] < vw->vrect_y) out[k].flags |= RC_ALIAS_TOP_CLIP;
+			if (out[k].v[0] > vw->vrectright) out[k].flags |= RC_ALIAS_RIGHT_CLIP;
+			if (out[k].v[1] > vw->vrectbottom) out[k].flags |= RC_ALIAS_BOTTOM_CLIP;
+			k++;
+		}
+		if (!flags)
+		{
+			out[k] = in[i];
+			k++;
+		}
+	}
+	return k;
+}
+
+/* One thread per (alias instance, triangle): the triangle loops of R_AliasPreparePoints
+ * (r_alias.c:340-362) / D_DrawNonSubdiv, including R_AliasClipTriangle (r_aclip.c:235-349). */
+RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti)
+{
+	const rc_aliasinst_t *in = &f->alias[ii];
+	const rc_aliasmodel_t *m = &f->amodels[in->model];
+	if (ti >= m->numtris)
+		return;
+	const rc_view_t *vw = &f->views[in->view - f->viewbase];
+	const int *tri = f->atris + 4 * ((size_t)m->tris_ofs + ti);
+	const rc_finalvert_t *pfv = f->finalverts + in->vertbase;
+	rc_polyctx_t c;
+	c.f = f; c.vw = vw;
+	c.skin = f->skinpixels + m->skins_ofs + (size_t)in->skin * m->skinwidth * m->skinheight;
+	c.colormap = f->colormaps + (size_t)in->colormap * 16384;
+	c.zplane = f->zres + (size_t)vw->zres_index * f->width * f->height;
+	c.skinwidth = m->skinwidth; c.skinsize = m->skinwidth * m->skinheight;
+	c.seamfixupX16 = (m->skinwidth >> 1) << 16;
+	c.orderbits = (((unsigned long long)in->order << 24) | ((unsigned long long)ti << 8)) << 8;
+	const rc_finalvert_t *a = &pfv[tri[1]], *b = &pfv[tri[2]], *d = &pfv[tri[3]];
+	const int facesfront = tri[0];
+	if (in->trivial_accept)
+	{
+		rc_polyset_triangle (&c, a->v, a->flags, b->v, b->flags, d->v, d->flags, facesfront, 0);
+		return;
+	}
+	if (a->flags & b->flags & d->flags & (RC_ALIAS_XY_CLIP_MASK | RC_ALIAS_Z_CLIP))
+		return;		/* completely clipped */
+	if (!((a->flags | b->flags | d->flags) & (RC_ALIAS_XY_CLIP_MASK | RC_ALIAS_Z_CLIP)))
+	{
+		rc_polyset_triangle (&c, a->v, a->flags, b->v, b->flags, d->v, d->flags, facesfront, 0);
+		return;
+	}
+	/* R_AliasClipTriangle */
+	rc_finalvert_t fv[2][8];
+	fv[0][0] = *a; fv[0][1] = *b; fv[0][2] = *d;
+	if (!facesfront)
+		for (int i = 0; i < 3; i++)
+			if (fv[0][i].flags & RC_ALIAS_ONSEAM)
+				fv[0][i].v[2] += c.seamfixupX16;
+	unsigned clipflags = fv[0][0].flags | fv[0][1].flags | fv[0][2].flags;
+	int k, pingpong;
+	if (clipflags & RC_ALIAS_Z_CLIP)
+	{
+		k = rc_alias_clip (vw, in->ziscale, fv[0], fv[1], RC_ALIAS_Z_CLIP, 3, -1);
+		if (k == 0)
+			return;
+		pingpong = 1;
+		clipflags = fv[1][0].flags | fv[1][1].flags | fv[1][2].flags;	/* first three only (H4) */
+	}
+	else
+	{
+		pingpong = 0;
+		k = 3;
+	}
+	const int order[4] = { RC_ALIAS_LEFT_CLIP, RC_ALIAS_RIGHT_CLIP, RC_ALIAS_BOTTOM_CLIP, RC_ALIAS_TOP_CLIP };
+	const int which[4] = { 0, 1, 3, 2 };
+	for (int s = 0; s < 4; s++)
+	{
+		if (clipflags & order[s])
+		{
+			k = rc_alias_clip (vw, in->ziscale, fv[pingpong], fv[pingpong ^ 1], order[s], k, which[s]);
+			if (k == 0)
+				return;
+			pingpong ^= 1;
+		}
+	}
+	for (int i = 0; i < k; i++)
+	{
+		rc_finalvert_t *p = &fv[pingpong][i];
+		if (p->v[0] < vw->vrect_x) p->v[0] = vw->vrect_x;
+		else if (p->v[0] > vw->vrectright) p->v[0] = vw->vrectright;
+		if (p->v[1] < vw->vrect_y) p->v[1] = vw->vrect_y;
+		else if (p->v[1] > vw->vrectbottom) p->v[1] = vw->vrectbottom;
+		p->flags = 0;
+	}
+	for (int i = 1; i < k - 1; i++)
+		rc_polyset_triangle (&c, fv[pingpong][0].v, 0, fv[pingpong][i].v, 0, fv[pingpong][i+1].v, 0, facesfront, i);
+}
+
+/* One thread per particle: D_DrawParticle (d_part.c:31-181) with r_pright/r_pup/r_ppn from
+ * R_DrawParticles (r_main.c:781-783). */
+RC_HD void rc_particle (const rc_frame_t *f, int pi)
+{
+	const rc_particle_t *p = &f->particles[pi];
+	const rc_view_t *vw = &f->views[p->view - f->viewbase];
+	float local[3], pright[3], pup[3], t[3];
+	for (int i = 0; i < 3; i++)
+	{
+		local[i] = p->org[i] - vw->origin[i];
+		pright[i] = vw->vright[i] * vw->xscaleshrink;
+		pup[i] = vw->vup[i] * vw->yscaleshrink;
+	}
+	t[2] = rc_dot3 (local, vw->vpn);
+	if (t[2] < 8.0)
+		return;
+	t[0] = rc_dot3 (local, pright);
+	t[1] = rc_dot3 (local, pup);
+	const float zi = 1.0 / t[2];
+	const int u = rc_f2i (vw->xcenter + zi * t[0]);
+	const int v = rc_f2i (vw->ycenter - zi * t[1]);
+	if ((v > vw->d_vrectbottom_particle) || (u > vw->d_vrectright_particle) || (v < vw->d_vrecty) || (u < vw->d_vrectx))
+		return;
+	const int izi = rc_f2i (zi * 0x8000);
+	int pix = izi >> vw->d_pix_shift;
+	if (pix < vw->d_pix_min) pix = vw->d_pix_min;
+	else if (pix > vw->d_pix_max) pix = vw->d_pix_max;
+	const int rows = pix << vw->d_y_aspect_shift;
+	unsigned long long *zplane = f->zres + (size_t)vw->zres_index * f->width * f->height;
+	const unsigned long long key = ((unsigned long long)(unsigned)(izi + 32768) << 48) |
+		((((unsigned long long)1 << 39) | (unsigned long long)p->order) << 8) | (unsigned long long)(p->color & 0xFF);
+	if (izi > 32767 || izi < -32768)
+		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+	for (int r = 0; r < rows; r++)
+		for (int i = 0; i < pix; i++)
+		{
+			const int x = u + i, y = v + r;
+			if ((unsigned)x < (unsigned)f->width && (unsigned)y < (unsigned)f->height)
+				RC_ATOMIC_MAX_ULL (&zplane[(size_t)y * f->width + x], key);
+		}
+}
+
+/* One thread per pixel of a view that drew alias models or particles: applies the winning
+ * fragment if it passes the reference's test against the world z (d_polyse.c:422, d_part.c:82). */
+RC_HD void rc_zresolve_pixel (const rc_frame_t *f, int vi, int x, int y)
+{
+	const rc_view_t *vw = &f->views[vi];
+	if (vw->zres_index < 0 || x >= f->width || y >= f->height)
+		return;
+	const size_t viewpix = (size_t)f->width * f->height;
+	const unsigned long long key = f->zres[(size_t)vw->zres_index * viewpix + (size_t)y * f->width + x];
+	if (!key)
+		return;
+	const int zf = (int)(key >> 48) - 32768;
+	int16_t *pz = f->zb + viewpix * vi + (size_t)vw->zwidth * y + x;
+	if (zf >= *pz)
+	{
+		*pz = (int16_t)zf;
+		uint8_t *base = vw->warp_index < 0 ? f->fb + viewpix * vi : f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H);
+		base[(size_t)vw->screenwidth * y + x] = (uint8_t)(key & 0xFF);
+	}
 }
 
 #endif /* RC_PIPELINE_H */

@@ -175,7 +175,8 @@ typedef struct {
     int   dlight_ofs;              /* first entry of this view in the batch's dlight array */
     int   warp_index;              /* r_dowarp: which 320x200 warp buffer this view renders into, else -1 */
     int   rd_x, rd_y, rd_w, rd_h;  /* r_refdef rectangle (D_WarpScreen target) */
-    int   pad1[2];
+    int   zres_index;              /* index of this view's entity z-resolve plane, -1: no alias models / particles */
+    int   pad1;
 } rc_view_t;
 
 /* dlight_t (client/ref.h:43-47) */
@@ -246,6 +247,49 @@ typedef struct {
     int pad2[3];
 } rc_cachejob_t;            /* 64 B */
 
+/* ---- alias models (MDL): ref_soft/r_alias.c, r_aclip.c, d_polyse.c ------------------------ */
+typedef struct {            /* one loaded model's slices of the shared device blobs */
+    int numverts, numtris, skinwidth, skinheight;
+    int stverts_ofs;        /* into stverts[] (int4: onseam, s<<16, t<<16, 0) */
+    int tris_ofs;           /* into tris[] (int4: facesfront, v0, v1, v2) */
+    int poses_ofs;          /* into poseverts[] (trivertx_t, 4 B each); pose p at poses_ofs + p*numverts */
+    int skins_ofs;          /* into skinpixels[]; skin k at skins_ofs + k*skinwidth*skinheight */
+} rc_aliasmodel_t;          /* 32 B */
+
+typedef struct {            /* one drawn alias entity of one view (host-prepared: R_DrawAliasModel, r_alias.c:734-788) */
+    int   view;
+    int   model;            /* index into the device model table */
+    int   trivial_accept;   /* R_AliasCheckBBox result (r_alias.c:135-296) */
+    int   order;            /* draw order of the entity inside its view (1-based) */
+    float xf[3][4];         /* aliastransform, pre-scaled when trivially accepted (r_alias.c:367-414) */
+    int   ambientlight;     /* r_ambientlight after R_AliasSetupLighting */
+    float shadelight;
+    int   shadequant;       /* row of r_avertexnormal_dots */
+    float framelerp;
+    int   pose_old, pose_new;
+    int   skin;             /* absolute offset of the skin in skinpixels[] */
+    float ziscale;
+    int   colormap;         /* index of the entity colormap in the batch's colormap table (0 = vid.colormap) */
+    int   vertbase;         /* first finalvert of this instance in the batch pool */
+    int   tribase;          /* first work item of this instance in the triangle work list */
+    int   pad;
+} rc_aliasinst_t;           /* 112 B */
+
+typedef struct {            /* finalvert_t, d_iface.h:37-41 (+ the auxvert_t view-space point) */
+    int   v[6];             /* u, v, s, t, l, 1/z */
+    int   flags;
+    float av[3];            /* auxvert_t.fv, r_local.h:37-39 (clipped path only) */
+    int   pad[2];
+} rc_finalvert_t;           /* 48 B */
+
+typedef struct {            /* particle_t (client/ref.h:37-41) + owning view */
+    float org[3];
+    int   color;
+    int   view;
+    int   order;            /* index within the view */
+    int   pad[2];
+} rc_particle_t;            /* 32 B */
+
 /* error / status bits returned through the C-ABI */
 #define RC_OK                    0
 #define RC_ERR_CUDA              (-1)
@@ -262,6 +306,8 @@ typedef struct {
 #define RC_STAT_CACHE_POOL       32  /* surface cache pool too small (retried by the host) */
 #define RC_STAT_STALE_CLIPVERT   64  /* reference would read r_rightenter/r_rightexit left over from an earlier face */
 #define RC_STAT_FACELIST         128 /* face list capacity exceeded */
+#define RC_STAT_UNSUPPORTED_ENT   256 /* a sprite / brush entity was skipped (not built yet) */
+#define RC_STAT_ALIAS_RANGE       512 /* alias rasteriser hit a case where the reference reads/loops out of range */
 
 #ifdef __cplusplus
 }
