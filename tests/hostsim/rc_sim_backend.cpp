@@ -122,7 +122,10 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	g->edges.assign ((size_t)n * f.edgecap, rc_edge_t ());
 	g->nedges.assign (n, 0);
 	f.edges = g->edges.data (); f.nedges = g->nedges.data ();
-	f.surfcap = f.facecap + 2;
+	f.bsurfcap = batch->nbents ? 512 : 0;
+	f.surfcap = f.facecap + 2 + f.bsurfcap;
+	std::vector<int> leafkey ((size_t)n * w->numleafs, 0), nbsurfs (n, 0);
+	f.leafkey = leafkey.data (); f.nbsurfs = nbsurfs.data (); f.bents = batch->bents; f.nbents = batch->nbents;
 	g->surfs.assign ((size_t)n * f.surfcap, rc_surf_t ());
 	f.surfs = g->surfs.data ();
 	f.spancap = n * g->height * 96;
@@ -157,12 +160,14 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p);
 	for (int vi = 0; vi < n; vi++)
 		for (int p = 0; p < nfaces[vi]; p++) rc_face_fixup (w, &f, vi, p);
+	for (int bi = 0; bi < batch->nbents; bi++)
+		for (int fi = 0; fi < batch->bents[bi].numfaces; fi++) rc_bmodel_face (w, &f, bi, fi);
 	for (int vi = 0; vi < n; vi++)
 		for (int line = 0; line < g->height; line++) rc_scan_line (w, &f, vi, line);
 	for (int vi = 0; vi < n; vi++)
-		for (int si = 1; si < nfaces[vi] + 2; si++) rc_surf_prep (w, &f, vi, si);
+		for (int i = 0, si; (si = rc_surf_slot (&f, vi, i)) >= 0; i++) rc_surf_prep (w, &f, vi, si);
 	for (int vi = 0; vi < n; vi++)
-		for (int si = 1; si < nfaces[vi] + 2; si++) rc_surf_resolve (&f, vi, si);
+		for (int i = 0, si; (si = rc_surf_slot (&f, vi, i)) >= 0; i++) rc_surf_resolve (&f, vi, si);
 	int njobs = (int)g->alloc[2];
 	if (njobs > f.jobcap) njobs = f.jobcap;
 	long long texels = 0;

@@ -47,13 +47,16 @@ def scene_info(name: str) -> dict:
     return _INFO[name]
 
 
-def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, entities: int = 0, particles: int = 0, **kw):
+def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, entities: int = 0, particles: int = 0,
+                doors: int = 0, **kw):
     if name == "box":
         vs = views.timerefresh_views((0, 0, 0), 128)[:n] if n <= 128 else views.timerefresh_views((0, 0, 0), n)
     else:
         vs = views.halton_views(scene_info(name), n, **kw)
     if dlights:
         add_dlights(vs, dlights)
+    if doors:
+        add_doors(vs, scene_info(name), doors)
     if entities:
         add_entities(vs, entities)
     if particles:
@@ -65,11 +68,32 @@ def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, 
     return vs
 
 
+def add_doors(specs, info, mode: int = 1):
+    """The map's door brush models ('*1', '*2', ...) as entities: mode 1 = in their doorways (clipped
+    to the world BSP), mode 2 = additionally slid / rotated per view, plus one floating in a room."""
+    import math
+    for i, sp in enumerate(specs):
+        ents = []
+        for d, org in enumerate(info.get("door_origins", [])):
+            o = list(org)
+            ang = (0.0, 0.0, 0.0)
+            if mode >= 2:
+                o[2] += 40.0 * views.halton(i * 7 + d + 1, 3)
+                if (i + d) % 3 == 1:
+                    ang = (0.0, 30.0 * views.halton(i + d + 1, 5), 0.0)
+                if (i + d) % 4 == 2:
+                    # carried into the middle of the camera's room: lies in a single leaf
+                    o = [sp.origin[0] + 90.0 * math.cos(math.radians(sp.angles[1])),
+                         sp.origin[1] + 90.0 * math.sin(math.radians(sp.angles[1])), 30.0]
+            ents.append(views.EntitySpec(f"*{d + 1}", tuple(o), ang, frame=(i + d) % 2))
+        sp.entities = ents + list(sp.entities)
+
+
 def add_entities(specs, k: int, near: float = 40.0):
     """k alias entities per view on a jittered ring in front of / around the camera."""
     import math
     for i, sp in enumerate(specs):
-        sp.entities = []
+        sp.entities = list(sp.entities)
         yaw = math.radians(sp.angles[1])
         for j in range(k):
             h = i * 53 + j * 11 + 3

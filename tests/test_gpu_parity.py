@@ -21,6 +21,8 @@ CASES = [
     ("full", 1280, 720, 6, 2.5, 0.5, dict(entities=64, particles=2048)),   # BASELINE config C3 (sample)
     ("multi", 320, 240, 48, 0.2, 0.05, dict(dlights=6)),                     # dynamic lights
     ("full", 640, 480, 12, 0.9, 0.11, dict(dlights=2, underwater_every=2, entities=12, particles=200)),  # warp + everything
+    ("full", 320, 240, 64, 0.37, 0.173, dict(doors=2, dlights=3)),           # brush entities: clipped to the BSP, rotated, in one leaf
+    ("full", 640, 480, 16, 1.1, 0.2, dict(doors=2, entities=10, particles=100, underwater_every=4)),
 ]
 
 

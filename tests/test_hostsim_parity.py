@@ -19,6 +19,8 @@ CASES = [
     ("full", 320, 200, 8, 0.9, 0.11, dict(dlights=2, underwater_every=2)),
     ("multi", 320, 240, 10, 0.3, 0.21, dict(entities=8, particles=120)),
     ("full", 640, 400, 4, 1.3, 0.4, dict(entities=20, particles=300, dlights=2, underwater_every=3)),
+    ("full", 320, 240, 24, 0.37, 0.173, dict(doors=2, dlights=2)),
+    ("full", 400, 300, 6, 2.0, 0.3, dict(doors=2, entities=6, particles=50)),
 ]
 
 

@@ -34,6 +34,7 @@ static struct {
 	rc_dlight_t *dlscratch; int dlscratchcap;
 	rc_aliasinst_t *aliasscratch; int aliasscratchcap;
 	rc_particle_t *partscratch; int partscratchcap;
+	rc_bent_t   *bentscratch; int bentscratchcap;
 	uint8_t     *cmapscratch; int cmapscratchcap;
 	float        anorm_dots[16 * 256];
 	int          alias_dirty;		/* alias models loaded since the last device upload */
@@ -149,7 +150,7 @@ void RC_Shutdown (void)
 	Mod_ClearAll ();
 	if (rc.gpu) rc_gpu_destroy (rc.gpu);
 	free (rc.viewscratch);
-	free (rc.dlscratch); free (rc.aliasscratch); free (rc.partscratch); free (rc.cmapscratch);
+	free (rc.dlscratch); free (rc.aliasscratch); free (rc.partscratch); free (rc.cmapscratch); free (rc.bentscratch);
 	memset (&rc, 0, sizeof(rc));
 }
 
@@ -281,7 +282,7 @@ int RC_LoadWorld (const char *name)
 /* ---- rendering --------------------------------------------------------------------------- */
 static int rc_prepare_views (const refdef_t *views, int n)
 {
-	int i, j, rcode, ndl, nwarp = 0;
+	int i, j, rcode, ndl, nwarp = 0, nbent_total = 0, nbents = 0, maxbfaces = 0;
 	rc.unsupported = 0;
 	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
 	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
@@ -294,7 +295,21 @@ static int rc_prepare_views (const refdef_t *views, int n)
 	}
 	ndl = 0;
 	for (i = 0; i < n; i++)
-		ndl += views[i].num_dlights > 0 ? views[i].num_dlights : 0;
+	{
+		int nd = views[i].num_dlights > 0 ? views[i].num_dlights : 0, nb = 0;
+		if (nd > MAX_DLIGHTS) return rc_fail (RC_ERR_ARG, "view %d: more than %d dlights", i, MAX_DLIGHTS);
+		for (j = 0; j < views[i].num_entities; j++)
+			if (views[i].entities[j].model && views[i].entities[j].model->type == rc_mod_brush) nb++;
+		ndl += nd * (1 + nb);
+		nbent_total += nb;
+	}
+	if (nbent_total > rc.bentscratchcap)
+	{
+		free (rc.bentscratch);
+		rc.bentscratch = (rc_bent_t *)malloc (sizeof(rc_bent_t) * nbent_total);
+		rc.bentscratchcap = rc.bentscratch ? nbent_total : 0;
+		if (!rc.bentscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	}
 	if (ndl > rc.dlscratchcap)
 	{
 		free (rc.dlscratch);
@@ -320,6 +335,51 @@ static int rc_prepare_views (const refdef_t *views, int n)
 		{
 			memcpy (rc.dlscratch[ndl].origin, views[i].dlights[j].origin, sizeof(float) * 3);
 			rc.dlscratch[ndl].radius = views[i].dlights[j].radius;
+		}
+		/* brush entities: R_DrawBEntitiesOnList, r_main.c:640-768 */
+		if (rc.cvars.r_drawentities && rc.world && !(views[i].flags & RDF_NOWORLDMODEL))
+		{
+			int border = 0, k;
+			for (j = 0; j < views[i].num_entities; j++)
+			{
+				const entity_t *e = &views[i].entities[j];
+				rc_bent_t *be;
+				if (!e->model || e->model->type != rc_mod_brush)
+					continue;
+				if (e->model->world != rc.world->world)
+					return rc_fail (RC_ERR_ARG, "view %d: brush entity %d does not belong to the loaded world", i, j);
+				be = &rc.bentscratch[nbents];
+				if (!RC_BmodelSetup (rc.world->world, e->model->submodel, e, &views[i], v, rc.vid.aspect, be))
+					continue;
+				be->view = i;
+				be->order = border++;
+				if (v->num_dlights)
+				{
+					/* r_main.c:708-735: the lights are moved into the entity's frame while it is marked and lit */
+					int rotated = (e->angles[0] || e->angles[1] || e->angles[2]);
+					float axis[3][3];
+					if (rotated)
+						RC_AngleVectors (e->angles, axis[0], axis[1], axis[2]);
+					be->dlight_ofs = ndl;
+					for (k = 0; k < v->num_dlights; k++, ndl++)
+					{
+						const dlight_t *l = &views[i].dlights[k];
+						float temp[3];
+						temp[0] = l->origin[0] - e->origin[0]; temp[1] = l->origin[1] - e->origin[1]; temp[2] = l->origin[2] - e->origin[2];
+						if (rotated)
+						{
+							rc.dlscratch[ndl].origin[0] = temp[0]*axis[0][0] + temp[1]*axis[0][1] + temp[2]*axis[0][2];
+							rc.dlscratch[ndl].origin[1] = -(temp[0]*axis[1][0] + temp[1]*axis[1][1] + temp[2]*axis[1][2]);
+							rc.dlscratch[ndl].origin[2] = temp[0]*axis[2][0] + temp[1]*axis[2][1] + temp[2]*axis[2][2];
+						}
+						else
+							memcpy (rc.dlscratch[ndl].origin, temp, sizeof(temp));
+						rc.dlscratch[ndl].radius = l->radius;
+					}
+				}
+				if (be->numfaces > maxbfaces) maxbfaces = be->numfaces;
+				nbents++;
+			}
 		}
 	}
 	/* ---- entities and particles (R_DrawEntitiesOnList r_main.c:489-533, R_DrawParticles :773) ---- */
@@ -441,6 +501,7 @@ static int rc_prepare_views (const refdef_t *views, int n)
 	rc.batch.views = rc.viewscratch; rc.batch.n = n;
 	rc.batch.dlights = rc.dlscratch; rc.batch.ndlights = ndl;
 	rc.batch.nwarp = nwarp;
+	rc.batch.bents = rc.bentscratch; rc.batch.nbents = nbents; rc.batch.maxbfaces = maxbfaces;
 	return RC_OK;
 }
 

@@ -73,6 +73,7 @@ struct rc_gpu_s {
 	uint8_t *d_colormaps; int colormapcap;
 	unsigned long long *d_zres; size_t zrescap;
 	int16_t *d_zscratch; size_t zscratchcap;
+	rc_bent_t *d_bents; int bentcap; int *d_leafkey; int *d_nbsurfs; int bsurfcap;
 	rc_cachejob_t *d_jobs;
 	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
 	int *d_status;
@@ -283,19 +284,24 @@ __global__ void k_scan_blocks (const __grid_constant__ rc_frame_t f, const rc_li
 		f.blockspan[li.blockbase + i] = -1;
 }
 
+__global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	rc_bmodel_face (&w, &f, f.bentbase + blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	int vi = blockIdx.x;
-	int si = 1 + blockIdx.y * blockDim.x + threadIdx.x;
-	if (si < f.nfaces[vi] + 2)
+	int si = rc_surf_slot (&f, vi, blockIdx.y * blockDim.x + threadIdx.x);
+	if (si >= 0)
 		rc_surf_prep (&w, &f, vi, si);
 }
 
 __global__ void k_resolve (const __grid_constant__ rc_frame_t f)
 {
 	int vi = blockIdx.x;
-	int si = 1 + blockIdx.y * blockDim.x + threadIdx.x;
-	if (si < f.nfaces[vi] + 2)
+	int si = rc_surf_slot (&f, vi, blockIdx.y * blockDim.x + threadIdx.x);
+	if (si >= 0)
 		rc_surf_resolve (&f, vi, si);
 }
 
@@ -470,6 +476,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
 	g->d_particles = NULL; g->particlecap = 0; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
+	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
 	g->walk_lanes = getenv ("RC_WALK_LANES") ? atoi (getenv ("RC_WALK_LANES")) : 4;
 	if (g->walk_lanes < 1 || g->walk_lanes > 32) g->walk_lanes = 32;
 	cudaDeviceProp prop;
@@ -508,6 +515,7 @@ static void free_chunk (rc_gpu_t *g)
 {
 	cudaFree (g->d_views); cudaFree (g->d_facelist); cudaFree (g->d_nfaces); cudaFree (g->d_facepos);
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
+	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
 	cudaFree (g->d_blockspan); cudaFree (g->d_jobs); cudaFree (g->d_lineinfo); cudaFree (g->d_aetpool); cudaFree (g->d_chk); cudaFree (g->d_spanaux);
 	g->d_views = NULL; g->chunkcap = 0;
@@ -635,14 +643,14 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 	       sizeof(rc_surf_t) * surfcap + (sizeof(rc_span_t) + 16) * spans + 16 * lines + 16 * blocks + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
-static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
+static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
 {
 	const rc_world_t *w = &g->w;
 	int facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
 	if (facecap < 1) facecap = 1;
-	int edgecap = g->maxedges, surfcap = facecap + 2;
+	int edgecap = g->maxedges, surfcap = facecap + 2 + want_bsurfs;
 	size_t freeb = 0, totalb = 0;
-	if (g->d_views && g->facecap == facecap && g->edgecap == edgecap && (g->chunkcap >= n || g->chunkcap == g->maxchunk))
+	if (g->d_views && g->facecap == facecap && g->edgecap == edgecap && g->bsurfcap == want_bsurfs && (g->chunkcap >= n || g->chunkcap == g->maxchunk))
 		return RC_OK;
 	cudaMemGetInfo (&freeb, &totalb);
 	size_t pv = per_view_bytes (g, facecap, edgecap, surfcap, w->numfaces);
@@ -654,7 +662,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 	int want = n < maxchunk ? n : maxchunk;
 	g->maxchunk = maxchunk;
 	free_chunk (g);
-	g->facecap = facecap; g->edgecap = edgecap; g->surfcap = surfcap;
+	g->facecap = facecap; g->edgecap = edgecap; g->surfcap = surfcap; g->bsurfcap = want_bsurfs;
 	size_t lines = (size_t)g->height * want;
 	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
 	size_t blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
@@ -668,6 +676,9 @@ static int ensure_chunk (rc_gpu_t *g, int n, char *err, size_t errlen)
 	CK (cudaMalloc (&g->d_facemark, sizeof(int) * (size_t)want * w->numfaces));
 	CK (cudaMalloc (&g->d_nodevisit, sizeof(rc_nodevisit_t) * (size_t)want * w->numnodes));
 	CK (cudaMalloc (&g->d_viewleaf, sizeof(int) * want));
+	CK (cudaMalloc (&g->d_nbsurfs, sizeof(int) * want));
+	if (want_bsurfs)
+		CK (cudaMalloc (&g->d_leafkey, sizeof(int) * (size_t)want * w->numleafs));
 	CK (cudaMalloc (&g->d_edges, sizeof(rc_edge_t) * (size_t)want * edgecap));
 	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
@@ -693,6 +704,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	memset (&f, 0, sizeof(f));
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views; f.dlights = g->d_dlights;
 	f.viewbase = first_view;
+	f.bents = g->d_bents; f.nbents = g->cur_batch ? g->cur_batch->nbents : 0;
+	f.leafkey = g->bsurfcap ? g->d_leafkey : NULL; f.nbsurfs = g->d_nbsurfs; f.bsurfcap = g->bsurfcap;
 	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
@@ -723,6 +736,23 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	dim3 gf (n, (g->facecap + 63) / 64);
 	k_faces<<<gf, 64, 0, s>>> (w, f);
 	k_fixup<<<gf, 64, 0, s>>> (w, f);
+	if (g->cur_batch && g->cur_batch->nbents)
+	{
+		const rc_batch_t *b = g->cur_batch;
+		int blo = 0, bhi;
+		while (blo < b->nbents && b->bents[blo].view < first_view) blo++;
+		bhi = blo;
+		while (bhi < b->nbents && b->bents[bhi].view < first_view + n) bhi++;
+		for (int first = blo; first < bhi; first += 32768)
+		{
+			int cnt = bhi - first < 32768 ? bhi - first : 32768;
+			rc_frame_t f2 = f;
+			f2.bentbase = first;	/* surf_t.entity indexes f.bents in the prep kernel: same base everywhere */
+			dim3 gb ((b->maxbfaces + 31) / 32, cnt);
+			k_bmodel<<<gb, 32, 0, s>>> (w, f2);
+			g->stats.kernel_launches++;
+		}
+	}
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
 	k_scan_sort<<<gs, SCAN_WARPS * 32, 0, s>>> (w, f, g->d_lineinfo, g->d_aetpool);
@@ -849,6 +879,13 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		g->warpcap = batch->nwarp;
 		CK (cudaMalloc (&g->d_warpbuf, (size_t)g->warpcap * RC_WARP_W * RC_WARP_H));
 	}
+	if (batch->nbents > g->bentcap)
+	{
+		cudaFree (g->d_bents); g->bentcap = batch->nbents + 256;
+		CK (cudaMalloc (&g->d_bents, sizeof(rc_bent_t) * g->bentcap));
+	}
+	if (batch->nbents)
+		CK (cudaMemcpyAsync (g->d_bents, batch->bents, sizeof(rc_bent_t) * batch->nbents, cudaMemcpyHostToDevice, s));
 	if (batch->nalias > g->aliascap)
 	{
 		cudaFree (g->d_alias); g->aliascap = batch->nalias + 256;
@@ -897,7 +934,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		CK (cudaMemcpyAsync (g->d_dlights, batch->dlights, sizeof(rc_dlight_t) * batch->ndlights, cudaMemcpyHostToDevice, s));
 	for (int attempt = 0; attempt < 4; attempt++)
 	{
-		int r = ensure_chunk (g, n, err, errlen);
+		int r = ensure_chunk (g, n, batch->nbents ? 512 : 0, err, errlen);
 		if (r != RC_OK) return r;
 		CK (cudaMemsetAsync (g->d_status, 0, sizeof(int), s));
 		st = 0;

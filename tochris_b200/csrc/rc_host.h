@@ -105,6 +105,11 @@ int  RC_VisCullEntity (const rc_hostworld_t *hw, const float *vieworg, const flo
 int  RC_AliasSetup (const rc_hostalias_t *a, const rc_hostworld_t *hw, const entity_t *e, const rc_refdef_t *rd,
                     const rc_view_t *v, const rc_cvars_t *cv, rc_aliasinst_t *out);
 
+/* R_DrawBEntitiesOnList per-entity setup (r_main.c:640-768); returns 1 when the entity is drawn */
+int  RC_BmodelSetup (const rc_hostworld_t *hw, int submodel, const entity_t *e, const rc_refdef_t *rd, const rc_view_t *v,
+                     float pixelAspect, rc_bent_t *out);
+int  RC_PointInLeaf (const rc_hostworld_t *hw, const float *p);
+
 /* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
 typedef struct rc_gpu_s rc_gpu_t;
 
@@ -118,6 +123,8 @@ typedef struct {
     const rc_particle_t *particles; int nparticles;
     const uint8_t *colormaps;    int ncolormaps;  /* entity colormaps (16 KB each); 0 = vid.colormap */
     int nzres;                   /* views that need an entity z-resolve plane */
+    const rc_bent_t *bents; int nbents;           /* drawn brush entities, ordered by (view, entity) */
+    int maxbfaces;               /* largest face count among them */
 } rc_batch_t;
 
 rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen);

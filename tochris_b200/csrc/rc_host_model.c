@@ -507,34 +507,43 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 		int *dfs_out = (int *)malloc (sizeof(int) * (w->numnodes + 2));
 		int sp = 0, counter = 0, norder = 0;
 		for (i = 0; i < w->numleafs; i++) leafdfs[i] = -1;
-		/* iterative pre-order from the world head node (model 0) */
-		stk[sp++] = hw->submodels[0].headnode;
-		while (sp)
+		/* iterative pre-order from every model's head node: model 0 is the world tree the walk
+		 * replays, the others are brush-entity trees (only R_MarkLights descends them) */
+		for (k = 0; k < hw->numsubmodels; k++)
 		{
-			int n = stk[--sp];
-			if (n < 0)
-			{
-				if (-1 - n != 0) leafdfs[-1 - n] = counter;	/* leaf 0 (solid) is shared: never numbered */
-				counter++;
+			int hn = hw->submodels[k].headnode;
+			if (hn < 0 || hn >= w->numnodes)
 				continue;
-			}
-			aux[n].dfs_in = counter++;
-			order[norder++] = n;
-			stk[sp++] = w->nodes[n].children[1];
-			stk[sp++] = w->nodes[n].children[0];
-		}
-		/* dfs_out and slot counts bottom-up (reverse pre-order) */
-		for (i = norder - 1; i >= 0; i--)
-		{
-			int n = order[i], out = aux[n].dfs_in + 1;
-			for (j = 0; j < 2; j++)
+			sp = 0; norder = 0;
+			if (k > 0) counter = 0;
+			stk[sp++] = hn;
+			while (sp)
 			{
-				int c = w->nodes[n].children[j];
-				if (c < 0) { aux[n].slots[j] = 1; out += 1; }
-				else { aux[n].slots[j] = aux[c].slots[0] + aux[c].slots[1] + w->nodes[c].numsurfaces + 1; out += dfs_out[c] - aux[c].dfs_in; }
-				if (j == 0) aux[n].dfs_mid = out;
+				int n = stk[--sp];
+				if (n < 0)
+				{
+					if (k == 0 && -1 - n != 0) leafdfs[-1 - n] = counter;	/* leaf 0 (solid) is shared: never numbered */
+					counter++;
+					continue;
+				}
+				aux[n].dfs_in = counter++;
+				order[norder++] = n;
+				stk[sp++] = w->nodes[n].children[1];
+				stk[sp++] = w->nodes[n].children[0];
 			}
-			dfs_out[n] = out;
+			/* dfs_mid and slot counts bottom-up (reverse pre-order) */
+			for (i = norder - 1; i >= 0; i--)
+			{
+				int n = order[i], out = aux[n].dfs_in + 1;
+				for (j = 0; j < 2; j++)
+				{
+					int c = w->nodes[n].children[j];
+					if (c < 0) { aux[n].slots[j] = 1; out += 1; }
+					else { aux[n].slots[j] = aux[c].slots[0] + aux[c].slots[1] + w->nodes[c].numsurfaces + 1; out += dfs_out[c] - aux[c].dfs_in; }
+					if (j == 0) aux[n].dfs_mid = out;
+				}
+				dfs_out[n] = out;
+			}
 		}
 		free (stk); free (order); free (dfs_out);
 		w->nodeaux = aux;

@@ -97,6 +97,12 @@ typedef struct {
     const uint8_t *colormaps;     /* [ncolormaps][16384]; 0 = vid.colormap */
     rc_finalvert_t *finalverts;
     const rc_particle_t *particles; int nparticles;
+    /* brush entities */
+    const rc_bent_t *bents; int nbents;
+    int bentbase;                 /* first brush entity handled by this launch */
+    int *leafkey;                 /* [nviews][numleafs]: BSP key of every leaf the walk reached (mleaf_t.key) */
+    int *nbsurfs;                 /* [nviews]: surf_t slots handed to brush-entity fragments */
+    int bsurfcap;                 /* per view; their slots start at facecap + 2 */
     unsigned long long *zres;     /* [nzres][height*width]: max over fragments of (z, draw order, colour) */
     int *status;
 } rc_frame_t;
@@ -178,6 +184,8 @@ RC_HD void rc_view_begin (const rc_world_t *w, const rc_frame_t *f, int vi)
 	bg->d_ziorigin = 0; bg->d_zistepu = 0; bg->d_zistepv = 0;
 	f->nedges[vi] = 0;
 	f->nfaces[vi] = 0;
+	if (f->nbsurfs)
+		f->nbsurfs[vi] = 0;
 	int n = 0;
 	while (n >= 0)
 	{
@@ -246,6 +254,8 @@ RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
 			const rc_leaf_t *lf = &w->leafs[L];
 			if (!rc_cull_box (v, lf->minmaxs, &clipflags))
 				return;
+			if (f->leafkey)
+				f->leafkey[(size_t)vi * w->numleafs + L] = key;
 			int *facemark = f->facemark + (size_t)vi * w->numfaces;
 			for (int m = 0; m < lf->nummarks; m++)
 				RC_ATOMIC_MIN_I (&facemark[w->marksurfaces[lf->firstmark + m]], key);
@@ -289,13 +299,17 @@ typedef struct {
 } rc_evert_t;
 
 /* transform and project one end point, r_rast.c:236-262 */
-RC_HD void rc_project (const rc_view_t *vw, const float *world, rc_evert_t *o)
+RC_HD const rc_xform_t *rc_view_xform (const rc_view_t *vw) { return (const rc_xform_t *)(const void *)vw->vpn; }
+
+RC_HD void rc_project (const rc_view_t *vw, const rc_xform_t *xf, const float *world, rc_evert_t *o)
 {
 	float local[3], t[3];
-	local[0] = world[0] - vw->origin[0];
-	local[1] = world[1] - vw->origin[1];
-	local[2] = world[2] - vw->origin[2];
-	rc_transform_vector (vw, local, t);
+	local[0] = world[0] - xf->origin[0];
+	local[1] = world[1] - xf->origin[1];
+	local[2] = world[2] - xf->origin[2];
+	t[0] = rc_dot3 (local, xf->vright);
+	t[1] = rc_dot3 (local, xf->vup);
+	t[2] = rc_dot3 (local, xf->vpn);
 	if (t[2] < RC_NEAR_CLIP)
 		t[2] = RC_NEAR_CLIP;
 	float lzi = 1.0 / t[2];
@@ -332,7 +346,7 @@ typedef struct {
  * (r_rast.c:213-383) for one polygon edge p0->p1 against the planes in `mask`
  * (bit i = view_clipplanes[i], tested in ascending i).  Pure: returns what the reference
  * would have written to its globals. */
-RC_HD void rc_clip_emit (const rc_view_t *vw, const float *p0in, const float *p1in, int mask,
+RC_HD void rc_clip_emit (const rc_view_t *vw, const rc_xform_t *xf, const float *p0in, const float *p1in, int mask,
 			 int nearzionly, rc_clipres_t *r)
 {
 	float p0[3], p1[3];
@@ -348,9 +362,9 @@ RC_HD void rc_clip_emit (const rc_view_t *vw, const float *p0in, const float *p1
 	{
 		if (!(mask & (1 << i)))
 			continue;
-		const float *nrm = vw->clipnormal[i];
-		float d0 = rc_dot3 (p0, nrm) - vw->clipdist[i];
-		float d1 = rc_dot3 (p1, nrm) - vw->clipdist[i];
+		const float *nrm = xf->clipnormal[i];
+		float d0 = rc_dot3 (p0, nrm) - xf->clipdist[i];
+		float d1 = rc_dot3 (p1, nrm) - xf->clipdist[i];
 		if (d0 >= 0)
 		{
 			if (d1 >= 0)
@@ -390,8 +404,8 @@ RC_HD void rc_clip_emit (const rc_view_t *vw, const float *p0in, const float *p1
 
 	/* R_EmitEdge */
 	rc_evert_t e0, e1;
-	rc_project (vw, p0, &e0);
-	rc_project (vw, p1, &e1);
+	rc_project (vw, xf, p0, &e0);
+	rc_project (vw, xf, p1, &e1);
 	float lzi0 = e0.lzi;
 	if (e1.lzi > lzi0)
 		lzi0 = e1.lzi;
@@ -482,7 +496,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 			int pm = pl > 0 ? pl : -pl;
 			const float *pa = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 0 : 1)]];
 			const float *pb = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 1 : 0)]];
-			rc_clip_emit (vw, pa, pb, list[q].clipflags, 0, &r);
+			rc_clip_emit (vw, rc_view_xform (vw), pa, pb, list[q].clipflags, 0, &r);
 			if (r.cls == RC_CLS_FULLCLIP)
 				continue;
 			if (r.cls == RC_CLS_CACHED)
@@ -495,7 +509,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 			}
 		}
 
-		rc_clip_emit (vw, va, vb, clipflags, 0, &r);
+		rc_clip_emit (vw, rc_view_xform (vw), va, vb, clipflags, 0, &r);
 		if (r.have_leftenter) { have_le = 1; leftenter[0] = r.leftenter[0]; leftenter[1] = r.leftenter[1]; leftenter[2] = r.leftenter[2]; }
 		if (r.have_leftexit) { have_lx = 1; leftexit[0] = r.leftexit[0]; leftexit[1] = r.leftexit[1]; leftexit[2] = r.leftexit[2]; }
 		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
@@ -532,7 +546,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 		int mask = clipflags & ~((2 << first) - 1);
 		if (!have_le || !have_lx)
 			RC_ATOMIC_OR_I (f->status, RC_STAT_STALE_CLIPVERT);
-		rc_clip_emit (vw, leftexit, leftenter, mask, 0, &r);
+		rc_clip_emit (vw, rc_view_xform (vw), leftexit, leftenter, mask, 0, &r);
 		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
 		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
 		if (r.reached_emit && r.nearzi > nearzi)
@@ -562,7 +576,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 		/* r_rast.c:669-675: only the effect on r_nearzi is wanted; planes after the right one */
 		if (have_re && have_rx)
 		{
-			rc_clip_emit (vw, rightexit, rightenter, clipflags & 0xC, 1, &r);
+			rc_clip_emit (vw, rc_view_xform (vw), rightexit, rightenter, clipflags & 0xC, 1, &r);
 			if (r.reached_emit && r.nearzi > nearzi)
 				nearzi = r.nearzi;
 		}
@@ -643,9 +657,309 @@ RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int 
 	if (surf->flags == -1)
 		return;
 	rc_clipres_t r;
-	rc_clip_emit (vw, rx, re, list[p].clipflags & 0xC, 1, &r);
+	rc_clip_emit (vw, rc_view_xform (vw), rx, re, list[p].clipflags & 0xC, 1, &r);
 	if (r.reached_emit && r.nearzi > surf->nearzi)
 		surf->nearzi = r.nearzi;
+}
+
+/* ------------------------------------------------------------- stage 2b: brush entities -- */
+#define RC_BMODEL_VERTS 96      /* reference: MAX_BMODEL_VERTS 500 / MAX_BMODEL_EDGES 1000 per face (r_bsp.c:41-42) */
+#define RC_BMODEL_EDGES 192
+#define RC_BMODEL_SEQ_BASE (1 << 25)
+
+typedef struct {
+	const rc_world_t *w;
+	const rc_frame_t *f;
+	const rc_view_t *vw;
+	const rc_bent_t *be;
+	int vi;			/* chunk-local view index */
+	int bi;			/* index of the brush entity in f->bents */
+	int face;		/* world face index of psurf */
+	int facei;		/* index of the face inside the submodel */
+	int frag;		/* R_RenderBmodelFace / R_RenderFace calls made for this face so far */
+	float bverts[RC_BMODEL_VERTS][3];
+	int numbverts;
+} rc_bctx_t;
+
+RC_HD const float *rc_bvert (const rc_bctx_t *c, int idx)
+{
+	return idx < 0 ? &c->w->vertexes[3 * (-1 - idx)] : c->bverts[idx];
+}
+
+/* R_RenderBmodelFace (r_rast.c:723-826) and, for entities that lie in a single leaf,
+ * R_RenderFace with insubmodel set (r_rast.c:518-716, no edge cache): pushes `n` polygon edges
+ * through the entity's clip planes and posts one surf_t whose key is the leaf's key. */
+RC_HD void rc_bmodel_emit (rc_bctx_t *c, const int *ev0, const int *ev1, int n, int clipflags, int key)
+{
+	const rc_frame_t *f = c->f;
+	const rc_view_t *vw = c->vw;
+	const rc_xform_t *xf = &c->be->x;
+	const rc_face_t *fa = &c->w->faces[c->face];
+	const int frag = c->frag++;
+	if (frag > 255 || n > RC_MAX_FACE_EDGES)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+		return;
+	}
+	int slot = RC_ATOMIC_ADD_I (&f->nbsurfs[c->vi], 1);
+	if (slot >= f->bsurfcap)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_SURF_OVERFLOW);
+		return;
+	}
+	const int surfidx = f->facecap + 2 + slot;
+	rc_surf_t *surf = f->surfs + (size_t)c->vi * f->surfcap + surfidx;
+	surf->flags = -1;
+	surf->hasspans = 0;
+	surf->miplevel = 0;
+	const uint32_t seq = (uint32_t)RC_BMODEL_SEQ_BASE + (((uint32_t)c->be->order & 127) << 18) + (((uint32_t)c->facei & 1023) << 8) + (uint32_t)frag;
+	if (c->be->order > 127 || c->facei > 1023)
+		RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+	rc_edge_t eb[RC_MAX_FACE_EDGES + 1];
+	int neb = 0, emitted = 0, makeleft = 0, makeright = 0;
+	float nearzi = 0;
+	float leftenter[3] = {0,0,0}, leftexit[3] = {0,0,0}, rightenter[3] = {0,0,0}, rightexit[3] = {0,0,0};
+	int have_le = 0, have_lx = 0, have_re = 0, have_rx = 0;
+	rc_clipres_t r;
+	for (int i = 0; i < n; i++)
+	{
+		rc_clip_emit (vw, xf, rc_bvert (c, ev0[i]), rc_bvert (c, ev1[i]), clipflags, 0, &r);
+		if (r.have_leftenter) { have_le = 1; leftenter[0] = r.leftenter[0]; leftenter[1] = r.leftenter[1]; leftenter[2] = r.leftenter[2]; }
+		if (r.have_leftexit) { have_lx = 1; leftexit[0] = r.leftexit[0]; leftexit[1] = r.leftexit[1]; leftexit[2] = r.leftexit[2]; }
+		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
+		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
+		if (r.leftclipped) makeleft = 1;
+		if (r.rightclipped) makeright = 1;
+		if (r.reached_emit && r.nearzi > nearzi) nearzi = r.nearzi;
+		if (r.emitted) emitted = 1;
+		if (r.made_edge)
+		{
+			rc_edge_t *e = &eb[neb++];
+			e->u = r.u; e->u_step = r.u_step; e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
+			e->surfs[0] = r.trailing ? surfidx : 0;
+			e->surfs[1] = r.trailing ? 0 : surfidx;
+			e->rank = ((uint32_t)r.trailing << 31) | (seq << 5) | (uint32_t)i;
+			e->pad[0] = e->pad[1] = e->pad[2] = 0;
+		}
+	}
+	if (makeleft)
+	{
+		int first = 0;
+		while (!(clipflags & (1 << first))) first++;
+		if (!have_le || !have_lx)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_STALE_CLIPVERT);
+		rc_clip_emit (vw, xf, leftexit, leftenter, clipflags & ~((2 << first) - 1), 0, &r);
+		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
+		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
+		if (r.reached_emit && r.nearzi > nearzi) nearzi = r.nearzi;
+		if (r.emitted) emitted = 1;
+		if (r.made_edge)
+		{
+			rc_edge_t *e = &eb[neb++];
+			e->u = r.u; e->u_step = r.u_step; e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
+			e->surfs[0] = r.trailing ? surfidx : 0;
+			e->surfs[1] = r.trailing ? 0 : surfidx;
+			e->rank = ((uint32_t)r.trailing << 31) | (seq << 5) | 31u;
+			e->pad[0] = e->pad[1] = e->pad[2] = 0;
+		}
+	}
+	if (makeright)
+	{
+		if (!have_re || !have_rx)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_STALE_CLIPVERT);
+		else
+		{
+			rc_clip_emit (vw, xf, rightexit, rightenter, clipflags & 0xC, 1, &r);
+			if (r.reached_emit && r.nearzi > nearzi) nearzi = r.nearzi;
+		}
+	}
+	if (neb)
+	{
+		int base = RC_ATOMIC_ADD_I (&f->nedges[c->vi], neb);
+		if (base + neb > f->edgecap)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
+		else
+		{
+			rc_edge_t *dst = f->edges + (size_t)c->vi * f->edgecap + base;
+			for (int i = 0; i < neb; i++)
+				dst[i] = eb[i];
+		}
+	}
+	if (!emitted)
+		return;
+	const rc_plane_t *pplane = &c->w->planes[fa->plane];
+	float p_normal[3];
+	p_normal[0] = rc_dot3 (pplane->normal, xf->vright);
+	p_normal[1] = rc_dot3 (pplane->normal, xf->vup);
+	p_normal[2] = rc_dot3 (pplane->normal, xf->vpn);
+	float distinv = 1.0 / (pplane->dist - rc_dot3 (xf->origin, pplane->normal));
+	surf->key = key;
+	surf->flags = fa->flags;
+	surf->face = c->face;
+	surf->insubmodel = 1;
+	surf->entity = c->bi;
+	surf->nearzi = nearzi;
+	surf->d_zistepu = p_normal[0] * vw->xscaleinv * distinv;
+	surf->d_zistepv = -p_normal[1] * vw->yscaleinv * distinv;
+	surf->d_ziorigin = p_normal[2] * distinv - vw->xcenter * surf->d_zistepu - vw->ycenter * surf->d_zistepv;
+}
+
+/* One thread per (brush entity, face): the face loops of R_DrawSubmodelPolygons (r_bsp.c:401-427)
+ * and R_DrawSolidClippedSubmodelPolygons (r_bsp.c:319-394) with R_RecursiveClipBPoly
+ * (r_bsp.c:161-311): the polygon is split by the world BSP planes below the entity's top node so
+ * that every fragment inherits the sort key of the world leaf it lies in. */
+RC_HD void rc_bmodel_face (const rc_world_t *w, const rc_frame_t *f, int bi, int facei)
+{
+	const rc_bent_t *be = &f->bents[bi];
+	if (facei >= be->numfaces)
+		return;
+	const int vi = be->view - f->viewbase;
+	const rc_view_t *vw = &f->views[vi];
+	const int face = be->firstface + facei;
+	const rc_face_t *psurf = &w->faces[face];
+	const rc_plane_t *pplane = &w->planes[psurf->plane];
+	const float dot = rc_plane_diff (be->x.origin, pplane);
+	if (!(((psurf->flags & RC_SURF_PLANEBACK) && (dot < -RC_BACKFACE_EPSILON)) ||
+	      (!(psurf->flags & RC_SURF_PLANEBACK) && (dot > RC_BACKFACE_EPSILON))))
+		return;
+	if (psurf->numedges > RC_MAX_FACE_EDGES || psurf->numedges < 1)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+		return;
+	}
+	rc_bctx_t c;
+	c.w = w; c.f = f; c.vw = vw; c.be = be; c.vi = vi; c.bi = bi; c.face = face; c.facei = facei; c.frag = 0; c.numbverts = 0;
+	const int *leafkey = f->leafkey + (size_t)vi * w->numleafs;
+	int ev0[RC_MAX_FACE_EDGES + 2], ev1[RC_MAX_FACE_EDGES + 2];
+
+	if (be->topnode < 0)
+	{
+		/* falls entirely in one leaf: all edges go in, 1/z sorting handles the order */
+		for (int j = 0; j < psurf->numedges; j++)
+		{
+			const int lindex = w->surfedges[psurf->firstedge + j];
+			const int m = lindex > 0 ? lindex : -lindex;
+			ev0[j] = -1 - (int)w->edges[2 * m + (lindex > 0 ? 0 : 1)];
+			ev1[j] = -1 - (int)w->edges[2 * m + (lindex > 0 ? 1 : 0)];
+		}
+		rc_bmodel_emit (&c, ev0, ev1, psurf->numedges, be->clipflags, leafkey[-1 - be->topnode]);
+		return;
+	}
+
+	/* bedge_t lists as index-linked arrays (r_local.h:31-35) */
+	int e_v0[RC_BMODEL_EDGES], e_v1[RC_BMODEL_EDGES], e_next[RC_BMODEL_EDGES];
+	int numbedges = psurf->numedges;
+	for (int j = 0; j < psurf->numedges; j++)
+	{
+		const int lindex = w->surfedges[psurf->firstedge + j];
+		const int m = lindex > 0 ? lindex : -lindex;
+		e_v0[j] = -1 - (int)w->edges[2 * m + (lindex > 0 ? 0 : 1)];
+		e_v1[j] = -1 - (int)w->edges[2 * m + (lindex > 0 ? 1 : 0)];
+		e_next[j] = j + 1;
+	}
+	e_next[psurf->numedges - 1] = -1;
+	const uint32_t *vis = w->nodevis + (size_t)f->viewleaf[vi] * w->visrowwords;
+	int st_head[64], st_node[64], sp = 0;
+	int pfrontenter = 0, pfrontexit = 0;		/* file statics in the reference */
+	st_head[sp] = 0; st_node[sp] = be->topnode; sp++;
+	while (sp)
+	{
+		sp--;
+		int pedges = st_head[sp];
+		if (st_node[sp] < 0)
+		{
+			/* reached a non-solid leaf: r_currentbkey = leaf->key; R_RenderBmodelFace */
+			int n = 0;
+			for (int e = pedges; e >= 0 && n < RC_MAX_FACE_EDGES + 1; e = e_next[e], n++)
+			{
+				ev0[n] = e_v0[e]; ev1[n] = e_v1[e];
+			}
+			rc_bmodel_emit (&c, ev0, ev1, n, be->clipflags, leafkey[-1 - st_node[sp]]);
+			continue;
+		}
+		const rc_node_t *pnode = &w->nodes[st_node[sp]];
+		int psideedges[2] = { -1, -1 };
+		int makeclippededge = 0;
+		/* transform the BSP plane into model space */
+		const rc_plane_t *splitplane = &w->planes[pnode->plane];
+		float tdist = splitplane->dist - rc_dot3 (be->origin, splitplane->normal);
+		float tnormal[3];
+		tnormal[0] = rc_dot3 (be->rot[0], splitplane->normal);
+		tnormal[1] = rc_dot3 (be->rot[1], splitplane->normal);
+		tnormal[2] = rc_dot3 (be->rot[2], splitplane->normal);
+		int overflow = 0;
+		for (int pnextedge; pedges >= 0; pedges = pnextedge)
+		{
+			pnextedge = e_next[pedges];
+			const int plastvert = e_v0[pedges], pvert = e_v1[pedges];
+			const float *lp = rc_bvert (&c, plastvert), *pp = rc_bvert (&c, pvert);
+			const float lastdist = rc_dot3 (lp, tnormal) - tdist;
+			const int lastside = (lastdist <= 0);
+			const float dist = rc_dot3 (pp, tnormal) - tdist;
+			const int side = (dist <= 0);
+			if (side != lastside)
+			{
+				if (c.numbverts >= RC_BMODEL_VERTS || numbedges >= RC_BMODEL_EDGES - 1)
+				{
+					overflow = 1;
+					break;
+				}
+				const float frac = lastdist / (lastdist - dist);
+				const int ptvert = c.numbverts++;
+				c.bverts[ptvert][0] = lp[0] + frac * (pp[0] - lp[0]);
+				c.bverts[ptvert][1] = lp[1] + frac * (pp[1] - lp[1]);
+				c.bverts[ptvert][2] = lp[2] + frac * (pp[2] - lp[2]);
+				int pt = numbedges;
+				e_next[pt] = psideedges[lastside]; psideedges[lastside] = pt; e_v0[pt] = plastvert; e_v1[pt] = ptvert;
+				pt = numbedges + 1;
+				e_next[pt] = psideedges[side]; psideedges[side] = pt; e_v0[pt] = ptvert; e_v1[pt] = pvert;
+				numbedges += 2;
+				if (side == 0) pfrontenter = ptvert; else pfrontexit = ptvert;
+				makeclippededge = 1;
+			}
+			else
+			{
+				e_next[pedges] = psideedges[side];
+				psideedges[side] = pedges;
+			}
+		}
+		if (overflow)
+		{
+			RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+			break;
+		}
+		if (makeclippededge)
+		{
+			if (numbedges >= RC_BMODEL_EDGES - 2)
+			{
+				RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+				break;
+			}
+			int pt = numbedges;
+			e_next[pt] = psideedges[0]; psideedges[0] = pt; e_v0[pt] = pfrontexit; e_v1[pt] = pfrontenter;
+			pt = numbedges + 1;
+			e_next[pt] = psideedges[1]; psideedges[1] = pt; e_v0[pt] = pfrontenter; e_v1[pt] = pfrontexit;
+			numbedges += 2;
+		}
+		/* the reference finishes child 0 (leaf: draw it, node: recurse) before child 1: push 1 then 0 */
+		for (int i = 1; i >= 0; i--)
+		{
+			if (psideedges[i] < 0)
+				continue;
+			const int pn = pnode->children[i];
+			const int idx = pn >= 0 ? pn : w->numnodes + (-1 - pn);
+			if (!rc_visbit (vis, idx))
+				continue;	/* this branch isn't in the PVS */
+			if (pn < 0 && w->leafs[-1 - pn].contents == RC_CONTENTS_SOLID)
+				continue;
+			if (sp >= 64)
+			{
+				RC_ATOMIC_OR_I (f->status, RC_STAT_BMODEL_OVERFLOW);
+				continue;
+			}
+			st_head[sp] = psideedges[i]; st_node[sp] = pn; sp++;
+		}
+	}
 }
 
 /* ------------------------------------------------------------------ stage 3: scan ------ */
@@ -930,6 +1244,23 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 		f->blockspan[blockbase + i] = -1;
 }
 
+/* surf_t slots of a view in use: 1 (background), 2 .. nfaces+1 (world faces), then the brush-entity
+ * fragments at facecap+2 ..; maps a dense index to the slot, -1 past the end */
+RC_HD int rc_surf_slot (const rc_frame_t *f, int vi, int idx)
+{
+	const int nf = f->nfaces[vi] < f->facecap ? f->nfaces[vi] : f->facecap;
+	if (idx < nf + 1)
+		return idx + 1;
+	idx -= nf + 1;
+	if (f->nbsurfs)
+	{
+		const int nb = f->nbsurfs[vi] < f->bsurfcap ? f->nbsurfs[vi] : f->bsurfcap;
+		if (idx < nb)
+			return f->facecap + 2 + idx;
+	}
+	return -1;
+}
+
 /* ------------------------------------------------------------- stage 4: surface prep --- */
 RC_HD int rc_lightadj_code (int value)
 {
@@ -947,14 +1278,14 @@ RC_HD uint32_t rc_hash64 (unsigned long long k)
 }
 
 /* D_CalcGradients, d_edge.c:96-157 */
-RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc_face_t *fa, int miplevel, rc_surf_t *s)
+RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc_xform_t *xf, const rc_face_t *fa, int miplevel, rc_surf_t *s)
 {
 	const rc_texinfo_t *ti = &w->texinfo[fa->texinfo];
 	float mipscale = 1.0 / (float)(1 << miplevel);
 	float p_saxis[3], p_taxis[3], p_temp1[3];
 	float t;
-	rc_transform_vector (vw, ti->vecs[0], p_saxis);
-	rc_transform_vector (vw, ti->vecs[1], p_taxis);
+	p_saxis[0] = rc_dot3 (ti->vecs[0], xf->vright); p_saxis[1] = rc_dot3 (ti->vecs[0], xf->vup); p_saxis[2] = rc_dot3 (ti->vecs[0], xf->vpn);
+	p_taxis[0] = rc_dot3 (ti->vecs[1], xf->vright); p_taxis[1] = rc_dot3 (ti->vecs[1], xf->vup); p_taxis[2] = rc_dot3 (ti->vecs[1], xf->vpn);
 	t = vw->xscaleinv * mipscale;
 	s->d_sdivzstepu = p_saxis[0] * t;
 	s->d_tdivzstepu = p_taxis[0] * t;
@@ -963,9 +1294,9 @@ RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc
 	s->d_tdivzstepv = -p_taxis[1] * t;
 	s->d_sdivzorigin = p_saxis[2] * mipscale - vw->xcenter * s->d_sdivzstepu - vw->ycenter * s->d_sdivzstepv;
 	s->d_tdivzorigin = p_taxis[2] * mipscale - vw->xcenter * s->d_tdivzstepu - vw->ycenter * s->d_tdivzstepv;
-	p_temp1[0] = vw->tmodelorg[0] * mipscale;
-	p_temp1[1] = vw->tmodelorg[1] * mipscale;
-	p_temp1[2] = vw->tmodelorg[2] * mipscale;
+	p_temp1[0] = xf->tmodelorg[0] * mipscale;
+	p_temp1[1] = xf->tmodelorg[1] * mipscale;
+	p_temp1[2] = xf->tmodelorg[2] * mipscale;
 	t = 0x10000*mipscale;
 	s->sadjust = rc_f2i ((float)(rc_d2i (rc_dot3 (p_temp1, p_saxis) * 0x10000 + 0.5) -
 			((fa->texturemins[0] << 16) >> miplevel)) + ti->vecs[0][3]*t);
@@ -984,14 +1315,14 @@ RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc
  * whose BSP descent reaches the face's node with |dist| <= radius.  The reference descends
  * from the root choosing children by plane distance; a node is marked iff no ancestor's
  * test sends the descent away from it and its own plane is within the radius. */
-RC_HD int rc_dlight_bits (const rc_world_t *w, const rc_frame_t *f, const rc_view_t *vw, int node)
+RC_HD int rc_dlight_bits (const rc_world_t *w, const rc_frame_t *f, int headnode, int dlbase, int num, int node)
 {
 	int bits = 0;
 	const int tx = w->nodeaux[node].dfs_in;
-	for (int l = 0; l < vw->num_dlights; l++)
+	for (int l = 0; l < num; l++)
 	{
-		const rc_dlight_t *dl = &f->dlights[vw->dlight_ofs + l];
-		int cur = 0;
+		const rc_dlight_t *dl = &f->dlights[dlbase + l];
+		int cur = headnode;
 		for (;;)
 		{
 			const rc_node_t *nd = &w->nodes[cur];
@@ -1041,12 +1372,15 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 	}
 	const rc_face_t *fa = &w->faces[s->face];
 	const rc_texinfo_t *ti = &w->texinfo[fa->texinfo];
+	/* brush-entity surfaces are textured in the entity's rotated frame (d_edge.c:247-264,290-306) */
+	const rc_bent_t *be = s->insubmodel ? &f->bents[s->entity] : (const rc_bent_t *)0;
+	const rc_xform_t *xf = be ? &be->x : rc_view_xform (vw);
 	if (s->flags & RC_SURF_DRAWTURB)
 	{
 		s->pad = RC_SRC_TEXELS;
 		s->cacheofs = w->textures[ti->texture].offsets[0];
 		s->cachewidth = 64;
-		rc_calc_gradients (w, vw, fa, 0, s);
+		rc_calc_gradients (w, vw, xf, fa, 0, s);
 		return;
 	}
 	/* D_MipLevelForScale, d_edge.c:44-63 */
@@ -1060,6 +1394,9 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 
 	/* R_TextureAnimation, r_surf.c:60-87 (world entity: frame 0) */
 	int tex = ti->texture;
+	if (be && be->frame && w->textures[tex].alternate_anims >= 0)
+		tex = w->textures[tex].alternate_anims;
+	const int basetex = tex;
 	if (w->textures[tex].anim_total)
 	{
 		int reletive = vw->animtime % w->textures[tex].anim_total;
@@ -1067,7 +1404,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		while (w->textures[tex].anim_min > reletive || w->textures[tex].anim_max <= reletive)
 		{
 			tex = w->textures[tex].anim_next;
-			if (tex < 0 || ++count > 100) { tex = ti->texture; break; }
+			if (tex < 0 || ++count > 100) { tex = basetex; break; }
 		}
 	}
 	int la[4], codes[4], cacheable = 1;
@@ -1079,8 +1416,9 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		if (codes[k] == 254) cacheable = 0;
 	}
 	int dlbits = 0;
-	if (vw->num_dlights && fa->node >= 0)
-		dlbits = rc_dlight_bits (w, f, vw, fa->node);
+	const int dlbase = be ? be->dlight_ofs : vw->dlight_ofs;
+	if (vw->num_dlights && fa->node >= 0 && dlbase >= 0)
+		dlbits = rc_dlight_bits (w, f, be ? be->headnode : 0, dlbase, vw->num_dlights, fa->node);
 	if (dlbits)
 		cacheable = 0;		/* cache->dlight: rebuilt every frame (d_surf.c:214-228), private to the view */
 	int bw = fa->extents[0] >> mip, bh = fa->extents[1] >> mip;
@@ -1118,6 +1456,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 			job->lightadj[0] = la[0]; job->lightadj[1] = la[1]; job->lightadj[2] = la[2]; job->lightadj[3] = la[3];
 			job->ambient = vw->ambientlight; job->dstofs = ofs; job->width = bw; job->height = bh;
 			job->view = dlbits ? vi : -1; job->pad = vw->fullbright; job->dlightbits = dlbits;
+			job->pad2[0] = dlbase; job->pad2[1] = vw->num_dlights;
 		}
 		if (creator)
 			f->cachevals[slot] = ofs;
@@ -1126,7 +1465,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 	s->cacheofs = ofs;
 	s->miplevel = (cacheable && !creator) ? slot : -1;
 	s->cachewidth = bw;
-	rc_calc_gradients (w, vw, fa, mip, s);
+	rc_calc_gradients (w, vw, xf, fa, mip, s);
 }
 
 RC_HD void rc_surf_resolve (const rc_frame_t *f, int vi, int si)
@@ -1161,15 +1500,16 @@ RC_HD unsigned rc_cache_luxel (const rc_world_t *w, const rc_frame_t *f, const r
 	if (job->dlightbits)
 	{
 		/* R_AddDynamicLights, r_light.c:274-365 (world entity: no rotation, origin 0) */
-		const rc_view_t *vw = &f->views[job->view];
+		/* job->pad2[0]: first dlight (already relative to the entity and rotated into its frame for brush
+		 * entities: r_light.c:300-311), job->pad2[1]: how many */
 		const rc_texinfo_t *tex = &w->texinfo[fa->texinfo];
 		const rc_plane_t *plane = &w->planes[fa->plane];
 		const int ls = i % smax, lt = i / smax;
-		for (int lnum = 0; lnum < vw->num_dlights; lnum++)
+		for (int lnum = 0; lnum < job->pad2[1]; lnum++)
 		{
 			if (!(job->dlightbits & (1 << lnum)))
 				continue;
-			const rc_dlight_t *l = &f->dlights[vw->dlight_ofs + lnum];
+			const rc_dlight_t *l = &f->dlights[job->pad2[0] + lnum];
 			float dlorigin[3], impact[3], local[2];
 			dlorigin[0] = l->origin[0] - 0.0f; dlorigin[1] = l->origin[1] - 0.0f; dlorigin[2] = l->origin[2] - 0.0f;
 			float rad = l->radius;

@@ -290,6 +290,29 @@ typedef struct {            /* particle_t (client/ref.h:37-41) + owning view */
     int   pad[2];
 } rc_particle_t;            /* 32 B */
 
+/* the part of rc_view_t that R_RotateBmodel (r_bsp.c:78-151) replaces while a brush entity is
+ * drawn; laid out exactly like rc_view_t from `vpn` to `clipdist` so a view can be used as one */
+typedef struct {
+    float vpn[3], vright[3], vup[3], origin[3];   /* origin = modelorg */
+    float tmodelorg[3];
+    float clipnormal[4][3];
+    float clipdist[4];
+} rc_xform_t;               /* 31 floats */
+
+typedef struct {            /* one drawn brush entity of one view (R_DrawBEntitiesOnList, r_main.c:640-768) */
+    int   view, order;      /* order: index among the view's brush entities */
+    int   firstface, numfaces;
+    int   headnode;         /* of the submodel (R_MarkLights) */
+    int   topnode;          /* R_FindTopNode: >= 0 node (clip to the world BSP), < 0 leaf -1-topnode */
+    int   clipflags;
+    int   frame;            /* entity->frame: alternate texture animation (r_surf.c:65-69) */
+    int   dlight_ofs;       /* this entity's model-space copies of the view's dlights, -1: none */
+    int   pad[2];
+    float origin[3];        /* r_entorigin */
+    float rot[3][3];        /* entity_rotation */
+    rc_xform_t x;           /* rotated basis, modelorg, frustum; tmodelorg as D_DrawSurfaces computes it */
+} rc_bent_t;                /* 220 B */
+
 /* error / status bits returned through the C-ABI */
 #define RC_OK                    0
 #define RC_ERR_CUDA              (-1)
@@ -307,7 +330,8 @@ typedef struct {            /* particle_t (client/ref.h:37-41) + owning view */
 #define RC_STAT_STALE_CLIPVERT   64  /* reference would read r_rightenter/r_rightexit left over from an earlier face */
 #define RC_STAT_FACELIST         128 /* face list capacity exceeded */
 #define RC_STAT_UNSUPPORTED_ENT   256 /* a sprite / brush entity was skipped (not built yet) */
-#define RC_STAT_ALIAS_RANGE       512 /* alias rasteriser hit a case where the reference reads/loops out of range */
+#define RC_STAT_ALIAS_RANGE       512
+#define RC_STAT_BMODEL_OVERFLOW   1024 /* brush entity clipping ran out of vertices/edges (reference: MAX_BMODEL_VERTS/EDGES) */ /* alias rasteriser hit a case where the reference reads/loops out of range */
 
 #ifdef __cplusplus
 }
