@@ -325,6 +325,7 @@ static int rc_prepare_views (const refdef_t *views, int n)
 			return rc_fail (RC_ERR_NOWORLD, "R_RenderView: NULL worldmodel");	/* r_main.c:1003 */
 		rcode = RC_SetupView (&views[i], &rc.vid, &rc.cvars, v);
 		if (rcode != RC_OK) return rc_fail (rcode, "view %d: bad refdef rectangle", i);
+		v->viewleaf = (rc.world && !(views[i].flags & RDF_NOWORLDMODEL)) ? RC_PointInLeaf (rc.world->world, views[i].vieworg) : -1;
 		if (views[i].num_dlights > MAX_DLIGHTS)
 			return rc_fail (RC_ERR_ARG, "view %d: more than %d dlights", i, MAX_DLIGHTS);
 		if (v->dowarp)

@@ -90,43 +90,80 @@ struct rc_gpu_s {
 };
 
 /* ------------------------------------------------------------------------ kernels ----- */
-__global__ void k_begin (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* Front end, one CTA per view: everything from the view leaf to the view's
+ * edge and surface records in ONE launch.  The phases are the former k_begin / k_visit /
+ * k_listfaces / k_faces / k_fixup bodies separated by __syncthreads(): a view's front end is a
+ * few hundred items per phase, so separate grids were launch- and tail-bound; in one CTA the
+ * per-view scratch (face marks, node visits, face list) is written and re-read by the same SM.
+ *   phase 0  reset the view's facepos / facemark / nodevisit rows, background surface
+ *   phase 1  rc_visit       per node-or-leaf: root->x replay (PVS, frustum, BSP sort key)
+ *   phase 2  rc_list_face   per world face: is R_RenderFace called on it
+ *   phase 3  rc_render_face per listed face: clip, project, edges, surf_t
+ *   phase 4  fix-up of faces that read r_rightenter/r_rightexit left by an earlier face:
+ *            the search for the latest earlier writer is done by the whole warp */
+#define FRONT_THREADS 256
+__global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	int vi = blockIdx.x * blockDim.x + threadIdx.x;
-	if (vi < f.nviews)
-		rc_view_begin (&w, &f, vi);
-}
-
-__global__ void k_visit (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
-{
-	int vi = blockIdx.x;
-	int x = blockIdx.y * blockDim.x + threadIdx.x;
-	if (x < w.numnodes + w.numleafs)
+	const int vi = blockIdx.x, tid = threadIdx.x;
+	{
+		uint16_t *facepos = f.facepos + (size_t)vi * w.numfaces;
+		int *facemark = f.facemark + (size_t)vi * w.numfaces;
+		unsigned long long *nv = reinterpret_cast<unsigned long long *>(f.nodevisit + (size_t)vi * w.numnodes);
+		for (int i = tid; i < w.numfaces; i += FRONT_THREADS) { facepos[i] = RC_FACEPOS_NONE; facemark[i] = 0x7F7F7F7F; }
+		for (int i = tid; i < w.numnodes; i += FRONT_THREADS) nv[i] = 0ull;
+		if (tid == 0)
+			rc_view_begin (&w, &f, vi);
+	}
+	__syncthreads ();
+	for (int x = tid; x < w.numnodes + w.numleafs; x += FRONT_THREADS)
 		rc_visit (&w, &f, vi, x);
-}
-
-__global__ void k_listfaces (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
-{
-	int vi = blockIdx.x;
-	int fi = blockIdx.y * blockDim.x + threadIdx.x;
-	if (fi < w.numworldfaces)
+	__syncthreads ();
+	for (int fi = tid; fi < w.numworldfaces; fi += FRONT_THREADS)
 		rc_list_face (&w, &f, vi, fi);
-}
-
-__global__ void k_faces (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
-{
-	int vi = blockIdx.x;
-	int p = blockIdx.y * blockDim.x + threadIdx.x;
-	if (p < f.nfaces[vi])
+	__syncthreads ();
+	const int nfraw = __ldcg (&f.nfaces[vi]);
+	const int nf = nfraw < f.facecap ? nfraw : f.facecap;
+	for (int p = tid; p < nf; p += FRONT_THREADS)
 		rc_render_face (&w, &f, vi, p);
-}
-
-__global__ void k_fixup (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
-{
-	int vi = blockIdx.x;
-	int p = blockIdx.y * blockDim.x + threadIdx.x;
-	if (p < f.nfaces[vi])
-		rc_face_fixup (&w, &f, vi, p);
+	__syncthreads ();
+	{
+		const int lane = tid & 31;
+		const rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
+		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
+		for (int p0 = (tid >> 5) << 5; p0 < nf; p0 += FRONT_THREADS)
+		{
+			const int p = p0 + lane;
+			const bool need = p < nf && (surfs[p + 2].miplevel & 4);
+			unsigned todo = __ballot_sync (0xFFFFFFFFu, need);
+			while (todo)
+			{
+				const int src = __ffs (todo) - 1;
+				todo &= todo - 1;
+				const int pp = p0 + src;
+				const int mykey = list[pp].key;
+				long long bre = -1, brx = -1;		/* key << 32 | slot: keys are unique */
+				for (int q = lane; q < nf; q += 32)
+				{
+					const int k = list[q].key;
+					const int m = surfs[q + 2].miplevel;
+					if (k < mykey)
+					{
+						const long long kv = ((long long)k << 32) | (unsigned)q;
+						if ((m & 1) && kv > bre) bre = kv;
+						if ((m & 2) && kv > brx) brx = kv;
+					}
+				}
+				for (int o = 16; o; o >>= 1)
+				{
+					const long long a = __shfl_xor_sync (0xFFFFFFFFu, bre, o), b = __shfl_xor_sync (0xFFFFFFFFu, brx, o);
+					if (a > bre) bre = a;
+					if (b > brx) brx = b;
+				}
+				if (lane == src)
+					rc_face_fixup_finish (&w, &f, vi, pp, bre < 0 ? -1 : (int)(bre & 0xFFFFFFFF), brx < 0 ? -1 : (int)(brx & 0xFFFFFFFF));
+			}
+		}
+	}
 }
 
 /* Scan stage, three kernels (R_ScanEdges and friends):
@@ -720,22 +757,11 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
-	CK (cudaMemsetAsync (g->d_facepos, 0xFF, sizeof(uint16_t) * (size_t)n * w.numfaces, s));
-	CK (cudaMemsetAsync (g->d_facemark, 0x7F, sizeof(int) * (size_t)n * w.numfaces, s));
-	CK (cudaMemsetAsync (g->d_nodevisit, 0, sizeof(rc_nodevisit_t) * (size_t)n * w.numnodes, s));
 	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
 	CK (cudaMemsetAsync (g->d_alloc + 2, 0, sizeof(unsigned long long), s));
-	g->stats.kernel_launches += 0;
 
-	k_begin<<<(n + 63) / 64, 64, 0, s>>> (w, f);
-	dim3 gv (n, (w.numnodes + w.numleafs + 63) / 64);
-	k_visit<<<gv, 64, 0, s>>> (w, f);
-	dim3 gl (n, (w.numworldfaces + 127) / 128);
-	k_listfaces<<<gl, 128, 0, s>>> (w, f);
+	k_front<<<n, FRONT_THREADS, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[1], s);
-	dim3 gf (n, (g->facecap + 63) / 64);
-	k_faces<<<gf, 64, 0, s>>> (w, f);
-	k_fixup<<<gf, 64, 0, s>>> (w, f);
 	if (g->cur_batch && g->cur_batch->nbents)
 	{
 		const rc_batch_t *b = g->cur_batch;
@@ -815,7 +841,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		g->stats.kernel_launches++;
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 13;
+	g->stats.kernel_launches += 9;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }

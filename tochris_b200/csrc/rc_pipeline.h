@@ -22,6 +22,7 @@
 #define RC_HD2 __device__ __forceinline__
 #define RC_DEBUG_PRINT(...) do { } while (0)
 #define RC_LDG(p) __ldg (p)
+#define RC_LDCG(p) __ldcg (p)   /* L2 read: values other threads of the CTA updated with atomics */
 #define RC_ATOMIC_ADD_I(p, v)   atomicAdd ((p), (v))
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
@@ -35,6 +36,7 @@
 #include <stdlib.h>
 #define RC_DEBUG_PRINT(...) do { if (getenv ("RC_DEBUG")) fprintf (stderr, __VA_ARGS__); } while (0)
 #define RC_LDG(p) (*(p))
+#define RC_LDCG(p) (*(p))
 static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline int rc_host_or_i (int *p, int v) { int o = *p; *p = o | v; return o; }
@@ -172,8 +174,9 @@ RC_HD float rc_plane_diff (const float *p, const rc_plane_t *pl)
 	return (pl->type < 3 ? p[pl->type] : rc_dot3 (p, pl->normal)) - pl->dist;
 }
 
-/* One thread per view: Mod_PointInLeaf (r_model.c:83-105) and the per-view resets
- * R_BeginEdgeFrame does (r_edge.c:81-112). */
+/* One thread per view: the per-view resets R_BeginEdgeFrame does (r_edge.c:81-112).  The view
+ * leaf (Mod_PointInLeaf, r_model.c:83-105) comes from the host with the other view constants:
+ * a serial pointer chase has no business on the device. */
 RC_HD void rc_view_begin (const rc_world_t *w, const rc_frame_t *f, int vi)
 {
 	const rc_view_t *v = &f->views[vi];
@@ -186,15 +189,7 @@ RC_HD void rc_view_begin (const rc_world_t *w, const rc_frame_t *f, int vi)
 	f->nfaces[vi] = 0;
 	if (f->nbsurfs)
 		f->nbsurfs[vi] = 0;
-	int n = 0;
-	while (n >= 0)
-	{
-		const rc_node_t *nd = &w->nodes[n];
-		const rc_plane_t *pl = &w->planes[nd->plane];
-		float d = rc_dot3 (v->origin, pl->normal) - pl->dist;
-		n = (d > 0) ? nd->children[0] : nd->children[1];
-	}
-	f->viewleaf[vi] = -1 - n;
+	f->viewleaf[vi] = v->viewleaf >= 0 && v->viewleaf < w->numleafs ? v->viewleaf : 0;
 }
 
 /* One thread per (view, node-or-leaf x): decides whether R_RecursiveWorldNode (r_bsp.c:436-557)
@@ -279,7 +274,7 @@ RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int f
 	if ((fa->flags & RC_SURF_PLANEBACK) != want)
 		return;
 	const int key = nv.facekey + (fi - w->nodes[fa->node].firstsurface);
-	if (!(f->facemark[(size_t)vi * w->numfaces + fi] < key))
+	if (!(RC_LDCG (&f->facemark[(size_t)vi * w->numfaces + fi]) < key))
 		return;
 	int p = RC_ATOMIC_ADD_I (&f->nfaces[vi], 1);
 	if (p >= f->facecap || p >= (int)RC_FACEPOS_MARKED - 1)
@@ -618,36 +613,21 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 /* One thread per (view, face-list slot), after rc_render_face: faces that must read an
  * r_rightenter / r_rightexit written by an earlier face (see above) walk the list backwards
  * for the most recent writer, then run the r_nearzionly clip of r_rast.c:669-675. */
-RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int p)
+/* second half of the fixup: best_re / best_rx = list slots of the latest earlier writers (-1: none) */
+RC_HD void rc_face_fixup_finish (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int best_re, int best_rx)
 {
 	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
 	rc_surf_t *surf = &surfs[p + 2];
-	if (!(surf->miplevel & 4))
-		return;
 	const rc_view_t *vw = &f->views[vi];
 	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
 	float re[3], rx[3];
 	int have_re = surf->miplevel & 1, have_rx = (surf->miplevel >> 1) & 1;
 	re[0] = surf->d_sdivzstepu; re[1] = surf->d_tdivzstepu; re[2] = surf->d_sdivzstepv;
 	rx[0] = surf->d_tdivzstepv; rx[1] = surf->d_sdivzorigin; rx[2] = surf->d_tdivzorigin;
-	{
-		/* the face list is unordered: take, per value, the writer with the largest key below ours */
-		const int mykey = list[p].key, nf = f->nfaces[vi] < f->facecap ? f->nfaces[vi] : f->facecap;
-		int best_re = -1, best_rx = -1, kre = -1, krx = -1;
-		for (int q = 0; q < nf; q++)
-		{
-			const int k = list[q].key;
-			if (k >= mykey)
-				continue;
-			const int m = surfs[q + 2].miplevel;
-			if (!have_re && (m & 1) && k > kre) { kre = k; best_re = q; }
-			if (!have_rx && (m & 2) && k > krx) { krx = k; best_rx = q; }
-		}
-		if (best_re >= 0)
-		{ const rc_surf_t *o = &surfs[best_re + 2]; have_re = 1; re[0] = o->d_sdivzstepu; re[1] = o->d_tdivzstepu; re[2] = o->d_sdivzstepv; }
-		if (best_rx >= 0)
-		{ const rc_surf_t *o = &surfs[best_rx + 2]; have_rx = 1; rx[0] = o->d_tdivzstepv; rx[1] = o->d_sdivzorigin; rx[2] = o->d_tdivzorigin; }
-	}
+	if (!have_re && best_re >= 0)
+	{ const rc_surf_t *o = &surfs[best_re + 2]; have_re = 1; re[0] = o->d_sdivzstepu; re[1] = o->d_tdivzstepu; re[2] = o->d_sdivzstepv; }
+	if (!have_rx && best_rx >= 0)
+	{ const rc_surf_t *o = &surfs[best_rx + 2]; have_rx = 1; rx[0] = o->d_tdivzstepv; rx[1] = o->d_sdivzorigin; rx[2] = o->d_tdivzorigin; }
 	if (!have_re || !have_rx)
 	{
 		/* nothing wrote it this frame: the reference would use last frame's leftovers */
@@ -660,6 +640,28 @@ RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int 
 	rc_clip_emit (vw, rc_view_xform (vw), rx, re, list[p].clipflags & 0xC, 1, &r);
 	if (r.reached_emit && r.nearzi > surf->nearzi)
 		surf->nearzi = r.nearzi;
+}
+
+RC_HD void rc_face_fixup (const rc_world_t *w, const rc_frame_t *f, int vi, int p)
+{
+	const rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
+	const int m0 = surfs[p + 2].miplevel;
+	if (!(m0 & 4))
+		return;
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	/* the face list is unordered: take, per value, the writer with the largest key below ours */
+	const int mykey = list[p].key, nf = f->nfaces[vi] < f->facecap ? f->nfaces[vi] : f->facecap;
+	int best_re = -1, best_rx = -1, kre = -1, krx = -1;
+	for (int q = 0; q < nf; q++)
+	{
+		const int k = list[q].key;
+		if (k >= mykey)
+			continue;
+		const int m = surfs[q + 2].miplevel;
+		if ((m & 1) && k > kre) { kre = k; best_re = q; }
+		if ((m & 2) && k > krx) { krx = k; best_rx = q; }
+	}
+	rc_face_fixup_finish (w, f, vi, p, best_re, best_rx);
 }
 
 /* ------------------------------------------------------------- stage 2b: brush entities -- */

@@ -176,7 +176,7 @@ typedef struct {
     int   warp_index;              /* r_dowarp: which 320x200 warp buffer this view renders into, else -1 */
     int   rd_x, rd_y, rd_w, rd_h;  /* r_refdef rectangle (D_WarpScreen target) */
     int   zres_index;              /* index of this view's entity z-resolve plane, -1: no alias models / particles */
-    int   pad1;
+    int   viewleaf;                /* Mod_PointInLeaf (r_model.c:83) of the view origin, done on the host; -1: no world */
 } rc_view_t;
 
 /* dlight_t (client/ref.h:43-47) */
