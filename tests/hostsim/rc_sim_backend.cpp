@@ -129,13 +129,13 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	g->surfs.assign ((size_t)n * f.surfcap, rc_surf_t ());
 	f.surfs = g->surfs.data ();
 	f.spancap = n * g->height * 96;
-	f.blockcap = n * g->height * ((g->width + 7) / 8 + 96);
+	const int cw = (g->width + 7) / 8;
+	f.chkcap = f.spancap + n * g->height * (cw / 4 + 1);
 	g->spans.assign (f.spancap, rc_span_t ());
-	std::vector<int> blockspan (f.blockcap, -1);
-	f.spans = g->spans.data (); f.blockspan = blockspan.data ();
-	std::vector<float> chk ((size_t)f.blockcap * 4, 0.f);
-	std::vector<int> spanaux ((size_t)f.spancap * 2, 0);
-	f.chk = chk.data (); f.spanaux = spanaux.data ();
+	std::vector<int> cellspan ((size_t)n * g->height * cw, -1);
+	f.spans = g->spans.data (); f.cellspan = cellspan.data ();
+	std::vector<float> chk ((size_t)f.chkcap * 4, 0.f);
+	f.chk = chk.data ();
 	g->alloc[0] = 0; g->alloc[2] = 0;
 	f.alloc = g->alloc;
 	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;
@@ -183,14 +183,12 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 				g->cachepool[job->dstofs + y * job->width + x] = rc_cache_texel (w, job, bl, x, y);
 		texels += (long long)job->width * job->height;
 	}
-	int nblocks = (int)(g->alloc[0] >> 32);
-	if (nblocks > f.blockcap) nblocks = f.blockcap;
-	{
-		int ns = (int)(g->alloc[0] & 0xFFFFFFFFu);
-		if (ns > f.spancap) ns = f.spancap;
-		for (int t = 0; t < ns; t++) rc_span_prep (w, &f, t);
-	}
-	for (int t = 0; t < nblocks; t++) rc_draw_block (w, &f, t);
+	int nspans = (int)(g->alloc[0] & 0xFFFFFFFFu);
+	if (nspans > f.spancap) nspans = f.spancap;
+	for (int t = 0; t < nspans; t++) rc_span_prep (w, &f, t);
+	for (int row = 0; row < n * g->height; row++)
+		for (int c = 0; c < cw; c++) rc_draw_cell (w, &f, row, c);
+	for (int t = 0; t < nspans; t++) rc_draw_head (w, &f, t);
 
 	/* alias models, particles, z resolve (R_DrawEntitiesOnList, R_DrawParticles) */
 	std::vector<rc_finalvert_t> finalverts ((size_t)batch->nfinalverts + 1);
@@ -218,7 +216,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	if (g->nspans > f.spancap) g->nspans = f.spancap;
 	g->edgecap = f.edgecap; g->surfcap = f.surfcap; g->nfaces = nfaces;
 	memset (&g->stats, 0, sizeof(g->stats));
-	g->stats.cache_jobs = njobs; g->stats.cache_texels = texels; g->stats.blocks = nblocks; g->stats.spans = g->nspans;
+	g->stats.cache_jobs = njobs; g->stats.cache_texels = texels; g->stats.blocks = (long long)n * g->height * cw + nspans; g->stats.spans = g->nspans;
 	for (int vi = 0; vi < n; vi++) { g->stats.edges += g->nedges[vi]; g->stats.faces += nfaces[vi]; }
 	if (status) *status = st;
 	return RC_OK;

@@ -44,19 +44,23 @@ class rc_edge_t(C.Structure):
                 ("surfs", C.c_ushort * 2), ("rank", C.c_uint), ("pad", C.c_int * 3)]
 
 
-class rc_surf_t(C.Structure):
+class rc_surf_t(C.Structure):       # rc_types.h rc_surf_t, 128 B
     _fields_ = [("key", C.c_int), ("flags", C.c_int), ("face", C.c_int), ("insubmodel", C.c_int),
                 ("nearzi", C.c_float), ("d_ziorigin", C.c_float), ("d_zistepu", C.c_float), ("d_zistepv", C.c_float),
-                ("miplevel", C.c_int), ("cacheofs", C.c_int), ("cachewidth", C.c_int), ("hasspans", C.c_int),
-                ("d_sdivzstepu", C.c_float), ("d_tdivzstepu", C.c_float), ("d_sdivzstepv", C.c_float),
-                ("d_tdivzstepv", C.c_float), ("d_sdivzorigin", C.c_float), ("d_tdivzorigin", C.c_float),
+                ("miplevel", C.c_int), ("hasspans", C.c_int), ("entity", C.c_int), ("pad0", C.c_int),
+                ("d_sdivzstepv", C.c_float), ("d_tdivzstepv", C.c_float), ("d_sdivzorigin", C.c_float), ("d_tdivzorigin", C.c_float),
+                ("cacheofs", C.c_int), ("cachewidth", C.c_int), ("srckind", C.c_int), ("drawflags", C.c_int),
+                ("d_sdivzstepu", C.c_float), ("d_tdivzstepu", C.c_float), ("d_zistepu_draw", C.c_float), ("izistep", C.c_int),
                 ("sadjust", C.c_int), ("tadjust", C.c_int), ("bbextents", C.c_int), ("bbextentt", C.c_int),
-                ("entity", C.c_int), ("pad", C.c_int)]
+                ("pad2", C.c_int * 4)]
 
 
-class rc_span_t(C.Structure):
-    _fields_ = [("view", C.c_int), ("surf", C.c_ushort), ("v", C.c_short), ("u", C.c_short), ("count", C.c_short),
-                ("firstblock", C.c_int)]
+class rc_span_t(C.Structure):       # rc_types.h rc_span_t, 32 B
+    _fields_ = [("view", C.c_int), ("gsurf", C.c_int), ("u", C.c_short), ("count", C.c_short), ("v", C.c_short),
+                ("flags", C.c_ushort), ("pixofs", C.c_int), ("chkbase", C.c_int), ("izi0", C.c_int), ("pad", C.c_int)]
+
+
+assert C.sizeof(rc_surf_t) == 128 and C.sizeof(rc_span_t) == 32 and C.sizeof(rc_edge_t) == 32
 
 
 def status_names(status: int):

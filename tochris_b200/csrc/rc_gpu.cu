@@ -34,7 +34,6 @@
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
 
-struct rc_lineinfo { int spanbase, blockbase, n, nsp; };
 
 struct rc_gpu_s {
 	int device, width, height, numsms;
@@ -52,16 +51,15 @@ struct rc_gpu_s {
 	int chunkcap;			/* views the buffers below are sized for */
 	int maxchunk;			/* largest chunk the memory budget allows */
 	int maxviews;			/* user cap on views in flight (0: auto) */
-	int facecap, edgecap, surfcap, spancap, blockcap, jobcap;
+	int facecap, edgecap, surfcap, spancap, chkcap, jobcap;
 	int spans_per_line;		/* sizing heuristic, doubled on RC_STAT_SPAN_POOL */
 	rc_view_t *d_views;
 	rc_facerec_t *d_facelist; int *d_nfaces; uint16_t *d_facepos;
 	int *d_facemark; rc_nodevisit_t *d_nodevisit; int *d_viewleaf;
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
-	rc_span_t *d_spans; int *d_blockspan;
-	rc_lineinfo *d_lineinfo; uint2 *d_aetpool; int walk_lanes;
-	float *d_chk; int *d_spanaux;
+	rc_span_t *d_spans; int *d_cellspan;
+	float *d_chk;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -166,75 +164,147 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 	}
 }
 
-/* Scan stage, three kernels (R_ScanEdges and friends):
- *  k_scan_sort   one WARP per (view, scanline): the lanes sweep the view's edge records
- *                (32 B each, coalesced), keep those with v <= line <= v2 (ballot + popc
- *                compaction into shared memory), rank-sort their keys (keys are unique: each
- *                lane counts the smaller keys of its elements) and write the line's sorted
- *                active-edge list (u, surfs) to HBM.  Also reserves the line's span/block room.
- *  k_scan_walk   one THREAD per (view, scanline): R_GenerateSpans over the sorted list.  The
- *                walk is inherently serial per line (every edge mutates the surface stack), so
- *                the parallelism is 32 scanlines per warp.
- *  k_scan_blocks one WARP per (view, scanline): expands the line's spans into the 8-pixel
- *                block list the draw kernel consumes.
- * Integer work throughout. */
+/* Scan stage (R_ScanEdges, R_InsertNewEdges, R_StepActiveU, R_GenerateSpans), one
+ * kernel, one WARP per (view, scanline), 8 lines per CTA.  Integer work throughout.
+ *   A  the CTA sweeps the view's edge records once (32 B each, coalesced) and keeps in shared
+ *      memory those that touch any of its 8 lines
+ *   B1 each warp filters the candidates active on its line (ballot + popc compaction), u on the line
+ *      is u0 + (line - v) * u_step in wrapping int32
+ *   B2 rank sort on u; equal u (shared vertices, re-emitted clipped edges) are ordered by the full
+ *      128-bit key that reproduces the reference's linked-list order (rc_aet_make)
+ *   B3 the reference walks the sorted edges keeping a key-ordered surface stack: inherently serial.
+ *      World surfaces have UNIQUE keys, so the top of the stack is simply the active surface with
+ *      the smallest key.  Surfaces with a leading edge on the line are ranked by key (<= 64 of them:
+ *      one bit each); every edge toggles the bits of its trailing / leading surface; an inclusive
+ *      XOR scan over the sorted edges gives the active set after every edge; find-first-set gives the
+ *      top.  Spans are the runs of constant top between change points, empty runs dropped.
+ *      Lines where this model does not hold -- brush-entity surfaces (equal keys, 1/z tie break,
+ *      r_edge.c:435-458), a surface with two leading edges, a trailing edge before / without its
+ *      leading edge (spanstate going negative), more than 64 surfaces -- are walked by lane 0 with the
+ *      reference's own algorithm (rc_span_walk).
+ *   C  spans are published: one atomicAdd per line reserves span + checkpoint records, then the cell
+ *      map the draw kernel indexes (binary search over the line's span starts). */
 #define SCAN_WARPS 8
+#define SCAN_CAND  768
+#define SCAN_LEADS 64
+#define SCAN_SPANS (RC_AET_MAX + 2)
 
-struct rc_aet_global {
-	const uint2 *e;		/* x = u (12.20), y = surfs[0] | surfs[1] << 16 */
-	__device__ __forceinline__ int iu (int k) const { return (int)e[k].x >> 20; }
-	__device__ __forceinline__ uint32_t surfs (int k) const { return e[k].y; }
-	__device__ __forceinline__ int u (int k) const { return (int)e[k].x; }
+struct rc_aet_sorted {
+	const int *su; const uint32_t *ss;
+	__device__ __forceinline__ int iu (int k) const { return su[k] >> 20; }
+	__device__ __forceinline__ uint32_t surfs (int k) const { return ss[k]; }
+	__device__ __forceinline__ int u (int k) const { return su[k]; }
 };
 
-__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_sort (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f,
-								  rc_lineinfo *lineinfo, uint2 *aetpool)
-{
-	__shared__ unsigned long long s_hi[SCAN_WARPS][RC_AET_MAX], s_lo[SCAN_WARPS][RC_AET_MAX];
-	__shared__ uint32_t s_sf[SCAN_WARPS][RC_AET_MAX];
-	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int vi = blockIdx.x;
-	const int line = blockIdx.y * SCAN_WARPS + wid;
-	if (line >= f.height)
-		return;
-	rc_lineinfo *li = &lineinfo[(size_t)vi * f.height + line];
-	const rc_view_t *vw = &f.views[vi];
-	if (line < vw->vrect_y || line >= vw->vrectbottom)
-	{
-		if (lane == 0) li->n = -1;
-		return;
-	}
-	const rc_edge_t *edges = f.edges + (size_t)vi * f.edgecap;
-	int E = f.nedges[vi];
-	if (E > f.edgecap) E = f.edgecap;
-	unsigned long long *hi = s_hi[wid], *lo = s_lo[wid];
-	uint32_t *sf = s_sf[wid];
+struct scan_warp_t {			/* per-warp shared memory */
+	union {
+		struct { uint32_t ku[RC_AET_MAX]; uint16_t kidx[RC_AET_MAX]; } k;	/* B1/B2: unsorted keys */
+		struct { int16_t x0[SCAN_SPANS], x1[SCAN_SPANS]; uint16_t sf[SCAN_SPANS]; } sp;	/* B3/C: change points, spans */
+	} a;
+	int      su[RC_AET_MAX];		/* sorted: u (12.20) */
+	uint32_t ss[RC_AET_MAX];		/* sorted: surfs[0] | surfs[1] << 16 */
+	int      lkey[SCAN_LEADS], tcount[SCAN_LEADS];
+	uint16_t lsurf[SCAN_LEADS], rsurf[SCAN_LEADS];
+	uint8_t  lk[SCAN_LEADS], lrank[SCAN_LEADS];
+	uint8_t  lidx[RC_AET_MAX];
+};
 
-	int n = 0;
-	for (int base = 0; base < E; base += 32)
+struct scan_cta_t {
+	int      c_u[SCAN_CAND], c_step[SCAN_CAND];
+	uint32_t c_vv[SCAN_CAND], c_sf[SCAN_CAND], c_rank[SCAN_CAND];
+	int      ncand;
+	scan_warp_t warp[SCAN_WARPS];
+};
+
+__device__ __forceinline__ void scan_full_key (const scan_cta_t *sh, int c, int line, unsigned long long *hi, unsigned long long *lo)
+{
+	rc_edge_t ed;
+	rc_aet_t a;
+	ed.u = sh->c_u[c]; ed.u_step = sh->c_step[c];
+	ed.v = (int16_t)(sh->c_vv[c] & 0xFFFF); ed.v2 = (int16_t)(sh->c_vv[c] >> 16);
+	ed.surfs[0] = (uint16_t)(sh->c_sf[c] & 0xFFFF); ed.surfs[1] = (uint16_t)(sh->c_sf[c] >> 16);
+	ed.rank = sh->c_rank[c];
+	rc_aet_make (&ed, line, &a);
+	*hi = a.hi; *lo = a.lo;
+}
+
+__global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	extern __shared__ __align__(16) unsigned char scan_smem[];
+	scan_cta_t *sh = reinterpret_cast<scan_cta_t *>(scan_smem);
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	const int vi = blockIdx.x;
+	const int line0 = blockIdx.y * SCAN_WARPS, line = line0 + wid;
+	const rc_view_t *vw = &f.views[vi];
+	const int vy0 = vw->vrect_y, vy1 = vw->vrectbottom;
+	const int cw = (f.width + 7) >> 3;
+
+	/* ---- A: candidates of the CTA's 8 lines ---- */
+	if (threadIdx.x == 0)
+		sh->ncand = 0;
+	__syncthreads ();
+	if (line0 < vy1 && line0 + SCAN_WARPS > vy0)
 	{
-		int e = base + lane;
-		bool act = false;
-		rc_aet_t a;
-		if (e < E)
+		const rc_edge_t *edges = f.edges + (size_t)vi * f.edgecap;
+		int E = f.nedges[vi];
+		if (E > f.edgecap) E = f.edgecap;
+		const int lhi = line0 + SCAN_WARPS - 1;
+		for (int e = threadIdx.x; e < E; e += SCAN_WARPS * 32)
 		{
-			const int4 q = *reinterpret_cast<const int4 *>(&edges[e]);	/* u, u_step, v|v2, surfs */
-			const int v = (int16_t)(q.z & 0xFFFF), v2 = (int16_t)(q.z >> 16);
-			if (v <= line && v2 >= line)
+			const int4 q = __ldg (reinterpret_cast<const int4 *>(&edges[e]));	/* u, u_step, v|v2, surfs */
+			const int v = (int16_t)(q.z & 0xFFFF), v2 = (int16_t)((unsigned)q.z >> 16);
+			if (v <= lhi && v2 >= line0)
 			{
-				rc_edge_t ed;
-				ed.u = q.x; ed.u_step = q.y; ed.v = (int16_t)v; ed.v2 = (int16_t)v2;
-				ed.surfs[0] = (uint16_t)(q.w & 0xFFFF); ed.surfs[1] = (uint16_t)((unsigned)q.w >> 16);
-				ed.rank = edges[e].rank;
-				act = true;
-				rc_aet_make (&ed, line, &a);
+				const int slot = atomicAdd (&sh->ncand, 1);
+				if (slot < SCAN_CAND)
+				{
+					sh->c_u[slot] = q.x; sh->c_step[slot] = q.y; sh->c_vv[slot] = (uint32_t)q.z; sh->c_sf[slot] = (uint32_t)q.w;
+					sh->c_rank[slot] = __ldg (&edges[e].rank);
+				}
 			}
 		}
-		unsigned m = __ballot_sync (0xFFFFFFFFu, act);
-		int pos = n + __popc (m & ((1u << lane) - 1));
+	}
+	__syncthreads ();
+	int ncand = sh->ncand;
+	if (ncand > SCAN_CAND)
+	{
+		if (threadIdx.x == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
+		ncand = SCAN_CAND;
+	}
+	if (line >= f.height)
+		return;
+	int *cells = f.cellspan + ((size_t)vi * f.height + line) * cw;
+	if (line < vy0 || line >= vy1)
+	{
+		for (int c = lane; c < cw; c += 32)
+			cells[c] = -1;
+		return;
+	}
+	scan_warp_t *sw = &sh->warp[wid];
+
+	/* ---- B1: active edges of this line ---- */
+	int n = 0;
+	for (int base = 0; base < ncand; base += 32)
+	{
+		const int c = base + lane;
+		bool act = false;
+		uint32_t key = 0;
+		if (c < ncand)
+		{
+			const uint32_t vv = sh->c_vv[c];
+			const int v = (int16_t)(vv & 0xFFFF), v2 = (int16_t)(vv >> 16);
+			if (v <= line && v2 >= line)
+			{
+				act = true;
+				key = ((uint32_t)sh->c_u[c] + (uint32_t)(line - v) * (uint32_t)sh->c_step[c]) ^ 0x80000000u;
+			}
+		}
+		const unsigned m = __ballot_sync (0xFFFFFFFFu, act);
+		const int pos = n + __popc (m & lt);
 		if (act && pos < RC_AET_MAX)
 		{
-			hi[pos] = a.hi; lo[pos] = a.lo; sf[pos] = a.surfs;
+			sw->a.k.ku[pos] = key; sw->a.k.kidx[pos] = (uint16_t)c;
 		}
 		n += __popc (m);
 	}
@@ -243,82 +313,236 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan_sort (const __grid_con
 		if (lane == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
 		n = RC_AET_MAX;
 	}
-	int spanbase = 0, spanroom = 0, blockbase = 0, blockroom = 0, ok = 0;
-	if (lane == 0)
-	{
-		ok = rc_scan_alloc (&f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom);
-		li->spanbase = spanbase; li->blockbase = blockbase; li->n = ok ? n : -1; li->nsp = 0;
-	}
-	ok = __shfl_sync (0xFFFFFFFFu, ok, 0);
-	if (!ok)
-		return;
-	spanbase = __shfl_sync (0xFFFFFFFFu, spanbase, 0);
 	__syncwarp ();
-	uint2 *out = aetpool + spanbase;		/* the line's span room (n+1 slots) doubles as its AET list */
+
+	/* ---- B2: rank sort (keys are unique) ---- */
 	for (int i = lane; i < n; i += 32)
 	{
-		const unsigned long long h = hi[i], l = lo[i];
+		const uint32_t ui = sw->a.k.ku[i];
 		int rank = 0;
 		for (int j = 0; j < n; j++)
 		{
-			const unsigned long long hj = hi[j];
-			rank += (hj < h || (hj == h && lo[j] < l)) ? 1 : 0;
+			const uint32_t uj = sw->a.k.ku[j];
+			rank += (uj < ui) ? 1 : 0;
+			if (uj == ui && j != i)
+			{
+				unsigned long long hi_i, lo_i, hi_j, lo_j;
+				scan_full_key (sh, sw->a.k.kidx[i], line, &hi_i, &lo_i);
+				scan_full_key (sh, sw->a.k.kidx[j], line, &hi_j, &lo_j);
+				rank += (hi_j < hi_i || (hi_j == hi_i && lo_j < lo_i)) ? 1 : 0;
+			}
 		}
-		out[rank] = make_uint2 ((uint32_t)(h >> 32) ^ 0x80000000u, sf[i]);
+		sw->su[rank] = (int)(ui ^ 0x80000000u);
+		sw->ss[rank] = sh->c_sf[sw->a.k.kidx[i]];
 	}
-}
+	__syncwarp ();
 
-__global__ void k_scan_walk (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f,
-			     rc_lineinfo *lineinfo, const uint2 *aetpool, int lanes_per_warp)
-{
-	const int lane = threadIdx.x & 31;
-	if (lane >= lanes_per_warp)
-		return;
-	const int vi = blockIdx.x;
-	const int line = (blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
-	if (line >= f.height)
-		return;
-	rc_lineinfo *li = &lineinfo[(size_t)vi * f.height + line];
-	const int n = li->n;
-	if (n < 0)
-		return;
-	const rc_view_t *vw = &f.views[vi];
+	/* ---- B3: spans ---- */
 	rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
-	const int spanbase = li->spanbase, blockbase = li->blockbase;
-	rc_aet_global acc; acc.e = aetpool + spanbase;
-	int nblk = 0;
-	li->nsp = rc_span_walk (&f, vw, surfs, vi, line, acc, n, spanbase, n + 1, blockbase, &nblk);
-}
-
-__global__ void k_scan_blocks (const __grid_constant__ rc_frame_t f, const rc_lineinfo *lineinfo)
-{
-	const int lane = threadIdx.x & 31;
-	const int vi = blockIdx.x;
-	const int line = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if (line >= f.height)
-		return;
-	const rc_lineinfo li = lineinfo[(size_t)vi * f.height + line];
-	if (li.n < 0)
-		return;
-	const rc_view_t *vw = &f.views[vi];
-	const int spanroom = li.n + 1, blockroom = ((vw->vrect_w + 7) >> 3) + li.n + 1;
-	int nblk = 0;
-	for (int i = lane; i < li.nsp; i += 32)
+	const int head_u = vw->vrect_x, tail_u = vw->vrectright;
+	bool fallback = false;
+	int m = 0, nsp = 0;
+	for (int base = 0; base < n; base += 32)
 	{
-		const rc_span_t sp = f.spans[li.spanbase + i];
-		const int nb = (sp.count + 7) >> 3;
-		for (int b = 0; b < nb; b++)
-			f.blockspan[sp.firstblock + b] = li.spanbase + i;
-		if (i == li.nsp - 1)
-			nblk = sp.firstblock + nb - li.blockbase;
+		const int k = base + lane;
+		int s1 = 0, key = 0, insub = 0;
+		if (k < n)
+		{
+			s1 = (int)(sw->ss[k] >> 16);
+			if (s1)
+			{
+				const int4 g = *reinterpret_cast<const int4 *>(&surfs[s1]);	/* key, flags, face, insubmodel */
+				key = g.x; insub = g.w;
+			}
+		}
+		if (insub) fallback = true;
+		const unsigned mask = __ballot_sync (0xFFFFFFFFu, s1 != 0);
+		const int pos = m + __popc (mask & lt);
+		if (s1)
+		{
+			if (pos < SCAN_LEADS)
+			{
+				sw->lkey[pos] = key; sw->lsurf[pos] = (uint16_t)s1; sw->lk[pos] = (uint8_t)k;
+			}
+			sw->lidx[k] = (uint8_t)(pos < SCAN_LEADS ? pos : 0);
+		}
+		m += __popc (mask);
 	}
-	/* the lane that owned the last span knows how many blocks are in use */
+	if (m > SCAN_LEADS) fallback = true;
+	fallback = __any_sync (0xFFFFFFFFu, fallback);
+	__syncwarp ();
+	if (!fallback)
+	{
+		/* rank of every leading surface by key */
+		for (int i = lane; i < m; i += 32)
+		{
+			const int ki = sw->lkey[i];
+			int r = 0;
+			for (int j = 0; j < m; j++)
+			{
+				const int kj = sw->lkey[j];
+				r += (kj < ki) ? 1 : 0;
+				if (kj == ki && j != i) fallback = true;	/* a second leading edge of the same surface */
+			}
+			sw->lrank[i] = (uint8_t)r;
+			sw->rsurf[r] = sw->lsurf[i];
+			sw->tcount[i] = 0;
+		}
+		fallback = __any_sync (0xFFFFFFFFu, fallback);
+		__syncwarp ();
+	}
+	if (!fallback)
+	{
+		/* toggles, XOR scan, top surface after every edge, change points (x0 / sf reuse the key area) */
+		unsigned long long carry = 0ull;
+		int prevtop = 1, nc = 1;
+		if (lane == 0) { sw->a.sp.x0[0] = (int16_t)head_u; sw->a.sp.sf[0] = 1; }
+		for (int base = 0; base < n; base += 32)
+		{
+			const int k = base + lane;
+			unsigned long long tog = 0ull;
+			int iu = 0;
+			if (k < n)
+			{
+				const uint32_t sfk = sw->ss[k];
+				const int s0 = (int)(sfk & 0xFFFF), s1 = (int)(sfk >> 16);
+				iu = sw->su[k] >> 20;
+				if (s1)
+					tog ^= 1ull << sw->lrank[sw->lidx[k]];
+				if (s0)
+				{
+					int found = -1;
+					for (int j = 0; j < m; j++)
+						if (sw->lsurf[j] == s0) found = j;
+					if (found < 0 || (int)sw->lk[found] >= k)
+						fallback = true;		/* trailing edge without / before its leading edge */
+					else
+					{
+						tog ^= 1ull << sw->lrank[found];
+						atomicAdd (&sw->tcount[found], 1);
+					}
+				}
+			}
+			unsigned long long v = tog;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const unsigned long long t = __shfl_up_sync (0xFFFFFFFFu, v, o);
+				if (lane >= o) v ^= t;
+			}
+			v ^= carry;
+			carry = __shfl_sync (0xFFFFFFFFu, v, 31);
+			const int top = v ? (int)sw->rsurf[__ffsll ((long long)v) - 1] : 1;
+			int pt = __shfl_up_sync (0xFFFFFFFFu, top, 1);
+			if (lane == 0) pt = prevtop;
+			prevtop = __shfl_sync (0xFFFFFFFFu, top, 31);
+			const bool chg = k < n && top != pt;
+			const unsigned mask = __ballot_sync (0xFFFFFFFFu, chg);
+			const int pos = nc + __popc (mask & lt);
+			if (chg) { sw->a.sp.x0[pos] = (int16_t)iu; sw->a.sp.sf[pos] = (uint16_t)top; }
+			nc += __popc (mask);
+		}
+		__syncwarp ();
+		for (int i = lane; i < m; i += 32)
+			if (sw->tcount[i] > 1) fallback = true;			/* two trailing edges of one surface */
+		fallback = __any_sync (0xFFFFFFFFu, fallback);
+		if (!fallback)
+		{
+			/* runs between change points -> spans, empty runs dropped (in place: writes never pass reads) */
+			for (int base = 0; base < nc; base += 32)
+			{
+				const int j = base + lane;
+				int st = 0, en = 0, sf = 0;
+				bool valid = false;
+				if (j < nc)
+				{
+					st = sw->a.sp.x0[j]; en = (j + 1 < nc) ? (int)sw->a.sp.x0[j + 1] : tail_u; sf = sw->a.sp.sf[j];
+					valid = en > st;
+				}
+				__syncwarp ();
+				const unsigned mask = __ballot_sync (0xFFFFFFFFu, valid);
+				const int pos = nsp + __popc (mask & lt);
+				if (valid) { sw->a.sp.x0[pos] = (int16_t)st; sw->a.sp.x1[pos] = (int16_t)en; sw->a.sp.sf[pos] = (uint16_t)sf; }
+				nsp += __popc (mask);
+				__syncwarp ();
+			}
+		}
+	}
+	if (fallback)
+	{
+		/* the reference's own walk, by one lane (r_edge.c:536-563) */
+		__syncwarp ();
+		if (lane == 0)
+		{
+			rc_aet_sorted acc; acc.su = sw->su; acc.ss = sw->ss;
+			rc_linespans_t ls; ls.surf = sw->a.sp.sf; ls.u0 = sw->a.sp.x0; ls.u1 = sw->a.sp.x1; ls.cap = SCAN_SPANS;
+			nsp = rc_span_walk (&f, vw, surfs, line, acc, n, &ls);
+		}
+		nsp = __shfl_sync (0xFFFFFFFFu, nsp, 0);
+	}
+	__syncwarp ();
+
+	/* ---- C: publish ---- */
+	int nchk = 0;
+	if (nsp <= SCAN_SPANS)
+		for (int j = lane; j < nsp; j += 32)
+			nchk += rc_span_chk_count (sw->a.sp.x1[j] - sw->a.sp.x0[j]);
+	#pragma unroll
 	for (int o = 16; o; o >>= 1)
-		nblk = max (nblk, __shfl_xor_sync (0xFFFFFFFFu, nblk, o));
-	for (int i = li.nsp + lane; i < spanroom; i += 32)
-		f.spans[li.spanbase + i].count = 0;
-	for (int i = nblk + lane; i < blockroom; i += 32)
-		f.blockspan[li.blockbase + i] = -1;
+		nchk += __shfl_xor_sync (0xFFFFFFFFu, nchk, o);
+	unsigned long long old = 0ull;
+	if (lane == 0)
+		old = atomicAdd (&f.alloc[0], (unsigned long long)nsp | ((unsigned long long)nchk << 32));
+	old = __shfl_sync (0xFFFFFFFFu, old, 0);
+	const int spanbase = (int)(old & 0xFFFFFFFFu);
+	int chkbase = (int)(old >> 32);
+	if (nsp > SCAN_SPANS || spanbase + nsp > f.spancap || chkbase + nchk > f.chkcap)
+	{
+		if (lane == 0) atomicOr (f.status, RC_STAT_SPAN_POOL);
+		for (int c = lane; c < cw; c += 32)
+			cells[c] = -1;
+		return;
+	}
+	const int pixrow = (vi * f.height + line) * f.width;
+	const uint32_t vflags = ((uint32_t)(uint16_t)line) | ((vw->warp_index >= 0 ? 1u : 0u) << 16);
+	for (int base = 0; base < nsp; base += 32)
+	{
+		const int j = base + lane;
+		int u0 = 0, cnt = 0, sf = 0, c = 0;
+		if (j < nsp)
+		{
+			u0 = sw->a.sp.x0[j]; cnt = sw->a.sp.x1[j] - u0; sf = sw->a.sp.sf[j];
+			c = rc_span_chk_count (cnt);
+		}
+		int incl = c;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int t = __shfl_up_sync (0xFFFFFFFFu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (j < nsp)
+		{
+			uint4 *dst = reinterpret_cast<uint4 *>(&f.spans[spanbase + j]);
+			dst[0] = make_uint4 ((uint32_t)vi, (uint32_t)(vi * f.surfcap + sf), (uint32_t)(uint16_t)u0 | ((uint32_t)cnt << 16), vflags);
+			dst[1] = make_uint4 ((uint32_t)(pixrow + u0), (uint32_t)(chkbase + incl - c), 0u, 0u);
+			surfs[sf].hasspans = 1;
+		}
+		chkbase += __shfl_sync (0xFFFFFFFFu, incl, 31);
+	}
+	/* cell map: the span that covers pixel 8c (spans are sorted and disjoint) */
+	for (int c = lane; c < cw; c += 32)
+	{
+		const int x = c << 3;
+		int lo = 0, hi = nsp - 1, idx = -1;
+		while (lo <= hi)
+		{
+			const int mid = (lo + hi) >> 1;
+			if (sw->a.sp.x0[mid] <= x) { idx = mid; lo = mid + 1; }
+			else hi = mid - 1;
+		}
+		cells[c] = (idx >= 0 && x < sw->a.sp.x1[idx]) ? spanbase + idx : -1;
+	}
 }
 
 __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -434,13 +658,24 @@ __global__ void k_spanprep (const __grid_constant__ rc_world_t w, const __grid_c
 		rc_span_prep (&w, &f, t);
 }
 
-__global__ void k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* Draw stage: first one thread per screen-aligned 8-pixel cell of every row (full cells: one
+ * 8-byte colour store + one 16-byte z store, both aligned and coalesced across the warp), then
+ * one thread per span head.  Rows = views x height. */
+__global__ void __launch_bounds__(128) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	const unsigned cw = (unsigned)((f.width + 7) >> 3);
+	const unsigned ncells = (unsigned)(f.nviews * f.height) * cw;
+	const unsigned stride = gridDim.x * blockDim.x;
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += stride)
+	{
+		const unsigned row = t / cw;
+		rc_draw_cell (&w, &f, (int)row, (int)(t - row * cw));
+	}
 	unsigned long long a = f.alloc[0];
-	int nblocks = (int)(a >> 32);
-	if (nblocks > f.blockcap) nblocks = f.blockcap;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nblocks; t += gridDim.x * blockDim.x)
-		rc_draw_block (&w, &f, t);
+	unsigned nspans = (unsigned)(a & 0xFFFFFFFFu);
+	if (nspans > (unsigned)f.spancap) nspans = (unsigned)f.spancap;
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nspans; t += stride)
+		rc_draw_head (&w, &f, (int)t);
 }
 
 __global__ void k_warp (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -514,8 +749,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
 	g->d_particles = NULL; g->particlecap = 0; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
-	g->walk_lanes = getenv ("RC_WALK_LANES") ? atoi (getenv ("RC_WALK_LANES")) : 4;
-	if (g->walk_lanes < 1 || g->walk_lanes > 32) g->walk_lanes = 32;
+	cudaFuncSetAttribute (k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t));
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties (&prop, device);
 	g->numsms = prop.multiProcessorCount;
@@ -554,7 +788,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_blockspan); cudaFree (g->d_jobs); cudaFree (g->d_lineinfo); cudaFree (g->d_aetpool); cudaFree (g->d_chk); cudaFree (g->d_spanaux);
+	cudaFree (g->d_cellspan); cudaFree (g->d_jobs); cudaFree (g->d_chk);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -675,9 +909,10 @@ static void do_flush (rc_gpu_t *g, cudaStream_t s)
 static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int surfcap, int numfaces)
 {
 	size_t lines = g->height;
-	size_t spans = lines * g->spans_per_line, blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
+	size_t cw = (g->width + 7) / 8;
+	size_t spans = lines * g->spans_per_line, chks = spans + lines * (cw / 4 + 1);
 	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
-	       sizeof(rc_surf_t) * surfcap + (sizeof(rc_span_t) + 16) * spans + 16 * lines + 16 * blocks + 4 * blocks + sizeof(rc_cachejob_t) * 8 + 16;
+	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + 16 * chks + 4 * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
 static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
@@ -695,6 +930,11 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	int maxchunk = (int)(budget / pv);
 	if (maxchunk < 1) maxchunk = 1;
 	if (maxchunk > 65535) maxchunk = 65535;		/* one grid dimension per view */
+	{
+		/* pixel indices inside a chunk are 32-bit (rc_span_t.pixofs) */
+		long long pxcap = 0x7FFFFFFFll / ((long long)g->width * g->height);
+		if (maxchunk > pxcap) maxchunk = (int)(pxcap > 0 ? pxcap : 1);
+	}
 	if (g->maxviews > 0 && maxchunk > g->maxviews) maxchunk = g->maxviews;
 	int want = n < maxchunk ? n : maxchunk;
 	g->maxchunk = maxchunk;
@@ -702,8 +942,9 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	g->facecap = facecap; g->edgecap = edgecap; g->surfcap = surfcap; g->bsurfcap = want_bsurfs;
 	size_t lines = (size_t)g->height * want;
 	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
-	size_t blocks = lines * ((g->width + 7) / 8 + g->spans_per_line);
-	g->blockcap = (int)(blocks < 0x7FFFFFFF ? blocks : 0x7FFFFFFF);
+	const size_t cw = (g->width + 7) / 8;
+	size_t chks = (size_t)g->spancap + lines * (cw / 4 + 1);
+	g->chkcap = (int)(chks < 0x7FFFFFFF ? chks : 0x7FFFFFFF);
 	g->jobcap = want * 8 + 4096;
 	if (g->jobcap > want * surfcap) g->jobcap = want * surfcap;
 	CK (cudaMalloc (&g->d_views, sizeof(rc_view_t) * want));
@@ -720,11 +961,8 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
 	CK (cudaMalloc (&g->d_spans, sizeof(rc_span_t) * (size_t)g->spancap));
-	CK (cudaMalloc (&g->d_blockspan, sizeof(int) * (size_t)g->blockcap));
-	CK (cudaMalloc (&g->d_lineinfo, sizeof(rc_lineinfo) * lines));
-	CK (cudaMalloc (&g->d_aetpool, sizeof(uint2) * (size_t)g->spancap));
-	CK (cudaMalloc (&g->d_chk, sizeof(float) * 4 * (size_t)g->blockcap));
-	CK (cudaMalloc (&g->d_spanaux, sizeof(int) * 2 * (size_t)g->spancap));
+	CK (cudaMalloc (&g->d_cellspan, sizeof(int) * lines * cw));
+	CK (cudaMalloc (&g->d_chk, sizeof(float) * 4 * (size_t)g->chkcap));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
 	g->chunkcap = want;
 	return RC_OK;
@@ -747,8 +985,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
-	f.spans = g->d_spans; f.spancap = g->spancap; f.blockspan = g->d_blockspan; f.blockcap = g->blockcap;
-	f.chk = g->d_chk; f.spanaux = g->d_spanaux;
+	f.spans = g->d_spans; f.spancap = g->spancap; f.cellspan = g->d_cellspan;
+	f.chk = g->d_chk; f.chkcap = g->chkcap;
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
@@ -781,13 +1019,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	}
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
-	k_scan_sort<<<gs, SCAN_WARPS * 32, 0, s>>> (w, f, g->d_lineinfo, g->d_aetpool);
-	{
-		const int lpw = g->walk_lanes, wpb = 2;		/* lines per warp, warps per CTA */
-		dim3 gw (n, (g->height + lpw * wpb - 1) / (lpw * wpb));
-		k_scan_walk<<<gw, wpb * 32, 0, s>>> (w, f, g->d_lineinfo, g->d_aetpool, lpw);
-	}
-	k_scan_blocks<<<gs, SCAN_WARPS * 32, 0, s>>> (f, g->d_lineinfo);
+	k_scan<<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t), s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
@@ -841,7 +1073,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		g->stats.kernel_launches++;
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 9;
+	g->stats.kernel_launches += 7;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }
@@ -851,7 +1083,7 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 	unsigned long long a[4];
 	cudaMemcpy (a, g->d_alloc, sizeof(a), cudaMemcpyDeviceToHost);
 	g->stats.spans += (long long)(a[0] & 0xFFFFFFFFu);
-	g->stats.blocks += (long long)(a[0] >> 32);
+	g->stats.blocks += (long long)n * g->height * ((g->width + 7) / 8) + (long long)(a[0] & 0xFFFFFFFFu);
 	g->stats.cache_jobs += (long long)a[2];
 	std::vector<int> ne (n), nf (n);
 	cudaMemcpy (ne.data (), g->d_nedges, sizeof(int) * n, cudaMemcpyDeviceToHost);

@@ -37,6 +37,10 @@
 #define RC_DEBUG_PRINT(...) do { if (getenv ("RC_DEBUG")) fprintf (stderr, __VA_ARGS__); } while (0)
 #define RC_LDG(p) (*(p))
 #define RC_LDCG(p) (*(p))
+struct rc_u2 { uint32_t x, y; };
+struct rc_u4 { uint32_t x, y, z, w; };
+#define uint2 rc_u2
+#define uint4 rc_u4
 static inline int rc_host_add_i (int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long rc_host_add_ull (unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline int rc_host_or_i (int *p, int v) { int o = *p; *p = o | v; return o; }
@@ -77,10 +81,9 @@ typedef struct {
     int maxedges, maxsurfs;       /* the reference's r_maxedges / r_maxsurfs (overflow reporting) */
     /* scan */
     rc_span_t *spans; int spancap;
-    int *blockspan; int blockcap;
-    float *chk;                   /* [blockcap][4]: s/z, t/z, 1/z checkpoints every 4th subdivision of a span */
-    int *spanaux;                 /* [spancap][2]: izi at span start, izistep */
-    unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 blocks used  [1]: cache pool cursor  [2]: jobs */
+    int *cellspan;                /* [nviews][height][(width+7)/8]: span covering the first pixel of each 8-pixel screen cell, -1: none */
+    float *chk; int chkcap;       /* [chkcap][4]: s/z, t/z, 1/z checkpoints every 4th subdivision of a span */
+    unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 checkpoints used  [1]: cache pool cursor  [2]: jobs */
     /* surface cache */
     unsigned long long *cachekeys; int *cachevals; int cachemask;
     uint8_t *cachepool; long long cachecap;
@@ -1007,30 +1010,33 @@ struct rc_aet_array {
 	RC_HD2 int u (int k) const { return (int)((uint32_t)(a[k].hi >> 32) ^ 0x80000000u); }
 };
 
+/* spans of one scanline before they are published (left to right: the walk emits them in
+ * increasing u): surface slot, first column, end column */
+typedef struct {
+	uint16_t *surf;
+	int16_t  *u0, *u1;
+	int       cap;
+} rc_linespans_t;
+
 #define RC_EMIT_SPAN(sidx, ustart, uend)                                                      \
 	do {                                                                                  \
-		if (nsp < spanroom) {                                                         \
-			rc_span_t *_s = &f->spans[spanbase + nsp];                            \
-			int _c = (uend) - (ustart);                                           \
-			_s->view = vi; _s->surf = (uint16_t)(sidx); _s->v = (int16_t)line;    \
-			_s->u = (int16_t)(ustart); _s->count = (int16_t)_c;                   \
-			_s->firstblock = blockbase + nblk;                                    \
-			nblk += (_c + 7) >> 3;                                                \
-			nsp++;                                                                \
-			surfs[sidx].hasspans = 1;                                             \
+		if (nsp < out->cap) {                                                         \
+			out->surf[nsp] = (uint16_t)(sidx);                                    \
+			out->u0[nsp] = (int16_t)(ustart); out->u1[nsp] = (int16_t)(uend);     \
 		}                                                                             \
+		nsp++;                                                                        \
 	} while (0)
 
 /* R_GenerateSpans (r_edge.c:536-563) with R_TrailingEdge (:370-407), R_LeadingEdge (:411-527)
  * and R_CleanupSpan (:256-285) over the sorted active edges of one scanline.  The active
  * surface stack is a small array ordered top..background instead of a linked list through
  * surf_t; spanstate lives in the stack entry (a surface is in the stack iff spanstate >= 1).
- * Returns spans written; *pnblk = 8-pixel blocks they cover. */
+ * Returns the number of spans emitted into `out` (more than out->cap: overflow). */
 template <class AET>
-RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *surfs, int vi, int line,
-			const AET aet, int n, int spanbase, int spanroom, int blockbase, int *pnblk)
+RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_t *surfs, int line,
+			const AET aet, int n, const rc_linespans_t *out)
 {
-	int nsp = 0, nblk = 0;
+	int nsp = 0;
 	rc_stk_t stk[RC_STACK_MAX];
 	int depth = 1;
 	int nneg = 0;
@@ -1177,33 +1183,73 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *sur
 		RC_EMIT_SPAN (stk[0].surf, stk[0].last_u, edge_tail_u);
 	if (nneg)
 		RC_ATOMIC_OR_I (f->status, RC_STAT_STACK_OVERFLOW);	/* spanstate would leak into the next line */
-	*pnblk = nblk;
 	return nsp;
 }
 
-/* room reserved per scanline: at most n+1 spans, (w+15)/16 + n+1 16-pixel chunks; one allocation per line */
-RC_HD int rc_scan_alloc (const rc_frame_t *f, const rc_view_t *vw, int n, int *spanbase, int *spanroom, int *blockbase, int *blockroom)
+/* ---- publishing a scanline's spans -----------------------------------------------------------
+ * Work list of the draw stage (DESIGN.md "draw"): world spans tile the view rectangle, so the draw
+ * kernel runs one thread per SCREEN-ALIGNED 8-pixel cell (full cells store one aligned 8-byte colour
+ * word and one aligned 16-byte z word) plus one thread per span whose first column is not a multiple
+ * of 8 (its "head", the pixels up to the next cell boundary).  cellspan[(view, line, cell)] = the span
+ * that covers the cell's first pixel, -1 outside the view rectangle. */
+RC_HD int rc_span_chk_count (int count) { return (((count + 7) >> 3) + 3) >> 2; }	/* checkpoint every 4th subdivision */
+
+RC_HD void rc_write_span (const rc_frame_t *f, const rc_view_t *vw, int vi, int line, int si, int surf, int u0, int count, int chkbase)
 {
-	*spanroom = n + 1;
-	*blockroom = ((vw->vrect_w + 7) >> 3) + n + 1;
-	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)*spanroom | ((unsigned long long)*blockroom << 32));
-	*spanbase = (int)(old & 0xFFFFFFFFu);
-	*blockbase = (int)(old >> 32);
-	if (*spanbase + *spanroom > f->spancap || *blockbase + *blockroom > f->blockcap)
+	rc_span_t *s = &f->spans[si];
+	s->view = vi; s->gsurf = vi * f->surfcap + surf;
+	s->u = (int16_t)u0; s->count = (int16_t)count; s->v = (int16_t)line; s->flags = (uint16_t)(vw->warp_index >= 0 ? 1 : 0);
+	s->pixofs = (vi * f->height + line) * f->width + u0;
+	s->chkbase = chkbase; s->izi0 = 0; s->pad = 0;
+}
+
+RC_HD void rc_line_clear (const rc_frame_t *f, int vi, int line)
+{
+	const int cw = (f->width + 7) >> 3;
+	int *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
+	for (int c = 0; c < cw; c++)
+		cells[c] = -1;
+}
+
+/* serial version (host simulation; the GPU scan kernel does the same with a warp) */
+RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *surfs, int vi, int line, const rc_linespans_t *ls, int nsp)
+{
+	int nchk = 0;
+	for (int i = 0; i < nsp; i++)
+		nchk += rc_span_chk_count (ls->u1[i] - ls->u0[i]);
+	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)nsp | ((unsigned long long)nchk << 32));
+	int spanbase = (int)(old & 0xFFFFFFFFu), chkbase = (int)(old >> 32);
+	if (nsp > ls->cap || spanbase + nsp > f->spancap || chkbase + nchk > f->chkcap)
 	{
 		RC_ATOMIC_OR_I (f->status, RC_STAT_SPAN_POOL);
-		return 0;
+		rc_line_clear (f, vi, line);
+		return;
 	}
-	return 1;
+	const int cw = (f->width + 7) >> 3;
+	int *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
+	for (int c = 0; c < cw; c++)
+		cells[c] = -1;
+	for (int i = 0; i < nsp; i++)
+	{
+		const int u0 = ls->u0[i], cnt = ls->u1[i] - u0;
+		rc_write_span (f, vw, vi, line, spanbase + i, ls->surf[i], u0, cnt, chkbase);
+		chkbase += rc_span_chk_count (cnt);
+		surfs[ls->surf[i]].hasspans = 1;
+		for (int c = (u0 + 7) >> 3; c <= (u0 + cnt - 1) >> 3; c++)
+			cells[c] = spanbase + i;
+	}
 }
 
 /* One thread per (view, scanline), fully serial: the reference implementation of the scan
- * stage (host simulation; the GPU runs the warp-cooperative k_scan built from the same parts). */
+ * stage (host simulation; the GPU runs the warp-per-line k_scan built from the same parts). */
 RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int line)
 {
 	const rc_view_t *vw = &f->views[vi];
 	if (line < vw->vrect_y || line >= vw->vrectbottom)
+	{
+		rc_line_clear (f, vi, line);
 		return;
+	}
 	const rc_edge_t *edges = f->edges + (size_t)vi * f->edgecap;
 	rc_surf_t *surfs = f->surfs + (size_t)vi * f->surfcap;
 	int E = f->nedges[vi];
@@ -1229,21 +1275,12 @@ RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int l
 		}
 		aet[j] = a;
 	}
-	int spanbase, spanroom, blockbase, blockroom, nblk = 0;
-	if (!rc_scan_alloc (f, vw, n, &spanbase, &spanroom, &blockbase, &blockroom))
-		return;
+	uint16_t lsurf[RC_AET_MAX + 2];
+	int16_t lu0[RC_AET_MAX + 2], lu1[RC_AET_MAX + 2];
+	rc_linespans_t ls; ls.surf = lsurf; ls.u0 = lu0; ls.u1 = lu1; ls.cap = RC_AET_MAX + 2;
 	rc_aet_array acc; acc.a = aet;
-	int nsp = rc_span_walk (f, vw, surfs, vi, line, acc, n, spanbase, spanroom, blockbase, &nblk);
-	for (int i = 0; i < nsp; i++)
-	{
-		const rc_span_t *sp = &f->spans[spanbase + i];
-		for (int b = 0; b < ((sp->count + 7) >> 3); b++)
-			f->blockspan[sp->firstblock + b] = spanbase + i;
-	}
-	for (int i = nsp; i < spanroom; i++)
-		f->spans[spanbase + i].count = 0;
-	for (int i = nblk; i < blockroom; i++)
-		f->blockspan[blockbase + i] = -1;
+	int nsp = rc_span_walk (f, vw, surfs, line, acc, n, &ls);
+	rc_line_publish (f, vw, surfs, vi, line, &ls, nsp);
 }
 
 /* surf_t slots of a view in use: 1 (background), 2 .. nfaces+1 (world faces), then the brush-entity
@@ -1359,6 +1396,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 	s->miplevel = -1;		/* reused as the cache-table slot to resolve, -1: none */
 	s->drawflags = s->flags;
 	s->d_zistepu_draw = s->d_zistepu;
+	s->izistep = rc_f2i (s->d_zistepu * 0x8000 * 0x10000);
 	if ((s->flags & RC_SURF_DRAWSKY) && !vw->fastsky)
 	{
 		s->pad = RC_SRC_SKY;		/* d_edge.c:186-193; z uses the surface's own 1/z plane */
@@ -1370,6 +1408,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		s->cachewidth = (s->flags & RC_SURF_DRAWBACKGROUND) ? vw->clearcolor : vw->skycolor;
 		s->d_ziorigin = -0.9; s->d_zistepu = 0; s->d_zistepv = 0;
 		s->d_zistepu_draw = 0;
+		s->izistep = 0;
 		return;
 	}
 	const rc_face_t *fa = &w->faces[s->face];
@@ -1619,34 +1658,32 @@ RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int
 
 /* ------------------------------------------------------------------ stage 6: draw ------ */
 /* One thread per span, before drawing: the per-span part of D_DrawSpans8 / D_DrawZSpans.
- *   spanaux[si] = { izi at the span start, izistep }                    (d_scan.c:399-413)
- *   chk[firstblock + 4j] = (s/z, t/z, 1/z) after 4j subdivision steps    (d_scan.c:278-315)
+ *   span.izi0 = 1/z at the span start in D_DrawZSpans fixed point          (d_scan.c:399-413)
+ *   chk[chkbase + j] = (s/z, t/z, 1/z) after 4j subdivision steps           (d_scan.c:278-315)
  * The float accumulators of D_DrawSpans8 are sequentially rounded sums, so subdivision k needs
  * k adds; checkpoints every 4 subdivisions bound the replay in the draw kernel to 3 steps. */
 RC_HD void rc_span_prep (const rc_world_t *w, const rc_frame_t *f, int si)
 {
-	const rc_span_t sp = f->spans[si];
-	if (sp.count <= 0)
+	rc_span_t *sp = &f->spans[si];
+	const int count = sp->count;
+	if (count <= 0)
 		return;
-	const rc_view_t *vw = &f->views[sp.view];
-	const rc_surf_t *s = f->surfs + (size_t)sp.view * f->surfcap + sp.surf;
-	const float du = (float)sp.u, dv = (float)sp.v;
+	const rc_surf_t *s = f->surfs + sp->gsurf;
+	const float du = (float)sp->u, dv = (float)sp->v;
 	const float zistepu = s->d_zistepu, zistepv = s->d_zistepv, ziorigin = s->d_ziorigin;
-	const int izistep = rc_f2i (zistepu * 0x8000 * 0x10000);
 	const double zid = ziorigin + dv*zistepv + du*zistepu;
-	f->spanaux[2 * si + 0] = rc_d2i (zid * 0x8000 * 0x10000);
-	f->spanaux[2 * si + 1] = izistep;
+	sp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
 	if (s->pad != RC_SRC_POOL && s->pad != RC_SRC_TEXELS)
 		return;
 	const float sdivz8stepu = s->d_sdivzstepu * 8, tdivz8stepu = s->d_tdivzstepu * 8, zi8stepu = zistepu * 8;
 	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*s->d_sdivzstepu;
 	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*s->d_tdivzstepu;
 	float zi = ziorigin + dv*zistepv + du*zistepu;
-	const int nblocks = (sp.count + 7) >> 3;
-	float *chk = f->chk + 4 * (size_t)sp.firstblock;
-	for (int j = 0; j < nblocks; j += 4)
+	const int nsub = (count + 7) >> 3;
+	float *chk = f->chk + 4 * (size_t)sp->chkbase;
+	for (int j = 0; j < nsub; j += 4)
 	{
-		chk[4 * j + 0] = sdivz; chk[4 * j + 1] = tdivz; chk[4 * j + 2] = zi; chk[4 * j + 3] = 0;
+		chk[j + 0] = sdivz; chk[j + 1] = tdivz; chk[j + 2] = zi; chk[j + 3] = 0;
 		for (int q = 0; q < 4; q++)
 		{
 			sdivz += sdivz8stepu;
@@ -1656,24 +1693,10 @@ RC_HD void rc_span_prep (const rc_world_t *w, const rc_frame_t *f, int si)
 	}
 }
 
-/* stores `cnt` (1..8) bytes held little-endian in (lo, hi) at p, using the widest aligned
- * stores the address allows: fewer, fuller L1/L2 sector writes than 8 byte stores */
-RC_HD void rc_store_bytes8 (uint8_t *p, uint32_t lo, uint32_t hi, int cnt)
-{
-	unsigned long long v = (unsigned long long)lo | ((unsigned long long)hi << 32);
-	int head = (int)((4 - ((size_t)p & 3)) & 3);
-	if (head > cnt) head = cnt;
-	for (int i = 0; i < head; i++) { p[i] = (uint8_t)v; v >>= 8; }
-	p += head; cnt -= head;
-	if (cnt >= 4) { *(uint32_t *)p = (uint32_t)v; v >>= 32; p += 4; cnt -= 4; }
-	if (cnt >= 4) { *(uint32_t *)p = (uint32_t)v; v >>= 32; p += 4; cnt -= 4; }
-	for (int i = 0; i < cnt; i++) { p[i] = (uint8_t)v; v >>= 8; }
-}
-
 /* the 48 bytes of rc_surf_t the draw kernel needs, fetched with three 16-byte loads */
 typedef struct {
 	int   cacheofs, cachewidth, srckind, flags;
-	float sdivzstepu, tdivzstepu, zistepu, pad1;
+	float sdivzstepu, tdivzstepu, zistepu; int izistep;
 	int   sadjust, tadjust, bbextents, bbextentt;
 } rc_drawsurf_t;
 
@@ -1684,232 +1707,313 @@ RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
 	const uint4 a = __ldg (q), b = __ldg (q + 1), c = __ldg (q + 2);
 	rc_drawsurf_t d;
 	d.cacheofs = (int)a.x; d.cachewidth = (int)a.y; d.srckind = (int)a.z; d.flags = (int)a.w;
-	d.sdivzstepu = __uint_as_float (b.x); d.tdivzstepu = __uint_as_float (b.y); d.zistepu = __uint_as_float (b.z); d.pad1 = 0;
+	d.sdivzstepu = __uint_as_float (b.x); d.tdivzstepu = __uint_as_float (b.y); d.zistepu = __uint_as_float (b.z); d.izistep = (int)b.w;
 	d.sadjust = (int)c.x; d.tadjust = (int)c.y; d.bbextents = (int)c.z; d.bbextentt = (int)c.w;
 	return d;
 }
 RC_HD rc_span_t rc_load_span (const rc_span_t *p)
 {
-	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p));
+	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p)), b = __ldg (reinterpret_cast<const uint4 *>(p) + 1);
 	rc_span_t s;
-	s.view = (int)a.x; s.surf = (uint16_t)(a.y & 0xFFFF); s.v = (int16_t)(a.y >> 16);
-	s.u = (int16_t)(a.z & 0xFFFF); s.count = (int16_t)(a.z >> 16); s.firstblock = (int)a.w;
+	s.view = (int)a.x; s.gsurf = (int)a.y; s.u = (int16_t)(a.z & 0xFFFF); s.count = (int16_t)(a.z >> 16);
+	s.v = (int16_t)(a.w & 0xFFFF); s.flags = (uint16_t)(a.w >> 16);
+	s.pixofs = (int)b.x; s.chkbase = (int)b.y; s.izi0 = (int)b.z; s.pad = 0;
 	return s;
 }
-RC_HD uint32_t rc_zpair (int a, int b) { return __byte_perm ((uint32_t)a, (uint32_t)b, 0x7632); }
+RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return __byte_perm (a, b, 0x5410); }
 #else
 RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
 {
 	rc_drawsurf_t d;
 	d.cacheofs = s->cacheofs; d.cachewidth = s->cachewidth; d.srckind = s->pad; d.flags = s->drawflags;
-	d.sdivzstepu = s->d_sdivzstepu; d.tdivzstepu = s->d_tdivzstepu; d.zistepu = s->d_zistepu_draw; d.pad1 = 0;
+	d.sdivzstepu = s->d_sdivzstepu; d.tdivzstepu = s->d_tdivzstepu; d.zistepu = s->d_zistepu_draw; d.izistep = s->izistep;
 	d.sadjust = s->sadjust; d.tadjust = s->tadjust; d.bbextents = s->bbextents; d.bbextentt = s->bbextentt;
 	return d;
 }
 RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
-RC_HD uint32_t rc_zpair (int a, int b) { return (((uint32_t)a >> 16) & 0xFFFFu) | ((uint32_t)b & 0xFFFF0000u); }
+RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 16); }
 #endif
 
-/* One thread per 8-pixel subdivision of a span: D_DrawSpans8 (d_scan.c:254-386) /
- * Turbulent8 (d_scan.c:121-251) / D_DrawSkyScans8 (d_sky.c:58) / D_DrawSolidSurface
- * (d_edge.c:72-90) fused with D_DrawZSpans (d_scan.c:388-439).  Span, surface and checkpoint
- * records come in as 16-byte loads; the eight texel gathers are issued together, results are
- * packed in registers and written with aligned word stores. */
-RC_HD void rc_draw_block (const rc_world_t *w, const rc_frame_t *f, int t)
+/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
+ * accumulators -> 16.16, clamped to [lo, bbextent] */
+RC_HD void rc_boundary_st (const rc_drawsurf_t *ds, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
 {
-	const int si = RC_LDG (&f->blockspan[t]);
-	if (si < 0)
-		return;
-	const rc_span_t sp = rc_load_span (&f->spans[si]);
-	const int k = t - sp.firstblock;
-	const rc_view_t *vw = &f->views[sp.view];
-	const rc_drawsurf_t ds = rc_load_drawsurf (f->surfs + (size_t)sp.view * f->surfcap + sp.surf);
-	const int first = k << 3;
-	const int total = sp.count - first;		/* pixels from this subdivision to the end of the span */
-	const int cnt = total > 8 ? 8 : total;
-	const size_t viewpix = (size_t)f->width * f->height;
-	uint8_t *pdest = (vw->warp_index < 0 ? f->fb + viewpix * sp.view : f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H)) +
-			 (size_t)vw->screenwidth * sp.v + sp.u + first;
+	const float z = (float)0x10000 / zi;
+	int ss = rc_addw (rc_f2i (sdivz * z), ds->sadjust);
+	int tt = rc_addw (rc_f2i (tdivz * z), ds->tadjust);
+	if (ss > ds->bbextents) ss = ds->bbextents; else if (ss < lo) ss = lo;
+	if (tt > ds->bbextentt) tt = ds->bbextentt; else if (tt < lo) tt = lo;
+	*ps = ss; *pt = tt;
+}
+
+/* truncating division by 1..7 (the last-subdivision step, d_scan.c:364-365) without the generic
+ * 32-bit divide: float estimate, exact integer correction */
+RC_HD int rc_div_small (int a, int d)
+{
+#ifdef __CUDACC__
+	if (a >= (1 << 24) || a <= -(1 << 24))
+		return a / d;				/* not exact in float: turbulent surfaces with huge extents */
+	int q = (int)((float)a * (1.0f / (float)d));	/* a is exact in float: off by at most one */
+	int r = a - q * d;
+	/* bring r into the range truncation leaves: same sign as a, |r| < d */
+	while (r >= d) { r -= d; q++; }
+	while (r <= -d) { r += d; q--; }
+	if (a >= 0 && r < 0) { q--; r += d; }
+	else if (a < 0 && r > 0) { q++; r -= d; }
+	return q;
+#else
+	return a / d;
+#endif
+}
+
+/* One draw work item (D_DrawSpans8 d_scan.c:254-386 / Turbulent8 :121-251 / D_DrawSkyScans8
+ * d_sky.c:58 / D_DrawSolidSurface d_edge.c:72-90, fused with D_DrawZSpans d_scan.c:388-439):
+ * `cnt` (1..8) consecutive pixels of span `si` starting `rel` pixels into the span.
+ *   cell items: the screen-aligned 8-pixel cell `t` (rel = 8*cell - u of the span covering it,
+ *               cnt = 8 unless the span ends inside the cell)
+ *   head items: a span's pixels up to the first cell boundary (rel = 0, cnt < 8)
+ * The reference's 8-pixel subdivision is span relative, so the item touches subdivision
+ * k = rel >> 3 from pixel a = rel & 7 on, and subdivision k+1 when a + cnt > 8.  Everything is
+ * computed for 8 pixels and predicated on j < cnt: no per-count code paths. */
+RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, const rc_span_t sp, int rel, int cnt)
+{
+	const rc_drawsurf_t ds = rc_load_drawsurf (f->surfs + sp.gsurf);
 	const int srckind = ds.srckind;
+	const int pix = sp.pixofs + rel;
+	uint8_t *pdest;
+	const rc_view_t *vw = &f->views[sp.view];		/* only dereferenced on the rare paths */
+	if (!(sp.flags & 1))
+		pdest = f->fb + pix;
+	else
+		pdest = f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H) + RC_WARP_W * sp.v + sp.u + rel;
 
 	/* ---- z (D_DrawZSpans) ---- */
 	if (f->zb)
 	{
-		const int izi0 = RC_LDG (&f->spanaux[2 * si]), izistep = RC_LDG (&f->spanaux[2 * si + 1]);
-		const size_t zindex = (size_t)vw->zwidth * sp.v + sp.u;
-		int16_t *pz = f->zb + viewpix * sp.view + zindex + first;
-		const int a0 = (int)(zindex & 1);
-		const int izif = rc_addw (izi0, rc_mulw (first, izistep));
-		const int prev0 = rc_addw (izif, -izistep), izil = rc_addw (izif, rc_mulw (7, izistep));
-		if (cnt == 8 && (prev0 | izif | izil) >= 0)
+		int16_t *pz = f->zb + pix;
+		const int izistep = ds.izistep;
+		int zz[8];
+		zz[0] = rc_addw (sp.izi0, rc_mulw (rel, izistep));
+		#pragma unroll
+		for (int j = 1; j < 8; j++)
+			zz[j] = rc_addw (zz[j-1], izistep);
+		const int prev0 = rc_addw (zz[0], -izistep);
+		uint32_t zs[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			zs[j] = ((uint32_t)zz[j] >> 16);
+		if ((prev0 | zz[0] | zz[1] | zz[2] | zz[3] | zz[4] | zz[5] | zz[6] | zz[7]) < 0)
 		{
-			/* no negative 1/z in reach: plain (izi >> 16) for every pixel, two per word */
-			int z0 = izif, z1 = rc_addw (z0, izistep), z2 = rc_addw (z1, izistep), z3 = rc_addw (z2, izistep);
-			int z4 = rc_addw (z3, izistep), z5 = rc_addw (z4, izistep), z6 = rc_addw (z5, izistep), z7 = rc_addw (z6, izistep);
-			if (((size_t)pz & 3) == 0)
+			/* a negative 1/z in reach: the second short of each 32-bit store of the reference gets the
+			 * sign extension of the first OR-ed in (d_scan.c:421-427: ltemp = izi >> 16 on a signed izi) */
+			const int a0 = (sp.pixofs - sp.view * f->width * f->height) & 1;	/* (zwidth*v + u) & 1: the short stored before the pairs */
+			const int doublecount = (sp.count - a0) >> 1;
+			int prev = prev0;
+			#pragma unroll
+			for (int j = 0; j < 8; j++)
 			{
-				uint32_t *pw = (uint32_t *)pz;
-				pw[0] = rc_zpair (z0, z1); pw[1] = rc_zpair (z2, z3); pw[2] = rc_zpair (z4, z5); pw[3] = rc_zpair (z6, z7);
+				const int r = rel + j - a0;
+				if (prev < 0 && r >= 0 && (r & 1) && (r >> 1) < doublecount)
+					zs[j] = 0xFFFFu;
+				prev = zz[j];
 			}
-			else
-			{
-				uint32_t *pw = (uint32_t *)(pz + 1);
-				pz[0] = (int16_t)(z0 >> 16);
-				pw[0] = rc_zpair (z1, z2); pw[1] = rc_zpair (z3, z4); pw[2] = rc_zpair (z5, z6);
-				pz[7] = (int16_t)(z7 >> 16);
-			}
+		}
+		if (cnt == 8 && ((size_t)pz & 15) == 0)
+		{
+			uint4 q;
+			q.x = rc_zpair (zs[0], zs[1]); q.y = rc_zpair (zs[2], zs[3]); q.z = rc_zpair (zs[4], zs[5]); q.w = rc_zpair (zs[6], zs[7]);
+			*reinterpret_cast<uint4 *>(pz) = q;
 		}
 		else
 		{
-			const int doublecount = (sp.count - a0) >> 1;
-			int izi = izif, prev = prev0;
-			for (int j = 0; j < cnt; j++)
-			{
-				uint32_t zval = (uint32_t)(izi >> 16) & 0xFFFFu;
-				const int rel = first + j - a0;
-				/* second short of a 32-bit store: the first one's sign extension is OR-ed in
-				 * (d_scan.c:421-427: ltemp = izi >> 16 on a signed izi) */
-				if (prev < 0 && rel >= 0 && (rel & 1) && (rel >> 1) < doublecount)
-					zval = 0xFFFFu;
-				pz[j] = (int16_t)zval;
-				prev = izi;
-				izi = rc_addw (izi, izistep);
-			}
+			#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (j < cnt)
+					pz[j] = (int16_t)zs[j];
 		}
 	}
 
 	/* ---- colour ---- */
+	uint32_t px[8];
 	if (srckind == RC_SRC_SOLID)
 	{
-		const uint32_t c = (uint32_t)(ds.cachewidth & 0xFF) * 0x01010101u;
-		rc_store_bytes8 (pdest, c, c, cnt);
-		return;
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			px[j] = (uint32_t)(ds.cachewidth & 0xFF);
 	}
-	if (srckind == RC_SRC_SKY)
+	else if (srckind == RC_SRC_SKY)
 	{
-		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form */
-		const int b32 = first >> 5;			/* which 32-pixel run of the span */
-		const int u0 = sp.u + (b32 << 5);
-		int remaining = sp.count - (b32 << 5);		/* pixels from the start of this run */
-		int spancount = remaining >= 32 ? 32 : remaining;
-		int ss, tt, snext = 0, tnext = 0, sstep = 0, tstep = 0;
-		rc_sky_uv_to_st (vw, u0, sp.v, &ss, &tt);
-		if (remaining - spancount)
+		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form; an item
+		 * touches at most two of a span's 32-pixel runs */
+		int cur = -1, ss = 0, tt = 0, sstep = 0, tstep = 0;
+		unsigned long long packed = 0ull;		/* a rolled loop must not index px[] (registers) */
+		#pragma unroll 1
+		for (int j = 0; j < cnt; j++)
 		{
-			rc_sky_uv_to_st (vw, u0 + spancount, sp.v, &snext, &tnext);
-			sstep = (snext - ss) >> 5;
-			tstep = (tnext - tt) >> 5;
+			const int pos = rel + j;
+			const int b32 = pos >> 5;			/* which 32-pixel run of the span */
+			if (b32 != cur)
+			{
+				const int u0 = sp.u + (b32 << 5);
+				const int remaining = sp.count - (b32 << 5);	/* pixels from the start of this run */
+				const int spancount = remaining >= 32 ? 32 : remaining;
+				int snext = 0, tnext = 0;
+				cur = b32; sstep = 0; tstep = 0;
+				rc_sky_uv_to_st (vw, u0, sp.v, &ss, &tt);
+				if (remaining - spancount)
+				{
+					rc_sky_uv_to_st (vw, u0 + spancount, sp.v, &snext, &tnext);
+					sstep = (snext - ss) >> 5;
+					tstep = (tnext - tt) >> 5;
+				}
+				else
+				{
+					const int spancountminus1 = spancount - 1;
+					if (spancountminus1 > 0)
+					{
+						rc_sky_uv_to_st (vw, u0 + spancountminus1, sp.v, &snext, &tnext);
+						sstep = (snext - ss) / spancountminus1;
+						tstep = (tnext - tt) / spancountminus1;
+					}
+				}
+				const int within = pos & 31;
+				ss = rc_addw (ss, rc_mulw (within, sstep));
+				tt = rc_addw (tt, rc_mulw (within, tstep));
+			}
+			packed |= (unsigned long long)rc_sky_texel (w, vw, ss, tt) << (8 * j);
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
+		}
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			px[j] = (uint32_t)(packed >> (8 * j)) & 0xFFu;
+	}
+	else
+	{
+		const int turb = (ds.flags & RC_SURF_DRAWTURB) != 0;
+		const uint8_t *pbase = (srckind == RC_SRC_TEXELS ? w->texels : f->cachepool) + ds.cacheofs;
+		const int cachewidth = ds.cachewidth;
+		const int k = rel >> 3, a = rel & 7;
+		const float sdivz8stepu = ds.sdivzstepu * 8, tdivz8stepu = ds.tdivzstepu * 8, zi8stepu = ds.zistepu * 8;
+		const float *chk = f->chk + 4 * (size_t)(sp.chkbase + (k >> 2));
+		float sdivz = RC_LDG (&chk[0]), tdivz = RC_LDG (&chk[1]), zi = RC_LDG (&chk[2]);
+		for (int j = 0; j < (k & 3); j++)
+		{
+			sdivz += sdivz8stepu;
+			tdivz += tdivz8stepu;
+			zi += zi8stepu;
+		}
+		/* boundary k: subdivision 0 starts from the span-start clamp, later ones from a `snext` clamp */
+		int s0, t0, s1, t1, s2 = 0, t2 = 0, sstep0 = 0, tstep0 = 0, sstep1 = 0, tstep1 = 0;
+		rc_boundary_st (&ds, sdivz, tdivz, zi, k ? 8 : 0, &s0, &t0);
+		int left = sp.count - (k << 3);		/* pixels from the start of subdivision k to the end of the span */
+		if (left > 8)
+		{
+			sdivz += sdivz8stepu; tdivz += tdivz8stepu; zi += zi8stepu;
+			rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s1, &t1);
+			sstep0 = (s1 - s0) >> 3;
+			tstep0 = (t1 - t0) >> 3;
+			if (a + cnt > 8)
+			{
+				/* the item runs on into subdivision k+1 */
+				left -= 8;
+				if (left > 8)
+				{
+					sdivz += sdivz8stepu; tdivz += tdivz8stepu; zi += zi8stepu;
+					rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s2, &t2);
+					sstep1 = (s2 - s1) >> 3;
+					tstep1 = (t2 - t1) >> 3;
+				}
+				else
+				{
+					const float m1 = (float)(left - 1);
+					sdivz += ds.sdivzstepu * m1; tdivz += ds.tdivzstepu * m1; zi += ds.zistepu * m1;
+					rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s2, &t2);
+					if (left > 1)
+					{
+						sstep1 = rc_div_small (s2 - s1, left - 1);
+						tstep1 = rc_div_small (t2 - t1, left - 1);
+					}
+				}
+			}
 		}
 		else
 		{
-			int spancountminus1 = spancount - 1;
-			if (spancountminus1 > 0)
+			const float m1 = (float)(left - 1);
+			sdivz += ds.sdivzstepu * m1; tdivz += ds.tdivzstepu * m1; zi += ds.zistepu * m1;
+			rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s1, &t1);
+			if (left > 1)
 			{
-				rc_sky_uv_to_st (vw, u0 + spancountminus1, sp.v, &snext, &tnext);
-				sstep = (snext - ss) / spancountminus1;
-				tstep = (tnext - tt) / spancountminus1;
+				sstep0 = rc_div_small (s1 - s0, left - 1);
+				tstep0 = rc_div_small (t1 - t0, left - 1);
 			}
 		}
-		const int within = first & 31;
-		ss = rc_addw (ss, rc_mulw (within, sstep));
-		tt = rc_addw (tt, rc_mulw (within, tstep));
-		for (int j = 0; j < cnt; j++)
-		{
-			pdest[j] = rc_sky_texel (w, vw, ss, tt);
-			ss = rc_addw (ss, sstep);
-			tt = rc_addw (tt, tstep);
-		}
-		return;
-	}
-	const int turb = (ds.flags & RC_SURF_DRAWTURB) != 0;
-	const uint8_t *pbase = (srckind == RC_SRC_TEXELS ? w->texels : f->cachepool) + ds.cacheofs;
-	const int cachewidth = ds.cachewidth;
-	const float sdivz8stepu = ds.sdivzstepu * 8, tdivz8stepu = ds.tdivzstepu * 8, zi8stepu = ds.zistepu * 8;
-	const float *chk = f->chk + 4 * (size_t)(sp.firstblock + (k & ~3));
-	float sdivz = RC_LDG (&chk[0]), tdivz = RC_LDG (&chk[1]), zi = RC_LDG (&chk[2]);
-	for (int j = 0; j < (k & 3); j++)
-	{
-		sdivz += sdivz8stepu;
-		tdivz += tdivz8stepu;
-		zi += zi8stepu;
-	}
-	float z = (float)0x10000 / zi;
-	int ss = rc_addw (rc_f2i (sdivz * z), ds.sadjust);
-	int tt = rc_addw (rc_f2i (tdivz * z), ds.tadjust);
-	const int lo = k ? 8 : 0;	/* subdivision 0 starts from the span-start clamp, later ones from a `snext` clamp */
-	if (ss > ds.bbextents) ss = ds.bbextents; else if (ss < lo) ss = lo;
-	if (tt > ds.bbextentt) tt = ds.bbextentt; else if (tt < lo) tt = lo;
-
-	int snext, tnext, sstep = 0, tstep = 0;
-	if (total > 8)
-	{
-		sdivz += sdivz8stepu;
-		tdivz += tdivz8stepu;
-		zi += zi8stepu;
-	}
-	else
-	{
-		float spancountminus1 = (float)(cnt - 1);
-		sdivz += ds.sdivzstepu * spancountminus1;
-		tdivz += ds.tdivzstepu * spancountminus1;
-		zi += ds.zistepu * spancountminus1;
-	}
-	z = (float)0x10000 / zi;
-	snext = rc_addw (rc_f2i (sdivz * z), ds.sadjust);
-	if (snext > ds.bbextents) snext = ds.bbextents; else if (snext < 8) snext = 8;
-	tnext = rc_addw (rc_f2i (tdivz * z), ds.tadjust);
-	if (tnext > ds.bbextentt) tnext = ds.bbextentt; else if (tnext < 8) tnext = 8;
-	if (total > 8)
-	{
-		sstep = (snext - ss) >> 3;
-		tstep = (tnext - tt) >> 3;
-	}
-	else if (cnt > 1)
-	{
-		sstep = (snext - ss) / (cnt - 1);
-		tstep = (tnext - tt) / (cnt - 1);
-	}
-	uint32_t plo = 0, phi = 0;
-	if (!turb && cnt == 8)
-	{
-		/* the common case, fully unrolled: 8 independent gathers, then one packed store */
-		uint32_t px[8];
+		int ss = rc_addw (s0, rc_mulw (a, sstep0)), tt = rc_addw (t0, rc_mulw (a, tstep0));
+		const int *turbtab = w->sintable;
+		if (turb)
+			turbtab += vw->turbphase;
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
 		{
-			px[j] = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
-			ss = rc_addw (ss, sstep);
-			tt = rc_addw (tt, tstep);
+			if (a + j == 8)
+			{
+				ss = s1; tt = t1; sstep0 = sstep1; tstep0 = tstep1;
+			}
+			px[j] = 0;
+			if (j < cnt)
+			{
+				if (!turb)
+					px[j] = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
+				else
+				{
+					const int sm = ss & ((RC_CYCLE << 16) - 1), tm = tt & ((RC_CYCLE << 16) - 1);
+					const int sturb = ((sm + RC_LDG (&turbtab[(tm >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
+					const int tturb = ((tm + RC_LDG (&turbtab[(sm >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
+					px[j] = RC_LDG (&pbase[(tturb << 6) + sturb]);
+				}
+			}
+			ss = rc_addw (ss, sstep0);
+			tt = rc_addw (tt, tstep0);
 		}
-		plo = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
-		phi = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
 	}
-	else if (!turb)
+	if (cnt == 8 && ((size_t)pdest & 7) == 0)
 	{
-		for (int j = 0; j < cnt; j++)
-		{
-			const uint32_t px = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
-			if (j < 4) plo |= px << (8 * j); else phi |= px << (8 * (j - 4));
-			ss = rc_addw (ss, sstep);
-			tt = rc_addw (tt, tstep);
-		}
+		uint2 q;
+		q.x = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+		q.y = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+		*reinterpret_cast<uint2 *>(pdest) = q;
 	}
 	else
 	{
-		const int *turbtab = w->sintable + vw->turbphase;
-		ss &= ((RC_CYCLE << 16) - 1);
-		tt &= ((RC_CYCLE << 16) - 1);
-		for (int j = 0; j < cnt; j++)
-		{
-			const int sturb = ((ss + RC_LDG (&turbtab[(tt >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
-			const int tturb = ((tt + RC_LDG (&turbtab[(ss >> 16) & (RC_CYCLE - 1)])) >> 16) & 63;
-			const uint32_t px = RC_LDG (&pbase[(tturb << 6) + sturb]);
-			if (j < 4) plo |= px << (8 * j); else phi |= px << (8 * (j - 4));
-			ss = rc_addw (ss, sstep);
-			tt = rc_addw (tt, tstep);
-		}
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			if (j < cnt)
+				pdest[j] = (uint8_t)px[j];
 	}
-	rc_store_bytes8 (pdest, plo, phi, cnt);
+}
+
+/* the two kinds of draw work item: screen cell `c` of row `row` = view * height + line, and the head of span `si` */
+RC_HD void rc_draw_cell (const rc_world_t *w, const rc_frame_t *f, int row, int c)
+{
+	const int cw = (f->width + 7) >> 3;
+	const int si = RC_LDG (&f->cellspan[(size_t)row * cw + c]);
+	if (si < 0)
+		return;
+	const rc_span_t sp = rc_load_span (&f->spans[si]);
+	const int rel = (c << 3) - sp.u;
+	int cnt = sp.count - rel;
+	if (cnt > 8) cnt = 8;
+	rc_draw_pixels (w, f, si, sp, rel, cnt);
+}
+
+RC_HD void rc_draw_head (const rc_world_t *w, const rc_frame_t *f, int si)
+{
+	const rc_span_t sp = rc_load_span (&f->spans[si]);
+	int cnt = 8 - (sp.u & 7);
+	if (cnt == 8 || sp.count <= 0)
+		return;
+	if (cnt > sp.count) cnt = sp.count;
+	rc_draw_pixels (w, f, si, sp, 0, cnt);
 }
 
 

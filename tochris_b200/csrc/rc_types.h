@@ -220,18 +220,22 @@ typedef struct {            /* surf_t replacement (r_shared.h:125-147) + drawing
     int   cachewidth;       /* row pitch of the block; constant colour for RC_SRC_SOLID */
     int   pad;              /* texel source, RC_SRC_* */
     int   drawflags;        /* copy of flags */
-    float d_sdivzstepu, d_tdivzstepu, d_zistepu_draw, pad1;
+    float d_sdivzstepu, d_tdivzstepu, d_zistepu_draw;
+    int   izistep;          /* (int)(d_zistepu * 0x8000 * 0x10000), d_scan.c:399 */
     int   sadjust, tadjust, bbextents, bbextentt;
     int   pad2[4];
 } rc_surf_t;                /* 128 B */
 
-typedef struct {            /* espan_t replacement (r_shared.h:117-121), 16 B */
+typedef struct {            /* espan_t replacement (r_shared.h:117-121) + per-span draw state; 32 B, two vector loads */
     int      view;
-    uint16_t surf;
+    int      gsurf;         /* view * surfcap + surf_t slot */
+    int16_t  u, count;
     int16_t  v;
-    int16_t  u;
-    int16_t  count;
-    int      firstblock;    /* index of this span's first 8-pixel block in the block list */
+    uint16_t flags;         /* bit 0: the view renders into its 320x200 warp buffer (r_dowarp) */
+    int      pixofs;        /* (view * height + v) * width + u: index of the first pixel in the batch's colour / z planes */
+    int      chkbase;       /* first (s/z, t/z, 1/z) checkpoint record of the span */
+    int      izi0;          /* 1/z at the span start in D_DrawZSpans fixed point (d_scan.c:411-413), by the span-prep kernel */
+    int      pad;
 } rc_span_t;
 
 /* surface-cache build job (d_surf.c:196 D_CacheSurface miss) */
