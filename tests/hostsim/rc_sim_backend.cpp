@@ -130,12 +130,12 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	f.surfs = g->surfs.data ();
 	f.spancap = n * g->height * 96;
 	const int cw = (g->width + 7) / 8;
-	f.chkcap = f.spancap + n * g->height * (cw / 4 + 1);
+	f.segcap = f.spancap + n * g->height * (cw / 8 + 1);
 	g->spans.assign (f.spancap, rc_span_t ());
 	std::vector<int> cellspan ((size_t)n * g->height * cw, -1);
 	f.spans = g->spans.data (); f.cellspan = cellspan.data ();
-	std::vector<float> chk ((size_t)f.chkcap * 4, 0.f);
-	f.chk = chk.data ();
+	std::vector<int> segspan ((size_t)f.segcap, -1), bnd ((size_t)f.segcap * RC_SEG_BND * 2, 0);
+	f.segspan = segspan.data (); f.bnd = bnd.data ();
 	g->alloc[0] = 0; g->alloc[2] = 0;
 	f.alloc = g->alloc;
 	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;
@@ -185,7 +185,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	}
 	int nspans = (int)(g->alloc[0] & 0xFFFFFFFFu);
 	if (nspans > f.spancap) nspans = f.spancap;
-	for (int t = 0; t < nspans; t++) rc_span_prep (w, &f, t);
+	int nsegs = (int)(g->alloc[0] >> 32);
+	if (nsegs > f.segcap) nsegs = f.segcap;
+	for (int t = 0; t < nsegs; t++) rc_span_seg (w, &f, t);
 	for (int row = 0; row < n * g->height; row++)
 		for (int c = 0; c < cw; c++) rc_draw_cell (w, &f, row, c);
 	for (int t = 0; t < nspans; t++) rc_draw_head (w, &f, t);

@@ -57,7 +57,7 @@ class rc_surf_t(C.Structure):       # rc_types.h rc_surf_t, 128 B
 
 class rc_span_t(C.Structure):       # rc_types.h rc_span_t, 32 B
     _fields_ = [("view", C.c_int), ("gsurf", C.c_int), ("u", C.c_short), ("count", C.c_short), ("v", C.c_short),
-                ("flags", C.c_ushort), ("pixofs", C.c_int), ("chkbase", C.c_int), ("izi0", C.c_int), ("pad", C.c_int)]
+                ("flags", C.c_ushort), ("pixofs", C.c_int), ("segbase", C.c_int), ("izi0", C.c_int), ("izistep", C.c_int)]
 
 
 assert C.sizeof(rc_surf_t) == 128 and C.sizeof(rc_span_t) == 32 and C.sizeof(rc_edge_t) == 32

@@ -51,7 +51,7 @@ struct rc_gpu_s {
 	int chunkcap;			/* views the buffers below are sized for */
 	int maxchunk;			/* largest chunk the memory budget allows */
 	int maxviews;			/* user cap on views in flight (0: auto) */
-	int facecap, edgecap, surfcap, spancap, chkcap, jobcap;
+	int facecap, edgecap, surfcap, spancap, segcap, jobcap;
 	int spans_per_line;		/* sizing heuristic, doubled on RC_STAT_SPAN_POOL */
 	rc_view_t *d_views;
 	rc_facerec_t *d_facelist; int *d_nfaces; uint16_t *d_facepos;
@@ -59,7 +59,7 @@ struct rc_gpu_s {
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
 	rc_span_t *d_spans; int *d_cellspan;
-	float *d_chk;
+	int *d_segspan, *d_bnd;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -100,9 +100,35 @@ struct rc_gpu_s {
  *   phase 4  fix-up of faces that read r_rightenter/r_rightexit left by an earlier face:
  *            the search for the latest earlier writer is done by the whole warp */
 #define FRONT_THREADS 256
+
+/* L2 prefetch of this CTA's 1/gridDim slice of a read-only array: the front end chases pointers
+ * through the BSP (node -> plane -> child ...), and after a cold start (the bench flushes L2 between
+ * steps) every level would otherwise be a dependent HBM miss */
+__device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
+{
+	const size_t lines = (bytes + 127) >> 7;
+	const size_t per = (lines + gridDim.x - 1) / gridDim.x;
+	const size_t lo = per * blockIdx.x;
+	size_t hi = lo + per;
+	if (hi > lines) hi = lines;
+	const char *base = reinterpret_cast<const char *>(p);
+	for (size_t i = lo + threadIdx.x; i < hi; i += FRONT_THREADS)
+		asm volatile ("prefetch.global.L2 [%0];" :: "l"(base + (i << 7)));
+}
 __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	const int vi = blockIdx.x, tid = threadIdx.x;
+	front_prefetch (w.nodes, sizeof(rc_node_t) * (size_t)w.numnodes);
+	front_prefetch (w.planes, sizeof(rc_plane_t) * (size_t)w.numplanes);
+	front_prefetch (w.nodeaux, sizeof(rc_nodeaux_t) * (size_t)w.numnodes);
+	front_prefetch (w.leafs, sizeof(rc_leaf_t) * (size_t)w.numleafs);
+	front_prefetch (w.leafdfs, sizeof(int) * (size_t)w.numleafs);
+	front_prefetch (w.marksurfaces, sizeof(int) * (size_t)w.nummarksurfaces);
+	front_prefetch (w.faces, sizeof(rc_face_t) * (size_t)w.numfaces);
+	front_prefetch (w.surfedges, sizeof(int) * (size_t)w.numsurfedges);
+	front_prefetch (w.separtner, sizeof(rc_separtner_t) * (size_t)w.numsurfedges);
+	front_prefetch (w.edges, sizeof(uint16_t) * 2 * (size_t)w.numedges);
+	front_prefetch (w.vertexes, sizeof(float) * 3 * (size_t)w.numvertexes);
 	{
 		uint16_t *facepos = f.facepos + (size_t)vi * w.numfaces;
 		int *facemark = f.facemark + (size_t)vi * w.numfaces;
@@ -198,7 +224,7 @@ struct rc_aet_sorted {
 
 struct scan_warp_t {			/* per-warp shared memory */
 	union {
-		struct { uint32_t ku[RC_AET_MAX]; uint16_t kidx[RC_AET_MAX]; } k;	/* B1/B2: unsorted keys */
+		struct { unsigned long long ku[RC_AET_MAX]; uint16_t kidx[RC_AET_MAX]; } k;	/* B1/B2: unsorted keys: u (biased) << 32 | step code */
 		struct { int16_t x0[SCAN_SPANS], x1[SCAN_SPANS]; uint16_t sf[SCAN_SPANS]; } sp;	/* B3/C: change points, spans */
 	} a;
 	int      su[RC_AET_MAX];		/* sorted: u (12.20) */
@@ -289,15 +315,24 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	{
 		const int c = base + lane;
 		bool act = false;
-		uint32_t key = 0;
+		unsigned long long key = 0ull;
 		if (c < ncand)
 		{
 			const uint32_t vv = sh->c_vv[c];
 			const int v = (int16_t)(vv & 0xFFFF), v2 = (int16_t)(vv >> 16);
 			if (v <= line && v2 >= line)
 			{
+				/* the high word of rc_aet_make's key: u on this line, then (edges that were already
+				 * active on the previous line) the larger step first; new edges before old ones */
+				const uint32_t step = (uint32_t)sh->c_step[c];
+				uint32_t code = 0;
+				if (line > v)
+				{
+					code = ~(step ^ 0x80000000u);
+					if (code == 0) code = 1;
+				}
 				act = true;
-				key = ((uint32_t)sh->c_u[c] + (uint32_t)(line - v) * (uint32_t)sh->c_step[c]) ^ 0x80000000u;
+				key = ((unsigned long long)(((uint32_t)sh->c_u[c] + (uint32_t)(line - v) * step) ^ 0x80000000u) << 32) | code;
 			}
 		}
 		const unsigned m = __ballot_sync (0xFFFFFFFFu, act);
@@ -318,21 +353,22 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	/* ---- B2: rank sort (keys are unique) ---- */
 	for (int i = lane; i < n; i += 32)
 	{
-		const uint32_t ui = sw->a.k.ku[i];
+		const unsigned long long ui = sw->a.k.ku[i];
 		int rank = 0;
 		for (int j = 0; j < n; j++)
 		{
-			const uint32_t uj = sw->a.k.ku[j];
+			const unsigned long long uj = sw->a.k.ku[j];
 			rank += (uj < ui) ? 1 : 0;
 			if (uj == ui && j != i)
 			{
+				/* same u and step: start line and emission order decide (rare) */
 				unsigned long long hi_i, lo_i, hi_j, lo_j;
 				scan_full_key (sh, sw->a.k.kidx[i], line, &hi_i, &lo_i);
 				scan_full_key (sh, sw->a.k.kidx[j], line, &hi_j, &lo_j);
-				rank += (hi_j < hi_i || (hi_j == hi_i && lo_j < lo_i)) ? 1 : 0;
+				rank += (lo_j < lo_i) ? 1 : 0;
 			}
 		}
-		sw->su[rank] = (int)(ui ^ 0x80000000u);
+		sw->su[rank] = (int)((uint32_t)(ui >> 32) ^ 0x80000000u);
 		sw->ss[rank] = sh->c_sf[sw->a.k.kidx[i]];
 	}
 	__syncwarp ();
@@ -483,20 +519,20 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	__syncwarp ();
 
 	/* ---- C: publish ---- */
-	int nchk = 0;
+	int nseg = 0;
 	if (nsp <= SCAN_SPANS)
 		for (int j = lane; j < nsp; j += 32)
-			nchk += rc_span_chk_count (sw->a.sp.x1[j] - sw->a.sp.x0[j]);
+			nseg += rc_span_seg_count (sw->a.sp.x1[j] - sw->a.sp.x0[j]);
 	#pragma unroll
 	for (int o = 16; o; o >>= 1)
-		nchk += __shfl_xor_sync (0xFFFFFFFFu, nchk, o);
+		nseg += __shfl_xor_sync (0xFFFFFFFFu, nseg, o);
 	unsigned long long old = 0ull;
 	if (lane == 0)
-		old = atomicAdd (&f.alloc[0], (unsigned long long)nsp | ((unsigned long long)nchk << 32));
+		old = atomicAdd (&f.alloc[0], (unsigned long long)nsp | ((unsigned long long)nseg << 32));
 	old = __shfl_sync (0xFFFFFFFFu, old, 0);
 	const int spanbase = (int)(old & 0xFFFFFFFFu);
-	int chkbase = (int)(old >> 32);
-	if (nsp > SCAN_SPANS || spanbase + nsp > f.spancap || chkbase + nchk > f.chkcap)
+	int segbase = (int)(old >> 32);
+	if (nsp > SCAN_SPANS || spanbase + nsp > f.spancap || segbase + nseg > f.segcap)
 	{
 		if (lane == 0) atomicOr (f.status, RC_STAT_SPAN_POOL);
 		for (int c = lane; c < cw; c += 32)
@@ -512,7 +548,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		if (j < nsp)
 		{
 			u0 = sw->a.sp.x0[j]; cnt = sw->a.sp.x1[j] - u0; sf = sw->a.sp.sf[j];
-			c = rc_span_chk_count (cnt);
+			c = rc_span_seg_count (cnt);
 		}
 		int incl = c;
 		#pragma unroll
@@ -525,10 +561,13 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		{
 			uint4 *dst = reinterpret_cast<uint4 *>(&f.spans[spanbase + j]);
 			dst[0] = make_uint4 ((uint32_t)vi, (uint32_t)(vi * f.surfcap + sf), (uint32_t)(uint16_t)u0 | ((uint32_t)cnt << 16), vflags);
-			dst[1] = make_uint4 ((uint32_t)(pixrow + u0), (uint32_t)(chkbase + incl - c), 0u, 0u);
+			const int myseg = segbase + incl - c;
+			dst[1] = make_uint4 ((uint32_t)(pixrow + u0), (uint32_t)myseg, 0u, 0u);
 			surfs[sf].hasspans = 1;
+			for (int q = 0; q < c; q++)
+				f.segspan[myseg + q] = spanbase + j;
 		}
-		chkbase += __shfl_sync (0xFFFFFFFFu, incl, 31);
+		segbase += __shfl_sync (0xFFFFFFFFu, incl, 31);
 	}
 	/* cell map: the span that covers pixel 8c (spans are sorted and disjoint) */
 	for (int c = lane; c < cw; c += 32)
@@ -558,14 +597,6 @@ __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_c
 		rc_surf_prep (&w, &f, vi, si);
 }
 
-__global__ void k_resolve (const __grid_constant__ rc_frame_t f)
-{
-	int vi = blockIdx.x;
-	int si = rc_surf_slot (&f, vi, blockIdx.y * blockDim.x + threadIdx.x);
-	if (si >= 0)
-		rc_surf_resolve (&f, vi, si);
-}
-
 /* Surface-cache build: R_BuildLightmap + R_DrawSurfaceBlock8_mip0..3 (r_light.c:372,
  * r_surf.c:187-375).  Persistent CTAs stride over the job list the prep kernel produced.
  *   - vid.colormap (16 KB) is staged in shared memory once per CTA
@@ -577,6 +608,15 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
 {
 	__shared__ __align__(16) uint8_t s_cmap[256 * 64];
 	__shared__ unsigned bl[18 * 18];
+	/* prologue: surfaces that found their block already in the cache table pick up its pool offset
+	 * (the creator stored it in the surface-prep kernel) */
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < f.nviews * f.surfcap; t += gridDim.x * blockDim.x)
+	{
+		const int vi = t / f.surfcap;
+		const int si = rc_surf_slot (&f, vi, t - vi * f.surfcap);
+		if (si >= 0)
+			rc_surf_resolve (&f, vi, si);
+	}
 	const unsigned long long nj = f.alloc[2];
 	const int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
 	if ((int)blockIdx.x >= njobs)
@@ -649,13 +689,13 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
 	}
 }
 
-__global__ void k_spanprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+__global__ void k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	unsigned long long a = f.alloc[0];
-	int nspans = (int)(a & 0xFFFFFFFFu);
-	if (nspans > f.spancap) nspans = f.spancap;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nspans; t += gridDim.x * blockDim.x)
-		rc_span_prep (&w, &f, t);
+	int nsegs = (int)(a >> 32);
+	if (nsegs > f.segcap) nsegs = f.segcap;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsegs; t += gridDim.x * blockDim.x)
+		rc_span_seg (&w, &f, t);
 }
 
 /* Draw stage: first one thread per screen-aligned 8-pixel cell of every row (full cells: one
@@ -788,7 +828,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_cellspan); cudaFree (g->d_jobs); cudaFree (g->d_chk);
+	cudaFree (g->d_cellspan); cudaFree (g->d_jobs); cudaFree (g->d_segspan); cudaFree (g->d_bnd);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -910,9 +950,9 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 {
 	size_t lines = g->height;
 	size_t cw = (g->width + 7) / 8;
-	size_t spans = lines * g->spans_per_line, chks = spans + lines * (cw / 4 + 1);
+	size_t spans = lines * g->spans_per_line, segs = spans + lines * (cw / 8 + 1);
 	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
-	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + 16 * chks + 4 * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
+	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + (4 + 8 * RC_SEG_BND) * segs + 4 * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
 static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
@@ -943,8 +983,8 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	size_t lines = (size_t)g->height * want;
 	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
 	const size_t cw = (g->width + 7) / 8;
-	size_t chks = (size_t)g->spancap + lines * (cw / 4 + 1);
-	g->chkcap = (int)(chks < 0x7FFFFFFF ? chks : 0x7FFFFFFF);
+	size_t segs = (size_t)g->spancap + lines * (cw / 8 + 1);
+	g->segcap = (int)(segs < 0x7FFFFFFF / (RC_SEG_BND * 2) ? segs : 0x7FFFFFFF / (RC_SEG_BND * 2));
 	g->jobcap = want * 8 + 4096;
 	if (g->jobcap > want * surfcap) g->jobcap = want * surfcap;
 	CK (cudaMalloc (&g->d_views, sizeof(rc_view_t) * want));
@@ -962,7 +1002,8 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
 	CK (cudaMalloc (&g->d_spans, sizeof(rc_span_t) * (size_t)g->spancap));
 	CK (cudaMalloc (&g->d_cellspan, sizeof(int) * lines * cw));
-	CK (cudaMalloc (&g->d_chk, sizeof(float) * 4 * (size_t)g->chkcap));
+	CK (cudaMalloc (&g->d_segspan, sizeof(int) * (size_t)g->segcap));
+	CK (cudaMalloc (&g->d_bnd, sizeof(int) * 2 * RC_SEG_BND * (size_t)g->segcap));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
 	g->chunkcap = want;
 	return RC_OK;
@@ -986,7 +1027,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
 	f.spans = g->d_spans; f.spancap = g->spancap; f.cellspan = g->d_cellspan;
-	f.chk = g->d_chk; f.chkcap = g->chkcap;
+	f.segspan = g->d_segspan; f.bnd = g->d_bnd; f.segcap = g->segcap;
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
@@ -1023,11 +1064,10 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
-	k_resolve<<<gp, 64, 0, s>>> (f);
 	if (timed) cudaEventRecord (g->ev[4], s);
 	k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[5], s);
-	k_spanprep<<<g->numsms * 8, 128, 0, s>>> (w, f);
+	k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
 	if (g->cur_batch && g->cur_batch->nzres)
 	{
@@ -1073,7 +1113,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		g->stats.kernel_launches++;
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 7;
+	g->stats.kernel_launches += 6;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }

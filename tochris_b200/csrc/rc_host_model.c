@@ -387,7 +387,10 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 			nodes[i].numsurfaces = nin[i].numfaces;
 			if (nodes[i].firstsurface + nodes[i].numsurfaces > w->numfaces) FAIL ("node %d bad faces", i);
 			for (j = 0; j < nodes[i].numsurfaces; j++)
+			{
 				((rc_face_t *)w->faces)[nodes[i].firstsurface + j].node = i;
+				((rc_face_t *)w->faces)[nodes[i].firstsurface + j].nodeslot = j;
+			}
 			nodes[i].parent = -1;
 			for (j = 0; j < 2; j++)
 			{

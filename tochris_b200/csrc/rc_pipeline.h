@@ -62,6 +62,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
 #define RC_WARP_W          320       /* WARP_WIDTH / WARP_HEIGHT, d_iface.h:22-23 */
 #define RC_WARP_H          200
+#define RC_SEG_BND         10        /* boundaries 8s .. 8s+9 of a span are stored with segment s */
 
 /* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
 typedef struct {
@@ -82,8 +83,9 @@ typedef struct {
     /* scan */
     rc_span_t *spans; int spancap;
     int *cellspan;                /* [nviews][height][(width+7)/8]: span covering the first pixel of each 8-pixel screen cell, -1: none */
-    float *chk; int chkcap;       /* [chkcap][4]: s/z, t/z, 1/z checkpoints every 4th subdivision of a span */
-    unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 checkpoints used  [1]: cache pool cursor  [2]: jobs */
+    int *segspan; int segcap;     /* [segcap]: owning span of every 64-pixel span segment (8 subdivisions) */
+    int *bnd;                     /* [segcap][RC_SEG_BND][2]: 16.16 (s, t) at the subdivision boundaries of a segment */
+    unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 segments used  [1]: cache pool cursor  [2]: jobs */
     /* surface cache */
     unsigned long long *cachekeys; int *cachevals; int cachemask;
     uint8_t *cachepool; long long cachecap;
@@ -276,7 +278,7 @@ RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int f
 	const int want = nv.state == 2 ? RC_SURF_PLANEBACK : 0;
 	if ((fa->flags & RC_SURF_PLANEBACK) != want)
 		return;
-	const int key = nv.facekey + (fi - w->nodes[fa->node].firstsurface);
+	const int key = nv.facekey + fa->nodeslot;
 	if (!(RC_LDCG (&f->facemark[(size_t)vi * w->numfaces + fi]) < key))
 		return;
 	int p = RC_ATOMIC_ADD_I (&f->nfaces[vi], 1);
@@ -1192,15 +1194,15 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
  * word and one aligned 16-byte z word) plus one thread per span whose first column is not a multiple
  * of 8 (its "head", the pixels up to the next cell boundary).  cellspan[(view, line, cell)] = the span
  * that covers the cell's first pixel, -1 outside the view rectangle. */
-RC_HD int rc_span_chk_count (int count) { return (((count + 7) >> 3) + 3) >> 2; }	/* checkpoint every 4th subdivision */
+RC_HD int rc_span_seg_count (int count) { return (((count + 7) >> 3) + 7) >> 3; }	/* segments of 8 subdivisions = 64 pixels */
 
-RC_HD void rc_write_span (const rc_frame_t *f, const rc_view_t *vw, int vi, int line, int si, int surf, int u0, int count, int chkbase)
+RC_HD void rc_write_span (const rc_frame_t *f, const rc_view_t *vw, int vi, int line, int si, int surf, int u0, int count, int segbase)
 {
 	rc_span_t *s = &f->spans[si];
 	s->view = vi; s->gsurf = vi * f->surfcap + surf;
 	s->u = (int16_t)u0; s->count = (int16_t)count; s->v = (int16_t)line; s->flags = (uint16_t)(vw->warp_index >= 0 ? 1 : 0);
 	s->pixofs = (vi * f->height + line) * f->width + u0;
-	s->chkbase = chkbase; s->izi0 = 0; s->pad = 0;
+	s->segbase = segbase; s->izi0 = 0; s->izistep = 0;
 }
 
 RC_HD void rc_line_clear (const rc_frame_t *f, int vi, int line)
@@ -1214,12 +1216,12 @@ RC_HD void rc_line_clear (const rc_frame_t *f, int vi, int line)
 /* serial version (host simulation; the GPU scan kernel does the same with a warp) */
 RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t *surfs, int vi, int line, const rc_linespans_t *ls, int nsp)
 {
-	int nchk = 0;
+	int nseg = 0;
 	for (int i = 0; i < nsp; i++)
-		nchk += rc_span_chk_count (ls->u1[i] - ls->u0[i]);
-	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)nsp | ((unsigned long long)nchk << 32));
-	int spanbase = (int)(old & 0xFFFFFFFFu), chkbase = (int)(old >> 32);
-	if (nsp > ls->cap || spanbase + nsp > f->spancap || chkbase + nchk > f->chkcap)
+		nseg += rc_span_seg_count (ls->u1[i] - ls->u0[i]);
+	unsigned long long old = RC_ATOMIC_ADD_ULL (&f->alloc[0], (unsigned long long)nsp | ((unsigned long long)nseg << 32));
+	int spanbase = (int)(old & 0xFFFFFFFFu), segbase = (int)(old >> 32);
+	if (nsp > ls->cap || spanbase + nsp > f->spancap || segbase + nseg > f->segcap)
 	{
 		RC_ATOMIC_OR_I (f->status, RC_STAT_SPAN_POOL);
 		rc_line_clear (f, vi, line);
@@ -1232,8 +1234,9 @@ RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t 
 	for (int i = 0; i < nsp; i++)
 	{
 		const int u0 = ls->u0[i], cnt = ls->u1[i] - u0;
-		rc_write_span (f, vw, vi, line, spanbase + i, ls->surf[i], u0, cnt, chkbase);
-		chkbase += rc_span_chk_count (cnt);
+		rc_write_span (f, vw, vi, line, spanbase + i, ls->surf[i], u0, cnt, segbase);
+		for (int q = rc_span_seg_count (cnt); q > 0; q--)
+			f->segspan[segbase++] = spanbase + i;
 		surfs[ls->surf[i]].hasspans = 1;
 		for (int c = (u0 + 7) >> 3; c <= (u0 + cnt - 1) >> 3; c++)
 			cells[c] = spanbase + i;
@@ -1657,58 +1660,95 @@ RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int
 }
 
 /* ------------------------------------------------------------------ stage 6: draw ------ */
-/* One thread per span, before drawing: the per-span part of D_DrawSpans8 / D_DrawZSpans.
- *   span.izi0 = 1/z at the span start in D_DrawZSpans fixed point          (d_scan.c:399-413)
- *   chk[chkbase + j] = (s/z, t/z, 1/z) after 4j subdivision steps           (d_scan.c:278-315)
- * The float accumulators of D_DrawSpans8 are sequentially rounded sums, so subdivision k needs
- * k adds; checkpoints every 4 subdivisions bound the replay in the draw kernel to 3 steps. */
-RC_HD void rc_span_prep (const rc_world_t *w, const rc_frame_t *f, int si)
+/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
+ * accumulators -> 16.16, clamped to [lo, bbextent] */
+RC_HD void rc_boundary_st (const rc_surf_t *s, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
 {
+	const float z = (float)0x10000 / zi;
+	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
+	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
+	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
+	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
+	*ps = ss; *pt = tt;
+}
+
+/* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
+ * D_DrawSpans8 (d_scan.c:278-360) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
+ * subdivision boundary instead of once per pixel block.
+ *   bnd[seg][i] = 16.16 (s, t) at subdivision boundary b = 8*segment + i, i = 0..9
+ *        b = 0              span start, clamped to [0, bbextent]
+ *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
+ *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
+ *   span.izi0 / span.izistep (segment 0 only)
+ * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
+ * adds: the segment replays the cheap adds from the span start and does the divide / convert /
+ * clamp only for its own boundaries. */
+RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
+{
+	const int si = f->segspan[seg];
 	rc_span_t *sp = &f->spans[si];
 	const int count = sp->count;
-	if (count <= 0)
-		return;
 	const rc_surf_t *s = f->surfs + sp->gsurf;
+	const int sidx = seg - sp->segbase;
 	const float du = (float)sp->u, dv = (float)sp->v;
 	const float zistepu = s->d_zistepu, zistepv = s->d_zistepv, ziorigin = s->d_ziorigin;
-	const double zid = ziorigin + dv*zistepv + du*zistepu;
-	sp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
+	if (sidx == 0)
+	{
+		const double zid = ziorigin + dv*zistepv + du*zistepu;
+		sp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
+		sp->izistep = s->izistep;
+	}
 	if (s->pad != RC_SRC_POOL && s->pad != RC_SRC_TEXELS)
 		return;
-	const float sdivz8stepu = s->d_sdivzstepu * 8, tdivz8stepu = s->d_tdivzstepu * 8, zi8stepu = zistepu * 8;
-	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*s->d_sdivzstepu;
-	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*s->d_tdivzstepu;
+	const float sstepu = s->d_sdivzstepu, tstepu = s->d_tdivzstepu;
+	const float sdivz8stepu = sstepu * 8, tdivz8stepu = tstepu * 8, zi8stepu = zistepu * 8;
+	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*sstepu;
+	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*tstepu;
 	float zi = ziorigin + dv*zistepv + du*zistepu;
-	const int nsub = (count + 7) >> 3;
-	float *chk = f->chk + 4 * (size_t)sp->chkbase;
-	for (int j = 0; j < nsub; j += 4)
+	float psdivz = sdivz, ptdivz = tdivz, pzi = zi;		/* the accumulators one step back */
+	for (int q = sidx << 3; q > 0; q--)
 	{
-		chk[j + 0] = sdivz; chk[j + 1] = tdivz; chk[j + 2] = zi; chk[j + 3] = 0;
-		for (int q = 0; q < 4; q++)
+		psdivz = sdivz; ptdivz = tdivz; pzi = zi;
+		sdivz += sdivz8stepu;
+		tdivz += tdivz8stepu;
+		zi += zi8stepu;
+	}
+	const int nsub = (count + 7) >> 3;
+	int *out = f->bnd + (size_t)seg * (RC_SEG_BND * 2);
+	for (int i = 0; i < RC_SEG_BND; i++)
+	{
+		const int b = (sidx << 3) + i;
+		int ss, tt;
+		if (b < nsub)
 		{
+			rc_boundary_st (s, sdivz, tdivz, zi, b ? 8 : 0, &ss, &tt);
+			psdivz = sdivz; ptdivz = tdivz; pzi = zi;
 			sdivz += sdivz8stepu;
 			tdivz += tdivz8stepu;
 			zi += zi8stepu;
 		}
+		else if (b == nsub)
+		{
+			const float m1 = (float)(count - ((nsub - 1) << 3) - 1);	/* spancountminus1 of the last subdivision */
+			rc_boundary_st (s, psdivz + sstepu * m1, ptdivz + tstepu * m1, pzi + zistepu * m1, 8, &ss, &tt);
+		}
+		else
+			break;
+		out[2 * i] = ss; out[2 * i + 1] = tt;
 	}
 }
 
-/* the 48 bytes of rc_surf_t the draw kernel needs, fetched with three 16-byte loads */
+/* the 16 bytes of rc_surf_t the draw kernel needs */
 typedef struct {
 	int   cacheofs, cachewidth, srckind, flags;
-	float sdivzstepu, tdivzstepu, zistepu; int izistep;
-	int   sadjust, tadjust, bbextents, bbextentt;
 } rc_drawsurf_t;
 
 #ifdef __CUDACC__
 RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
 {
-	const uint4 *q = reinterpret_cast<const uint4 *>(&s->cacheofs);
-	const uint4 a = __ldg (q), b = __ldg (q + 1), c = __ldg (q + 2);
+	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(&s->cacheofs));
 	rc_drawsurf_t d;
 	d.cacheofs = (int)a.x; d.cachewidth = (int)a.y; d.srckind = (int)a.z; d.flags = (int)a.w;
-	d.sdivzstepu = __uint_as_float (b.x); d.tdivzstepu = __uint_as_float (b.y); d.zistepu = __uint_as_float (b.z); d.izistep = (int)b.w;
-	d.sadjust = (int)c.x; d.tadjust = (int)c.y; d.bbextents = (int)c.z; d.bbextentt = (int)c.w;
 	return d;
 }
 RC_HD rc_span_t rc_load_span (const rc_span_t *p)
@@ -1717,7 +1757,7 @@ RC_HD rc_span_t rc_load_span (const rc_span_t *p)
 	rc_span_t s;
 	s.view = (int)a.x; s.gsurf = (int)a.y; s.u = (int16_t)(a.z & 0xFFFF); s.count = (int16_t)(a.z >> 16);
 	s.v = (int16_t)(a.w & 0xFFFF); s.flags = (uint16_t)(a.w >> 16);
-	s.pixofs = (int)b.x; s.chkbase = (int)b.y; s.izi0 = (int)b.z; s.pad = 0;
+	s.pixofs = (int)b.x; s.segbase = (int)b.y; s.izi0 = (int)b.z; s.izistep = (int)b.w;
 	return s;
 }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return __byte_perm (a, b, 0x5410); }
@@ -1726,41 +1766,24 @@ RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
 {
 	rc_drawsurf_t d;
 	d.cacheofs = s->cacheofs; d.cachewidth = s->cachewidth; d.srckind = s->pad; d.flags = s->drawflags;
-	d.sdivzstepu = s->d_sdivzstepu; d.tdivzstepu = s->d_tdivzstepu; d.zistepu = s->d_zistepu_draw; d.izistep = s->izistep;
-	d.sadjust = s->sadjust; d.tadjust = s->tadjust; d.bbextents = s->bbextents; d.bbextentt = s->bbextentt;
 	return d;
 }
 RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 16); }
 #endif
 
-/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
- * accumulators -> 16.16, clamped to [lo, bbextent] */
-RC_HD void rc_boundary_st (const rc_drawsurf_t *ds, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
-{
-	const float z = (float)0x10000 / zi;
-	int ss = rc_addw (rc_f2i (sdivz * z), ds->sadjust);
-	int tt = rc_addw (rc_f2i (tdivz * z), ds->tadjust);
-	if (ss > ds->bbextents) ss = ds->bbextents; else if (ss < lo) ss = lo;
-	if (tt > ds->bbextentt) tt = ds->bbextentt; else if (tt < lo) tt = lo;
-	*ps = ss; *pt = tt;
-}
-
-/* truncating division by 1..7 (the last-subdivision step, d_scan.c:364-365) without the generic
- * 32-bit divide: float estimate, exact integer correction */
+/* truncating division by d = 1..7 (the last-subdivision step, d_scan.c:364-365) as a multiply by
+ * ceil(2^32 / d): exact for |a| < 2^24 (7 * 2^24 < 2^32), which covers every cached surface
+ * (extents <= 256 texels in 16.16); larger differences (turbulent surfaces) take the divide. */
 RC_HD int rc_div_small (int a, int d)
 {
 #ifdef __CUDACC__
 	if (a >= (1 << 24) || a <= -(1 << 24))
-		return a / d;				/* not exact in float: turbulent surfaces with huge extents */
-	int q = (int)((float)a * (1.0f / (float)d));	/* a is exact in float: off by at most one */
-	int r = a - q * d;
-	/* bring r into the range truncation leaves: same sign as a, |r| < d */
-	while (r >= d) { r -= d; q++; }
-	while (r <= -d) { r += d; q--; }
-	if (a >= 0 && r < 0) { q--; r += d; }
-	else if (a < 0 && r > 0) { q++; r -= d; }
-	return q;
+		return a / d;
+	const unsigned long long m = d == 1 ? 0x100000000ull : (unsigned long long)(0xFFFFFFFFu / (unsigned)d + 1u);
+	const unsigned mag = (unsigned)(a < 0 ? -a : a);
+	const int q = (int)((mag * m) >> 32);
+	return a < 0 ? -q : q;
 #else
 	return a / d;
 #endif
@@ -1791,7 +1814,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 	if (f->zb)
 	{
 		int16_t *pz = f->zb + pix;
-		const int izistep = ds.izistep;
+		const int izistep = sp.izistep;
 		int zz[8];
 		zz[0] = rc_addw (sp.izi0, rc_mulw (rel, izistep));
 		#pragma unroll
@@ -1894,59 +1917,32 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 		const uint8_t *pbase = (srckind == RC_SRC_TEXELS ? w->texels : f->cachepool) + ds.cacheofs;
 		const int cachewidth = ds.cachewidth;
 		const int k = rel >> 3, a = rel & 7;
-		const float sdivz8stepu = ds.sdivzstepu * 8, tdivz8stepu = ds.tdivzstepu * 8, zi8stepu = ds.zistepu * 8;
-		const float *chk = f->chk + 4 * (size_t)(sp.chkbase + (k >> 2));
-		float sdivz = RC_LDG (&chk[0]), tdivz = RC_LDG (&chk[1]), zi = RC_LDG (&chk[2]);
-		for (int j = 0; j < (k & 3); j++)
-		{
-			sdivz += sdivz8stepu;
-			tdivz += tdivz8stepu;
-			zi += zi8stepu;
-		}
-		/* boundary k: subdivision 0 starts from the span-start clamp, later ones from a `snext` clamp */
-		int s0, t0, s1, t1, s2 = 0, t2 = 0, sstep0 = 0, tstep0 = 0, sstep1 = 0, tstep1 = 0;
-		rc_boundary_st (&ds, sdivz, tdivz, zi, k ? 8 : 0, &s0, &t0);
-		int left = sp.count - (k << 3);		/* pixels from the start of subdivision k to the end of the span */
+		/* boundaries k, k+1, k+2 of the span, precomputed by rc_span_seg */
+		const int *bp = f->bnd + ((size_t)(sp.segbase + (k >> 3)) * RC_SEG_BND + (k & 7)) * 2;
+		const int left = sp.count - (k << 3);	/* pixels from the start of subdivision k to the end of the span */
+		const int two = a + cnt > 8;		/* the item runs on into subdivision k+1 */
+		int s0, t0, s1, t1, s2 = 0, t2 = 0, sstep0, tstep0, sstep1 = 0, tstep1 = 0;
+		s0 = RC_LDG (&bp[0]); t0 = RC_LDG (&bp[1]); s1 = RC_LDG (&bp[2]); t1 = RC_LDG (&bp[3]);
+		if (two) { s2 = RC_LDG (&bp[4]); t2 = RC_LDG (&bp[5]); }
 		if (left > 8)
 		{
-			sdivz += sdivz8stepu; tdivz += tdivz8stepu; zi += zi8stepu;
-			rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s1, &t1);
 			sstep0 = (s1 - s0) >> 3;
 			tstep0 = (t1 - t0) >> 3;
-			if (a + cnt > 8)
+			if (left > 16)
 			{
-				/* the item runs on into subdivision k+1 */
-				left -= 8;
-				if (left > 8)
-				{
-					sdivz += sdivz8stepu; tdivz += tdivz8stepu; zi += zi8stepu;
-					rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s2, &t2);
-					sstep1 = (s2 - s1) >> 3;
-					tstep1 = (t2 - t1) >> 3;
-				}
-				else
-				{
-					const float m1 = (float)(left - 1);
-					sdivz += ds.sdivzstepu * m1; tdivz += ds.tdivzstepu * m1; zi += ds.zistepu * m1;
-					rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s2, &t2);
-					if (left > 1)
-					{
-						sstep1 = rc_div_small (s2 - s1, left - 1);
-						tstep1 = rc_div_small (t2 - t1, left - 1);
-					}
-				}
+				sstep1 = (s2 - s1) >> 3;
+				tstep1 = (t2 - t1) >> 3;
+			}
+			else if (two && left > 9)
+			{
+				sstep1 = rc_div_small (s2 - s1, left - 9);
+				tstep1 = rc_div_small (t2 - t1, left - 9);
 			}
 		}
 		else
 		{
-			const float m1 = (float)(left - 1);
-			sdivz += ds.sdivzstepu * m1; tdivz += ds.tdivzstepu * m1; zi += ds.zistepu * m1;
-			rc_boundary_st (&ds, sdivz, tdivz, zi, 8, &s1, &t1);
-			if (left > 1)
-			{
-				sstep0 = rc_div_small (s1 - s0, left - 1);
-				tstep0 = rc_div_small (t1 - t0, left - 1);
-			}
+			sstep0 = left > 1 ? rc_div_small (s1 - s0, left - 1) : 0;
+			tstep0 = left > 1 ? rc_div_small (t1 - t0, left - 1) : 0;
 		}
 		int ss = rc_addw (s0, rc_mulw (a, sstep0)), tt = rc_addw (t0, rc_mulw (a, tstep0));
 		const int *turbtab = w->sintable;

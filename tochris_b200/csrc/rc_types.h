@@ -71,7 +71,8 @@ typedef struct {            /* msurface_t, r_model.h:98-116 (static part) */
     uint8_t  styles[4];
     int      lightofs;      /* offset into lightdata or -1 */
     int      node;          /* owning node (load-time derived) */
-    int      pad[2];
+    int      nodeslot;      /* index among the node's faces: face - nodes[node].firstsurface */
+    int      pad;
 } rc_face_t;                /* 48 B */
 
 typedef struct {            /* mtexinfo_t, r_model.h:90-96 */
@@ -233,9 +234,9 @@ typedef struct {            /* espan_t replacement (r_shared.h:117-121) + per-sp
     int16_t  v;
     uint16_t flags;         /* bit 0: the view renders into its 320x200 warp buffer (r_dowarp) */
     int      pixofs;        /* (view * height + v) * width + u: index of the first pixel in the batch's colour / z planes */
-    int      chkbase;       /* first (s/z, t/z, 1/z) checkpoint record of the span */
-    int      izi0;          /* 1/z at the span start in D_DrawZSpans fixed point (d_scan.c:411-413), by the span-prep kernel */
-    int      pad;
+    int      segbase;       /* first 64-pixel segment record of the span (subdivision boundaries, see rc_span_seg) */
+    int      izi0;          /* 1/z at the span start in D_DrawZSpans fixed point (d_scan.c:411-413), by the segment kernel */
+    int      izistep;       /* (int)(d_zistepu * 0x8000 * 0x10000), d_scan.c:399 */
 } rc_span_t;
 
 /* surface-cache build job (d_surf.c:196 D_CacheSurface miss) */
