@@ -144,6 +144,7 @@ typedef struct {
     long long edges, surfs, spans, blocks, cache_texels, cache_jobs, faces;
     float  ms_walk, ms_faces, ms_scan, ms_surfprep, ms_cache, ms_draw, ms_total;
     float  ms_h2d, ms_d2h;
+    float  ms_spanseg;        /* part of ms_draw spent in the span-segment kernel */
 } rc_stats_t;
 void RC_GetStats (rc_stats_t *out);
 void RC_SetProfiling (int on);

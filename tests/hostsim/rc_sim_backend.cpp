@@ -155,9 +155,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	for (int vi = 0; vi < n; vi++)
 		for (int x = 0; x < w->numnodes + w->numleafs; x++) rc_visit (w, &f, vi, x);
 	for (int vi = 0; vi < n; vi++)
-		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi);
+		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi, &f.nfaces[vi]);
 	for (int vi = 0; vi < n; vi++)
-		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p);
+		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p, &f.nedges[vi]);
 	for (int vi = 0; vi < n; vi++)
 		for (int p = 0; p < nfaces[vi]; p++) rc_face_fixup (w, &f, vi, p);
 	for (int bi = 0; bi < batch->nbents; bi++)

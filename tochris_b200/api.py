@@ -36,7 +36,7 @@ class rc_stats_t(C.Structure):
                 ("cache_texels", C.c_longlong), ("cache_jobs", C.c_longlong), ("faces", C.c_longlong),
                 ("ms_walk", C.c_float), ("ms_faces", C.c_float), ("ms_scan", C.c_float), ("ms_surfprep", C.c_float),
                 ("ms_cache", C.c_float), ("ms_draw", C.c_float), ("ms_total", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float)]
 
 
 class rc_edge_t(C.Structure):

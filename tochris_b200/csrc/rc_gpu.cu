@@ -117,7 +117,16 @@ __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
 }
 __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	__shared__ int s_nfaces, s_nedges;
 	const int vi = blockIdx.x, tid = threadIdx.x;
+	if (tid == 0) { s_nfaces = 0; s_nedges = 0; }
+#ifdef RC_FRONT_TIMING
+	long long tq[6]; 
+	#define TQ(i) do { if (tid == 0) tq[i] = clock64 (); } while (0)
+#else
+	#define TQ(i) do { } while (0)
+#endif
+	TQ(0);
 	front_prefetch (w.nodes, sizeof(rc_node_t) * (size_t)w.numnodes);
 	front_prefetch (w.planes, sizeof(rc_plane_t) * (size_t)w.numplanes);
 	front_prefetch (w.nodeaux, sizeof(rc_nodeaux_t) * (size_t)w.numnodes);
@@ -125,10 +134,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 	front_prefetch (w.leafdfs, sizeof(int) * (size_t)w.numleafs);
 	front_prefetch (w.marksurfaces, sizeof(int) * (size_t)w.nummarksurfaces);
 	front_prefetch (w.faces, sizeof(rc_face_t) * (size_t)w.numfaces);
-	front_prefetch (w.surfedges, sizeof(int) * (size_t)w.numsurfedges);
-	front_prefetch (w.separtner, sizeof(rc_separtner_t) * (size_t)w.numsurfedges);
-	front_prefetch (w.edges, sizeof(uint16_t) * 2 * (size_t)w.numedges);
-	front_prefetch (w.vertexes, sizeof(float) * 3 * (size_t)w.numvertexes);
+	front_prefetch (w.fedges, sizeof(rc_fedge_t) * (size_t)w.numsurfedges);
 	{
 		uint16_t *facepos = f.facepos + (size_t)vi * w.numfaces;
 		int *facemark = f.facemark + (size_t)vi * w.numfaces;
@@ -139,17 +145,23 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 			rc_view_begin (&w, &f, vi);
 	}
 	__syncthreads ();
+	TQ(1);
 	for (int x = tid; x < w.numnodes + w.numleafs; x += FRONT_THREADS)
 		rc_visit (&w, &f, vi, x);
 	__syncthreads ();
+	TQ(2);
 	for (int fi = tid; fi < w.numworldfaces; fi += FRONT_THREADS)
-		rc_list_face (&w, &f, vi, fi);
+		rc_list_face (&w, &f, vi, fi, &s_nfaces);
 	__syncthreads ();
-	const int nfraw = __ldcg (&f.nfaces[vi]);
+	TQ(3);
+	const int nfraw = s_nfaces;
 	const int nf = nfraw < f.facecap ? nfraw : f.facecap;
+	if (tid == 0) f.nfaces[vi] = nfraw;
 	for (int p = tid; p < nf; p += FRONT_THREADS)
-		rc_render_face (&w, &f, vi, p);
+		rc_render_face (&w, &f, vi, p, &s_nedges);
 	__syncthreads ();
+	if (tid == 0) f.nedges[vi] = s_nedges;
+	TQ(4);
 	{
 		const int lane = tid & 31;
 		const rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
@@ -188,6 +200,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 			}
 		}
 	}
+#ifdef RC_FRONT_TIMING
+	__syncthreads ();
+	TQ(5);
+	if (tid == 0)
+		for (int i = 0; i < 5; i++)
+			atomicMax (&f.status[4 + i], (int)(tq[i + 1] - tq[i]));
+#endif
 }
 
 /* Scan stage (R_ScanEdges, R_InsertNewEdges, R_StepActiveU, R_GenerateSpans), one
@@ -706,10 +725,26 @@ __global__ void __launch_bounds__(128) k_draw (const __grid_constant__ rc_world_
 	const unsigned cw = (unsigned)((f.width + 7) >> 3);
 	const unsigned ncells = (unsigned)(f.nviews * f.height) * cw;
 	const unsigned stride = gridDim.x * blockDim.x;
-	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += stride)
+	/* cell -> span -> (surface, boundaries) -> texels is a chain of dependent loads: the first two
+	 * levels of the next grid-stride iterations are fetched while the current cell is drawn */
+	unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = t0 + stride;
+	int si0 = t0 < ncells ? __ldg (&f.cellspan[t0]) : -1;
+	int si1 = t1 < ncells ? __ldg (&f.cellspan[t1]) : -1;
+	rc_span_t sp0 = rc_load_span (&f.spans[si0 < 0 ? 0 : si0]);
+	while (t0 < ncells)
 	{
-		const unsigned row = t / cw;
-		rc_draw_cell (&w, &f, (int)row, (int)(t - row * cw));
+		const unsigned t2 = t1 + stride;
+		const int si2 = t2 < ncells ? __ldg (&f.cellspan[t2]) : -1;
+		const rc_span_t sp1 = rc_load_span (&f.spans[si1 < 0 ? 0 : si1]);
+		if (si0 >= 0)
+		{
+			const unsigned row = t0 / cw;
+			const int rel = (int)((t0 - row * cw) << 3) - sp0.u;
+			int cnt = sp0.count - rel;
+			if (cnt > 8) cnt = 8;
+			rc_draw_pixels (&w, &f, si0, sp0, rel, cnt);
+		}
+		t0 = t1; t1 = t2; si0 = si1; si1 = si2; sp0 = sp1;
 	}
 	unsigned long long a = f.alloc[0];
 	unsigned nspans = (unsigned)(a & 0xFFFFFFFFu);
@@ -810,7 +845,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	    cudaMalloc (&g->d_cachekeys, sizeof(unsigned long long) * g->cacheslots) != cudaSuccess ||
 	    cudaMalloc (&g->d_cachevals, sizeof(int) * g->cacheslots) != cudaSuccess ||
 	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 4) != cudaSuccess ||
-	    cudaMalloc (&g->d_status, sizeof(int) * 4) != cudaSuccess)
+	    cudaMalloc (&g->d_status, sizeof(int) * 16) != cudaSuccess)
 	{
 		snprintf (err, errlen, "cudaMalloc (surface cache) failed: %s", cudaGetErrorString (cudaGetLastError ()));
 		delete g;
@@ -913,6 +948,7 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	UP (faces, h->numfaces + 6)
 	UP (surfedges, h->numsurfedges + 24)
 	UP (separtner, h->numsurfedges + 1)
+	UP (fedges, h->numsurfedges + 1)
 	UP (edges, (size_t)(h->numedges + 13) * 2)
 	UP (vertexes, (size_t)(h->numvertexes + 8) * 3)
 	UP (texinfo, h->numtexinfo + 6)
@@ -1068,6 +1104,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[5], s);
 	k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
+	if (timed) cudaEventRecord (g->ev[7], s);
 	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
 	if (g->cur_batch && g->cur_batch->nzres)
 	{
@@ -1145,6 +1182,7 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 		cudaEventElapsedTime (&ms, g->ev[3], g->ev[4]); g->stats.ms_surfprep += ms;
 		cudaEventElapsedTime (&ms, g->ev[4], g->ev[5]); g->stats.ms_cache += ms;
 		cudaEventElapsedTime (&ms, g->ev[5], g->ev[6]); g->stats.ms_draw += ms;
+		cudaEventElapsedTime (&ms, g->ev[5], g->ev[7]); g->stats.ms_spanseg += ms;
 		cudaEventElapsedTime (&ms, g->ev[0], g->ev[6]); g->stats.ms_total += ms;
 	}
 }
@@ -1234,7 +1272,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	{
 		int r = ensure_chunk (g, n, batch->nbents ? 512 : 0, err, errlen);
 		if (r != RC_OK) return r;
-		CK (cudaMemsetAsync (g->d_status, 0, sizeof(int), s));
+		CK (cudaMemsetAsync (g->d_status, 0, sizeof(int) * 16, s));
 		st = 0;
 		for (int first = 0; first < n; first += g->chunkcap)
 		{
@@ -1251,6 +1289,13 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		}
 		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
+#ifdef RC_FRONT_TIMING
+		{
+			int tq[16];
+			cudaMemcpy (tq, g->d_status, sizeof(tq), cudaMemcpyDeviceToHost);
+			fprintf (stderr, "k_front max cycles: reset %d visit %d list %d faces %d fixup %d\n", tq[4], tq[5], tq[6], tq[7], tq[8]);
+		}
+#endif
 		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL)))
 			break;
 		if (st & RC_STAT_SPAN_POOL)

@@ -587,6 +587,26 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 				sp[se].partner_slot = other - w->faces[k].firstedge;
 			}
 		w->separtner = sp;
+		{
+			/* flattened per-surfedge records for the face kernel */
+			rc_fedge_t *fe = (rc_fedge_t *)own (hw, sizeof(rc_fedge_t) * (w->numsurfedges + 1));
+			for (i = 0; i < w->numsurfedges; i++)
+			{
+				int l = w->surfedges[i], m = abs (l);
+				const float *a = &w->vertexes[3 * w->edges[2 * m + (l > 0 ? 0 : 1)]];
+				const float *b = &w->vertexes[3 * w->edges[2 * m + (l > 0 ? 1 : 0)]];
+				memcpy (fe[i].v0, a, sizeof(float) * 3);
+				memcpy (fe[i].v1, b, sizeof(float) * 3);
+				fe[i].partner_face = sp[i].partner_face;
+				fe[i].partner_rev = 0;
+				if (sp[i].partner_face >= 0)
+				{
+					int pl = w->surfedges[w->faces[sp[i].partner_face].firstedge + sp[i].partner_slot];
+					fe[i].partner_rev = ((pl > 0) != (l > 0));
+				}
+			}
+			w->fedges = fe;
+		}
 		free (se_face);
 		free (medge_refs);
 		medge_refs = NULL;

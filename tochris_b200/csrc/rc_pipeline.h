@@ -267,7 +267,7 @@ RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
 
 /* One thread per (view, world face): the face loop of R_RecursiveWorldNode (r_bsp.c:520-549):
  * right side of its node's plane, marked by an earlier leaf -> R_RenderFace is called on it. */
-RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int fi)
+RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int fi, int *nfaces)
 {
 	const rc_face_t *fa = &w->faces[fi];
 	if (fa->node < 0)
@@ -281,7 +281,7 @@ RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int f
 	const int key = nv.facekey + fa->nodeslot;
 	if (!(RC_LDCG (&f->facemark[(size_t)vi * w->numfaces + fi]) < key))
 		return;
-	int p = RC_ATOMIC_ADD_I (&f->nfaces[vi], 1);
+	int p = RC_ATOMIC_ADD_I (nfaces, 1);	/* the view's counter: in shared memory on the GPU (same-address L2 atomics serialise) */
 	if (p >= f->facecap || p >= (int)RC_FACEPOS_MARKED - 1)
 	{
 		RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
@@ -449,7 +449,7 @@ RC_HD void rc_clip_emit (const rc_view_t *vw, const rc_xform_t *xf, const float 
 }
 
 /* One thread per (view, face-list slot): R_RenderFace, r_rast.c:518-716. */
-RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int p)
+RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int *nedges)
 {
 	const rc_view_t *vw = &f->views[vi];
 	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
@@ -478,24 +478,27 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 
 	for (int i = 0; i < fa->numedges; i++)
 	{
-		int lindex = w->surfedges[fa->firstedge + i];
-		int m = lindex > 0 ? lindex : -lindex;
-		const float *va = &w->vertexes[3 * w->edges[2 * m + (lindex > 0 ? 0 : 1)]];
-		const float *vb = &w->vertexes[3 * w->edges[2 * m + (lindex > 0 ? 1 : 0)]];
-		const rc_separtner_t sp = w->separtner[fa->firstedge + i];
+		rc_fedge_t fe;
+#ifdef __CUDACC__
+		{
+			const uint4 *q4 = reinterpret_cast<const uint4 *>(&w->fedges[fa->firstedge + i]);
+			const uint4 x = __ldg (q4), y = __ldg (q4 + 1);
+			fe.v0[0] = __uint_as_float (x.x); fe.v0[1] = __uint_as_float (x.y); fe.v0[2] = __uint_as_float (x.z); fe.partner_face = (int)x.w;
+			fe.v1[0] = __uint_as_float (y.x); fe.v1[1] = __uint_as_float (y.y); fe.v1[2] = __uint_as_float (y.z); fe.partner_rev = (int)y.w;
+		}
+#else
+		fe = w->fedges[fa->firstedge + i];
+#endif
+		const float *va = fe.v0, *vb = fe.v1;
 		int q = RC_FACEPOS_NONE;
-		if (sp.partner_face >= 0)
-			q = facepos[sp.partner_face];
+		if (fe.partner_face >= 0)
+			q = facepos[fe.partner_face];
 
 		if (q < (int)RC_FACEPOS_MARKED && list[q].key < rec.key)
 		{
-			/* the partner face ran first: redo its R_ClipEdge to learn what it left in
-			 * medge_t.cachededgeoffset (r_rast.c:583-603) */
-			const rc_face_t *pf = &w->faces[sp.partner_face];
-			int pl = w->surfedges[pf->firstedge + sp.partner_slot];
-			int pm = pl > 0 ? pl : -pl;
-			const float *pa = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 0 : 1)]];
-			const float *pb = &w->vertexes[3 * w->edges[2 * pm + (pl > 0 ? 1 : 0)]];
+			/* the partner face ran first: redo its R_ClipEdge (same medge, its direction, its
+			 * clipflags) to learn what it left in medge_t.cachededgeoffset (r_rast.c:583-603) */
+			const float *pa = fe.partner_rev ? vb : va, *pb = fe.partner_rev ? va : vb;
 			rc_clip_emit (vw, rc_view_xform (vw), pa, pb, list[q].clipflags, 0, &r);
 			if (r.cls == RC_CLS_FULLCLIP)
 				continue;
@@ -586,7 +589,7 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 
 	if (neb)
 	{
-		int base = RC_ATOMIC_ADD_I (&f->nedges[vi], neb);
+		int base = RC_ATOMIC_ADD_I (nedges, neb);
 		if (base + neb > f->edgecap)
 			RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
 		else
@@ -1660,84 +1663,6 @@ RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int
 }
 
 /* ------------------------------------------------------------------ stage 6: draw ------ */
-/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
- * accumulators -> 16.16, clamped to [lo, bbextent] */
-RC_HD void rc_boundary_st (const rc_surf_t *s, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
-{
-	const float z = (float)0x10000 / zi;
-	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
-	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
-	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
-	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
-	*ps = ss; *pt = tt;
-}
-
-/* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
- * D_DrawSpans8 (d_scan.c:278-360) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
- * subdivision boundary instead of once per pixel block.
- *   bnd[seg][i] = 16.16 (s, t) at subdivision boundary b = 8*segment + i, i = 0..9
- *        b = 0              span start, clamped to [0, bbextent]
- *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
- *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
- *   span.izi0 / span.izistep (segment 0 only)
- * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
- * adds: the segment replays the cheap adds from the span start and does the divide / convert /
- * clamp only for its own boundaries. */
-RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
-{
-	const int si = f->segspan[seg];
-	rc_span_t *sp = &f->spans[si];
-	const int count = sp->count;
-	const rc_surf_t *s = f->surfs + sp->gsurf;
-	const int sidx = seg - sp->segbase;
-	const float du = (float)sp->u, dv = (float)sp->v;
-	const float zistepu = s->d_zistepu, zistepv = s->d_zistepv, ziorigin = s->d_ziorigin;
-	if (sidx == 0)
-	{
-		const double zid = ziorigin + dv*zistepv + du*zistepu;
-		sp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
-		sp->izistep = s->izistep;
-	}
-	if (s->pad != RC_SRC_POOL && s->pad != RC_SRC_TEXELS)
-		return;
-	const float sstepu = s->d_sdivzstepu, tstepu = s->d_tdivzstepu;
-	const float sdivz8stepu = sstepu * 8, tdivz8stepu = tstepu * 8, zi8stepu = zistepu * 8;
-	float sdivz = s->d_sdivzorigin + dv*s->d_sdivzstepv + du*sstepu;
-	float tdivz = s->d_tdivzorigin + dv*s->d_tdivzstepv + du*tstepu;
-	float zi = ziorigin + dv*zistepv + du*zistepu;
-	float psdivz = sdivz, ptdivz = tdivz, pzi = zi;		/* the accumulators one step back */
-	for (int q = sidx << 3; q > 0; q--)
-	{
-		psdivz = sdivz; ptdivz = tdivz; pzi = zi;
-		sdivz += sdivz8stepu;
-		tdivz += tdivz8stepu;
-		zi += zi8stepu;
-	}
-	const int nsub = (count + 7) >> 3;
-	int *out = f->bnd + (size_t)seg * (RC_SEG_BND * 2);
-	for (int i = 0; i < RC_SEG_BND; i++)
-	{
-		const int b = (sidx << 3) + i;
-		int ss, tt;
-		if (b < nsub)
-		{
-			rc_boundary_st (s, sdivz, tdivz, zi, b ? 8 : 0, &ss, &tt);
-			psdivz = sdivz; ptdivz = tdivz; pzi = zi;
-			sdivz += sdivz8stepu;
-			tdivz += tdivz8stepu;
-			zi += zi8stepu;
-		}
-		else if (b == nsub)
-		{
-			const float m1 = (float)(count - ((nsub - 1) << 3) - 1);	/* spancountminus1 of the last subdivision */
-			rc_boundary_st (s, psdivz + sstepu * m1, ptdivz + tstepu * m1, pzi + zistepu * m1, 8, &ss, &tt);
-		}
-		else
-			break;
-		out[2 * i] = ss; out[2 * i + 1] = tt;
-	}
-}
-
 /* the 16 bytes of rc_surf_t the draw kernel needs */
 typedef struct {
 	int   cacheofs, cachewidth, srckind, flags;
@@ -1772,17 +1697,152 @@ RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 16); }
 #endif
 
+/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
+ * accumulators -> 16.16, clamped to [lo, bbextent] */
+RC_HD void rc_boundary_st (const rc_surf_t *s, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
+{
+	const float z = (float)0x10000 / zi;
+	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
+	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
+	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
+	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
+	*ps = ss; *pt = tt;
+}
+
+/* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
+ * D_DrawSpans8 (d_scan.c:278-360) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
+ * subdivision boundary instead of once per pixel block.
+ *   bnd[seg][i] = 16.16 (s, t) at subdivision boundary b = 8*segment + i, i = 0..9
+ *        b = 0              span start, clamped to [0, bbextent]
+ *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
+ *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
+ *   span.izi0 / span.izistep (segment 0 only)
+ * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
+ * adds: the segment replays the cheap adds from the span start and does the divide / convert /
+ * clamp only for its own boundaries. */
+typedef struct {		/* what the segment kernel reads of a surface: five 16-byte groups of rc_surf_t */
+	float nearzi, d_ziorigin, d_zistepu, d_zistepv;
+	float d_sdivzstepv, d_tdivzstepv, d_sdivzorigin, d_tdivzorigin;
+	int   cacheofs, cachewidth, srckind, drawflags;
+	float d_sdivzstepu, d_tdivzstepu, d_zistepu_draw; int izistep;
+	int   sadjust, tadjust, bbextents, bbextentt;
+} rc_segsurf_t;
+
+RC_HD rc_segsurf_t rc_load_segsurf (const rc_surf_t *s)
+{
+	rc_segsurf_t d;
+#ifdef __CUDACC__
+	const uint4 *q = reinterpret_cast<const uint4 *>(s);
+	const uint4 g1 = q[1], g3 = q[3], g4 = q[4], g5 = q[5], g6 = q[6];
+	d.nearzi = __uint_as_float (g1.x); d.d_ziorigin = __uint_as_float (g1.y); d.d_zistepu = __uint_as_float (g1.z); d.d_zistepv = __uint_as_float (g1.w);
+	d.d_sdivzstepv = __uint_as_float (g3.x); d.d_tdivzstepv = __uint_as_float (g3.y); d.d_sdivzorigin = __uint_as_float (g3.z); d.d_tdivzorigin = __uint_as_float (g3.w);
+	d.cacheofs = (int)g4.x; d.cachewidth = (int)g4.y; d.srckind = (int)g4.z; d.drawflags = (int)g4.w;
+	d.d_sdivzstepu = __uint_as_float (g5.x); d.d_tdivzstepu = __uint_as_float (g5.y); d.d_zistepu_draw = __uint_as_float (g5.z); d.izistep = (int)g5.w;
+	d.sadjust = (int)g6.x; d.tadjust = (int)g6.y; d.bbextents = (int)g6.z; d.bbextentt = (int)g6.w;
+#else
+	d.nearzi = s->nearzi; d.d_ziorigin = s->d_ziorigin; d.d_zistepu = s->d_zistepu; d.d_zistepv = s->d_zistepv;
+	d.d_sdivzstepv = s->d_sdivzstepv; d.d_tdivzstepv = s->d_tdivzstepv; d.d_sdivzorigin = s->d_sdivzorigin; d.d_tdivzorigin = s->d_tdivzorigin;
+	d.cacheofs = s->cacheofs; d.cachewidth = s->cachewidth; d.srckind = s->pad; d.drawflags = s->drawflags;
+	d.d_sdivzstepu = s->d_sdivzstepu; d.d_tdivzstepu = s->d_tdivzstepu; d.d_zistepu_draw = s->d_zistepu_draw; d.izistep = s->izistep;
+	d.sadjust = s->sadjust; d.tadjust = s->tadjust; d.bbextents = s->bbextents; d.bbextentt = s->bbextentt;
+#endif
+	return d;
+}
+
+RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
+{
+	const int si = f->segspan[seg];
+	rc_span_t *spp = &f->spans[si];
+	const rc_span_t sp = rc_load_span (spp);
+	const int count = sp.count;
+	const rc_segsurf_t s = rc_load_segsurf (f->surfs + sp.gsurf);
+	const int sidx = seg - sp.segbase;
+	const float du = (float)sp.u, dv = (float)sp.v;
+	const float zistepu = s.d_zistepu, zistepv = s.d_zistepv, ziorigin = s.d_ziorigin;
+	if (sidx == 0)
+	{
+		const double zid = ziorigin + dv*zistepv + du*zistepu;
+		spp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
+		spp->izistep = s.izistep;
+	}
+	if (s.srckind != RC_SRC_POOL && s.srckind != RC_SRC_TEXELS)
+		return;
+	const float sstepu = s.d_sdivzstepu, tstepu = s.d_tdivzstepu;
+	const float sdivz8stepu = sstepu * 8, tdivz8stepu = tstepu * 8, zi8stepu = zistepu * 8;
+	float sdivz = s.d_sdivzorigin + dv*s.d_sdivzstepv + du*sstepu;
+	float tdivz = s.d_tdivzorigin + dv*s.d_tdivzstepv + du*tstepu;
+	float zi = ziorigin + dv*zistepv + du*zistepu;
+	float psdivz = sdivz, ptdivz = tdivz, pzi = zi;		/* the accumulators one step back */
+	for (int q = sidx << 3; q > 0; q--)
+	{
+		psdivz = sdivz; ptdivz = tdivz; pzi = zi;
+		sdivz += sdivz8stepu;
+		tdivz += tdivz8stepu;
+		zi += zi8stepu;
+	}
+	const int nsub = (count + 7) >> 3;
+	int *out = f->bnd + (size_t)seg * (RC_SEG_BND * 2);
+	const float m1 = (float)(count - ((nsub - 1) << 3) - 1);	/* spancountminus1 of the last subdivision */
+	const int sadjust = s.sadjust, tadjust = s.tadjust, bbextents = s.bbextents, bbextentt = s.bbextentt;
+	/* first the (cheap, serial) accumulator values of the ten boundaries, then ten independent
+	 * divide / convert / clamp chains the scheduler can overlap */
+	float as[RC_SEG_BND], at[RC_SEG_BND], az[RC_SEG_BND];
+	#pragma unroll
+	for (int i = 0; i < RC_SEG_BND; i++)
+	{
+		const int b = (sidx << 3) + i;
+		if (b == nsub)
+		{
+			as[i] = psdivz + sstepu * m1; at[i] = ptdivz + tstepu * m1; az[i] = pzi + zistepu * m1;
+		}
+		else
+		{
+			as[i] = sdivz; at[i] = tdivz; az[i] = zi;
+		}
+		psdivz = sdivz; ptdivz = tdivz; pzi = zi;
+		sdivz += sdivz8stepu;
+		tdivz += tdivz8stepu;
+		zi += zi8stepu;
+	}
+	int st[RC_SEG_BND * 2];
+	#pragma unroll
+	for (int i = 0; i < RC_SEG_BND; i++)
+	{
+		const int b = (sidx << 3) + i;
+		const int lo = b ? 8 : 0;
+		const float z = (float)0x10000 / az[i];
+		int ss = rc_addw (rc_f2i (as[i] * z), sadjust);
+		int tt = rc_addw (rc_f2i (at[i] * z), tadjust);
+		if (ss > bbextents) ss = bbextents; else if (ss < lo) ss = lo;
+		if (tt > bbextentt) tt = bbextentt; else if (tt < lo) tt = lo;
+		st[2 * i] = ss; st[2 * i + 1] = tt;
+	}
+	/* boundaries past the span's last one are never read: the whole 80-byte record is written with
+	 * five 16-byte stores */
+#ifdef __CUDACC__
+	#pragma unroll
+	for (int i = 0; i < RC_SEG_BND / 2; i++)
+		reinterpret_cast<uint4 *>(out)[i] = make_uint4 ((uint32_t)st[4*i], (uint32_t)st[4*i+1], (uint32_t)st[4*i+2], (uint32_t)st[4*i+3]);
+#else
+	for (int i = 0; i < RC_SEG_BND * 2; i++)
+		out[i] = st[i];
+#endif
+}
+
 /* truncating division by d = 1..7 (the last-subdivision step, d_scan.c:364-365) as a multiply by
  * ceil(2^32 / d): exact for |a| < 2^24 (7 * 2^24 < 2^32), which covers every cached surface
  * (extents <= 256 texels in 16.16); larger differences (turbulent surfaces) take the divide. */
+#ifdef __CUDACC__
+static __device__ __constant__ unsigned rc_divmagic[8] = {	/* ceil(2^32 / d), d = 2..7 (0, 1 unused) */
+	0u, 0u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2AAAAAABu, 0x24924925u };
+#endif
 RC_HD int rc_div_small (int a, int d)
 {
 #ifdef __CUDACC__
 	if (a >= (1 << 24) || a <= -(1 << 24))
 		return a / d;
-	const unsigned long long m = d == 1 ? 0x100000000ull : (unsigned long long)(0xFFFFFFFFu / (unsigned)d + 1u);
 	const unsigned mag = (unsigned)(a < 0 ? -a : a);
-	const int q = (int)((mag * m) >> 32);
+	const int q = d == 1 ? (int)mag : (int)__umulhi (mag, rc_divmagic[d & 7]);
 	return a < 0 ? -q : q;
 #else
 	return a / d;

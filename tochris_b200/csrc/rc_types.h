@@ -112,6 +112,16 @@ typedef struct {
     int partner_slot;       /* index of the medge inside the partner's surfedge run */
 } rc_separtner_t;
 
+/* one per surfedge, flattened at load time so the face kernel reads an edge with two vector loads
+ * instead of chasing surfedges -> medges -> vertexes (three dependent levels, twice when the
+ * partner's use of the edge has to be re-clipped) */
+typedef struct {
+    float v0[3];            /* first vertex in this face's winding direction (r_rast.c:560-575) */
+    int   partner_face;     /* as rc_separtner_t, -1: none */
+    float v1[3];
+    int   partner_rev;      /* 1: the partner walks the medge in the opposite direction */
+} rc_fedge_t;               /* 32 B */
+
 typedef struct {            /* device-resident world; all pointers are device pointers */
     int numplanes, numnodes, numleafs /* incl. leaf 0 */, numfaces, numsurfedges, numedges,
         numvertexes, numtexinfo, numtextures, nummarksurfaces, visleafs, haslight;
@@ -125,6 +135,7 @@ typedef struct {            /* device-resident world; all pointers are device po
     const rc_face_t      *faces;
     const int            *surfedges;
     const rc_separtner_t *separtner;
+    const rc_fedge_t     *fedges;      /* [numsurfedges] */
     const uint16_t       *edges;       /* 2 x uint16 per medge_t */
     const float          *vertexes;    /* 3 floats per mvertex_t */
     const rc_texinfo_t   *texinfo;
