@@ -24,6 +24,7 @@
  * are consumed by grid-stride loops, so the host never waits inside a batch.
  */
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -77,6 +78,8 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
+	cudaStream_t copystream; cudaEvent_t evgroup[8], evcopy;
+	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
 	int profiling;
@@ -88,22 +91,25 @@ struct rc_gpu_s {
 };
 
 /* ------------------------------------------------------------------------ kernels ----- */
-/* Front end, one CTA per view: everything from the view leaf to the view's
- * edge and surface records in ONE launch.  The phases are the former k_begin / k_visit /
- * k_listfaces / k_faces / k_fixup bodies separated by __syncthreads(): a view's front end is a
- * few hundred items per phase, so separate grids were launch- and tail-bound; in one CTA the
- * per-view scratch (face marks, node visits, face list) is written and re-read by the same SM.
+/* Front end, one thread-block CLUSTER per view: everything from the view leaf
+ * to the view's edge and surface records in ONE launch.  The phases are the former k_begin /
+ * k_visit / k_listfaces / k_faces / k_fixup bodies separated by cluster barriers.  A view's front
+ * end is ~50 K warp-instructions of branchy, dependent code: one CTA per view left most of the 148
+ * SMs idle at BASELINE's batch of 64, so the host picks a cluster of 1-8 CTAs per view such that the
+ * grid covers the machine; the CTAs of a cluster split every phase's items and share the view's two
+ * counters through distributed shared memory (rank 0's).
  *   phase 0  reset the view's facepos / facemark / nodevisit rows, background surface
  *   phase 1  rc_visit       per node-or-leaf: root->x replay (PVS, frustum, BSP sort key)
  *   phase 2  rc_list_face   per world face: is R_RenderFace called on it
  *   phase 3  rc_render_face per listed face: clip, project, edges, surf_t
  *   phase 4  fix-up of faces that read r_rightenter/r_rightexit left by an earlier face:
  *            the search for the latest earlier writer is done by the whole warp */
-#define FRONT_THREADS 256
+#define FRONT_THREADS 512
+#define FRONT_WARPS (FRONT_THREADS / 32)
 
-/* L2 prefetch of this CTA's 1/gridDim slice of a read-only array: the front end chases pointers
- * through the BSP (node -> plane -> child ...), and after a cold start (the bench flushes L2 between
- * steps) every level would otherwise be a dependent HBM miss */
+/* L2 prefetch of a slice of a read-only array: the front end chases pointers through the BSP
+ * (node -> plane -> child ...), and after a cold start (the bench flushes L2 between steps) every
+ * level would otherwise be a dependent HBM miss */
 __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
 {
 	const size_t lines = (bytes + 127) >> 7;
@@ -115,18 +121,17 @@ __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
 	for (size_t i = lo + threadIdx.x; i < hi; i += FRONT_THREADS)
 		asm volatile ("prefetch.global.L2 [%0];" :: "l"(base + (i << 7)));
 }
+
 __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	__shared__ int s_nfaces, s_nedges;
-	const int vi = blockIdx.x, tid = threadIdx.x;
-	if (tid == 0) { s_nfaces = 0; s_nedges = 0; }
-#ifdef RC_FRONT_TIMING
-	long long tq[6]; 
-	#define TQ(i) do { if (tid == 0) tq[i] = clock64 (); } while (0)
-#else
-	#define TQ(i) do { } while (0)
-#endif
-	TQ(0);
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster ();
+	__shared__ int s_counters[2];			/* listed faces, emitted edges of the view (rank 0's copy is the live one) */
+	const int csize = (int)cluster.num_blocks (), crank = (int)cluster.block_rank ();
+	const int vi = blockIdx.x / csize, tid = threadIdx.x;
+	const int gtid = crank * FRONT_THREADS + tid, gthreads = csize * FRONT_THREADS;
+	int *ctr = cluster.map_shared_rank (s_counters, 0);
+	if (tid < 2) s_counters[tid] = 0;
 	front_prefetch (w.nodes, sizeof(rc_node_t) * (size_t)w.numnodes);
 	front_prefetch (w.planes, sizeof(rc_plane_t) * (size_t)w.numplanes);
 	front_prefetch (w.nodeaux, sizeof(rc_nodeaux_t) * (size_t)w.numnodes);
@@ -139,34 +144,34 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 		uint16_t *facepos = f.facepos + (size_t)vi * w.numfaces;
 		int *facemark = f.facemark + (size_t)vi * w.numfaces;
 		unsigned long long *nv = reinterpret_cast<unsigned long long *>(f.nodevisit + (size_t)vi * w.numnodes);
-		for (int i = tid; i < w.numfaces; i += FRONT_THREADS) { facepos[i] = RC_FACEPOS_NONE; facemark[i] = 0x7F7F7F7F; }
-		for (int i = tid; i < w.numnodes; i += FRONT_THREADS) nv[i] = 0ull;
-		if (tid == 0)
+		for (int i = gtid; i < w.numfaces; i += gthreads) { facepos[i] = RC_FACEPOS_NONE; facemark[i] = 0x7F7F7F7F; }
+		for (int i = gtid; i < w.numnodes; i += gthreads) nv[i] = 0ull;
+		if (gtid == 0)
 			rc_view_begin (&w, &f, vi);
 	}
-	__syncthreads ();
-	TQ(1);
-	for (int x = tid; x < w.numnodes + w.numleafs; x += FRONT_THREADS)
+	cluster.sync ();
+	/* visit and face items are long, branchy and all different: a warp pays for the union of its
+	 * lanes' paths, so items are dealt round-robin to the WARPS of the cluster (item i -> warp
+	 * i % nwarps, lane i / nwarps) instead of filling one warp after the other */
+	const int nwarps = csize * FRONT_WARPS;
+	const int spread = (tid & 31) * nwarps + crank * FRONT_WARPS + (tid >> 5);
+	for (int x = spread; x < w.numnodes + w.numleafs; x += gthreads)
 		rc_visit (&w, &f, vi, x);
-	__syncthreads ();
-	TQ(2);
-	for (int fi = tid; fi < w.numworldfaces; fi += FRONT_THREADS)
-		rc_list_face (&w, &f, vi, fi, &s_nfaces);
-	__syncthreads ();
-	TQ(3);
-	const int nfraw = s_nfaces;
+	cluster.sync ();
+	for (int fi = gtid; fi < w.numworldfaces; fi += gthreads)
+		rc_list_face (&w, &f, vi, fi, &ctr[0]);
+	cluster.sync ();
+	const int nfraw = ctr[0];
 	const int nf = nfraw < f.facecap ? nfraw : f.facecap;
-	if (tid == 0) f.nfaces[vi] = nfraw;
-	for (int p = tid; p < nf; p += FRONT_THREADS)
-		rc_render_face (&w, &f, vi, p, &s_nedges);
-	__syncthreads ();
-	if (tid == 0) f.nedges[vi] = s_nedges;
-	TQ(4);
+	for (int p = spread; p < nf; p += gthreads)
+		rc_render_face (&w, &f, vi, p, &ctr[1]);
+	cluster.sync ();
+	if (gtid == 0) { f.nfaces[vi] = nfraw; f.nedges[vi] = ctr[1]; }
 	{
 		const int lane = tid & 31;
 		const rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
 		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
-		for (int p0 = (tid >> 5) << 5; p0 < nf; p0 += FRONT_THREADS)
+		for (int p0 = (gtid >> 5) << 5; p0 < nf; p0 += gthreads)
 		{
 			const int p = p0 + lane;
 			const bool need = p < nf && (surfs[p + 2].miplevel & 4);
@@ -200,13 +205,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 			}
 		}
 	}
-#ifdef RC_FRONT_TIMING
-	__syncthreads ();
-	TQ(5);
-	if (tid == 0)
-		for (int i = 0; i < 5; i++)
-			atomicMax (&f.status[4 + i], (int)(tq[i + 1] - tq[i]));
-#endif
+	cluster.sync ();		/* rank 0's shared memory must outlive the other ranks' reads */
 }
 
 /* Scan stage (R_ScanEdges, R_InsertNewEdges, R_StepActiveU, R_GenerateSpans), one
@@ -723,11 +722,11 @@ __global__ void k_spanseg (const __grid_constant__ rc_world_t w, const __grid_co
 __global__ void __launch_bounds__(128) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	const unsigned cw = (unsigned)((f.width + 7) >> 3);
-	const unsigned ncells = (unsigned)(f.nviews * f.height) * cw;
+	const unsigned ncells = (unsigned)(f.drawview1 * f.height) * cw;
 	const unsigned stride = gridDim.x * blockDim.x;
 	/* cell -> span -> (surface, boundaries) -> texels is a chain of dependent loads: the first two
 	 * levels of the next grid-stride iterations are fetched while the current cell is drawn */
-	unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x, t1 = t0 + stride;
+	unsigned t0 = (unsigned)(f.drawview0 * f.height) * cw + blockIdx.x * blockDim.x + threadIdx.x, t1 = t0 + stride;
 	int si0 = t0 < ncells ? __ldg (&f.cellspan[t0]) : -1;
 	int si1 = t1 < ncells ? __ldg (&f.cellspan[t1]) : -1;
 	rc_span_t sp0 = rc_load_span (&f.spans[si0 < 0 ? 0 : si0]);
@@ -749,8 +748,17 @@ __global__ void __launch_bounds__(128) k_draw (const __grid_constant__ rc_world_
 	unsigned long long a = f.alloc[0];
 	unsigned nspans = (unsigned)(a & 0xFFFFFFFFu);
 	if (nspans > (unsigned)f.spancap) nspans = (unsigned)f.spancap;
+	const bool allviews = f.drawview0 == 0 && f.drawview1 == f.nviews;
 	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nspans; t += stride)
+	{
+		if (!allviews)
+		{
+			const int v = __ldg (&f.spans[t].view);
+			if (v < f.drawview0 || v >= f.drawview1)
+				continue;
+		}
 		rc_draw_head (&w, &f, (int)t);
+	}
 }
 
 __global__ void k_warp (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -829,6 +837,10 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaGetDeviceProperties (&prop, device);
 	g->numsms = prop.multiProcessorCount;
 	cudaStreamCreateWithFlags (&g->stream, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags (&g->copystream, cudaStreamNonBlocking);
+	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags (&g->evgroup[i], cudaEventDisableTiming);
+	cudaEventCreateWithFlags (&g->evcopy, cudaEventDisableTiming);
+	g->host_fb = NULL; g->host_z = NULL;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
 
 	std::vector<int> st (RC_SIN_BUFFER_SIZE), ist (RC_SIN_BUFFER_SIZE);
@@ -1075,7 +1087,19 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
 	CK (cudaMemsetAsync (g->d_alloc + 2, 0, sizeof(unsigned long long), s));
 
-	k_front<<<n, FRONT_THREADS, 0, s>>> (w, f);
+	{
+		/* cluster size: as many CTAs per view as fit the machine in one wave, at most 8 */
+		int csize = 1;
+		while (csize < 8 && n * csize * 2 <= g->numsms) csize *= 2;	/* one wave, one CTA per SM */
+		cudaLaunchConfig_t cfg;
+		cudaLaunchAttribute attr[1];
+		memset (&cfg, 0, sizeof(cfg));
+		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (FRONT_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		CK (cudaLaunchKernelEx (&cfg, k_front, w, f));
+	}
 	if (timed) cudaEventRecord (g->ev[1], s);
 	if (g->cur_batch && g->cur_batch->nbents)
 	{
@@ -1105,7 +1129,39 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	if (timed) cudaEventRecord (g->ev[5], s);
 	k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[7], s);
-	k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+	const bool entities = g->cur_batch && g->cur_batch->nzres;
+	bool grouped = false;
+	if (g->host_fb && !entities && !anywarp && n >= 8)
+	{
+		grouped = true;
+		/* host-output path: the D2H copy (PCIe) is the longest single item of a batch, so the views are
+		 * drawn in groups and every finished group is copied out on a second stream while the next
+		 * one is drawn */
+		const int ngroups = n >= 32 ? 4 : 2;
+		const size_t px = (size_t)g->width * g->height;
+		for (int gi = 0; gi < ngroups; gi++)
+		{
+			f.drawview0 = (int)((long long)n * gi / ngroups); f.drawview1 = (int)((long long)n * (gi + 1) / ngroups);
+			const int nv = f.drawview1 - f.drawview0;
+			int ctas = (int)(((size_t)nv * g->height * ((g->width + 7) / 8) + 127) / 128);
+			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
+			k_draw<<<ctas, 128, 0, s>>> (w, f);
+			cudaEventRecord (g->evgroup[gi], s);
+			cudaStreamWaitEvent (g->copystream, g->evgroup[gi], 0);
+			const size_t ofs = px * (size_t)(first_view + f.drawview0);
+			CK (cudaMemcpyAsync (g->host_fb + ofs, fb + px * f.drawview0, px * nv, cudaMemcpyDeviceToHost, g->copystream));
+			if (g->host_z)
+				CK (cudaMemcpyAsync (g->host_z + ofs, zb + px * f.drawview0, px * nv * sizeof(int16_t), cudaMemcpyDeviceToHost, g->copystream));
+		}
+		g->stats.kernel_launches += ngroups - 1;
+		cudaEventRecord (g->evcopy, g->copystream);
+		cudaStreamWaitEvent (s, g->evcopy, 0);		/* the stream's work is complete only when the copies are */
+	}
+	else
+	{
+		f.drawview0 = 0; f.drawview1 = n;
+		k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+	}
 	if (g->cur_batch && g->cur_batch->nzres)
 	{
 		const rc_batch_t *b = g->cur_batch;
@@ -1148,6 +1204,14 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		dim3 gw2 ((g->width + 127) / 128, g->height, n);
 		k_warp<<<gw2, 128, 0, s>>> (w, f);
 		g->stats.kernel_launches++;
+	}
+	if (g->host_fb && !grouped)
+	{
+		/* entity / warp kernels touched the frame after the draw: one copy at the end of the chunk */
+		const size_t px = (size_t)g->width * g->height;
+		CK (cudaMemcpyAsync (g->host_fb + px * first_view, fb, px * n, cudaMemcpyDeviceToHost, s));
+		if (g->host_z)
+			CK (cudaMemcpyAsync (g->host_z + px * first_view, zb, px * n * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
 	g->stats.kernel_launches += 6;
@@ -1289,13 +1353,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		}
 		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
-#ifdef RC_FRONT_TIMING
-		{
-			int tq[16];
-			cudaMemcpy (tq, g->d_status, sizeof(tq), cudaMemcpyDeviceToHost);
-			fprintf (stderr, "k_front max cycles: reset %d visit %d list %d faces %d fixup %d\n", tq[4], tq[5], tq[6], tq[7], tq[8]);
-		}
-#endif
+
 		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL)))
 			break;
 		if (st & RC_STAT_SPAN_POOL)
@@ -1331,12 +1389,12 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 	/* every pixel of a full-screen view is written by the world spans; views that use a
 	 * sub-rectangle leave the rest as the caller's buffer had it in the reference, here 0 */
 	CK (cudaMemsetAsync (g->d_fb, 0, px * n, g->stream));
+	/* the device->host copies are issued by run_chunk (overlapped with the draw kernel where possible);
+	 * rc_gpu_render returns when the stream, copies included, has drained */
+	g->host_fb = fb_out; g->host_z = z_out;
 	int r = rc_gpu_render (g, batch, g->d_fb, g->d_zb, NULL, status, err, errlen);
-	if (r != RC_OK) return r;
-	CK (cudaMemcpyAsync (fb_out, g->d_fb, px * n, cudaMemcpyDeviceToHost, g->stream));
-	if (z_out) CK (cudaMemcpyAsync (z_out, g->d_zb, px * n * sizeof(int16_t), cudaMemcpyDeviceToHost, g->stream));
-	CK (cudaStreamSynchronize (g->stream));
-	return RC_OK;
+	g->host_fb = NULL; g->host_z = NULL;
+	return r;
 }
 
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }

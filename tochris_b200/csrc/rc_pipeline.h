@@ -92,6 +92,7 @@ typedef struct {
     rc_cachejob_t *jobs; int jobcap;
     /* outputs */
     uint8_t *fb; int16_t *zb;
+    int drawview0, drawview1;     /* views [drawview0, drawview1) are drawn by this launch of the draw kernel */
     uint8_t *warpbuf;             /* [nwarp][320*200]: r_warpbuffer of the views that render under water */
     /* alias models and particles */
     const rc_aliasinst_t *alias; int nalias;

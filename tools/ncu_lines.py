@@ -37,7 +37,7 @@ def sass_lines(kernel):
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             lines.append((cur, ln.split("*/", 1)[1].strip().rstrip(";")))
     return lines
 
