@@ -124,7 +124,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	f.edges = g->edges.data (); f.nedges = g->nedges.data ();
 	f.bsurfcap = batch->nbents ? 512 : 0;
 	f.surfcap = f.facecap + 2 + f.bsurfcap;
-	std::vector<int> leafkey ((size_t)n * w->numleafs, 0), nbsurfs (n, 0);
+	std::vector<int> leafkey ((size_t)n * w->numleafs, 0x7FFFFFFF), nbsurfs (n, 0);
 	f.leafkey = leafkey.data (); f.nbsurfs = nbsurfs.data (); f.bents = batch->bents; f.nbents = batch->nbents;
 	g->surfs.assign ((size_t)n * f.surfcap, rc_surf_t ());
 	f.surfs = g->surfs.data ();
@@ -152,8 +152,16 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	std::vector<rc_nodevisit_t> nodevisit ((size_t)n * w->numnodes, rc_nodevisit_t ());
 	f.facemark = facemark.data (); f.viewleaf = viewleaf.data (); f.nodevisit = nodevisit.data ();
 	for (int vi = 0; vi < n; vi++) rc_view_begin (w, &f, vi);
-	for (int vi = 0; vi < n; vi++)
-		for (int x = 0; x < w->numnodes + w->numleafs; x++) rc_visit (w, &f, vi, x);
+	{
+		std::vector<uint16_t> masks (w->numnodes + 1);
+		for (int vi = 0; vi < n; vi++)
+		{
+			for (int i = 0; i < w->numnodes; i++) masks[i] = rc_node_test (w, &f, vi, i);
+			for (int x = 0; x < w->numnodes + w->numleafs; x++) rc_visit_walk (w, &f, vi, x, masks.data ());
+			if (w->marksplit)
+				for (int m = 0; m < w->nummarksurfaces; m++) rc_mark_face (w, &f, vi, m);
+		}
+	}
 	for (int vi = 0; vi < n; vi++)
 		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi, &f.nfaces[vi]);
 	for (int vi = 0; vi < n; vi++)

@@ -106,38 +106,50 @@ struct rc_gpu_s {
  *            the search for the latest earlier writer is done by the whole warp */
 #define FRONT_THREADS 512
 #define FRONT_WARPS (FRONT_THREADS / 32)
+#define FRONT_EDGE_SLOTS 1024
+#define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
 
 /* L2 prefetch of a slice of a read-only array: the front end chases pointers through the BSP
  * (node -> plane -> child ...), and after a cold start (the bench flushes L2 between steps) every
  * level would otherwise be a dependent HBM miss */
 __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
 {
-	const size_t lines = (bytes + 127) >> 7;
-	const size_t per = (lines + gridDim.x - 1) / gridDim.x;
-	const size_t lo = per * blockIdx.x;
-	size_t hi = lo + per;
+	const unsigned lines = (unsigned)((bytes + 127) >> 7);
+	const unsigned per = (lines + gridDim.x - 1) / gridDim.x;
+	const unsigned lo = per * blockIdx.x;
+	unsigned hi = lo + per;
 	if (hi > lines) hi = lines;
 	const char *base = reinterpret_cast<const char *>(p);
-	for (size_t i = lo + threadIdx.x; i < hi; i += FRONT_THREADS)
-		asm volatile ("prefetch.global.L2 [%0];" :: "l"(base + (i << 7)));
+	for (unsigned i = lo + threadIdx.x; i < hi; i += FRONT_THREADS)
+		asm volatile ("prefetch.global.L2 [%0];" :: "l"(base + ((size_t)i << 7)));
 }
 
 __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster ();
+	extern __shared__ __align__(16) unsigned char front_smem[];
 	__shared__ int s_counters[2];			/* listed faces, emitted edges of the view (rank 0's copy is the live one) */
 	const int csize = (int)cluster.num_blocks (), crank = (int)cluster.block_rank ();
 	const int vi = blockIdx.x / csize, tid = threadIdx.x;
 	const int gtid = crank * FRONT_THREADS + tid, gthreads = csize * FRONT_THREADS;
 	int *ctr = cluster.map_shared_rank (s_counters, 0);
 	if (tid < 2) s_counters[tid] = 0;
+#ifdef RC_FRONT_TIMING
+	long long tq[16];
+	int tqn = 0;
+	#define TQ() do { if (tid == 0) tq[tqn++] = clock64 (); } while (0)
+#else
+	#define TQ() do { } while (0)
+#endif
+	TQ ();
 	front_prefetch (w.nodes, sizeof(rc_node_t) * (size_t)w.numnodes);
 	front_prefetch (w.planes, sizeof(rc_plane_t) * (size_t)w.numplanes);
 	front_prefetch (w.nodeaux, sizeof(rc_nodeaux_t) * (size_t)w.numnodes);
 	front_prefetch (w.leafs, sizeof(rc_leaf_t) * (size_t)w.numleafs);
 	front_prefetch (w.leafdfs, sizeof(int) * (size_t)w.numleafs);
 	front_prefetch (w.marksurfaces, sizeof(int) * (size_t)w.nummarksurfaces);
+	front_prefetch (w.markleaf, sizeof(int) * (size_t)w.nummarksurfaces);
 	front_prefetch (w.faces, sizeof(rc_face_t) * (size_t)w.numfaces);
 	front_prefetch (w.fedges, sizeof(rc_fedge_t) * (size_t)w.numsurfedges);
 	{
@@ -146,26 +158,145 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 		unsigned long long *nv = reinterpret_cast<unsigned long long *>(f.nodevisit + (size_t)vi * w.numnodes);
 		for (int i = gtid; i < w.numfaces; i += gthreads) { facepos[i] = RC_FACEPOS_NONE; facemark[i] = 0x7F7F7F7F; }
 		for (int i = gtid; i < w.numnodes; i += gthreads) nv[i] = 0ull;
+		int *leafkey = f.leafkey + (size_t)vi * w.numleafs;
+		for (int i = gtid; i < w.numleafs; i += gthreads) leafkey[i] = 0x7FFFFFFF;
 		if (gtid == 0)
 			rc_view_begin (&w, &f, vi);
 	}
 	cluster.sync ();
+	TQ ();
 	/* visit and face items are long, branchy and all different: a warp pays for the union of its
 	 * lanes' paths, so items are dealt round-robin to the WARPS of the cluster (item i -> warp
 	 * i % nwarps, lane i / nwarps) instead of filling one warp after the other */
 	const int nwarps = csize * FRONT_WARPS;
 	const int spread = (tid & 31) * nwarps + crank * FRONT_WARPS + (tid >> 5);
-	for (int x = spread; x < w.numnodes + w.numleafs; x += gthreads)
-		rc_visit (&w, &f, vi, x);
+	{
+		/* phase 1a: per-node frustum / plane-side tests into shared memory (every CTA of the cluster
+		 * keeps its own copy: the tests are cheap, remote shared memory is not) */
+		uint16_t *s_mask = reinterpret_cast<uint16_t *>(front_smem);
+		for (int i = tid; i < w.numnodes; i += FRONT_THREADS)
+		{
+			s_mask[i] = rc_node_test (&w, &f, vi, i);
+			asm volatile ("prefetch.global.L1 [%0];" :: "l"(&w.nodeaux[i]));	/* the walk reads these */
+		}
+		__syncthreads ();
+		TQ ();
+		/* phase 1b: root->x replay over the masks */
+		for (int x = spread; x < w.numnodes + w.numleafs; x += gthreads)
+			rc_visit_walk (&w, &f, vi, x, s_mask);
+	}
 	cluster.sync ();
+	TQ ();
+	/* phase 1c: visited leaves stamp their faces */
+	if (w.marksplit)
+	{
+		for (int m = gtid; m < w.nummarksurfaces; m += gthreads)
+			rc_mark_face (&w, &f, vi, m);
+		cluster.sync ();
+	}
+	TQ ();
 	for (int fi = gtid; fi < w.numworldfaces; fi += gthreads)
 		rc_list_face (&w, &f, vi, fi, &ctr[0]);
 	cluster.sync ();
+	TQ ();
 	const int nfraw = ctr[0];
 	const int nf = nfraw < f.facecap ? nfraw : f.facecap;
-	for (int p = spread; p < nf; p += gthreads)
-		rc_render_face (&w, &f, vi, p, &ctr[1]);
+	{
+		/* phase 3, two steps per batch of faces (this CTA's contiguous share of the list):
+		 *   a  one thread per polygon EDGE: edge-cache decision, clip, project   (rc_face_edge)
+		 *   b  one thread per face: fold the edge results, surf_t, edge records  (rc_face_finish)
+		 * A face is a serial chain of 4-8 edges in the reference; giving every edge its own thread cuts the
+		 * phase's critical path by that factor.  Edge results live in shared memory. */
+		rc_edgeres_t *s_res = reinterpret_cast<rc_edgeres_t *>(front_smem);
+		uint32_t *s_owner = reinterpret_cast<uint32_t *>(front_smem + sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS);
+		__shared__ int s_wsum[FRONT_WARPS], s_included, s_total;
+		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
+		const int plo = (int)((long long)nf * crank / csize), phi = (int)((long long)nf * (crank + 1) / csize);
+		const int lane = tid & 31, wid = tid >> 5;
+		for (int pb = plo; pb < phi; )
+		{
+			const int p = pb + tid;
+			int ne = 0;
+			bool toobig = false;
+			if (p < phi)
+			{
+				ne = w.faces[list[p].face].numedges;
+				if (ne > RC_MAX_FACE_EDGES) { toobig = true; ne = 0; }
+			}
+			/* block-wide exclusive scan of the edge counts */
+			int incl = ne;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int t = __shfl_up_sync (0xFFFFFFFFu, incl, o);
+				if (lane >= o) incl += t;
+			}
+			if (lane == 31) s_wsum[wid] = incl;
+			if (tid == 0) { s_included = 0; s_total = 0; }
+			__syncthreads ();
+			int wbase = 0;
+			for (int q = 0; q < wid; q++) wbase += s_wsum[q];
+			const int off = wbase + incl - ne;
+			const bool inc = p < phi && off + ne <= FRONT_EDGE_SLOTS;
+			if (inc)
+			{
+				atomicAdd (&s_included, 1);
+				atomicMax (&s_total, off + ne);
+				for (int i = 0; i < ne; i++)
+					s_owner[off + i] = (uint32_t)tid | ((uint32_t)i << 16);
+			}
+			__syncthreads ();
+			TQ ();
+			const int total = s_total, included = s_included;
+			for (int e = tid; e < total; e += FRONT_THREADS)
+			{
+				const uint32_t own = s_owner[e];
+				rc_face_edge (&w, &f, vi, pb + (int)(own & 0xFFFFu), (int)(own >> 16), &s_res[e]);
+			}
+			__syncthreads ();
+			TQ ();
+			/* b: fold, then ONE reservation of edge records per batch (a block scan of the faces'
+			 * counts; same-address atomics from every face thread serialise), then emit */
+			rc_facefold_t st;
+			st.neb = 0;
+			if (inc && !toobig)
+				rc_face_fold (&w, &f, vi, p, &s_res[off], &st);
+			int einc = st.neb;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int t = __shfl_up_sync (0xFFFFFFFFu, einc, o);
+				if (lane >= o) einc += t;
+			}
+			if (lane == 31) s_wsum[wid] = einc;
+			__syncthreads ();
+			if (tid == 0)
+			{
+				int tot = 0;
+				for (int q = 0; q < FRONT_WARPS; q++) tot += s_wsum[q];
+				s_total = tot ? atomicAdd (&ctr[1], tot) : 0;
+			}
+			int ebase = 0;
+			for (int q = 0; q < wid; q++) ebase += s_wsum[q];
+			__syncthreads ();
+			ebase += s_total + einc - st.neb;
+			if (inc)
+			{
+				if (toobig)
+				{
+					rc_surf_t *surf = f.surfs + (size_t)vi * f.surfcap + (p + 2);
+					surf->flags = -1; surf->hasspans = 0;
+					atomicOr (f.status, RC_STAT_EDGE_OVERFLOW);
+				}
+				else
+					rc_face_emit (&w, &f, vi, p, &s_res[off], &st, ebase);
+			}
+			__syncthreads ();
+			pb += included;		/* included faces are a prefix of the batch (offsets grow) */
+		}
+	}
 	cluster.sync ();
+	TQ ();
 	if (gtid == 0) { f.nfaces[vi] = nfraw; f.nedges[vi] = ctr[1]; }
 	{
 		const int lane = tid & 31;
@@ -206,6 +337,12 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 		}
 	}
 	cluster.sync ();		/* rank 0's shared memory must outlive the other ranks' reads */
+#ifdef RC_FRONT_TIMING
+	TQ ();
+	if (tid == 0)
+		for (int i = 0; i + 1 < tqn; i++)
+			atomicMax (&f.status[4 + i], (int)(tq[i + 1] - tq[i]));
+#endif
 }
 
 /* Scan stage (R_ScanEdges, R_InsertNewEdges, R_StepActiveU, R_GenerateSpans), one
@@ -833,6 +970,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_particles = NULL; g->particlecap = 0; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
 	cudaFuncSetAttribute (k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t));
+	cudaFuncSetAttribute (k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties (&prop, device);
 	g->numsms = prop.multiProcessorCount;
@@ -968,6 +1106,7 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	UP (texels, hw->texelbytes + 16)
 	UP (lightdata, hw->lightbytes + 16)
 	UP (marksurfaces, h->nummarksurfaces + 1)
+	UP (markleaf, h->nummarksurfaces + 1)
 	UP (nodevis, (size_t)h->visrowwords * h->numleafs)
 	UP (colormap, 256 * 64)
 	UP (nodeaux, h->numnodes + 1)
@@ -1043,8 +1182,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_nodevisit, sizeof(rc_nodevisit_t) * (size_t)want * w->numnodes));
 	CK (cudaMalloc (&g->d_viewleaf, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_nbsurfs, sizeof(int) * want));
-	if (want_bsurfs)
-		CK (cudaMalloc (&g->d_leafkey, sizeof(int) * (size_t)want * w->numleafs));
+	CK (cudaMalloc (&g->d_leafkey, sizeof(int) * (size_t)want * w->numleafs));
 	CK (cudaMalloc (&g->d_edges, sizeof(rc_edge_t) * (size_t)want * edgecap));
 	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
@@ -1069,7 +1207,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = g->d_views; f.dlights = g->d_dlights;
 	f.viewbase = first_view;
 	f.bents = g->d_bents; f.nbents = g->cur_batch ? g->cur_batch->nbents : 0;
-	f.leafkey = g->bsurfcap ? g->d_leafkey : NULL; f.nbsurfs = g->d_nbsurfs; f.bsurfcap = g->bsurfcap;
+	f.leafkey = g->d_leafkey; f.nbsurfs = g->d_nbsurfs; f.bsurfcap = g->bsurfcap;
 	f.facelist = g->d_facelist; f.facecap = g->facecap; f.nfaces = g->d_nfaces; f.facepos = g->d_facepos;
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
@@ -1094,7 +1232,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaLaunchConfig_t cfg;
 		cudaLaunchAttribute attr[1];
 		memset (&cfg, 0, sizeof(cfg));
-		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (FRONT_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
@@ -1353,6 +1491,13 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		}
 		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
+#ifdef RC_FRONT_TIMING
+		{
+			int tq[16];
+			cudaMemcpy (tq, g->d_status, sizeof(tq), cudaMemcpyDeviceToHost);
+			fprintf (stderr, "k_front max cycles: reset %d nodetest %d walk %d mark %d list %d | facescan %d edge %d finish %d | fixup %d\n", tq[4], tq[5], tq[6], tq[7], tq[8], tq[9], tq[10], tq[11], tq[12]);
+		}
+#endif
 
 		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL)))
 			break;

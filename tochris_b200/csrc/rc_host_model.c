@@ -353,6 +353,12 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 		}
 		w->nummarksurfaces = n;
 		w->marksurfaces = out;
+		{
+			int *ml = (int *)own (hw, sizeof(int) * (n + 1));
+			for (i = 0; i <= n; i++) ml[i] = -1;
+			w->markleaf = ml;
+			w->marksplit = 1;
+		}
 	}
 
 	/* leafs, nodes (r_model.c:872-963) */
@@ -377,6 +383,12 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 			leafs[i].nummarks = lin[i].nummarksurfaces;
 			leafs[i].parent = -1;
 			if (leafs[i].firstmark + leafs[i].nummarks > w->nummarksurfaces) FAIL ("leaf %d bad marksurfaces", i);
+			for (j = 0; j < leafs[i].nummarks; j++)
+			{
+				int *ml = (int *)w->markleaf;
+				if (ml[leafs[i].firstmark + j] != -1) w->marksplit = 0;
+				ml[leafs[i].firstmark + j] = i;
+			}
 		}
 		for (i = 0; i < nn; i++)
 		{

@@ -198,17 +198,49 @@ RC_HD void rc_view_begin (const rc_world_t *w, const rc_frame_t *f, int vi)
 	f->viewleaf[vi] = v->viewleaf >= 0 && v->viewleaf < w->numleafs ? v->viewleaf : 0;
 }
 
-/* One thread per (view, node-or-leaf x): decides whether R_RecursiveWorldNode (r_bsp.c:436-557)
- * reaches x for this view, by replaying the root->x descent: every ancestor must be in the
- * PVS-marked set (precomputed R_MarkLeaves row) and survive the bbox/frustum test with the
- * clipflags it inherits.  The BSP sort key is accumulated on the way down from static subtree
- * slot counts: front subtree first, then the node's faces, then the back subtree -- the same
- * order in which the reference increments r_currentkey, so keys compare identically.
+/* The BSP walk, R_RecursiveWorldNode (r_bsp.c:436-557), in two parallel steps.
+ *
+ * rc_node_test, one thread per (view, node): everything the recursion computes AT a node that does
+ * not depend on the path taken to it: for each of the four frustum planes whether the node's box is
+ * rejected (bits 0-3) or fully accepted (bits 4-7) -- the reference only evaluates planes still set
+ * in the inherited clipflags, which the walk below re-applies --, the side of the node's plane the
+ * view is on (bit 8) and the three-way front/back/on-plane state (bits 9-10).  Bit 15: the node is in
+ * the PVS-marked set of the view leaf (precomputed R_MarkLeaves row).
+ *
+ * rc_visit_walk, one thread per (view, node-or-leaf x): decides whether the recursion reaches x by
+ * replaying the root->x descent over those masks: every ancestor must survive the reject test with
+ * the clipflags it inherits.  The BSP sort key is accumulated on the way down from static subtree
+ * slot counts: front subtree first, then the node's faces, then the back subtree -- the same order
+ * in which the reference increments r_currentkey, so keys compare identically.
  *   visited node -> f->nodevisit[x] (side, clipflags, key of its first face)
  *   visited leaf -> atomicMin of the leaf's key into f->facemark[] for its marksurfaces
  *                   (surf->visframe = r_framecount happens when the leaf is reached, so a face
  *                   is drawn only if some leaf with a SMALLER key marked it). */
-RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
+RC_HD uint16_t rc_node_test (const rc_world_t *w, const rc_frame_t *f, int vi, int n)
+{
+	const rc_view_t *v = &f->views[vi];
+	if (v->rdflags & 1 /* RDF_NOWORLDMODEL */)
+		return 0;
+	const uint32_t *vis = w->nodevis + (size_t)f->viewleaf[vi] * w->visrowwords;
+	if (!rc_visbit (vis, n))
+		return 0;
+	const rc_node_t *nd = &w->nodes[n];
+	int m = 0x8000;
+	for (int i = 0; i < 4; i++)
+	{
+		int one = 1 << i;
+		if (!rc_cull_box (v, nd->minmaxs, &one))
+			m |= 1 << i;		/* rejectpt behind plane i */
+		else if (!one)
+			m |= 16 << i;		/* acceptpt in front: the whole box is inside plane i */
+	}
+	double dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
+	if (dot < 0) m |= 0x100;
+	m |= (dot > RC_BACKFACE_EPSILON ? 1 : (dot < -RC_BACKFACE_EPSILON ? 2 : 3)) << 9;
+	return (uint16_t)m;
+}
+
+RC_HD void rc_visit_walk (const rc_world_t *w, const rc_frame_t *f, int vi, int x, const uint16_t *masks)
 {
 	const rc_view_t *v = &f->views[vi];
 	if (v->rdflags & 1 /* RDF_NOWORLDMODEL */)
@@ -223,27 +255,32 @@ RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
 		tx = w->leafdfs[L];
 		if (tx < 0)
 			return;
+		const uint32_t *vis = w->nodevis + (size_t)f->viewleaf[vi] * w->visrowwords;
+		if (!rc_visbit (vis, x))
+			return;
 	}
 	else
+	{
+		if (!(masks[x] & 0x8000))
+			return;
 		tx = w->nodeaux[x].dfs_in;
-	const uint32_t *vis = w->nodevis + (size_t)f->viewleaf[vi] * w->visrowwords;
-	if (!rc_visbit (vis, x))
-		return;
+	}
 	int cur = 0, clipflags = 15, key = 0;
 	for (;;)
 	{
+		const int m = masks[cur];
+		if (m & clipflags & 15)
+			return;				/* an ancestor's box is outside a plane still being tested */
+		clipflags &= ~((m >> 4) & 15);
+		const int side = (m >> 8) & 1;
 		const rc_node_t *nd = &w->nodes[cur];
-		if (!rc_cull_box (v, nd->minmaxs, &clipflags))
-			return;
-		double dot = rc_plane_diff (v->origin, &w->planes[nd->plane]);
-		const int side = (dot < 0);
 		const rc_nodeaux_t aux = w->nodeaux[cur];
 		if (!is_leaf && cur == x)
 		{
 			rc_nodevisit_t *nv = &f->nodevisit[(size_t)vi * w->numnodes + x];
 			nv->clipflags = (int16_t)clipflags;
 			nv->facekey = key + aux.slots[side];
-			nv->state = (int16_t)(dot > RC_BACKFACE_EPSILON ? 1 : (dot < -RC_BACKFACE_EPSILON ? 2 : 3));
+			nv->state = (int16_t)((m >> 9) & 3);
 			return;
 		}
 		const int c = (tx < aux.dfs_mid) ? 0 : 1;
@@ -255,15 +292,29 @@ RC_HD void rc_visit (const rc_world_t *w, const rc_frame_t *f, int vi, int x)
 			const rc_leaf_t *lf = &w->leafs[L];
 			if (!rc_cull_box (v, lf->minmaxs, &clipflags))
 				return;
-			if (f->leafkey)
-				f->leafkey[(size_t)vi * w->numleafs + L] = key;
-			int *facemark = f->facemark + (size_t)vi * w->numfaces;
-			for (int m = 0; m < lf->nummarks; m++)
-				RC_ATOMIC_MIN_I (&facemark[w->marksurfaces[lf->firstmark + m]], key);
+			f->leafkey[(size_t)vi * w->numleafs + L] = key;	/* mleaf_t.key; rc_mark_face stamps the leaf's faces */
+			if (!w->marksplit)
+			{
+				int *facemark = f->facemark + (size_t)vi * w->numfaces;
+				for (int q = 0; q < lf->nummarks; q++)
+					RC_ATOMIC_MIN_I (&facemark[w->marksurfaces[lf->firstmark + q]], key);
+			}
 			return;
 		}
 		cur = child;
 	}
+}
+
+/* One thread per (view, marksurfaces entry): the marking loop of a visited leaf (r_bsp.c:500-512),
+ * taken out of the leaf's thread: a room-sized leaf marks a hundred faces. */
+RC_HD void rc_mark_face (const rc_world_t *w, const rc_frame_t *f, int vi, int m)
+{
+	const int leaf = w->markleaf[m];
+	if (leaf < 0)
+		return;
+	const int key = RC_LDCG (&f->leafkey[(size_t)vi * w->numleafs + leaf]);
+	if (key != 0x7FFFFFFF)
+		RC_ATOMIC_MIN_I (&f->facemark[(size_t)vi * w->numfaces + w->marksurfaces[m]], key);
 }
 
 /* One thread per (view, world face): the face loop of R_RecursiveWorldNode (r_bsp.c:520-549):
@@ -449,99 +500,155 @@ RC_HD void rc_clip_emit (const rc_view_t *vw, const rc_xform_t *xf, const float 
 		r->u = vw->vrectright_adj_shift20;
 }
 
-/* One thread per (view, face-list slot): R_RenderFace, r_rast.c:518-716. */
-RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int *nedges)
+/* R_RenderFace (r_rast.c:518-716) in two steps so that a face's edges can be clipped and projected
+ * by different threads:
+ *   rc_face_edge    one polygon edge: the edge-cache decision (partner face's use of the same medge),
+ *                   R_ClipEdge + R_EmitEdge; everything it would have written to the reference's
+ *                   globals goes into an rc_edgeres_t
+ *   rc_face_fold    folds the edge results in winding order (later edges overwrite r_leftenter & co.
+ *                   exactly as the globals would be), clips the left-clip edge, runs the right-clip
+ *                   nearzi pass and counts the edge records the face emits
+ *   rc_face_emit    writes them at the slot the caller reserved, and the surf_t */
+#define RC_ER_SKIP      1	/* partner cached it as fully clipped: nothing happens */
+#define RC_ER_CACHED    2	/* partner's edge_t carries this surface (R_EmitCachedEdge) */
+#define RC_ER_EMITTED   4
+#define RC_ER_MADE      8	/* an edge_t comes out */
+#define RC_ER_LEFTCLIP  16
+#define RC_ER_RIGHTCLIP 32
+#define RC_ER_LE        64	/* pl is r_leftenter */
+#define RC_ER_LX        128	/* pl is r_leftexit */
+#define RC_ER_RE        256	/* pr is r_rightenter */
+#define RC_ER_RX        512	/* pr is r_rightexit */
+#define RC_ER_REACHED   1024	/* R_EmitEdge ran: nearzi valid */
+typedef struct {
+	int   flags;
+	float nearzi;
+	int   u, u_step;
+	int   vv;		/* v | v2 << 16 */
+	int   surfs;		/* surfs[0] | surfs[1] << 16 */
+	float pl[3], pr[3];	/* crossing point with the left / right clip plane */
+} rc_edgeres_t;			/* 48 B */
+
+RC_HD void rc_face_edge (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int i, rc_edgeres_t *out)
 {
 	const rc_view_t *vw = &f->views[vi];
 	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
 	const uint16_t *facepos = f->facepos + (size_t)vi * w->numfaces;
 	const rc_facerec_t rec = list[p];
 	const rc_face_t *fa = &w->faces[rec.face];
+	const int surfidx = p + 2;
+	rc_clipres_t r;
+	rc_fedge_t fe;
+#ifdef __CUDACC__
+	{
+		const uint4 *q4 = reinterpret_cast<const uint4 *>(&w->fedges[fa->firstedge + i]);
+		const uint4 x = __ldg (q4), y = __ldg (q4 + 1);
+		fe.v0[0] = __uint_as_float (x.x); fe.v0[1] = __uint_as_float (x.y); fe.v0[2] = __uint_as_float (x.z); fe.partner_face = (int)x.w;
+		fe.v1[0] = __uint_as_float (y.x); fe.v1[1] = __uint_as_float (y.y); fe.v1[2] = __uint_as_float (y.z); fe.partner_rev = (int)y.w;
+	}
+#else
+	fe = w->fedges[fa->firstedge + i];
+#endif
+	const float *va = fe.v0, *vb = fe.v1;
+	int q = RC_FACEPOS_NONE;
+	if (fe.partner_face >= 0)
+		q = facepos[fe.partner_face];
+	out->flags = 0; out->nearzi = 0;
+
+	if (q < (int)RC_FACEPOS_MARKED && list[q].key < rec.key)
+	{
+		/* the partner face ran first: redo its R_ClipEdge (same medge, its direction, its
+		 * clipflags) to learn what it left in medge_t.cachededgeoffset (r_rast.c:583-603) */
+		const float *pa = fe.partner_rev ? vb : va, *pb = fe.partner_rev ? va : vb;
+		rc_clip_emit (vw, rc_view_xform (vw), pa, pb, list[q].clipflags, 0, &r);
+		if (r.cls == RC_CLS_FULLCLIP)
+		{
+			out->flags = RC_ER_SKIP;
+			return;
+		}
+		if (r.cls == RC_CLS_CACHED)
+		{
+			/* R_EmitCachedEdge: the partner's edge_t carries this surface */
+			out->flags = RC_ER_CACHED;
+			out->nearzi = r.nearzi;
+			return;
+		}
+	}
+
+	rc_clip_emit (vw, rc_view_xform (vw), va, vb, rec.clipflags, 0, &r);
+	int fl = 0;
+	if (r.have_leftenter) { fl |= RC_ER_LE; out->pl[0] = r.leftenter[0]; out->pl[1] = r.leftenter[1]; out->pl[2] = r.leftenter[2]; }
+	if (r.have_leftexit) { fl |= RC_ER_LX; out->pl[0] = r.leftexit[0]; out->pl[1] = r.leftexit[1]; out->pl[2] = r.leftexit[2]; }
+	if (r.have_rightenter) { fl |= RC_ER_RE; out->pr[0] = r.rightenter[0]; out->pr[1] = r.rightenter[1]; out->pr[2] = r.rightenter[2]; }
+	if (r.have_rightexit) { fl |= RC_ER_RX; out->pr[0] = r.rightexit[0]; out->pr[1] = r.rightexit[1]; out->pr[2] = r.rightexit[2]; }
+	if (r.leftclipped) fl |= RC_ER_LEFTCLIP;
+	if (r.rightclipped) fl |= RC_ER_RIGHTCLIP;
+	if (r.reached_emit) { fl |= RC_ER_REACHED; out->nearzi = r.nearzi; }
+	if (r.emitted) fl |= RC_ER_EMITTED;
+	if (r.made_edge)
+	{
+		int s0 = r.trailing ? surfidx : 0, s1 = r.trailing ? 0 : surfidx;
+		fl |= RC_ER_MADE;
+		if (r.cls == RC_CLS_CACHED && q < (int)RC_FACEPOS_MARKED && list[q].key > rec.key)
+		{
+			/* the partner will find this edge cached and add itself (R_EmitCachedEdge) */
+			if (r.trailing) s1 = q + 2;
+			else s0 = q + 2;
+		}
+		out->u = r.u; out->u_step = r.u_step;
+		out->vv = (int)(((uint32_t)(uint16_t)(int16_t)r.v) | ((uint32_t)(uint16_t)(int16_t)r.v2 << 16));
+		out->surfs = (int)((uint32_t)s0 | ((uint32_t)s1 << 16));
+		if (r.trailing) fl |= (int)0x80000000;
+	}
+	out->flags = fl;
+}
+
+typedef struct {		/* what rc_face_fold hands to rc_face_emit */
+	int   neb;		/* edge_t records the face emits */
+	int   emitted;
+	int   haveleftedge, lu, lu_step, lv, lv2, ltrailing;	/* the left-clip edge (r_rast.c:661-666) */
+	float nearzi;
+} rc_facefold_t;
+
+RC_HD void rc_face_fold (const rc_world_t *w, const rc_frame_t *f, int vi, int p, const rc_edgeres_t *res, rc_facefold_t *st)
+{
+	const rc_view_t *vw = &f->views[vi];
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	const rc_facerec_t rec = list[p];
+	const rc_face_t *fa = &w->faces[rec.face];
 	rc_surf_t *surf = f->surfs + (size_t)vi * f->surfcap + (p + 2);
 	const int clipflags = rec.clipflags;
-	const int surfidx = p + 2;
-
-	rc_edge_t eb[RC_MAX_FACE_EDGES + 1];
-	int neb = 0;
-	int emitted = 0, makeleft = 0, makeright = 0;
+	const int ne = fa->numedges;
+	int emitted = 0, makeleft = 0, makeright = 0, neb = 0;
 	float nearzi = 0;
 	float leftenter[3] = {0,0,0}, leftexit[3] = {0,0,0}, rightenter[3] = {0,0,0}, rightexit[3] = {0,0,0};
 	int have_le = 0, have_lx = 0, have_re = 0, have_rx = 0;
 	rc_clipres_t r;
 
-	surf->flags = -1;		/* not posted unless an edge comes out */
-	surf->hasspans = 0;
-	if (fa->numedges > RC_MAX_FACE_EDGES)
+	for (int i = 0; i < ne; i++)
 	{
-		RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
-		return;
-	}
-
-	for (int i = 0; i < fa->numedges; i++)
-	{
-		rc_fedge_t fe;
-#ifdef __CUDACC__
+		const rc_edgeres_t *e = &res[i];
+		const int fl = e->flags;
+		if (fl & RC_ER_SKIP)
+			continue;
+		if (fl & RC_ER_CACHED)
 		{
-			const uint4 *q4 = reinterpret_cast<const uint4 *>(&w->fedges[fa->firstedge + i]);
-			const uint4 x = __ldg (q4), y = __ldg (q4 + 1);
-			fe.v0[0] = __uint_as_float (x.x); fe.v0[1] = __uint_as_float (x.y); fe.v0[2] = __uint_as_float (x.z); fe.partner_face = (int)x.w;
-			fe.v1[0] = __uint_as_float (y.x); fe.v1[1] = __uint_as_float (y.y); fe.v1[2] = __uint_as_float (y.z); fe.partner_rev = (int)y.w;
-		}
-#else
-		fe = w->fedges[fa->firstedge + i];
-#endif
-		const float *va = fe.v0, *vb = fe.v1;
-		int q = RC_FACEPOS_NONE;
-		if (fe.partner_face >= 0)
-			q = facepos[fe.partner_face];
-
-		if (q < (int)RC_FACEPOS_MARKED && list[q].key < rec.key)
-		{
-			/* the partner face ran first: redo its R_ClipEdge (same medge, its direction, its
-			 * clipflags) to learn what it left in medge_t.cachededgeoffset (r_rast.c:583-603) */
-			const float *pa = fe.partner_rev ? vb : va, *pb = fe.partner_rev ? va : vb;
-			rc_clip_emit (vw, rc_view_xform (vw), pa, pb, list[q].clipflags, 0, &r);
-			if (r.cls == RC_CLS_FULLCLIP)
-				continue;
-			if (r.cls == RC_CLS_CACHED)
-			{
-				/* R_EmitCachedEdge: the partner's edge_t carries this surface */
-				if (r.nearzi > nearzi)
-					nearzi = r.nearzi;
-				emitted = 1;
-				continue;
-			}
-		}
-
-		rc_clip_emit (vw, rc_view_xform (vw), va, vb, clipflags, 0, &r);
-		if (r.have_leftenter) { have_le = 1; leftenter[0] = r.leftenter[0]; leftenter[1] = r.leftenter[1]; leftenter[2] = r.leftenter[2]; }
-		if (r.have_leftexit) { have_lx = 1; leftexit[0] = r.leftexit[0]; leftexit[1] = r.leftexit[1]; leftexit[2] = r.leftexit[2]; }
-		if (r.have_rightenter) { have_re = 1; rightenter[0] = r.rightenter[0]; rightenter[1] = r.rightenter[1]; rightenter[2] = r.rightenter[2]; }
-		if (r.have_rightexit) { have_rx = 1; rightexit[0] = r.rightexit[0]; rightexit[1] = r.rightexit[1]; rightexit[2] = r.rightexit[2]; }
-		if (r.leftclipped) makeleft = 1;
-		if (r.rightclipped) makeright = 1;
-		if (r.reached_emit && r.nearzi > nearzi)
-			nearzi = r.nearzi;
-		if (r.emitted)
+			if (e->nearzi > nearzi) nearzi = e->nearzi;
 			emitted = 1;
-		if (r.made_edge)
-		{
-			rc_edge_t *e = &eb[neb++];
-			e->u = r.u; e->u_step = r.u_step;
-			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
-			e->surfs[0] = r.trailing ? surfidx : 0;
-			e->surfs[1] = r.trailing ? 0 : surfidx;
-			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)rec.key << 5) | (uint32_t)i;
-			e->pad[0] = e->pad[1] = e->pad[2] = 0;
-			if (r.cls == RC_CLS_CACHED && q < (int)RC_FACEPOS_MARKED && list[q].key > rec.key)
-			{
-				/* the partner will find this edge cached and add itself (R_EmitCachedEdge) */
-				if (r.trailing) e->surfs[1] = (uint16_t)(q + 2);
-				else e->surfs[0] = (uint16_t)(q + 2);
-			}
+			continue;
 		}
+		if (fl & RC_ER_LE) { have_le = 1; leftenter[0] = e->pl[0]; leftenter[1] = e->pl[1]; leftenter[2] = e->pl[2]; }
+		if (fl & RC_ER_LX) { have_lx = 1; leftexit[0] = e->pl[0]; leftexit[1] = e->pl[1]; leftexit[2] = e->pl[2]; }
+		if (fl & RC_ER_RE) { have_re = 1; rightenter[0] = e->pr[0]; rightenter[1] = e->pr[1]; rightenter[2] = e->pr[2]; }
+		if (fl & RC_ER_RX) { have_rx = 1; rightexit[0] = e->pr[0]; rightexit[1] = e->pr[1]; rightexit[2] = e->pr[2]; }
+		if (fl & RC_ER_LEFTCLIP) makeleft = 1;
+		if (fl & RC_ER_RIGHTCLIP) makeright = 1;
+		if ((fl & RC_ER_REACHED) && e->nearzi > nearzi) nearzi = e->nearzi;
+		if (fl & RC_ER_EMITTED) emitted = 1;
+		if (fl & RC_ER_MADE) neb++;
 	}
 
+	st->haveleftedge = 0;
 	if (makeleft)
 	{
 		/* r_rast.c:661-666: R_ClipEdge (&r_leftexit, &r_leftenter, pclip->next) */
@@ -559,15 +666,13 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 			emitted = 1;
 		if (r.made_edge)
 		{
-			rc_edge_t *e = &eb[neb++];
-			e->u = r.u; e->u_step = r.u_step;
-			e->v = (int16_t)r.v; e->v2 = (int16_t)r.v2;
-			e->surfs[0] = r.trailing ? surfidx : 0;
-			e->surfs[1] = r.trailing ? 0 : surfidx;
-			e->rank = ((uint32_t)r.trailing << 31) | ((uint32_t)rec.key << 5) | 31u;
-			e->pad[0] = e->pad[1] = e->pad[2] = 0;
+			st->haveleftedge = 1;
+			st->lu = r.u; st->lu_step = r.u_step; st->lv = r.v; st->lv2 = r.v2; st->ltrailing = r.trailing;
+			neb++;
 		}
 	}
+	surf->flags = -1;		/* not posted unless an edge comes out */
+	surf->hasspans = 0;
 	/* r_rightenter / r_rightexit are globals in the reference: a face whose own edges wrote
 	 * only one of them (the other crossing edge was skipped as FULLY_CLIPPED_CACHED) reads the
 	 * value an EARLIER face left behind.  Publish what this face wrote; rc_face_fixup resolves
@@ -587,20 +692,51 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 		else
 			surf->miplevel |= 4;
 	}
+	st->neb = neb; st->emitted = emitted; st->nearzi = nearzi;
+}
 
-	if (neb)
+/* `base`: the face's first slot in the view's edge array (the caller reserved st->neb records) */
+RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p, const rc_edgeres_t *res, const rc_facefold_t *st, int base)
+{
+	const rc_view_t *vw = &f->views[vi];
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	const rc_facerec_t rec = list[p];
+	const rc_face_t *fa = &w->faces[rec.face];
+	rc_surf_t *surf = f->surfs + (size_t)vi * f->surfcap + (p + 2);
+	const int surfidx = p + 2;
+	const int ne = fa->numedges;
+	if (st->neb)
 	{
-		int base = RC_ATOMIC_ADD_I (nedges, neb);
-		if (base + neb > f->edgecap)
+		if (base + st->neb > f->edgecap)
 			RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
 		else
 		{
 			rc_edge_t *dst = f->edges + (size_t)vi * f->edgecap + base;
-			for (int i = 0; i < neb; i++)
-				dst[i] = eb[i];
+			for (int i = 0; i < ne; i++)
+			{
+				const rc_edgeres_t *e = &res[i];
+				if ((e->flags & (RC_ER_SKIP | RC_ER_CACHED)) || !(e->flags & RC_ER_MADE))
+					continue;
+				const uint32_t trailing = (uint32_t)e->flags >> 31;
+				dst->u = e->u; dst->u_step = e->u_step;
+				dst->v = (int16_t)(e->vv & 0xFFFF); dst->v2 = (int16_t)((uint32_t)e->vv >> 16);
+				dst->surfs[0] = (uint16_t)(e->surfs & 0xFFFF); dst->surfs[1] = (uint16_t)((uint32_t)e->surfs >> 16);
+				dst->rank = (trailing << 31) | ((uint32_t)rec.key << 5) | (uint32_t)i;
+				dst->pad[0] = dst->pad[1] = dst->pad[2] = 0;
+				dst++;
+			}
+			if (st->haveleftedge)
+			{
+				dst->u = st->lu; dst->u_step = st->lu_step;
+				dst->v = (int16_t)st->lv; dst->v2 = (int16_t)st->lv2;
+				dst->surfs[0] = st->ltrailing ? surfidx : 0;
+				dst->surfs[1] = st->ltrailing ? 0 : surfidx;
+				dst->rank = ((uint32_t)st->ltrailing << 31) | ((uint32_t)rec.key << 5) | 31u;
+				dst->pad[0] = dst->pad[1] = dst->pad[2] = 0;
+			}
 		}
 	}
-	if (!emitted)
+	if (!st->emitted)
 		return;
 
 	/* r_rast.c:693-714 */
@@ -613,15 +749,33 @@ RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int
 	surf->face = rec.face;
 	surf->insubmodel = 0;
 	surf->entity = -1;
-	surf->nearzi = nearzi;
+	surf->nearzi = st->nearzi;
 	surf->d_zistepu = p_normal[0] * vw->xscaleinv * distinv;
 	surf->d_zistepv = -p_normal[1] * vw->yscaleinv * distinv;
 	surf->d_ziorigin = p_normal[2] * distinv - vw->xcenter * surf->d_zistepu - vw->ycenter * surf->d_zistepv;
 }
 
-/* One thread per (view, face-list slot), after rc_render_face: faces that must read an
- * r_rightenter / r_rightexit written by an earlier face (see above) walk the list backwards
- * for the most recent writer, then run the r_nearzionly clip of r_rast.c:669-675. */
+/* One thread per (view, face-list slot): both steps serially (host simulation). */
+RC_HD void rc_render_face (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int *nedges)
+{
+	const rc_facerec_t *list = f->facelist + (size_t)vi * f->facecap;
+	const rc_face_t *fa = &w->faces[list[p].face];
+	rc_surf_t *surf = f->surfs + (size_t)vi * f->surfcap + (p + 2);
+	rc_edgeres_t res[RC_MAX_FACE_EDGES];
+	if (fa->numedges > RC_MAX_FACE_EDGES)
+	{
+		surf->flags = -1;
+		surf->hasspans = 0;
+		RC_ATOMIC_OR_I (f->status, RC_STAT_EDGE_OVERFLOW);
+		return;
+	}
+	for (int i = 0; i < fa->numedges; i++)
+		rc_face_edge (w, f, vi, p, i, &res[i]);
+	rc_facefold_t st;
+	rc_face_fold (w, f, vi, p, res, &st);
+	rc_face_emit (w, f, vi, p, res, &st, st.neb ? RC_ATOMIC_ADD_I (nedges, st.neb) : 0);
+}
+
 /* second half of the fixup: best_re / best_rx = list slots of the latest earlier writers (-1: none) */
 RC_HD void rc_face_fixup_finish (const rc_world_t *w, const rc_frame_t *f, int vi, int p, int best_re, int best_rx)
 {

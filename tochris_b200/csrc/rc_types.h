@@ -127,7 +127,7 @@ typedef struct {            /* device-resident world; all pointers are device po
         numvertexes, numtexinfo, numtextures, nummarksurfaces, visleafs, haslight;
     int numworldfaces;      /* faces of model 0 (without skybox faces) */
     int skytexofs;          /* texel offset of the 256x128 sky texture R_InitSky copied last (r_sky.c:53), -1: none */
-    int pad0;
+    int marksplit;          /* 1: markleaf[] is valid (no two leaves share a marksurfaces entry) */
     int visrowwords;        /* words per row of nodevis */
     const rc_plane_t     *planes;
     const rc_node_t      *nodes;
@@ -143,6 +143,7 @@ typedef struct {            /* device-resident world; all pointers are device po
     const uint8_t        *texels;      /* all miptex pixel data */
     const uint8_t        *lightdata;
     const int            *marksurfaces;
+    const int            *markleaf;    /* [nummarksurfaces]: the leaf that owns each entry, -1: none */
     const uint32_t       *nodevis;     /* [numleafs][visrowwords]: bit i<numnodes: node i, else leaf */
     const uint8_t        *colormap;    /* vid.colormap, 64*256 */
     const int            *sintable;    /* r_rast.c:45, SIN_BUFFER_SIZE ints */
