@@ -14,7 +14,7 @@ import numpy as np
 from .refdef import refdef_t
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libref_cuda.so")
+LIBPATH = os.environ.get("RC_LIBPATH") or os.path.join(HERE, "libref_cuda.so")   # RC_LIBPATH: kernel-variant experiments
 
 RC_STAT = {1: "EDGE_OVERFLOW", 2: "SURF_OVERFLOW", 4: "SPAN_POOL", 8: "AET_OVERFLOW", 16: "STACK_OVERFLOW",
            32: "CACHE_POOL", 64: "STALE_CLIPVERT", 128: "FACELIST"}

@@ -856,7 +856,10 @@ __global__ void k_spanseg (const __grid_constant__ rc_world_t w, const __grid_co
 /* Draw stage: first one thread per screen-aligned 8-pixel cell of every row (full cells: one
  * 8-byte colour store + one 16-byte z store, both aligned and coalesced across the warp), then
  * one thread per span head.  Rows = views x height. */
-__global__ void __launch_bounds__(128) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+#ifndef DRAW_MINB
+#define DRAW_MINB 8	/* 64 registers: 32 warps per SM hide the dependent cell -> span -> texel loads (measured: 8 > 9 > 10 > 7) */
+#endif
+__global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	const unsigned cw = (unsigned)((f.width + 7) >> 3);
 	const unsigned ncells = (unsigned)(f.drawview1 * f.height) * cw;
