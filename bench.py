@@ -151,6 +151,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    from tochris_b200 import shard
     from tochris_b200.api import RefCuda, status_names
     from tochris_b200.scenes.views import build_refdefs
 
@@ -184,7 +185,7 @@ def run_ours(args):
             timed_events[0].record(stream)
         st = r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
         if world > 1:
-            dist.gather(fb, gather, dst=0)
+            shard.gather_frames(fb, n * world, rank, world, dst=0, bufs=gather, concat=False)
         if timed_events is not None:
             timed_events[1].record(stream)
         return st
@@ -259,9 +260,20 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    draw_ms = prof["ms_draw"] / args.steps
+    # the dominant kernel: k_draw alone (ms_draw brackets k_spanseg + k_draw, ms_spanseg the first of the two)
+    draw_ms = (prof["ms_draw"] - prof.get("ms_spanseg", 0.0)) / args.steps
     alg_bytes = 4.0 * px                      # 1 B texel + 1 B colour + 2 B z per pixel
     achieved = alg_bytes / (draw_ms * 1e-3) / 1e9 if draw_ms > 0 else 0.0
+    traffic, traffic_src = None, None         # DRAM bytes per launch of k_draw from the newest committed ncu --set full capture
+    try:
+        pdir = os.path.join(ROOT, "profiles")
+        for fn in sorted(f for f in os.listdir(pdir) if f.endswith("_ncu_summary.json")):
+            for l in json.load(open(os.path.join(pdir, fn)))["launches"]:
+                if l.get("kernel") == "k_draw" and (W, H, n) == (640, 480, 64):
+                    traffic = int((l["dram_read_mb"] + l["dram_write_mb"]) * 1e6)
+                    traffic_src = f"profiles/{fn}"
+    except Exception:  # noqa: BLE001
+        pass
     out = {
         "metric": "frames/s, batched ref_soft views (pixel-exact 8-bit framebuffer + int16 z-buffer)",
         "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -281,7 +293,7 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "status": status_names(status),
         "roofline": {"bound": "hbm", "kernel": "k_draw (span texture mapping + z-buffer)", "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "alg_bytes_per_launch": int(alg_bytes), "kernel_ms": round(draw_ms, 4),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
         "kernel_ms_per_step": {k[3:]: round(v / args.steps, 4) for k, v in prof.items() if k.startswith("ms_") and k not in ("ms_h2d", "ms_d2h")},
