@@ -78,7 +78,7 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
-	cudaStream_t copystream; cudaEvent_t evgroup[8], evcopy;
+	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
@@ -981,6 +981,9 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaStreamCreateWithFlags (&g->copystream, cudaStreamNonBlocking);
 	for (int i = 0; i < 8; i++) cudaEventCreateWithFlags (&g->evgroup[i], cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evcopy, cudaEventDisableTiming);
+	cudaStreamCreateWithFlags (&g->sidestream, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
 	g->host_fb = NULL; g->host_z = NULL;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
 
@@ -1266,10 +1269,24 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[4], s);
-	k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
-	if (timed) cudaEventRecord (g->ev[5], s);
-	k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
-	if (timed) cudaEventRecord (g->ev[7], s);
+	if (timed)
+	{
+		k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
+		cudaEventRecord (g->ev[5], s);
+		k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
+		cudaEventRecord (g->ev[7], s);
+	}
+	else
+	{
+		/* the surface-cache build and the span-segment kernel only depend on the prep kernel: they run
+		 * side by side (second stream forked and joined with events) */
+		cudaEventRecord (g->evfork, s);
+		cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
+		k_spanseg<<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
+		cudaEventRecord (g->evjoin, g->sidestream);
+		k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
+		cudaStreamWaitEvent (s, g->evjoin, 0);
+	}
 	const bool entities = g->cur_batch && g->cur_batch->nzres;
 	bool grouped = false;
 	if (g->host_fb && !entities && !anywarp && n >= 8)
