@@ -859,6 +859,7 @@ __global__ void k_spanseg (const __grid_constant__ rc_world_t w, const __grid_co
 #ifndef DRAW_MINB
 #define DRAW_MINB 8	/* 64 registers: 32 warps per SM hide the dependent cell -> span -> texel loads (measured: 8 > 9 > 10 > 7) */
 #endif
+template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	const unsigned cw = (unsigned)((f.width + 7) >> 3);
@@ -867,6 +868,9 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 	/* cell -> span -> (surface, boundaries) -> texels is a chain of dependent loads: the first two
 	 * levels of the next grid-stride iterations are fetched while the current cell is drawn */
 	unsigned t0 = (unsigned)(f.drawview0 * f.height) * cw + blockIdx.x * blockDim.x + threadIdx.x, t1 = t0 + stride;
+	/* the cell's column inside its row, kept incrementally (no divide per item) */
+	const unsigned cstep = stride % cw;
+	unsigned c0 = t0 % cw;
 	int si0 = t0 < ncells ? __ldg (&f.cellspan[t0]) : -1;
 	int si1 = t1 < ncells ? __ldg (&f.cellspan[t1]) : -1;
 	rc_span_t sp0 = rc_load_span (&f.spans[si0 < 0 ? 0 : si0]);
@@ -877,13 +881,14 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 		const rc_span_t sp1 = rc_load_span (&f.spans[si1 < 0 ? 0 : si1]);
 		if (si0 >= 0)
 		{
-			const unsigned row = t0 / cw;
-			const int rel = (int)((t0 - row * cw) << 3) - sp0.u;
+			const int rel = (int)(c0 << 3) - sp0.u;
 			int cnt = sp0.count - rel;
 			if (cnt > 8) cnt = 8;
-			rc_draw_pixels (&w, &f, si0, sp0, rel, cnt);
+			rc_draw_pixels (&w, &f, si0, sp0, rel, cnt, WARPVIEWS);
 		}
 		t0 = t1; t1 = t2; si0 = si1; si1 = si2; sp0 = sp1;
+		c0 += cstep;
+		if (c0 >= cw) c0 -= cw;
 	}
 	unsigned long long a = f.alloc[0];
 	unsigned nspans = (unsigned)(a & 0xFFFFFFFFu);
@@ -897,7 +902,7 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 			if (v < f.drawview0 || v >= f.drawview1)
 				continue;
 		}
-		rc_draw_head (&w, &f, (int)t);
+		rc_draw_head (&w, &f, (int)t, WARPVIEWS);
 	}
 }
 
@@ -1303,7 +1308,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			const int nv = f.drawview1 - f.drawview0;
 			int ctas = (int)(((size_t)nv * g->height * ((g->width + 7) / 8) + 127) / 128);
 			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
-			k_draw<<<ctas, 128, 0, s>>> (w, f);
+			k_draw<false><<<ctas, 128, 0, s>>> (w, f);
 			cudaEventRecord (g->evgroup[gi], s);
 			cudaStreamWaitEvent (g->copystream, g->evgroup[gi], 0);
 			const size_t ofs = px * (size_t)(first_view + f.drawview0);
@@ -1318,7 +1323,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	else
 	{
 		f.drawview0 = 0; f.drawview1 = n;
-		k_draw<<<g->numsms * 16, 128, 0, s>>> (w, f);
+		if (anywarp) k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f);
+		else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
 	}
 	if (g->cur_batch && g->cur_batch->nzres)
 	{

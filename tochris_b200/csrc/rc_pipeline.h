@@ -62,7 +62,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
 #define RC_WARP_W          320       /* WARP_WIDTH / WARP_HEIGHT, d_iface.h:22-23 */
 #define RC_WARP_H          200
-#define RC_SEG_BND         10        /* boundaries 8s .. 8s+9 of a span are stored with segment s */
+#define RC_SEG_BND         12        /* entries 8s .. 8s+11 of a span's boundary table are stored with segment s */
 
 /* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
 typedef struct {
@@ -1871,6 +1871,9 @@ RC_HD void rc_boundary_st (const rc_surf_t *s, float sdivz, float tdivz, float z
  *        b = 0              span start, clamped to [0, bbextent]
  *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
  *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
+ *        b = nsub + 1       not a boundary: the (s, t) step of the last subdivision,
+ *                           (B[nsub] - B[nsub-1]) / (left - 1) truncated (d_scan.c:364-365), so that the
+ *                           draw kernel never divides
  *   span.izi0 / span.izistep (segment 0 only)
  * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
  * adds: the segment replays the cheap adds from the span start and does the divide / convert /
@@ -1972,8 +1975,24 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 		if (tt > bbextentt) tt = bbextentt; else if (tt < lo) tt = lo;
 		st[2 * i] = ss; st[2 * i + 1] = tt;
 	}
-	/* boundaries past the span's last one are never read: the whole 80-byte record is written with
-	 * five 16-byte stores */
+	{
+		/* entry nsub+1: the last subdivision's step.  Only segments where it lands at i >= 2 are ever
+		 * asked for it (an item reads entries (k&7) .. (k&7)+3 of segment k>>3, k <= nsub-1) */
+		const int it = nsub + 1 - (sidx << 3);
+		const int lastn = count - ((nsub - 1) << 3);		/* pixels of the last subdivision */
+		int ds_ = 0, dt_ = 0;
+		#pragma unroll
+		for (int i = 2; i < RC_SEG_BND; i++)
+			if (i == it) { ds_ = st[2*i - 2] - st[2*i - 4]; dt_ = st[2*i - 1] - st[2*i - 3]; }
+		if (it >= 2 && it < RC_SEG_BND)
+		{
+			const int sstep = lastn > 1 ? ds_ / (lastn - 1) : 0, tstep = lastn > 1 ? dt_ / (lastn - 1) : 0;
+			#pragma unroll
+			for (int i = 2; i < RC_SEG_BND; i++)
+				if (i == it) { st[2*i] = sstep; st[2*i + 1] = tstep; }
+		}
+	}
+	/* entries past nsub+1 are never read: the whole 96-byte record is written with six 16-byte stores */
 #ifdef __CUDACC__
 	#pragma unroll
 	for (int i = 0; i < RC_SEG_BND / 2; i++)
@@ -1981,26 +2000,6 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 #else
 	for (int i = 0; i < RC_SEG_BND * 2; i++)
 		out[i] = st[i];
-#endif
-}
-
-/* truncating division by d = 1..7 (the last-subdivision step, d_scan.c:364-365) as a multiply by
- * ceil(2^32 / d): exact for |a| < 2^24 (7 * 2^24 < 2^32), which covers every cached surface
- * (extents <= 256 texels in 16.16); larger differences (turbulent surfaces) take the divide. */
-#ifdef __CUDACC__
-static __device__ __constant__ unsigned rc_divmagic[8] = {	/* ceil(2^32 / d), d = 2..7 (0, 1 unused) */
-	0u, 0u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2AAAAAABu, 0x24924925u };
-#endif
-RC_HD int rc_div_small (int a, int d)
-{
-#ifdef __CUDACC__
-	if (a >= (1 << 24) || a <= -(1 << 24))
-		return a / d;
-	const unsigned mag = (unsigned)(a < 0 ? -a : a);
-	const int q = d == 1 ? (int)mag : (int)__umulhi (mag, rc_divmagic[d & 7]);
-	return a < 0 ? -q : q;
-#else
-	return a / d;
 #endif
 }
 
@@ -2013,17 +2012,16 @@ RC_HD int rc_div_small (int a, int d)
  * The reference's 8-pixel subdivision is span relative, so the item touches subdivision
  * k = rel >> 3 from pixel a = rel & 7 on, and subdivision k+1 when a + cnt > 8.  Everything is
  * computed for 8 pixels and predicated on j < cnt: no per-count code paths. */
-RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, const rc_span_t sp, int rel, int cnt)
+RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, const rc_span_t sp, int rel, int cnt, const bool warpviews)
 {
 	const rc_drawsurf_t ds = rc_load_drawsurf (f->surfs + sp.gsurf);
 	const int srckind = ds.srckind;
 	const int pix = sp.pixofs + rel;
-	uint8_t *pdest;
 	const rc_view_t *vw = &f->views[sp.view];		/* only dereferenced on the rare paths */
-	if (!(sp.flags & 1))
-		pdest = f->fb + pix;
-	else
+	uint8_t *pdest = f->fb + pix;
+	if (warpviews && (sp.flags & 1))		/* under water: the view's 320x200 warp buffer (the kernel variant without such views drops this) */
 		pdest = f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H) + RC_WARP_W * sp.v + sp.u + rel;
+	const unsigned vmask = 0xFFu >> (8 - cnt);		/* bit j: pixel j belongs to the item */
 
 	/* ---- z (D_DrawZSpans) ---- */
 	if (f->zb)
@@ -2066,7 +2064,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 		{
 			#pragma unroll
 			for (int j = 0; j < 8; j++)
-				if (j < cnt)
+				if (vmask & (1u << j))
 					pz[j] = (int16_t)zs[j];
 		}
 	}
@@ -2136,9 +2134,12 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 		const int *bp = f->bnd + ((size_t)(sp.segbase + (k >> 3)) * RC_SEG_BND + (k & 7)) * 2;
 		const int left = sp.count - (k << 3);	/* pixels from the start of subdivision k to the end of the span */
 		const int two = a + cnt > 8;		/* the item runs on into subdivision k+1 */
-		int s0, t0, s1, t1, s2 = 0, t2 = 0, sstep0, tstep0, sstep1 = 0, tstep1 = 0;
+		/* bp[0..1] = B[k], bp[2..3] = B[k+1], bp[4..5] = B[k+2] -- or, when k is the last subdivision, its
+		 * precomputed step; bp[6..7] = the step of k+1 when that one is the last */
+		int s0, t0, s1, t1, s2 = 0, t2 = 0, s3 = 0, t3 = 0, sstep0, tstep0, sstep1 = 0, tstep1 = 0;
 		s0 = RC_LDG (&bp[0]); t0 = RC_LDG (&bp[1]); s1 = RC_LDG (&bp[2]); t1 = RC_LDG (&bp[3]);
-		if (two) { s2 = RC_LDG (&bp[4]); t2 = RC_LDG (&bp[5]); }
+		if (two || left <= 8) { s2 = RC_LDG (&bp[4]); t2 = RC_LDG (&bp[5]); }
+		if (two && left <= 16) { s3 = RC_LDG (&bp[6]); t3 = RC_LDG (&bp[7]); }
 		if (left > 8)
 		{
 			sstep0 = (s1 - s0) >> 3;
@@ -2148,16 +2149,16 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 				sstep1 = (s2 - s1) >> 3;
 				tstep1 = (t2 - t1) >> 3;
 			}
-			else if (two && left > 9)
+			else
 			{
-				sstep1 = rc_div_small (s2 - s1, left - 9);
-				tstep1 = rc_div_small (t2 - t1, left - 9);
+				sstep1 = s3;
+				tstep1 = t3;
 			}
 		}
 		else
 		{
-			sstep0 = left > 1 ? rc_div_small (s1 - s0, left - 1) : 0;
-			tstep0 = left > 1 ? rc_div_small (t1 - t0, left - 1) : 0;
+			sstep0 = s2;
+			tstep0 = t2;
 		}
 		int ss = rc_addw (s0, rc_mulw (a, sstep0)), tt = rc_addw (t0, rc_mulw (a, tstep0));
 		const int *turbtab = w->sintable;
@@ -2171,7 +2172,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 				ss = s1; tt = t1; sstep0 = sstep1; tstep0 = tstep1;
 			}
 			px[j] = 0;
-			if (j < cnt)
+			if (vmask & (1u << j))
 			{
 				if (!turb)
 					px[j] = RC_LDG (&pbase[(ss >> 16) + (tt >> 16) * cachewidth]);
@@ -2198,7 +2199,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 	{
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
-			if (j < cnt)
+			if (vmask & (1u << j))
 				pdest[j] = (uint8_t)px[j];
 	}
 }
@@ -2214,17 +2215,17 @@ RC_HD void rc_draw_cell (const rc_world_t *w, const rc_frame_t *f, int row, int 
 	const int rel = (c << 3) - sp.u;
 	int cnt = sp.count - rel;
 	if (cnt > 8) cnt = 8;
-	rc_draw_pixels (w, f, si, sp, rel, cnt);
+	rc_draw_pixels (w, f, si, sp, rel, cnt, true);
 }
 
-RC_HD void rc_draw_head (const rc_world_t *w, const rc_frame_t *f, int si)
+RC_HD void rc_draw_head (const rc_world_t *w, const rc_frame_t *f, int si, const bool warpviews = true)
 {
 	const rc_span_t sp = rc_load_span (&f->spans[si]);
 	int cnt = 8 - (sp.u & 7);
 	if (cnt == 8 || sp.count <= 0)
 		return;
 	if (cnt > sp.count) cnt = sp.count;
-	rc_draw_pixels (w, f, si, sp, 0, cnt);
+	rc_draw_pixels (w, f, si, sp, 0, cnt, warpviews);
 }
 
 
