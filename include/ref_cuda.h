@@ -133,6 +133,13 @@ int  RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_o
  * (a cudaStream_t, 0 = legacy default) and is complete when the stream reaches this point. */
 int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status);
 
+/* The `loadsky <name>` command / r_skyname cvar (ref_soft/r_main.c:169-177, r_sky.c:138-194):
+ * loads <basedir>/id1/env/<name>{rt,bk,lf,ft,up,dn}.pcx (six 256x256 8-bit PCX pictures); from then on
+ * sky surfaces make the renderer draw the six faces of a box around the viewer instead of the
+ * scrolling sky (R_EmitSkyBox, r_rast.c:165-205).  name NULL or "" switches it off.  Returns RC_OK,
+ * or RC_ERR_FILE / RC_ERR_FORMAT and leaves the sky box off (the reference prints and does the same). */
+int  RC_SetSkybox (const char *name);
+
 /* Drops every cached surface block (D_FlushCaches, d_surf.c:101). */
 void RC_FlushCaches (void);
 

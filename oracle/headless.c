@@ -225,6 +225,15 @@ int orc_set_cvar (const char *name, float value)
 	return 0;
 }
 
+/* string cvars (r_skyname: its change callback loads the sky box, r_sky.c:189-194) */
+int orc_set_cvar_string (const char *name, const char *value)
+{
+	cvar_t *v = Cvar_FindVar ((char *)name);
+	if (!v) return -1;
+	Cvar_Set (v, (char *)value);
+	return 0;
+}
+
 void *orc_model (const char *name)
 {
 	model_t *m;

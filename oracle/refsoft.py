@@ -48,6 +48,7 @@ class RefSoft:
         L.orc_model.restype = C.c_void_p
         L.orc_load_world.restype = C.c_void_p
         L.orc_set_cvar.argtypes = [C.c_char_p, C.c_float]
+        L.orc_set_cvar_string.argtypes = [C.c_char_p, C.c_char_p]
         L.orc_render.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.c_void_p]
         L.orc_render_batch.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         self.width, self.height = width, height
@@ -69,8 +70,11 @@ class RefSoft:
             raise RuntimeError("orc_model: " + self.err())
         return p
 
-    def set_cvar(self, name: str, value: float):
-        if self.lib.orc_set_cvar(name.encode(), value) != 0:
+    def set_cvar(self, name: str, value):
+        if isinstance(value, str):
+            if self.lib.orc_set_cvar_string(name.encode(), value.encode()) != 0:
+                raise KeyError(name)
+        elif self.lib.orc_set_cvar(name.encode(), value) != 0:
             raise KeyError(name)
 
     def struct_sizes(self):

@@ -20,8 +20,12 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         import ctypes as C
         r = RefSoft(basedir, width, height, heap_mb=96)
         for k, v in (cvars or {}).items():
-            r.set_cvar(k, v)
+            if not isinstance(v, str):
+                r.set_cvar(k, v)
         r.load_world(mapname)
+        for k, v in (cvars or {}).items():
+            if isinstance(v, str):
+                r.set_cvar(k, v)            # r_skyname: loads the pictures (needs the file system up)
         cm = C.addressof(C.c_char.in_dll(r.lib, "vid")) + 8     # vid.colormap (client/vid.h:36: after `byte *buffer`)
         rds = build_refdefs(specs, width, height, model_resolver=r.model, colormap_ptr=cm)
         out = {}

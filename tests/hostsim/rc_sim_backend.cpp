@@ -19,6 +19,7 @@ struct rc_gpu_s {
 	int width, height;
 	rc_world_t w;
 	bool haveworld;
+	int skybox = 0;
 	int maxedges, maxsurfs;
 	std::vector<int> sintable, intsintable;
 	std::vector<unsigned long long> cachekeys;
@@ -63,6 +64,7 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	g->w = hw->w;
 	g->w.sintable = g->sintable.data ();
 	g->w.intsintable = g->intsintable.data ();
+	g->w.drawskybox = g->skybox;
 	g->haveworld = true;
 	g->maxedges = maxedges; g->maxsurfs = maxsurfs;
 	rc_gpu_flush_caches (g);
@@ -97,7 +99,16 @@ int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const floa
 void rc_gpu_flush_caches (rc_gpu_t *g)
 {
 	std::fill (g->cachekeys.begin (), g->cachekeys.end (), RC_CACHE_EMPTY);
-	g->alloc[1] = 0;
+	g->alloc[1] = RC_SKYBOX_BYTES;		/* the pool starts after the sky-box pictures */
+}
+
+int rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen)
+{
+	(void)err; (void)errlen;
+	if (pixels) memcpy (g->cachepool.data (), pixels, RC_SKYBOX_BYTES);
+	g->skybox = pixels != NULL;
+	g->w.drawskybox = g->skybox;
+	return RC_OK;
 }
 
 int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
@@ -112,8 +123,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	memset (&f, 0, sizeof(f));
 	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views; f.dlights = batch->dlights; f.viewbase = 0;
-	f.facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
-	if (f.facecap < 1) f.facecap = 1;
+	f.facecap = (w->numworldfaces < 65000 ? w->numworldfaces : 65000) + 6;
 	std::vector<rc_facerec_t> facelist ((size_t)n * f.facecap);
 	std::vector<int> nfaces (n, 0);
 	std::vector<uint16_t> facepos ((size_t)n * w->numfaces, 0xFFFF);
@@ -163,7 +173,16 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		}
 	}
 	for (int vi = 0; vi < n; vi++)
-		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi, &f.nfaces[vi]);
+	{
+		int skykey = 0x7FFFFFFF;
+		for (int fi = 0; fi < w->numworldfaces; fi++) rc_list_face (w, &f, vi, fi, &f.nfaces[vi], &skykey);
+		if (w->drawskybox && skykey != 0x7FFFFFFF)
+		{
+			const int listed = nfaces[vi] < f.facecap ? nfaces[vi] : f.facecap;
+			for (int i = 0; i < 6; i++) rc_list_skybox (w, &f, vi, i, listed, skykey);
+			nfaces[vi] += 6;
+		}
+	}
 	for (int vi = 0; vi < n; vi++)
 		for (int p = 0; p < nfaces[vi]; p++) rc_render_face (w, &f, vi, p, &f.nedges[vi]);
 	for (int vi = 0; vi < n; vi++)

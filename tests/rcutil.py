@@ -28,7 +28,10 @@ def scene_defs():
 
 def make_assets(basedir: str, names=None):
     from tochris_b200.scenes import mdlgen
+    from tochris_b200.scenes import assets as assets_mod
     views.write_base_assets(basedir)
+    for suf, pcx in assets_mod.skybox_pcx("testsky").items():
+        views.write_file(basedir, f"env/testsky{suf}.pcx", pcx)
     views.write_file(basedir, "progs/ball.mdl", mdlgen.icosphere_mdl())
     views.write_file(basedir, "progs/blob.mdl", mdlgen.icosphere_mdl(seed=77, subdiv=1, radius=14.0, nframes=2,
                                                                        frame_group=False, skin_group=True, skin_w=64, skin_h=96))
@@ -143,8 +146,12 @@ def sha(a: np.ndarray) -> str:
 def _rc_worker(q, libpath, basedir, mapname, width, height, specs, cvars, want_debug):
     try:
         from tochris_b200.api import RefCuda
-        r = RefCuda(basedir, width, height, libpath=libpath, **(cvars or {}))
+        cvars = dict(cvars or {})
+        skyname = cvars.pop("r_skyname", None)
+        r = RefCuda(basedir, width, height, libpath=libpath, **cvars)
         r.load_world(mapname)
+        if skyname:
+            r.set_skybox(skyname)
         rds = views.build_refdefs(specs, width, height, model_resolver=r.model)
         fb, z, st = r.render(rds)
         out = dict(fb=fb, z=z, status=st, stats=r.stats())

@@ -23,6 +23,8 @@ CASES = [
     ("full", 640, 480, 12, 0.9, 0.11, dict(dlights=2, underwater_every=2, entities=12, particles=200)),  # warp + everything
     ("full", 320, 240, 64, 0.37, 0.173, dict(doors=2, dlights=3)),           # brush entities: clipped to the BSP, rotated, in one leaf
     ("full", 640, 480, 16, 1.1, 0.2, dict(doors=2, entities=10, particles=100, underwater_every=4)),
+    ("full", 320, 240, 64, 0.37, 0.173, dict(skybox="testsky")),             # loadsky: the six sky-box faces
+    ("full", 640, 480, 12, 1.1, 0.3, dict(skybox="testsky", doors=2, entities=6, dlights=2, underwater_every=5)),
 ]
 
 
@@ -32,11 +34,13 @@ def test_matches_oracle(assets_dir, oracle_available, scene, w, h, n, t0, dt, ex
         pytest.skip("oracle/_ref not built")
     from oracle import run_oracle
     kw = dict(extra)
+    skybox = kw.pop("skybox", None)
+    cvars = {"r_skyname": skybox} if skybox else None
     if scene != "box":
         kw.update(time=t0, time_step=dt)
     specs = rcutil.scene_views(scene, n, **kw)
-    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
-    r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
+    r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
     assert r["stats"]["kernel_launches"] > 0
     rcutil.assert_parity(o, r, specs, w, h)
 

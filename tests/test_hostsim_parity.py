@@ -21,6 +21,8 @@ CASES = [
     ("full", 640, 400, 4, 1.3, 0.4, dict(entities=20, particles=300, dlights=2, underwater_every=3)),
     ("full", 320, 240, 24, 0.37, 0.173, dict(doors=2, dlights=2)),
     ("full", 400, 300, 6, 2.0, 0.3, dict(doors=2, entities=6, particles=50)),
+    ("full", 320, 240, 24, 0.37, 0.173, dict(skybox="testsky")),                     # loadsky: six box faces instead of the scrolling sky
+    ("full", 400, 300, 8, 1.1, 0.3, dict(skybox="testsky", doors=2, entities=6, dlights=2)),
 ]
 
 
@@ -30,11 +32,13 @@ def test_sim_matches_oracle(assets_dir, sim_lib, oracle_available, scene, w, h, 
         pytest.skip("oracle/_ref not built")
     from oracle import run_oracle
     kw = dict(extra)
+    skybox = kw.pop("skybox", None)
+    cvars = {"r_skyname": skybox} if skybox else None
     if scene != "box":
         kw.update(time=t0, time_step=dt)
     specs = rcutil.scene_views(scene, n, **kw)
-    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
-    r = rcutil.render_rc(sim_lib, assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
+    r = rcutil.render_rc(sim_lib, assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
     rcutil.assert_parity(o, r, specs, w, h)
     return
     if not extra.get("underwater_every"):

@@ -81,6 +81,7 @@ class RefCuda:
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.RC_RenderViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.RC_DebugRead.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.RC_SetSkybox.argtypes = [C.c_char_p]
         L.Mod_ForName.restype = C.c_void_p
         L.Mod_ForName.argtypes = [C.c_char_p, C.c_int]
         cfg = rc_config_t()
@@ -128,6 +129,12 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"RC_RenderViewsDevice failed ({rc}): {self.err()}")
         return st.value
+
+    def set_skybox(self, name: str | None):
+        """`loadsky <name>` / r_skyname (r_sky.c:138-194); None or '' switches the sky box off."""
+        rc = self.lib.RC_SetSkybox((name or "").encode())
+        if rc != 0:
+            raise RuntimeError(f"RC_SetSkybox({name}) failed ({rc}): {self.err()}")
 
     def flush_caches(self):
         self.lib.RC_FlushCaches()

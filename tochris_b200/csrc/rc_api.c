@@ -526,6 +526,44 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 	return r;
 }
 
+int RC_SetSkybox (const char *name)
+{
+	/* R_LoadSkybox, r_sky.c:138-187 */
+	static const char *suf[6] = {"rt", "bk", "lf", "ft", "up", "dn"};
+	static const int r_skysideimage[6] = {5, 2, 4, 1, 0, 3};
+	uint8_t *pix;
+	int i, r;
+	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	if (!name || !name[0])
+		return rc_gpu_set_skybox (rc.gpu, NULL, rc.err, sizeof(rc.err));
+	pix = (uint8_t *)malloc (RC_SKYBOX_BYTES);
+	if (!pix) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	for (i = 0; i < 6; i++)
+	{
+		char path[256];
+		size_t len = 0;
+		int w = 0, h = 0;
+		void *buf;
+		unsigned char *pic;
+		snprintf (path, sizeof(path), "env/%s%s.pcx", name, suf[r_skysideimage[i]]);
+		buf = rc_read_file (path, &len);
+		pic = buf ? RC_DecodePCX (buf, len, &w, &h) : NULL;
+		free (buf);
+		if (!pic || w != 256 || h != 256)
+		{
+			r = pic ? rc_fail (RC_ERR_FORMAT, "%s must be 256x256", path) : rc_fail (RC_ERR_FILE, "Couldn't load %s", path);
+			free (pic); free (pix);
+			rc_gpu_set_skybox (rc.gpu, NULL, rc.err + strlen (rc.err), 0);
+			return r;
+		}
+		memcpy (pix + (size_t)i * 65536, pic, 65536);
+		free (pic);
+	}
+	r = rc_gpu_set_skybox (rc.gpu, pix, rc.err, sizeof(rc.err));
+	free (pix);
+	return r;
+}
+
 void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }
 void RC_GetStats (rc_stats_t *out) { if (rc.gpu) rc_gpu_get_stats (rc.gpu, out); else memset (out, 0, sizeof(*out)); }
 void RC_SetProfiling (int on) { if (rc.gpu) rc_gpu_set_profiling (rc.gpu, on); }

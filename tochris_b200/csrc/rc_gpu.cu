@@ -43,6 +43,7 @@ struct rc_gpu_s {
 	rc_world_t w;			/* device pointers */
 	std::vector<void *> worldallocs;
 	bool haveworld;
+	int skybox;			/* r_drawskybox */
 	int maxedges, maxsurfs;
 	int *d_sintable, *d_intsintable;
 	/* surface cache (persists across batches) */
@@ -129,12 +130,12 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster ();
 	extern __shared__ __align__(16) unsigned char front_smem[];
-	__shared__ int s_counters[2];			/* listed faces, emitted edges of the view (rank 0's copy is the live one) */
+	__shared__ int s_counters[3];			/* listed faces, emitted edges, BSP key of the first sky face (rank 0's copy is the live one) */
 	const int csize = (int)cluster.num_blocks (), crank = (int)cluster.block_rank ();
 	const int vi = blockIdx.x / csize, tid = threadIdx.x;
 	const int gtid = crank * FRONT_THREADS + tid, gthreads = csize * FRONT_THREADS;
 	int *ctr = cluster.map_shared_rank (s_counters, 0);
-	if (tid < 2) s_counters[tid] = 0;
+	if (tid < 3) s_counters[tid] = tid == 2 ? 0x7FFFFFFF : 0;
 #ifdef RC_FRONT_TIMING
 	long long tq[16];
 	int tqn = 0;
@@ -196,9 +197,20 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 	}
 	TQ ();
 	for (int fi = gtid; fi < w.numworldfaces; fi += gthreads)
-		rc_list_face (&w, &f, vi, fi, &ctr[0]);
+		rc_list_face (&w, &f, vi, fi, &ctr[0], &ctr[2]);
 	cluster.sync ();
 	TQ ();
+	if (w.drawskybox && ctr[2] != 0x7FFFFFFF)
+	{
+		/* a sky face was reached: the six faces of the sky box join the list (R_EmitSkyBox) */
+		const int listed = ctr[0];
+		cluster.sync ();
+		if (gtid < 6)
+			rc_list_skybox (&w, &f, vi, gtid, listed < f.facecap ? listed : f.facecap, ctr[2]);
+		if (gtid == 0)
+			ctr[0] = listed + 6;
+		cluster.sync ();
+	}
 	const int nfraw = ctr[0];
 	const int nf = nfraw < f.facecap ? nfraw : f.facecap;
 	{
@@ -971,7 +983,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	rc_gpu_t *g = new rc_gpu_s ();
 	memset (&g->stats, 0, sizeof(g->stats));
 	g->device = device; g->width = width; g->height = height;
-	g->haveworld = false; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
+	g->haveworld = false; g->skybox = 0; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
@@ -1106,10 +1118,10 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 	UP (planes, h->numplanes + 6)
 	UP (nodes, h->numnodes)
 	UP (leafs, h->numleafs)
-	UP (faces, h->numfaces + 6)
+	UP (faces, h->numfaces)
 	UP (surfedges, h->numsurfedges + 24)
 	UP (separtner, h->numsurfedges + 1)
-	UP (fedges, h->numsurfedges + 1)
+	UP (fedges, h->numsurfedges + 24 + 1)
 	UP (edges, (size_t)(h->numedges + 13) * 2)
 	UP (vertexes, (size_t)(h->numvertexes + 8) * 3)
 	UP (texinfo, h->numtexinfo + 6)
@@ -1125,6 +1137,7 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 #undef UP
 	g->w.sintable = g->d_sintable;
 	g->w.intsintable = g->d_intsintable;
+	g->w.drawskybox = g->skybox;
 	g->maxedges = maxedges; g->maxsurfs = maxsurfs;
 	g->haveworld = true;
 	rc_gpu_flush_caches (g);
@@ -1136,11 +1149,26 @@ void rc_gpu_flush_caches (rc_gpu_t *g)
 	g->flush_pending = 1;
 }
 
+int rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	if (pixels)
+		CK (cudaMemcpy (g->d_cachepool, pixels, RC_SKYBOX_BYTES, cudaMemcpyHostToDevice));
+	g->skybox = pixels != NULL;
+	g->w.drawskybox = g->skybox;
+	return RC_OK;
+}
+
 static void do_flush (rc_gpu_t *g, cudaStream_t s)
 {
 	/* only the slots that can be in use are cleared: the table is sized for the pool */
 	k_fill64<<<g->numsms * 4, 256, 0, s>>> (g->d_cachekeys, RC_CACHE_EMPTY, (size_t)g->cacheslots);
-	cudaMemsetAsync (g->d_alloc + 1, 0, sizeof(unsigned long long), s);
+	{
+		/* the pool starts after the sky-box pictures */
+		static const unsigned long long first = RC_SKYBOX_BYTES;
+		cudaMemcpyAsync (g->d_alloc + 1, &first, sizeof(first), cudaMemcpyHostToDevice, s);
+	}
 	g->flush_pending = 0;
 }
 
@@ -1156,8 +1184,7 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
 {
 	const rc_world_t *w = &g->w;
-	int facecap = w->numworldfaces < 65000 ? w->numworldfaces : 65000;
-	if (facecap < 1) facecap = 1;
+	int facecap = (w->numworldfaces < 65000 ? w->numworldfaces : 65000) + 6;	/* + the six sky-box faces */
 	int edgecap = g->maxedges, surfcap = facecap + 2 + want_bsurfs;
 	size_t freeb = 0, totalb = 0;
 	if (g->d_views && g->facecap == facecap && g->edgecap == edgecap && g->bsurfcap == want_bsurfs && (g->chunkcap >= n || g->chunkcap == g->maxchunk))

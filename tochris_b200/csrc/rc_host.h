@@ -109,6 +109,7 @@ int  RC_AliasSetup (const rc_hostalias_t *a, const rc_hostworld_t *hw, const ent
 int  RC_BmodelSetup (const rc_hostworld_t *hw, int submodel, const entity_t *e, const rc_refdef_t *rd, const rc_view_t *v,
                      float pixelAspect, rc_bent_t *out);
 int  RC_PointInLeaf (const rc_hostworld_t *hw, const float *p);
+unsigned char *RC_DecodePCX (const void *data, size_t len, int *width, int *height);
 
 /* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
 typedef struct rc_gpu_s rc_gpu_t;
@@ -138,6 +139,8 @@ int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_
 int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
 void rc_gpu_flush_caches (rc_gpu_t *g);
+/* pixels: six 256x256 pictures in r_skysideimage order, or NULL to switch the sky box off */
+int  rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen);
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out);
 void rc_gpu_set_profiling (rc_gpu_t *g, int on);
 int  rc_gpu_debug_read (rc_gpu_t *g, int kind, int view, void *dst, int cap);

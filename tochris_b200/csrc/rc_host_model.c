@@ -601,7 +601,7 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 		w->separtner = sp;
 		{
 			/* flattened per-surfedge records for the face kernel */
-			rc_fedge_t *fe = (rc_fedge_t *)own (hw, sizeof(rc_fedge_t) * (w->numsurfedges + 1));
+			rc_fedge_t *fe = (rc_fedge_t *)own (hw, sizeof(rc_fedge_t) * (w->numsurfedges + 24 + 1));
 			for (i = 0; i < w->numsurfedges; i++)
 			{
 				int l = w->surfedges[i], m = abs (l);
@@ -622,6 +622,63 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 		free (se_face);
 		free (medge_refs);
 		medge_refs = NULL;
+	}
+
+	/* R_InitSkyBox (r_rast.c:74-157): six faces of a box around the viewer, appended after every other
+	 * face.  What depends on the view origin (vertex positions, plane distances, texture offsets) is
+	 * applied per view on the device; here: topology, axis, sign, texture axes.  v0/v1 of the box's
+	 * rc_fedge_t hold the vertex SIGNS (box_verts), plane.dist holds +-128. */
+	{
+		static const int skybox_planes[12] = {2,-128, 0,-128, 2,128, 1,128, 0,128, 1,-128};
+		static const int box_surfedges[24] = { 1,2,3,4,  -1,5,6,7,  8,9,-6,10,  -2,-7,-9,11,  12,-3,-11,-8,  -12,-10,-5,-4};
+		static const int box_edges[24] = { 1,2, 2,3, 3,4, 4,1, 1,5, 5,6, 6,2, 7,8, 8,6, 5,7, 8,3, 7,4};
+		static const int box_faces[6] = {0,0,2,2,2,0};
+		static const float box_vecs[6][2][3] = {
+			{ {0,-1,0}, {-1,0,0} }, { {0,1,0}, {0,0,-1} }, { {0,-1,0}, {1,0,0} },
+			{ {1,0,0}, {0,0,-1} }, { {0,-1,0}, {0,0,-1} }, { {-1,0,0}, {0,0,-1} } };
+		static const float box_verts[8][3] = { {-1,-1,-1}, {-1,1,-1}, {1,1,-1}, {1,-1,-1}, {-1,-1,1}, {-1,1,1}, {1,-1,1}, {1,1,1} };
+		rc_face_t *faces = (rc_face_t *)w->faces;
+		rc_plane_t *planes = (rc_plane_t *)w->planes;
+		rc_texinfo_t *ti = (rc_texinfo_t *)w->texinfo;
+		rc_fedge_t *fe = (rc_fedge_t *)w->fedges;
+		w->skyfirst = w->numfaces;
+		w->drawskybox = 0;
+		for (i = 0; i < 6; i++)
+		{
+			rc_face_t *f = &faces[w->numfaces + i];
+			memset (f, 0, sizeof(*f));
+			memset (&planes[w->numplanes + i], 0, sizeof(rc_plane_t));
+			planes[w->numplanes + i].normal[skybox_planes[i*2]] = 1;
+			planes[w->numplanes + i].dist = skybox_planes[i*2+1];
+			planes[w->numplanes + i].type = skybox_planes[i*2];		/* ours: the axis (the reference leaves 0, never read) */
+			memset (&ti[w->numtexinfo + i], 0, sizeof(rc_texinfo_t));
+			for (j = 0; j < 3; j++) { ti[w->numtexinfo + i].vecs[0][j] = box_vecs[i][0][j]; ti[w->numtexinfo + i].vecs[1][j] = box_vecs[i][1][j]; }
+			ti[w->numtexinfo + i].mipadjust = 1; ti[w->numtexinfo + i].texture = 0;
+			f->plane = w->numplanes + i;
+			f->numedges = 4;
+			f->flags = box_faces[i] | RC_SURF_DRAWSKYBOX;
+			f->firstedge = w->numsurfedges + i*4;
+			f->texinfo = w->numtexinfo + i;
+			f->texturemins[0] = -128; f->texturemins[1] = -128;
+			f->extents[0] = 256; f->extents[1] = 256;
+			f->styles[0] = f->styles[1] = f->styles[2] = f->styles[3] = 255;
+			f->lightofs = -1; f->node = -1;
+		}
+		for (i = 0; i < 24; i++)
+		{
+			int l = box_surfedges[i], m = abs (l);
+			int a = box_edges[(m-1)*2 + (l > 0 ? 0 : 1)] - 1, b = box_edges[(m-1)*2 + (l > 0 ? 1 : 0)] - 1;
+			rc_fedge_t *e = &fe[w->numsurfedges + i];
+			for (j = 0; j < 3; j++) { e->v0[j] = box_verts[a][j]; e->v1[j] = box_verts[b][j]; }
+			e->partner_face = -1; e->partner_rev = 0;
+			for (k = 0; k < 24; k++)
+				if (k != i && abs (box_surfedges[k]) == m)
+				{
+					e->partner_face = w->numfaces + k / 4;
+					e->partner_rev = ((box_surfedges[k] > 0) != (l > 0));
+				}
+		}
+		w->numfaces += 6;
 	}
 
 	w->colormap = colormap;

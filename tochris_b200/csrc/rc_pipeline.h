@@ -319,7 +319,7 @@ RC_HD void rc_mark_face (const rc_world_t *w, const rc_frame_t *f, int vi, int m
 
 /* One thread per (view, world face): the face loop of R_RecursiveWorldNode (r_bsp.c:520-549):
  * right side of its node's plane, marked by an earlier leaf -> R_RenderFace is called on it. */
-RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int fi, int *nfaces)
+RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int fi, int *nfaces, int *skykey)
 {
 	const rc_face_t *fa = &w->faces[fi];
 	if (fa->node < 0)
@@ -333,6 +333,8 @@ RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int f
 	const int key = nv.facekey + fa->nodeslot;
 	if (!(RC_LDCG (&f->facemark[(size_t)vi * w->numfaces + fi]) < key))
 		return;
+	if ((fa->flags & RC_SURF_DRAWSKY) && w->drawskybox)
+		RC_ATOMIC_MIN_I (skykey, key);		/* the first sky face in BSP order triggers R_EmitSkyBox (r_rast.c:530-533) */
 	int p = RC_ATOMIC_ADD_I (nfaces, 1);	/* the view's counter: in shared memory on the GPU (same-address L2 atomics serialise) */
 	if (p >= f->facecap || p >= (int)RC_FACEPOS_MARKED - 1)
 	{
@@ -342,6 +344,24 @@ RC_HD void rc_list_face (const rc_world_t *w, const rc_frame_t *f, int vi, int f
 	rc_facerec_t *rec = f->facelist + (size_t)vi * f->facecap + p;
 	rec->face = fi; rec->clipflags = nv.clipflags; rec->key = key; rec->pad = 0;
 	f->facepos[(size_t)vi * w->numfaces + fi] = (uint16_t)p;
+}
+
+/* R_EmitSkyBox (r_rast.c:165-205): when a sky face was reached and a sky box is loaded, the six box
+ * faces go through R_RenderFace with all four clip planes and the keys 0x7ffffff0.. (behind every
+ * world face, in front of the background).  The reference numbers only the faces that emit; fixed
+ * keys 0x7ffffff0 + i compare the same.  rec.pad = BSP key of the triggering sky face = the box's
+ * place in the emission order (edge rank).  One thread per box face, i = 0..5. */
+RC_HD void rc_list_skybox (const rc_world_t *w, const rc_frame_t *f, int vi, int i, int nlisted, int skykey)
+{
+	const int p = nlisted + i;
+	if (p >= f->facecap)
+	{
+		RC_ATOMIC_OR_I (f->status, RC_STAT_FACELIST);
+		return;
+	}
+	rc_facerec_t *rec = f->facelist + (size_t)vi * f->facecap + p;
+	rec->face = w->skyfirst + i; rec->clipflags = 15; rec->key = RC_SKYBOX_KEY + i; rec->pad = skykey;
+	f->facepos[(size_t)vi * w->numfaces + w->skyfirst + i] = (uint16_t)p;
 }
 
 /* ------------------------------------------------------------- stage 2: face -> edges -- */
@@ -549,11 +569,27 @@ RC_HD void rc_face_edge (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 #else
 	fe = w->fedges[fa->firstedge + i];
 #endif
+	out->flags = 0; out->nearzi = 0;
+	if ((fa->flags & RC_SURF_DRAWSKY) && w->drawskybox)
+	{
+		out->flags = RC_ER_SKIP;		/* r_rast.c:530-533: the sky box is drawn instead */
+		return;
+	}
+	if (rec.face >= w->skyfirst)
+	{
+		/* the box follows the viewer: r_skyverts = r_origin + box_verts * 128 (r_rast.c:177-180) */
+		for (int j = 0; j < 3; j++)
+		{
+			fe.v0[j] = vw->origin[j] + fe.v0[j]*128;
+			fe.v1[j] = vw->origin[j] + fe.v1[j]*128;
+		}
+	}
 	const float *va = fe.v0, *vb = fe.v1;
 	int q = RC_FACEPOS_NONE;
 	if (fe.partner_face >= 0)
 		q = facepos[fe.partner_face];
-	out->flags = 0; out->nearzi = 0;
+	if (w->drawskybox && q < (int)RC_FACEPOS_MARKED && (w->faces[fe.partner_face].flags & RC_SURF_DRAWSKY))
+		q = RC_FACEPOS_NONE;			/* a sky face leaves the edge cache alone when the box is drawn in its place */
 
 	if (q < (int)RC_FACEPOS_MARKED && list[q].key < rec.key)
 	{
@@ -705,6 +741,11 @@ RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 	rc_surf_t *surf = f->surfs + (size_t)vi * f->surfcap + (p + 2);
 	const int surfidx = p + 2;
 	const int ne = fa->numedges;
+	/* place in the reference's emission order (newedges[] tie order): a world face's BSP key; the six
+	 * box faces are emitted where the first sky face was met, five slots each */
+	const int isbox = rec.face >= w->skyfirst;
+	const uint32_t orderkey = (uint32_t)(isbox ? rec.pad : rec.key);
+	const int slot0 = isbox ? (rec.face - w->skyfirst) * 5 : 0;
 	if (st->neb)
 	{
 		if (base + st->neb > f->edgecap)
@@ -721,7 +762,7 @@ RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 				dst->u = e->u; dst->u_step = e->u_step;
 				dst->v = (int16_t)(e->vv & 0xFFFF); dst->v2 = (int16_t)((uint32_t)e->vv >> 16);
 				dst->surfs[0] = (uint16_t)(e->surfs & 0xFFFF); dst->surfs[1] = (uint16_t)((uint32_t)e->surfs >> 16);
-				dst->rank = (trailing << 31) | ((uint32_t)rec.key << 5) | (uint32_t)i;
+				dst->rank = (trailing << 31) | (orderkey << 5) | (uint32_t)(slot0 + i);
 				dst->pad[0] = dst->pad[1] = dst->pad[2] = 0;
 				dst++;
 			}
@@ -731,7 +772,7 @@ RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 				dst->v = (int16_t)st->lv; dst->v2 = (int16_t)st->lv2;
 				dst->surfs[0] = st->ltrailing ? surfidx : 0;
 				dst->surfs[1] = st->ltrailing ? 0 : surfidx;
-				dst->rank = ((uint32_t)st->ltrailing << 31) | ((uint32_t)rec.key << 5) | 31u;
+				dst->rank = ((uint32_t)st->ltrailing << 31) | (orderkey << 5) | (isbox ? (uint32_t)(slot0 + 4) : 31u);
 				dst->pad[0] = dst->pad[1] = dst->pad[2] = 0;
 			}
 		}
@@ -743,7 +784,10 @@ RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 	const rc_plane_t *pplane = &w->planes[fa->plane];
 	float p_normal[3];
 	rc_transform_vector (vw, pplane->normal, p_normal);
-	float distinv = 1.0 / (pplane->dist - rc_dot3 (vw->origin, pplane->normal));
+	float planedist = pplane->dist;
+	if (isbox)
+		planedist = vw->origin[pplane->type] + pplane->dist;	/* r_rast.c:183-187: r_origin[axis] +- 128 */
+	float distinv = 1.0 / (planedist - rc_dot3 (vw->origin, pplane->normal));
 	surf->key = rec.key;
 	surf->flags = fa->flags;
 	surf->face = rec.face;
@@ -1478,9 +1522,8 @@ RC_HD uint32_t rc_hash64 (unsigned long long k)
 }
 
 /* D_CalcGradients, d_edge.c:96-157 */
-RC_HD void rc_calc_gradients (const rc_world_t *w, const rc_view_t *vw, const rc_xform_t *xf, const rc_face_t *fa, int miplevel, rc_surf_t *s)
+RC_HD void rc_calc_gradients (const rc_view_t *vw, const rc_xform_t *xf, const rc_face_t *fa, const rc_texinfo_t *ti, int miplevel, rc_surf_t *s)
 {
-	const rc_texinfo_t *ti = &w->texinfo[fa->texinfo];
 	float mipscale = 1.0 / (float)(1 << miplevel);
 	float p_saxis[3], p_taxis[3], p_temp1[3];
 	float t;
@@ -1558,6 +1601,22 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 	s->drawflags = s->flags;
 	s->d_zistepu_draw = s->d_zistepu;
 	s->izistep = rc_f2i (s->d_zistepu * 0x8000 * 0x10000);
+	if (s->flags & RC_SURF_DRAWSKYBOX)
+	{
+		/* d_edge.c:211-235: one of the six 256x256 pictures (at the start of the cache pool), mip 0,
+		 * texture axes of the box face with offsets that follow the viewer (r_rast.c:190-194); the
+		 * z-buffer gets the background value (rc_span_seg) */
+		const rc_face_t *bf = &w->faces[s->face];
+		rc_texinfo_t ti = w->texinfo[bf->texinfo];
+		ti.vecs[0][3] = -rc_dot3 (vw->origin, ti.vecs[0]);
+		ti.vecs[1][3] = -rc_dot3 (vw->origin, ti.vecs[1]);
+		s->pad = RC_SRC_POOL;
+		s->cacheofs = (s->face - w->skyfirst) * (256 * 256);
+		s->cachewidth = 256;
+		s->izistep = 0;
+		rc_calc_gradients (vw, rc_view_xform (vw), bf, &ti, 0, s);
+		return;
+	}
 	if ((s->flags & RC_SURF_DRAWSKY) && !vw->fastsky)
 	{
 		s->pad = RC_SRC_SKY;		/* d_edge.c:186-193; z uses the surface's own 1/z plane */
@@ -1582,7 +1641,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 		s->pad = RC_SRC_TEXELS;
 		s->cacheofs = w->textures[ti->texture].offsets[0];
 		s->cachewidth = 64;
-		rc_calc_gradients (w, vw, xf, fa, 0, s);
+		rc_calc_gradients (vw, xf, fa, ti, 0, s);
 		return;
 	}
 	/* D_MipLevelForScale, d_edge.c:44-63 */
@@ -1667,7 +1726,7 @@ RC_HD void rc_surf_prep (const rc_world_t *w, const rc_frame_t *f, int vi, int s
 	s->cacheofs = ofs;
 	s->miplevel = (cacheable && !creator) ? slot : -1;
 	s->cachewidth = bw;
-	rc_calc_gradients (w, vw, xf, fa, mip, s);
+	rc_calc_gradients (vw, xf, fa, ti, mip, s);
 }
 
 RC_HD void rc_surf_resolve (const rc_frame_t *f, int vi, int si)
@@ -1919,7 +1978,13 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 	const float zistepu = s.d_zistepu, zistepv = s.d_zistepv, ziorigin = s.d_ziorigin;
 	if (sidx == 0)
 	{
-		const double zid = ziorigin + dv*zistepv + du*zistepu;
+		double zid = ziorigin + dv*zistepv + du*zistepu;
+		if (s.drawflags & RC_SURF_DRAWSKYBOX)
+		{
+			/* d_edge.c:228-234: d_ziorigin = -0.9, no steps: "effectively at infinity" */
+			const float bgzi = -0.9, zero = 0;
+			zid = bgzi + dv*zero + du*zero;
+		}
 		spp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
 		spp->izistep = s.izistep;
 	}

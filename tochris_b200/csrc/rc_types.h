@@ -36,6 +36,8 @@ extern "C" {
 #define RC_SURF_DRAWSKYBOX     0x80
 
 #define RC_CONTENTS_SOLID (-2)
+#define RC_SKYBOX_BYTES   (6 * 256 * 256)   /* r_skypixels, r_sky.c:135: reserved at the start of the surface-cache pool */
+#define RC_SKYBOX_KEY     0x7ffffff0        /* r_rast.c:199 */
 
 /* ---- world model (replaces model_t's brush arrays, ref_soft/r_model.h:290-340) ------ */
 typedef struct {            /* cplane_t, common/mathlib.h */
@@ -128,6 +130,8 @@ typedef struct {            /* device-resident world; all pointers are device po
     int numworldfaces;      /* faces of model 0 (without skybox faces) */
     int skytexofs;          /* texel offset of the 256x128 sky texture R_InitSky copied last (r_sky.c:53), -1: none */
     int marksplit;          /* 1: markleaf[] is valid (no two leaves share a marksurfaces entry) */
+    int skyfirst;           /* first of the six sky-box faces R_InitSkyBox appends (r_rast.c:108-157); they are the last six of faces[] */
+    int drawskybox;         /* r_drawskybox: a sky box is loaded (r_sky.c:189-194); its six 256x256 pictures sit at the start of the cache pool */
     int visrowwords;        /* words per row of nodevis */
     const rc_plane_t     *planes;
     const rc_node_t      *nodes;

@@ -115,3 +115,43 @@ def make_sky_pixels(seed: int) -> np.ndarray:
     front = np.where(cloud, 16 * 1 + 10 + (n % 4), 0)
     px = np.where(xx < 128, front, back)
     return px.astype(np.uint8)
+
+
+def encode_pcx(pixels: np.ndarray, palette: np.ndarray) -> bytes:
+    """8-bit run-length PCX, the format LoadPCX accepts (ref_soft/pcx.c:33-95: manufacturer 0x0a,
+    version 5, encoding 1, 8 bits per pixel) and WritePCXfile emits (pcx.c:103-160)."""
+    import struct
+    h, w = pixels.shape
+    hdr = struct.pack("<BBBBHHHHHH48sBBHH58s", 0x0A, 5, 1, 8, 0, 0, w - 1, h - 1, w, h, bytes(48), 0, 1, w, 2, bytes(58))
+    out = bytearray(hdr)
+    for y in range(h):
+        row = pixels[y]
+        x = 0
+        while x < w:
+            v = int(row[x])
+            run = 1
+            while x + run < w and run < 63 and int(row[x + run]) == v:
+                run += 1
+            if run > 1 or (v & 0xC0) == 0xC0:
+                out.append(0xC0 | run)
+            out.append(v)
+            x += run
+    out.append(0x0C)
+    out += palette.astype(np.uint8).tobytes()
+    return bytes(out)
+
+
+def skybox_pcx(name: str, seed: int = 0x51AB) -> dict:
+    """Six 256x256 pictures for `loadsky <name>` (env/<name>{rt,bk,lf,ft,up,dn}.pcx, r_sky.c:138-187):
+    a different gradient + noise pattern per side so that a swapped or mirrored face is visible."""
+    pal = make_palette()
+    out = {}
+    for k, suf in enumerate(["rt", "bk", "lf", "ft", "up", "dn"]):
+        yy, xx = np.mgrid[0:256, 0:256]
+        noise = ((xx * 1103515245 + yy * 12345 + seed * (k + 1)) >> 7) & 7
+        band = ((xx * (k + 1) + yy * (6 - k)) >> 4) & 15
+        pix = (16 * (2 * k + 1) + ((band + noise) & 15)).astype(np.uint8)
+        pix[:8, :] = 250 - k                      # a bright stripe along the top edge
+        pix[:, :4] = 200 + k
+        out[suf] = encode_pcx(pix, pal)
+    return out
