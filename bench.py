@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--keep-cache", action="store_true", help="do not flush the surface cache between steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--gather", default="peer-copy", choices=["peer-copy", "peer", "nccl", "nccl-groups"], help="N>1: how framebuffers reach rank 0")
     return ap.parse_args()
 
 
@@ -172,7 +173,38 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     fb = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
     zb = torch.empty((n, H, W), dtype=torch.int16, device=dev)
-    gather = [torch.empty_like(fb) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # N>1: the path's only cross-GPU step is bringing the framebuffers to rank 0.
+    #   peer-copy (default): rank 0 exports its gather buffer (CUDA IPC); every rank renders locally and copies each
+    #                   finished group of 16 views into its slice over NVLink while the next group is drawn
+    #   peer:           every rank renders straight into its slice: the draw kernel's stores cross NVLink
+    #   nccl:           render locally, then one NCCL gather to rank 0
+    #   nccl-groups:    NCCL gather per group of 16 views on a side stream while the next group is drawn
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    gbufs = {}
+    gather = None
+    fb_target = fb.data_ptr()
+    px1 = H * W
+    if world > 1 and args.gather in ("peer", "peer-copy"):
+        hbuf = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            root_ptr = r.device_alloc(world * n * px1)
+            hbuf.copy_(torch.frombuffer(bytearray(r.ipc_export(root_ptr)), dtype=torch.uint8))
+        dist.broadcast(hbuf, src=0)
+        if rank != 0:
+            root_ptr = r.ipc_import(bytes(hbuf.cpu().numpy().tobytes()))
+        if args.gather == "peer":
+            fb_target = root_ptr + rank * n * px1
+        else:
+            r.set_mirror_output(root_ptr + rank * n * px1)
+    elif world > 1 and args.gather == "nccl":
+        gather = [torch.empty_like(fb) for _ in range(world)] if rank == 0 else None
+    elif world > 1:
+        def on_group(first, num):
+            with torch.cuda.stream(side):
+                if rank == 0 and first not in gbufs:
+                    gbufs[first] = [torch.empty((num, H, W), dtype=torch.uint8, device=dev) for _ in range(world)]
+                dist.gather(fb[first:first + num], gbufs.get(first), dst=0)
+        r.set_group_callback(on_group, side.cuda_stream, 4)
     l2flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     px = n * W * H
@@ -183,9 +215,11 @@ def run_ours(args):
         l2flush.zero_()                    # evict the previous step's data from the 126 MB L2
         if timed_events is not None:
             timed_events[0].record(stream)
-        st = r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
-        if world > 1:
+        st = r.render_device(rds, n, fb_target, zb.data_ptr(), stream.cuda_stream)
+        if world > 1 and args.gather == "nccl":
             shard.gather_frames(fb, n * world, rank, world, dst=0, bufs=gather, concat=False)
+        elif world > 1 and args.gather == "nccl-groups":
+            stream.wait_stream(side)       # the step ends when the last group has arrived on rank 0
         if timed_events is not None:
             timed_events[1].record(stream)
         return st
@@ -212,6 +246,26 @@ def run_ours(args):
         dist.barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     sampler.stop = True
+    if world > 1 and args.gather == "nccl-groups":
+        r.set_group_callback(None)
+    gather_check = None
+    if world > 1 and args.gather in ("peer", "peer-copy"):
+        r.set_mirror_output(0)
+        # once, outside the timed region: what arrived on rank 0 over NVLink equals what each rank renders locally
+        r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        wts = torch.arange(1, n * px1 + 1, device=dev, dtype=torch.int64) % 65521
+        mine = torch.stack([(fb.view(-1).to(torch.int64) * wts).sum(), fb.view(-1).to(torch.int64).sum()])
+        allsums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+        if rank == 0:
+            import ctypes as C
+            arrived = torch.empty(world * n * px1, dtype=torch.uint8, device=dev)
+            C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(arrived.data_ptr()), C.c_void_p(root_ptr), C.c_size_t(world * n * px1), 3)
+            gather_check = True
+            for q in range(world):
+                sl = arrived[q * n * px1:(q + 1) * n * px1].to(torch.int64)
+                gather_check &= bool(((sl * wts).sum() == allsums[q][0]) and (sl.sum() == allsums[q][1]))
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers ----
     fb_host = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
@@ -283,7 +337,7 @@ def run_ours(args):
                    "width": W, "height": H, "views_per_gpu": n, "global_batch": n * world, "parallelism": f"dp{world} by view",
                    "l2": "flushed between steps (256 MiB write)",
                    "surface_cache": "kept across steps" if args.keep_cache else "flushed before every step (all visible blocks rebuilt inside the timed region)",
-                   "collective": "NCCL gather of framebuffers to rank 0 inside the timed region" if world > 1 else "none"},
+                   "collective": ({"peer-copy": "none: rank 0 exports its gather buffer (CUDA IPC peer memory); every rank copies each finished group of 16 views into its slice over NVLink on a second stream while the next group is drawn; NCCL only for the handle broadcast and the closing barrier", "peer": "none: every rank renders straight into rank 0's gather buffer (CUDA IPC peer memory), the draw kernel's stores cross NVLink as they are produced; NCCL only for the handle broadcast and the closing barrier", "nccl": "NCCL gather of framebuffers to rank 0 inside the timed region", "nccl-groups": "NCCL gather per group of 16 views, overlapped with the draw of the next group"}[args.gather] if world > 1 else "none"), "gather_verified": gather_check},
         "mpixel_per_s": round(value * W * H / 1e6, 1),
         "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),
         "e2e": {"value": round(n * world * args.steps / e2e_s, 1), "unit": "frames/s",

@@ -133,6 +133,32 @@ int  RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_o
  * (a cudaStream_t, 0 = legacy default) and is complete when the stream reaches this point. */
 int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status);
 
+/* Overlapping a consumer with the draw stage.  With a callback set, RC_RenderViewsDevice draws the
+ * views of a batch in `ngroups` groups (batches with alias models, particles or under-water views are
+ * still drawn in one piece); after a group's draw kernel is enqueued, `side_stream` (a cudaStream_t)
+ * is made to wait for it and fn (user, first_view, num_views) is called, so the caller can enqueue
+ * work that reads fb_dev[first_view .. first_view + num_views) on side_stream -- bench.py sends the
+ * finished group to rank 0 over NCCL while the next group is drawn.  fn NULL switches it off. */
+typedef void (*rc_group_fn) (void *user, int first_view, int num_views);
+void RC_SetGroupCallback (rc_group_fn fn, void *user, void *side_stream, int ngroups);
+
+/* Multi-GPU output placement (one process per GPU).  The only cross-GPU step of the path is
+ * bringing the finished framebuffers to one rank.  Instead of a collective after the fact, a rank can
+ * render straight into the root's memory: the root allocates the gather buffer with RC_DeviceAlloc and
+ * exports it (CUDA IPC, 64-byte handle), every other rank imports it and passes its slice as fb_dev to
+ * RC_RenderViewsDevice -- the draw kernel's aligned 8-byte stores then travel over NVLink as they are
+ * produced --, or, usually faster, keeps rendering into local memory and names its slice as a MIRROR:
+ * RC_SetMirrorOutput (fb, z) makes every following RC_RenderViewsDevice copy each finished group of views
+ * to fb (any unified-addressing pointer: peer device memory or pinned host memory; z may be NULL) on a
+ * second stream while the next group is drawn; the call's stream completes after the copies.
+ * RC_SetMirrorOutput (NULL, NULL) switches it off.  Returns RC_OK or RC_ERR_CUDA. */
+int  RC_DeviceAlloc (size_t bytes, void **ptr);
+void RC_DeviceFree (void *ptr);
+int  RC_IpcExport (void *ptr, unsigned char handle[64]);
+int  RC_IpcImport (const unsigned char handle[64], void **ptr);
+void RC_IpcClose (void *ptr);
+void RC_SetMirrorOutput (void *fb, void *z);
+
 /* The `loadsky <name>` command / r_skyname cvar (ref_soft/r_main.c:169-177, r_sky.c:138-194):
  * loads <basedir>/id1/env/<name>{rt,bk,lf,ft,up,dn}.pcx (six 256x256 8-bit PCX pictures); from then on
  * sky surfaces make the renderer draw the six faces of a box around the viewer instead of the

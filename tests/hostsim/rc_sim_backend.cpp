@@ -102,6 +102,18 @@ void rc_gpu_flush_caches (rc_gpu_t *g)
 	g->alloc[1] = RC_SKYBOX_BYTES;		/* the pool starts after the sky-box pictures */
 }
 
+int rc_gpu_device_alloc (rc_gpu_t *g, size_t bytes, void **ptr) { (void)g; *ptr = malloc (bytes); return *ptr ? RC_OK : RC_ERR_NOMEM; }
+void rc_gpu_device_free (rc_gpu_t *g, void *ptr) { (void)g; free (ptr); }
+int rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle) { (void)g; (void)ptr; (void)handle; return RC_ERR_CUDA; }
+int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr) { (void)g; (void)handle; (void)ptr; return RC_ERR_CUDA; }
+void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { (void)g; (void)ptr; }
+void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { (void)g; (void)fb; (void)z; }
+
+void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)
+{
+	(void)g; (void)fn; (void)user; (void)side_stream; (void)ngroups;	/* the simulator draws a batch in one piece */
+}
+
 int rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen)
 {
 	(void)err; (void)errlen;

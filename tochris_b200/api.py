@@ -67,6 +67,9 @@ def status_names(status: int):
     return [n for b, n in RC_STAT.items() if status & b]
 
 
+GROUPFN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)
+
+
 class RefCuda:
     """One renderer instance per process (the C library keeps one global renderer, as the
     reference does)."""
@@ -82,6 +85,14 @@ class RefCuda:
         L.RC_RenderViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.RC_DebugRead.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.RC_SetSkybox.argtypes = [C.c_char_p]
+        L.RC_DeviceAlloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.RC_DeviceFree.argtypes = [C.c_void_p]
+        L.RC_IpcExport.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte)]
+        L.RC_IpcImport.argtypes = [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+        L.RC_IpcClose.argtypes = [C.c_void_p]
+        L.RC_SetMirrorOutput.argtypes = [C.c_void_p, C.c_void_p]
+        L.RC_SetGroupCallback.argtypes = [GROUPFN, C.c_void_p, C.c_void_p, C.c_int]
+        L.RC_SetGroupCallback.restype = None
         L.Mod_ForName.restype = C.c_void_p
         L.Mod_ForName.argtypes = [C.c_char_p, C.c_int]
         cfg = rc_config_t()
@@ -135,6 +146,40 @@ class RefCuda:
         rc = self.lib.RC_SetSkybox((name or "").encode())
         if rc != 0:
             raise RuntimeError(f"RC_SetSkybox({name}) failed ({rc}): {self.err()}")
+
+    def set_group_callback(self, fn, side_stream: int = 0, ngroups: int = 4):
+        """fn(first_view, num_views) is called after each group of views of a render_device() batch has been
+        enqueued; side_stream (raw cudaStream_t) already waits for the group.  fn None switches it off."""
+        if fn is None:
+            self._group_cb = None
+            self.lib.RC_SetGroupCallback(GROUPFN(), None, None, 0)     # a NULL function pointer
+            return
+        self._group_cb = GROUPFN(lambda user, first, num: fn(first, num))
+        self.lib.RC_SetGroupCallback(self._group_cb, None, C.c_void_p(side_stream), ngroups)
+
+    # ---- multi-GPU output placement (RC_DeviceAlloc / RC_Ipc*) ----
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        if self.lib.RC_DeviceAlloc(C.c_size_t(nbytes), C.byref(p)) != 0:
+            raise RuntimeError("RC_DeviceAlloc failed")
+        return p.value
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        if self.lib.RC_IpcExport(C.c_void_p(ptr), h) != 0:
+            raise RuntimeError("RC_IpcExport failed")
+        return bytes(h)
+
+    def ipc_import(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        if self.lib.RC_IpcImport(h, C.byref(p)) != 0:
+            raise RuntimeError("RC_IpcImport failed")
+        return p.value
+
+    def set_mirror_output(self, fb_ptr: int = 0, z_ptr: int = 0):
+        """RC_SetMirrorOutput: finished view groups of render_device() are also copied to fb_ptr (peer or host)."""
+        self.lib.RC_SetMirrorOutput(C.c_void_p(fb_ptr or None), C.c_void_p(z_ptr or None))
 
     def flush_caches(self):
         self.lib.RC_FlushCaches()

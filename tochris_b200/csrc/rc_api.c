@@ -526,6 +526,18 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 	return r;
 }
 
+void RC_SetGroupCallback (rc_group_fn fn, void *user, void *side_stream, int ngroups)
+{
+	if (rc.gpu) rc_gpu_set_group_callback (rc.gpu, fn, user, side_stream, ngroups);
+}
+
+int  RC_DeviceAlloc (size_t bytes, void **ptr) { return rc.gpu ? rc_gpu_device_alloc (rc.gpu, bytes, ptr) : RC_ERR_ARG; }
+void RC_DeviceFree (void *ptr) { if (rc.gpu) rc_gpu_device_free (rc.gpu, ptr); }
+int  RC_IpcExport (void *ptr, unsigned char handle[64]) { return rc.gpu ? rc_gpu_ipc_export (rc.gpu, ptr, handle) : RC_ERR_ARG; }
+int  RC_IpcImport (const unsigned char handle[64], void **ptr) { return rc.gpu ? rc_gpu_ipc_import (rc.gpu, handle, ptr) : RC_ERR_ARG; }
+void RC_IpcClose (void *ptr) { if (rc.gpu) rc_gpu_ipc_close (rc.gpu, ptr); }
+void RC_SetMirrorOutput (void *fb, void *z) { if (rc.gpu) rc_gpu_set_mirror (rc.gpu, fb, z); }
+
 int RC_SetSkybox (const char *name)
 {
 	/* R_LoadSkybox, r_sky.c:138-187 */

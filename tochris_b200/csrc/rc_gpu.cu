@@ -80,6 +80,8 @@ struct rc_gpu_s {
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
+	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
+	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
@@ -1001,7 +1003,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaStreamCreateWithFlags (&g->sidestream, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
-	g->host_fb = NULL; g->host_z = NULL;
+	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
 
 	std::vector<int> st (RC_SIN_BUFFER_SIZE), ist (RC_SIN_BUFFER_SIZE);
@@ -1147,6 +1149,40 @@ int rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, in
 void rc_gpu_flush_caches (rc_gpu_t *g)
 {
 	g->flush_pending = 1;
+}
+
+int rc_gpu_device_alloc (rc_gpu_t *g, size_t bytes, void **ptr)
+{
+	cudaSetDevice (g->device);
+	return cudaMalloc (ptr, bytes) == cudaSuccess ? RC_OK : RC_ERR_CUDA;
+}
+
+void rc_gpu_device_free (rc_gpu_t *g, void *ptr) { cudaSetDevice (g->device); cudaFree (ptr); }
+
+int rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle)
+{
+	cudaIpcMemHandle_t h;
+	static_assert (sizeof(h) == 64, "CUDA IPC handle size");
+	cudaSetDevice (g->device);
+	if (cudaIpcGetMemHandle (&h, ptr) != cudaSuccess) return RC_ERR_CUDA;
+	memcpy (handle, &h, sizeof(h));
+	return RC_OK;
+}
+
+int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr)
+{
+	cudaIpcMemHandle_t h;
+	cudaSetDevice (g->device);
+	memcpy (&h, handle, sizeof(h));
+	return cudaIpcOpenMemHandle (ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? RC_OK : RC_ERR_CUDA;
+}
+
+void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { cudaSetDevice (g->device); cudaIpcCloseMemHandle (ptr); }
+void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { g->mirror_fb = (uint8_t *)fb; g->mirror_z = (int16_t *)z; }
+
+void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)
+{
+	g->groupfn = fn; g->groupuser = user; g->groupstream = (cudaStream_t)side_stream; g->ngroups = ngroups;
 }
 
 int rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen)
@@ -1321,13 +1357,14 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	}
 	const bool entities = g->cur_batch && g->cur_batch->nzres;
 	bool grouped = false;
-	if (g->host_fb && !entities && !anywarp && n >= 8)
+	if ((g->host_fb || g->groupfn) && !entities && !anywarp && n >= 8)
 	{
+		/* the views are drawn in groups and every finished group is handed to its consumer on a second
+		 * stream while the next one is drawn: the D2H copy of the host-output path (PCIe: the longest single
+		 * item of a batch), or whatever the caller's callback enqueues (bench.py: the NCCL gather) */
 		grouped = true;
-		/* host-output path: the D2H copy (PCIe) is the longest single item of a batch, so the views are
-		 * drawn in groups and every finished group is copied out on a second stream while the next
-		 * one is drawn */
-		const int ngroups = n >= 32 ? 4 : 2;
+		const int ngroups = g->host_fb ? (n >= 32 ? 4 : 2) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
+		cudaStream_t side = g->host_fb ? g->copystream : g->groupstream;
 		const size_t px = (size_t)g->width * g->height;
 		for (int gi = 0; gi < ngroups; gi++)
 		{
@@ -1337,15 +1374,23 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
 			k_draw<false><<<ctas, 128, 0, s>>> (w, f);
 			cudaEventRecord (g->evgroup[gi], s);
-			cudaStreamWaitEvent (g->copystream, g->evgroup[gi], 0);
-			const size_t ofs = px * (size_t)(first_view + f.drawview0);
-			CK (cudaMemcpyAsync (g->host_fb + ofs, fb + px * f.drawview0, px * nv, cudaMemcpyDeviceToHost, g->copystream));
-			if (g->host_z)
-				CK (cudaMemcpyAsync (g->host_z + ofs, zb + px * f.drawview0, px * nv * sizeof(int16_t), cudaMemcpyDeviceToHost, g->copystream));
+			cudaStreamWaitEvent (side, g->evgroup[gi], 0);
+			if (g->host_fb)
+			{
+				const size_t ofs = px * (size_t)(first_view + f.drawview0);
+				CK (cudaMemcpyAsync (g->host_fb + ofs, fb + px * f.drawview0, px * nv, cudaMemcpyDefault, side));
+				if (g->host_z)
+					CK (cudaMemcpyAsync (g->host_z + ofs, zb + px * f.drawview0, px * nv * sizeof(int16_t), cudaMemcpyDefault, side));
+			}
+			else
+				g->groupfn (g->groupuser, first_view + f.drawview0, nv);
 		}
 		g->stats.kernel_launches += ngroups - 1;
-		cudaEventRecord (g->evcopy, g->copystream);
-		cudaStreamWaitEvent (s, g->evcopy, 0);		/* the stream's work is complete only when the copies are */
+		if (g->host_fb)
+		{
+			cudaEventRecord (g->evcopy, side);
+			cudaStreamWaitEvent (s, g->evcopy, 0);		/* the stream's work is complete only when the copies are */
+		}
 	}
 	else
 	{
@@ -1396,13 +1441,20 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		k_warp<<<gw2, 128, 0, s>>> (w, f);
 		g->stats.kernel_launches++;
 	}
+	if (g->groupfn && !g->host_fb && !grouped)
+	{
+		/* one group: the whole chunk, after the entity / warp kernels */
+		cudaEventRecord (g->evgroup[0], s);
+		cudaStreamWaitEvent (g->groupstream, g->evgroup[0], 0);
+		g->groupfn (g->groupuser, first_view, n);
+	}
 	if (g->host_fb && !grouped)
 	{
 		/* entity / warp kernels touched the frame after the draw: one copy at the end of the chunk */
 		const size_t px = (size_t)g->width * g->height;
-		CK (cudaMemcpyAsync (g->host_fb + px * first_view, fb, px * n, cudaMemcpyDeviceToHost, s));
+		CK (cudaMemcpyAsync (g->host_fb + px * first_view, fb, px * n, cudaMemcpyDefault, s));
 		if (g->host_z)
-			CK (cudaMemcpyAsync (g->host_z + px * first_view, zb, px * n * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+			CK (cudaMemcpyAsync (g->host_z + px * first_view, zb, px * n * sizeof(int16_t), cudaMemcpyDefault, s));
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
 	g->stats.kernel_launches += 6;
@@ -1448,6 +1500,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	const rc_view_t *views = batch->views;
 	const int n = batch->n;
 	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	const bool mirrored = !g->host_fb && g->mirror_fb;
+	if (mirrored) { g->host_fb = g->mirror_fb; g->host_z = z_dev ? g->mirror_z : NULL; }
+	struct unmirror_t { rc_gpu_t *g; bool on; ~unmirror_t () { if (on) { g->host_fb = NULL; g->host_z = NULL; } } } unmirror = { g, mirrored };
 	size_t px = (size_t)g->width * g->height;
 	int st = 0;
 	if (!g->haveworld) { snprintf (err, errlen, "no world loaded"); return RC_ERR_NOWORLD; }

@@ -139,6 +139,13 @@ int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_
 int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
 void rc_gpu_flush_caches (rc_gpu_t *g);
+int  rc_gpu_device_alloc (rc_gpu_t *g, size_t bytes, void **ptr);
+void rc_gpu_device_free (rc_gpu_t *g, void *ptr);
+int  rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle);
+int  rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr);
+void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr);
+void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z);
+void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups);
 /* pixels: six 256x256 pictures in r_skysideimage order, or NULL to switch the sky box off */
 int  rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen);
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out);
