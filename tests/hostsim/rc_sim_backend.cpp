@@ -36,6 +36,7 @@ struct rc_gpu_s {
 	std::vector<int> stverts, atris;
 	std::vector<uint8_t> poseverts, skinpixels;
 	std::vector<float> anormdots;
+	std::vector<uint8_t> spritepixels;
 	int maxverts, maxtris;
 };
 
@@ -92,6 +93,18 @@ int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const floa
 		a->device_index = i;
 		if (a->numverts > g->maxverts) g->maxverts = a->numverts;
 		if (a->numtris > g->maxtris) g->maxtris = a->numtris;
+	}
+	return RC_OK;
+}
+
+int rc_gpu_upload_sprites (rc_gpu_t *g, rc_hostsprite_t **models, int n, char *err, size_t errlen)
+{
+	(void)err; (void)errlen;
+	g->spritepixels.clear ();
+	for (int i = 0; i < n; i++)
+	{
+		models[i]->device_ofs = (int)g->spritepixels.size ();
+		g->spritepixels.insert (g->spritepixels.end (), models[i]->pixels, models[i]->pixels + models[i]->pixelbytes);
 	}
 	return RC_OK;
 }
@@ -243,6 +256,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		for (int v = 0; v < g->amodels[batch->alias[ii].model].numverts; v++) rc_alias_vertex (&f, ii, v);
 	for (int ii = 0; ii < batch->nalias; ii++)
 		for (int t = 0; t < g->amodels[batch->alias[ii].model].numtris; t++) rc_alias_triangle (&f, ii, t);
+	f.sprites = batch->sprites; f.nsprites = batch->nsprites; f.spritepixels = g->spritepixels.data ();
+	for (int si = 0; si < batch->nsprites; si++)
+		for (int k = 0; k <= g->height; k++) rc_sprite_span (&f, si, k);
 	for (int pi = 0; pi < batch->nparticles; pi++) rc_particle (&f, pi);
 	if (batch->nzres)
 		for (int vi = 0; vi < n; vi++)

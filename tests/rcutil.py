@@ -32,6 +32,11 @@ def make_assets(basedir: str, names=None):
     views.write_base_assets(basedir)
     for suf, pcx in assets_mod.skybox_pcx("testsky").items():
         views.write_file(basedir, f"env/testsky{suf}.pcx", pcx)
+    from tochris_b200.scenes import sprgen
+    for k in range(5):        # one sprite model per orientation type (spritegn.h:82-86)
+        views.write_file(basedir, f"progs/spr{k}.spr", sprgen.sprite(sprtype=k, width=32 + 8 * k, height=24 + 8 * k, nframes=2,
+                                                                        group=(k % 2 == 0), beamlength=(6.0 if k == 1 else 0.0),
+                                                                        synctype=(1 if k == 2 else 0), seed=3 + k))
     views.write_file(basedir, "progs/ball.mdl", mdlgen.icosphere_mdl())
     views.write_file(basedir, "progs/blob.mdl", mdlgen.icosphere_mdl(seed=77, subdiv=1, radius=14.0, nframes=2,
                                                                        frame_group=False, skin_group=True, skin_w=64, skin_h=96))
@@ -51,7 +56,7 @@ def scene_info(name: str) -> dict:
 
 
 def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, entities: int = 0, particles: int = 0,
-                doors: int = 0, **kw):
+                doors: int = 0, sprites: int = 0, **kw):
     if name == "box":
         vs = views.timerefresh_views((0, 0, 0), 128)[:n] if n <= 128 else views.timerefresh_views((0, 0, 0), n)
     else:
@@ -62,6 +67,8 @@ def scene_views(name: str, n: int, dlights: int = 0, underwater_every: int = 0, 
         add_doors(vs, scene_info(name), doors)
     if entities:
         add_entities(vs, entities)
+    if sprites:
+        add_sprites(vs, sprites)
     if particles:
         add_particles(vs, particles)
     if underwater_every:
@@ -110,6 +117,26 @@ def add_entities(specs, k: int, near: float = 40.0):
             sp.entities.append(views.EntitySpec(model, (ox, oy, oz), (views.halton(h, 7) * 30 - 15, views.halton(h, 11) * 360, 0.0),
                                                 frame=j % nfr, oldframe=(j + 1) % nfr, framelerp=views.halton(h, 13),
                                                 flags=(8 if j % 5 == 0 else 0) | (16 if j % 7 == 3 else 0)))
+
+
+def add_sprites(specs, k: int, near: float = 30.0):
+    """k sprite entities per view (all five orientation types, single frames and groups), interleaved with the
+    alias entities already in the list so that the shared draw order matters."""
+    import math
+    for i, sp in enumerate(specs):
+        ents = list(sp.entities)
+        yaw = math.radians(sp.angles[1])
+        for j in range(k):
+            h = i * 61 + j * 17 + 7
+            ang = yaw + (views.halton(h, 2) - 0.5) * 1.6
+            dist = near + views.halton(h, 3) * 220.0
+            org = (sp.origin[0] + math.cos(ang) * dist, sp.origin[1] + math.sin(ang) * dist,
+                   sp.origin[2] - 16.0 + views.halton(h, 5) * 48.0)
+            e = views.EntitySpec(f"progs/spr{(i + j) % 5}.spr", org,
+                                 (views.halton(h, 7) * 40 - 20, views.halton(h, 11) * 360, views.halton(h, 13) * 90 - 45),
+                                 frame=j % 2, syncbase=views.halton(h, 17))
+            ents.insert((j * 3) % (len(ents) + 1), e)
+        sp.entities = ents
 
 
 def add_particles(specs, k: int):

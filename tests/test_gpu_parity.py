@@ -25,6 +25,8 @@ CASES = [
     ("full", 640, 480, 16, 1.1, 0.2, dict(doors=2, entities=10, particles=100, underwater_every=4)),
     ("full", 320, 240, 64, 0.37, 0.173, dict(skybox="testsky")),             # loadsky: the six sky-box faces
     ("full", 640, 480, 12, 1.1, 0.3, dict(skybox="testsky", doors=2, entities=6, dlights=2, underwater_every=5)),
+    ("multi", 320, 240, 48, 0.3, 0.21, dict(sprites=12)),                     # sprite entities
+    ("full", 640, 480, 12, 0.9, 0.17, dict(sprites=10, entities=8, particles=100, doors=2, underwater_every=5)),
 ]
 
 

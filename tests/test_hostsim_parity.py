@@ -23,6 +23,8 @@ CASES = [
     ("full", 400, 300, 6, 2.0, 0.3, dict(doors=2, entities=6, particles=50)),
     ("full", 320, 240, 24, 0.37, 0.173, dict(skybox="testsky")),                     # loadsky: six box faces instead of the scrolling sky
     ("full", 400, 300, 8, 1.1, 0.3, dict(skybox="testsky", doors=2, entities=6, dlights=2)),
+    ("multi", 320, 240, 12, 0.3, 0.21, dict(sprites=10)),                             # sprite entities: five orientation types, groups
+    ("full", 400, 300, 8, 0.9, 0.17, dict(sprites=8, entities=6, particles=60, doors=2)),
 ]
 
 

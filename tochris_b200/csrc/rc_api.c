@@ -38,6 +38,8 @@ static struct {
 	uint8_t     *cmapscratch; int cmapscratchcap;
 	float        anorm_dots[16 * 256];
 	int          alias_dirty;		/* alias models loaded since the last device upload */
+	int          sprite_dirty;		/* ditto sprite models */
+	rc_spriteinst_t *spritescratch; int spritescratchcap;
 	rc_batch_t   batch;
 } rc;
 
@@ -166,11 +168,13 @@ void Mod_ClearAll (void)
 		if (m->type == rc_mod_brush && m->submodel == 0 && m->world)
 			RC_FreeHostWorld (m->world);
 		RC_FreeHostAlias (m->alias);
+		RC_FreeHostSprite (m->sprite);
 		free (m);
 	}
 	rc.nummodels = 0;
 	rc.world = NULL;
 	rc.alias_dirty = 1;
+	rc.sprite_dirty = 1;
 	if (rc.gpu) rc_gpu_flush_caches (rc.gpu);	/* D_FlushCaches, r_model.c:178 */
 }
 
@@ -233,6 +237,20 @@ static struct model_s *rc_load_model (const char *name)
 		m->type = rc_mod_alias; m->alias = a; m->flags = a->flags; m->numframes = a->numframes; m->synctype = a->synctype;
 		memcpy (m->mins, a->mins, sizeof(m->mins)); memcpy (m->maxs, a->maxs, sizeof(m->maxs));
 		rc.alias_dirty = 1;
+		return m;
+	}
+	if (len >= 4 && !memcmp (buf, "IDSP", 4))
+	{
+		/* Mod_LoadSpriteModel, r_model.c:1671-1741 */
+		rc_hostsprite_t *sp = RC_LoadSpriteModel (buf, len, rc.err, sizeof(rc.err));
+		free (buf);
+		if (!sp) return NULL;
+		m = rc_new_model (name);
+		if (!m) { RC_FreeHostSprite (sp); rc_fail (RC_ERR_NOMEM, "too many models"); return NULL; }
+		m->type = rc_mod_sprite; m->sprite = sp; m->flags = 0; m->numframes = sp->numframes; m->synctype = sp->synctype;
+		m->mins[0] = m->mins[1] = -sp->maxwidth/2; m->maxs[0] = m->maxs[1] = sp->maxwidth/2;
+		m->mins[2] = -sp->maxheight/2; m->maxs[2] = sp->maxheight/2;
+		rc.sprite_dirty = 1;
 		return m;
 	}
 	free (buf);
@@ -385,7 +403,7 @@ static int rc_prepare_views (const refdef_t *views, int n)
 	}
 	/* ---- entities and particles (R_DrawEntitiesOnList r_main.c:489-533, R_DrawParticles :773) ---- */
 	{
-		int nent = 0, npart = 0, nalias = 0, nverts = 0, ncmap = 1, nzres = 0, maxcmaps = 1;
+		int nent = 0, npart = 0, nalias = 0, nverts = 0, ncmap = 1, nzres = 0, maxcmaps = 1, nsprites = 0;
 		const byte *cmaps[64];
 		rc_hostalias_t *amodels[RC_MAX_MODELS];
 		int namodels = 0;
@@ -393,6 +411,24 @@ static int rc_prepare_views (const refdef_t *views, int n)
 		{
 			nent += views[i].num_entities > 0 ? views[i].num_entities : 0;
 			npart += views[i].num_particles > 0 ? views[i].num_particles : 0;
+		}
+		if (rc.sprite_dirty && nent)
+		{
+			rc_hostsprite_t *smodels[RC_MAX_MODELS];
+			int nsm = 0;
+			for (i = 0; i < rc.nummodels; i++)
+				if (rc.models[i]->type == rc_mod_sprite)
+					smodels[nsm++] = rc.models[i]->sprite;
+			if (rc_gpu_upload_sprites (rc.gpu, smodels, nsm, rc.err, sizeof(rc.err)) != RC_OK)
+				return RC_ERR_CUDA;
+			rc.sprite_dirty = 0;
+		}
+		if (nent > rc.spritescratchcap)
+		{
+			free (rc.spritescratch);
+			rc.spritescratch = (rc_spriteinst_t *)malloc (sizeof(rc_spriteinst_t) * nent);
+			rc.spritescratchcap = rc.spritescratch ? nent : 0;
+			if (!rc.spritescratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
 		}
 		if (rc.alias_dirty && nent)
 		{
@@ -434,17 +470,28 @@ static int rc_prepare_views (const refdef_t *views, int n)
 					int c;
 					if (!mod) continue;
 					if ((e->flags & RF_WEAPONMODEL) && !rc.cvars.r_drawviewmodel) continue;
-					if (mod->type != rc_mod_alias)
-					{
-						if (mod->type == rc_mod_sprite) rc.unsupported = 1;
+					if (mod->type != rc_mod_alias && mod->type != rc_mod_sprite)
 						continue;		/* brush entities are handled with the world (R_DrawBEntitiesOnList) */
-					}
 					if (e->flags & RF_CULLVIS)
 					{
 						float mins[3], maxs[3];
 						for (c = 0; c < 3; c++) { mins[c] = e->origin[c] + mod->mins[c]; maxs[c] = e->origin[c] + mod->maxs[c]; }
 						if (!rc.world || !RC_VisCullEntity (rc.world->world, views[i].vieworg, mins, maxs))
 							continue;
+					}
+					if (mod->type == rc_mod_sprite)
+					{
+						/* R_DrawSprite, r_sprite.c:288-403 */
+						rc_spriteinst_t *si = &rc.spritescratch[nsprites];
+						if (!RC_SpriteSetup (mod->sprite, e, &views[i], v, mod->synctype, si))
+							continue;
+						si->view = i;
+						si->order = ++order;
+						si->pixofs += mod->sprite->device_ofs;
+						nsprites++;
+						used = 1;
+						if (order >= 32767) return rc_fail (RC_ERR_ARG, "view %d: too many entities", i);
+						continue;
 					}
 					inst = &rc.aliasscratch[nalias];
 					if (!RC_AliasSetup (mod->alias, rc.world ? rc.world->world : NULL, e, &views[i], v, &rc.cvars, inst))
@@ -496,6 +543,7 @@ static int rc_prepare_views (const refdef_t *views, int n)
 			memcpy (rc.cmapscratch + (size_t)i * 16384, cmaps[i], 16384);
 		rc.batch.alias = rc.aliasscratch; rc.batch.nalias = nalias; rc.batch.nfinalverts = nverts; rc.batch.ntriwork = 0;
 		rc.batch.particles = rc.partscratch; rc.batch.nparticles = npart;
+		rc.batch.sprites = rc.spritescratch; rc.batch.nsprites = nsprites;
 		rc.batch.colormaps = rc.cmapscratch; rc.batch.ncolormaps = ncmap;
 		rc.batch.nzres = nzres;
 	}

@@ -70,6 +70,7 @@ struct rc_gpu_s {
 	rc_aliasinst_t *d_alias; int aliascap;
 	rc_finalvert_t *d_finalverts; int finalvertcap;
 	rc_particle_t *d_particles; int particlecap;
+	rc_spriteinst_t *d_sprites; int spritecap; uint8_t *d_spritepixels;
 	uint8_t *d_colormaps; int colormapcap;
 	unsigned long long *d_zres; size_t zrescap;
 	int16_t *d_zscratch; size_t zscratchcap;
@@ -937,6 +938,11 @@ __global__ void k_alias_tris (const __grid_constant__ rc_frame_t f)
 	rc_alias_triangle (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void k_sprites (const __grid_constant__ rc_frame_t f)
+{
+	rc_sprite_span (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 __global__ void k_particles (const __grid_constant__ rc_frame_t f)
 {
 	int pi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,7 +995,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
-	g->d_particles = NULL; g->particlecap = 0; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
+	g->d_particles = NULL; g->particlecap = 0; g->d_sprites = NULL; g->spritecap = 0; g->d_spritepixels = NULL; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
 	cudaFuncSetAttribute (k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t));
 	cudaFuncSetAttribute (k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -1058,6 +1064,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_cachepool); cudaFree (g->d_cachekeys); cudaFree (g->d_cachevals);
 	cudaFree (g->d_alloc); cudaFree (g->d_status); cudaFree (g->d_sintable); cudaFree (g->d_intsintable);
 	cudaFree (g->d_fb); cudaFree (g->d_zb); cudaFree (g->d_dlights); cudaFree (g->d_warpbuf);
+	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
 	delete g;
@@ -1105,6 +1112,23 @@ int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const floa
 		CK (cudaMemcpy (g->d_skinpixels, skin.data (), skin.size (), cudaMemcpyHostToDevice));
 	}
 	CK (cudaMemcpy (g->d_anormdots, anorm_dots, sizeof(float) * 16 * 256, cudaMemcpyHostToDevice));
+	return RC_OK;
+}
+
+int rc_gpu_upload_sprites (rc_gpu_t *g, rc_hostsprite_t **models, int n, char *err, size_t errlen)
+{
+	std::vector<uint8_t> pix;
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	for (int i = 0; i < n; i++)
+	{
+		models[i]->device_ofs = (int)pix.size ();
+		pix.insert (pix.end (), models[i]->pixels, models[i]->pixels + models[i]->pixelbytes);
+	}
+	cudaFree (g->d_spritepixels); g->d_spritepixels = NULL;
+	CK (cudaMalloc (&g->d_spritepixels, pix.size () + 16));
+	if (!pix.empty ())
+		CK (cudaMemcpy (g->d_spritepixels, pix.data (), pix.size (), cudaMemcpyHostToDevice));
 	return RC_OK;
 }
 
@@ -1424,6 +1448,22 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			k_alias_tris<<<gt, 64, 0, s>>> (f2);
 			g->stats.kernel_launches += 2;
 		}
+		{
+			/* sprite entities of this chunk's views (ordered by view) */
+			int slo = 0, shi;
+			while (slo < b->nsprites && b->sprites[slo].view < first_view) slo++;
+			shi = slo;
+			while (shi < b->nsprites && b->sprites[shi].view < first_view + n) shi++;
+			for (int first = slo; first < shi; first += 32768)
+			{
+				int cnt = shi - first < 32768 ? shi - first : 32768;
+				rc_frame_t f4 = f;
+				f4.sprites = g->d_sprites + first; f4.nsprites = cnt; f4.spritepixels = g->d_spritepixels;
+				dim3 gsprite ((g->height + 1 + 63) / 64, cnt);
+				k_sprites<<<gsprite, 64, 0, s>>> (f4);
+				g->stats.kernel_launches++;
+			}
+		}
 		if (phi > plo)
 		{
 			rc_frame_t f3 = f;
@@ -1542,6 +1582,13 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		cudaFree (g->d_finalverts); g->finalvertcap = batch->nfinalverts + 4096;
 		CK (cudaMalloc (&g->d_finalverts, sizeof(rc_finalvert_t) * (size_t)g->finalvertcap));
 	}
+	if (batch->nsprites > g->spritecap)
+	{
+		cudaFree (g->d_sprites); g->spritecap = batch->nsprites + 256;
+		CK (cudaMalloc (&g->d_sprites, sizeof(rc_spriteinst_t) * (size_t)g->spritecap));
+	}
+	if (batch->nsprites)
+		CK (cudaMemcpyAsync (g->d_sprites, batch->sprites, sizeof(rc_spriteinst_t) * batch->nsprites, cudaMemcpyHostToDevice, s));
 	if (batch->nparticles > g->particlecap)
 	{
 		cudaFree (g->d_particles); g->particlecap = batch->nparticles + 4096;

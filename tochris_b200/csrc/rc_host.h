@@ -70,6 +70,18 @@ typedef struct rc_hostalias_s {  /* aliashdr_t + mdl_t, flattened */
     int   device_index;        /* slot in the device model table, -1 until uploaded */
 } rc_hostalias_t;
 
+typedef struct { int type; int first, count; int intervals; } rc_spriteframe_t;   /* mspriteframedesc_t: single (0) or group */
+typedef struct { int width, height; float up, down, left, right; int pixofs; } rc_spritesub_t;   /* mspriteframe_t */
+typedef struct rc_hostsprite_s {   /* msprite_t (r_model.h:194-203), flattened */
+    int   type, maxwidth, maxheight, numframes, synctype;
+    float beamlength;
+    rc_spriteframe_t *frames;
+    rc_spritesub_t   *subframes; int numsubframes;
+    float *intervals;
+    unsigned char *pixels; size_t pixelbytes;
+    int   device_ofs;          /* offset of pixels[] in the device sprite blob, -1 until uploaded */
+} rc_hostsprite_t;
+
 struct model_s {
     char          name[64];
     rc_modtype_t  type;
@@ -81,6 +93,7 @@ struct model_s {
     int           submodel;    /* index into world->submodels */
     /* alias: filled by rc_host_alias.c */
     rc_hostalias_t *alias;
+    rc_hostsprite_t *sprite;
     int           synctype;
 };
 
@@ -109,6 +122,9 @@ int  RC_AliasSetup (const rc_hostalias_t *a, const rc_hostworld_t *hw, const ent
 int  RC_BmodelSetup (const rc_hostworld_t *hw, int submodel, const entity_t *e, const rc_refdef_t *rd, const rc_view_t *v,
                      float pixelAspect, rc_bent_t *out);
 int  RC_PointInLeaf (const rc_hostworld_t *hw, const float *p);
+rc_hostsprite_t *RC_LoadSpriteModel (const void *data, size_t len, char *err, size_t errlen);
+void RC_FreeHostSprite (rc_hostsprite_t *s);
+int  RC_SpriteSetup (const rc_hostsprite_t *s, const entity_t *e, const rc_refdef_t *rd, const rc_view_t *v, int synctype, rc_spriteinst_t *out);
 unsigned char *RC_DecodePCX (const void *data, size_t len, int *width, int *height);
 
 /* ---- GPU side (rc_gpu.cu) ----------------------------------------------------------- */
@@ -125,6 +141,7 @@ typedef struct {
     const uint8_t *colormaps;    int ncolormaps;  /* entity colormaps (16 KB each); 0 = vid.colormap */
     int nzres;                   /* views that need an entity z-resolve plane */
     const rc_bent_t *bents; int nbents;           /* drawn brush entities, ordered by (view, entity) */
+    const rc_spriteinst_t *sprites; int nsprites; /* drawn sprite entities, ordered by (view, entity) */
     int maxbfaces;               /* largest face count among them */
 } rc_batch_t;
 
@@ -132,6 +149,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 void rc_gpu_destroy (rc_gpu_t *g);
 /* (re)uploads every loaded alias model; models[i]->device_index = i */
 int  rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const float *anorm_dots, char *err, size_t errlen);
+/* (re)uploads the pixels of every loaded sprite model; models[i]->device_ofs is set */
+int  rc_gpu_upload_sprites (rc_gpu_t *g, rc_hostsprite_t **models, int n, char *err, size_t errlen);
 int  rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, int maxsurfs, char *err, size_t errlen);
 /* renders n prepared views; fb_dev/z_dev are device pointers (z may be NULL) */
 int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,

@@ -105,6 +105,8 @@ typedef struct {
     const uint8_t *colormaps;     /* [ncolormaps][16384]; 0 = vid.colormap */
     rc_finalvert_t *finalverts;
     const rc_particle_t *particles; int nparticles;
+    const rc_spriteinst_t *sprites; int nsprites;   /* drawn sprite entities */
+    const uint8_t *spritepixels;  /* frames of every loaded sprite model */
     /* brush entities */
     const rc_bent_t *bents; int nbents;
     int bentbase;                 /* first brush entity handled by this launch */
@@ -2923,6 +2925,280 @@ RC_HD void rc_particle (const rc_frame_t *f, int pi)
 			if ((unsigned)x < (unsigned)f->width && (unsigned)y < (unsigned)f->height)
 				RC_ATOMIC_MAX_ULL (&zplane[(size_t)y * f->width + x], key);
 		}
+}
+
+/* ---- sprites (ref_soft/r_sprite.c, d_sprite.c) ---------------------------------------------- */
+#define RC_SPRITE_VERTS 12	/* MAXWORKINGVERTS: a quad clipped by four planes has at most 8 */
+
+/* R_ClipSpriteFace, r_sprite.c:57-123: clips the winding in `in` (nump x {x,y,z,s,t}) to one plane */
+RC_HD int rc_sprite_clip (const float *normal, float clipdist, float (*in)[5], float (*outv)[5], int nump)
+{
+	float dists[RC_SPRITE_VERTS + 1];
+	int outcount = 0;
+	for (int i = 0; i < nump; i++)
+		dists[i] = rc_dot3 (in[i], normal) - clipdist;
+	dists[nump] = dists[0];
+	for (int q = 0; q < 5; q++) in[nump][q] = in[0][q];
+	for (int i = 0; i < nump; i++)
+	{
+		if (dists[i] >= 0)
+		{
+			for (int q = 0; q < 5; q++) outv[outcount][q] = in[i][q];
+			outcount++;
+		}
+		if (dists[i] == 0 || dists[i+1] == 0)
+			continue;
+		if ((dists[i] > 0) == (dists[i+1] > 0))
+			continue;
+		const float frac = dists[i] / (dists[i] - dists[i+1]);
+		for (int q = 0; q < 5; q++)
+			outv[outcount][q] = in[i][q] + frac*(in[i+1][q] - in[i][q]);
+		outcount++;
+	}
+	return outcount;
+}
+
+/* One thread per (drawn sprite, span index k): R_SetupAndDrawSprite (r_sprite.c:131-226) and
+ * D_DrawSprite (d_sprite.c:388-441) up to the span list are recomputed by every thread of the sprite
+ * (a few hundred operations), then the thread draws the k-th span of the list with D_SpriteDrawSpans
+ * (d_sprite.c:36-196): perspective texturing with the 8-pixel subdivision, texel 255 transparent,
+ * z test `*pz <= izi >> 16` -- here one atomicMax of (z, draw order, colour) per opaque pixel into
+ * the view's resolve plane, like the alias rasteriser. */
+RC_HD void rc_sprite_span (const rc_frame_t *f, int si, int k)
+{
+	const rc_spriteinst_t *sp = &f->sprites[si];
+	const rc_view_t *vw = &f->views[sp->view - f->viewbase];
+	float cv[2][RC_SPRITE_VERTS + 1][5];
+	float pu[RC_SPRITE_VERTS + 1], pv[RC_SPRITE_VERTS + 1];
+
+	/* backface cull */
+	if (rc_dot3 (sp->vpn, sp->modelorg) >= 0)
+		return;
+	/* the poster in world space */
+	float right[3], up[3], left[3], down[3];
+	for (int i = 0; i < 3; i++)
+	{
+		right[i] = sp->vright[i] * sp->right; up[i] = sp->vup[i] * sp->up;
+		left[i] = sp->vright[i] * sp->left; down[i] = sp->vup[i] * sp->down;
+	}
+	const float sprite_width = (float)sp->width, sprite_height = (float)sp->height;
+	for (int i = 0; i < 3; i++)
+	{
+		cv[0][0][i] = sp->entorigin[i] + up[i] + left[i];
+		cv[0][1][i] = sp->entorigin[i] + up[i] + right[i];
+		cv[0][2][i] = sp->entorigin[i] + down[i] + right[i];
+		cv[0][3][i] = sp->entorigin[i] + down[i] + left[i];
+	}
+	cv[0][0][3] = 0; cv[0][0][4] = 0;
+	cv[0][1][3] = sprite_width; cv[0][1][4] = 0;
+	cv[0][2][3] = sprite_width; cv[0][2][4] = sprite_height;
+	cv[0][3][3] = 0; cv[0][3][4] = sprite_height;
+	/* clip to the frustum in world space */
+	int nump = 4, cur = 0;
+	for (int i = 0; i < 4; i++)
+	{
+		nump = rc_sprite_clip (vw->clipnormal[i], vw->clipdist[i], cv[cur], cv[cur ^ 1], nump);
+		cur ^= 1;
+		if (nump < 3)
+			return;
+		if (nump >= RC_SPRITE_VERTS)
+			return;		/* the reference: Sys_Error ("too many points") */
+	}
+	/* transform into view space and project */
+	for (int i = 0; i < nump; i++)
+	{
+		float local[3], t[3];
+		local[0] = cv[cur][i][0] - vw->origin[0]; local[1] = cv[cur][i][1] - vw->origin[1]; local[2] = cv[cur][i][2] - vw->origin[2];
+		rc_transform_vector (vw, local, t);
+		if (t[2] < RC_NEAR_CLIP)
+			t[2] = RC_NEAR_CLIP;
+		const float zi = 1.0 / t[2];
+		float scale = vw->xscale * zi;
+		pu[i] = (vw->xcenter + scale * t[0]);
+		scale = vw->yscale * zi;
+		pv[i] = (vw->ycenter - scale * t[1]);
+	}
+	/* D_DrawSprite: top and bottom vertices */
+	float ymin = 999999.9, ymax = -999999.9;
+	int minindex = 0, maxindex = 0;
+	for (int i = 0; i < nump; i++)
+	{
+		if (pv[i] < ymin) { ymin = pv[i]; minindex = i; }
+		if (pv[i] > ymax) { ymax = pv[i]; maxindex = i; }
+	}
+	ymin = ceil ((double)ymin);
+	ymax = ceil ((double)ymax);
+	if (ymin >= ymax)
+		return;
+	pu[nump] = pu[0]; pv[nump] = pv[0];
+
+	/* D_SpriteScanLeftEdge, d_sprite.c:204-258: the k-th entry of the span list */
+	int span_u = 0, span_v = 0, haveleft = 0;
+	{
+		int i = minindex, lmaxindex = maxindex, n = 0;
+		if (i == 0) i = nump;
+		if (lmaxindex == 0) lmaxindex = nump;
+		float vtop = ceil ((double)pv[i]);
+		do
+		{
+			const float vbottom = ceil ((double)pv[i - 1]);
+			if (vtop < vbottom)
+			{
+				const float du = pu[i - 1] - pu[i], dv = pv[i - 1] - pv[i];
+				const float slope = du / dv;
+				const int u_step = rc_f2i (slope * 0x10000);
+				const int u = rc_addw (rc_f2i ((pu[i] + (slope * (vtop - pv[i]))) * 0x10000), (0x10000 - 1));
+				const int itop = rc_f2i (vtop), ibottom = rc_f2i (vbottom);
+				if (!haveleft && k < n + (ibottom - itop))
+				{
+					const int j = k - n;
+					span_u = rc_addw (u, rc_mulw (j, u_step)) >> 16;
+					span_v = itop + j;
+					haveleft = 1;
+				}
+				n += ibottom - itop;
+			}
+			vtop = vbottom;
+			i--;
+			if (i == 0) i = nump;
+		} while (i != lmaxindex);
+	}
+	/* D_SpriteScanRightEdge, d_sprite.c:266-338 */
+	int span_count = 0, haveright = 0;
+	{
+		int i = minindex, n = 0;
+		float vvert = pv[i];
+		if (vvert < vw->fvrecty_adj) vvert = vw->fvrecty_adj;
+		if (vvert > vw->fvrectbottom_adj) vvert = vw->fvrectbottom_adj;
+		float vtop = ceil ((double)vvert);
+		do
+		{
+			float vnext = pv[i + 1];
+			if (vnext < vw->fvrecty_adj) vnext = vw->fvrecty_adj;
+			if (vnext > vw->fvrectbottom_adj) vnext = vw->fvrectbottom_adj;
+			const float vbottom = ceil ((double)vnext);
+			if (vtop < vbottom)
+			{
+				float uvert = pu[i], unext = pu[i + 1];
+				if (uvert < vw->fvrectx_adj) uvert = vw->fvrectx_adj;
+				if (uvert > vw->fvrectright_adj) uvert = vw->fvrectright_adj;
+				if (unext < vw->fvrectx_adj) unext = vw->fvrectx_adj;
+				if (unext > vw->fvrectright_adj) unext = vw->fvrectright_adj;
+				const float du = unext - uvert, dv = vnext - vvert;
+				const float slope = du / dv;
+				const int u_step = rc_f2i (slope * 0x10000);
+				const int u = rc_addw (rc_f2i ((uvert + (slope * (vtop - vvert))) * 0x10000), (0x10000 - 1));
+				const int itop = rc_f2i (vtop), ibottom = rc_f2i (vbottom);
+				if (!haveright && k < n + (ibottom - itop))
+				{
+					span_count = (rc_addw (u, rc_mulw (k - n, u_step)) >> 16) - span_u;
+					haveright = 1;
+				}
+				n += ibottom - itop;
+			}
+			vtop = vbottom;
+			vvert = vnext;
+			i++;
+			if (i == nump) i = 0;
+		} while (i != maxindex);
+	}
+	if (!haveright)
+		return;				/* past DS_SPAN_LIST_END */
+	if (!haveleft)
+	{
+		/* the reference would read a span the left scan never wrote (stack garbage) */
+		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		return;
+	}
+	if (span_count <= 0)
+		return;
+
+	/* D_SpriteCalculateGradients, d_sprite.c:346-381 */
+	float p_normal[3], p_saxis[3], p_taxis[3], p_temp1[3];
+	rc_transform_vector (vw, sp->vpn, p_normal);
+	rc_transform_vector (vw, sp->vright, p_saxis);
+	rc_transform_vector (vw, sp->vup, p_taxis);
+	p_taxis[0] = -p_taxis[0]; p_taxis[1] = -p_taxis[1]; p_taxis[2] = -p_taxis[2];
+	const float distinv = 1.0 / (-rc_dot3 (sp->modelorg, sp->vpn));
+	const float d_sdivzstepu = p_saxis[0] * vw->xscaleinv, d_tdivzstepu = p_taxis[0] * vw->xscaleinv;
+	const float d_sdivzstepv = -p_saxis[1] * vw->yscaleinv, d_tdivzstepv = -p_taxis[1] * vw->yscaleinv;
+	const float d_zistepu = p_normal[0] * vw->xscaleinv * distinv, d_zistepv = -p_normal[1] * vw->yscaleinv * distinv;
+	const float d_sdivzorigin = p_saxis[2] - vw->xcenter * d_sdivzstepu - vw->ycenter * d_sdivzstepv;
+	const float d_tdivzorigin = p_taxis[2] - vw->xcenter * d_tdivzstepu - vw->ycenter * d_tdivzstepv;
+	const float d_ziorigin = p_normal[2] * distinv - vw->xcenter * d_zistepu - vw->ycenter * d_zistepv;
+	rc_transform_vector (vw, sp->modelorg, p_temp1);
+	const int cachewidth = sp->width, sheight = sp->height;
+	const int sadjust = rc_d2i (rc_dot3 (p_temp1, p_saxis) * 0x10000 + 0.5) - (-(cachewidth >> 1) << 16);
+	const int tadjust = rc_d2i (rc_dot3 (p_temp1, p_taxis) * 0x10000 + 0.5) - (-(sheight >> 1) << 16);
+	const int bbextents = (cachewidth << 16) - 1, bbextentt = (sheight << 16) - 1;
+
+	/* D_SpriteDrawSpans, d_sprite.c:36-196, one span */
+	if ((unsigned)span_v >= (unsigned)f->height)
+		return;
+	const uint8_t *pbase = f->spritepixels + sp->pixofs;
+	unsigned long long *zrow = f->zres + (size_t)vw->zres_index * f->width * f->height + (size_t)span_v * f->width;
+	const unsigned long long orderbits = ((unsigned long long)sp->order << 24) << 8;
+	const float sdivz8stepu = d_sdivzstepu * 8, tdivz8stepu = d_tdivzstepu * 8, zi8stepu = d_zistepu * 8;
+	const int izistep = rc_f2i (d_zistepu * 0x8000 * 0x10000);
+	int count = span_count, x = span_u;
+	const float du = (float)span_u, dv = (float)span_v;
+	float sdivz = d_sdivzorigin + dv*d_sdivzstepv + du*d_sdivzstepu;
+	float tdivz = d_tdivzorigin + dv*d_tdivzstepv + du*d_tdivzstepu;
+	float zi = d_ziorigin + dv*d_zistepv + du*d_zistepu;
+	float z = (float)0x10000 / zi;
+	int izi = rc_f2i (zi * 0x8000 * 0x10000);
+	int s = rc_addw (rc_f2i (sdivz * z), sadjust);
+	if (s > bbextents) s = bbextents; else if (s < 0) s = 0;
+	int t = rc_addw (rc_f2i (tdivz * z), tadjust);
+	if (t > bbextentt) t = bbextentt; else if (t < 0) t = 0;
+	int sstep = 0, tstep = 0;
+	do
+	{
+		int spancount = count >= 8 ? 8 : count, snext, tnext;
+		count -= spancount;
+		if (count)
+		{
+			sdivz += sdivz8stepu; tdivz += tdivz8stepu; zi += zi8stepu;
+			z = (float)0x10000 / zi;
+			snext = rc_addw (rc_f2i (sdivz * z), sadjust);
+			if (snext > bbextents) snext = bbextents; else if (snext < 8) snext = 8;
+			tnext = rc_addw (rc_f2i (tdivz * z), tadjust);
+			if (tnext > bbextentt) tnext = bbextentt; else if (tnext < 8) tnext = 8;
+			sstep = (snext - s) >> 3;
+			tstep = (tnext - t) >> 3;
+		}
+		else
+		{
+			const float spancountminus1 = (float)(spancount - 1);
+			sdivz += d_sdivzstepu * spancountminus1; tdivz += d_tdivzstepu * spancountminus1; zi += d_zistepu * spancountminus1;
+			z = (float)0x10000 / zi;
+			snext = rc_addw (rc_f2i (sdivz * z), sadjust);
+			if (snext > bbextents) snext = bbextents; else if (snext < 8) snext = 8;
+			tnext = rc_addw (rc_f2i (tdivz * z), tadjust);
+			if (tnext > bbextentt) tnext = bbextentt; else if (tnext < 8) tnext = 8;
+			if (spancount > 1)
+			{
+				sstep = (snext - s) / (spancount - 1);
+				tstep = (tnext - t) / (spancount - 1);
+			}
+		}
+		do
+		{
+			const uint8_t btemp = pbase[(s >> 16) + (t >> 16) * cachewidth];
+			if (btemp != 255 && (unsigned)x < (unsigned)f->width)
+			{
+				const int z16 = izi >> 16;
+				const unsigned long long key = ((unsigned long long)(unsigned)(z16 + 32768) << 48) | orderbits | btemp;
+				RC_ATOMIC_MAX_ULL (&zrow[x], key);
+			}
+			izi = rc_addw (izi, izistep);
+			x++;
+			s = rc_addw (s, sstep);
+			t = rc_addw (t, tstep);
+		} while (--spancount > 0);
+		s = snext;
+		t = tnext;
+	} while (count > 0);
 }
 
 /* One thread per pixel of a view that drew alias models or particles: applies the winning

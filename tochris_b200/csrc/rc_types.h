@@ -303,6 +303,18 @@ typedef struct {            /* finalvert_t, d_iface.h:37-41 (+ the auxvert_t vie
     int   pad[2];
 } rc_finalvert_t;           /* 48 B */
 
+typedef struct {            /* one drawn sprite entity of one view (host-prepared: R_DrawSprite, r_sprite.c:288-403) */
+    int   view;
+    int   order;            /* draw order of the entity inside its view (1-based, shared with alias entities) */
+    int   pixofs;           /* the chosen frame's pixels in the device sprite blob */
+    int   width, height;    /* mspriteframe_t (r_model.h:172-179) */
+    float up, down, left, right;
+    float vpn[3], vright[3], vup[3];   /* r_spritedesc axes for the sprite's orientation type */
+    float entorigin[3];     /* r_entorigin after R_RotateSprite */
+    float modelorg[3];      /* modelorg after R_RotateSprite */
+    int   pad[4];
+} rc_spriteinst_t;          /* 112 B */
+
 typedef struct {            /* particle_t (client/ref.h:37-41) + owning view */
     float org[3];
     int   color;

@@ -22,6 +22,7 @@ class EntitySpec:
     framelerp: float = 0.0
     skinnum: int = 0
     flags: int = 0
+    syncbase: float = 0.0
 
 
 @dataclass
@@ -110,6 +111,7 @@ def build_refdefs(specs: Sequence[ViewSpec], width: int, height: int,
                     ents[j].angles[k] = float(e.angles[k])
                 ents[j].frame = e.frame
                 ents[j].oldframe = e.oldframe
+                ents[j].syncbase = e.syncbase
             rd.num_entities = len(sp.entities)
             rd.entities = ents
             keep.append(ents)
