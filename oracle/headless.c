@@ -221,7 +221,7 @@ int orc_set_cvar (const char *name, float value)
 {
 	cvar_t *v = Cvar_FindVar ((char *)name);
 	if (!v) return -1;
-	Cvar_SetValue ((char *)name, value);
+	Cvar_SetValue (v, value);		/* common/cvar.h:74 takes the cvar_t */
 	return 0;
 }
 

@@ -14,6 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "librefsoft.so")
+LIB_BIG = os.path.join(HERE, "_ref", "librefsoft_big.so")   # MAXWIDTH 2047 / MAXHEIGHT 1200 / MAXSPANS 6000 (`make -C oracle big`)
 
 sys.path.insert(0, os.path.dirname(HERE))
 from tochris_b200.refdef import refdef_t  # noqa: E402
@@ -34,15 +35,18 @@ class orc_span_t(C.Structure):
     _fields_ = [("u", C.c_int), ("v", C.c_int), ("count", C.c_int), ("surf", C.c_int)]
 
 
-def available() -> bool:
-    return os.path.exists(LIB)
+def available(big: bool = False) -> bool:
+    return os.path.exists(LIB_BIG if big else LIB)
 
 
 class RefSoft:
     def __init__(self, basedir: str, width: int, height: int, heap_mb: int = 64, verbose: int = 0):
+        big = width > 1280 or height > 1024       # the stock build's static arrays end there (r_shared.h:40-41)
+        if big and not available(True):
+            raise RuntimeError("oracle/_ref/librefsoft_big.so missing: run `make -C oracle big` where /root/reference exists")
         if not available():
             raise RuntimeError("oracle/_ref/librefsoft.so missing: run `make -C oracle` where /root/reference exists")
-        self.lib = C.CDLL(LIB)
+        self.lib = C.CDLL(LIB_BIG if big else LIB)
         L = self.lib
         L.orc_last_error.restype = C.c_char_p
         L.orc_model.restype = C.c_void_p

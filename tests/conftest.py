@@ -35,4 +35,6 @@ def oracle_available():
     from oracle import refsoft
     if not refsoft.available() and os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    if not refsoft.available(True) and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "big"])
     return refsoft.available()

@@ -25,6 +25,8 @@ CASES = [
     ("full", 400, 300, 8, 1.1, 0.3, dict(skybox="testsky", doors=2, entities=6, dlights=2)),
     ("multi", 320, 240, 12, 0.3, 0.21, dict(sprites=10)),                             # sprite entities: five orientation types, groups
     ("full", 400, 300, 8, 0.9, 0.17, dict(sprites=8, entities=6, particles=60, doors=2)),
+    # BASELINE config C5 substitute: above 1280x1024 the reference needs MAXWIDTH / MAXHEIGHT / MAXSPANS raised
+    ("full", 1920, 1080, 2, 1.7, 0.4, dict(dlights=8, underwater_every=2, big=True)),
 ]
 
 
@@ -35,7 +37,9 @@ def test_sim_matches_oracle(assets_dir, sim_lib, oracle_available, scene, w, h, 
     from oracle import run_oracle
     kw = dict(extra)
     skybox = kw.pop("skybox", None)
-    cvars = {"r_skyname": skybox} if skybox else None
+    cvars = {"r_skyname": skybox} if skybox else {}
+    if kw.pop("big", False):
+        cvars.update(r_maxsurfs=4000.0, r_maxedges=12000.0)     # same pools on both sides (r_main.c:265-300)
     if scene != "box":
         kw.update(time=t0, time_step=dt)
     specs = rcutil.scene_views(scene, n, **kw)
