@@ -178,6 +178,9 @@ typedef struct {
     float  ms_walk, ms_faces, ms_scan, ms_surfprep, ms_cache, ms_draw, ms_total;
     float  ms_h2d, ms_d2h;
     float  ms_spanseg;        /* part of ms_draw spent in the span-segment kernel */
+    float  ms_cells;          /* part of ms_draw spent in k_draw proper (full cells, straight-line code) */
+    long long fullcells;      /* screen cells covered by one span (k_draw items) */
+    long long slowcells;      /* of those, cells k_draw queued for the general code (turbulent, sky, solid, warp views, negative 1/z) */
 } rc_stats_t;
 void RC_GetStats (rc_stats_t *out);
 void RC_SetProfiling (int on);

@@ -167,10 +167,12 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	const int cw = (g->width + 7) / 8;
 	f.segcap = f.spancap + n * g->height * (cw / 8 + 1);
 	g->spans.assign (f.spancap, rc_span_t ());
-	std::vector<int> cellspan ((size_t)n * g->height * cw, -1);
+	rc_cell_t nocell; nocell.si = -1; nocell.sub = 0;
+	std::vector<rc_cell_t> cellspan ((size_t)n * g->height * cw, nocell);
 	f.spans = g->spans.data (); f.cellspan = cellspan.data ();
-	std::vector<int> segspan ((size_t)f.segcap, -1), bnd ((size_t)f.segcap * RC_SEG_BND * 2, 0);
-	f.segspan = segspan.data (); f.bnd = bnd.data ();
+	std::vector<int> segspan ((size_t)f.segcap, -1);
+	std::vector<rc_sub_t> sub ((size_t)f.segcap * 8 + 8, rc_sub_t ());
+	f.segspan = segspan.data (); f.sub = sub.data ();
 	g->alloc[0] = 0; g->alloc[2] = 0;
 	f.alloc = g->alloc;
 	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;
@@ -242,7 +244,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	for (int t = 0; t < nsegs; t++) rc_span_seg (w, &f, t);
 	for (int row = 0; row < n * g->height; row++)
 		for (int c = 0; c < cw; c++) rc_draw_cell (w, &f, row, c);
-	for (int t = 0; t < nspans; t++) rc_draw_head (w, &f, t);
+	for (int t = 0; t < nspans; t++) { rc_draw_mixed (w, &f, t, 0, nspans); rc_draw_mixed (w, &f, t, 1, nspans); }
 
 	/* alias models, particles, z resolve (R_DrawEntitiesOnList, R_DrawParticles) */
 	std::vector<rc_finalvert_t> finalverts ((size_t)batch->nfinalverts + 1);

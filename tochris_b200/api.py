@@ -36,7 +36,8 @@ class rc_stats_t(C.Structure):
                 ("cache_texels", C.c_longlong), ("cache_jobs", C.c_longlong), ("faces", C.c_longlong),
                 ("ms_walk", C.c_float), ("ms_faces", C.c_float), ("ms_scan", C.c_float), ("ms_surfprep", C.c_float),
                 ("ms_cache", C.c_float), ("ms_draw", C.c_float), ("ms_total", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float), ("ms_cells", C.c_float),
+                ("fullcells", C.c_longlong), ("slowcells", C.c_longlong)]
 
 
 class rc_edge_t(C.Structure):
@@ -56,8 +57,8 @@ class rc_surf_t(C.Structure):       # rc_types.h rc_surf_t, 128 B
 
 
 class rc_span_t(C.Structure):       # rc_types.h rc_span_t, 32 B
-    _fields_ = [("view", C.c_int), ("gsurf", C.c_int), ("u", C.c_short), ("count", C.c_short), ("v", C.c_short),
-                ("flags", C.c_ushort), ("pixofs", C.c_int), ("segbase", C.c_int), ("izi0", C.c_int), ("izistep", C.c_int)]
+    _fields_ = [("u", C.c_short), ("count", C.c_short), ("pixofs", C.c_int), ("segbase", C.c_int), ("gsurf", C.c_int),
+                ("iziorg", C.c_int), ("izistep", C.c_int), ("cacheofs", C.c_int), ("cwk", C.c_uint)]
 
 
 assert C.sizeof(rc_surf_t) == 128 and C.sizeof(rc_span_t) == 32 and C.sizeof(rc_edge_t) == 32
@@ -198,7 +199,16 @@ class RefCuda:
         n = self.lib.RC_DebugRead(kind, view, buf, cap)
         if n < 0:
             raise RuntimeError("RC_DebugRead failed")
-        return np.frombuffer(buf, dtype=np.dtype(ty))[:n].copy()
+        a = np.frombuffer(buf, dtype=np.dtype(ty))[:n].copy()
+        if kind == 2:
+            # scanline and view are packed / implied in the record: unpack them for the stage-dump tests
+            out = np.zeros(n, dtype=a.dtype.descr + [("v", "<i4"), ("view", "<i4")])
+            for name in a.dtype.names:
+                out[name] = a[name]
+            out["v"] = a["cwk"] >> 20
+            out["view"] = a["pixofs"] // (self.width * self.height)
+            return out
+        return a
 
     def shutdown(self):
         self.lib.RC_Shutdown()

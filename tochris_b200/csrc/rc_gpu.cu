@@ -60,8 +60,8 @@ struct rc_gpu_s {
 	int *d_facemark; rc_nodevisit_t *d_nodevisit; int *d_viewleaf;
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
-	rc_span_t *d_spans; int *d_cellspan;
-	int *d_segspan, *d_bnd;
+	rc_span_t *d_spans; rc_cell_t *d_cellspan; int2 *d_slowcells;
+	int *d_segspan; rc_sub_t *d_sub;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -76,7 +76,7 @@ struct rc_gpu_s {
 	int16_t *d_zscratch; size_t zscratchcap;
 	rc_bent_t *d_bents; int bentcap; int *d_leafkey; int *d_nbsurfs; int bsurfcap;
 	rc_cachejob_t *d_jobs;
-	unsigned long long *d_alloc;	/* [0] spans|blocks<<32, [1] cache cursor, [2] jobs */
+	unsigned long long *d_alloc;	/* [0] spans|segments<<32, [1] cache cursor, [2] jobs, [3] cells queued for k_slowcells, [4] full cells */
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
@@ -397,7 +397,7 @@ struct scan_warp_t {			/* per-warp shared memory */
 		struct { unsigned long long ku[RC_AET_MAX]; uint16_t kidx[RC_AET_MAX]; } k;	/* B1/B2: unsorted keys: u (biased) << 32 | step code */
 		struct { int16_t x0[SCAN_SPANS], x1[SCAN_SPANS]; uint16_t sf[SCAN_SPANS]; } sp;	/* B3/C: change points, spans */
 	} a;
-	int      su[RC_AET_MAX];		/* sorted: u (12.20) */
+	int      su[SCAN_SPANS];		/* sorted: u (12.20); at publish time: first segment of every span */
 	uint32_t ss[RC_AET_MAX];		/* sorted: surfs[0] | surfs[1] << 16 */
 	int      lkey[SCAN_LEADS], tcount[SCAN_LEADS];
 	uint16_t lsurf[SCAN_LEADS], rsurf[SCAN_LEADS];
@@ -470,11 +470,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	}
 	if (line >= f.height)
 		return;
-	int *cells = f.cellspan + ((size_t)vi * f.height + line) * cw;
+	int2 *cells = reinterpret_cast<int2 *>(f.cellspan + ((size_t)vi * f.height + line) * cw);
 	if (line < vy0 || line >= vy1)
 	{
 		for (int c = lane; c < cw; c += 32)
-			cells[c] = -1;
+			cells[c] = make_int2 (-1, 0);
 		return;
 	}
 	scan_warp_t *sw = &sh->warp[wid];
@@ -706,11 +706,12 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	{
 		if (lane == 0) atomicOr (f.status, RC_STAT_SPAN_POOL);
 		for (int c = lane; c < cw; c += 32)
-			cells[c] = -1;
+			cells[c] = make_int2 (-1, 0);
 		return;
 	}
 	const int pixrow = (vi * f.height + line) * f.width;
-	const uint32_t vflags = ((uint32_t)(uint16_t)line) | ((vw->warp_index >= 0 ? 1u : 0u) << 16);
+	const uint32_t vflags = ((uint32_t)line << 20) | (vw->warp_index >= 0 ? RC_SPAN_WARPBIT : 0u);
+	__syncwarp ();		/* sw->su is reused below */
 	for (int base = 0; base < nsp; base += 32)
 	{
 		const int j = base + lane;
@@ -730,16 +731,19 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		if (j < nsp)
 		{
 			uint4 *dst = reinterpret_cast<uint4 *>(&f.spans[spanbase + j]);
-			dst[0] = make_uint4 ((uint32_t)vi, (uint32_t)(vi * f.surfcap + sf), (uint32_t)(uint16_t)u0 | ((uint32_t)cnt << 16), vflags);
 			const int myseg = segbase + incl - c;
-			dst[1] = make_uint4 ((uint32_t)(pixrow + u0), (uint32_t)myseg, 0u, 0u);
+			dst[0] = make_uint4 ((uint32_t)(uint16_t)u0 | ((uint32_t)cnt << 16), (uint32_t)(pixrow + u0), (uint32_t)myseg, (uint32_t)(vi * f.surfcap + sf));
+			dst[1] = make_uint4 (0u, 0u, 0u, vflags);
+			sw->su[j] = myseg;
 			surfs[sf].hasspans = 1;
 			for (int q = 0; q < c; q++)
 				f.segspan[myseg + q] = spanbase + j;
 		}
 		segbase += __shfl_sync (0xFFFFFFFFu, incl, 31);
 	}
-	/* cell map: the span that covers pixel 8c (spans are sorted and disjoint) */
+	__syncwarp ();
+	/* cell map: the span that covers all of pixels 8c .. 8c+7, if one does (spans are sorted and disjoint) */
+	int nfull = 0;
 	for (int c = lane; c < cw; c += 32)
 	{
 		const int x = c << 3;
@@ -750,8 +754,19 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			if (sw->a.sp.x0[mid] <= x) { idx = mid; lo = mid + 1; }
 			else hi = mid - 1;
 		}
-		cells[c] = (idx >= 0 && x < sw->a.sp.x1[idx]) ? spanbase + idx : -1;
+		int2 cell = make_int2 (-1, 0);
+		if (idx >= 0 && x + 8 <= sw->a.sp.x1[idx])
+		{
+			cell = make_int2 (spanbase + idx, (int)((uint32_t)sw->su[idx] * 64u + (uint32_t)(x - sw->a.sp.x0[idx])));
+			nfull++;
+		}
+		cells[c] = cell;
 	}
+	#pragma unroll
+	for (int o = 16; o; o >>= 1)
+		nfull += __shfl_xor_sync (0xFFFFFFFFu, nfull, o);
+	if (lane == 0)
+		atomicAdd (&f.alloc[4], (unsigned long long)nfull);		/* statistics only */
 }
 
 __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -778,15 +793,6 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
 {
 	__shared__ __align__(16) uint8_t s_cmap[256 * 64];
 	__shared__ unsigned bl[18 * 18];
-	/* prologue: surfaces that found their block already in the cache table pick up its pool offset
-	 * (the creator stored it in the surface-prep kernel) */
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < f.nviews * f.surfcap; t += gridDim.x * blockDim.x)
-	{
-		const int vi = t / f.surfcap;
-		const int si = rc_surf_slot (&f, vi, t - vi * f.surfcap);
-		if (si >= 0)
-			rc_surf_resolve (&f, vi, si);
-	}
 	const unsigned long long nj = f.alloc[2];
 	const int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
 	if ((int)blockIdx.x >= njobs)
@@ -859,65 +865,386 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
 	}
 }
 
-__global__ void k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* Span-segment kernel: one thread per 64-pixel segment (rc_span_seg).  A thread's eight subdivision
+ * records are 128 contiguous bytes, a warp's 4 KB: they are staged in shared memory (swizzled, conflict
+ * free) and written out by the whole warp, 512 contiguous bytes per store instruction instead of 32
+ * scattered 16-byte pieces. */
+__global__ void __launch_bounds__(128) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	__shared__ uint4 stage[128 * 8];
 	unsigned long long a = f.alloc[0];
 	int nsegs = (int)(a >> 32);
 	if (nsegs > f.segcap) nsegs = f.segcap;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsegs; t += gridDim.x * blockDim.x)
-		rc_span_seg (&w, &f, t);
+	const int lane = threadIdx.x & 31;
+	uint4 *wst = stage + (threadIdx.x & ~31) * 8;
+	uint4 *sub4 = reinterpret_cast<uint4 *>(f.sub);
+	for (int t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); t0 < nsegs; t0 += gridDim.x * blockDim.x)
+	{
+		const int t = t0 + lane;
+		int wrote = 0;
+		if (t < nsegs)
+			wrote = rc_span_seg (&w, &f, t, reinterpret_cast<rc_sub_t *>(wst + lane * 8), lane & 7);
+		const unsigned m = __ballot_sync (0xFFFFFFFFu, wrote);
+		__syncwarp ();
+		#pragma unroll
+		for (int r = 0; r < 8; r++)
+		{
+			const int seg = r * 4 + (lane >> 3), rec = lane & 7;
+			if (m & (1u << seg))
+				sub4[(size_t)(t0 + seg) * 8 + rec] = wst[seg * 8 + (rec ^ (seg & 7))];
+		}
+		__syncwarp ();
+	}
 }
 
-/* Draw stage: first one thread per screen-aligned 8-pixel cell of every row (full cells: one
- * 8-byte colour store + one 16-byte z store, both aligned and coalesced across the warp), then
- * one thread per span head.  Rows = views x height. */
+/* Draw stage.
+ * Cell pass: one thread per screen-aligned 8-pixel cell that a single span covers completely.  A warp
+ * draws a TILE of 8 cells x 4 rows (64 x 4 pixels): the texel gathers of its 32 lanes then fall into a
+ * compact patch of the surface-cache block instead of a 256-pixel strip, which is what bounds this
+ * kernel (L1 wavefronts per gather, profiles/).  Per cell the thread needs the cell record
+ * (span, subdivision), the span record (1/z, texel block) and two subdivision records (texture
+ * coordinates and steps): the cell records of the item after next and the span / subdivision records
+ * of the next item are in flight while a cell is drawn, so only the texel gathers are exposed.
+ * Common case (cache block or texel blob, no negative 1/z in reach, frame buffer target): straight-line
+ * code, one aligned 8-byte colour store and one aligned 16-byte z store.  Everything else (turbulent,
+ * sky, solid, warp-buffer views, negative 1/z) goes through the general item rc_draw_pixels.
+ * The cells that hold a span boundary are drawn by k_ends. */
 #ifndef DRAW_MINB
-#define DRAW_MINB 8	/* 64 registers: 32 warps per SM hide the dependent cell -> span -> texel loads (measured: 8 > 9 > 10 > 7) */
+#define DRAW_MINB 6	/* 80 registers: the prefetched records of the next cell stay in registers (64 spills them) */
 #endif
+__device__ __noinline__ void draw_general (const rc_world_t *w, const rc_frame_t *f, int si, int rel, bool warpviews)
+{
+	const rc_span_t sp = rc_load_span (&f->spans[si]);
+	rc_draw_pixels (w, f, sp, rel, warpviews);
+}
+
+struct draw_item_t {
+	int   si;		/* span, -1: nothing to draw */
+	uint32_t sub;		/* cell record: subdivision record << 3 | position in it */
+	uint32_t pix;		/* first pixel of the cell in the colour / z planes */
+	uint4 sb;		/* second half of the span record: iziorg, izistep, cacheofs, cwk */
+	uint4 r0, r1;		/* subdivision records k, k+1 */
+};
+
+#ifndef DRAW_TW
+#define DRAW_TW 8		/* tile = DRAW_TW cells x 32 / DRAW_TW rows per warp */
+#endif
+#ifndef DRAW_PF
+#define DRAW_PF 0		/* 0: next item's records prefetched into registers, 1: into L1 (prefetch.global.L1) */
+#endif
+#define DRAW_TH (32 / DRAW_TW)
+
+__device__ __forceinline__ void draw_prefetch_l1 (const void *p)
+{
+	asm volatile ("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+/* the common case of a full cell: D_DrawZSpans + D_DrawSpans8 for 8 screen-aligned pixels */
+__device__ __forceinline__ bool draw_cell_fast (const rc_world_t &w, const rc_frame_t &f, const uint32_t sub, const uint32_t pix,
+	const uint4 sb, const uint4 r0, const uint4 r1, const bool fast_ok)
+{
+	const unsigned a = sub & 7u;
+	const uint32_t izistep = sb.y;
+	uint32_t zz[8];
+	zz[0] = sb.x + pix * izistep;
+	#pragma unroll
+	for (int j = 1; j < 8; j++)
+		zz[j] = zz[j-1] + izistep;
+	const uint32_t anyneg = (zz[0] - izistep) | zz[0] | zz[1] | zz[2] | zz[3] | zz[4] | zz[5] | zz[6] | zz[7];
+	const uint32_t cwk = sb.w;
+	if (!(fast_ok && (cwk & 0xE0000u) == 0 && (int)anyneg >= 0))
+		return false;
+	/* D_DrawZSpans: the high halves of consecutive 1/z values, pairwise */
+	uint4 zq;
+	zq.x = __byte_perm (zz[0], zz[1], 0x7632); zq.y = __byte_perm (zz[2], zz[3], 0x7632);
+	zq.z = __byte_perm (zz[4], zz[5], 0x7632); zq.w = __byte_perm (zz[6], zz[7], 0x7632);
+	*reinterpret_cast<uint4 *>(f.zb + pix) = zq;
+	/* D_DrawSpans8: subdivision k from its pixel a on, subdivision k+1 from cell pixel 8 - a on */
+	const uint8_t *pbase = ((cwk & 0x10000u) ? w.texels : f.cachepool) + (int)sb.z;
+	const int cachewidth = (int)(cwk & 0xFFFFu);
+	uint32_t sstep = r0.z, tstep = r0.w;
+	uint32_t ss = r0.x + a * sstep, tt = r0.y + a * tstep;
+	uint32_t px[8];
+	#pragma unroll
+	for (int j = 0; j < 8; j++)
+	{
+		if (j > 0 && a + j == 8)
+		{
+			ss = r1.x; tt = r1.y; sstep = r1.z; tstep = r1.w;
+		}
+		px[j] = __ldg (&pbase[((int)ss >> 16) + ((int)tt >> 16) * cachewidth]);
+		ss += sstep; tt += tstep;
+	}
+	uint2 q;
+	q.x = __byte_perm (__byte_perm (px[0], px[1], 0x0040), __byte_perm (px[2], px[3], 0x0040), 0x5410);
+	q.y = __byte_perm (__byte_perm (px[4], px[5], 0x0040), __byte_perm (px[6], px[7], 0x0040), 0x5410);
+	*reinterpret_cast<uint2 *>(f.fb + pix) = q;
+	return true;
+}
+
 template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	const unsigned cw = (unsigned)((f.width + 7) >> 3);
-	const unsigned ncells = (unsigned)(f.drawview1 * f.height) * cw;
-	const unsigned stride = gridDim.x * blockDim.x;
-	/* cell -> span -> (surface, boundaries) -> texels is a chain of dependent loads: the first two
-	 * levels of the next grid-stride iterations are fetched while the current cell is drawn */
-	unsigned t0 = (unsigned)(f.drawview0 * f.height) * cw + blockIdx.x * blockDim.x + threadIdx.x, t1 = t0 + stride;
-	/* the cell's column inside its row, kept incrementally (no divide per item) */
-	const unsigned cstep = stride % cw;
-	unsigned c0 = t0 % cw;
-	int si0 = t0 < ncells ? __ldg (&f.cellspan[t0]) : -1;
-	int si1 = t1 < ncells ? __ldg (&f.cellspan[t1]) : -1;
-	rc_span_t sp0 = rc_load_span (&f.spans[si0 < 0 ? 0 : si0]);
-	while (t0 < ncells)
+	const unsigned cw = (unsigned)((f.width + 7) >> 3), tilesx = (cw + DRAW_TW - 1) / DRAW_TW;
+	const unsigned row0 = (unsigned)(f.drawview0 * f.height), nrows = (unsigned)((f.drawview1 - f.drawview0) * f.height);
+	const unsigned ntiles = tilesx * ((nrows + DRAW_TH - 1) / DRAW_TH);
+	const unsigned lane = threadIdx.x & 31, lx = lane % DRAW_TW, ly = lane / DRAW_TW;
+	const unsigned wstride = gridDim.x * (blockDim.x >> 5);
+	const bool fast_ok = f.zb != NULL && (f.width & 7) == 0;
+	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
+	const uint4 *sub4 = reinterpret_cast<const uint4 *>(f.sub);
+	const int2 *cells = reinterpret_cast<const int2 *>(f.cellspan);
+	/* tile -> (tx, ty), kept incrementally (no divide per item) */
+	unsigned tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	unsigned ty = tile / tilesx, tx = tile - ty * tilesx;
+	const unsigned dty = wstride / tilesx, dtx = wstride - dty * tilesx;
+
+	/* cell record + first pixel of the tile's cell for this lane; advances (tile, tx, ty) */
+	auto fetch_cell = [&] (int2 &cell, uint32_t &pix)
 	{
-		const unsigned t2 = t1 + stride;
-		const int si2 = t2 < ncells ? __ldg (&f.cellspan[t2]) : -1;
-		const rc_span_t sp1 = rc_load_span (&f.spans[si1 < 0 ? 0 : si1]);
-		if (si0 >= 0)
+		const unsigned c = tx * DRAW_TW + lx, r = ty * DRAW_TH + ly;
+		cell = make_int2 (-1, 0);
+		pix = ((row0 + r) * (unsigned)f.width) + (c << 3);
+		if (tile < ntiles && c < cw && r < nrows)
+			cell = __ldg (&cells[(size_t)(row0 + r) * cw + c]);
+		tile += wstride; tx += dtx; ty += dty;
+		if (tx >= tilesx) { tx -= tilesx; ty++; }
+	};
+	auto issue = [&] (draw_item_t &it, const int2 cell, const uint32_t pix)
+	{
+		it.si = cell.x; it.sub = (uint32_t)cell.y; it.pix = pix;
+		const unsigned s = cell.x < 0 ? 0u : (unsigned)cell.x;
+		it.sb = __ldg (&spans4[2 * (size_t)s + 1]);
+		const unsigned k = it.sub >> 3;
+		it.r0 = __ldg (&sub4[k]); it.r1 = __ldg (&sub4[k + 1]);
+	};
+
+	unsigned t0 = tile;
+	int2 c0, c1; uint32_t p0, p1;
+	fetch_cell (c0, p0);
+	fetch_cell (c1, p1);
+#if DRAW_PF == 0
+	draw_item_t cur;
+	issue (cur, c0, p0);
+#endif
+#ifdef DRAW_SKIP_CELLS
+	t0 = ntiles;
+#endif
+	while (t0 < ntiles)
+	{
+		int2 c2; uint32_t p2;
+		fetch_cell (c2, p2);
+#if DRAW_PF == 0
+		draw_item_t nxt;
+		issue (nxt, c1, p1);
+#else
+		if (c1.x >= 0)
 		{
-			const int rel = (int)(c0 << 3) - sp0.u;
-			int cnt = sp0.count - rel;
-			if (cnt > 8) cnt = 8;
-			rc_draw_pixels (&w, &f, si0, sp0, rel, cnt, WARPVIEWS);
+			draw_prefetch_l1 (&spans4[2 * (size_t)c1.x + 1]);
+			draw_prefetch_l1 (&sub4[(uint32_t)c1.y >> 3]);
+			draw_prefetch_l1 (&sub4[((uint32_t)c1.y >> 3) + 1]);
 		}
-		t0 = t1; t1 = t2; si0 = si1; si1 = si2; sp0 = sp1;
-		c0 += cstep;
-		if (c0 >= cw) c0 -= cw;
+		draw_item_t cur;
+		issue (cur, c0, p0);
+#endif
+		/* cells the straight-line code does not handle are queued for the general kernel (k_ends):
+		 * one atomicAdd per warp */
+		const bool slow = cur.si >= 0 && !draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, cur.r0, cur.r1, fast_ok);
+		const unsigned sm = __ballot_sync (0xFFFFFFFFu, slow);
+		if (sm)
+		{
+			unsigned long long base = 0ull;
+			if (lane == (unsigned)(__ffs (sm) - 1))
+				base = atomicAdd (&f.alloc[3], (unsigned long long)__popc (sm));
+			base = __shfl_sync (0xFFFFFFFFu, base, __ffs (sm) - 1);
+			if (slow)
+				f.slowcells[base + __popc (sm & ((1u << lane) - 1u))] = make_int2 (cur.si, (int)cur.pix);
+		}
+#if DRAW_PF == 0
+		cur = nxt;
+#else
+		c0 = c1; p0 = p1;
+#endif
+		c1 = c2; p1 = p2;
+		t0 += wstride;
 	}
-	unsigned long long a = f.alloc[0];
-	unsigned nspans = (unsigned)(a & 0xFFFFFFFFu);
-	if (nspans > (unsigned)f.spancap) nspans = (unsigned)f.spancap;
+
+}
+
+__device__ __noinline__ void draw_mixed_general (const rc_world_t *w, const rc_frame_t *f, int first, int nspans, int cellx, int rowstart, bool warpviews)
+{
+	rc_draw_mixed_cell (w, f, first, nspans, cellx, rowstart, warpviews);
+}
+
+/* Second kernel of the draw stage: the mixed cells (rc_mixed_owner) and the full cells k_draw queued.
+ * One item per span; lanes are consecutive spans.  The item loads the records of spans si-1 .. si+2
+ * (one 128-byte line) at once: ownership of the cell around the span's first pixel and the list of
+ * spans that share that cell (up to three here, else the general code) follow from registers, so the
+ * thread has three dependent load levels in all -- span records, subdivision records, texels -- before
+ * it stores the cell once.  Shares are merged in registers by the straight-line code of k_draw under a
+ * pixel mask; a share that code does not handle sends the whole cell to the general code. */
+#ifndef ENDS_MINB
+#define ENDS_MINB 4
+#endif
+template <bool WARPVIEWS>
+__global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
+	const uint4 *sub4 = reinterpret_cast<const uint4 *>(f.sub);
+	unsigned long long al = f.alloc[0];
+	int nspans = (int)(al & 0xFFFFFFFFu);
+	if (nspans > f.spancap) nspans = f.spancap;
+#ifdef DRAW_SKIP_ENDS
+	nspans = 0;
+#endif
 	const bool allviews = f.drawview0 == 0 && f.drawview1 == f.nviews;
-	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nspans; t += stride)
+	for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < nspans; si += gridDim.x * blockDim.x)
 	{
+		/* level 0: records si-1 .. si+2 */
+		uint4 A[4], B[3];
+		#pragma unroll
+		for (int q = 0; q < 4; q++)
+		{
+			int idx = si - 1 + q;
+			idx = idx < 0 ? 0 : (idx >= nspans ? nspans - 1 : idx);
+			A[q] = __ldg (&spans4[2 * (size_t)idx]);
+			if (q < 3) B[q] = __ldg (&spans4[2 * (size_t)idx + 1]);
+		}
+		const int u = (int16_t)(A[1].x & 0xFFFF), count = (int16_t)(A[1].x >> 16), e = u + count;
+		if (count <= 0)
+			continue;
+		const int rowstart = (int)A[1].y - u;
 		if (!allviews)
 		{
-			const int v = __ldg (&f.spans[t].view);
+			const int v = (int)A[1].w / f.surfcap;
 			if (v < f.drawview0 || v >= f.drawview1)
 				continue;
 		}
-		rc_draw_head (&w, &f, (int)t, WARPVIEWS);
+		int uq[4]; bool row[4];
+		#pragma unroll
+		for (int q = 0; q < 4; q++)
+		{
+			uq[q] = (int16_t)(A[q].x & 0xFFFF);
+			row[q] = (si - 1 + q >= 0) && (si - 1 + q < nspans) && ((int)A[q].y - uq[q] == rowstart) && ((int16_t)(A[q].x >> 16) > 0);
+		}
+		/* the cell around the span's end (rc_mixed_owner, which = 1): only where the view rectangle ends inside a cell */
+		if ((e & 7) && u <= (e & ~7) && !(row[2] && uq[2] < (e & ~7) + 8))
+			draw_mixed_general (&w, &f, si, nspans, e & ~7, rowstart, WARPVIEWS);
+		/* the cell around its first pixel (which = 0) */
+		if (!(u & 7))
+			continue;
+		const int cellx = u & ~7;
+		if (row[0] && uq[0] > cellx)
+			continue;			/* an earlier span starts inside the same cell */
+		const int firstq = row[0] ? 0 : 1;
+		const uint32_t pix = (uint32_t)(rowstart + cellx);
+		bool general = f.zb == NULL || (row[3] && uq[3] < cellx + 8);
+		/* shares: records firstq .. 2 while they start before the cell's end */
+		bool act[3]; int rel[3];
+		#pragma unroll
+		for (int q = 0; q < 3; q++)
+		{
+			act[q] = q >= firstq && row[q] && uq[q] < cellx + 8;
+			rel[q] = cellx - uq[q];
+		}
+		/* level 1: subdivision records of every share */
+		uint4 R0[3], R1[3];
+		#pragma unroll
+		for (int q = 0; q < 3; q++)
+		{
+			const int k = rel[q] < 0 ? 0 : rel[q] >> 3;
+			const uint4 *rp = sub4 + (act[q] ? (size_t)A[q].z * 8 + k : 0);
+			R0[q] = __ldg (rp); R1[q] = __ldg (rp + 1);
+		}
+		uint32_t px[8], zq[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++) { px[j] = 0; zq[j] = 0; }
+		unsigned mask = 0u;
+		#pragma unroll
+		for (int q = 0; q < 3; q++)
+		{
+			if (!act[q] || general)
+				continue;
+			const int cnt = (int16_t)(A[q].x >> 16);
+			const int lo = rel[q] < 0 ? -rel[q] : 0;
+			const int hi = cnt - rel[q] < 8 ? cnt - rel[q] : 8;
+			if (hi <= lo)
+				continue;
+			const unsigned vmask = (0xFFu >> (8 - hi)) & (0xFFu << lo);
+			const uint32_t izistep = B[q].y;
+			uint32_t zz[8];
+			zz[0] = B[q].x + pix * izistep;
+			#pragma unroll
+			for (int j = 1; j < 8; j++)
+				zz[j] = zz[j-1] + izistep;
+			const uint32_t anyneg = (zz[0] - izistep) | zz[0] | zz[1] | zz[2] | zz[3] | zz[4] | zz[5] | zz[6] | zz[7];
+			const uint32_t cwk = B[q].w;
+			if ((cwk & 0xE0000u) != 0 || (int)anyneg < 0)
+			{
+				general = true;
+				continue;
+			}
+			const int a = rel[q] < 0 ? rel[q] : rel[q] & 7;
+			const uint8_t *pbase = ((cwk & 0x10000u) ? w.texels : f.cachepool) + (int)B[q].z;
+			const int cachewidth = (int)(cwk & 0xFFFFu);
+			uint32_t sstep = R0[q].z, tstep = R0[q].w;
+			uint32_t ss = R0[q].x + (uint32_t)a * sstep, tt = R0[q].y + (uint32_t)a * tstep;
+			#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				if (j > 0 && a + j == 8)
+				{
+					ss = R1[q].x; tt = R1[q].y; sstep = R1[q].z; tstep = R1[q].w;
+				}
+				if (vmask & (1u << j))
+				{
+					px[j] = __ldg (&pbase[((int)ss >> 16) + ((int)tt >> 16) * cachewidth]);
+					zq[j] = zz[j];
+				}
+				ss += sstep; tt += tstep;
+			}
+			mask |= vmask;
+		}
+		if (general)
+		{
+			draw_mixed_general (&w, &f, si - 1 + firstq, nspans, cellx, rowstart, WARPVIEWS);
+			continue;
+		}
+		uint8_t *pd = f.fb + pix;
+		int16_t *pz = f.zb + pix;
+		if (mask == 0xFFu && (pix & 7u) == 0)
+		{
+			uint4 z4;
+			z4.x = __byte_perm (zq[0], zq[1], 0x7632); z4.y = __byte_perm (zq[2], zq[3], 0x7632);
+			z4.z = __byte_perm (zq[4], zq[5], 0x7632); z4.w = __byte_perm (zq[6], zq[7], 0x7632);
+			*reinterpret_cast<uint4 *>(pz) = z4;
+			uint2 q;
+			q.x = __byte_perm (__byte_perm (px[0], px[1], 0x0040), __byte_perm (px[2], px[3], 0x0040), 0x5410);
+			q.y = __byte_perm (__byte_perm (px[4], px[5], 0x0040), __byte_perm (px[6], px[7], 0x0040), 0x5410);
+			*reinterpret_cast<uint2 *>(pd) = q;
+		}
+		else
+		{
+			#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (mask & (1u << j))
+				{
+					pd[j] = (uint8_t)px[j];
+					pz[j] = (int16_t)(zq[j] >> 16);
+				}
+		}
+	}
+}
+
+/* the full cells k_draw left to the general code (turbulent, sky, solid, warp-buffer views, negative 1/z) */
+template <bool WARPVIEWS>
+__global__ void __launch_bounds__(128) k_slowcells (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	const unsigned nslow = (unsigned)f.alloc[3];
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nslow; t += gridDim.x * blockDim.x)
+	{
+		const int2 sc = f.slowcells[t];
+		draw_general (&w, &f, sc.x, sc.y - __ldg (&f.spans[sc.x].pixofs), WARPVIEWS);
 	}
 }
 
@@ -1025,14 +1352,14 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	if (cudaMalloc (&g->d_cachepool, g->cachecap) != cudaSuccess ||
 	    cudaMalloc (&g->d_cachekeys, sizeof(unsigned long long) * g->cacheslots) != cudaSuccess ||
 	    cudaMalloc (&g->d_cachevals, sizeof(int) * g->cacheslots) != cudaSuccess ||
-	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 4) != cudaSuccess ||
+	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 8) != cudaSuccess ||
 	    cudaMalloc (&g->d_status, sizeof(int) * 16) != cudaSuccess)
 	{
 		snprintf (err, errlen, "cudaMalloc (surface cache) failed: %s", cudaGetErrorString (cudaGetLastError ()));
 		delete g;
 		return NULL;
 	}
-	cudaMemset (g->d_alloc, 0, sizeof(unsigned long long) * 4);
+	cudaMemset (g->d_alloc, 0, sizeof(unsigned long long) * 8);
 	cudaMemset (g->d_cachekeys, 0xFF, sizeof(unsigned long long) * g->cacheslots);
 	cudaDeviceSynchronize ();
 	return g;
@@ -1044,7 +1371,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_cellspan); cudaFree (g->d_jobs); cudaFree (g->d_segspan); cudaFree (g->d_bnd);
+	cudaFree (g->d_cellspan); cudaFree (g->d_slowcells); cudaFree (g->d_jobs); cudaFree (g->d_segspan); cudaFree (g->d_sub);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -1238,7 +1565,7 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 	size_t cw = (g->width + 7) / 8;
 	size_t spans = lines * g->spans_per_line, segs = spans + lines * (cw / 8 + 1);
 	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
-	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + (4 + 8 * RC_SEG_BND) * segs + 4 * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
+	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + (4 + 8 * sizeof(rc_sub_t)) * segs + (sizeof(rc_cell_t) + 8) * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
 static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
@@ -1269,7 +1596,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
 	const size_t cw = (g->width + 7) / 8;
 	size_t segs = (size_t)g->spancap + lines * (cw / 8 + 1);
-	g->segcap = (int)(segs < 0x7FFFFFFF / (RC_SEG_BND * 2) ? segs : 0x7FFFFFFF / (RC_SEG_BND * 2));
+	g->segcap = (int)(segs < (1 << 26) - 2 ? segs : (1 << 26) - 2);	/* rc_cell_t.sub holds segment * 64 + pixel in 32 bits */
 	g->jobcap = want * 8 + 4096;
 	if (g->jobcap > want * surfcap) g->jobcap = want * surfcap;
 	CK (cudaMalloc (&g->d_views, sizeof(rc_view_t) * want));
@@ -1285,9 +1612,10 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_nedges, sizeof(int) * want));
 	CK (cudaMalloc (&g->d_surfs, sizeof(rc_surf_t) * (size_t)want * surfcap));
 	CK (cudaMalloc (&g->d_spans, sizeof(rc_span_t) * (size_t)g->spancap));
-	CK (cudaMalloc (&g->d_cellspan, sizeof(int) * lines * cw));
+	CK (cudaMalloc (&g->d_cellspan, sizeof(rc_cell_t) * lines * cw));
+	CK (cudaMalloc (&g->d_slowcells, sizeof(int2) * lines * cw));
 	CK (cudaMalloc (&g->d_segspan, sizeof(int) * (size_t)g->segcap));
-	CK (cudaMalloc (&g->d_bnd, sizeof(int) * 2 * RC_SEG_BND * (size_t)g->segcap));
+	CK (cudaMalloc (&g->d_sub, sizeof(rc_sub_t) * (8 * (size_t)g->segcap + 8)));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
 	g->chunkcap = want;
 	return RC_OK;
@@ -1310,8 +1638,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.facemark = g->d_facemark; f.nodevisit = g->d_nodevisit; f.viewleaf = g->d_viewleaf;
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
-	f.spans = g->d_spans; f.spancap = g->spancap; f.cellspan = g->d_cellspan;
-	f.segspan = g->d_segspan; f.bnd = g->d_bnd; f.segcap = g->segcap;
+	f.spans = g->d_spans; f.spancap = g->spancap; f.cellspan = g->d_cellspan; f.slowcells = g->d_slowcells;
+	f.segspan = g->d_segspan; f.sub = g->d_sub; f.segcap = g->segcap;
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
@@ -1321,7 +1649,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
 	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
-	CK (cudaMemsetAsync (g->d_alloc + 2, 0, sizeof(unsigned long long), s));
+	CK (cudaMemsetAsync (g->d_alloc + 2, 0, 3 * sizeof(unsigned long long), s));	/* jobs, queued cells, full-cell count */
 
 	{
 		/* cluster size: as many CTAs per view as fit the machine in one wave, at most 8 */
@@ -1396,7 +1724,16 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			const int nv = f.drawview1 - f.drawview0;
 			int ctas = (int)(((size_t)nv * g->height * ((g->width + 7) / 8) + 127) / 128);
 			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
+			/* mixed cells on the second stream, beside the full cells */
+			cudaEventRecord (g->evfork, s);
+			cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
+			k_ends<false><<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
+			cudaEventRecord (g->evjoin, g->sidestream);
 			k_draw<false><<<ctas, 128, 0, s>>> (w, f);
+			if (timed) cudaEventRecord (g->ev[8], s);
+			k_slowcells<false><<<g->numsms * 4, 128, 0, s>>> (w, f);
+			cudaMemsetAsync (g->d_alloc + 3, 0, sizeof(unsigned long long), s);
+			cudaStreamWaitEvent (s, g->evjoin, 0);
 			cudaEventRecord (g->evgroup[gi], s);
 			cudaStreamWaitEvent (side, g->evgroup[gi], 0);
 			if (g->host_fb)
@@ -1409,7 +1746,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			else
 				g->groupfn (g->groupuser, first_view + f.drawview0, nv);
 		}
-		g->stats.kernel_launches += ngroups - 1;
+		g->stats.kernel_launches += 3 * ngroups - 1;
 		if (g->host_fb)
 		{
 			cudaEventRecord (g->evcopy, side);
@@ -1419,8 +1756,27 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	else
 	{
 		f.drawview0 = 0; f.drawview1 = n;
-		if (anywarp) k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f);
-		else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
+		if (timed)
+		{
+			if (anywarp) k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f);
+			else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
+			cudaEventRecord (g->ev[8], s);
+			if (anywarp) { k_ends<true><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<true><<<g->numsms * 8, 128, 0, s>>> (w, f); }
+			else { k_ends<false><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<false><<<g->numsms * 8, 128, 0, s>>> (w, f); }
+		}
+		else
+		{
+			/* mixed cells on the second stream, beside the full cells (disjoint pixels; both only read the
+			 * span / subdivision records and the cache) */
+			cudaEventRecord (g->evfork, s);
+			cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
+			if (anywarp) k_ends<true><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
+			else k_ends<false><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
+			cudaEventRecord (g->evjoin, g->sidestream);
+			if (anywarp) { k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<true><<<g->numsms * 8, 128, 0, s>>> (w, f); }
+			else { k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<false><<<g->numsms * 8, 128, 0, s>>> (w, f); }
+			cudaStreamWaitEvent (s, g->evjoin, 0);
+		}
 	}
 	if (g->cur_batch && g->cur_batch->nzres)
 	{
@@ -1497,15 +1853,17 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			CK (cudaMemcpyAsync (g->host_z + px * first_view, zb, px * n * sizeof(int16_t), cudaMemcpyDefault, s));
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 6;
+	g->stats.kernel_launches += 8;
 	CK (cudaGetLastError ());
 	return RC_OK;
 }
 
 static void collect_stats (rc_gpu_t *g, int n, bool timed)
 {
-	unsigned long long a[4];
+	unsigned long long a[8];
 	cudaMemcpy (a, g->d_alloc, sizeof(a), cudaMemcpyDeviceToHost);
+	g->stats.fullcells += (long long)a[4];
+	g->stats.slowcells += (long long)a[3];
 	g->stats.spans += (long long)(a[0] & 0xFFFFFFFFu);
 	g->stats.blocks += (long long)n * g->height * ((g->width + 7) / 8) + (long long)(a[0] & 0xFFFFFFFFu);
 	g->stats.cache_jobs += (long long)a[2];
@@ -1530,6 +1888,8 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 		cudaEventElapsedTime (&ms, g->ev[4], g->ev[5]); g->stats.ms_cache += ms;
 		cudaEventElapsedTime (&ms, g->ev[5], g->ev[6]); g->stats.ms_draw += ms;
 		cudaEventElapsedTime (&ms, g->ev[5], g->ev[7]); g->stats.ms_spanseg += ms;
+		if (cudaEventElapsedTime (&ms, g->ev[7], g->ev[8]) == cudaSuccess) g->stats.ms_cells += ms;
+		else cudaGetLastError ();
 		cudaEventElapsedTime (&ms, g->ev[0], g->ev[6]); g->stats.ms_total += ms;
 	}
 }

@@ -62,7 +62,7 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
 #define RC_WARP_W          320       /* WARP_WIDTH / WARP_HEIGHT, d_iface.h:22-23 */
 #define RC_WARP_H          200
-#define RC_SEG_BND         12        /* entries 8s .. 8s+11 of a span's boundary table are stored with segment s */
+#define RC_SEG_BND         9         /* boundaries 8s .. 8s+8 of a span are evaluated by segment s (rc_span_seg) */
 
 /* per-batch buffers (device pointers inside kernels, host pointers in the simulator) */
 typedef struct {
@@ -82,9 +82,14 @@ typedef struct {
     int maxedges, maxsurfs;       /* the reference's r_maxedges / r_maxsurfs (overflow reporting) */
     /* scan */
     rc_span_t *spans; int spancap;
-    int *cellspan;                /* [nviews][height][(width+7)/8]: span covering the first pixel of each 8-pixel screen cell, -1: none */
+    rc_cell_t *cellspan;          /* [nviews][height][(width+7)/8]: the span that covers ALL eight pixels of a screen cell, si -1: none */
     int *segspan; int segcap;     /* [segcap]: owning span of every 64-pixel span segment (8 subdivisions) */
-    int *bnd;                     /* [segcap][RC_SEG_BND][2]: 16.16 (s, t) at the subdivision boundaries of a segment */
+    rc_sub_t *sub;                /* [segcap * 8 + 8]: subdivision k of a span is record segbase * 8 + k */
+#ifdef __CUDACC__
+    int2 *slowcells;              /* GPU only: {span, first pixel} of the full cells k_draw queues for the general code; count in alloc[3] */
+#else
+    void *slowcells;
+#endif
     unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 segments used  [1]: cache pool cursor  [2]: jobs */
     /* surface cache */
     unsigned long long *cachekeys; int *cachevals; int cachemask;
@@ -1393,28 +1398,32 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
 }
 
 /* ---- publishing a scanline's spans -----------------------------------------------------------
- * Work list of the draw stage (DESIGN.md "draw"): world spans tile the view rectangle, so the draw
- * kernel runs one thread per SCREEN-ALIGNED 8-pixel cell (full cells store one aligned 8-byte colour
- * word and one aligned 16-byte z word) plus one thread per span whose first column is not a multiple
- * of 8 (its "head", the pixels up to the next cell boundary).  cellspan[(view, line, cell)] = the span
- * that covers the cell's first pixel, -1 outside the view rectangle. */
+ * Work list of the draw stage (DESIGN.md "draw"): world spans tile the view rectangle.  The draw
+ * kernel runs one thread per SCREEN-ALIGNED 8-pixel cell that a single span covers completely (one
+ * aligned 8-byte colour store and one aligned 16-byte z store, no masks); the cells that hold a span
+ * boundary are drawn whole by one owner from the shares of their spans (rc_mixed_owner).
+ * cellspan[(view, line, cell)] = {span, subdivision record of the cell's first pixel * 8 + its
+ * position inside that subdivision}; si = -1 where no span covers the whole cell. */
 RC_HD int rc_span_seg_count (int count) { return (((count + 7) >> 3) + 7) >> 3; }	/* segments of 8 subdivisions = 64 pixels */
 
 RC_HD void rc_write_span (const rc_frame_t *f, const rc_view_t *vw, int vi, int line, int si, int surf, int u0, int count, int segbase)
 {
 	rc_span_t *s = &f->spans[si];
-	s->view = vi; s->gsurf = vi * f->surfcap + surf;
-	s->u = (int16_t)u0; s->count = (int16_t)count; s->v = (int16_t)line; s->flags = (uint16_t)(vw->warp_index >= 0 ? 1 : 0);
+	s->u = (int16_t)u0; s->count = (int16_t)count;
 	s->pixofs = (vi * f->height + line) * f->width + u0;
-	s->segbase = segbase; s->izi0 = 0; s->izistep = 0;
+	s->segbase = segbase; s->iziorg = 0; s->izistep = 0; s->cacheofs = 0;
+	s->cwk = ((uint32_t)line << 20) | (vw->warp_index >= 0 ? RC_SPAN_WARPBIT : 0u);
+	s->gsurf = vi * f->surfcap + surf;
 }
 
 RC_HD void rc_line_clear (const rc_frame_t *f, int vi, int line)
 {
 	const int cw = (f->width + 7) >> 3;
-	int *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
+	rc_cell_t *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
 	for (int c = 0; c < cw; c++)
-		cells[c] = -1;
+	{
+		cells[c].si = -1; cells[c].sub = 0;
+	}
 }
 
 /* serial version (host simulation; the GPU scan kernel does the same with a warp) */
@@ -1432,18 +1441,20 @@ RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t 
 		return;
 	}
 	const int cw = (f->width + 7) >> 3;
-	int *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
-	for (int c = 0; c < cw; c++)
-		cells[c] = -1;
+	rc_cell_t *cells = f->cellspan + ((size_t)vi * f->height + line) * cw;
+	rc_line_clear (f, vi, line);
 	for (int i = 0; i < nsp; i++)
 	{
 		const int u0 = ls->u0[i], cnt = ls->u1[i] - u0;
 		rc_write_span (f, vw, vi, line, spanbase + i, ls->surf[i], u0, cnt, segbase);
+		for (int c = (u0 + 7) >> 3; (c << 3) + 8 <= u0 + cnt; c++)
+		{
+			cells[c].si = spanbase + i;
+			cells[c].sub = (uint32_t)(segbase * 8) * 8u + (uint32_t)((c << 3) - u0);
+		}
 		for (int q = rc_span_seg_count (cnt); q > 0; q--)
 			f->segspan[segbase++] = spanbase + i;
 		surfs[ls->surf[i]].hasspans = 1;
-		for (int c = (u0 + 7) >> 3; c <= (u0 + cnt - 1) >> 3; c++)
-			cells[c] = spanbase + i;
 	}
 }
 
@@ -1879,63 +1890,40 @@ RC_HD uint8_t rc_sky_texel (const rc_world_t *w, const rc_view_t *vw, int s, int
 }
 
 /* ------------------------------------------------------------------ stage 6: draw ------ */
-/* the 16 bytes of rc_surf_t the draw kernel needs */
-typedef struct {
-	int   cacheofs, cachewidth, srckind, flags;
-} rc_drawsurf_t;
-
 #ifdef __CUDACC__
-RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
-{
-	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(&s->cacheofs));
-	rc_drawsurf_t d;
-	d.cacheofs = (int)a.x; d.cachewidth = (int)a.y; d.srckind = (int)a.z; d.flags = (int)a.w;
-	return d;
-}
 RC_HD rc_span_t rc_load_span (const rc_span_t *p)
 {
 	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p)), b = __ldg (reinterpret_cast<const uint4 *>(p) + 1);
 	rc_span_t s;
-	s.view = (int)a.x; s.gsurf = (int)a.y; s.u = (int16_t)(a.z & 0xFFFF); s.count = (int16_t)(a.z >> 16);
-	s.v = (int16_t)(a.w & 0xFFFF); s.flags = (uint16_t)(a.w >> 16);
-	s.pixofs = (int)b.x; s.segbase = (int)b.y; s.izi0 = (int)b.z; s.izistep = (int)b.w;
+	s.u = (int16_t)(a.x & 0xFFFF); s.count = (int16_t)(a.x >> 16);
+	s.pixofs = (int)a.y; s.segbase = (int)a.z; s.gsurf = (int)a.w;
+	s.iziorg = (int)b.x; s.izistep = (int)b.y; s.cacheofs = (int)b.z; s.cwk = b.w;
 	return s;
+}
+RC_HD rc_sub_t rc_load_sub (const rc_sub_t *p)
+{
+	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p));
+	rc_sub_t r;
+	r.s = (int)a.x; r.t = (int)a.y; r.sstep = (int)a.z; r.tstep = (int)a.w;
+	return r;
 }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return __byte_perm (a, b, 0x5410); }
 #else
-RC_HD rc_drawsurf_t rc_load_drawsurf (const rc_surf_t *s)
-{
-	rc_drawsurf_t d;
-	d.cacheofs = s->cacheofs; d.cachewidth = s->cachewidth; d.srckind = s->pad; d.flags = s->drawflags;
-	return d;
-}
 RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
+RC_HD rc_sub_t rc_load_sub (const rc_sub_t *p) { return *p; }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 16); }
 #endif
 
-/* texture coordinates at a subdivision boundary (d_scan.c:291-300, 316-332, 347-360): the float
- * accumulators -> 16.16, clamped to [lo, bbextent] */
-RC_HD void rc_boundary_st (const rc_surf_t *s, float sdivz, float tdivz, float zi, int lo, int *ps, int *pt)
-{
-	const float z = (float)0x10000 / zi;
-	int ss = rc_addw (rc_f2i (sdivz * z), s->sadjust);
-	int tt = rc_addw (rc_f2i (tdivz * z), s->tadjust);
-	if (ss > s->bbextents) ss = s->bbextents; else if (ss < lo) ss = lo;
-	if (tt > s->bbextentt) tt = s->bbextentt; else if (tt < lo) tt = lo;
-	*ps = ss; *pt = tt;
-}
-
 /* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
- * D_DrawSpans8 (d_scan.c:278-360) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
- * subdivision boundary instead of once per pixel block.
- *   bnd[seg][i] = 16.16 (s, t) at subdivision boundary b = 8*segment + i, i = 0..9
+ * D_DrawSpans8 (d_scan.c:278-365) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
+ * subdivision instead of once per pixel block.  With B[b] = the 16.16 (s, t) at subdivision boundary b,
  *        b = 0              span start, clamped to [0, bbextent]
  *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
  *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
- *        b = nsub + 1       not a boundary: the (s, t) step of the last subdivision,
- *                           (B[nsub] - B[nsub-1]) / (left - 1) truncated (d_scan.c:364-365), so that the
- *                           draw kernel never divides
- *   span.izi0 / span.izistep (segment 0 only)
+ * the record of subdivision k is {B[k], step}: step = (B[k+1] - B[k]) >> 3 (d_scan.c:334-335), and for the
+ * last subdivision (B[nsub] - B[nsub-1]) / (left - 1) truncated (d_scan.c:364-365) -- the draw kernel
+ * never divides.  Segment 0 also completes the span record with what the draw kernel needs of the
+ * surface: 1/z start and step, texel block and pitch, kind.
  * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
  * adds: the segment replays the cheap adds from the span start and does the divide / convert /
  * clamp only for its own boundaries. */
@@ -1968,16 +1956,20 @@ RC_HD rc_segsurf_t rc_load_segsurf (const rc_surf_t *s)
 	return d;
 }
 
-RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
+/* `stage` (GPU): the thread's eight records go to this (shared-memory) slot, record i at index i ^ swz, and the
+ * caller copies them out; returns 1 when records were produced */
+RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_sub_t *stage = 0, int swz = 0)
 {
 	const int si = f->segspan[seg];
 	rc_span_t *spp = &f->spans[si];
 	const rc_span_t sp = rc_load_span (spp);
 	const int count = sp.count;
-	const rc_segsurf_t s = rc_load_segsurf (f->surfs + sp.gsurf);
+	const rc_surf_t *sfp = f->surfs + sp.gsurf;
+	const rc_segsurf_t s = rc_load_segsurf (sfp);
 	const int sidx = seg - sp.segbase;
-	const float du = (float)sp.u, dv = (float)sp.v;
+	const float du = (float)sp.u, dv = (float)(int)(sp.cwk >> 20);
 	const float zistepu = s.d_zistepu, zistepv = s.d_zistepv, ziorigin = s.d_ziorigin;
+	const int texels = s.srckind == RC_SRC_POOL || s.srckind == RC_SRC_TEXELS;
 	if (sidx == 0)
 	{
 		double zid = ziorigin + dv*zistepv + du*zistepu;
@@ -1987,11 +1979,25 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 			const float bgzi = -0.9, zero = 0;
 			zid = bgzi + dv*zero + du*zero;
 		}
-		spp->izi0 = rc_d2i (zid * 0x8000 * 0x10000);
-		spp->izistep = s.izistep;
+		/* the surface's cache block: creators of a block stored its pool offset in the surface-prep
+		 * stage, every other user of the same (face, mip, texture, light) key looks it up now */
+		int cacheofs = s.cacheofs;
+		if (s.srckind == RC_SRC_POOL && sfp->miplevel >= 0)
+			cacheofs = f->cachevals[sfp->miplevel];
+		uint32_t kind = RC_KIND_POOL;
+		if (s.srckind == RC_SRC_TEXELS) kind = (s.drawflags & RC_SURF_DRAWTURB) ? RC_KIND_TURB : RC_KIND_TEXELS;
+		else if (s.srckind == RC_SRC_SKY) kind = RC_KIND_SKY;
+		else if (s.srckind == RC_SRC_SOLID) kind = RC_KIND_SOLID;
+		const uint32_t cwk = (sp.cwk & 0xFFF80000u) | (kind << 16) | ((uint32_t)s.cachewidth & 0xFFFFu);
+		const int iziorg = rc_addw (rc_d2i (zid * 0x8000 * 0x10000), -rc_mulw (sp.pixofs, s.izistep));
+#ifdef __CUDACC__
+		*(reinterpret_cast<uint4 *>(spp) + 1) = make_uint4 ((uint32_t)iziorg, (uint32_t)s.izistep, (uint32_t)cacheofs, cwk);
+#else
+		spp->iziorg = iziorg; spp->izistep = s.izistep; spp->cacheofs = cacheofs; spp->cwk = cwk;
+#endif
 	}
-	if (s.srckind != RC_SRC_POOL && s.srckind != RC_SRC_TEXELS)
-		return;
+	if (!texels)
+		return 0;
 	const float sstepu = s.d_sdivzstepu, tstepu = s.d_tdivzstepu;
 	const float sdivz8stepu = sstepu * 8, tdivz8stepu = tstepu * 8, zi8stepu = zistepu * 8;
 	float sdivz = s.d_sdivzorigin + dv*s.d_sdivzstepv + du*sstepu;
@@ -2006,10 +2012,9 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 		zi += zi8stepu;
 	}
 	const int nsub = (count + 7) >> 3;
-	int *out = f->bnd + (size_t)seg * (RC_SEG_BND * 2);
 	const float m1 = (float)(count - ((nsub - 1) << 3) - 1);	/* spancountminus1 of the last subdivision */
 	const int sadjust = s.sadjust, tadjust = s.tadjust, bbextents = s.bbextents, bbextentt = s.bbextentt;
-	/* first the (cheap, serial) accumulator values of the ten boundaries, then ten independent
+	/* first the (cheap, serial) accumulator values of the nine boundaries, then nine independent
 	 * divide / convert / clamp chains the scheduler can overlap */
 	float as[RC_SEG_BND], at[RC_SEG_BND], az[RC_SEG_BND];
 	#pragma unroll
@@ -2042,74 +2047,92 @@ RC_HD void rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg)
 		if (tt > bbextentt) tt = bbextentt; else if (tt < lo) tt = lo;
 		st[2 * i] = ss; st[2 * i + 1] = tt;
 	}
+	/* per-pixel steps; the one truncating division of the span is done once, outside the unrolled loop */
+	int stp[16];
+	#pragma unroll
+	for (int i = 0; i < 8; i++)
 	{
-		/* entry nsub+1: the last subdivision's step.  Only segments where it lands at i >= 2 are ever
-		 * asked for it (an item reads entries (k&7) .. (k&7)+3 of segment k>>3, k <= nsub-1) */
-		const int it = nsub + 1 - (sidx << 3);
-		const int lastn = count - ((nsub - 1) << 3);		/* pixels of the last subdivision */
-		int ds_ = 0, dt_ = 0;
-		#pragma unroll
-		for (int i = 2; i < RC_SEG_BND; i++)
-			if (i == it) { ds_ = st[2*i - 2] - st[2*i - 4]; dt_ = st[2*i - 1] - st[2*i - 3]; }
-		if (it >= 2 && it < RC_SEG_BND)
+		stp[2 * i] = (st[2 * i + 2] - st[2 * i]) >> 3;
+		stp[2 * i + 1] = (st[2 * i + 3] - st[2 * i + 1]) >> 3;
+	}
+	{
+		const int il = nsub - 1 - (sidx << 3);			/* the last subdivision's place in this segment */
+		if (il >= 0 && il < 8)
 		{
+			const int lastn = count - ((nsub - 1) << 3);		/* its pixels */
+			int ds_ = 0, dt_ = 0;
+			#pragma unroll
+			for (int i = 0; i < 8; i++)
+				if (i == il) { ds_ = st[2 * i + 2] - st[2 * i]; dt_ = st[2 * i + 3] - st[2 * i + 1]; }
 			const int sstep = lastn > 1 ? ds_ / (lastn - 1) : 0, tstep = lastn > 1 ? dt_ / (lastn - 1) : 0;
 			#pragma unroll
-			for (int i = 2; i < RC_SEG_BND; i++)
-				if (i == it) { st[2*i] = sstep; st[2*i + 1] = tstep; }
+			for (int i = 0; i < 8; i++)
+				if (i == il) { stp[2 * i] = sstep; stp[2 * i + 1] = tstep; }
 		}
 	}
-	/* entries past nsub+1 are never read: the whole 96-byte record is written with six 16-byte stores */
+	/* records past the last subdivision are never used: all eight are written, one 16-byte store each */
+	rc_sub_t *out = f->sub + (size_t)seg * 8;
 #ifdef __CUDACC__
+	if (stage)
+	{
+		#pragma unroll
+		for (int i = 0; i < 8; i++)
+			reinterpret_cast<uint4 *>(stage)[i ^ swz] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)stp[2*i], (uint32_t)stp[2*i+1]);
+		return 1;
+	}
 	#pragma unroll
-	for (int i = 0; i < RC_SEG_BND / 2; i++)
-		reinterpret_cast<uint4 *>(out)[i] = make_uint4 ((uint32_t)st[4*i], (uint32_t)st[4*i+1], (uint32_t)st[4*i+2], (uint32_t)st[4*i+3]);
+	for (int i = 0; i < 8; i++)
+		reinterpret_cast<uint4 *>(out)[i] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)stp[2*i], (uint32_t)stp[2*i+1]);
 #else
-	for (int i = 0; i < RC_SEG_BND * 2; i++)
-		out[i] = st[i];
+	for (int i = 0; i < 8; i++)
+	{
+		out[i].s = st[2*i]; out[i].t = st[2*i+1]; out[i].sstep = stp[2*i]; out[i].tstep = stp[2*i+1];
+	}
 #endif
+	return 1;
 }
 
-/* One draw work item (D_DrawSpans8 d_scan.c:254-386 / Turbulent8 :121-251 / D_DrawSkyScans8
- * d_sky.c:58 / D_DrawSolidSurface d_edge.c:72-90, fused with D_DrawZSpans d_scan.c:388-439):
- * `cnt` (1..8) consecutive pixels of span `si` starting `rel` pixels into the span.
- *   cell items: the screen-aligned 8-pixel cell `t` (rel = 8*cell - u of the span covering it,
- *               cnt = 8 unless the span ends inside the cell)
- *   head items: a span's pixels up to the first cell boundary (rel = 0, cnt < 8)
- * The reference's 8-pixel subdivision is span relative, so the item touches subdivision
- * k = rel >> 3 from pixel a = rel & 7 on, and subdivision k+1 when a + cnt > 8.  Everything is
- * computed for 8 pixels and predicated on j < cnt: no per-count code paths. */
-RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, const rc_span_t sp, int rel, int cnt, const bool warpviews)
+/* The part of span `sp` that lies inside one 8-pixel window, general form (D_DrawSpans8 d_scan.c:254-386 /
+ * Turbulent8 :121-251 / D_DrawSkyScans8 d_sky.c:58 / D_DrawSolidSurface d_edge.c:72-90, fused with
+ * D_DrawZSpans d_scan.c:388-439).  Window pixel j is span pixel rel + j; rel may be negative (the span
+ * starts inside the window).  Colour and z (as the 16-bit value the reference stores) of the window
+ * pixels that belong to the span are written to px[] / zs[]; the others are left alone.  Returns the
+ * mask of the pixels written.
+ * The reference's 8-pixel subdivision is span relative, so the window touches subdivision
+ * k = rel >> 3 from pixel a = rel & 7 on, and subdivision k+1 when it runs past it.  Everything is
+ * computed for 8 pixels and predicated on the mask: no per-count code paths. */
+RC_HD unsigned rc_cell_part (const rc_world_t *w, const rc_frame_t *f, const rc_span_t sp, int rel, uint32_t *px, uint32_t *zs)
 {
-	const rc_drawsurf_t ds = rc_load_drawsurf (f->surfs + sp.gsurf);
-	const int srckind = ds.srckind;
+	const int lo = rel < 0 ? -rel : 0;
+	int hi = sp.count - rel;
+	if (hi > 8) hi = 8;
+	if (hi <= lo)
+		return 0u;
+	const unsigned vmask = (0xFFu >> (8 - hi)) & (0xFFu << lo);		/* bit j: window pixel j belongs to the span */
+	const int kind = (int)((sp.cwk >> 16) & 7u);
+	const int cachewidth = (int)(sp.cwk & 0xFFFFu);
+	const int spv = (int)(sp.cwk >> 20);
 	const int pix = sp.pixofs + rel;
-	const rc_view_t *vw = &f->views[sp.view];		/* only dereferenced on the rare paths */
-	uint8_t *pdest = f->fb + pix;
-	if (warpviews && (sp.flags & 1))		/* under water: the view's 320x200 warp buffer (the kernel variant without such views drops this) */
-		pdest = f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H) + RC_WARP_W * sp.v + sp.u + rel;
-	const unsigned vmask = 0xFFu >> (8 - cnt);		/* bit j: pixel j belongs to the item */
 
 	/* ---- z (D_DrawZSpans) ---- */
-	if (f->zb)
 	{
-		int16_t *pz = f->zb + pix;
 		const int izistep = sp.izistep;
 		int zz[8];
-		zz[0] = rc_addw (sp.izi0, rc_mulw (rel, izistep));
+		zz[0] = rc_addw (sp.iziorg, rc_mulw (pix, izistep));
 		#pragma unroll
 		for (int j = 1; j < 8; j++)
 			zz[j] = rc_addw (zz[j-1], izistep);
 		const int prev0 = rc_addw (zz[0], -izistep);
-		uint32_t zs[8];
+		uint32_t zt[8];
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
-			zs[j] = ((uint32_t)zz[j] >> 16);
+			zt[j] = ((uint32_t)zz[j] >> 16);
 		if ((prev0 | zz[0] | zz[1] | zz[2] | zz[3] | zz[4] | zz[5] | zz[6] | zz[7]) < 0)
 		{
 			/* a negative 1/z in reach: the second short of each 32-bit store of the reference gets the
 			 * sign extension of the first OR-ed in (d_scan.c:421-427: ltemp = izi >> 16 on a signed izi) */
-			const int a0 = (sp.pixofs - sp.view * f->width * f->height) & 1;	/* (zwidth*v + u) & 1: the short stored before the pairs */
+			const int view = sp.gsurf / f->surfcap;
+			const int a0 = (sp.pixofs - view * f->width * f->height) & 1;	/* (zwidth*v + u) & 1: the short stored before the pairs */
 			const int doublecount = (sp.count - a0) >> 1;
 			int prev = prev0;
 			#pragma unroll
@@ -2117,41 +2140,33 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 			{
 				const int r = rel + j - a0;
 				if (prev < 0 && r >= 0 && (r & 1) && (r >> 1) < doublecount)
-					zs[j] = 0xFFFFu;
+					zt[j] = 0xFFFFu;
 				prev = zz[j];
 			}
 		}
-		if (cnt == 8 && ((size_t)pz & 15) == 0)
-		{
-			uint4 q;
-			q.x = rc_zpair (zs[0], zs[1]); q.y = rc_zpair (zs[2], zs[3]); q.z = rc_zpair (zs[4], zs[5]); q.w = rc_zpair (zs[6], zs[7]);
-			*reinterpret_cast<uint4 *>(pz) = q;
-		}
-		else
-		{
-			#pragma unroll
-			for (int j = 0; j < 8; j++)
-				if (vmask & (1u << j))
-					pz[j] = (int16_t)zs[j];
-		}
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			if (vmask & (1u << j))
+				zs[j] = zt[j];
 	}
 
 	/* ---- colour ---- */
-	uint32_t px[8];
-	if (srckind == RC_SRC_SOLID)
+	if (kind == RC_KIND_SOLID)
 	{
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
-			px[j] = (uint32_t)(ds.cachewidth & 0xFF);
+			if (vmask & (1u << j))
+				px[j] = (uint32_t)(cachewidth & 0xFF);
 	}
-	else if (srckind == RC_SRC_SKY)
+	else if (kind == RC_KIND_SKY)
 	{
-		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form; an item
+		/* D_DrawSkyScans8, d_sky.c:58-131: 32-pixel subdivision, end points in closed form; a window
 		 * touches at most two of a span's 32-pixel runs */
+		const rc_view_t *vw = &f->views[sp.gsurf / f->surfcap];
 		int cur = -1, ss = 0, tt = 0, sstep = 0, tstep = 0;
 		unsigned long long packed = 0ull;		/* a rolled loop must not index px[] (registers) */
 		#pragma unroll 1
-		for (int j = 0; j < cnt; j++)
+		for (int j = lo; j < hi; j++)
 		{
 			const int pos = rel + j;
 			const int b32 = pos >> 5;			/* which 32-pixel run of the span */
@@ -2162,10 +2177,10 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 				const int spancount = remaining >= 32 ? 32 : remaining;
 				int snext = 0, tnext = 0;
 				cur = b32; sstep = 0; tstep = 0;
-				rc_sky_uv_to_st (vw, u0, sp.v, &ss, &tt);
+				rc_sky_uv_to_st (vw, u0, spv, &ss, &tt);
 				if (remaining - spancount)
 				{
-					rc_sky_uv_to_st (vw, u0 + spancount, sp.v, &snext, &tnext);
+					rc_sky_uv_to_st (vw, u0 + spancount, spv, &snext, &tnext);
 					sstep = (snext - ss) >> 5;
 					tstep = (tnext - tt) >> 5;
 				}
@@ -2174,7 +2189,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 					const int spancountminus1 = spancount - 1;
 					if (spancountminus1 > 0)
 					{
-						rc_sky_uv_to_st (vw, u0 + spancountminus1, sp.v, &snext, &tnext);
+						rc_sky_uv_to_st (vw, u0 + spancountminus1, spv, &snext, &tnext);
 						sstep = (snext - ss) / spancountminus1;
 						tstep = (tnext - tt) / spancountminus1;
 					}
@@ -2189,56 +2204,32 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 		}
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
-			px[j] = (uint32_t)(packed >> (8 * j)) & 0xFFu;
+			if (vmask & (1u << j))
+				px[j] = (uint32_t)(packed >> (8 * j)) & 0xFFu;
 	}
 	else
 	{
-		const int turb = (ds.flags & RC_SURF_DRAWTURB) != 0;
-		const uint8_t *pbase = (srckind == RC_SRC_TEXELS ? w->texels : f->cachepool) + ds.cacheofs;
-		const int cachewidth = ds.cachewidth;
-		const int k = rel >> 3, a = rel & 7;
-		/* boundaries k, k+1, k+2 of the span, precomputed by rc_span_seg */
-		const int *bp = f->bnd + ((size_t)(sp.segbase + (k >> 3)) * RC_SEG_BND + (k & 7)) * 2;
-		const int left = sp.count - (k << 3);	/* pixels from the start of subdivision k to the end of the span */
-		const int two = a + cnt > 8;		/* the item runs on into subdivision k+1 */
-		/* bp[0..1] = B[k], bp[2..3] = B[k+1], bp[4..5] = B[k+2] -- or, when k is the last subdivision, its
-		 * precomputed step; bp[6..7] = the step of k+1 when that one is the last */
-		int s0, t0, s1, t1, s2 = 0, t2 = 0, s3 = 0, t3 = 0, sstep0, tstep0, sstep1 = 0, tstep1 = 0;
-		s0 = RC_LDG (&bp[0]); t0 = RC_LDG (&bp[1]); s1 = RC_LDG (&bp[2]); t1 = RC_LDG (&bp[3]);
-		if (two || left <= 8) { s2 = RC_LDG (&bp[4]); t2 = RC_LDG (&bp[5]); }
-		if (two && left <= 16) { s3 = RC_LDG (&bp[6]); t3 = RC_LDG (&bp[7]); }
-		if (left > 8)
-		{
-			sstep0 = (s1 - s0) >> 3;
-			tstep0 = (t1 - t0) >> 3;
-			if (left > 16)
-			{
-				sstep1 = (s2 - s1) >> 3;
-				tstep1 = (t2 - t1) >> 3;
-			}
-			else
-			{
-				sstep1 = s3;
-				tstep1 = t3;
-			}
-		}
-		else
-		{
-			sstep0 = s2;
-			tstep0 = t2;
-		}
-		int ss = rc_addw (s0, rc_mulw (a, sstep0)), tt = rc_addw (t0, rc_mulw (a, tstep0));
+		const int turb = kind == RC_KIND_TURB;
+		const uint8_t *pbase = (kind == RC_KIND_POOL ? f->cachepool : w->texels) + sp.cacheofs;
+		/* a span that starts inside the window: subdivision 0 from window pixel -rel on (a < 0, no crossing) */
+		const int k = rel < 0 ? 0 : rel >> 3, a = rel < 0 ? rel : rel & 7;
+		const rc_sub_t *rp = f->sub + (size_t)sp.segbase * 8 + k;
+		const rc_sub_t r0 = rc_load_sub (rp);
+		rc_sub_t r1 = r0;
+		if (a + hi > 8)		/* the window runs on into subdivision k+1 */
+			r1 = rc_load_sub (rp + 1);
+		int sstep = r0.sstep, tstep = r0.tstep;
+		int ss = rc_addw (r0.s, rc_mulw (a, sstep)), tt = rc_addw (r0.t, rc_mulw (a, tstep));
 		const int *turbtab = w->sintable;
 		if (turb)
-			turbtab += vw->turbphase;
+			turbtab += f->views[sp.gsurf / f->surfcap].turbphase;
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
 		{
 			if (a + j == 8)
 			{
-				ss = s1; tt = t1; sstep0 = sstep1; tstep0 = tstep1;
+				ss = r1.s; tt = r1.t; sstep = r1.sstep; tstep = r1.tstep;
 			}
-			px[j] = 0;
 			if (vmask & (1u << j))
 			{
 				if (!turb)
@@ -2251,11 +2242,37 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 					px[j] = RC_LDG (&pbase[(tturb << 6) + sturb]);
 				}
 			}
-			ss = rc_addw (ss, sstep0);
-			tt = rc_addw (tt, tstep0);
+			ss = rc_addw (ss, sstep);
+			tt = rc_addw (tt, tstep);
 		}
 	}
-	if (cnt == 8 && ((size_t)pdest & 7) == 0)
+	return vmask;
+}
+
+/* stores the window pixels of `vmask`: one aligned 8-byte colour store and one aligned 16-byte z store
+ * when the window is complete and aligned, single pixels otherwise */
+RC_HD void rc_store_part (uint8_t *pdest, int16_t *pz, unsigned vmask, const uint32_t *px, const uint32_t *zs)
+{
+	if (pz)
+	{
+#ifdef __CUDACC__
+		if (vmask == 0xFFu && ((size_t)pz & 15) == 0)
+		{
+			uint4 q;
+			q.x = rc_zpair (zs[0], zs[1]); q.y = rc_zpair (zs[2], zs[3]); q.z = rc_zpair (zs[4], zs[5]); q.w = rc_zpair (zs[6], zs[7]);
+			*reinterpret_cast<uint4 *>(pz) = q;
+		}
+		else
+#endif
+		{
+			#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (vmask & (1u << j))
+					pz[j] = (int16_t)zs[j];
+		}
+	}
+#ifdef __CUDACC__
+	if (vmask == 0xFFu && ((size_t)pdest & 7) == 0)
 	{
 		uint2 q;
 		q.x = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
@@ -2263,6 +2280,7 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 		*reinterpret_cast<uint2 *>(pdest) = q;
 	}
 	else
+#endif
 	{
 		#pragma unroll
 		for (int j = 0; j < 8; j++)
@@ -2271,28 +2289,113 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, int si, con
 	}
 }
 
-/* the two kinds of draw work item: screen cell `c` of row `row` = view * height + line, and the head of span `si` */
+/* colour destination of span pixel `rel`: the frame buffer, or the view's 320x200 warp buffer when it
+ * renders under water (r_dowarp; the kernel variant without such views drops the test) */
+RC_HD uint8_t *rc_span_dest (const rc_frame_t *f, const rc_span_t sp, int rel, const bool warpviews)
+{
+	if (warpviews && (sp.cwk & RC_SPAN_WARPBIT))
+	{
+		const rc_view_t *vw = &f->views[sp.gsurf / f->surfcap];
+		return f->warpbuf + (size_t)vw->warp_index * (RC_WARP_W * RC_WARP_H) + RC_WARP_W * (int)(sp.cwk >> 20) + sp.u + rel;
+	}
+	return f->fb + sp.pixofs + rel;
+}
+
+/* one span's share of a window, drawn on its own */
+RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, const rc_span_t sp, int rel, const bool warpviews)
+{
+	uint32_t px[8], zs[8];
+	#pragma unroll
+	for (int j = 0; j < 8; j++) { px[j] = 0; zs[j] = 0; }
+	const unsigned vmask = rc_cell_part (w, f, sp, rel, px, zs);
+	if (vmask)
+		rc_store_part (rc_span_dest (f, sp, rel, warpviews), f->zb ? f->zb + sp.pixofs + rel : (int16_t *)0, vmask, px, zs);
+}
+
+/* The two kinds of draw work item.
+ * Full cells: screen cell `c` of row `row` = view * height + line, covered by one span (the GPU draws
+ * the common case -- cache block or texel blob, no negative 1/z, frame-buffer target -- with its own
+ * straight-line code, k_draw, and comes here for the rest). */
 RC_HD void rc_draw_cell (const rc_world_t *w, const rc_frame_t *f, int row, int c)
 {
 	const int cw = (f->width + 7) >> 3;
-	const int si = RC_LDG (&f->cellspan[(size_t)row * cw + c]);
+	const int si = f->cellspan[(size_t)row * cw + c].si;
 	if (si < 0)
 		return;
 	const rc_span_t sp = rc_load_span (&f->spans[si]);
-	const int rel = (c << 3) - sp.u;
-	int cnt = sp.count - rel;
-	if (cnt > 8) cnt = 8;
-	rc_draw_pixels (w, f, si, sp, rel, cnt, true);
+	rc_draw_pixels (w, f, sp, (c << 3) - sp.u, true);
 }
 
-RC_HD void rc_draw_head (const rc_world_t *w, const rc_frame_t *f, int si, const bool warpviews = true)
+/* Mixed cells: the screen cells that hold a span boundary (or an end of the view rectangle).  They are
+ * drawn WHOLE by one owner -- complete cells leave as one aligned colour store and one aligned z store
+ * instead of single pixels from two threads.  Two candidate items per span:
+ *   which = 0: the cell around the span's first pixel, owned by the first span that starts inside it
+ *              (the share of the span before it, which covers the cell's first pixel, comes first);
+ *   which = 1: the cell around the span's end, when the span covers that cell's first pixel and no
+ *              later span of the row starts inside it (the right end of the view rectangle).
+ * Returns 1 and the first span to visit, the cell's column and the row's first pixel index. */
+RC_HD int rc_mixed_owner (const rc_frame_t *f, int si, int which, int nspans, int *first, int *cellx, int *rowstart)
 {
-	const rc_span_t sp = rc_load_span (&f->spans[si]);
-	int cnt = 8 - (sp.u & 7);
-	if (cnt == 8 || sp.count <= 0)
-		return;
-	if (cnt > sp.count) cnt = sp.count;
-	rc_draw_pixels (w, f, si, sp, 0, cnt, warpviews);
+	const rc_span_t *sp = &f->spans[si];
+	const int u = sp->u, count = sp->count, e = u + count;
+	if (count <= 0)
+		return 0;
+	*rowstart = sp->pixofs - u;
+	*first = si;
+	if (!which)
+	{
+		if (!(u & 7))
+			return 0;
+		*cellx = u & ~7;
+		if (si > 0)
+		{
+			const rc_span_t *pv = sp - 1;
+			if (pv->pixofs - pv->u == *rowstart && pv->count > 0)
+			{
+				if (pv->u > *cellx)
+					return 0;		/* an earlier span starts inside the same cell */
+				*first = si - 1;
+			}
+		}
+		return 1;
+	}
+	if (!(e & 7) || u > (e & ~7))
+		return 0;
+	*cellx = e & ~7;
+	if (si + 1 < nspans)
+	{
+		const rc_span_t *nx = sp + 1;
+		if (nx->pixofs - nx->u == *rowstart && nx->count > 0 && nx->u < *cellx + 8)
+			return 0;			/* the next span starts inside that cell and owns it */
+	}
+	return 1;
+}
+
+RC_HD void rc_draw_mixed_cell (const rc_world_t *w, const rc_frame_t *f, int first, int nspans, int cellx, int rowstart, const bool warpviews)
+{
+	uint32_t px[8], zs[8];
+	#pragma unroll
+	for (int j = 0; j < 8; j++) { px[j] = 0; zs[j] = 0; }
+	unsigned mask = 0u;
+	for (int s = first; s < nspans; s++)
+	{
+		const rc_span_t sp = rc_load_span (&f->spans[s]);
+		if (sp.pixofs - sp.u != rowstart || sp.u >= cellx + 8)
+			break;
+		if (warpviews && (sp.cwk & RC_SPAN_WARPBIT))
+			rc_draw_pixels (w, f, sp, cellx - sp.u, warpviews);	/* warp buffer rows are not cell aligned: span by span */
+		else
+			mask |= rc_cell_part (w, f, sp, cellx - sp.u, px, zs);
+	}
+	if (mask)
+		rc_store_part (f->fb + rowstart + cellx, f->zb ? f->zb + rowstart + cellx : (int16_t *)0, mask, px, zs);
+}
+
+RC_HD void rc_draw_mixed (const rc_world_t *w, const rc_frame_t *f, int si, int which, int nspans, const bool warpviews = true)
+{
+	int first, cellx, rowstart;
+	if (rc_mixed_owner (f, si, which, nspans, &first, &cellx, &rowstart))
+		rc_draw_mixed_cell (w, f, first, nspans, cellx, rowstart, warpviews);
 }
 
 

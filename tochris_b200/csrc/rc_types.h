@@ -243,17 +243,37 @@ typedef struct {            /* surf_t replacement (r_shared.h:125-147) + drawing
     int   pad2[4];
 } rc_surf_t;                /* 128 B */
 
-typedef struct {            /* espan_t replacement (r_shared.h:117-121) + per-span draw state; 32 B, two vector loads */
-    int      view;
-    int      gsurf;         /* view * surfcap + surf_t slot */
+typedef struct {            /* espan_t replacement (r_shared.h:117-121) + everything the draw kernel needs of the span's
+                             * surface; 32 B, two vector loads.  Written by the scan stage (u, count, pixofs, segbase, gsurf,
+                             * v / warp bits of cwk) and completed by the segment stage (izi0, izistep, cacheofs, cwk) */
     int16_t  u, count;
-    int16_t  v;
-    uint16_t flags;         /* bit 0: the view renders into its 320x200 warp buffer (r_dowarp) */
     int      pixofs;        /* (view * height + v) * width + u: index of the first pixel in the batch's colour / z planes */
-    int      segbase;       /* first 64-pixel segment record of the span (subdivision boundaries, see rc_span_seg) */
-    int      izi0;          /* 1/z at the span start in D_DrawZSpans fixed point (d_scan.c:411-413), by the segment kernel */
+    int      segbase;       /* first 64-pixel segment record of the span (8 subdivision records each, see rc_span_seg) */
+    int      gsurf;         /* view * surfcap + surf_t slot */
+    /* -- second 16 bytes: all the draw kernel's full-cell path reads -- */
+    int      iziorg;        /* D_DrawZSpans fixed-point 1/z (d_scan.c:411-413) extrapolated to pixel index 0 of the planes:
+                             * izi(pixel p) = iziorg + p * izistep in wrapping 32-bit arithmetic, as the reference's adds */
     int      izistep;       /* (int)(d_zistepu * 0x8000 * 0x10000), d_scan.c:399 */
+    int      cacheofs;      /* byte offset of the surface's texel block (cache pool or texel blob) */
+    uint32_t cwk;           /* bits 0-15 row pitch of the block (constant colour for RC_KIND_SOLID), 16-18 RC_KIND_*,
+                             * 19 the view renders into its 320x200 warp buffer (r_dowarp), 20-31 scanline v */
 } rc_span_t;
+#define RC_KIND_POOL   0    /* surface-cache block, D_DrawSpans8 */
+#define RC_KIND_TEXELS 1    /* texel blob (sky-box pictures), D_DrawSpans8 */
+#define RC_KIND_TURB   2    /* texel blob, Turbulent8 */
+#define RC_KIND_SKY    3    /* D_DrawSkyScans8 */
+#define RC_KIND_SOLID  4    /* D_DrawSolidSurface */
+#define RC_SPAN_WARPBIT 0x80000u
+
+typedef struct {            /* one 8-pixel subdivision of a span (d_scan.c:278-365): 16.16 texture coordinates of its
+                             * first pixel and the per-pixel step the reference uses inside it */
+    int s, t, sstep, tstep;
+} rc_sub_t;
+
+typedef struct {            /* draw work item: a screen-aligned 8-pixel cell covered by one span */
+    int      si;            /* span, -1: none (the cell is drawn by span heads / tails, or lies outside the view rectangle) */
+    uint32_t sub;           /* (segbase * 8 + k) << 3 | a: the subdivision record of the cell's first pixel and its position in it */
+} rc_cell_t;
 
 /* surface-cache build job (d_surf.c:196 D_CacheSurface miss) */
 typedef struct {

@@ -20,7 +20,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def sass_lines(kernel):
+def sass_lines(kernel, mangled=None):
     tmp = tempfile.mkdtemp(prefix="cub_")
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "tochris_b200", "libref_cuda.so")], cwd=tmp,
                           stdout=subprocess.DEVNULL)
@@ -29,7 +29,7 @@ def sass_lines(kernel):
     lines, cur, infn = [], ("?", 0), False
     for ln in out.splitlines():
         if ln.startswith(".text."):
-            infn = re.search(r"\b%s\b|_Z\d+%s" % (kernel, kernel), ln) is not None
+            infn = (mangled in ln) if mangled else re.search(r"\b%s\b|_Z\d+%s" % (kernel, kernel), ln) is not None
             continue
         if not infn:
             continue
@@ -48,6 +48,7 @@ def main():
     ap.add_argument("kernel")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0, help="which launch of the kernel in the report")
+    ap.add_argument("--mangled", default=None, help="substring of the mangled name, to pick one template instance (e.g. k_drawILb0E)")
     a = ap.parse_args()
     txt = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", "--kernel-name", a.kernel], capture_output=True, text=True).stdout
     # the page repeats per launch: split on the "Kernel Name" header rows
@@ -56,7 +57,7 @@ def main():
     hdr = rows[0]
     ci = {n: hdr.index(n) for n in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed")}
     body = [r for r in rows[1:] if len(r) > ci["Thread Instructions Executed"]]
-    sl = sass_lines(a.kernel)
+    sl = sass_lines(a.kernel, a.mangled)
     if len(sl) != len(body):
         print(f"warning: {len(body)} SASS rows in the report vs {len(sl)} in the current cubin (different build?)")
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
