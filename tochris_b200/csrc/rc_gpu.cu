@@ -736,14 +736,27 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			dst[1] = make_uint4 (0u, 0u, 0u, vflags);
 			sw->su[j] = myseg;
 			surfs[sf].hasspans = 1;
-			for (int q = 0; q < c; q++)
-				f.segspan[myseg + q] = spanbase + j;
 		}
 		segbase += __shfl_sync (0xFFFFFFFFu, incl, 31);
 	}
 	__syncwarp ();
+	/* owner of every segment of the line: the last span whose first segment is not after it */
+	{
+		const int seg0 = (int)(old >> 32);
+		for (int q = lane; q < nseg; q += 32)
+		{
+			int lo = 0, hi = nsp - 1, idx = 0;
+			while (lo <= hi)
+			{
+				const int mid = (lo + hi) >> 1;
+				if (sw->su[mid] <= seg0 + q) { idx = mid; lo = mid + 1; }
+				else hi = mid - 1;
+			}
+			f.segspan[seg0 + q] = spanbase + idx;
+		}
+	}
+	__syncwarp ();
 	/* cell map: the span that covers all of pixels 8c .. 8c+7, if one does (spans are sorted and disjoint) */
-	int nfull = 0;
 	for (int c = lane; c < cw; c += 32)
 	{
 		const int x = c << 3;
@@ -756,17 +769,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		}
 		int2 cell = make_int2 (-1, 0);
 		if (idx >= 0 && x + 8 <= sw->a.sp.x1[idx])
-		{
 			cell = make_int2 (spanbase + idx, (int)((uint32_t)sw->su[idx] * 64u + (uint32_t)(x - sw->a.sp.x0[idx])));
-			nfull++;
-		}
 		cells[c] = cell;
 	}
-	#pragma unroll
-	for (int o = 16; o; o >>= 1)
-		nfull += __shfl_xor_sync (0xFFFFFFFFu, nfull, o);
-	if (lane == 0)
-		atomicAdd (&f.alloc[4], (unsigned long long)nfull);		/* statistics only */
 }
 
 __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -1020,6 +1025,7 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 	};
 
 	unsigned t0 = tile;
+	unsigned nfull = 0;			/* statistics: cells drawn here or queued */
 	int2 c0, c1; uint32_t p0, p1;
 	fetch_cell (c0, p0);
 	fetch_cell (c1, p1);
@@ -1049,6 +1055,7 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 #endif
 		/* cells the straight-line code does not handle are queued for the general kernel (k_ends):
 		 * one atomicAdd per warp */
+		nfull += cur.si >= 0;
 		const bool slow = cur.si >= 0 && !draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, cur.r0, cur.r1, fast_ok);
 		const unsigned sm = __ballot_sync (0xFFFFFFFFu, slow);
 		if (sm)
@@ -1068,7 +1075,11 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 		c1 = c2; p1 = p2;
 		t0 += wstride;
 	}
-
+	#pragma unroll
+	for (int o = 16; o; o >>= 1)
+		nfull += __shfl_xor_sync (0xFFFFFFFFu, nfull, o);
+	if (lane == 0 && nfull)
+		atomicAdd (&f.alloc[4], (unsigned long long)nfull);
 }
 
 __device__ __noinline__ void draw_mixed_general (const rc_world_t *w, const rc_frame_t *f, int first, int nspans, int cellx, int rowstart, bool warpviews)
