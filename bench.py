@@ -267,10 +267,11 @@ def run_ours(args):
                 sl = arrived[q * n * px1:(q + 1) * n * px1].to(torch.int64)
                 gather_check &= bool(((sl * wts).sum() == allsums[q][0]) and (sl.sum() == allsums[q][1]))
 
-    # ---- e2e: the reference-facing C-ABI call with HOST buffers ----
+    # ---- e2e: the reference-facing C-ABI calls with HOST buffers ----
+    # (1) blocking RC_RenderViews, one call per step, timed call by call
     fb_host = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
     fb_np = fb_host.numpy()
-    e2e_s = 0.0
+    e2e_sync_s = 0.0
     for k in range(3 + args.steps):
         if not args.keep_cache:
             r.flush_caches()
@@ -281,7 +282,34 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         status |= st
         if k >= 3:
-            e2e_s += dt
+            e2e_sync_s += dt
+    ref_sum = int(fb_np.astype(np.uint64).sum())
+    # (2) the pipelined form a stream of batches uses (RC_RenderViewsAsync / RC_WaitViews, two batches in flight, two
+    # pinned output buffers): every step still uploads its refdefs, flushes the surface cache and L2, renders and brings
+    # its frame buffers to the host inside the timed region; the copy of step k overlaps the kernels of step k+1.
+    fb_host2 = [torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    fb_np2 = [t.numpy() for t in fb_host2]
+    e2e_ok = True
+
+    def pipelined(steps):
+        nonlocal status
+        for k in range(steps):
+            if k >= 2:
+                st = r.wait()
+                status |= st
+            if not args.keep_cache:
+                r.flush_caches()
+            l2flush.zero_()
+            r.render_async(rds, n, fb_np2[k & 1])
+        for k in range(min(2, steps)):
+            status |= r.wait()
+    pipelined(3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_ok &= all(int(b.astype(np.uint64).sum()) == ref_sum for b in fb_np2)
     # ---- extra: the same steps with the surface cache KEPT across steps, which is how ref_soft (and the CPU arm
     # below, after its warm-up pass) normally runs: D_CacheSurface hits.  Reported beside `value`, not as it.
     warm_ms = None
@@ -309,10 +337,10 @@ def run_ours(args):
     r.set_profiling(False)
     torch.cuda.synchronize()
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,7 +390,10 @@ def run_ours(args):
         "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),
         "e2e": {"value": round(n * world * args.steps / e2e_s, 1), "unit": "frames/s",
                 "h2d_bytes_per_step": int(n * 648), "d2h_bytes_per_step": int(px), "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
-                "note": "RC_RenderViews: refdef_t[] in host memory -> 8-bit framebuffers in pinned host memory (z stays on device)"},
+                "note": "RC_RenderViewsAsync / RC_WaitViews, two batches in flight: refdef_t[] in host memory -> 8-bit framebuffers in pinned host memory (z stays on device); every step uploads, flushes the surface cache and L2, renders and downloads inside the timed region, the PCIe copy of step k overlapping the kernels of step k+1",
+                "verified": bool(e2e_ok),
+                "blocking_call": {"value": round(n * world * args.steps / e2e_sync_s, 1), "ms_per_step": round(e2e_sync_s / args.steps * 1e3, 4),
+                                  "note": "RC_RenderViews, one blocking call per step, timed call by call"}},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "status": status_names(status),

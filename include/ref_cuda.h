@@ -133,6 +133,16 @@ int  RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_o
  * (a cudaStream_t, 0 = legacy default) and is complete when the stream reaches this point. */
 int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status);
 
+/* Pipelined form of RC_RenderViews for streams of batches (timedemo-style replay, RL roll-outs): the call
+ * enqueues the batch and returns; RC_WaitViews blocks until the OLDEST outstanding call has delivered its
+ * frame buffers (page-locked host memory recommended) and returns its status.  At most two calls may be
+ * outstanding, so the device->host copy of one batch (PCIe: the longest single item) runs while the next
+ * batch is rendered.  The refdef_t array and what it points to may be reused as soon as the call returns;
+ * fb_out / z_out belong to the renderer until the matching RC_WaitViews.  A status with RC_STAT_SPAN_POOL or
+ * RC_STAT_CACHE_POOL set means the batch must be rendered again with RC_RenderViews (which grows the pools). */
+int  RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out);
+int  RC_WaitViews (int *status);
+
 /* Overlapping a consumer with the draw stage.  With a callback set, RC_RenderViewsDevice draws the
  * views of a batch in `ngroups` groups (batches with alias models, particles or under-water views are
  * still drawn in one piece); after a group's draw kernel is enqueued, `side_stream` (a cudaStream_t)

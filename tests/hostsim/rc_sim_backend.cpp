@@ -293,6 +293,24 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 	return rc_gpu_render (g, batch, fb_out, z_out, NULL, status, err, errlen);
 }
 
+/* the simulator has nothing to overlap: the "asynchronous" call renders at once and the wait hands back its status */
+static int sim_async_status[2], sim_async_head, sim_async_n;
+int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen)
+{
+	if (sim_async_n >= 2) { snprintf (err, errlen, "two asynchronous calls already in flight: RC_WaitViews first"); return RC_ERR_ARG; }
+	int st = 0;
+	int r = rc_gpu_render_host (g, batch, fb_out, z_out, &st, err, errlen);
+	if (r == RC_OK) { sim_async_status[(sim_async_head + sim_async_n) & 1] = st; sim_async_n++; }
+	return r;
+}
+int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
+{
+	if (sim_async_n <= 0) { snprintf (err, errlen, "no asynchronous call in flight"); return RC_ERR_ARG; }
+	if (status) *status = sim_async_status[sim_async_head];
+	sim_async_head ^= 1; sim_async_n--;
+	return RC_OK;
+}
+
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }
 void rc_gpu_set_profiling (rc_gpu_t *g, int on) { (void)g; (void)on; }
 

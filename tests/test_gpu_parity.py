@@ -122,3 +122,38 @@ def test_c4_full_batch_properties(assets_dir, oracle_available):
     assert r["n"] == 65536 and r["status"] == 0
     assert (r["fb"] == o["fb"]).all() and (r["z"] == o["z"]).all()
     assert r["same"]
+
+
+@pytest.mark.gpu
+def test_async_pipeline_matches_blocking_call(assets_dir):
+    """RC_RenderViewsAsync / RC_WaitViews (two batches in flight, copies overlapping the next batch's kernels)
+    deliver the same bytes as the blocking RC_RenderViews, in order."""
+    import numpy as np
+    from tochris_b200.api import RefCuda
+    from tochris_b200.scenes import views
+    r = RefCuda(assets_dir, 320, 240)
+    r.load_world("maps/multi.bsp")
+    batches = []
+    for b in range(4):
+        specs = rcutil.scene_views("multi", 16, time=0.5 + b, time_step=0.07)
+        batches.append(views.build_refdefs(specs, 320, 240, model_resolver=r.model))
+    want = []
+    for rds in batches:
+        fb, z, st = r.render(rds)
+        assert st == 0
+        want.append((fb.copy(), z.copy()))
+    bufs = [(np.zeros((16, 240, 320), np.uint8), np.zeros((16, 240, 320), np.int16)) for _ in range(2)]
+    got = []
+    for k, rds in enumerate(batches):
+        if k >= 2:
+            assert r.wait() == 0
+            got.append((bufs[k & 1][0].copy(), bufs[k & 1][1].copy()))
+        r.render_async(rds, 16, bufs[k & 1][0], bufs[k & 1][1])
+    for k in range(2, 4):
+        assert r.wait() == 0
+        got.append((bufs[k & 1][0].copy(), bufs[k & 1][1].copy()))
+    with pytest.raises(RuntimeError):
+        r.wait()                       # nothing outstanding
+    for (wf, wz), (gf, gz) in zip(want, got):
+        assert np.array_equal(wf, gf) and np.array_equal(wz, gz)
+    r.shutdown()

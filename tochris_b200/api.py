@@ -83,6 +83,8 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_RenderViewsAsync.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p]
+        L.RC_WaitViews.argtypes = [C.POINTER(C.c_int)]
         L.RC_RenderViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.RC_DebugRead.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.RC_SetSkybox.argtypes = [C.c_char_p]
@@ -134,6 +136,20 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"RC_RenderViews failed ({rc}): {self.err()}")
         return fb, (z if want_z else None), st.value
+
+    def render_async(self, rds, n: int, fb, z=None) -> None:
+        """RC_RenderViewsAsync: enqueue a batch into caller-owned (pinned) numpy buffers; at most two outstanding."""
+        rc = self.lib.RC_RenderViewsAsync(rds, n, fb.ctypes.data, z.ctypes.data if z is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"RC_RenderViewsAsync failed ({rc}): {self.err()}")
+
+    def wait(self) -> int:
+        """RC_WaitViews: block until the oldest outstanding batch has arrived; returns its status bits."""
+        st = C.c_int(0)
+        rc = self.lib.RC_WaitViews(C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"RC_WaitViews failed ({rc}): {self.err()}")
+        return st.value
 
     def render_device(self, rds, n: int, fb_ptr: int, z_ptr: int = 0, stream: int = 0) -> int:
         st = C.c_int(0)

@@ -28,6 +28,7 @@ static struct {
 	struct model_s *world;
 	char         err[1024];
 	int          unsupported;
+	int          async_unsupported[2]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
 	rc_view_t   *viewscratch; int viewscratchcap;
@@ -561,6 +562,32 @@ int RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_ou
 	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
 	r = rc_gpu_render_host (rc.gpu, &rc.batch, fb_out, z_out, status, rc.err, sizeof(rc.err));
 	if (status && rc.unsupported) *status |= RC_STAT_UNSUPPORTED_ENT;
+	return r;
+}
+
+int RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out)
+{
+	int r = rc_prepare_views (views, n);
+	if (r != RC_OK) return r;
+	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
+	r = rc_gpu_render_host_async (rc.gpu, &rc.batch, fb_out, z_out, rc.err, sizeof(rc.err));
+	if (r == RC_OK)
+	{
+		rc.async_unsupported[rc.async_tail & 1] = rc.unsupported; rc.async_tail++;
+	}
+	return r;
+}
+
+int RC_WaitViews (int *status)
+{
+	int r;
+	if (!rc.gpu) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	r = rc_gpu_wait_host (rc.gpu, status, rc.err, sizeof(rc.err));
+	if (r == RC_OK)
+	{
+		if (status && rc.async_unsupported[rc.async_head & 1]) *status |= RC_STAT_UNSUPPORTED_ENT;
+		rc.async_head++;
+	}
 	return r;
 }
 

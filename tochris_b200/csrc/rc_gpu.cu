@@ -80,6 +80,10 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
+	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
+	uint8_t *d_afb[2]; int16_t *d_azb[2]; size_t aoutcap[2];
+	cudaEvent_t adone_s[2], adone_copy[2]; int *astatus;	/* pinned */
+	int ahead, ainflight, amode;	/* amode: slot + 1 while an asynchronous call is being enqueued */
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
@@ -1330,6 +1334,14 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	memset (&g->stats, 0, sizeof(g->stats));
 	g->device = device; g->width = width; g->height = height;
 	g->haveworld = false; g->skybox = 0; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
+	for (int i = 0; i < 2; i++)
+	{
+		g->d_afb[i] = NULL; g->d_azb[i] = NULL; g->aoutcap[i] = 0;
+		cudaEventCreateWithFlags (&g->adone_s[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags (&g->adone_copy[i], cudaEventDisableTiming);
+	}
+	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * 2, cudaHostAllocDefault);
+	g->ahead = 0; g->ainflight = 0; g->amode = 0;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
@@ -1402,6 +1414,8 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_cachepool); cudaFree (g->d_cachekeys); cudaFree (g->d_cachevals);
 	cudaFree (g->d_alloc); cudaFree (g->d_status); cudaFree (g->d_sintable); cudaFree (g->d_intsintable);
 	cudaFree (g->d_fb); cudaFree (g->d_zb); cudaFree (g->d_dlights); cudaFree (g->d_warpbuf);
+	for (int i = 0; i < 2; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
+	cudaFreeHost (g->astatus);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
@@ -1758,7 +1772,9 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 				g->groupfn (g->groupuser, first_view + f.drawview0, nv);
 		}
 		g->stats.kernel_launches += 3 * ngroups - 1;
-		if (g->host_fb)
+		if (g->host_fb && g->amode)
+			cudaEventRecord (g->adone_copy[g->amode - 1], side);	/* the caller waits for it (rc_gpu_wait_host); the next call's kernels do not */
+		else if (g->host_fb)
 		{
 			cudaEventRecord (g->evcopy, side);
 			cudaStreamWaitEvent (s, g->evcopy, 0);		/* the stream's work is complete only when the copies are */
@@ -2015,6 +2031,14 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 				if (g->profiling) collect_stats (g, cn, true);
 			}
 		}
+		if (g->amode)
+		{
+			/* pipelined call: the status lands in pinned memory, nothing waits here; a pool overflow is
+			 * reported by rc_gpu_wait_host and the caller renders that batch again with the blocking call */
+			CK (cudaMemcpyAsync (&g->astatus[g->amode - 1], g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+			CK (cudaEventRecord (g->adone_s[g->amode - 1], s));
+			break;
+		}
 		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
 #ifdef RC_FRONT_TIMING
@@ -2066,6 +2090,49 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 	int r = rc_gpu_render (g, batch, g->d_fb, g->d_zb, NULL, status, err, errlen);
 	g->host_fb = NULL; g->host_z = NULL;
 	return r;
+}
+
+/* Pipelined host output: enqueues the batch and returns; at most two calls in flight.  The device->host
+ * copies of this call run on the copy stream while the next call's kernels run, each call drawing into
+ * its own device planes. */
+int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen)
+{
+	const int n = batch->n;
+	size_t px = (size_t)g->width * g->height;
+	cudaSetDevice (g->device);
+	if (g->ainflight >= 2) { snprintf (err, errlen, "two asynchronous calls already in flight: RC_WaitViews first"); return RC_ERR_ARG; }
+	if (g->profiling) { snprintf (err, errlen, "asynchronous rendering needs profiling off"); return RC_ERR_ARG; }
+	const int slot = (g->ahead + g->ainflight) & 1;
+	if (g->aoutcap[slot] < px * n)
+	{
+		cudaFree (g->d_afb[slot]); cudaFree (g->d_azb[slot]);
+		g->d_afb[slot] = NULL; g->d_azb[slot] = NULL; g->aoutcap[slot] = 0;
+		CK (cudaMalloc (&g->d_afb[slot], px * n));
+		CK (cudaMalloc (&g->d_azb[slot], px * n * sizeof(int16_t)));
+		g->aoutcap[slot] = px * n;
+	}
+	CK (cudaMemsetAsync (g->d_afb[slot], 0, px * n, g->stream));
+	g->astatus[slot] = 0;
+	CK (cudaEventRecord (g->adone_copy[slot], g->copystream));	/* paths that copy on the main stream leave this one as "done" */
+	g->host_fb = fb_out; g->host_z = z_out; g->amode = slot + 1;
+	int st = 0;
+	int r = rc_gpu_render (g, batch, g->d_afb[slot], g->d_azb[slot], NULL, &st, err, errlen);
+	g->host_fb = NULL; g->host_z = NULL; g->amode = 0;
+	if (r == RC_OK) g->ainflight++;
+	return r;
+}
+
+/* waits for the oldest asynchronous call; its buffers are complete when this returns */
+int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	if (g->ainflight <= 0) { snprintf (err, errlen, "no asynchronous call in flight"); return RC_ERR_ARG; }
+	const int slot = g->ahead;
+	CK (cudaEventSynchronize (g->adone_s[slot]));
+	CK (cudaEventSynchronize (g->adone_copy[slot]));
+	if (status) *status = g->astatus[slot];
+	g->ahead ^= 1; g->ainflight--;
+	return RC_OK;
 }
 
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }

@@ -157,6 +157,8 @@ int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_
                     int *status, char *err, size_t errlen);
 int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
+int  rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen);
+int  rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen);
 void rc_gpu_flush_caches (rc_gpu_t *g);
 int  rc_gpu_device_alloc (rc_gpu_t *g, size_t bytes, void **ptr);
 void rc_gpu_device_free (rc_gpu_t *g, void *ptr);
