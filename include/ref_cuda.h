@@ -133,6 +133,23 @@ int  RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_o
  * (a cudaStream_t, 0 = legacy default) and is complete when the stream reaches this point. */
 int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status);
 
+/* ------------------------------------------------------------------ R_EndFrame on batches ----
+ * The reference ends a frame by rebuilding the palette from the view's colour shifts and the gamma cvar and
+ * handing it to the video driver (R_UpdatePalette -> VID_ShiftPalette, ref_soft/r_main.c:839-875,794-832); the
+ * driver's palette then turns the 8-bit frame buffer into display colours.  For batches that is:
+ *   RC_SetGamma            the `gamma` cvar (v_gamma, r_main.c:131), default 1
+ *   RC_ViewPalette         the 768-byte palette R_UpdatePalette builds for one view (a pure function of the
+ *                          view: where the reference skips the upload -- no colour shifts, gamma unchanged --
+ *                          this is the base palette through the gamma table)
+ *   RC_PresentViewsDevice  frame buffers of n views (device, as RC_RenderViewsDevice left them) -> 32-bit
+ *                          pixels R | G << 8 | B << 16 | 255 << 24 (d_8to24table's layout, ref_gl/gl_vidnt.c),
+ *                          each view through its own palette, on `stream`
+ *   RC_PresentViews        the same from / to host memory (test and tooling path) */
+void RC_SetGamma (float gamma);
+int  RC_ViewPalette (const refdef_t *view, unsigned char *pal768_out);
+int  RC_PresentViewsDevice (const refdef_t *views, int n, const void *fb_dev, void *rgbx_dev, void *stream);
+int  RC_PresentViews (const refdef_t *views, int n, const uint8_t *fb_in, uint32_t *rgbx_out);
+
 /* Pipelined form of RC_RenderViews for streams of batches (timedemo-style replay, RL roll-outs): the call
  * enqueues the batch and returns; RC_WaitViews blocks until the OLDEST outstanding call has delivered its
  * frame buffers (page-locked host memory recommended) and returns its status.  At most two calls may be

@@ -85,7 +85,10 @@ void Con_SafePrintf (char *fmt, ...) { (void)fmt; }
 void Sys_Printf (char *fmt, ...) { (void)fmt; }
 void SV_BroadcastPrintf (char *fmt, ...) { (void)fmt; }
 void S_ExtraUpdate (void) {}
-void VID_ShiftPalette (unsigned char *p) { (void)p; }
+/* the palette R_UpdatePalette hands to the video driver (r_main.c:874), kept for orc_end_frame */
+unsigned char orc_palette[768];
+int orc_palette_uploads;
+void VID_ShiftPalette (unsigned char *p) { memcpy (orc_palette, p, 768); orc_palette_uploads++; }
 void VID_SetPalette (unsigned char *p) { (void)p; }
 void VID_Update (vrect_t *r) { (void)r; }
 void Sys_mkdir (char *path) { (void)path; }
@@ -410,6 +413,21 @@ int orc_render_batch (refdef_t *rds, int n, byte *fb_out, short *z_out, double *
 	if (seconds) *seconds = Sys_FloatTime () - t0;
 	orc_abort_armed = 0;
 	return 0;
+}
+
+/* R_EndFrame (r_main.c:961-980) after an orc_render of the same view (R_RenderView leaves it in r_refdef):
+ * returns 1 and the palette the reference uploaded, 0 when it skipped the upload (no colour shifts, gamma unchanged). */
+int orc_end_frame (unsigned char *pal_out)
+{
+	int before = orc_palette_uploads;
+	orc_abort_armed = 1;
+	if (setjmp (orc_abort)) { orc_abort_armed = 0; return -1; }
+	R_EndFrame ();
+	orc_abort_armed = 0;
+	if (orc_palette_uploads == before)
+		return 0;
+	if (pal_out) memcpy (pal_out, orc_palette, 768);
+	return 1;
 }
 
 void orc_clear_buffers (int fbval, int zval)

@@ -51,6 +51,7 @@ class RefSoft:
         L.orc_last_error.restype = C.c_char_p
         L.orc_model.restype = C.c_void_p
         L.orc_load_world.restype = C.c_void_p
+        L.orc_end_frame.argtypes = [C.c_void_p]
         L.orc_set_cvar.argtypes = [C.c_char_p, C.c_float]
         L.orc_set_cvar_string.argtypes = [C.c_char_p, C.c_char_p]
         L.orc_render.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.c_void_p]
@@ -99,6 +100,15 @@ class RefSoft:
         if rc != 0:
             raise RuntimeError("orc_render: " + self.err())
         return fb, z
+
+    def end_frame(self):
+        """R_EndFrame after render() of the same view: the palette R_UpdatePalette uploaded (768 bytes), or None
+        when the reference skipped the upload (no colour shifts and gamma unchanged)."""
+        pal = np.empty(768, dtype=np.uint8)
+        rc = self.lib.orc_end_frame(pal.ctypes.data)
+        if rc < 0:
+            raise RuntimeError("orc_end_frame: " + self.err())
+        return pal if rc == 1 else None
 
     def render_batch(self, rds, want_fb: bool = True, want_z: bool = True):
         n = len(rds)

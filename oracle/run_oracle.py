@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat):
+def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette=False):
     try:
         sys.path.insert(0, ROOT)
         from oracle.refsoft import RefSoft
@@ -29,7 +29,15 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         cm = C.addressof(C.c_char.in_dll(r.lib, "vid")) + 8     # vid.colormap (client/vid.h:36: after `byte *buffer`)
         rds = build_refdefs(specs, width, height, model_resolver=r.model, colormap_ptr=cm)
         out = {}
-        if want_dump:
+        if want_palette:
+            # one view at a time, R_EndFrame after each: frame buffer + the palette the reference uploaded
+            fbs, pals = [], []
+            for i in range(len(specs)):
+                fb, _ = r.render(rds[i], False)
+                fbs.append(fb)
+                pals.append(r.end_frame())
+            out["fb"] = np.stack(fbs); out["z"] = None; out["palettes"] = pals
+        elif want_dump:
             r.dump_enable(True)
             fbs, zs, dumps = [], [], []
             for i in range(len(specs)):
@@ -49,10 +57,10 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         q.put(("err", traceback.format_exc()))
 
 
-def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600):
+def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600, want_palette=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat))
+    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette))
     p.start()
     try:
         kind, payload = q.get(timeout=timeout)

@@ -311,6 +311,17 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 	return RC_OK;
 }
 
+int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, void *rgbx, void *stream, int host, char *err, size_t errlen)
+{
+	/* test infrastructure: the simulator only has host memory */
+	const size_t px = (size_t)g->width * g->height;
+	const uint8_t *in = (const uint8_t *)fb; uint32_t *out = (uint32_t *)rgbx;
+	for (int v = 0; v < n; v++)
+		for (size_t p = 0; p < px; p++)
+			out[v * px + p] = pal32[v * 256 + in[v * px + p]];
+	return RC_OK;
+}
+
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out) { *out = g->stats; }
 void rc_gpu_set_profiling (rc_gpu_t *g, int on) { (void)g; (void)on; }
 

@@ -83,6 +83,11 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_SetGamma.argtypes = [C.c_float]
+        L.RC_SetGamma.restype = None
+        L.RC_ViewPalette.argtypes = [C.POINTER(refdef_t), C.c_void_p]
+        L.RC_PresentViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p]
+        L.RC_PresentViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.RC_RenderViewsAsync.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p]
         L.RC_WaitViews.argtypes = [C.POINTER(C.c_int)]
         L.RC_RenderViewsDevice.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
@@ -136,6 +141,29 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"RC_RenderViews failed ({rc}): {self.err()}")
         return fb, (z if want_z else None), st.value
+
+    def set_gamma(self, gamma: float):
+        self.lib.RC_SetGamma(gamma)
+
+    def view_palette(self, rd) -> np.ndarray:
+        """RC_ViewPalette: the 768-byte palette R_UpdatePalette builds for one view."""
+        pal = np.empty(768, dtype=np.uint8)
+        if self.lib.RC_ViewPalette(C.byref(rd), pal.ctypes.data) != 0:
+            raise RuntimeError(f"RC_ViewPalette failed: {self.err()}")
+        return pal
+
+    def present(self, rds, fb: np.ndarray) -> np.ndarray:
+        """RC_PresentViews: 8-bit frame buffers (host) -> 32-bit display pixels (host), each view through its palette."""
+        n = fb.shape[0]
+        out = np.empty(fb.shape, dtype=np.uint32)
+        fbc = np.ascontiguousarray(fb)
+        if self.lib.RC_PresentViews(rds, n, fbc.ctypes.data, out.ctypes.data) != 0:
+            raise RuntimeError(f"RC_PresentViews failed: {self.err()}")
+        return out
+
+    def present_device(self, rds, n: int, fb_ptr: int, rgbx_ptr: int, stream: int = 0):
+        if self.lib.RC_PresentViewsDevice(rds, n, fb_ptr, rgbx_ptr, stream or None) != 0:
+            raise RuntimeError(f"RC_PresentViewsDevice failed: {self.err()}")
 
     def render_async(self, rds, n: int, fb, z=None) -> None:
         """RC_RenderViewsAsync: enqueue a batch into caller-owned (pinned) numpy buffers; at most two outstanding."""

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <math.h>
 #include <dlfcn.h>
 #include "rc_host.h"
 
@@ -28,6 +29,8 @@ static struct {
 	struct model_s *world;
 	char         err[1024];
 	int          unsupported;
+	float        gamma; uint8_t gammatable[256]; int gamma_valid;	/* v_gamma + R_BuildGammaTable */
+	uint32_t    *palscratch; int palscratchcap;
 	int          async_unsupported[2]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
@@ -655,6 +658,91 @@ void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }
 void RC_GetStats (rc_stats_t *out) { if (rc.gpu) rc_gpu_get_stats (rc.gpu, out); else memset (out, 0, sizeof(*out)); }
 void RC_SetProfiling (int on) { if (rc.gpu) rc_gpu_set_profiling (rc.gpu, on); }
 int  RC_DebugRead (int kind, int view, void *dst, int cap) { return rc.gpu ? rc_gpu_debug_read (rc.gpu, kind, view, dst, cap) : RC_ERR_ARG; }
+
+/* R_BuildGammaTable, ref_soft/r_main.c:794-817 (libm pow on the host, as the reference) */
+static void rc_build_gamma (void)
+{
+	int i, inf;
+	float g = rc.gamma_valid ? rc.gamma : 1.0f;
+	if (g == 1.0)
+	{
+		for (i = 0; i < 256; i++)
+			rc.gammatable[i] = (uint8_t)i;
+	}
+	else
+		for (i = 0; i < 256; i++)
+		{
+			inf = (int)(255.0 * pow (((float)i + 0.5) / 255.5, g) + 0.5);
+			if (inf < 0) inf = 0;
+			if (inf > 255) inf = 255;
+			rc.gammatable[i] = (uint8_t)inf;
+		}
+	rc.gamma_valid = 2;
+}
+
+void RC_SetGamma (float gamma)
+{
+	rc.gamma = gamma; rc.gamma_valid = 1;
+}
+
+/* R_UpdatePalette, ref_soft/r_main.c:839-875: colour shifts blended in 8.8 fixed point one after the other,
+ * then the gamma table.  (r can leave 0..255 only with percent > 256 or destcolor outside 0..255; the
+ * reference indexes gammatable with it regardless, here it is clamped to the table.) */
+int RC_ViewPalette (const refdef_t *view, unsigned char *pal)
+{
+	int i, j, c;
+	if (!view || !pal) return rc_fail (RC_ERR_ARG, "RC_ViewPalette: NULL argument");
+	if (rc.gamma_valid != 2) rc_build_gamma ();
+	for (i = 0; i < 256; i++)
+	{
+		int rgb[3];
+		rgb[0] = rc.palette[i * 3]; rgb[1] = rc.palette[i * 3 + 1]; rgb[2] = rc.palette[i * 3 + 2];
+		for (j = 0; j < view->num_cshifts; j++)
+			for (c = 0; c < 3; c++)
+				rgb[c] += (view->cshifts[j].percent * (view->cshifts[j].destcolor[c] - rgb[c])) >> 8;
+		for (c = 0; c < 3; c++)
+			pal[i * 3 + c] = rc.gammatable[rgb[c] < 0 ? 0 : (rgb[c] > 255 ? 255 : rgb[c])];
+	}
+	return RC_OK;
+}
+
+static int rc_view_palettes32 (const refdef_t *views, int n)
+{
+	int i, k;
+	unsigned char pal[768];
+	if (n * 256 > rc.palscratchcap)
+	{
+		free (rc.palscratch);
+		rc.palscratch = (uint32_t *)malloc (sizeof(uint32_t) * 256 * (size_t)n);
+		rc.palscratchcap = rc.palscratch ? n * 256 : 0;
+		if (!rc.palscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	}
+	for (i = 0; i < n; i++)
+	{
+		RC_ViewPalette (&views[i], pal);
+		for (k = 0; k < 256; k++)
+			rc.palscratch[i * 256 + k] = (uint32_t)pal[k * 3] | ((uint32_t)pal[k * 3 + 1] << 8) | ((uint32_t)pal[k * 3 + 2] << 16) | 0xFF000000u;
+	}
+	return RC_OK;
+}
+
+int RC_PresentViewsDevice (const refdef_t *views, int n, const void *fb_dev, void *rgbx_dev, void *stream)
+{
+	int r;
+	if (!rc.gpu) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	if (!views || n <= 0 || !fb_dev || !rgbx_dev) return rc_fail (RC_ERR_ARG, "RC_PresentViewsDevice: bad argument");
+	if ((r = rc_view_palettes32 (views, n)) != RC_OK) return r;
+	return rc_gpu_present (rc.gpu, rc.palscratch, n, fb_dev, rgbx_dev, stream, 0, rc.err, sizeof(rc.err));
+}
+
+int RC_PresentViews (const refdef_t *views, int n, const uint8_t *fb_in, uint32_t *rgbx_out)
+{
+	int r;
+	if (!rc.gpu) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	if (!views || n <= 0 || !fb_in || !rgbx_out) return rc_fail (RC_ERR_ARG, "RC_PresentViews: bad argument");
+	if ((r = rc_view_palettes32 (views, n)) != RC_OK) return r;
+	return rc_gpu_present (rc.gpu, rc.palscratch, n, fb_in, rgbx_out, NULL, 1, rc.err, sizeof(rc.err));
+}
 
 void RC_SetVidBuffers (uint8_t *buffer, int rowbytes, int16_t *zbuffer)
 {

@@ -80,6 +80,7 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
+	uint32_t *d_pal32; int palcap; uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
 	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
 	uint8_t *d_afb[2]; int16_t *d_azb[2]; size_t aoutcap[2];
 	cudaEvent_t adone_s[2], adone_copy[2]; int *astatus;	/* pinned */
@@ -1297,6 +1298,44 @@ __global__ void k_zresolve (const __grid_constant__ rc_frame_t f)
 	rc_zresolve_pixel (&f, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
 }
 
+/* R_EndFrame for batches: 8-bit frame buffers -> 32-bit display pixels, every view through its own
+ * palette (what VID_ShiftPalette + the video driver do with the palette R_UpdatePalette built,
+ * r_main.c:839-875).  Pure streaming: 1 B read + 4 B written per pixel.  blockIdx.y = view; the view's
+ * 1 KB palette sits in shared memory; a thread turns 4 pixels (one 32-bit load) into one 16-byte store, so
+ * a warp reads 128 and writes 512 contiguous bytes per instruction; four such groups are in flight per thread. */
+__global__ void __launch_bounds__(256) k_present (const uint8_t * __restrict__ fb, uint32_t * __restrict__ out, const uint32_t * __restrict__ pal32, unsigned px)
+{
+	__shared__ uint32_t spal[256];
+	const unsigned vi = blockIdx.y;
+	spal[threadIdx.x] = pal32[vi * 256 + threadIdx.x];
+	__syncthreads ();
+	const uint32_t *src = reinterpret_cast<const uint32_t *>(fb + (size_t)vi * px);
+	uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)vi * px);
+	const unsigned nq = px >> 2, stride = gridDim.x * blockDim.x;
+	unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+	for (; q + 3 * stride < nq; q += 4 * stride)
+	{
+		uint32_t v[4];
+		#pragma unroll
+		for (int i = 0; i < 4; i++)
+			v[i] = __ldcs (&src[q + i * stride]);
+		#pragma unroll
+		for (int i = 0; i < 4; i++)
+			__stcs (&dst[q + i * stride], make_uint4 (spal[v[i] & 0xFF], spal[(v[i] >> 8) & 0xFF], spal[(v[i] >> 16) & 0xFF], spal[v[i] >> 24]));
+	}
+	for (; q < nq; q += stride)
+	{
+		const uint32_t v = __ldcs (&src[q]);
+		__stcs (&dst[q], make_uint4 (spal[v & 0xFF], spal[(v >> 8) & 0xFF], spal[(v >> 16) & 0xFF], spal[v >> 24]));
+	}
+	/* a plane whose size is not a multiple of 4 pixels: the last ones, one by one */
+	if (blockIdx.x == 0 && threadIdx.x < (px & 3u))
+	{
+		const unsigned p = (px & ~3u) + threadIdx.x;
+		out[(size_t)vi * px + p] = spal[fb[(size_t)vi * px + p]];
+	}
+}
+
 __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1340,6 +1379,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 		cudaEventCreateWithFlags (&g->adone_s[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags (&g->adone_copy[i], cudaEventDisableTiming);
 	}
+	g->d_pal32 = NULL; g->palcap = 0; g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
 	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * 2, cudaHostAllocDefault);
 	g->ahead = 0; g->ainflight = 0; g->amode = 0;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
@@ -1416,6 +1456,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_fb); cudaFree (g->d_zb); cudaFree (g->d_dlights); cudaFree (g->d_warpbuf);
 	for (int i = 0; i < 2; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
 	cudaFreeHost (g->astatus);
+	cudaFree (g->d_pal32); cudaFree (g->d_presentin); cudaFree (g->d_presentout);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
@@ -2132,6 +2173,47 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 	CK (cudaEventSynchronize (g->adone_copy[slot]));
 	if (status) *status = g->astatus[slot];
 	g->ahead ^= 1; g->ainflight--;
+	return RC_OK;
+}
+
+int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, void *rgbx, void *stream, int host, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	const size_t px = (size_t)g->width * g->height;
+	if (n > g->palcap)
+	{
+		cudaFree (g->d_pal32); g->d_pal32 = NULL; g->palcap = 0;
+		CK (cudaMalloc (&g->d_pal32, sizeof(uint32_t) * 256 * (size_t)(n + 64)));
+		g->palcap = n + 64;
+	}
+	const uint8_t *fbd = (const uint8_t *)fb;
+	uint32_t *outd = (uint32_t *)rgbx;
+	if (host)
+	{
+		if (g->presentcap < px * n)
+		{
+			cudaFree (g->d_presentin); cudaFree (g->d_presentout); g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
+			CK (cudaMalloc (&g->d_presentin, px * n));
+			CK (cudaMalloc (&g->d_presentout, px * n * sizeof(uint32_t)));
+			g->presentcap = px * n;
+		}
+		CK (cudaMemcpyAsync (g->d_presentin, fb, px * n, cudaMemcpyHostToDevice, s));
+		fbd = g->d_presentin; outd = g->d_presentout;
+	}
+	/* the upload is stream ordered; pal32 is the caller's scratch, staged by the runtime before this returns */
+	CK (cudaMemcpyAsync (g->d_pal32, pal32, sizeof(uint32_t) * 256 * (size_t)n, cudaMemcpyHostToDevice, s));
+	int bx = (int)((px / 4 + 256 * 4 - 1) / (256 * 4));
+	const int cap = (g->numsms * 8 + n - 1) / n;		/* about 8 resident CTAs per SM over the whole batch */
+	if (bx > cap) bx = cap;
+	if (bx < 1) bx = 1;
+	k_present<<<dim3 (bx, n), 256, 0, s>>> (fbd, outd, g->d_pal32, (unsigned)px);
+	CK (cudaGetLastError ());
+	if (host)
+	{
+		CK (cudaMemcpyAsync (rgbx, g->d_presentout, px * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CK (cudaStreamSynchronize (s));
+	}
 	return RC_OK;
 }
 

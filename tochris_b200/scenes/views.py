@@ -9,7 +9,7 @@ from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
 
 from . import assets
-from ..refdef import (refdef_t, entity_t, dlight_t, particle_t, default_lightstyles)
+from ..refdef import (refdef_t, entity_t, dlight_t, particle_t, cshift_t, default_lightstyles)
 
 
 @dataclass
@@ -36,6 +36,7 @@ class ViewSpec:
     entities: List[EntitySpec] = field(default_factory=list)
     dlights: List[Tuple[float, float, float, float]] = field(default_factory=list)   # x, y, z, radius
     particles: List[Tuple[float, float, float, int]] = field(default_factory=list)   # x, y, z, colour
+    cshifts: List[Tuple[int, int, int, int]] = field(default_factory=list)           # r, g, b, percent (ref.h:49-53)
 
 
 def write_base_assets(basedir: str):
@@ -130,6 +131,13 @@ def build_refdefs(specs: Sequence[ViewSpec], width: int, height: int,
             rd.num_particles = len(sp.particles)
             rd.particles = pt
             keep.append(pt)
+        if sp.cshifts:
+            cs = (cshift_t * len(sp.cshifts))()
+            for j, c in enumerate(sp.cshifts):
+                cs[j].destcolor[0], cs[j].destcolor[1], cs[j].destcolor[2], cs[j].percent = c
+            rd.num_cshifts = len(sp.cshifts)
+            rd.cshifts = cs
+            keep.append(cs)
     rds._keep = keep
     return rds
 
