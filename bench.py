@@ -329,13 +329,16 @@ def run_ours(args):
     if world == 1:
         rgbx = torch.empty((n, H, W), dtype=torch.int32, device=dev)
         pevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for k in range(3 + args.steps):
-            l2flush.zero_()
-            if k >= 3:
-                pevs[k - 3][0].record(stream)
-            r.present_device(rds, n, fb.data_ptr(), rgbx.data_ptr(), stream.cuda_stream)
-            if k >= 3:
-                pevs[k - 3][1].record(stream)
+        pstream = torch.cuda.Stream(dev)      # the call is asynchronous: time it on the stream it is given
+        torch.cuda.synchronize()
+        with torch.cuda.stream(pstream):
+            for k in range(3 + args.steps):
+                l2flush.zero_()
+                if k >= 3:
+                    pevs[k - 3][0].record(pstream)
+                r.present_device(rds, n, fb.data_ptr(), rgbx.data_ptr(), pstream.cuda_stream)
+                if k >= 3:
+                    pevs[k - 3][1].record(pstream)
         torch.cuda.synchronize()
         pms = sum(a.elapsed_time(b) for a, b in pevs) / args.steps
         present = {"kernel": "k_present (palette expansion, R_EndFrame for batches)", "ms_per_step": round(pms, 4),
@@ -407,9 +410,11 @@ def run_ours(args):
                                if warm_ms else None),
         "present": (dict(present, frac=round(present["achieved_gbs"] / peak, 4)) if present else None),
         "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),
-        "e2e": {"value": round(n * world * args.steps / e2e_s, 1), "unit": "frames/s",
-                "h2d_bytes_per_step": int(n * 648), "d2h_bytes_per_step": int(px), "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
-                "note": "RC_RenderViewsAsync / RC_WaitViews, two batches in flight: refdef_t[] in host memory -> 8-bit framebuffers in pinned host memory (z stays on device); every step uploads, flushes the surface cache and L2, renders and downloads inside the timed region, the PCIe copy of step k overlapping the kernels of step k+1",
+        "e2e": {"value": round(n * world * args.steps / min(e2e_s, e2e_sync_s), 1), "unit": "frames/s",
+                "h2d_bytes_per_step": int(n * 648), "d2h_bytes_per_step": int(px), "ms_per_step": round(min(e2e_s, e2e_sync_s) / args.steps * 1e3, 4),
+                "api": "RC_RenderViewsAsync + RC_WaitViews" if e2e_s <= e2e_sync_s else "RC_RenderViews",
+                "pipelined_call": {"value": round(n * world * args.steps / e2e_s, 1), "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+                "note": "refdef_t[] in host memory -> 8-bit framebuffers in pinned host memory (z stays on device); every step uploads, flushes the surface cache and L2, renders and downloads inside the timed region.  Both host APIs are measured, the faster one is `value`: the blocking RC_RenderViews (timed call by call) and the pipelined RC_RenderViewsAsync / RC_WaitViews (two batches in flight, the PCIe copy of step k beside the kernels of step k+1; timed over all steps).  The 19.7 MB PCIe copy (about 0.47 ms at 40 GB/s) bounds both",
                 "verified": bool(e2e_ok),
                 "blocking_call": {"value": round(n * world * args.steps / e2e_sync_s, 1), "ms_per_step": round(e2e_sync_s / args.steps * 1e3, 4),
                                   "note": "RC_RenderViews, one blocking call per step, timed call by call"}},

@@ -80,7 +80,8 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
-	uint32_t *d_pal32; int palcap; uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
+	uint32_t *d_pal32; int palcap; uint32_t *h_pal32[2]; cudaEvent_t evpal[2]; int palslot;	/* pinned staging ring for the palettes */
+	uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
 	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
 	uint8_t *d_afb[2]; int16_t *d_azb[2]; size_t aoutcap[2];
 	cudaEvent_t adone_s[2], adone_copy[2]; int *astatus;	/* pinned */
@@ -1379,7 +1380,9 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 		cudaEventCreateWithFlags (&g->adone_s[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags (&g->adone_copy[i], cudaEventDisableTiming);
 	}
-	g->d_pal32 = NULL; g->palcap = 0; g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
+	g->d_pal32 = NULL; g->palcap = 0; g->h_pal32[0] = g->h_pal32[1] = NULL; g->palslot = 0;
+	cudaEventCreateWithFlags (&g->evpal[0], cudaEventDisableTiming); cudaEventCreateWithFlags (&g->evpal[1], cudaEventDisableTiming);
+	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
 	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * 2, cudaHostAllocDefault);
 	g->ahead = 0; g->ainflight = 0; g->amode = 0;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
@@ -1457,6 +1460,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	for (int i = 0; i < 2; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
 	cudaFreeHost (g->astatus);
 	cudaFree (g->d_pal32); cudaFree (g->d_presentin); cudaFree (g->d_presentout);
+	cudaFreeHost (g->h_pal32[0]); cudaFreeHost (g->h_pal32[1]); cudaEventDestroy (g->evpal[0]); cudaEventDestroy (g->evpal[1]);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
 	cudaStreamDestroy (g->stream);
@@ -2183,9 +2187,14 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 	const size_t px = (size_t)g->width * g->height;
 	if (n > g->palcap)
 	{
+		cudaDeviceSynchronize ();
 		cudaFree (g->d_pal32); g->d_pal32 = NULL; g->palcap = 0;
+		cudaFreeHost (g->h_pal32[0]); cudaFreeHost (g->h_pal32[1]); g->h_pal32[0] = g->h_pal32[1] = NULL;
 		CK (cudaMalloc (&g->d_pal32, sizeof(uint32_t) * 256 * (size_t)(n + 64)));
+		CK (cudaHostAlloc (&g->h_pal32[0], sizeof(uint32_t) * 256 * (size_t)(n + 64), cudaHostAllocDefault));
+		CK (cudaHostAlloc (&g->h_pal32[1], sizeof(uint32_t) * 256 * (size_t)(n + 64), cudaHostAllocDefault));
 		g->palcap = n + 64;
+		cudaEventRecord (g->evpal[0], s); cudaEventRecord (g->evpal[1], s);
 	}
 	const uint8_t *fbd = (const uint8_t *)fb;
 	uint32_t *outd = (uint32_t *)rgbx;
@@ -2201,8 +2210,15 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 		CK (cudaMemcpyAsync (g->d_presentin, fb, px * n, cudaMemcpyHostToDevice, s));
 		fbd = g->d_presentin; outd = g->d_presentout;
 	}
-	/* the upload is stream ordered; pal32 is the caller's scratch, staged by the runtime before this returns */
-	CK (cudaMemcpyAsync (g->d_pal32, pal32, sizeof(uint32_t) * 256 * (size_t)n, cudaMemcpyHostToDevice, s));
+	/* palettes go through a pinned two-slot ring, so the upload is a true asynchronous copy (a pageable source costs the
+	 * stream tens of microseconds); a slot is reused only after the copy that read it has completed */
+	{
+		const int slot = g->palslot; g->palslot ^= 1;
+		CK (cudaEventSynchronize (g->evpal[slot]));
+		memcpy (g->h_pal32[slot], pal32, sizeof(uint32_t) * 256 * (size_t)n);
+		CK (cudaMemcpyAsync (g->d_pal32, g->h_pal32[slot], sizeof(uint32_t) * 256 * (size_t)n, cudaMemcpyHostToDevice, s));
+		CK (cudaEventRecord (g->evpal[slot], s));
+	}
 	int bx = (int)((px / 4 + 256 * 4 - 1) / (256 * 4));
 	const int cap = (g->numsms * 8 + n - 1) / n;		/* about 8 resident CTAs per SM over the whole batch */
 	if (bx > cap) bx = cap;
