@@ -475,7 +475,22 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # the contract is ONE JSON line on stdout: libraries that print there while they initialise (NCCL announces its
+    # version on stdout on some boxes) are sent to stderr, and only the result line goes to the real stdout
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001
+        _buf.append(" ".join(str(x) for x in args))
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        sys.stdout.flush()
+        for line in _buf:
+            os.write(_real_stdout, (line + "\n").encode())

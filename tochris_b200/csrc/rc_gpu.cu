@@ -950,9 +950,24 @@ __device__ __forceinline__ void draw_prefetch_l1 (const void *p)
 	asm volatile ("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
+/* does the straight-line code handle this full cell?  (cache block or texel blob, frame-buffer target, no negative 1/z in reach) */
+__device__ __forceinline__ bool draw_cell_is_fast (const uint4 sb, const uint32_t pix, const bool fast_ok)
+{
+	const uint32_t izistep = sb.y;
+	uint32_t zz = sb.x + pix * izistep, anyneg = (zz - izistep) | zz;
+	#pragma unroll
+	for (int j = 1; j < 8; j++)
+	{
+		zz += izistep; anyneg |= zz;
+	}
+	return fast_ok && (sb.w & 0xE0000u) == 0 && (int)anyneg >= 0;
+}
+
 /* the common case of a full cell: D_DrawZSpans + D_DrawSpans8 for 8 screen-aligned pixels */
+/* (the eight texels are only gathered here: px[] is packed and stored one tile later by the caller, so that the
+ * gathers have a whole iteration to arrive) */
 __device__ __forceinline__ bool draw_cell_fast (const rc_world_t &w, const rc_frame_t &f, const uint32_t sub, const uint32_t pix,
-	const uint4 sb, const uint4 r0, const uint4 r1, const bool fast_ok)
+	const uint4 sb, const uint4 r0, const uint4 r1, const bool fast_ok, uint32_t (&px)[8])
 {
 	const unsigned a = sub & 7u;
 	const uint32_t izistep = sb.y;
@@ -975,7 +990,6 @@ __device__ __forceinline__ bool draw_cell_fast (const rc_world_t &w, const rc_fr
 	const int cachewidth = (int)(cwk & 0xFFFFu);
 	uint32_t sstep = r0.z, tstep = r0.w;
 	uint32_t ss = r0.x + a * sstep, tt = r0.y + a * tstep;
-	uint32_t px[8];
 	#pragma unroll
 	for (int j = 0; j < 8; j++)
 	{
@@ -986,11 +1000,15 @@ __device__ __forceinline__ bool draw_cell_fast (const rc_world_t &w, const rc_fr
 		px[j] = __ldg (&pbase[((int)ss >> 16) + ((int)tt >> 16) * cachewidth]);
 		ss += sstep; tt += tstep;
 	}
+	return true;
+}
+
+__device__ __forceinline__ void draw_cell_store (const rc_frame_t &f, const uint32_t pix, const uint32_t (&px)[8])
+{
 	uint2 q;
 	q.x = __byte_perm (__byte_perm (px[0], px[1], 0x0040), __byte_perm (px[2], px[3], 0x0040), 0x5410);
 	q.y = __byte_perm (__byte_perm (px[4], px[5], 0x0040), __byte_perm (px[6], px[7], 0x0040), 0x5410);
 	*reinterpret_cast<uint2 *>(f.fb + pix) = q;
-	return true;
 }
 
 template <bool WARPVIEWS>
@@ -1032,6 +1050,10 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 
 	unsigned t0 = tile;
 	unsigned nfull = 0;			/* statistics: cells drawn here or queued */
+	uint32_t pxo[8]; uint32_t pendpix = 0; bool pend = false;	/* texels gathered for the previous tile's cell, not stored yet */
+	#pragma unroll
+	for (int j = 0; j < 8; j++)
+		pxo[j] = 0;
 	int2 c0, c1; uint32_t p0, p1;
 	fetch_cell (c0, p0);
 	fetch_cell (c1, p1);
@@ -1062,8 +1084,17 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 		/* cells the straight-line code does not handle are queued for the general kernel (k_ends):
 		 * one atomicAdd per warp */
 		nfull += cur.si >= 0;
-		const bool slow = cur.si >= 0 && !draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, cur.r0, cur.r1, fast_ok);
-		const unsigned sm = __ballot_sync (0xFFFFFFFFu, slow);
+		uint32_t pxn[8];
+		const bool fast = cur.si >= 0 && draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, cur.r0, cur.r1, fast_ok, pxn);
+		const bool slow = cur.si >= 0 && !fast;
+		/* colour of the PREVIOUS tile's cell: its gathers were issued one iteration ago */
+		if (pend)
+			draw_cell_store (f, pendpix, pxo);
+		pend = fast; pendpix = cur.pix;
+		#pragma unroll
+		for (int j = 0; j < 8; j++)
+			pxo[j] = pxn[j];
+		const unsigned sm = f.slowmode ? 0u : __ballot_sync (0xFFFFFFFFu, slow);
 		if (sm)
 		{
 			unsigned long long base = 0ull;
@@ -1081,6 +1112,8 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 		c1 = c2; p1 = p2;
 		t0 += wstride;
 	}
+	if (pend)
+		draw_cell_store (f, pendpix, pxo);
 	#pragma unroll
 	for (int o = 16; o; o >>= 1)
 		nfull += __shfl_xor_sync (0xFFFFFFFFu, nfull, o);
@@ -1249,6 +1282,28 @@ __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant_
 					pd[j] = (uint8_t)px[j];
 					pz[j] = (int16_t)(zq[j] >> 16);
 				}
+		}
+	}
+	if (!f.slowmode)
+		return;
+	/* grouped drawing: k_draw skipped the full cells it does not handle (same test, draw_cell_is_fast) instead of
+	 * queueing them; this kernel has issue slots to spare, so it streams over the cell records and draws those */
+	{
+		const unsigned cw = (unsigned)((f.width + 7) >> 3);
+		const unsigned ncells = (unsigned)(f.drawview1 * f.height) * cw;
+		const bool fast_ok = f.zb != NULL && (f.width & 7) == 0;
+		const int2 *cells = reinterpret_cast<const int2 *>(f.cellspan);
+		for (unsigned t = (unsigned)(f.drawview0 * f.height) * cw + blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += gridDim.x * blockDim.x)
+		{
+			const int2 cell = __ldg (&cells[t]);
+			if (cell.x < 0)
+				continue;
+			const uint4 sb = __ldg (&spans4[2 * (size_t)cell.x + 1]);
+			const unsigned row = t / cw, c = t - row * cw;
+			const uint32_t pix = row * (unsigned)f.width + (c << 3);
+			if (draw_cell_is_fast (sb, pix, fast_ok))
+				continue;
+			draw_general (&w, &f, cell.x, (int)pix - __ldg (&f.spans[cell.x].pixofs), WARPVIEWS);
 		}
 	}
 }
@@ -1785,25 +1840,27 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		 * stream while the next one is drawn: the D2H copy of the host-output path (PCIe: the longest single
 		 * item of a batch), or whatever the caller's callback enqueues (bench.py: the NCCL gather) */
 		grouped = true;
-		const int ngroups = g->host_fb ? (n >= 32 ? 4 : 2) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
+		/* host output crosses PCIe (the copy of a group is longer than its draw: four groups); a mirror in peer memory
+		 * is an NVLink copy, short next to the per-launch cost of a group: two */
+		const int ngroups = g->host_fb ? ((n >= 32 && g->host_fb != g->mirror_fb) ? 4 : 2) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
 		cudaStream_t side = g->host_fb ? g->copystream : g->groupstream;
 		const size_t px = (size_t)g->width * g->height;
+		/* the mixed cells of ALL views in one launch on the second stream, beside the first groups' full cells
+		 * (latency bound, about as long as the draw of two groups): the first group waits for it */
+		f.drawview0 = 0; f.drawview1 = n; f.slowmode = 1;
+		cudaEventRecord (g->evfork, s);
+		cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
+		k_ends<false><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
+		cudaEventRecord (g->evjoin, g->sidestream);
 		for (int gi = 0; gi < ngroups; gi++)
 		{
 			f.drawview0 = (int)((long long)n * gi / ngroups); f.drawview1 = (int)((long long)n * (gi + 1) / ngroups);
 			const int nv = f.drawview1 - f.drawview0;
 			int ctas = (int)(((size_t)nv * g->height * ((g->width + 7) / 8) + 127) / 128);
 			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
-			/* mixed cells on the second stream, beside the full cells */
-			cudaEventRecord (g->evfork, s);
-			cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
-			k_ends<false><<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
-			cudaEventRecord (g->evjoin, g->sidestream);
 			k_draw<false><<<ctas, 128, 0, s>>> (w, f);
 			if (timed) cudaEventRecord (g->ev[8], s);
-			k_slowcells<false><<<g->numsms * 4, 128, 0, s>>> (w, f);
-			cudaMemsetAsync (g->d_alloc + 3, 0, sizeof(unsigned long long), s);
-			cudaStreamWaitEvent (s, g->evjoin, 0);
+			if (gi == 0) cudaStreamWaitEvent (s, g->evjoin, 0);
 			cudaEventRecord (g->evgroup[gi], s);
 			cudaStreamWaitEvent (side, g->evgroup[gi], 0);
 			if (g->host_fb)
@@ -1816,7 +1873,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			else
 				g->groupfn (g->groupuser, first_view + f.drawview0, nv);
 		}
-		g->stats.kernel_launches += 3 * ngroups - 1;
+		g->stats.kernel_launches += ngroups - 2;	/* ngroups draws + one k_ends, no k_slowcells; 8 are counted below */
+		f.slowmode = 0;
 		if (g->host_fb && g->amode)
 			cudaEventRecord (g->adone_copy[g->amode - 1], side);	/* the caller waits for it (rc_gpu_wait_host); the next call's kernels do not */
 		else if (g->host_fb)

@@ -90,6 +90,8 @@ typedef struct {
 #else
     void *slowcells;
 #endif
+    int slowmode;                 /* GPU only: 0 k_draw queues the cells it leaves to the general code (k_slowcells draws them),
+                                   * 1 it skips them and k_ends finds them itself (grouped drawing: no per-group launches) */
     unsigned long long *alloc;    /* [0]: lo32 spans used, hi32 segments used  [1]: cache pool cursor  [2]: jobs */
     /* surface cache */
     unsigned long long *cachekeys; int *cachevals; int cachemask;
