@@ -185,6 +185,10 @@ int  RC_IpcExport (void *ptr, unsigned char handle[64]);
 int  RC_IpcImport (const unsigned char handle[64], void **ptr);
 void RC_IpcClose (void *ptr);
 void RC_SetMirrorOutput (void *fb, void *z);
+/* groups of views a batch is drawn in when a mirror is set (1..8; default 2).  More groups start the copies earlier --
+ * worth it when the destination's ingress is the bound (many ranks mirroring into one root) -- at the cost of one
+ * more draw launch per group. */
+void RC_SetMirrorGroups (int ngroups);
 
 /* The `loadsky <name>` command / r_skyname cvar (ref_soft/r_main.c:169-177, r_sky.c:138-194):
  * loads <basedir>/id1/env/<name>{rt,bk,lf,ft,up,dn}.pcx (six 256x256 8-bit PCX pictures); from then on

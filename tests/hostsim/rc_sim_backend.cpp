@@ -120,6 +120,7 @@ void rc_gpu_device_free (rc_gpu_t *g, void *ptr) { (void)g; free (ptr); }
 int rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle) { (void)g; (void)ptr; (void)handle; return RC_ERR_CUDA; }
 int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr) { (void)g; (void)handle; (void)ptr; return RC_ERR_CUDA; }
 void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { (void)g; (void)ptr; }
+void rc_gpu_set_mirror_groups (rc_gpu_t *g, int ngroups) { (void)g; (void)ngroups; }
 void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { (void)g; (void)fb; (void)z; }
 
 void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)

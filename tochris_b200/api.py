@@ -99,6 +99,7 @@ class RefCuda:
         L.RC_IpcImport.argtypes = [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
         L.RC_IpcClose.argtypes = [C.c_void_p]
         L.RC_SetMirrorOutput.argtypes = [C.c_void_p, C.c_void_p]
+        L.RC_SetMirrorGroups.argtypes = [C.c_int]
         L.RC_SetGroupCallback.argtypes = [GROUPFN, C.c_void_p, C.c_void_p, C.c_int]
         L.RC_SetGroupCallback.restype = None
         L.Mod_ForName.restype = C.c_void_p
@@ -225,6 +226,9 @@ class RefCuda:
     def set_mirror_output(self, fb_ptr: int = 0, z_ptr: int = 0):
         """RC_SetMirrorOutput: finished view groups of render_device() are also copied to fb_ptr (peer or host)."""
         self.lib.RC_SetMirrorOutput(C.c_void_p(fb_ptr or None), C.c_void_p(z_ptr or None))
+
+    def set_mirror_groups(self, ngroups: int):
+        self.lib.RC_SetMirrorGroups(ngroups)
 
     def flush_caches(self):
         self.lib.RC_FlushCaches()

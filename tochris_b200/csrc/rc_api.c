@@ -615,6 +615,7 @@ int  RC_IpcExport (void *ptr, unsigned char handle[64]) { return rc.gpu ? rc_gpu
 int  RC_IpcImport (const unsigned char handle[64], void **ptr) { return rc.gpu ? rc_gpu_ipc_import (rc.gpu, handle, ptr) : RC_ERR_ARG; }
 void RC_IpcClose (void *ptr) { if (rc.gpu) rc_gpu_ipc_close (rc.gpu, ptr); }
 void RC_SetMirrorOutput (void *fb, void *z) { if (rc.gpu) rc_gpu_set_mirror (rc.gpu, fb, z); }
+void RC_SetMirrorGroups (int ngroups) { if (rc.gpu) rc_gpu_set_mirror_groups (rc.gpu, ngroups); }
 
 int RC_SetSkybox (const char *name)
 {

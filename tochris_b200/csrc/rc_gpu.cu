@@ -89,6 +89,7 @@ struct rc_gpu_s {
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
+	int mirrorgroups;
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
@@ -1457,6 +1458,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaStreamCreateWithFlags (&g->sidestream, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
+	g->mirrorgroups = 0;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
 
@@ -1654,6 +1656,7 @@ int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr)
 }
 
 void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { cudaSetDevice (g->device); cudaIpcCloseMemHandle (ptr); }
+void rc_gpu_set_mirror_groups (rc_gpu_t *g, int ngroups) { g->mirrorgroups = ngroups; }
 void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { g->mirror_fb = (uint8_t *)fb; g->mirror_z = (int16_t *)z; }
 
 void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)
@@ -1842,7 +1845,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		grouped = true;
 		/* host output crosses PCIe (the copy of a group is longer than its draw: four groups); a mirror in peer memory
 		 * is an NVLink copy, short next to the per-launch cost of a group: two */
-		const int ngroups = g->host_fb ? ((n >= 32 && g->host_fb != g->mirror_fb) ? 4 : 2) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
+		const int mgroups = g->mirrorgroups >= 1 && g->mirrorgroups <= 8 ? (g->mirrorgroups <= n ? g->mirrorgroups : n) : 2;
+		const int ngroups = g->host_fb ? (g->host_fb == g->mirror_fb ? mgroups : (n >= 32 ? 4 : 2)) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
 		cudaStream_t side = g->host_fb ? g->copystream : g->groupstream;
 		const size_t px = (size_t)g->width * g->height;
 		/* the mixed cells of ALL views in one launch on the second stream, beside the first groups' full cells
