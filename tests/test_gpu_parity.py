@@ -157,3 +157,22 @@ def test_async_pipeline_matches_blocking_call(assets_dir):
     for (wf, wz), (gf, gz) in zip(want, got):
         assert np.array_equal(wf, gf) and np.array_equal(wz, gz)
     r.shutdown()
+
+
+@pytest.mark.gpu
+def test_sub_rectangles_match_oracle_gpu(assets_dir, oracle_available):
+    """Sub-rectangle views on the device: view-rectangle edges inside 8-pixel cells (k_ends' end-of-row ownership),
+    and a width that is not a multiple of 8 (k_draw hands every cell to the general code)."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import run_oracle
+    import test_hostsim_parity as hp
+    specs = hp._rect_specs(20)
+    o = run_oracle.render(assets_dir, "maps/full.bsp", 320, 200, specs)
+    r = rcutil.render_rc(api.LIBPATH, assets_dir, "maps/full.bsp", 320, 200, specs)
+    assert r["status"] == 0
+    hp.check_rect_parity(o, r, specs)
+    specs = rcutil.scene_views("multi", 6, time=0.3, time_step=0.2)          # 324 is not a multiple of 8
+    o = run_oracle.render(assets_dir, "maps/multi.bsp", 324, 202, specs)
+    r = rcutil.render_rc(api.LIBPATH, assets_dir, "maps/multi.bsp", 324, 202, specs)
+    rcutil.assert_parity(o, r, specs, 324, 202)
