@@ -96,6 +96,20 @@ void  R_BeginFrame (void);                                     /* render.h:36  r
 void  R_EndFrame (void);                                       /* render.h:37  r_main.c:961 */
 void  R_NewMap (struct model_s *worldmodel);                   /* render.h:39  r_main.c:258 */
 void  R_TranslatePlayerSkin (int playernum, struct model_s *model, int skinnum, int top, int bottom); /* render.h:40 (empty in ref_soft, r_misc.c:372) */
+/* 2D (render.h:42-53, ref_soft/r_draw.c): recorded per frame, applied to vid.buffer by R_EndFrame; mpic_t as r_shared.h:78-85 */
+struct mpic_s;
+void  Draw_Init (void);
+void  Draw_Character (int x, int y, int num);
+void  Draw_Pic (int x, int y, struct mpic_s *pic);
+void  Draw_TransPic (int x, int y, struct mpic_s *pic);
+void  Draw_TransPicTranslate (int x, int y, struct mpic_s *pic, unsigned char *translation);
+void  Draw_ConsoleBackground (int lines);
+void  Draw_TileClear (int x, int y, int w, int h);
+void  Draw_Fill (int x, int y, int w, int h, int c);
+void  Draw_FadeScreen (void);
+void  Draw_String (int x, int y, char *str);
+struct mpic_s *Draw_PicFromWad (char *name);
+struct mpic_s *Draw_CachePic (char *path);
 
 /* ---------------------------------------------------------------- batched extension ---- */
 typedef struct {
@@ -149,6 +163,28 @@ void RC_SetGamma (float gamma);
 int  RC_ViewPalette (const refdef_t *view, unsigned char *pal768_out);
 int  RC_PresentViewsDevice (const refdef_t *views, int n, const void *fb_dev, void *rgbx_dev, void *stream);
 int  RC_PresentViews (const refdef_t *views, int n, const uint8_t *fb_in, uint32_t *rgbx_out);
+
+/* ----------------------------------------------------------------------- 2D overlay ----
+ * ref_soft/r_draw.c.  The render.h functions (client/render.h:42-53) are exported with the reference's signatures
+ * for an engine build: they record one command each and R_EndFrame applies the frame's list to the engine's
+ * vid.buffer on the device.  Batches pass command lists directly: */
+enum { RC_D2_CHAR = 1, RC_D2_PIC, RC_D2_TRANSPIC, RC_D2_TRANSPIC_TRANSLATE, RC_D2_CONBACK, RC_D2_TILECLEAR, RC_D2_FILL, RC_D2_FADESCREEN };
+typedef struct {
+    int op;                   /* RC_D2_* */
+    int x, y, w, h;           /* Draw_Character / Draw_Pic*: x, y; Draw_TileClear / Draw_Fill: x, y, w, h */
+    int arg;                  /* character number, console lines, fill colour */
+    int pic;                  /* handle from RC_DrawPicFromWad / RC_DrawCachePic */
+    int table;                /* handle from RC_DrawTranslation (Draw_TransPicTranslate) */
+} rc_draw2d_t;
+int  RC_DrawInit (void);                                     /* Draw_Init, r_draw.c:122: conchars, disc, backtile of gfx.wad */
+int  RC_DrawPicFromWad (const char *name);                   /* Draw_PicFromWad, r_draw.c:54 -> handle > 0, or RC_ERR_* */
+int  RC_DrawCachePic (const char *path);                     /* Draw_CachePic, r_draw.c:72 (qpic .lmp under <basedir>/id1) */
+int  RC_DrawTranslation (const unsigned char *table256);     /* a 256-byte translation table -> handle */
+void RC_SetConsoleVersion (const char *text);                /* the string Draw_ConsoleBackground stamps into conback (r_draw.c:416-433) */
+/* applies cmds[first[i] .. first[i+1]) in order to view i's 8-bit plane; a command the reference would Sys_Error on
+ * (picture outside the screen) fails the call with RC_ERR_ARG before anything is drawn */
+int  RC_DrawOverlayDevice (const rc_draw2d_t *cmds, const int *first, int n, void *fb_dev, void *stream);
+int  RC_DrawOverlay (const rc_draw2d_t *cmds, const int *first, int n, uint8_t *fb_inout);
 
 /* Pipelined form of RC_RenderViews for streams of batches (timedemo-style replay, RL roll-outs): the call
  * enqueues the batch and returns; RC_WaitViews blocks until the OLDEST outstanding call has delivered its

@@ -86,6 +86,7 @@ void Sys_Printf (char *fmt, ...) { (void)fmt; }
 void SV_BroadcastPrintf (char *fmt, ...) { (void)fmt; }
 void S_ExtraUpdate (void) {}
 /* the palette R_UpdatePalette hands to the video driver (r_main.c:874), kept for orc_end_frame */
+static int orc_have_draw;
 unsigned char orc_palette[768];
 int orc_palette_uploads;
 void VID_ShiftPalette (unsigned char *p) { memcpy (orc_palette, p, 768); orc_palette_uploads++; }
@@ -210,6 +211,20 @@ int orc_init (const char *basedir, int width, int height, int heap_mb, int verbo
 	cachesize = D_SurfaceCacheForRes (width, height);
 	orc_surfcache = calloc (1, cachesize);
 	D_InitCaches (orc_surfcache, cachesize);
+
+	/* host.c:815,839: W_LoadWadFile ("gfx.wad") + Draw_Init, when the 2D assets were generated */
+	{
+		char path[600];
+		FILE *fw;
+		snprintf (path, sizeof(path), "%s/id1/gfx.wad", orc_basedir);
+		if ((fw = fopen (path, "rb")) != NULL)
+		{
+			fclose (fw);
+			W_LoadWadFile ("gfx.wad");
+			Draw_Init ();
+			orc_have_draw = 1;
+		}
+	}
 
 	R_Init ();
 
@@ -411,6 +426,37 @@ int orc_render_batch (refdef_t *rds, int n, byte *fb_out, short *z_out, double *
 		if (z_out) memcpy (z_out + px * i, d_pzbuffer, px * sizeof(short));
 	}
 	if (seconds) *seconds = Sys_FloatTime () - t0;
+	orc_abort_armed = 0;
+	return 0;
+}
+
+/* 2D overlay: one reference Draw_* call per command on vid.buffer as the last orc_render left it (our own dispatcher,
+ * the drawing is the reference's r_draw.c).  fb_out (may be NULL) receives vid.buffer afterwards. */
+typedef struct { int op, x, y, w, h, arg; char pic[40]; int fromwad; const unsigned char *table; } orc_cmd2d_t;
+int orc_draw2d (const orc_cmd2d_t *c, int n, byte *fb_out)
+{
+	int i;
+	if (!orc_have_draw) { strcpy (orc_errmsg, "gfx.wad was not present at orc_init"); return -1; }
+	orc_abort_armed = 1;
+	if (setjmp (orc_abort)) { orc_abort_armed = 0; return -1; }
+	for (i = 0; i < n; i++, c++)
+	{
+		mpic_t *pic = NULL;
+		if (c->op >= 2 && c->op <= 4)
+			pic = c->fromwad ? Draw_PicFromWad ((char *)c->pic) : Draw_CachePic ((char *)c->pic);
+		switch (c->op)
+		{
+		case 1: Draw_Character (c->x, c->y, c->arg); break;
+		case 2: Draw_Pic (c->x, c->y, pic); break;
+		case 3: Draw_TransPic (c->x, c->y, pic); break;
+		case 4: Draw_TransPicTranslate (c->x, c->y, pic, (byte *)c->table); break;
+		case 5: Draw_ConsoleBackground (c->arg); break;
+		case 6: Draw_TileClear (c->x, c->y, c->w, c->h); break;
+		case 7: Draw_Fill (c->x, c->y, c->w, c->h, c->arg); break;
+		case 8: Draw_FadeScreen (); break;
+		}
+	}
+	if (fb_out) memcpy (fb_out, vid.buffer, (size_t)vid.width * vid.height);
 	orc_abort_armed = 0;
 	return 0;
 }

@@ -39,6 +39,11 @@ def available(big: bool = False) -> bool:
     return os.path.exists(LIB_BIG if big else LIB)
 
 
+class orc_cmd2d_t(C.Structure):
+    _fields_ = [("op", C.c_int), ("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int), ("arg", C.c_int),
+                ("pic", C.c_char * 40), ("fromwad", C.c_int), ("table", C.c_void_p)]
+
+
 class RefSoft:
     def __init__(self, basedir: str, width: int, height: int, heap_mb: int = 64, verbose: int = 0):
         big = width > 1280 or height > 1024       # the stock build's static arrays end there (r_shared.h:40-41)
@@ -52,6 +57,7 @@ class RefSoft:
         L.orc_model.restype = C.c_void_p
         L.orc_load_world.restype = C.c_void_p
         L.orc_end_frame.argtypes = [C.c_void_p]
+        L.orc_draw2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_set_cvar.argtypes = [C.c_char_p, C.c_float]
         L.orc_set_cvar_string.argtypes = [C.c_char_p, C.c_char_p]
         L.orc_render.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.c_void_p]
@@ -100,6 +106,25 @@ class RefSoft:
         if rc != 0:
             raise RuntimeError("orc_render: " + self.err())
         return fb, z
+
+    def draw2d(self, cmds):
+        """cmds: list of dicts (op, x, y, w, h, arg, pic, fromwad, table) -> the reference's Draw_* calls on vid.buffer
+        as the last render() left it; returns the frame buffer."""
+        arr = (orc_cmd2d_t * max(1, len(cmds)))()
+        keep = []
+        for i, c in enumerate(cmds):
+            a = arr[i]
+            a.op, a.x, a.y, a.w, a.h, a.arg = c["op"], c.get("x", 0), c.get("y", 0), c.get("w", 0), c.get("h", 0), c.get("arg", 0)
+            a.pic = c.get("pic", "").encode()
+            a.fromwad = int(c.get("fromwad", 0))
+            if c.get("table") is not None:
+                t = (C.c_ubyte * 256)(*c["table"])
+                keep.append(t)
+                a.table = C.cast(t, C.c_void_p)
+        fb = np.empty((self.height, self.width), dtype=np.uint8)
+        if self.lib.orc_draw2d(arr, len(cmds), fb.ctypes.data) != 0:
+            raise RuntimeError("orc_draw2d: " + self.err())
+        return fb
 
     def end_frame(self):
         """R_EndFrame after render() of the same view: the palette R_UpdatePalette uploaded (768 bytes), or None

@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette=False):
+def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette=False, overlays=None):
     try:
         sys.path.insert(0, ROOT)
         from oracle.refsoft import RefSoft
@@ -29,7 +29,14 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         cm = C.addressof(C.c_char.in_dll(r.lib, "vid")) + 8     # vid.colormap (client/vid.h:36: after `byte *buffer`)
         rds = build_refdefs(specs, width, height, model_resolver=r.model, colormap_ptr=cm)
         out = {}
-        if want_palette:
+        if overlays is not None:
+            # one view at a time, the view's Draw_* commands on top of it
+            fbs = []
+            for i in range(len(specs)):
+                r.render(rds[i], False)
+                fbs.append(r.draw2d(overlays[i]))
+            out["fb"] = np.stack(fbs); out["z"] = None
+        elif want_palette:
             # one view at a time, R_EndFrame after each: frame buffer + the palette the reference uploaded
             fbs, pals = [], []
             for i in range(len(specs)):
@@ -57,10 +64,10 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         q.put(("err", traceback.format_exc()))
 
 
-def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600, want_palette=False):
+def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600, want_palette=False, overlays=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette))
+    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette, overlays))
     p.start()
     try:
         kind, payload = q.get(timeout=timeout)

@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../tochris_b200/csrc/rc_host.h"
 #include "../../tochris_b200/csrc/rc_pipeline.h"
+#include "../../tochris_b200/csrc/rc_draw2d.h"
 
 struct rc_gpu_s {
 	int width, height;
@@ -320,6 +321,29 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 	for (int v = 0; v < n; v++)
 		for (size_t p = 0; p < px; p++)
 			out[v * px + p] = pal32[v * 256 + in[v * px + p]];
+	return RC_OK;
+}
+
+/* test infrastructure: the 2D overlay as a host loop over the same per-pixel body (rc_draw2d.h) */
+static std::vector<uint8_t> sim_d2blob;
+static std::vector<rc_pic_t> sim_d2pics;
+int rc_gpu_upload_draw2d (rc_gpu_t *g, const uint8_t *blob, size_t len, const void *pics, int npics, char *err, size_t errlen)
+{
+	sim_d2blob.assign (blob, blob + len);
+	sim_d2pics.assign ((const rc_pic_t *)pics, (const rc_pic_t *)pics + npics);
+	return RC_OK;
+}
+int rc_gpu_draw2d (rc_gpu_t *g, const rc_draw2d_t *cmds, int ncmds, const int *first, int n, void *fb, void *stream, int host, char *err, size_t errlen)
+{
+	rc_d2ctx_t x;
+	x.blob = sim_d2blob.data (); x.pics = sim_d2pics.data (); x.width = g->width; x.height = g->height;
+	for (int v = 0; v < n; v++)
+		for (int ci = first[v]; ci < first[v + 1]; ci++)
+		{
+			const int cnt = rc_d2_count (&x, &cmds[ci]);
+			for (int p = 0; p < cnt; p++)
+				rc_d2_pixel (&x, &cmds[ci], p, (uint8_t *)fb + (size_t)v * g->width * g->height);
+		}
 	return RC_OK;
 }
 

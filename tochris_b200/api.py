@@ -56,6 +56,11 @@ class rc_surf_t(C.Structure):       # rc_types.h rc_surf_t, 128 B
                 ("pad2", C.c_int * 4)]
 
 
+class rc_draw2d_t(C.Structure):    # include/ref_cuda.h rc_draw2d_t
+    _fields_ = [("op", C.c_int), ("x", C.c_int), ("y", C.c_int), ("w", C.c_int), ("h", C.c_int), ("arg", C.c_int),
+                ("pic", C.c_int), ("table", C.c_int)]
+
+
 class rc_span_t(C.Structure):       # rc_types.h rc_span_t, 32 B
     _fields_ = [("u", C.c_short), ("count", C.c_short), ("pixofs", C.c_int), ("segbase", C.c_int), ("gsurf", C.c_int),
                 ("iziorg", C.c_int), ("izistep", C.c_int), ("cacheofs", C.c_int), ("cwk", C.c_uint)]
@@ -83,6 +88,13 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_DrawPicFromWad.argtypes = [C.c_char_p]
+        L.RC_DrawCachePic.argtypes = [C.c_char_p]
+        L.RC_DrawTranslation.argtypes = [C.c_void_p]
+        L.RC_SetConsoleVersion.argtypes = [C.c_char_p]
+        L.RC_SetConsoleVersion.restype = None
+        L.RC_DrawOverlay.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.RC_DrawOverlayDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.RC_SetGamma.argtypes = [C.c_float]
         L.RC_SetGamma.restype = None
         L.RC_ViewPalette.argtypes = [C.POINTER(refdef_t), C.c_void_p]
@@ -142,6 +154,52 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"RC_RenderViews failed ({rc}): {self.err()}")
         return fb, (z if want_z else None), st.value
+
+    # ---- 2D overlay (r_draw.c) ----
+    def set_console_version(self, text: str):
+        self.lib.RC_SetConsoleVersion(text.encode())
+
+    def draw_init(self):
+        if self.lib.RC_DrawInit() != 0:
+            raise RuntimeError(f"RC_DrawInit failed: {self.err()}")
+
+    def pic(self, name: str, fromwad: bool) -> int:
+        h = (self.lib.RC_DrawPicFromWad if fromwad else self.lib.RC_DrawCachePic)(name.encode())
+        if h <= 0:
+            raise RuntimeError(f"picture {name}: {self.err()}")
+        return h
+
+    def translation(self, table) -> int:
+        t = (C.c_ubyte * 256)(*table)
+        h = self.lib.RC_DrawTranslation(t)
+        if h <= 0:
+            raise RuntimeError(f"RC_DrawTranslation: {self.err()}")
+        return h
+
+    def pack_overlays(self, overlays):
+        """overlays: per view, a list of dicts like oracle.refsoft.RefSoft.draw2d takes -> (rc_draw2d_t[], first[])."""
+        total = sum(len(o) for o in overlays)
+        cmds = (rc_draw2d_t * max(1, total))()
+        first = (C.c_int * (len(overlays) + 1))()
+        k = 0
+        for i, o in enumerate(overlays):
+            first[i] = k
+            for c in o:
+                a = cmds[k]
+                a.op, a.x, a.y, a.w, a.h, a.arg = c["op"], c.get("x", 0), c.get("y", 0), c.get("w", 0), c.get("h", 0), c.get("arg", 0)
+                if c.get("pic"):
+                    a.pic = self.pic(c["pic"], bool(c.get("fromwad", 0)))
+                if c.get("table") is not None:
+                    a.table = self.translation(c["table"])
+                k += 1
+        first[len(overlays)] = k
+        return cmds, first
+
+    def draw_overlay(self, overlays, fb: np.ndarray) -> int:
+        """RC_DrawOverlay: applies each view's command list to its plane of `fb` (host, in place); returns the C return code."""
+        cmds, first = self.pack_overlays(overlays)
+        assert fb.flags["C_CONTIGUOUS"] and fb.dtype == np.uint8
+        return self.lib.RC_DrawOverlay(cmds, first, len(overlays), fb.ctypes.data)
 
     def set_gamma(self, gamma: float):
         self.lib.RC_SetGamma(gamma)

@@ -12,8 +12,10 @@
 #include <math.h>
 #include <dlfcn.h>
 #include "rc_host.h"
+#include "rc_draw2d.h"
 
 #define RC_MAX_MODELS 512
+#define RC_MAX_PICS 256
 
 static struct {
 	int          inited;
@@ -29,6 +31,14 @@ static struct {
 	struct model_s *world;
 	char         err[1024];
 	int          unsupported;
+	/* 2D overlay (r_draw.c): conchars + pictures + translation tables in one blob, mirrored on the device */
+	uint8_t     *d2blob; size_t d2len, d2cap;
+	rc_pic_t     d2pics[RC_MAX_PICS]; char d2names[RC_MAX_PICS][64]; int d2npics;
+	struct mpic_s *d2mpics[RC_MAX_PICS];	/* mpic_t views of the pictures for the render.h functions */
+	int          d2dirty, d2ready;
+	char         d2version[100];
+	uint8_t     *wad; size_t wadlen;
+	rc_draw2d_t *d2frame; int d2framen, d2framecap;	/* commands recorded by the render.h Draw_* functions since R_BeginFrame */
 	float        gamma; uint8_t gammatable[256]; int gamma_valid;	/* v_gamma + R_BuildGammaTable */
 	uint32_t    *palscratch; int palscratchcap;
 	int          async_unsupported[2]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
@@ -745,6 +755,300 @@ int RC_PresentViews (const refdef_t *views, int n, const uint8_t *fb_in, uint32_
 	return rc_gpu_present (rc.gpu, rc.palscratch, n, fb_in, rgbx_out, NULL, 1, rc.err, sizeof(rc.err));
 }
 
+/* ------------------------------------------------------------------ 2D overlay (r_draw.c) ---- */
+typedef struct { char identification[4]; int numlumps; int infotableofs; } rc_wadinfo_t;			/* wad.h:47-52 */
+typedef struct { int filepos, disksize, size; char type, compression, pad1, pad2; char name[16]; } rc_lumpinfo_t;	/* wad.h:54-63 */
+struct mpic_s { int width; short height; unsigned char alpha, pad; unsigned char data[4]; };		/* r_shared.h:78-85 */
+
+static int rc_d2_append (const void *data, size_t len, int align)
+{
+	size_t ofs = (rc.d2len + (size_t)align - 1) & ~((size_t)align - 1);
+	if (ofs + len > rc.d2cap)
+	{
+		size_t ncap = (ofs + len) * 2 + 65536;
+		uint8_t *nb = (uint8_t *)realloc (rc.d2blob, ncap);
+		if (!nb) return -1;
+		memset (nb + rc.d2cap, 0, ncap - rc.d2cap);
+		rc.d2blob = nb; rc.d2cap = ncap;
+	}
+	if (data) memcpy (rc.d2blob + ofs, data, len);
+	rc.d2len = ofs + len;
+	rc.d2dirty = 1;
+	return (int)ofs;
+}
+
+/* W_GetLumpName (wad.c:124-140) with W_CleanupName's case folding */
+static const uint8_t *rc_wad_lump (const char *name, int *size)
+{
+	const rc_wadinfo_t *h = (const rc_wadinfo_t *)rc.wad;
+	const rc_lumpinfo_t *l;
+	int i, k;
+	if (!rc.wad) return NULL;
+	l = (const rc_lumpinfo_t *)(rc.wad + h->infotableofs);
+	for (i = 0; i < h->numlumps; i++, l++)
+	{
+		for (k = 0; k < 16; k++)
+		{
+			int a = (unsigned char)l->name[k], b = (unsigned char)name[k];
+			if (a >= 'A' && a <= 'Z') a += 'a' - 'A';
+			if (b >= 'A' && b <= 'Z') b += 'a' - 'A';
+			if (a != b) break;
+			if (!a) { k = 16; break; }
+		}
+		if (k == 16)
+		{
+			if ((size_t)l->filepos + (size_t)l->size > rc.wadlen) return NULL;
+			if (size) *size = l->size;
+			return rc.wad + l->filepos;
+		}
+	}
+	return NULL;
+}
+
+/* registers a qpic_t (int width, height, data) under `name`; returns the handle */
+static int rc_d2_add_qpic (const char *name, const uint8_t *qpic, size_t len, int slot)
+{
+	int w, h, ofs, i;
+	if (len < 8) return rc_fail (RC_ERR_FORMAT, "%s: not a qpic", name);
+	memcpy (&w, qpic, 4); memcpy (&h, qpic + 4, 4);
+	if (w <= 0 || h <= 0 || w > 4096 || h > 4096 || (size_t)w * h + 8 > len) return rc_fail (RC_ERR_FORMAT, "%s: bad qpic size %dx%d", name, w, h);
+	if (slot < 0)
+	{
+		if (rc.d2npics >= RC_MAX_PICS) return rc_fail (RC_ERR_NOMEM, "too many pictures");
+		slot = rc.d2npics++;
+	}
+	ofs = rc_d2_append (qpic + 8, (size_t)w * h, 16);
+	if (ofs < 0) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	rc.d2pics[slot].ofs = ofs; rc.d2pics[slot].width = w; rc.d2pics[slot].height = h;
+	rc.d2pics[slot].alpha = memchr (qpic + 8, 255, (size_t)w * h) != NULL;		/* r_draw.c:62 */
+	snprintf (rc.d2names[slot], sizeof(rc.d2names[slot]), "%s", name);
+	free (rc.d2mpics[slot]);
+	rc.d2mpics[slot] = (struct mpic_s *)malloc (sizeof(struct mpic_s) + (size_t)w * h);
+	if (rc.d2mpics[slot])
+	{
+		rc.d2mpics[slot]->width = w; rc.d2mpics[slot]->height = (short)h; rc.d2mpics[slot]->alpha = (unsigned char)rc.d2pics[slot].alpha; rc.d2mpics[slot]->pad = 0;
+		memcpy (rc.d2mpics[slot]->data, qpic + 8, (size_t)w * h);
+	}
+	(void)i;
+	return slot;
+}
+
+/* Draw_CharToConback, r_draw.c:377-400: the version string stamped into the console picture */
+static void rc_d2_stamp_conback (void)
+{
+	const rc_pic_t *pc = &rc.d2pics[2];
+	const char *ver = rc.d2version;
+	size_t n = strlen (ver), x;
+	uint8_t *dest0;
+	if (pc->width != 320 || pc->height != 200 || !n || 11 + 8 * n > 320) return;
+	dest0 = rc.d2blob + pc->ofs + 320 * 186 + 320 - 11 - 8 * n;
+	for (x = 0; x < n; x++)
+	{
+		int num = (unsigned char)ver[x], drawline, xx;
+		const uint8_t *source = rc.d2blob + ((num >> 4) << 10) + ((num & 15) << 3);
+		uint8_t *dest = dest0 + (x << 3);
+		for (drawline = 0; drawline < 8; drawline++, source += 128, dest += 320)
+			for (xx = 0; xx < 8; xx++)
+				if (source[xx])
+					dest[xx] = (uint8_t)(0x60 + source[xx]);
+	}
+	rc.d2dirty = 1;
+}
+
+void RC_SetConsoleVersion (const char *text)
+{
+	snprintf (rc.d2version, sizeof(rc.d2version), "%s", text ? text : "");
+}
+
+int RC_DrawInit (void)
+{
+	const uint8_t *l;
+	int size = 0, r;
+	size_t len;
+	uint8_t *cb;
+	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
+	if (rc.d2ready) return RC_OK;
+	free (rc.wad);
+	rc.wad = (uint8_t *)rc_read_file ("gfx.wad", &rc.wadlen);		/* host.c:815 W_LoadWadFile ("gfx.wad") */
+	if (!rc.wad || rc.wadlen < sizeof(rc_wadinfo_t) || memcmp (rc.wad, "WAD2", 4))
+		return rc_fail (RC_ERR_FILE, "W_LoadWadFile: couldn't load gfx.wad");
+	{
+		const rc_wadinfo_t *h = (const rc_wadinfo_t *)rc.wad;
+		if (h->numlumps < 0 || h->infotableofs < 0 || (size_t)h->infotableofs + (size_t)h->numlumps * sizeof(rc_lumpinfo_t) > rc.wadlen)
+			return rc_fail (RC_ERR_FORMAT, "gfx.wad: bad directory");
+	}
+	rc.d2len = 0;
+	l = rc_wad_lump ("conchars", &size);
+	if (!l || size < 128 * 128) return rc_fail (RC_ERR_FILE, "W_GetLumpinfo: conchars not found");
+	if (rc_d2_append (l, 128 * 128, 16) != 0) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	rc.d2npics = 3;			/* 0 unused, 1 backtile, 2 conback */
+	memset (&rc.d2pics[0], 0, sizeof(rc.d2pics[0]));
+	l = rc_wad_lump ("backtile", &size);
+	if (!l) return rc_fail (RC_ERR_FILE, "W_GetLumpinfo: backtile not found");
+	if ((r = rc_d2_add_qpic ("backtile", l, (size_t)size, 1)) < 0) return r;
+	if (!rc_wad_lump ("disc", &size)) return rc_fail (RC_ERR_FILE, "W_GetLumpinfo: disc not found");
+	/* Draw_ConsoleBackground loads gfx/conback.lmp on first use (r_draw.c:415); absent: a 320x200 picture of colour 0 */
+	cb = (uint8_t *)rc_read_file ("gfx/conback.lmp", &len);
+	if (cb)
+		r = rc_d2_add_qpic ("gfx/conback.lmp", cb, len, 2);
+	else
+	{
+		uint8_t *blank = (uint8_t *)calloc (1, 8 + 320 * 200);
+		int w = 320, h = 200;
+		if (!blank) return rc_fail (RC_ERR_NOMEM, "out of memory");
+		memcpy (blank, &w, 4); memcpy (blank + 4, &h, 4);
+		r = rc_d2_add_qpic ("gfx/conback.lmp", blank, 8 + 320 * 200, 2);
+		free (blank);
+	}
+	free (cb);
+	if (r < 0) return r;
+	rc_d2_stamp_conback ();
+	rc.d2ready = 1;
+	return RC_OK;
+}
+
+static int rc_d2_find (const char *name)
+{
+	int i;
+	for (i = 3; i < rc.d2npics; i++)
+		if (!strcmp (rc.d2names[i], name)) return i;
+	return -1;
+}
+
+int RC_DrawPicFromWad (const char *name)
+{
+	const uint8_t *l;
+	int size = 0, i, r;
+	char key[64];
+	if ((r = RC_DrawInit ()) != RC_OK) return r;
+	snprintf (key, sizeof(key), "wad:%s", name);
+	if ((i = rc_d2_find (key)) >= 0) return i;
+	l = rc_wad_lump (name, &size);
+	if (!l) return rc_fail (RC_ERR_FILE, "W_GetLumpinfo: %s not found", name);
+	return rc_d2_add_qpic (key, l, (size_t)size, -1);
+}
+
+int RC_DrawCachePic (const char *path)
+{
+	int i, r;
+	size_t len;
+	uint8_t *buf;
+	if ((r = RC_DrawInit ()) != RC_OK) return r;
+	if (!strcmp (path, "gfx/conback.lmp")) return 2;
+	if ((i = rc_d2_find (path)) >= 0) return i;
+	buf = (uint8_t *)rc_read_file (path, &len);
+	if (!buf) return rc_fail (RC_ERR_FILE, "Draw_CachePic: failed to load %s", path);
+	r = rc_d2_add_qpic (path, buf, len, -1);
+	free (buf);
+	return r;
+}
+
+int RC_DrawTranslation (const unsigned char *table256)
+{
+	int r, ofs;
+	if ((r = RC_DrawInit ()) != RC_OK) return r;
+	if (!table256) return rc_fail (RC_ERR_ARG, "RC_DrawTranslation: NULL table");
+	ofs = rc_d2_append (table256, 256, 16);
+	if (ofs < 0) return rc_fail (RC_ERR_NOMEM, "out of memory");
+	return ofs;			/* the handle is the table's place in the blob */
+}
+
+/* the checks the reference makes before it touches vid.buffer: Sys_Error there, RC_ERR_ARG here; commands that
+ * the reference silently ignores (characters off screen) stay in the list and draw nothing */
+static int rc_d2_validate (const rc_draw2d_t *c, int idx)
+{
+	const int W = rc.vid.width, H = rc.vid.height;
+	switch (c->op)
+	{
+	case RC_D2_CHAR: return RC_OK;
+	case RC_D2_PIC: case RC_D2_TRANSPIC: case RC_D2_TRANSPIC_TRANSLATE:
+		if (c->pic < 1 || c->pic >= rc.d2npics) return rc_fail (RC_ERR_ARG, "draw command %d: bad picture handle %d", idx, c->pic);
+		if (c->x < 0 || c->y < 0 || c->x + rc.d2pics[c->pic].width > W || c->y + rc.d2pics[c->pic].height > H)
+			return rc_fail (RC_ERR_ARG, "draw command %d: Draw_Pic: bad coordinates", idx);		/* r_draw.c:237-243,267-271 */
+		if (c->op == RC_D2_TRANSPIC_TRANSLATE && (c->table < 128 * 128 || (size_t)c->table + 256 > rc.d2len))
+			return rc_fail (RC_ERR_ARG, "draw command %d: bad translation handle", idx);
+		return RC_OK;
+	case RC_D2_CONBACK:
+		if (c->arg < 0 || c->arg > H) return rc_fail (RC_ERR_ARG, "draw command %d: Draw_ConsoleBackground: %d lines", idx, c->arg);
+		return RC_OK;
+	case RC_D2_TILECLEAR: case RC_D2_FILL:
+		/* the reference writes whatever rectangle it is given; outside the screen that is a stray write */
+		if (c->w < 0 || c->h < 0 || c->x < 0 || c->y < 0 || c->x + c->w > W || c->y + c->h > H)
+			return rc_fail (RC_ERR_ARG, "draw command %d: rectangle outside the screen", idx);
+		return RC_OK;
+	case RC_D2_FADESCREEN: return RC_OK;
+	}
+	return rc_fail (RC_ERR_ARG, "draw command %d: unknown op %d", idx, c->op);
+}
+
+static int rc_d2_run (const rc_draw2d_t *cmds, const int *first, int n, void *fb, void *stream, int host)
+{
+	int i, r, total;
+	if ((r = RC_DrawInit ()) != RC_OK) return r;
+	if (!cmds || !first || n <= 0 || !fb) return rc_fail (RC_ERR_ARG, "RC_DrawOverlay: bad argument");
+	total = first[n];
+	for (i = 0; i < n; i++)
+		if (first[i] < 0 || first[i] > first[i + 1]) return rc_fail (RC_ERR_ARG, "RC_DrawOverlay: `first` must be non-decreasing");
+	for (i = first[0]; i < total; i++)
+		if ((r = rc_d2_validate (&cmds[i], i)) != RC_OK) return r;
+	if (rc.d2dirty)
+	{
+		if ((r = rc_gpu_upload_draw2d (rc.gpu, rc.d2blob, rc.d2len, rc.d2pics, rc.d2npics, rc.err, sizeof(rc.err))) != RC_OK) return r;
+		rc.d2dirty = 0;
+	}
+	return rc_gpu_draw2d (rc.gpu, cmds, total, first, n, fb, stream, host, rc.err, sizeof(rc.err));
+}
+
+int RC_DrawOverlayDevice (const rc_draw2d_t *cmds, const int *first, int n, void *fb_dev, void *stream)
+{
+	return rc_d2_run (cmds, first, n, fb_dev, stream, 0);
+}
+
+int RC_DrawOverlay (const rc_draw2d_t *cmds, const int *first, int n, uint8_t *fb_inout)
+{
+	return rc_d2_run (cmds, first, n, fb_inout, NULL, 1);
+}
+
+/* ---- the render.h names (client/render.h:42-53): one recorded command each, applied by R_EndFrame ---- */
+static void rc_d2_record (int op, int x, int y, int w, int h, int arg, int pic, int table)
+{
+	rc_draw2d_t *c;
+	if (rc.d2framen >= rc.d2framecap)
+	{
+		int ncap = rc.d2framecap ? rc.d2framecap * 2 : 256;
+		rc_draw2d_t *nb = (rc_draw2d_t *)realloc (rc.d2frame, sizeof(rc_draw2d_t) * (size_t)ncap);
+		if (!nb) return;
+		rc.d2frame = nb; rc.d2framecap = ncap;
+	}
+	c = &rc.d2frame[rc.d2framen++];
+	c->op = op; c->x = x; c->y = y; c->w = w; c->h = h; c->arg = arg; c->pic = pic; c->table = table;
+}
+
+static int rc_d2_handle_of (struct mpic_s *pic)
+{
+	int i;
+	for (i = 1; i < rc.d2npics; i++)
+		if (rc.d2mpics[i] == pic) return i;
+	return 0;
+}
+
+void Draw_Init (void) { if (RC_DrawInit () != RC_OK) fprintf (stderr, "ref_cuda: %s\n", rc.err); }
+struct mpic_s *Draw_PicFromWad (char *name) { int h = RC_DrawPicFromWad (name); return h > 0 ? rc.d2mpics[h] : NULL; }
+struct mpic_s *Draw_CachePic (char *path) { int h = RC_DrawCachePic (path); return h > 0 ? rc.d2mpics[h] : NULL; }
+void Draw_Character (int x, int y, int num) { rc_d2_record (RC_D2_CHAR, x, y, 0, 0, num, 0, 0); }
+void Draw_String (int x, int y, char *str) { for (; *str; str++, x += 8) Draw_Character (x, y, *str); }		/* r_draw.c:211-219 */
+void Draw_Pic (int x, int y, struct mpic_s *pic) { rc_d2_record (RC_D2_PIC, x, y, 0, 0, 0, rc_d2_handle_of (pic), 0); }
+void Draw_TransPic (int x, int y, struct mpic_s *pic) { rc_d2_record (RC_D2_TRANSPIC, x, y, 0, 0, 0, rc_d2_handle_of (pic), 0); }
+void Draw_TransPicTranslate (int x, int y, struct mpic_s *pic, unsigned char *translation)
+{
+	int t = RC_DrawTranslation (translation);
+	if (t > 0) rc_d2_record (RC_D2_TRANSPIC_TRANSLATE, x, y, 0, 0, 0, rc_d2_handle_of (pic), t);
+}
+void Draw_ConsoleBackground (int lines) { rc_d2_record (RC_D2_CONBACK, 0, 0, 0, 0, lines, 0, 0); }
+void Draw_TileClear (int x, int y, int w, int h) { rc_d2_record (RC_D2_TILECLEAR, x, y, w, h, 0, 0, 0); }
+void Draw_Fill (int x, int y, int w, int h, int c) { rc_d2_record (RC_D2_FILL, x, y, w, h, c, 0, 0); }
+void Draw_FadeScreen (void) { rc_d2_record (RC_D2_FADESCREEN, 0, 0, 0, 0, 0, 0, 0); }
+
 void RC_SetVidBuffers (uint8_t *buffer, int rowbytes, int16_t *zbuffer)
 {
 	rc.vidbuffer = buffer; rc.vidrowbytes = rowbytes; rc.zbuffer = zbuffer;
@@ -752,8 +1056,21 @@ void RC_SetVidBuffers (uint8_t *buffer, int rowbytes, int16_t *zbuffer)
 
 /* the render.h single-view path: one view through the batched pipeline, copied into the
  * engine's vid.buffer / d_pzbuffer */
-void R_BeginFrame (void) {}
-void R_EndFrame (void) {}
+void R_BeginFrame (void) { rc.d2framen = 0; }
+
+/* r_main.c:961-980.  The frame's 2D commands are applied to the engine's vid.buffer on the device (upload, k_draw2d,
+ * download); the palette is the caller's business (RC_ViewPalette -> VID_ShiftPalette). */
+void R_EndFrame (void)
+{
+	if (rc.d2framen && rc.vidbuffer && rc.vidrowbytes == rc.vid.width)
+	{
+		int first[2];
+		first[0] = 0; first[1] = rc.d2framen;
+		if (RC_DrawOverlay (rc.d2frame, first, 1, rc.vidbuffer) != RC_OK)
+			fprintf (stderr, "ref_cuda: %s\n", rc.err);
+	}
+	rc.d2framen = 0;
+}
 
 void R_RenderView (refdef_t *refdef)
 {

@@ -31,6 +31,7 @@
 #include <vector>
 #include "rc_host.h"
 #include "rc_pipeline.h"
+#include "rc_draw2d.h"
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
 	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
@@ -80,6 +81,7 @@ struct rc_gpu_s {
 	int *d_status;
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
+	uint8_t *d_d2blob; void *d_d2pics; rc_draw2d_t *d_d2cmds; int *d_d2first; int d2cmdcap, d2firstcap;	/* 2D overlay */
 	uint32_t *d_pal32; int palcap; uint32_t *h_pal32[2]; cudaEvent_t evpal[2]; int palslot;	/* pinned staging ring for the palettes */
 	uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
 	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
@@ -1393,6 +1395,22 @@ __global__ void __launch_bounds__(256) k_present (const uint8_t * __restrict__ f
 	}
 }
 
+/* 2D overlay (r_draw.c): one CTA per view runs the view's commands IN ORDER (later commands overwrite earlier ones),
+ * its threads share the pixels of each command. */
+__global__ void __launch_bounds__(256) k_draw2d (const rc_d2ctx_t x, const rc_draw2d_t * __restrict__ cmds, const int * __restrict__ first, uint8_t *fb)
+{
+	const int vi = blockIdx.x;
+	uint8_t *plane = fb + (size_t)vi * x.width * x.height;
+	for (int ci = first[vi]; ci < first[vi + 1]; ci++)
+	{
+		const rc_draw2d_t c = cmds[ci];
+		const int cnt = rc_d2_count (&x, &c);
+		for (int p = threadIdx.x; p < cnt; p += blockDim.x)
+			rc_d2_pixel (&x, &c, p, plane);
+		__syncthreads ();
+	}
+}
+
 __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1436,6 +1454,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 		cudaEventCreateWithFlags (&g->adone_s[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags (&g->adone_copy[i], cudaEventDisableTiming);
 	}
+	g->d_d2blob = NULL; g->d_d2pics = NULL; g->d_d2cmds = NULL; g->d_d2first = NULL; g->d2cmdcap = 0; g->d2firstcap = 0;
 	g->d_pal32 = NULL; g->palcap = 0; g->h_pal32[0] = g->h_pal32[1] = NULL; g->palslot = 0;
 	cudaEventCreateWithFlags (&g->evpal[0], cudaEventDisableTiming); cudaEventCreateWithFlags (&g->evpal[1], cudaEventDisableTiming);
 	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
@@ -1517,6 +1536,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	for (int i = 0; i < 2; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
 	cudaFreeHost (g->astatus);
 	cudaFree (g->d_pal32); cudaFree (g->d_presentin); cudaFree (g->d_presentout);
+	cudaFree (g->d_d2blob); cudaFree (g->d_d2pics); cudaFree (g->d_d2cmds); cudaFree (g->d_d2first);
 	cudaFreeHost (g->h_pal32[0]); cudaFreeHost (g->h_pal32[1]); cudaEventDestroy (g->evpal[0]); cudaEventDestroy (g->evpal[1]);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
@@ -2292,6 +2312,61 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 		CK (cudaMemcpyAsync (rgbx, g->d_presentout, px * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
 	}
+	return RC_OK;
+}
+
+int rc_gpu_upload_draw2d (rc_gpu_t *g, const uint8_t *blob, size_t len, const void *pics, int npics, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	cudaDeviceSynchronize ();
+	cudaFree (g->d_d2blob); cudaFree (g->d_d2pics); g->d_d2blob = NULL; g->d_d2pics = NULL;
+	CK (cudaMalloc (&g->d_d2blob, len + 16));
+	CK (cudaMalloc (&g->d_d2pics, sizeof(rc_pic_t) * (size_t)(npics + 1)));
+	CK (cudaMemcpy (g->d_d2blob, blob, len, cudaMemcpyHostToDevice));
+	CK (cudaMemcpy (g->d_d2pics, pics, sizeof(rc_pic_t) * (size_t)npics, cudaMemcpyHostToDevice));
+	return RC_OK;
+}
+
+int rc_gpu_draw2d (rc_gpu_t *g, const rc_draw2d_t *cmds, int ncmds, const int *first, int n, void *fb, void *stream, int host, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	const size_t px = (size_t)g->width * g->height;
+	if (!g->d_d2blob) { snprintf (err, errlen, "2D assets not uploaded"); return RC_ERR_ARG; }
+	if (ncmds > g->d2cmdcap || n + 1 > g->d2firstcap)
+	{
+		cudaStreamSynchronize (s);
+		cudaFree (g->d_d2cmds); cudaFree (g->d_d2first); g->d_d2cmds = NULL; g->d_d2first = NULL;
+		g->d2cmdcap = ncmds + 1024; g->d2firstcap = n + 1 + 256;
+		CK (cudaMalloc (&g->d_d2cmds, sizeof(rc_draw2d_t) * (size_t)g->d2cmdcap));
+		CK (cudaMalloc (&g->d_d2first, sizeof(int) * (size_t)g->d2firstcap));
+	}
+	if (ncmds) CK (cudaMemcpyAsync (g->d_d2cmds, cmds, sizeof(rc_draw2d_t) * (size_t)ncmds, cudaMemcpyHostToDevice, s));
+	CK (cudaMemcpyAsync (g->d_d2first, first, sizeof(int) * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
+	uint8_t *fbd = (uint8_t *)fb;
+	if (host)
+	{
+		if (g->presentcap < px * n)
+		{
+			cudaFree (g->d_presentin); cudaFree (g->d_presentout); g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
+			CK (cudaMalloc (&g->d_presentin, px * n));
+			CK (cudaMalloc (&g->d_presentout, px * n * sizeof(uint32_t)));
+			g->presentcap = px * n;
+		}
+		CK (cudaMemcpyAsync (g->d_presentin, fb, px * n, cudaMemcpyHostToDevice, s));
+		fbd = g->d_presentin;
+	}
+	rc_d2ctx_t x;
+	x.blob = g->d_d2blob; x.pics = (const rc_pic_t *)g->d_d2pics; x.width = g->width; x.height = g->height;
+	k_draw2d<<<n, 256, 0, s>>> (x, g->d_d2cmds, g->d_d2first, fbd);
+	CK (cudaGetLastError ());
+	if (host)
+	{
+		CK (cudaMemcpyAsync (fb, g->d_presentin, px * n, cudaMemcpyDeviceToHost, s));
+		CK (cudaStreamSynchronize (s));
+	}
+	else
+		CK (cudaStreamSynchronize (s));		/* cmds / first are the caller's: they may be reused when this returns */
 	return RC_OK;
 }
 

@@ -172,6 +172,10 @@ void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *s
 int  rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen);
 /* pal32: n x 256 palette entries (R | G << 8 | B << 16 | 255 << 24); fb / rgbx device pointers, or host pointers with host != 0 */
 int  rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, void *rgbx, void *stream, int host, char *err, size_t errlen);
+/* 2D overlay: the blob (conchars, pictures, translation tables) and picture table; then command lists per view */
+struct rc_pic_s;
+int  rc_gpu_upload_draw2d (rc_gpu_t *g, const uint8_t *blob, size_t len, const void *pics, int npics, char *err, size_t errlen);
+int  rc_gpu_draw2d (rc_gpu_t *g, const rc_draw2d_t *cmds, int ncmds, const int *first, int n, void *fb, void *stream, int host, char *err, size_t errlen);
 void rc_gpu_get_stats (rc_gpu_t *g, rc_stats_t *out);
 void rc_gpu_set_profiling (rc_gpu_t *g, int on);
 int  rc_gpu_debug_read (rc_gpu_t *g, int kind, int view, void *dst, int cap);

@@ -155,3 +155,57 @@ def skybox_pcx(name: str, seed: int = 0x51AB) -> dict:
         pix[:, :4] = 200 + k
         out[suf] = encode_pcx(pix, pal)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# 2D assets: gfx.wad (WAD2, common/wad.c:66-110, wad.h:30-75) and qpic .lmp files (Draw_CachePic, r_draw.c:72)
+
+TYP_QPIC, TYP_LUMPY = 66, 64
+
+
+def make_qpic(w: int, h: int, seed: int, transparent: bool = False) -> bytes:
+    """qpic_t: int width, height, then w*h palette indices; index 255 (TRANSPARENT_COLOR) only when asked for."""
+    pix = (_lcg_noise(seed, w, h).astype(np.uint32) * 7 + np.add.outer(np.arange(h), np.arange(w)).astype(np.uint32)) % 224
+    pix = pix.astype(np.uint8)
+    if transparent:
+        hole = (_lcg_noise(seed ^ 0x5A5A, w, h) & 3) == 0
+        pix[hole] = 255
+    return struct.pack("<ii", w, h) + pix.tobytes()
+
+
+def make_conchars(seed: int = 0x51AB) -> bytes:
+    """128x128 character sheet, 0 = transparent (Draw_Character, r_draw.c:152-205)."""
+    pix = _lcg_noise(seed, 128, 128)
+    glyph = (_lcg_noise(seed ^ 0x77, 128, 128) & 1).astype(bool)
+    out = np.where(glyph, (pix % 200 + 1).astype(np.uint8), 0).astype(np.uint8)
+    return out.tobytes()
+
+
+def make_wad2(lumps) -> bytes:
+    """lumps: list of (name, type, bytes).  Header, lump data, then the info table."""
+    blob = bytearray(b"WAD2" + struct.pack("<ii", len(lumps), 0))
+    info = []
+    for name, typ, data in lumps:
+        while len(blob) & 3:
+            blob.append(0)
+        info.append((len(blob), len(data), typ, name))
+        blob += data
+    while len(blob) & 3:
+        blob.append(0)
+    ofs = len(blob)
+    for pos, size, typ, name in info:
+        blob += struct.pack("<iiibbbb16s", pos, size, size, typ, 0, 0, 0, name.upper().encode())
+    struct.pack_into("<i", blob, 8, ofs)
+    return bytes(blob)
+
+
+def gfx_wad() -> bytes:
+    return make_wad2([
+        ("conchars", TYP_LUMPY, make_conchars()),
+        ("disc", TYP_QPIC, make_qpic(24, 24, 11, transparent=True)),
+        ("backtile", TYP_QPIC, make_qpic(64, 64, 12)),
+        ("sbar", TYP_QPIC, make_qpic(320, 24, 13)),
+        ("num_3", TYP_QPIC, make_qpic(24, 24, 14, transparent=True)),
+        ("face1", TYP_QPIC, make_qpic(21, 19, 15, transparent=True)),      # width not a multiple of 8: the "general" loops
+        ("ibar", TYP_QPIC, make_qpic(320, 24, 16)),
+    ])

@@ -50,6 +50,13 @@ def write_base_assets(basedir: str):
         f.write(pal.tobytes())
     with open(os.path.join(gfx, "colormap.lmp"), "wb") as f:
         f.write(assets.make_colormap(pal))
+    # 2D assets: host.c:815 loads gfx.wad, Draw_ConsoleBackground / the menus load qpic lumps with Draw_CachePic
+    with open(os.path.join(basedir, "id1", "gfx.wad"), "wb") as f:
+        f.write(assets.gfx_wad())
+    with open(os.path.join(gfx, "conback.lmp"), "wb") as f:
+        f.write(assets.make_qpic(320, 200, 21))
+    with open(os.path.join(gfx, "menuplyr.lmp"), "wb") as f:
+        f.write(assets.make_qpic(48, 56, 22, transparent=True))
 
 
 def write_file(basedir: str, relname: str, data: bytes):
