@@ -135,6 +135,9 @@ const char *RC_LastError (void);
 /* Mod_ForName + R_NewMap in one call, with an error code instead of Sys_Error
  * (client/cl_parse.c:271,294). */
 int  RC_LoadWorld (const char *name);
+/* the r_loadlits cvar (r_main.c:130, Mod_LoadLighting r_model.c:528-566): brush models loaded afterwards take their
+ * light samples from "<map>.lit" (QLIT version 1, max of r, g, b) when that file exists */
+void RC_SetLoadLits (int on);
 
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)

@@ -88,6 +88,8 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_SetLoadLits.argtypes = [C.c_int]
+        L.RC_SetLoadLits.restype = None
         L.RC_DrawPicFromWad.argtypes = [C.c_char_p]
         L.RC_DrawCachePic.argtypes = [C.c_char_p]
         L.RC_DrawTranslation.argtypes = [C.c_void_p]
@@ -121,12 +123,17 @@ class RefCuda:
         cfg.width, cfg.height, cfg.device = width, height, device
         self._basedir = basedir.encode()
         cfg.basedir = self._basedir
+        loadlits = cvars.pop("r_loadlits", 0)            # not a field of rc_config_t: its own call (RC_SetLoadLits)
+        gamma = cvars.pop("gamma", None)
         for k, v in cvars.items():
             setattr(cfg, k, v)
         self.width, self.height = width, height
         rc = L.RC_Init(C.byref(cfg))
         if rc != 0:
             raise RuntimeError(f"RC_Init failed ({rc}): {L.RC_LastError().decode()}")
+        L.RC_SetLoadLits(int(bool(loadlits)))
+        if gamma is not None:
+            L.RC_SetGamma(float(gamma))
 
     def err(self) -> str:
         return self.lib.RC_LastError().decode()

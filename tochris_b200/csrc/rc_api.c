@@ -31,6 +31,7 @@ static struct {
 	struct model_s *world;
 	char         err[1024];
 	int          unsupported;
+	int          loadlits;		/* r_loadlits (r_main.c:130) */
 	/* 2D overlay (r_draw.c): conchars + pictures + translation tables in one blob, mirrored on the device */
 	uint8_t     *d2blob; size_t d2len, d2cap;
 	rc_pic_t     d2pics[RC_MAX_PICS]; char d2names[RC_MAX_PICS][64]; int d2npics;
@@ -225,6 +226,21 @@ static struct model_s *rc_load_model (const char *name)
 		rc_hostworld_t *hw = RC_LoadBrushModel (buf, len, rc.colormap, rc.err, sizeof(rc.err));
 		free (buf);
 		if (!hw) return NULL;
+		if (rc.loadlits)
+		{
+			/* r_model.c:533-536: the model's name with the extension replaced by ".lit" */
+			char litname[600];
+			char *dot;
+			size_t litlen;
+			void *lit;
+			snprintf (litname, sizeof(litname) - 5, "%s", name);
+			dot = strrchr (litname, '.');
+			if (dot && !strchr (dot, '/')) *dot = 0;
+			strcat (litname, ".lit");
+			lit = rc_read_file (litname, &litlen);
+			if (lit) RC_ApplyLit (hw, (const uint8_t *)lit, litlen);
+			free (lit);
+		}
 		/* r_model.c:1098-1126: model 0 under its file name, submodels as "*1", "*2", ... */
 		for (i = 0; i < hw->numsubmodels; i++)
 		{
@@ -690,6 +706,8 @@ static void rc_build_gamma (void)
 		}
 	rc.gamma_valid = 2;
 }
+
+void RC_SetLoadLits (int on) { rc.loadlits = on; }
 
 void RC_SetGamma (float gamma)
 {

@@ -109,6 +109,7 @@ void RC_BuildTurbTables (int *sintable, int *intsintable, int n);
 /* BSP29 -> flat arrays.  Mirrors Mod_LoadBrushModel (ref_soft/r_model.c:1062-1127).
  * Returns NULL and fills err on malformed data (the reference calls Sys_Error). */
 rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *colormap, char *err, size_t errlen);
+int  RC_ApplyLit (rc_hostworld_t *hw, const uint8_t *lit, size_t litlen);
 void RC_FreeHostWorld (rc_hostworld_t *hw);
 
 rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, char *err, size_t errlen);

@@ -62,6 +62,29 @@ static float vector_length (const float *v)
 	return length;
 }
 
+/* Mod_LoadLighting with r_loadlits set (r_model.c:528-566): "<map>.lit", "QLIT" version 1, RGB triples; the software
+ * renderer keeps max (r, g, b) per sample.  Anything else leaves the BSP's own lighting lump in place, as the
+ * reference falls back to it.  Returns 1 when the .lit was used. */
+int RC_ApplyLit (rc_hostworld_t *hw, const uint8_t *lit, size_t litlen)
+{
+	uint8_t *out = (uint8_t *)hw->w.lightdata;
+	size_t i, s;
+	int ver;
+	if (!hw->w.haslight || !lit || litlen < 8) return 0;		/* r_model.c:516-520: no lump, no light data at all */
+	if (lit[0] != 'Q' || lit[1] != 'L' || lit[2] != 'I' || lit[3] != 'T') return 0;
+	memcpy (&ver, lit + 4, 4);
+	if (ver != 1) return 0;
+	s = (litlen - 8) / 3;
+	if (s > hw->lightbytes) s = hw->lightbytes;			/* samples past the lump are never indexed (lightofs is checked against it) */
+	for (i = 0; i < s; i++)
+	{
+		const uint8_t *t = lit + 8 + 3 * i;
+		uint8_t p = t[0] > t[1] ? t[0] : t[1];
+		out[i] = p > t[2] ? p : t[2];
+	}
+	return 1;
+}
+
 rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *colormap, char *err, size_t errlen)
 {
 	const unsigned char *base = (const unsigned char *)data;
