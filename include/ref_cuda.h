@@ -138,6 +138,11 @@ int  RC_LoadWorld (const char *name);
 /* the r_loadlits cvar (r_main.c:130, Mod_LoadLighting r_model.c:528-566): brush models loaded afterwards take their
  * light samples from "<map>.lit" (QLIT version 1, max of r, g, b) when that file exists */
 void RC_SetLoadLits (int on);
+/* the step before the path: the contents of the world leaf holding a point (Mod_PointInLeaf,
+ * r_model.c:83) and the refdef_t.flags the client derives from it (RDF_UNDERWATER when contents <= CONTENTS_WATER,
+ * cl_view.c:786-791) */
+int  RC_PointContents (const float *org);
+int  RC_ViewFlagsForOrigin (const float *org);
 
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)

@@ -476,6 +476,16 @@ int orc_end_frame (unsigned char *pal_out)
 	return 1;
 }
 
+/* Mod_PointInLeaf (r_model.c:83-105) of the loaded world: the leaf's contents */
+int orc_point_contents (const float *org)
+{
+	extern model_t *r_worldmodel;
+	vec3_t p;
+	if (!r_worldmodel) return 0;
+	p[0] = org[0]; p[1] = org[1]; p[2] = org[2];
+	return Mod_PointInLeaf (p, r_worldmodel)->contents;
+}
+
 void orc_clear_buffers (int fbval, int zval)
 {
 	size_t i, px = (size_t)vid.width * vid.height;

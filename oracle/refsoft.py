@@ -126,6 +126,10 @@ class RefSoft:
             raise RuntimeError("orc_draw2d: " + self.err())
         return fb
 
+    def point_contents(self, org) -> int:
+        a = (C.c_float * 3)(*org)
+        return self.lib.orc_point_contents(a)
+
     def end_frame(self):
         """R_EndFrame after render() of the same view: the palette R_UpdatePalette uploaded (768 bytes), or None
         when the reference skipped the upload (no colour shifts and gamma unchanged)."""

@@ -208,6 +208,14 @@ class RefCuda:
         assert fb.flags["C_CONTIGUOUS"] and fb.dtype == np.uint8
         return self.lib.RC_DrawOverlay(cmds, first, len(overlays), fb.ctypes.data)
 
+    def point_contents(self, org) -> int:
+        a = (C.c_float * 3)(*org)
+        return self.lib.RC_PointContents(a)
+
+    def view_flags_for_origin(self, org) -> int:
+        a = (C.c_float * 3)(*org)
+        return self.lib.RC_ViewFlagsForOrigin(a)
+
     def set_gamma(self, gamma: float):
         self.lib.RC_SetGamma(gamma)
 

@@ -709,6 +709,20 @@ static void rc_build_gamma (void)
 
 void RC_SetLoadLits (int on) { rc.loadlits = on; }
 
+/* What the client asks before it builds a refdef_t (cl_view.c:786-791,865-870: contents <= CONTENTS_WATER sets
+ * RDF_UNDERWATER): the contents of the world leaf that holds the point, Mod_PointInLeaf (r_model.c:83-105) ->contents.
+ * Returns the CONTENTS_* value (negative), or 0 without a world. */
+int RC_PointContents (const float *org)
+{
+	if (!rc.world || !rc.world->world || !org) return 0;
+	return rc.world->world->w.leafs[RC_PointInLeaf (rc.world->world, org)].contents;
+}
+
+int RC_ViewFlagsForOrigin (const float *org)
+{
+	return RC_PointContents (org) <= -3 /* CONTENTS_WATER, bspfile.h */ ? RDF_UNDERWATER : 0;
+}
+
 void RC_SetGamma (float gamma)
 {
 	rc.gamma = gamma; rc.gamma_valid = 1;
