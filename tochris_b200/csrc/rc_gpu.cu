@@ -92,6 +92,8 @@ struct rc_gpu_s {
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
+	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
+	cudaGraphExec_t graph_exec; rc_world_t graph_w; rc_frame_t graph_f; int use_graphs;
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
@@ -1478,6 +1480,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
 	g->mirrorgroups = 0;
+	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
 
@@ -1794,8 +1797,31 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.jobs = g->d_jobs; f.jobcap = g->jobcap;
 	f.fb = fb; f.zb = zb; f.status = g->d_status; f.warpbuf = g->d_warpbuf;
 
+	/* The plain device path (no entities, no warp views, no per-group consumers, no profiling) is a fixed sequence of
+	 * memsets and kernels on two streams whose parameters only change with the world or the buffers: it is captured
+	 * into a CUDA graph once and relaunched, which removes the launch gaps and the event round trips of the forks. */
+	const bool capturable = g->use_graphs && !timed && !g->host_fb && !g->groupfn && !anywarp &&
+		!(g->cur_batch && (g->cur_batch->nzres || g->cur_batch->nbents));
+	rc_frame_t f0;
+	memcpy (&f0, &f, sizeof(f));
+	struct capture_guard_t {
+		cudaStream_t s; bool on;
+		~capture_guard_t () { if (on) { cudaGraph_t gr = NULL; cudaStreamEndCapture (s, &gr); if (gr) cudaGraphDestroy (gr); } }
+	} capture = { s, false };
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
+	if (capturable)
+	{
+		if (g->graph_exec && !memcmp (&g->graph_w, &w, sizeof(w)) && !memcmp (&g->graph_f, &f0, sizeof(f0)))
+		{
+			CK (cudaGraphLaunch (g->graph_exec, s));
+			g->stats.kernel_launches += 8;
+			return RC_OK;
+		}
+		if (g->graph_exec) { cudaGraphExecDestroy (g->graph_exec); g->graph_exec = NULL; }
+		CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
+		capture.on = true;
+	}
 	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
 	CK (cudaMemsetAsync (g->d_alloc + 2, 0, 3 * sizeof(unsigned long long), s));	/* jobs, queued cells, full-cell count */
 
@@ -2008,6 +2034,17 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
 	g->stats.kernel_launches += 8;
+	if (capture.on)
+	{
+		cudaGraph_t graph = NULL;
+		capture.on = false;
+		CK (cudaStreamEndCapture (s, &graph));
+		cudaError_t ge = cudaGraphInstantiate (&g->graph_exec, graph, 0);
+		cudaGraphDestroy (graph);
+		if (ge != cudaSuccess) { g->graph_exec = NULL; snprintf (err, errlen, "cudaGraphInstantiate: %s", cudaGetErrorString (ge)); return RC_ERR_CUDA; }
+		memcpy (&g->graph_w, &w, sizeof(w)); memcpy (&g->graph_f, &f0, sizeof(f0));
+		CK (cudaGraphLaunch (g->graph_exec, s));
+	}
 	CK (cudaGetLastError ());
 	return RC_OK;
 }
