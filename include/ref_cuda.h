@@ -200,7 +200,8 @@ int  RC_DrawOverlay (const rc_draw2d_t *cmds, const int *first, int n, uint8_t *
  * outstanding, so the device->host copy of one batch (PCIe: the longest single item) runs while the next
  * batch is rendered.  The refdef_t array and what it points to may be reused as soon as the call returns;
  * fb_out / z_out belong to the renderer until the matching RC_WaitViews.  A status with RC_STAT_SPAN_POOL or
- * RC_STAT_CACHE_POOL set means the batch must be rendered again with RC_RenderViews (which grows the pools). */
+ * RC_STAT_CACHE_POOL or RC_STAT_AET_OVERFLOW set means the batch must be rendered again with RC_RenderViews (which
+ * grows the pools / switches to the large scan kernel). */
 int  RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out);
 int  RC_WaitViews (int *status);
 

@@ -92,6 +92,7 @@ struct rc_gpu_s {
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
+	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
 	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
 	cudaGraphExec_t graph_exec; rc_world_t graph_w; rc_frame_t graph_f; int use_graphs;
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
@@ -391,10 +392,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
  *      reference's own algorithm (rc_span_walk).
  *   C  spans are published: one atomicAdd per line reserves span + checkpoint records, then the cell
  *      map the draw kernel indexes (binary search over the line's span starts). */
+#ifndef SCAN_WARPS
 #define SCAN_WARPS 8
+#endif
+#ifndef SCAN_CAND
 #define SCAN_CAND  768
+#endif
 #define SCAN_LEADS 64
-#define SCAN_SPANS (RC_AET_MAX + 2)
 
 struct rc_aet_sorted {
 	const int *su; const uint32_t *ss;
@@ -403,27 +407,34 @@ struct rc_aet_sorted {
 	__device__ __forceinline__ int u (int k) const { return su[k]; }
 };
 
+/* AET: active edges a scanline may hold, CAND: edges that may touch the CTA's lines.  Shared memory per CTA bounds the
+ * occupancy of this kernel, so the sizes are template parameters: the host starts with the small instance and moves to
+ * the large one for good when a scene overflows it (RC_STAT_AET_OVERFLOW, rc_gpu_render). */
+template <int AET>
 struct scan_warp_t {			/* per-warp shared memory */
+	static constexpr int SPANS = AET + 2;
 	union {
-		struct { unsigned long long ku[RC_AET_MAX]; uint16_t kidx[RC_AET_MAX]; } k;	/* B1/B2: unsorted keys: u (biased) << 32 | step code */
-		struct { int16_t x0[SCAN_SPANS], x1[SCAN_SPANS]; uint16_t sf[SCAN_SPANS]; } sp;	/* B3/C: change points, spans */
+		struct { unsigned long long ku[AET]; uint16_t kidx[AET]; } k;	/* B1/B2: unsorted keys: u (biased) << 32 | step code */
+		struct { int16_t x0[SPANS], x1[SPANS]; uint16_t sf[SPANS]; } sp;	/* B3/C: change points, spans */
 	} a;
-	int      su[SCAN_SPANS];		/* sorted: u (12.20); at publish time: first segment of every span */
-	uint32_t ss[RC_AET_MAX];		/* sorted: surfs[0] | surfs[1] << 16 */
+	int      su[SPANS];		/* sorted: u (12.20); at publish time: first segment of every span */
+	uint32_t ss[AET];		/* sorted: surfs[0] | surfs[1] << 16 */
 	int      lkey[SCAN_LEADS], tcount[SCAN_LEADS];
 	uint16_t lsurf[SCAN_LEADS], rsurf[SCAN_LEADS];
 	uint8_t  lk[SCAN_LEADS], lrank[SCAN_LEADS];
-	uint8_t  lidx[RC_AET_MAX];
+	uint8_t  lidx[AET];
 };
 
+template <int AET, int CAND>
 struct scan_cta_t {
-	int      c_u[SCAN_CAND], c_step[SCAN_CAND];
-	uint32_t c_vv[SCAN_CAND], c_sf[SCAN_CAND], c_rank[SCAN_CAND];
+	int      c_u[CAND], c_step[CAND];
+	uint32_t c_vv[CAND], c_sf[CAND], c_rank[CAND];
 	int      ncand;
-	scan_warp_t warp[SCAN_WARPS];
+	scan_warp_t<AET> warp[SCAN_WARPS];
 };
 
-__device__ __forceinline__ void scan_full_key (const scan_cta_t *sh, int c, int line, unsigned long long *hi, unsigned long long *lo)
+template <int AET, int CAND>
+__device__ __forceinline__ void scan_full_key (const scan_cta_t<AET, CAND> *sh, int c, int line, unsigned long long *hi, unsigned long long *lo)
 {
 	rc_edge_t ed;
 	rc_aet_t a;
@@ -435,10 +446,12 @@ __device__ __forceinline__ void scan_full_key (const scan_cta_t *sh, int c, int 
 	*hi = a.hi; *lo = a.lo;
 }
 
+template <int AET, int CAND>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	extern __shared__ __align__(16) unsigned char scan_smem[];
-	scan_cta_t *sh = reinterpret_cast<scan_cta_t *>(scan_smem);
+	constexpr int SPANS = AET + 2;
+	scan_cta_t<AET, CAND> *sh = reinterpret_cast<scan_cta_t<AET, CAND> *>(scan_smem);
 	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	const int vi = blockIdx.x;
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			if (v <= lhi && v2 >= line0)
 			{
 				const int slot = atomicAdd (&sh->ncand, 1);
-				if (slot < SCAN_CAND)
+				if (slot < CAND)
 				{
 					sh->c_u[slot] = q.x; sh->c_step[slot] = q.y; sh->c_vv[slot] = (uint32_t)q.z; sh->c_sf[slot] = (uint32_t)q.w;
 					sh->c_rank[slot] = __ldg (&edges[e].rank);
@@ -474,10 +487,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	}
 	__syncthreads ();
 	int ncand = sh->ncand;
-	if (ncand > SCAN_CAND)
+	if (ncand > CAND)
 	{
 		if (threadIdx.x == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
-		ncand = SCAN_CAND;
+		ncand = CAND;
 	}
 	if (line >= f.height)
 		return;
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			cells[c] = make_int2 (-1, 0);
 		return;
 	}
-	scan_warp_t *sw = &sh->warp[wid];
+	scan_warp_t<AET> *sw = &sh->warp[wid];
 
 	/* ---- B1: active edges of this line ---- */
 	int n = 0;
@@ -518,16 +531,16 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		}
 		const unsigned m = __ballot_sync (0xFFFFFFFFu, act);
 		const int pos = n + __popc (m & lt);
-		if (act && pos < RC_AET_MAX)
+		if (act && pos < AET)
 		{
 			sw->a.k.ku[pos] = key; sw->a.k.kidx[pos] = (uint16_t)c;
 		}
 		n += __popc (m);
 	}
-	if (n > RC_AET_MAX)
+	if (n > AET)
 	{
 		if (lane == 0) atomicOr (f.status, RC_STAT_AET_OVERFLOW);
-		n = RC_AET_MAX;
+		n = AET;
 	}
 	__syncwarp ();
 
@@ -692,7 +705,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		if (lane == 0)
 		{
 			rc_aet_sorted acc; acc.su = sw->su; acc.ss = sw->ss;
-			rc_linespans_t ls; ls.surf = sw->a.sp.sf; ls.u0 = sw->a.sp.x0; ls.u1 = sw->a.sp.x1; ls.cap = SCAN_SPANS;
+			rc_linespans_t ls; ls.surf = sw->a.sp.sf; ls.u0 = sw->a.sp.x0; ls.u1 = sw->a.sp.x1; ls.cap = SPANS;
 			nsp = rc_span_walk (&f, vw, surfs, line, acc, n, &ls);
 		}
 		nsp = __shfl_sync (0xFFFFFFFFu, nsp, 0);
@@ -701,7 +714,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 
 	/* ---- C: publish ---- */
 	int nseg = 0;
-	if (nsp <= SCAN_SPANS)
+	if (nsp <= SPANS)
 		for (int j = lane; j < nsp; j += 32)
 			nseg += rc_span_seg_count (sw->a.sp.x1[j] - sw->a.sp.x0[j]);
 	#pragma unroll
@@ -713,7 +726,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	old = __shfl_sync (0xFFFFFFFFu, old, 0);
 	const int spanbase = (int)(old & 0xFFFFFFFFu);
 	int segbase = (int)(old >> 32);
-	if (nsp > SCAN_SPANS || spanbase + nsp > f.spancap || segbase + nseg > f.segcap)
+	if (nsp > SPANS || spanbase + nsp > f.spancap || segbase + nseg > f.segcap)
 	{
 		if (lane == 0) atomicOr (f.status, RC_STAT_SPAN_POOL);
 		for (int c = lane; c < cw; c += 32)
@@ -1467,7 +1480,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
 	g->d_particles = NULL; g->particlecap = 0; g->d_sprites = NULL; g->spritecap = 0; g->d_spritepixels = NULL; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
-	cudaFuncSetAttribute (k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t));
+	cudaFuncSetAttribute (k_scan<128, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<128, 384>));
+	cudaFuncSetAttribute (k_scan<256, SCAN_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<256, SCAN_CAND>));
 	cudaFuncSetAttribute (k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties (&prop, device);
@@ -1480,6 +1494,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
 	g->mirrorgroups = 0;
+	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
 	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
 	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
@@ -1858,7 +1873,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	}
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
-	k_scan<<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t), s>>> (w, f);
+	if (g->scan_large) k_scan<256, SCAN_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<256, SCAN_CAND>), s>>> (w, f);
+	else k_scan<128, 384><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<128, 384>), s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
@@ -2213,6 +2229,15 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		}
 #endif
 
+		if ((st & RC_STAT_AET_OVERFLOW) && !g->scan_large && !g->amode)
+		{
+			/* more active edges on a scanline (or candidates in an 8-line band) than the small instance of the scan
+			 * kernel holds: the large one from now on, and this batch again */
+			g->scan_large = 1;
+			if (g->graph_exec) { cudaGraphExecDestroy (g->graph_exec); g->graph_exec = NULL; }
+			memset (&g->stats, 0, sizeof(g->stats));
+			continue;
+		}
 		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL)))
 			break;
 		if (st & RC_STAT_SPAN_POOL)

@@ -57,7 +57,9 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_FACEPOS_MARKED  0xFFFEu   /* marked (surf->visframe == r_framecount), not rendered */
 #define RC_MAX_FACE_EDGES  30        /* per face; slot 31 is the synthetic left-clip edge */
 #define RC_WALK_STACK      512
+#ifndef RC_AET_MAX
 #define RC_AET_MAX         256       /* active edges per scanline the scan kernel holds (shared memory) */
+#endif
 #define RC_STACK_MAX       96        /* active surface stack depth held by the scan thread */
 #define RC_CACHE_EMPTY     0xFFFFFFFFFFFFFFFFull
 #define RC_WARP_W          320       /* WARP_WIDTH / WARP_HEIGHT, d_iface.h:22-23 */
