@@ -120,7 +120,12 @@ struct rc_gpu_s {
  *   phase 3  rc_render_face per listed face: clip, project, edges, surf_t
  *   phase 4  fix-up of faces that read r_rightenter/r_rightexit left by an earlier face:
  *            the search for the latest earlier writer is done by the whole warp */
+#ifndef FRONT_THREADS
 #define FRONT_THREADS 512
+#endif
+#ifndef FRONT_CTAS_PER_SM
+#define FRONT_CTAS_PER_SM 1
+#endif
 #define FRONT_WARPS (FRONT_THREADS / 32)
 #define FRONT_EDGE_SLOTS 1024
 #define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
@@ -399,6 +404,10 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 #define SCAN_CAND  768
 #endif
 #define SCAN_LEADS 64
+#ifndef SCAN_SMALL_AET
+#define SCAN_SMALL_AET 128
+#define SCAN_SMALL_CAND 384
+#endif
 
 struct rc_aet_sorted {
 	const int *su; const uint32_t *ss;
@@ -1480,7 +1489,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
 	g->d_particles = NULL; g->particlecap = 0; g->d_sprites = NULL; g->spritecap = 0; g->d_spritepixels = NULL; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
-	cudaFuncSetAttribute (k_scan<128, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<128, 384>));
+	cudaFuncSetAttribute (k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>));
 	cudaFuncSetAttribute (k_scan<256, SCAN_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<256, SCAN_CAND>));
 	cudaFuncSetAttribute (k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaDeviceProp prop;
@@ -1843,7 +1852,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	{
 		/* cluster size: as many CTAs per view as fit the machine in one wave, at most 8 */
 		int csize = 1;
-		while (csize < 8 && n * csize * 2 <= g->numsms) csize *= 2;	/* one wave, one CTA per SM */
+		while (csize < 8 && n * csize * 2 <= g->numsms * FRONT_CTAS_PER_SM) csize *= 2;	/* one wave */
 		cudaLaunchConfig_t cfg;
 		cudaLaunchAttribute attr[1];
 		memset (&cfg, 0, sizeof(cfg));
@@ -1874,7 +1883,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
 	if (g->scan_large) k_scan<256, SCAN_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<256, SCAN_CAND>), s>>> (w, f);
-	else k_scan<128, 384><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<128, 384>), s>>> (w, f);
+	else k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>), s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
 	k_surfprep<<<gp, 64, 0, s>>> (w, f);
