@@ -339,11 +339,20 @@ def run_ours(args):
                 r.present_device(rds, n, fb.data_ptr(), rgbx.data_ptr(), pstream.cuda_stream)
                 if k >= 3:
                     pevs[k - 3][1].record(pstream)
+            torch.cuda.synchronize()
+            kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):       # the kernel alone: palettes of the previous call, nothing uploaded
+                l2flush.zero_()
+                kevs[k][0].record(pstream)
+                r.present_device(None, n, fb.data_ptr(), rgbx.data_ptr(), pstream.cuda_stream)
+                kevs[k][1].record(pstream)
         torch.cuda.synchronize()
         pms = sum(a.elapsed_time(b) for a, b in pevs) / args.steps
-        present = {"kernel": "k_present (palette expansion, R_EndFrame for batches)", "ms_per_step": round(pms, 4),
-                   "alg_bytes_per_launch": int(5 * px), "achieved_gbs": round(5 * px / (pms * 1e-3) / 1e9, 1),
-                   "note": "includes the 64 KB palette upload issued by the same call"}
+        kms = sum(a.elapsed_time(b) for a, b in kevs) / args.steps
+        present = {"kernel": "k_present (palette expansion, R_EndFrame for batches)", "ms_per_step": round(kms, 4),
+                   "alg_bytes_per_launch": int(5 * px), "achieved_gbs": round(5 * px / (kms * 1e-3) / 1e9, 1),
+                   "call_ms_with_palette_upload": round(pms, 4),
+                   "note": "1 B read + 4 B written per pixel; kernel alone (palettes already on the device), and the whole call with its 64 KB palette upload"}
     # ---- per-kernel times (profiling mode puts events between the kernels) ----
     r.set_profiling(True)
     prof = {}

@@ -165,7 +165,8 @@ int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_d
  *                          this is the base palette through the gamma table)
  *   RC_PresentViewsDevice  frame buffers of n views (device, as RC_RenderViewsDevice left them) -> 32-bit
  *                          pixels R | G << 8 | B << 16 | 255 << 24 (d_8to24table's layout, ref_gl/gl_vidnt.c),
- *                          each view through its own palette, on `stream`
+ *                          each view through its own palette, on `stream`; views == NULL: the palettes of
+ *                          the previous call again (nothing is uploaded)
  *   RC_PresentViews        the same from / to host memory (test and tooling path) */
 void RC_SetGamma (float gamma);
 int  RC_ViewPalette (const refdef_t *view, unsigned char *pal768_out);

@@ -316,6 +316,7 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, void *rgbx, void *stream, int host, char *err, size_t errlen)
 {
 	/* test infrastructure: the simulator only has host memory */
+	if (!pal32) { snprintf (err, errlen, "the simulator keeps no palettes between calls"); return RC_ERR_ARG; }
 	const size_t px = (size_t)g->width * g->height;
 	const uint8_t *in = (const uint8_t *)fb; uint32_t *out = (uint32_t *)rgbx;
 	for (int v = 0; v < n; v++)

@@ -236,7 +236,7 @@ class RefCuda:
         return out
 
     def present_device(self, rds, n: int, fb_ptr: int, rgbx_ptr: int, stream: int = 0):
-        if self.lib.RC_PresentViewsDevice(rds, n, fb_ptr, rgbx_ptr, stream or None) != 0:
+        if self.lib.RC_PresentViewsDevice(rds, n, fb_ptr, rgbx_ptr, stream or None) != 0:      # rds None: previous palettes
             raise RuntimeError(f"RC_PresentViewsDevice failed: {self.err()}")
 
     def render_async(self, rds, n: int, fb, z=None) -> None:

@@ -773,7 +773,9 @@ int RC_PresentViewsDevice (const refdef_t *views, int n, const void *fb_dev, voi
 {
 	int r;
 	if (!rc.gpu) return rc_fail (RC_ERR_ARG, "RC_Init first");
-	if (!views || n <= 0 || !fb_dev || !rgbx_dev) return rc_fail (RC_ERR_ARG, "RC_PresentViewsDevice: bad argument");
+	if (n <= 0 || !fb_dev || !rgbx_dev) return rc_fail (RC_ERR_ARG, "RC_PresentViewsDevice: bad argument");
+	if (!views)		/* the palettes of the previous call again (same n): nothing is uploaded */
+		return rc_gpu_present (rc.gpu, NULL, n, fb_dev, rgbx_dev, stream, 0, rc.err, sizeof(rc.err));
 	if ((r = rc_view_palettes32 (views, n)) != RC_OK) return r;
 	return rc_gpu_present (rc.gpu, rc.palscratch, n, fb_dev, rgbx_dev, stream, 0, rc.err, sizeof(rc.err));
 }

@@ -82,6 +82,7 @@ struct rc_gpu_s {
 	/* host-output path */
 	uint8_t *d_fb; int16_t *d_zb; size_t outcap;
 	uint8_t *d_d2blob; void *d_d2pics; rc_draw2d_t *d_d2cmds; int *d_d2first; int d2cmdcap, d2firstcap;	/* 2D overlay */
+	int palvalid;
 	uint32_t *d_pal32; int palcap; uint32_t *h_pal32[2]; cudaEvent_t evpal[2]; int palslot;	/* pinned staging ring for the palettes */
 	uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
 	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
@@ -1479,6 +1480,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 		cudaEventCreateWithFlags (&g->adone_copy[i], cudaEventDisableTiming);
 	}
 	g->d_d2blob = NULL; g->d_d2pics = NULL; g->d_d2cmds = NULL; g->d_d2first = NULL; g->d2cmdcap = 0; g->d2firstcap = 0;
+	g->palvalid = 0;
 	g->d_pal32 = NULL; g->palcap = 0; g->h_pal32[0] = g->h_pal32[1] = NULL; g->palslot = 0;
 	cudaEventCreateWithFlags (&g->evpal[0], cudaEventDisableTiming); cudaEventCreateWithFlags (&g->evpal[1], cudaEventDisableTiming);
 	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
@@ -2346,7 +2348,7 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 		CK (cudaMalloc (&g->d_pal32, sizeof(uint32_t) * 256 * (size_t)(n + 64)));
 		CK (cudaHostAlloc (&g->h_pal32[0], sizeof(uint32_t) * 256 * (size_t)(n + 64), cudaHostAllocDefault));
 		CK (cudaHostAlloc (&g->h_pal32[1], sizeof(uint32_t) * 256 * (size_t)(n + 64), cudaHostAllocDefault));
-		g->palcap = n + 64;
+		g->palcap = n + 64; g->palvalid = 0;
 		cudaEventRecord (g->evpal[0], s); cudaEventRecord (g->evpal[1], s);
 	}
 	const uint8_t *fbd = (const uint8_t *)fb;
@@ -2365,8 +2367,14 @@ int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, v
 	}
 	/* palettes go through a pinned two-slot ring, so the upload is a true asynchronous copy (a pageable source costs the
 	 * stream tens of microseconds); a slot is reused only after the copy that read it has completed */
+	if (!pal32)
+	{
+		if (n > g->palvalid) { snprintf (err, errlen, "no palettes from a previous call for %d views", n); return RC_ERR_ARG; }
+	}
+	else
 	{
 		const int slot = g->palslot; g->palslot ^= 1;
+		g->palvalid = n;
 		CK (cudaEventSynchronize (g->evpal[slot]));
 		memcpy (g->h_pal32[slot], pal32, sizeof(uint32_t) * 256 * (size_t)n);
 		CK (cudaMemcpyAsync (g->d_pal32, g->h_pal32[slot], sizeof(uint32_t) * 256 * (size_t)n, cudaMemcpyHostToDevice, s));
