@@ -908,7 +908,10 @@ __global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world
  * records are 128 contiguous bytes, a warp's 4 KB: they are staged in shared memory (swizzled, conflict
  * free) and written out by the whole warp, 512 contiguous bytes per store instruction instead of 32
  * scattered 16-byte pieces. */
-__global__ void __launch_bounds__(128) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+#ifndef SEG_MINB
+#define SEG_MINB 8	/* 64 registers: 24.5 us instead of 30 (measured 1 / 6 / 8 / 10 CTAs per SM) */
+#endif
+__global__ void __launch_bounds__(128, SEG_MINB) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	__shared__ uint4 stage[128 * 8];
 	unsigned long long a = f.alloc[0];
