@@ -141,6 +141,9 @@ void RC_SetLoadLits (int on);
 /* the step before the path: the contents of the world leaf holding a point (Mod_PointInLeaf,
  * r_model.c:83) and the refdef_t.flags the client derives from it (RDF_UNDERWATER when contents <= CONTENTS_WATER,
  * cl_view.c:786-791) */
+/* the `timerefresh` console command (R_TimeRefresh_f, r_misc.c:29-64), the reference's own renderer benchmark: the
+ * 128-step yaw sweep of `base` as ONE batch; fb_out NULL keeps the frames on the device */
+int  RC_TimeRefresh (const refdef_t *base, uint8_t *fb_out, double *seconds, int *status);
 int  RC_PointContents (const float *org);
 int  RC_ViewFlagsForOrigin (const float *org);
 

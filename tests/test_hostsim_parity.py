@@ -113,3 +113,21 @@ def test_sub_rectangles_match_oracle(assets_dir, sim_lib, oracle_available):
     r = rcutil.render_rc(sim_lib, assets_dir, "maps/full.bsp", 320, 200, specs)
     assert r["status"] == 0
     check_rect_parity(o, r, specs)
+
+
+def test_timerefresh_matches_oracle_sweep(assets_dir, sim_lib, oracle_available):
+    """RC_TimeRefresh = R_TimeRefresh_f (r_misc.c:29-64): 128 yaw steps of one refdef, as one batch; BASELINE config C1."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import run_oracle
+    from tochris_b200.api import RefCuda
+    from tochris_b200.scenes import views
+    specs = views.timerefresh_views((0, 0, 0), 128)
+    o = run_oracle.render(assets_dir, "maps/box.bsp", 320, 200, specs)
+    r = RefCuda(assets_dir, 320, 200, libpath=sim_lib)
+    r.load_world("maps/box.bsp")
+    rds = views.build_refdefs(specs[:1], 320, 200, model_resolver=r.model)
+    fb, secs, st = r.timerefresh(rds[0])
+    assert st == 0 and secs > 0
+    assert np.array_equal(fb, o["fb"])
+    r.shutdown()

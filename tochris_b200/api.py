@@ -88,6 +88,7 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_TimeRefresh.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.RC_SetLoadLits.argtypes = [C.c_int]
         L.RC_SetLoadLits.restype = None
         L.RC_DrawPicFromWad.argtypes = [C.c_char_p]
@@ -207,6 +208,15 @@ class RefCuda:
         cmds, first = self.pack_overlays(overlays)
         assert fb.flags["C_CONTIGUOUS"] and fb.dtype == np.uint8
         return self.lib.RC_DrawOverlay(cmds, first, len(overlays), fb.ctypes.data)
+
+    def timerefresh(self, rd, want_frames: bool = True):
+        """RC_TimeRefresh: the reference's `timerefresh` sweep (128 yaw steps of `rd`) as one batch -> (frames or None, seconds, status)."""
+        fb = np.empty((128, self.height, self.width), dtype=np.uint8) if want_frames else None
+        secs, st = C.c_double(0), C.c_int(0)
+        rc = self.lib.RC_TimeRefresh(C.byref(rd), fb.ctypes.data if want_frames else None, C.byref(secs), C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"RC_TimeRefresh failed ({rc}): {self.err()}")
+        return fb, secs.value, st.value
 
     def point_contents(self, org) -> int:
         a = (C.c_float * 3)(*org)

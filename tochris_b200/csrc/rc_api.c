@@ -10,6 +10,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <math.h>
+#include <time.h>
 #include <dlfcn.h>
 #include "rc_host.h"
 #include "rc_draw2d.h"
@@ -708,6 +709,36 @@ static void rc_build_gamma (void)
 }
 
 void RC_SetLoadLits (int on) { rc.loadlits = on; }
+
+/* R_TimeRefresh_f (the `timerefresh` console command, ref_soft/r_misc.c:29-64): 128 views of the given refdef with
+ * viewangles[1] = i / 128 * 360 -- here one batch instead of 128 frames.  fb_out (may be NULL) receives the 128 frames;
+ * *seconds the wall time of the batch, host copies included when fb_out is given.  Returns RC_OK or RC_ERR_*. */
+int RC_TimeRefresh (const refdef_t *base, uint8_t *fb_out, double *seconds, int *status)
+{
+	static refdef_t rds[128];
+	struct timespec t0, t1;
+	int i, r;
+	if (!rc.inited || !base) return rc_fail (RC_ERR_ARG, "RC_TimeRefresh: bad argument");
+	for (i = 0; i < 128; i++)
+	{
+		rds[i] = *base;
+		rds[i].viewangles[1] = i / 128.0 * 360.0;
+	}
+	clock_gettime (CLOCK_MONOTONIC, &t0);
+	if (fb_out)
+		r = RC_RenderViews (rds, 128, fb_out, NULL, status);
+	else
+	{
+		size_t px = (size_t)rc.vid.width * rc.vid.height;
+		void *fb = NULL;
+		if (RC_DeviceAlloc (px * 128, &fb) != RC_OK) return rc_fail (RC_ERR_NOMEM, "RC_TimeRefresh: device memory");
+		r = RC_RenderViewsDevice (rds, 128, fb, NULL, NULL, status);
+		RC_DeviceFree (fb);
+	}
+	clock_gettime (CLOCK_MONOTONIC, &t1);
+	if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+	return r;
+}
 
 /* What the client asks before it builds a refdef_t (cl_view.c:786-791,865-870: contents <= CONTENTS_WATER sets
  * RDF_UNDERWATER): the contents of the world leaf that holds the point, Mod_PointInLeaf (r_model.c:83-105) ->contents.
