@@ -129,6 +129,7 @@ struct rc_gpu_s {
 #endif
 #define FRONT_WARPS (FRONT_THREADS / 32)
 #define FRONT_EDGE_SLOTS 1024
+#define FRONT_FIXLIST 1024
 #define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
 
 /* L2 prefetch of a slice of a read-only array: the front end chases pointers through the BSP
@@ -332,41 +333,55 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front (const __grid_constant_
 	TQ ();
 	if (gtid == 0) { f.nfaces[vi] = nfraw; f.nedges[vi] = ctr[1]; }
 	{
-		const int lane = tid & 31;
+		/* phase 4: the faces that need the fix-up are few and clustered in list order: every CTA compacts them into a
+		 * list and the warps of the whole cluster take them round robin (one warp-wide search per face) */
+		const int lane = tid & 31, wid = tid >> 5;
 		const rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
 		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
-		for (int p0 = (gtid >> 5) << 5; p0 < nf; p0 += gthreads)
-		{
-			const int p = p0 + lane;
-			const bool need = p < nf && (surfs[p + 2].miplevel & 4);
-			unsigned todo = __ballot_sync (0xFFFFFFFFu, need);
-			while (todo)
+		__shared__ int s_nfix, s_fix[FRONT_FIXLIST];
+		if (tid == 0) s_nfix = 0;
+		__syncthreads ();
+		for (int p = tid; p < nf; p += FRONT_THREADS)
+			if (surfs[p + 2].miplevel & 4)
 			{
-				const int src = __ffs (todo) - 1;
-				todo &= todo - 1;
-				const int pp = p0 + src;
-				const int mykey = list[pp].key;
-				long long bre = -1, brx = -1;		/* key << 32 | slot: keys are unique */
-				for (int q = lane; q < nf; q += 32)
-				{
-					const int k = list[q].key;
-					const int m = surfs[q + 2].miplevel;
-					if (k < mykey)
-					{
-						const long long kv = ((long long)k << 32) | (unsigned)q;
-						if ((m & 1) && kv > bre) bre = kv;
-						if ((m & 2) && kv > brx) brx = kv;
-					}
-				}
-				for (int o = 16; o; o >>= 1)
-				{
-					const long long a = __shfl_xor_sync (0xFFFFFFFFu, bre, o), b = __shfl_xor_sync (0xFFFFFFFFu, brx, o);
-					if (a > bre) bre = a;
-					if (b > brx) brx = b;
-				}
-				if (lane == src)
-					rc_face_fixup_finish (&w, &f, vi, pp, bre < 0 ? -1 : (int)(bre & 0xFFFFFFFF), brx < 0 ? -1 : (int)(brx & 0xFFFFFFFF));
+				const int k = atomicAdd (&s_nfix, 1);
+				if (k < FRONT_FIXLIST) s_fix[k] = p;
 			}
+		__syncthreads ();
+		const int nfix = s_nfix;
+		const bool listed = nfix <= FRONT_FIXLIST;		/* else: every warp walks its own 32 faces, as a list would */
+		const int nitems = listed ? nfix : ((nf + 31) & ~31);
+		for (int it = crank * FRONT_WARPS + wid; it < nitems; it += csize * FRONT_WARPS)
+		{
+			int pp;
+			if (listed)
+				pp = s_fix[it];
+			else
+			{
+				pp = it;
+				if (pp >= nf || !(surfs[pp + 2].miplevel & 4)) continue;
+			}
+			const int mykey = list[pp].key;
+			long long bre = -1, brx = -1;		/* key << 32 | slot: keys are unique */
+			for (int q = lane; q < nf; q += 32)
+			{
+				const int k = list[q].key;
+				const int m = surfs[q + 2].miplevel;
+				if (k < mykey)
+				{
+					const long long kv = ((long long)k << 32) | (unsigned)q;
+					if ((m & 1) && kv > bre) bre = kv;
+					if ((m & 2) && kv > brx) brx = kv;
+				}
+			}
+			for (int o = 16; o; o >>= 1)
+			{
+				const long long a = __shfl_xor_sync (0xFFFFFFFFu, bre, o), b = __shfl_xor_sync (0xFFFFFFFFu, brx, o);
+				if (a > bre) bre = a;
+				if (b > brx) brx = b;
+			}
+			if (lane == 0)
+				rc_face_fixup_finish (&w, &f, vi, pp, bre < 0 ? -1 : (int)(bre & 0xFFFFFFFF), brx < 0 ? -1 : (int)(brx & 0xFFFFFFFF));
 		}
 	}
 	cluster.sync ();		/* rank 0's shared memory must outlive the other ranks' reads */
