@@ -128,6 +128,9 @@ struct rc_gpu_s {
 #define FRONT_CTAS_PER_SM 1
 #endif
 #define FRONT_WARPS (FRONT_THREADS / 32)
+#ifndef FRONT_MANY
+#define FRONT_MANY 256
+#endif
 #define FRONT_EDGE_SLOTS 1024
 #define FRONT_FIXLIST 1024
 #define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
@@ -1516,7 +1519,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaFuncSetAttribute (k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>));
 	cudaFuncSetAttribute (k_scan<256, SCAN_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<256, SCAN_CAND>));
 	cudaFuncSetAttribute (k_front<FRONT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-	cudaFuncSetAttribute (k_front<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	cudaFuncSetAttribute (k_front<FRONT_MANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties (&prop, device);
 	g->numsms = prop.multiProcessorCount;
@@ -1882,11 +1885,11 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaLaunchAttribute attr[1];
 		memset (&cfg, 0, sizeof(cfg));
 		const bool manyviews = n > g->numsms && !getenv ("RC_FRONT_512");	/* more views than SMs: several waves */
-		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? 256 : FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
+		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? FRONT_MANY : FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
-		if (manyviews) CK (cudaLaunchKernelEx (&cfg, k_front<256>, w, f));
+		if (manyviews) CK (cudaLaunchKernelEx (&cfg, k_front<FRONT_MANY>, w, f));
 		else CK (cudaLaunchKernelEx (&cfg, k_front<FRONT_THREADS>, w, f));
 	}
 	if (timed) cudaEventRecord (g->ev[1], s);
