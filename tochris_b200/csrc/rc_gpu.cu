@@ -93,6 +93,7 @@ struct rc_gpu_s {
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
+	int slow_in_ends;
 	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
 	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
 	cudaGraphExec_t graph_exec; rc_world_t graph_w; rc_frame_t graph_f; int use_graphs;
@@ -1531,6 +1532,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
 	g->mirrorgroups = 0;
+	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
 	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
@@ -2003,14 +2005,23 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		{
 			/* mixed cells on the second stream, beside the full cells (disjoint pixels; both only read the
 			 * span / subdivision records and the cache) */
+			/* the cells k_draw leaves to the general code are queued for k_slowcells; letting k_ends find them itself
+			 * (slowmode 1, as grouped drawing does to save launches) measured slower here */
+			f.slowmode = g->slow_in_ends;
 			cudaEventRecord (g->evfork, s);
 			cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
 			if (anywarp) k_ends<true><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
 			else k_ends<false><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
 			cudaEventRecord (g->evjoin, g->sidestream);
-			if (anywarp) { k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<true><<<g->numsms * 8, 128, 0, s>>> (w, f); }
-			else { k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f); k_slowcells<false><<<g->numsms * 8, 128, 0, s>>> (w, f); }
+			if (anywarp) k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f);
+			else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
+			if (!f.slowmode)
+			{
+				if (anywarp) k_slowcells<true><<<g->numsms * 8, 128, 0, s>>> (w, f);
+				else k_slowcells<false><<<g->numsms * 8, 128, 0, s>>> (w, f);
+			}
 			cudaStreamWaitEvent (s, g->evjoin, 0);
+			f.slowmode = 0;
 		}
 	}
 	if (g->cur_batch && g->cur_batch->nzres)
