@@ -70,7 +70,25 @@ def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want
     p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette, overlays))
     p.start()
     try:
-        kind, payload = q.get(timeout=timeout)
+        # a worker that dies (a crash inside the C library) never answers: notice it instead of waiting out the timeout
+        import queue as _queue
+        import time as _time
+        deadline = _time.monotonic() + timeout
+        while True:
+            try:
+                kind, payload = q.get(timeout=1.0)
+                break
+            except _queue.Empty:
+                if not p.is_alive():
+                    try:
+                        kind, payload = q.get(timeout=1.0)
+                        break
+                    except _queue.Empty:
+                        kind, payload = "err", f"worker process died (exit code {p.exitcode})"
+                        break
+                if _time.monotonic() > deadline:
+                    kind, payload = "err", f"no answer within {timeout} s"
+                    break
     finally:
         p.join(timeout=30)
         if p.is_alive():

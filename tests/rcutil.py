@@ -199,7 +199,25 @@ def render_rc(libpath, basedir, mapname, width, height, specs, cvars=None, want_
     p = ctx.Process(target=_rc_worker, args=(q, libpath, basedir, mapname, width, height, specs, cvars, want_debug))
     p.start()
     try:
-        kind, payload = q.get(timeout=timeout)
+        # a worker that dies (a crash inside the C library) never answers: notice it instead of waiting out the timeout
+        import queue as _queue
+        import time as _time
+        deadline = _time.monotonic() + timeout
+        while True:
+            try:
+                kind, payload = q.get(timeout=1.0)
+                break
+            except _queue.Empty:
+                if not p.is_alive():
+                    try:
+                        kind, payload = q.get(timeout=1.0)
+                        break
+                    except _queue.Empty:
+                        kind, payload = "err", f"worker process died (exit code {p.exitcode})"
+                        break
+                if _time.monotonic() > deadline:
+                    kind, payload = "err", f"no answer within {timeout} s"
+                    break
     finally:
         p.join(timeout=30)
         if p.is_alive():

@@ -176,3 +176,26 @@ def test_sub_rectangles_match_oracle_gpu(assets_dir, oracle_available):
     o = run_oracle.render(assets_dir, "maps/multi.bsp", 324, 202, specs)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, "maps/multi.bsp", 324, 202, specs)
     rcutil.assert_parity(o, r, specs, 324, 202)
+
+
+FUZZ = [
+    # scene, w, h, views, seed time, step -- shapes that stress the draw stage's cell logic: widths that are 8 but not
+    # 16 aligned, odd heights, very narrow and very wide frames, many short spans (full scene from far away)
+    ("full", 336, 243, 96, 0.11, 0.37),
+    ("full", 200, 151, 128, 3.3, 0.29),
+    ("multi", 1016, 571, 24, 0.7, 0.41),
+    ("full", 72, 48, 256, 1.9, 0.13),
+    ("multi", 1912, 300, 8, 2.2, 0.5),
+    ("full", 644, 483, 24, 0.05, 0.77),          # 644 = 4 mod 8: every cell through the general code
+]
+
+
+@pytest.mark.parametrize("scene,w,h,n,t0,dt", FUZZ)
+def test_fuzz_shapes_match_oracle(assets_dir, oracle_available, scene, w, h, n, t0, dt):
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import run_oracle
+    specs = rcutil.scene_views(scene, n, time=t0, time_step=dt)
+    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
+    rcutil.assert_parity(o, r, specs, w, h)
