@@ -95,6 +95,7 @@ int   Mod_Flags (struct model_s *model);                       /* render.h:34 */
 void  R_BeginFrame (void);                                     /* render.h:36  r_main.c:951 */
 void  R_EndFrame (void);                                       /* render.h:37  r_main.c:961 */
 void  R_NewMap (struct model_s *worldmodel);                   /* render.h:39  r_main.c:258 */
+void  R_ScreenShot_f (void);                                   /* render.h:30  r_misc.c:117: <basedir>/id1/quakeNN.pcx of vid.buffer */
 void  R_TranslatePlayerSkin (int playernum, struct model_s *model, int skinnum, int top, int bottom); /* render.h:40 (empty in ref_soft, r_misc.c:372) */
 /* 2D (render.h:42-53, ref_soft/r_draw.c): recorded per frame, applied to vid.buffer by R_EndFrame; mpic_t as r_shared.h:78-85 */
 struct mpic_s;
@@ -171,6 +172,8 @@ int  RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_d
  *                          each view through its own palette, on `stream`; views == NULL: the palettes of
  *                          the previous call again (nothing is uploaded)
  *   RC_PresentViews        the same from / to host memory (test and tooling path) */
+/* WritePCXfile (ref_soft/pcx.c:103): the screenshot format; palette NULL = the base palette */
+int  RC_WritePCX (const char *path, const uint8_t *data, int width, int height, int rowbytes, const uint8_t *palette768);
 void RC_SetGamma (float gamma);
 int  RC_ViewPalette (const refdef_t *view, unsigned char *pal768_out);
 int  RC_PresentViewsDevice (const refdef_t *views, int n, const void *fb_dev, void *rgbx_dev, void *stream);

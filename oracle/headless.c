@@ -476,6 +476,17 @@ int orc_end_frame (unsigned char *pal_out)
 	return 1;
 }
 
+/* the `screenshot` command (R_ScreenShot_f, r_misc.c:117-149) on vid.buffer as the last orc_render left it */
+int orc_screenshot (void)
+{
+	extern void R_ScreenShot_f (void);
+	orc_abort_armed = 1;
+	if (setjmp (orc_abort)) { orc_abort_armed = 0; return -1; }
+	R_ScreenShot_f ();
+	orc_abort_armed = 0;
+	return 0;
+}
+
 /* Mod_PointInLeaf (r_model.c:83-105) of the loaded world: the leaf's contents */
 int orc_point_contents (const float *org)
 {

@@ -126,6 +126,10 @@ class RefSoft:
             raise RuntimeError("orc_draw2d: " + self.err())
         return fb
 
+    def screenshot(self):
+        if self.lib.orc_screenshot() != 0:
+            raise RuntimeError("orc_screenshot: " + self.err())
+
     def point_contents(self, org) -> int:
         a = (C.c_float * 3)(*org)
         return self.lib.orc_point_contents(a)

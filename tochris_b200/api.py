@@ -88,6 +88,11 @@ class RefCuda:
         L = self.lib
         L.RC_LastError.restype = C.c_char_p
         L.RC_RenderViews.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_SetVidBuffers.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.RC_SetVidBuffers.restype = None
+        L.R_RenderView.argtypes = [C.POINTER(refdef_t)]
+        L.R_RenderView.restype = None
+        L.R_ScreenShot_f.restype = None
         L.RC_TimeRefresh.argtypes = [C.POINTER(refdef_t), C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.RC_SetLoadLits.argtypes = [C.c_int]
         L.RC_SetLoadLits.restype = None

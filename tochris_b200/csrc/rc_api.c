@@ -1157,6 +1157,62 @@ void R_RenderView (refdef_t *refdef)
 	free (fb); free (zb);
 }
 
+/* WritePCXfile, ref_soft/pcx.c:103-160: 128-byte header, every byte with its two top bits set escaped by 0xc1 (no run
+ * lengths), 0x0c and the 768-byte palette.  File output of a finished frame: host code. */
+int RC_WritePCX (const char *path, const uint8_t *data, int width, int height, int rowbytes, const uint8_t *palette)
+{
+	uint8_t *buf, *pack;
+	FILE *fp;
+	int i, j;
+	if (!path || !data || width <= 0 || height <= 0) return rc_fail (RC_ERR_ARG, "RC_WritePCX: bad argument");
+	buf = (uint8_t *)calloc (1, (size_t)width * height * 2 + 1000);
+	if (!buf) return rc_fail (RC_ERR_NOMEM, "SCR_ScreenShot_f: not enough memory");
+	buf[0] = 0x0a; buf[1] = 5; buf[2] = 1; buf[3] = 8;			/* manufacturer, version, encoding, bits_per_pixel */
+	buf[8] = (uint8_t)((width - 1) & 255); buf[9] = (uint8_t)(((width - 1) >> 8) & 255);		/* xmax */
+	buf[10] = (uint8_t)((height - 1) & 255); buf[11] = (uint8_t)(((height - 1) >> 8) & 255);	/* ymax */
+	buf[12] = (uint8_t)(width & 255); buf[13] = (uint8_t)((width >> 8) & 255);			/* hres */
+	buf[14] = (uint8_t)(height & 255); buf[15] = (uint8_t)((height >> 8) & 255);			/* vres */
+	buf[65] = 1;								/* color_planes (palette[48] at 16, reserved at 64) */
+	buf[66] = (uint8_t)(width & 255); buf[67] = (uint8_t)((width >> 8) & 255);			/* bytes_per_line */
+	buf[68] = 2;								/* palette_type */
+	pack = buf + 128;
+	for (i = 0; i < height; i++, data += rowbytes)
+		for (j = 0; j < width; j++)
+		{
+			if ((data[j] & 0xc0) == 0xc0)
+				*pack++ = 0xc1;
+			*pack++ = data[j];
+		}
+	*pack++ = 0x0c;
+	memcpy (pack, palette ? palette : rc.palette, 768);
+	pack += 768;
+	fp = fopen (path, "wb");
+	if (!fp) { free (buf); return rc_fail (RC_ERR_FILE, "COM_WriteFile: couldn't open %s", path); }
+	fwrite (buf, 1, (size_t)(pack - buf), fp);
+	fclose (fp);
+	free (buf);
+	return RC_OK;
+}
+
+/* R_ScreenShot_f, ref_soft/r_misc.c:117-149: the first free <gamedir>/quakeNN.pcx, vid.buffer with the base palette */
+void R_ScreenShot_f (void)
+{
+	char name[700];
+	int i;
+	FILE *fp;
+	if (!rc.vidbuffer) { rc_fail (RC_ERR_ARG, "RC_SetVidBuffers first"); return; }
+	for (i = 0; i <= 99; i++)
+	{
+		snprintf (name, sizeof(name), "%s/id1/quake%d%d.pcx", rc.basedir, i / 10, i % 10);
+		if ((fp = fopen (name, "rb")) == NULL)
+			break;
+		fclose (fp);
+	}
+	if (i == 100) { fprintf (stderr, "SCR_ScreenShot_f: Couldn't create a PCX file\n"); return; }
+	if (RC_WritePCX (name, rc.vidbuffer, rc.vid.width, rc.vid.height, rc.vidrowbytes, rc.palette) != RC_OK)
+		fprintf (stderr, "ref_cuda: %s\n", rc.err);
+}
+
 static struct model_s *rc_register_model (char *name) { return Mod_ForName (name, 0); }
 
 refexport_t GetRefAPI (int api_version)
