@@ -203,12 +203,13 @@ int  RC_DrawOverlay (const rc_draw2d_t *cmds, const int *first, int n, uint8_t *
 
 /* Pipelined form of RC_RenderViews for streams of batches (timedemo-style replay, RL roll-outs): the call
  * enqueues the batch and returns; RC_WaitViews blocks until the OLDEST outstanding call has delivered its
- * frame buffers (page-locked host memory recommended) and returns its status.  At most two calls may be
- * outstanding, so the device->host copy of one batch (PCIe: the longest single item) runs while the next
- * batch is rendered.  The refdef_t array and what it points to may be reused as soon as the call returns;
+ * frame buffers (page-locked host memory recommended) and returns its status.  At most RC_ASYNC_CALLS (three) calls may
+ * be outstanding: the device->host copy of one batch (PCIe: the longest single item) runs while the next batch is
+ * rendered and a third waits behind it, so the copy engine never idles between batches.  The refdef_t array and what it points to may be reused as soon as the call returns;
  * fb_out / z_out belong to the renderer until the matching RC_WaitViews.  A status with RC_STAT_SPAN_POOL or
  * RC_STAT_CACHE_POOL or RC_STAT_AET_OVERFLOW set means the batch must be rendered again with RC_RenderViews (which
  * grows the pools / switches to the large scan kernel). */
+#define RC_ASYNC_CALLS 3
 int  RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_out);
 int  RC_WaitViews (int *status);
 

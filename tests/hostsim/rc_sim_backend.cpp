@@ -296,20 +296,20 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 }
 
 /* the simulator has nothing to overlap: the "asynchronous" call renders at once and the wait hands back its status */
-static int sim_async_status[2], sim_async_head, sim_async_n;
+static int sim_async_status[RC_ASYNC_DEPTH], sim_async_head, sim_async_n;
 int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen)
 {
-	if (sim_async_n >= 2) { snprintf (err, errlen, "two asynchronous calls already in flight: RC_WaitViews first"); return RC_ERR_ARG; }
+	if (sim_async_n >= RC_ASYNC_DEPTH) { snprintf (err, errlen, "%d asynchronous calls already in flight: RC_WaitViews first", RC_ASYNC_DEPTH); return RC_ERR_ARG; }
 	int st = 0;
 	int r = rc_gpu_render_host (g, batch, fb_out, z_out, &st, err, errlen);
-	if (r == RC_OK) { sim_async_status[(sim_async_head + sim_async_n) & 1] = st; sim_async_n++; }
+	if (r == RC_OK) { sim_async_status[(sim_async_head + sim_async_n) % RC_ASYNC_DEPTH] = st; sim_async_n++; }
 	return r;
 }
 int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 {
 	if (sim_async_n <= 0) { snprintf (err, errlen, "no asynchronous call in flight"); return RC_ERR_ARG; }
 	if (status) *status = sim_async_status[sim_async_head];
-	sim_async_head ^= 1; sim_async_n--;
+	sim_async_head = (sim_async_head + 1) % RC_ASYNC_DEPTH; sim_async_n--;
 	return RC_OK;
 }
 

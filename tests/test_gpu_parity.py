@@ -126,7 +126,7 @@ def test_c4_full_batch_properties(assets_dir, oracle_available):
 
 @pytest.mark.gpu
 def test_async_pipeline_matches_blocking_call(assets_dir):
-    """RC_RenderViewsAsync / RC_WaitViews (two batches in flight, copies overlapping the next batch's kernels)
+    """RC_RenderViewsAsync / RC_WaitViews (up to three batches outstanding, copies overlapping the next batches' kernels)
     deliver the same bytes as the blocking RC_RenderViews, in order."""
     import numpy as np
     from tochris_b200.api import RefCuda
@@ -134,7 +134,7 @@ def test_async_pipeline_matches_blocking_call(assets_dir):
     r = RefCuda(assets_dir, 320, 240)
     r.load_world("maps/multi.bsp")
     batches = []
-    for b in range(4):
+    for b in range(7):
         specs = rcutil.scene_views("multi", 16, time=0.5 + b, time_step=0.07)
         batches.append(views.build_refdefs(specs, 320, 240, model_resolver=r.model))
     want = []
@@ -142,16 +142,19 @@ def test_async_pipeline_matches_blocking_call(assets_dir):
         fb, z, st = r.render(rds)
         assert st == 0
         want.append((fb.copy(), z.copy()))
-    bufs = [(np.zeros((16, 240, 320), np.uint8), np.zeros((16, 240, 320), np.int16)) for _ in range(2)]
+    bufs = [(np.zeros((16, 240, 320), np.uint8), np.zeros((16, 240, 320), np.int16)) for _ in range(3)]
     got = []
     for k, rds in enumerate(batches):
-        if k >= 2:
+        if k >= 3:
             assert r.wait() == 0
-            got.append((bufs[k & 1][0].copy(), bufs[k & 1][1].copy()))
-        r.render_async(rds, 16, bufs[k & 1][0], bufs[k & 1][1])
-    for k in range(2, 4):
+            got.append((bufs[k % 3][0].copy(), bufs[k % 3][1].copy()))
+        r.render_async(rds, 16, bufs[k % 3][0], bufs[k % 3][1])
+        if k == 2:
+            with pytest.raises(RuntimeError):      # a fourth outstanding call is refused, nothing is enqueued
+                r.render_async(rds, 16, bufs[0][0], bufs[0][1])
+    for k in range(4, 7):
         assert r.wait() == 0
-        got.append((bufs[k & 1][0].copy(), bufs[k & 1][1].copy()))
+        got.append((bufs[k % 3][0].copy(), bufs[k % 3][1].copy()))
     with pytest.raises(RuntimeError):
         r.wait()                       # nothing outstanding
     for (wf, wz), (gf, gz) in zip(want, got):

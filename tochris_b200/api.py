@@ -255,7 +255,7 @@ class RefCuda:
             raise RuntimeError(f"RC_PresentViewsDevice failed: {self.err()}")
 
     def render_async(self, rds, n: int, fb, z=None) -> None:
-        """RC_RenderViewsAsync: enqueue a batch into caller-owned (pinned) numpy buffers; at most two outstanding."""
+        """RC_RenderViewsAsync: enqueue a batch into caller-owned (pinned) numpy buffers; at most three outstanding (RC_ASYNC_CALLS)."""
         rc = self.lib.RC_RenderViewsAsync(rds, n, fb.ctypes.data, z.ctypes.data if z is not None else None)
         if rc != 0:
             raise RuntimeError(f"RC_RenderViewsAsync failed ({rc}): {self.err()}")

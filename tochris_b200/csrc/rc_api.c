@@ -43,7 +43,7 @@ static struct {
 	rc_draw2d_t *d2frame; int d2framen, d2framecap;	/* commands recorded by the render.h Draw_* functions since R_BeginFrame */
 	float        gamma; uint8_t gammatable[256]; int gamma_valid;	/* v_gamma + R_BuildGammaTable */
 	uint32_t    *palscratch; int palscratchcap;
-	int          async_unsupported[2]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
+	int          async_unsupported[RC_ASYNC_DEPTH]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
 	rc_view_t   *viewscratch; int viewscratchcap;
@@ -603,7 +603,7 @@ int RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t 
 	r = rc_gpu_render_host_async (rc.gpu, &rc.batch, fb_out, z_out, rc.err, sizeof(rc.err));
 	if (r == RC_OK)
 	{
-		rc.async_unsupported[rc.async_tail & 1] = rc.unsupported; rc.async_tail++;
+		rc.async_unsupported[rc.async_tail] = rc.unsupported; rc.async_tail = (rc.async_tail + 1) % RC_ASYNC_DEPTH;
 	}
 	return r;
 }
@@ -615,8 +615,8 @@ int RC_WaitViews (int *status)
 	r = rc_gpu_wait_host (rc.gpu, status, rc.err, sizeof(rc.err));
 	if (r == RC_OK)
 	{
-		if (status && rc.async_unsupported[rc.async_head & 1]) *status |= RC_STAT_UNSUPPORTED_ENT;
-		rc.async_head++;
+		if (status && rc.async_unsupported[rc.async_head]) *status |= RC_STAT_UNSUPPORTED_ENT;
+		rc.async_head = (rc.async_head + 1) % RC_ASYNC_DEPTH;
 	}
 	return r;
 }

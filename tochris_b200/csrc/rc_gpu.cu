@@ -85,9 +85,9 @@ struct rc_gpu_s {
 	int palvalid;
 	uint32_t *d_pal32; int palcap; uint32_t *h_pal32[2]; cudaEvent_t evpal[2]; int palslot;	/* pinned staging ring for the palettes */
 	uint8_t *d_presentin; uint32_t *d_presentout; size_t presentcap;	/* rc_gpu_present */
-	/* pipelined host output (rc_gpu_render_host_async): two calls in flight, each with its own device planes */
-	uint8_t *d_afb[2]; int16_t *d_azb[2]; size_t aoutcap[2];
-	cudaEvent_t adone_s[2], adone_copy[2]; int *astatus;	/* pinned */
+	/* pipelined host output (rc_gpu_render_host_async): RC_ASYNC_DEPTH calls in flight, each with its own device planes */
+	uint8_t *d_afb[RC_ASYNC_DEPTH]; int16_t *d_azb[RC_ASYNC_DEPTH]; size_t aoutcap[RC_ASYNC_DEPTH];
+	cudaEvent_t adone_s[RC_ASYNC_DEPTH], adone_copy[RC_ASYNC_DEPTH]; int *astatus;	/* pinned */
 	int ahead, ainflight, amode;	/* amode: slot + 1 while an asynchronous call is being enqueued */
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
@@ -1468,6 +1468,15 @@ __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 		p[i] = v;
 }
 
+/* status word of a pipelined call, stored straight into pinned host memory: a device->host cudaMemcpyAsync would
+ * queue on the copy engine behind the previous batch's frame-buffer copies and, being in stream order, hold the
+ * next batch's kernels back until those copies are through */
+__global__ void k_status_out (const int *d_status, int *host_status)
+{
+	*host_status = *d_status;
+	__threadfence_system ();
+}
+
 /* ------------------------------------------------------------------------- host ------- */
 template <typename T>
 static int upload (rc_gpu_t *g, const T *src, size_t count, const T **dst, char *err, size_t errlen)
@@ -1499,7 +1508,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	memset (&g->stats, 0, sizeof(g->stats));
 	g->device = device; g->width = width; g->height = height;
 	g->haveworld = false; g->skybox = 0; g->chunkcap = 0; g->maxchunk = 0; g->maxviews = max_views; g->spans_per_line = 24;
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < RC_ASYNC_DEPTH; i++)
 	{
 		g->d_afb[i] = NULL; g->d_azb[i] = NULL; g->aoutcap[i] = 0;
 		cudaEventCreateWithFlags (&g->adone_s[i], cudaEventDisableTiming);
@@ -1510,7 +1519,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_pal32 = NULL; g->palcap = 0; g->h_pal32[0] = g->h_pal32[1] = NULL; g->palslot = 0;
 	cudaEventCreateWithFlags (&g->evpal[0], cudaEventDisableTiming); cudaEventCreateWithFlags (&g->evpal[1], cudaEventDisableTiming);
 	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
-	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * 2, cudaHostAllocDefault);
+	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * RC_ASYNC_DEPTH, cudaHostAllocDefault);
 	g->ahead = 0; g->ainflight = 0; g->amode = 0;
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
@@ -1590,7 +1599,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_cachepool); cudaFree (g->d_cachekeys); cudaFree (g->d_cachevals);
 	cudaFree (g->d_alloc); cudaFree (g->d_status); cudaFree (g->d_sintable); cudaFree (g->d_intsintable);
 	cudaFree (g->d_fb); cudaFree (g->d_zb); cudaFree (g->d_dlights); cudaFree (g->d_warpbuf);
-	for (int i = 0; i < 2; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
+	for (int i = 0; i < RC_ASYNC_DEPTH; i++) { cudaFree (g->d_afb[i]); cudaFree (g->d_azb[i]); cudaEventDestroy (g->adone_s[i]); cudaEventDestroy (g->adone_copy[i]); }
 	cudaFreeHost (g->astatus);
 	cudaFree (g->d_pal32); cudaFree (g->d_presentin); cudaFree (g->d_presentout);
 	cudaFree (g->d_d2blob); cudaFree (g->d_d2pics); cudaFree (g->d_d2cmds); cudaFree (g->d_d2first);
@@ -2265,7 +2274,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		{
 			/* pipelined call: the status lands in pinned memory, nothing waits here; a pool overflow is
 			 * reported by rc_gpu_wait_host and the caller renders that batch again with the blocking call */
-			CK (cudaMemcpyAsync (&g->astatus[g->amode - 1], g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+			k_status_out<<<1, 1, 0, s>>> (g->d_status, &g->astatus[g->amode - 1]);
 			CK (cudaEventRecord (g->adone_s[g->amode - 1], s));
 			break;
 		}
@@ -2331,7 +2340,7 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 	return r;
 }
 
-/* Pipelined host output: enqueues the batch and returns; at most two calls in flight.  The device->host
+/* Pipelined host output: enqueues the batch and returns; at most RC_ASYNC_DEPTH calls in flight.  The device->host
  * copies of this call run on the copy stream while the next call's kernels run, each call drawing into
  * its own device planes. */
 int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen)
@@ -2339,18 +2348,20 @@ int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_
 	const int n = batch->n;
 	size_t px = (size_t)g->width * g->height;
 	cudaSetDevice (g->device);
-	if (g->ainflight >= 2) { snprintf (err, errlen, "two asynchronous calls already in flight: RC_WaitViews first"); return RC_ERR_ARG; }
+	if (g->ainflight >= RC_ASYNC_DEPTH) { snprintf (err, errlen, "%d asynchronous calls already in flight: RC_WaitViews first", RC_ASYNC_DEPTH); return RC_ERR_ARG; }
 	if (g->profiling) { snprintf (err, errlen, "asynchronous rendering needs profiling off"); return RC_ERR_ARG; }
-	const int slot = (g->ahead + g->ainflight) & 1;
+	const int slot = (g->ahead + g->ainflight) % RC_ASYNC_DEPTH;
 	if (g->aoutcap[slot] < px * n)
 	{
 		cudaFree (g->d_afb[slot]); cudaFree (g->d_azb[slot]);
 		g->d_afb[slot] = NULL; g->d_azb[slot] = NULL; g->aoutcap[slot] = 0;
-		CK (cudaMalloc (&g->d_afb[slot], px * n));
+		CK (cudaMalloc (&g->d_afb[slot], px * n + 8));
 		CK (cudaMalloc (&g->d_azb[slot], px * n * sizeof(int16_t)));
 		g->aoutcap[slot] = px * n;
 	}
-	CK (cudaMemsetAsync (g->d_afb[slot], 0, px * n, g->stream));
+	/* cleared by a kernel, not cudaMemsetAsync: nothing of this call may queue on a copy engine ahead of its own
+	 * frame-buffer copies (the engine would be busy with the previous call's) */
+	k_fill64<<<g->numsms * 4, 256, 0, g->stream>>> ((unsigned long long *)g->d_afb[slot], 0ull, (px * n + 7) / 8);
 	g->astatus[slot] = 0;
 	CK (cudaEventRecord (g->adone_copy[slot], g->copystream));	/* paths that copy on the main stream leave this one as "done" */
 	g->host_fb = fb_out; g->host_z = z_out; g->amode = slot + 1;
@@ -2370,7 +2381,7 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 	CK (cudaEventSynchronize (g->adone_s[slot]));
 	CK (cudaEventSynchronize (g->adone_copy[slot]));
 	if (status) *status = g->astatus[slot];
-	g->ahead ^= 1; g->ainflight--;
+	g->ahead = (g->ahead + 1) % RC_ASYNC_DEPTH; g->ainflight--;
 	return RC_OK;
 }
 

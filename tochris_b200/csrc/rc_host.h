@@ -158,6 +158,7 @@ int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_
                     int *status, char *err, size_t errlen);
 int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
+#define RC_ASYNC_DEPTH 3	/* RC_RenderViewsAsync calls that may be outstanding: one being copied out, one drawn, one queued behind it */
 int  rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out, char *err, size_t errlen);
 int  rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen);
 void rc_gpu_flush_caches (rc_gpu_t *g);

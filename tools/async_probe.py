@@ -13,7 +13,7 @@ specs = rcutil.scene_views("multi", n, time=1.0)
 r = RefCuda(base, W, H)
 r.load_world("maps/multi.bsp")
 rds = views.build_refdefs(specs, W, H, model_resolver=r.model)
-bufs = [torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+bufs = [torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(3)]
 l2flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 side = torch.cuda.Stream()
 for flush in (False, True, "l2", "l2side"):
@@ -22,14 +22,14 @@ for flush in (False, True, "l2", "l2side"):
         torch.cuda.synchronize(); t00 = time.perf_counter()
         K = 20
         for k in range(K):
-            if k >= 2:
+            if k >= 3:
                 t0 = time.perf_counter(); r.wait(); tw += time.perf_counter() - t0
             if flush: r.flush_caches()
             if flush == "l2": l2flush.zero_()
             if flush == "l2side":
                 with torch.cuda.stream(side): l2flush.zero_()
-            t0 = time.perf_counter(); r.render_async(rds, n, bufs[k & 1]); tq += time.perf_counter() - t0
-        for k in range(2):
+            t0 = time.perf_counter(); r.render_async(rds, n, bufs[k % 3]); tq += time.perf_counter() - t0
+        for k in range(3):
             t0 = time.perf_counter(); r.wait(); tw += time.perf_counter() - t0
         tot = time.perf_counter() - t00
         print(f"flush={flush} rep={rep}: total {tot/K*1e3:.3f} ms/step, enqueue {tq/K*1e3:.3f}, wait {tw/K*1e3:.3f}")
