@@ -88,6 +88,7 @@ struct rc_gpu_s {
 	/* pipelined host output (rc_gpu_render_host_async): RC_ASYNC_DEPTH calls in flight, each with its own device planes */
 	uint8_t *d_afb[RC_ASYNC_DEPTH]; int16_t *d_azb[RC_ASYNC_DEPTH]; size_t aoutcap[RC_ASYNC_DEPTH];
 	cudaEvent_t adone_s[RC_ASYNC_DEPTH], adone_copy[RC_ASYNC_DEPTH]; int *astatus;	/* pinned */
+	int agroups;	/* groups of a pipelined call (RC_ASYNC_GROUPS) */
 	int ahead, ainflight, amode;	/* amode: slot + 1 while an asynchronous call is being enqueued */
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
@@ -1521,6 +1522,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
 	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * RC_ASYNC_DEPTH, cudaHostAllocDefault);
 	g->ahead = 0; g->ainflight = 0; g->amode = 0;
+	{ const char *e = getenv ("RC_ASYNC_GROUPS"); g->agroups = e && atoi (e) >= 1 && atoi (e) <= 8 ? atoi (e) : 4; }
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
@@ -1958,7 +1960,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		/* host output crosses PCIe (the copy of a group is longer than its draw: four groups); a mirror in peer memory
 		 * is an NVLink copy, short next to the per-launch cost of a group: two */
 		const int mgroups = g->mirrorgroups >= 1 && g->mirrorgroups <= 8 ? (g->mirrorgroups <= n ? g->mirrorgroups : n) : 2;
-		const int ngroups = g->host_fb ? (g->host_fb == g->mirror_fb ? mgroups : (n >= 32 ? 4 : 2)) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
+		const int ngroups = g->host_fb ? (g->host_fb == g->mirror_fb ? mgroups : (g->amode ? g->agroups : (n >= 32 ? 4 : 2))) : (g->ngroups > 0 && g->ngroups <= 8 ? (g->ngroups <= n ? g->ngroups : n) : 4);
 		cudaStream_t side = g->host_fb ? g->copystream : g->groupstream;
 		const size_t px = (size_t)g->width * g->height;
 		/* the mixed cells of ALL views in one launch on the second stream, beside the first groups' full cells

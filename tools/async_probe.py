@@ -36,3 +36,22 @@ for flush in (False, True, "l2", "l2side"):
 t0 = time.perf_counter()
 for k in range(20): r.render(rds, n, want_z=False, fb=bufs[0])
 print(f"blocking: {(time.perf_counter()-t0)/20*1e3:.3f} ms/step")
+# plain D2H copies of one step's frame buffers while device-output renders run on another stream: how much the
+# render's memory traffic slows the PCIe copy (and the other way round)
+fbd = torch.empty((n, H, W), dtype=torch.uint8, device="cuda"); zd = torch.empty((n, H, W), dtype=torch.int16, device="cuda")
+hb = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+for load in (False, True):
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(s1)
+    if load:
+        for k in range(40): r.render_device(rds, n, fbd.data_ptr(), zd.data_ptr(), s1.cuda_stream)
+    r1.record(s1)
+    with torch.cuda.stream(s2):
+        for a, b in evs:
+            a.record(s2); hb.copy_(fbd, non_blocking=True); b.record(s2)
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    print(f"copy alone={not load}: median {ts[10]:.3f} ms, max {ts[-1]:.3f}; 40 renders beside it {r0.elapsed_time(r1)/40:.3f} ms each")
