@@ -131,3 +131,42 @@ def test_timerefresh_matches_oracle_sweep(assets_dir, sim_lib, oracle_available)
     assert st == 0 and secs > 0
     assert np.array_equal(fb, o["fb"])
     r.shutdown()
+
+
+def test_async_call_bookkeeping(assets_dir, sim_lib):
+    """RC_RenderViewsAsync / RC_WaitViews host logic (include/ref_cuda.h): RC_ASYNC_CALLS = 3 calls may be outstanding,
+    a fourth is refused without side effects, RC_WaitViews answers in submission order and fails when nothing is
+    outstanding; the bytes equal the blocking call's."""
+    from tochris_b200.api import RefCuda
+    from tochris_b200.scenes import views
+    r = RefCuda(assets_dir, 160, 120, libpath=sim_lib)
+    r.load_world("maps/small.bsp")
+    batches, want = [], []
+    for b in range(5):
+        specs = rcutil.scene_views("small", 2, time=0.3 + b, time_step=0.11)
+        rds = views.build_refdefs(specs, 160, 120, model_resolver=r.model)
+        batches.append(rds)
+        fb, z, st = r.render(rds)
+        assert st == 0
+        want.append((fb.copy(), z.copy()))
+    bufs = [(np.zeros((2, 120, 160), np.uint8), np.zeros((2, 120, 160), np.int16)) for _ in range(3)]
+    got = []
+    with pytest.raises(RuntimeError):
+        r.wait()
+    for k, rds in enumerate(batches):
+        if k >= 3:
+            assert r.wait() == 0
+            got.append(tuple(a.copy() for a in bufs[k % 3]))
+        r.render_async(rds, 2, *bufs[k % 3])
+        if k == 2:
+            with pytest.raises(RuntimeError):
+                r.render_async(rds, 2, *bufs[0])
+    for k in range(2, 5):
+        assert r.wait() == 0
+        got.append(tuple(a.copy() for a in bufs[k % 3]))
+    with pytest.raises(RuntimeError):
+        r.wait()
+    assert len(got) == 5
+    for (wf, wz), (gf, gz) in zip(want, got):
+        assert np.array_equal(wf, gf) and np.array_equal(wz, gz)
+    r.shutdown()
