@@ -1469,6 +1469,25 @@ __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 		p[i] = v;
 }
 
+__global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long long *poolptr, unsigned long long first)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		keys[i] = RC_CACHE_EMPTY;
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		*poolptr = first;
+}
+
+/* start of a chunk: the span / job / queued-cell / full-cell counters (alloc[0], alloc[2..4]; alloc[1] is the surface
+ * cache's) and, for the first chunk of a batch, the status words -- one launch instead of three memsets */
+__global__ void k_reset_chunk (unsigned long long *alloc, int *status)
+{
+	const unsigned t = threadIdx.x;
+	if (t == 0 || (t >= 2 && t <= 4))
+		alloc[t] = 0ull;
+	if (status && t < 16)
+		status[t] = 0;
+}
+
 /* status word of a pipelined call, stored straight into pinned host memory: a device->host cudaMemcpyAsync would
  * queue on the copy engine behind the previous batch's frame-buffer copies and, being in stream order, hold the
  * next batch's kernels back until those copies are through */
@@ -1766,12 +1785,9 @@ int rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t err
 static void do_flush (rc_gpu_t *g, cudaStream_t s)
 {
 	/* only the slots that can be in use are cleared: the table is sized for the pool */
-	k_fill64<<<g->numsms * 4, 256, 0, s>>> (g->d_cachekeys, RC_CACHE_EMPTY, (size_t)g->cacheslots);
-	{
-		/* the pool starts after the sky-box pictures */
-		static const unsigned long long first = RC_SKYBOX_BYTES;
-		cudaMemcpyAsync (g->d_alloc + 1, &first, sizeof(first), cudaMemcpyHostToDevice, s);
-	}
+	/* the pool starts after the sky-box pictures (the allocation pointer is reset by the same kernel: one item in
+	 * stream order instead of a kernel and a copy) */
+	k_flush_cache<<<g->numsms * 4, 256, 0, s>>> (g->d_cachekeys, (size_t)g->cacheslots, g->d_alloc + 1, (unsigned long long)RC_SKYBOX_BYTES);
 	g->flush_pending = 0;
 }
 
@@ -1880,15 +1896,14 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		if (g->graph_exec && !memcmp (&g->graph_w, &w, sizeof(w)) && !memcmp (&g->graph_f, &f0, sizeof(f0)))
 		{
 			CK (cudaGraphLaunch (g->graph_exec, s));
-			g->stats.kernel_launches += 8;
+			g->stats.kernel_launches += 9;	/* the eight pipeline kernels + k_reset_chunk */
 			return RC_OK;
 		}
 		if (g->graph_exec) { cudaGraphExecDestroy (g->graph_exec); g->graph_exec = NULL; }
 		CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
 		capture.on = true;
 	}
-	CK (cudaMemsetAsync (g->d_alloc, 0, sizeof(unsigned long long), s));
-	CK (cudaMemsetAsync (g->d_alloc + 2, 0, 3 * sizeof(unsigned long long), s));	/* jobs, queued cells, full-cell count */
+	k_reset_chunk<<<1, 32, 0, s>>> (g->d_alloc, first_view == 0 ? g->d_status : NULL);
 
 	{
 		/* cluster size: as many CTAs per view as fit the machine in one wave, at most 8 */
@@ -2110,7 +2125,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			CK (cudaMemcpyAsync (g->host_z + px * first_view, zb, px * n * sizeof(int16_t), cudaMemcpyDefault, s));
 	}
 	if (timed) cudaEventRecord (g->ev[6], s);
-	g->stats.kernel_launches += 8;
+	g->stats.kernel_launches += 9;
 	if (capture.on)
 	{
 		cudaGraph_t graph = NULL;
@@ -2257,8 +2272,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	{
 		int r = ensure_chunk (g, n, batch->nbents ? 512 : 0, err, errlen);
 		if (r != RC_OK) return r;
-		CK (cudaMemsetAsync (g->d_status, 0, sizeof(int) * 16, s));
-		st = 0;
+		st = 0;		/* the device status words are cleared by the first chunk's k_reset_chunk */
 		for (int first = 0; first < n; first += g->chunkcap)
 		{
 			int cn = n - first < g->chunkcap ? n - first : g->chunkcap;
