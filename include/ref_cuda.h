@@ -265,6 +265,8 @@ typedef struct {
     float  ms_cells;          /* part of ms_draw spent in k_draw proper (full cells, straight-line code) */
     long long fullcells;      /* screen cells covered by one span (k_draw items) */
     long long slowcells;      /* of those, cells k_draw queued for the general code (turbulent, sky, solid, warp views, negative 1/z) */
+    long long alias_range_events; /* how often the entity rasterisers met a case the reference itself handles out of range
+                               * (status bit 512, RC_STAT_ALIAS_RANGE); blocking calls only */
 } rc_stats_t;
 void RC_GetStats (rc_stats_t *out);
 void RC_SetProfiling (int on);

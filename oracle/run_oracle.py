@@ -12,7 +12,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette=False, overlays=None):
+def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette=False, overlays=None, clear_each=False):
     try:
         sys.path.insert(0, ROOT)
         from oracle.refsoft import RefSoft
@@ -36,6 +36,15 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
                 r.render(rds[i], False)
                 fbs.append(r.draw2d(overlays[i]))
             out["fb"] = np.stack(fbs); out["z"] = None
+        elif clear_each:
+            # one view at a time into cleared buffers (colour 0, z 0): what a view leaves untouched -- everything but the
+            # entities of an RDF_NOWORLDMODEL view, the screen outside a sub-rectangle -- then compares as 0
+            fbs, zs = [], []
+            for i in range(len(specs)):
+                r.clear(0, 0)
+                fb, z = r.render(rds[i], True)
+                fbs.append(fb); zs.append(z)
+            out["fb"] = np.stack(fbs); out["z"] = np.stack(zs)
         elif want_palette:
             # one view at a time, R_EndFrame after each: frame buffer + the palette the reference uploaded
             fbs, pals = [], []
@@ -64,10 +73,10 @@ def _worker(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump,
         q.put(("err", traceback.format_exc()))
 
 
-def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600, want_palette=False, overlays=None):
+def render(basedir, mapname, width, height, specs, cvars=None, want_z=True, want_dump=False, repeat=1, timeout=600, want_palette=False, overlays=None, clear_each=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette, overlays))
+    p = ctx.Process(target=_worker, args=(q, basedir, mapname, width, height, specs, cvars, want_z, want_dump, repeat, want_palette, overlays, clear_each))
     p.start()
     try:
         # a worker that dies (a crash inside the C library) never answers: notice it instead of waiting out the timeout

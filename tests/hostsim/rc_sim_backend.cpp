@@ -145,7 +145,8 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	const rc_view_t *views = batch->views;
 	const int n = batch->n;
 	const rc_world_t *w = &g->w;
-	int st = 0;
+	int stw[16] = {0};
+	int &st = stw[0];
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
 	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
@@ -185,7 +186,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	f.fb = (uint8_t *)fb_dev; f.zb = (int16_t *)z_dev;
 	std::vector<uint8_t> warpbuf ((size_t)(batch->nwarp + 1) * RC_WARP_W * RC_WARP_H, 0);
 	f.warpbuf = warpbuf.data ();
-	f.status = &st;
+	f.status = stw;
 
 	std::vector<int> facemark ((size_t)n * w->numfaces, 0x7F7F7F7F), viewleaf (n, 0);
 	std::vector<rc_nodevisit_t> nodevisit ((size_t)n * w->numnodes, rc_nodevisit_t ());
@@ -279,6 +280,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	memset (&g->stats, 0, sizeof(g->stats));
 	g->stats.cache_jobs = njobs; g->stats.cache_texels = texels; g->stats.blocks = (long long)n * g->height * cw + nspans; g->stats.spans = g->nspans;
 	for (int vi = 0; vi < n; vi++) { g->stats.edges += g->nedges[vi]; g->stats.faces += nfaces[vi]; }
+	g->stats.alias_range_events = stw[1];
 	if (status) *status = st;
 	return RC_OK;
 }

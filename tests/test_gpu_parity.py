@@ -202,3 +202,67 @@ def test_fuzz_shapes_match_oracle(assets_dir, oracle_available, scene, w, h, n, 
     o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
     rcutil.assert_parity(o, r, specs, w, h)
+
+
+@pytest.mark.parametrize("scene,w,h,n,kw", [("multi", 320, 240, 6, {}), ("multi", 640, 480, 4, dict(dlights=3)), ("full", 400, 300, 6, {})])
+def test_stage_dumps_match_oracle_gpu(assets_dir, oracle_available, scene, w, h, n, kw):
+    """Stage-level differential test on the REAL kernels (k_front's edges and surfaces, k_scan's spans) through RC_DebugRead,
+    against the dumps taken inside the reference -- not only on the host simulator."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    import test_hostsim_parity as hp
+    hp.check_stage_dumps(api.LIBPATH, assets_dir, scene, w, h, n, **kw)
+
+
+@pytest.mark.gpu
+def test_async_stream_with_a_tiny_surface_cache_never_delivers_wrong_pixels(assets_dir):
+    """A surface-cache pool that holds one batch's blocks but not two: in a pipelined stream (RC_RenderViewsAsync) the second
+    batch runs out of pool.  Every batch must either come back clean and correct or carry RC_STAT_CACHE_POOL -- including
+    the batches queued BEHIND the one that overflowed, which meet keys whose creator got no block --, and the blocking
+    re-render the caller owes a flagged batch must be clean (the overflow schedules D_FlushCaches)."""
+    import numpy as np
+    from tochris_b200.api import RefCuda
+    from tochris_b200.scenes import views
+    W, H, n = 320, 240, 12
+    sets = [rcutil.scene_views("multi", n, start=1 + 40 * k, time=0.5 + k) for k in range(2)]
+    r = RefCuda(assets_dir, W, H)
+    r.load_world("maps/multi.bsp")
+    want, texels = [], []
+    r.set_profiling(True)
+    for sp in sets:
+        r.flush_caches()
+        fb, _, st = r.render(views.build_refdefs(sp, W, H, model_resolver=r.model), want_z=False)
+        assert st == 0
+        want.append(fb.copy()); texels.append(r.stats()["cache_texels"])
+    r.set_profiling(False)
+    r.shutdown()
+    pool = 6 * 256 * 256 + int(max(texels) * 1.25) + 4096            # the sky-box pictures + one batch's blocks and a bit
+    assert pool < 6 * 256 * 256 + sum(texels)
+    r = RefCuda(assets_dir, W, H, surfcache_bytes=pool)
+    r.load_world("maps/multi.bsp")
+    rds = [views.build_refdefs(sp, W, H, model_resolver=r.model) for sp in sets]
+    bufs = [np.zeros((n, H, W), np.uint8) for _ in range(3)]
+    order = [0, 1, 0, 1, 0, 1, 1, 0]
+    flagged = clean = 0
+    pending = []
+    for k, which in enumerate(order + [None] * 3):
+        if len(pending) == 3 or which is None:
+            if not pending:
+                break
+            slot, w_ = pending.pop(0)
+            st = r.wait()
+            if st == 0:
+                assert np.array_equal(bufs[slot], want[w_]), "a batch with a clean status has wrong pixels"
+                clean += 1
+            else:
+                assert st == 32, api.status_names(st)            # RC_STAT_CACHE_POOL and nothing else
+                flagged += 1
+        if which is not None:
+            slot = k % 3
+            r.render_async(rds[which], n, bufs[slot])
+            pending.append((slot, which))
+    assert flagged >= 1 and clean >= 1, (flagged, clean)
+    for which in (1, 0):                                             # the blocking re-render: flushed first, then clean
+        fb, _, st = r.render(rds[which], want_z=False)
+        assert st == 0 and np.array_equal(fb, want[which])
+    r.shutdown()

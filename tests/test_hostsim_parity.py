@@ -63,15 +63,16 @@ def test_sim_matches_golden(assets_dir, sim_lib):
     assert rcutil.sha(r["fb"]) == str(g["fb_sha"]) and rcutil.sha(r["z"]) == str(g["z_sha"])
 
 
-def test_stage_dumps_match(assets_dir, sim_lib, oracle_available):
-    """Per-stage differential test: emitted edges and spans, not only pixels."""
-    if not oracle_available:
-        pytest.skip("oracle/_ref not built")
+def check_stage_dumps(lib, assets_dir, scene="multi", w=320, h=240, n=4, **kw):
+    """Per-stage differential test: the emitted edges (u, u_step, v, v2, and which surfaces they lead / trail
+    by BSP key), the surfaces (key, flags, 1/z gradients) and the spans (u, v, count), not only pixels, against the dumps
+    the oracle shim takes inside the reference (oracle/headless.c: R_ScanEdges / D_DrawSurfaces interposed)."""
     from oracle import run_oracle
-    specs = rcutil.scene_views("multi", 4, time=1.0)
-    o = run_oracle.render(assets_dir, "maps/multi.bsp", 320, 240, specs, want_dump=True)
-    r = rcutil.render_rc(sim_lib, assets_dir, "maps/multi.bsp", 320, 240, specs, want_debug=True)
-    for vi in range(4):
+    specs = rcutil.scene_views(scene, n, time=1.0, **kw)
+    o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs, want_dump=True)
+    r = rcutil.render_rc(lib, assets_dir, f"maps/{scene}.bsp", w, h, specs, want_debug=True)
+    assert r["status"] == 0
+    for vi in range(n):
         oe, os_, osp, cnt = o["dumps"][vi]
         assert cnt["outofedges"] == 0 and cnt["outofsurfaces"] == 0
         re = r["edges"][vi]
@@ -79,10 +80,24 @@ def test_stage_dumps_match(assets_dir, sim_lib, oracle_available):
         a = sorted((int(e["u"]), int(e["u_step"]), int(e["v"]), int(e["v2"])) for e in oe)
         b = sorted((int(e["u"]), int(e["u_step"]), int(e["v"]), int(e["v2"])) for e in re)
         assert a == b
+        # the surfaces that got spans: same faces, flags and 1/z planes (d_ziorigin / d_zistepu / d_zistepv, r_rast.c:660-667)
+        rs = r["surfs"][vi]
+        used = set(int(sp["surf"]) for sp in osp)
+        osd = sorted((int(os_[i]["face"]), int(os_[i]["flags"]), float(os_[i]["d_ziorigin"]), float(os_[i]["d_zistepu"]),
+                      float(os_[i]["d_zistepv"])) for i in used)
+        rsd = sorted((int(s["face"]), int(s["flags"]), float(s["d_ziorigin"]), float(s["d_zistepu"]), float(s["d_zistepv"]))
+                     for s in rs[1:] if s["hasspans"] and s["flags"] >= 0)
+        assert osd == rsd, (vi, len(osd), len(rsd), osd[:3], rsd[:3])
         rsp = r["spans"][(r["spans"]["view"] == vi) & (r["spans"]["count"] > 0)]
         a = sorted((int(s["u"]), int(s["v"]), int(s["count"])) for s in osp)
         b = sorted((int(s["u"]), int(s["v"]), int(s["count"])) for s in rsp)
         assert a == b
+
+
+def test_stage_dumps_match(assets_dir, sim_lib, oracle_available):
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    check_stage_dumps(sim_lib, assets_dir)
 
 
 RECTS = [(8, 4, 304, 190), (13, 7, 291, 173), (0, 0, 317, 199), (5, 0, 40, 33), (100, 50, 9, 9)]

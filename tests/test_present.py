@@ -83,3 +83,23 @@ def test_present_on_device_matches_reference(assets_dir, oracle_available):
             assert np.array_equal(a, b)
     assert np.array_equal(r.present(rds, fb), _expand(fb, pals))
     r.shutdown()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(322, 201), (70, 51), (324, 202)])
+def test_present_with_plane_sizes_that_are_not_multiples_of_four(assets_dir, w, h):
+    """k_present's vector path needs 4 / 16-byte aligned planes; width * height that is not a multiple of 4 puts every
+    view after the first off that alignment: the kernel must take its one-pixel path (misaligned-address fault)."""
+    from tochris_b200.api import RefCuda
+    from tochris_b200.scenes import views
+    specs = _specs(5)
+    r = RefCuda(assets_dir, w, h)
+    r.load_world("maps/small.bsp")
+    rds = views.build_refdefs(specs, w, h, model_resolver=r.model)
+    fb, _, st = r.render(rds)
+    assert st == 0
+    pals = [r.view_palette(rds[i]) for i in range(len(specs))]
+    assert np.array_equal(r.present(rds, fb), _expand(fb, pals))
+    fb2, _, st = r.render(rds)                      # the context is still healthy
+    assert st == 0 and np.array_equal(fb, fb2)
+    r.shutdown()

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get("RC_LIBPATH") or os.path.join(HERE, "libref_cuda.so")   # RC_LIBPATH: kernel-variant experiments
 
 RC_STAT = {1: "EDGE_OVERFLOW", 2: "SURF_OVERFLOW", 4: "SPAN_POOL", 8: "AET_OVERFLOW", 16: "STACK_OVERFLOW",
-           32: "CACHE_POOL", 64: "STALE_CLIPVERT", 128: "FACELIST"}
+           32: "CACHE_POOL", 64: "STALE_CLIPVERT", 128: "FACELIST", 512: "ALIAS_RANGE", 1024: "BMODEL_OVERFLOW"}
 
 
 class rc_config_t(C.Structure):
@@ -37,7 +37,7 @@ class rc_stats_t(C.Structure):
                 ("ms_walk", C.c_float), ("ms_faces", C.c_float), ("ms_scan", C.c_float), ("ms_surfprep", C.c_float),
                 ("ms_cache", C.c_float), ("ms_draw", C.c_float), ("ms_total", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float), ("ms_cells", C.c_float),
-                ("fullcells", C.c_longlong), ("slowcells", C.c_longlong)]
+                ("fullcells", C.c_longlong), ("slowcells", C.c_longlong), ("alias_range_events", C.c_longlong)]
 
 
 class rc_edge_t(C.Structure):
@@ -297,6 +297,12 @@ class RefCuda:
         if self.lib.RC_DeviceAlloc(C.c_size_t(nbytes), C.byref(p)) != 0:
             raise RuntimeError("RC_DeviceAlloc failed")
         return p.value
+
+    def device_free(self, ptr: int):
+        self.lib.RC_DeviceFree(C.c_void_p(ptr))
+
+    def ipc_close(self, ptr: int):
+        self.lib.RC_IpcClose(C.c_void_p(ptr))
 
     def ipc_export(self, ptr: int) -> bytes:
         h = (C.c_ubyte * 64)()

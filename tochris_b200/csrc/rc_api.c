@@ -31,7 +31,6 @@ static struct {
 	int          nummodels;
 	struct model_s *world;
 	char         err[1024];
-	int          unsupported;
 	int          loadlits;		/* r_loadlits (r_main.c:130) */
 	/* 2D overlay (r_draw.c): conchars + pictures + translation tables in one blob, mirrored on the device */
 	uint8_t     *d2blob; size_t d2len, d2cap;
@@ -43,7 +42,6 @@ static struct {
 	rc_draw2d_t *d2frame; int d2framen, d2framecap;	/* commands recorded by the render.h Draw_* functions since R_BeginFrame */
 	float        gamma; uint8_t gammatable[256]; int gamma_valid;	/* v_gamma + R_BuildGammaTable */
 	uint32_t    *palscratch; int palscratchcap;
-	int          async_unsupported[RC_ASYNC_DEPTH]; unsigned async_head, async_tail;	/* RC_RenderViewsAsync calls in flight */
 	/* single-view path targets (RC_SetVidBuffers) */
 	uint8_t     *vidbuffer; int vidrowbytes; int16_t *zbuffer;
 	rc_view_t   *viewscratch; int viewscratchcap;
@@ -332,7 +330,6 @@ int RC_LoadWorld (const char *name)
 static int rc_prepare_views (const refdef_t *views, int n)
 {
 	int i, j, rcode, ndl, nwarp = 0, nbent_total = 0, nbents = 0, maxbfaces = 0;
-	rc.unsupported = 0;
 	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
 	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
 	if (n > rc.viewscratchcap)
@@ -591,7 +588,6 @@ int RC_RenderViews (const refdef_t *views, int n, uint8_t *fb_out, int16_t *z_ou
 	if (r != RC_OK) return r;
 	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
 	r = rc_gpu_render_host (rc.gpu, &rc.batch, fb_out, z_out, status, rc.err, sizeof(rc.err));
-	if (status && rc.unsupported) *status |= RC_STAT_UNSUPPORTED_ENT;
 	return r;
 }
 
@@ -601,24 +597,13 @@ int RC_RenderViewsAsync (const refdef_t *views, int n, uint8_t *fb_out, int16_t 
 	if (r != RC_OK) return r;
 	if (!fb_out) return rc_fail (RC_ERR_ARG, "fb_out is NULL");
 	r = rc_gpu_render_host_async (rc.gpu, &rc.batch, fb_out, z_out, rc.err, sizeof(rc.err));
-	if (r == RC_OK)
-	{
-		rc.async_unsupported[rc.async_tail] = rc.unsupported; rc.async_tail = (rc.async_tail + 1) % RC_ASYNC_DEPTH;
-	}
 	return r;
 }
 
 int RC_WaitViews (int *status)
 {
-	int r;
 	if (!rc.gpu) return rc_fail (RC_ERR_ARG, "RC_Init first");
-	r = rc_gpu_wait_host (rc.gpu, status, rc.err, sizeof(rc.err));
-	if (r == RC_OK)
-	{
-		if (status && rc.async_unsupported[rc.async_head]) *status |= RC_STAT_UNSUPPORTED_ENT;
-		rc.async_head = (rc.async_head + 1) % RC_ASYNC_DEPTH;
-	}
-	return r;
+	return rc_gpu_wait_host (rc.gpu, status, rc.err, sizeof(rc.err));
 }
 
 int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
@@ -627,7 +612,6 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 	if (r != RC_OK) return r;
 	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
 	r = rc_gpu_render (rc.gpu, &rc.batch, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));
-	if (status && rc.unsupported) *status |= RC_STAT_UNSUPPORTED_ENT;
 	return r;
 }
 
@@ -1127,33 +1111,83 @@ void R_BeginFrame (void) { rc.d2framen = 0; }
  * download); the palette is the caller's business (RC_ViewPalette -> VID_ShiftPalette). */
 void R_EndFrame (void)
 {
-	if (rc.d2framen && rc.vidbuffer && rc.vidrowbytes == rc.vid.width)
+	if (rc.d2framen && rc.vidbuffer)
 	{
 		int first[2];
 		first[0] = 0; first[1] = rc.d2framen;
-		if (RC_DrawOverlay (rc.d2frame, first, 1, rc.vidbuffer) != RC_OK)
-			fprintf (stderr, "ref_cuda: %s\n", rc.err);
+		if (rc.vidrowbytes == rc.vid.width)
+		{
+			if (RC_DrawOverlay (rc.d2frame, first, 1, rc.vidbuffer) != RC_OK)
+				fprintf (stderr, "ref_cuda: %s\n", rc.err);
+		}
+		else
+		{
+			/* vid.rowbytes "may be > width if displayed in a window" (client/vid.h:38): the rows are packed for
+			 * the device and unpacked again */
+			const size_t w = (size_t)rc.vid.width;
+			uint8_t *tmp = (uint8_t *)malloc (w * rc.vid.height);
+			int y;
+			if (tmp)
+			{
+				for (y = 0; y < rc.vid.height; y++)
+					memcpy (tmp + y * w, rc.vidbuffer + (size_t)y * rc.vidrowbytes, w);
+				if (RC_DrawOverlay (rc.d2frame, first, 1, tmp) != RC_OK)
+					fprintf (stderr, "ref_cuda: %s\n", rc.err);
+				else
+					for (y = 0; y < rc.vid.height; y++)
+						memcpy (rc.vidbuffer + (size_t)y * rc.vidrowbytes, tmp + y * w, w);
+				free (tmp);
+			}
+		}
 	}
 	rc.d2framen = 0;
 }
 
+/* What a frame touches in the engine's buffers (the rest keeps what earlier frames and the 2D code left there: sbar and
+ * console redraw their areas only when they change):
+ *   colour  the refdef rectangle (under water D_WarpScreen writes the same rectangle, d_scan.c:43-103)
+ *   z       the refdef rectangle; under water the warp rectangle at the origin, <= 320x200 (r_misc.c:448-454);
+ *           with RDF_NOWORLDMODEL the whole buffer (0xFFFF, d_modech.c:103-106) and of the colour plane only the
+ *           entities' pixels -- the ones whose z is no longer 0xFFFF */
 void R_RenderView (refdef_t *refdef)
 {
 	size_t px = (size_t)rc.vid.width * rc.vid.height;
+	const int W = rc.vid.width;
 	uint8_t *fb;
 	int16_t *zb;
-	int y, status = 0;
+	int x, y, status = 0;
 	if (!rc.vidbuffer) { rc_fail (RC_ERR_ARG, "RC_SetVidBuffers first"); return; }
 	fb = (uint8_t *)malloc (px);
-	zb = rc.zbuffer ? (int16_t *)malloc (px * 2) : NULL;
-	if (RC_RenderViews (refdef, 1, fb, zb, &status) == RC_OK)
+	zb = (int16_t *)malloc (px * 2);
+	if (fb && zb && RC_RenderViews (refdef, 1, fb, zb, &status) == RC_OK)
 	{
-		for (y = 0; y < rc.vid.height; y++)
-			memcpy (rc.vidbuffer + (size_t)y * rc.vidrowbytes, fb + (size_t)y * rc.vid.width, rc.vid.width);
-		if (zb) memcpy (rc.zbuffer, zb, px * 2);
+		const int x0 = refdef->x, y0 = refdef->y, x1 = refdef->x + refdef->width, y1 = refdef->y + refdef->height;
+		if (refdef->flags & RDF_NOWORLDMODEL)
+		{
+			for (y = y0; y < y1; y++)
+				for (x = x0; x < x1; x++)
+					if (zb[(size_t)y * W + x] != (int16_t)-1)
+						rc.vidbuffer[(size_t)y * rc.vidrowbytes + x] = fb[(size_t)y * W + x];
+			if (rc.zbuffer) memcpy (rc.zbuffer, zb, px * 2);
+		}
+		else
+		{
+			int zx0 = x0, zy0 = y0, zx1 = x1, zy1 = y1;
+			for (y = y0; y < y1; y++)
+				memcpy (rc.vidbuffer + (size_t)y * rc.vidrowbytes + x0, fb + (size_t)y * W + x0, (size_t)(x1 - x0));
+			if (rc.cvars.r_waterwarp && (refdef->flags & RDF_UNDERWATER))
+			{
+				zx0 = 0; zy0 = 0;
+				zx1 = refdef->width < RC_WARP_WIDTH ? refdef->width : RC_WARP_WIDTH;
+				zy1 = refdef->height < RC_WARP_HEIGHT ? refdef->height : RC_WARP_HEIGHT;
+			}
+			if (rc.zbuffer)
+				for (y = zy0; y < zy1; y++)
+					memcpy (rc.zbuffer + (size_t)y * W + zx0, zb + (size_t)y * W + zx0, (size_t)(zx1 - zx0) * 2);
+		}
 	}
 	else
-		fprintf (stderr, "ref_cuda: R_RenderView: %s\n", rc.err);
+		fprintf (stderr, "ref_cuda: R_RenderView: %s\n", fb && zb ? rc.err : "out of memory");
 	free (fb); free (zb);
 }
 

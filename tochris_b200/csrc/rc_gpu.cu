@@ -95,6 +95,7 @@ struct rc_gpu_s {
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
 	int slow_in_ends;
+	int front_512;			/* RC_FRONT_512: keep 512-thread front-end CTAs on many-view batches (experiment knob) */
 	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
 	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
 	cudaGraphExec_t graph_exec; rc_world_t graph_w; rc_frame_t graph_f; int use_graphs;
@@ -529,10 +530,17 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	if (line >= f.height)
 		return;
 	int2 *cells = reinterpret_cast<int2 *>(f.cellspan + ((size_t)vi * f.height + line) * cw);
-	if (line < vy0 || line >= vy1)
+	if (line < vy0 || line >= vy1 || (vw->rdflags & 1))
 	{
 		for (int c = lane; c < cw; c += 32)
 			cells[c] = make_int2 (-1, 0);
+		if ((vw->rdflags & 1 /* RDF_NOWORLDMODEL */) && f.zb)
+		{
+			/* no world, no spans (r_main.c:889); the whole z-buffer is 0xFFFF for the entities (d_modech.c:103-106) */
+			int16_t *zrow = f.zb + ((size_t)vi * f.height + line) * f.width;
+			for (int x = lane; x < f.width; x += 32)
+				zrow[x] = (int16_t)-1;
+		}
 		return;
 	}
 	scan_warp_t<AET> *sw = &sh->warp[wid];
@@ -1420,10 +1428,19 @@ __global__ void __launch_bounds__(256) k_present (const uint8_t * __restrict__ f
 	const unsigned vi = blockIdx.y;
 	spal[threadIdx.x] = pal32[vi * 256 + threadIdx.x];
 	__syncthreads ();
+	const unsigned stride = gridDim.x * blockDim.x;
+	unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+	if ((px & 3u) || (reinterpret_cast<size_t>(fb) & 3) || (reinterpret_cast<size_t>(out) & 15))
+	{
+		/* a plane size that is not a multiple of 4 pixels puts every view after the first off the 4 / 16-byte
+		 * alignment the vector path needs (as does an unaligned slice from the caller): one pixel per thread */
+		for (; q < px; q += stride)
+			out[(size_t)vi * px + q] = spal[fb[(size_t)vi * px + q]];
+		return;
+	}
 	const uint32_t *src = reinterpret_cast<const uint32_t *>(fb + (size_t)vi * px);
 	uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)vi * px);
-	const unsigned nq = px >> 2, stride = gridDim.x * blockDim.x;
-	unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned nq = px >> 2;
 	for (; q + 3 * stride < nq; q += 4 * stride)
 	{
 		uint32_t v[4];
@@ -1438,12 +1455,6 @@ __global__ void __launch_bounds__(256) k_present (const uint8_t * __restrict__ f
 	{
 		const uint32_t v = __ldcs (&src[q]);
 		__stcs (&dst[q], make_uint4 (spal[v & 0xFF], spal[(v >> 8) & 0xFF], spal[(v >> 16) & 0xFF], spal[v >> 24]));
-	}
-	/* a plane whose size is not a multiple of 4 pixels: the last ones, one by one */
-	if (blockIdx.x == 0 && threadIdx.x < (px & 3u))
-	{
-		const unsigned p = (px & ~3u) + threadIdx.x;
-		out[(size_t)vi * px + p] = spal[fb[(size_t)vi * px + p]];
 	}
 }
 
@@ -1539,7 +1550,13 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_pal32 = NULL; g->palcap = 0; g->h_pal32[0] = g->h_pal32[1] = NULL; g->palslot = 0;
 	cudaEventCreateWithFlags (&g->evpal[0], cudaEventDisableTiming); cudaEventCreateWithFlags (&g->evpal[1], cudaEventDisableTiming);
 	g->d_presentin = NULL; g->d_presentout = NULL; g->presentcap = 0;
-	g->astatus = NULL; cudaHostAlloc (&g->astatus, sizeof(int) * RC_ASYNC_DEPTH, cudaHostAllocDefault);
+	g->astatus = NULL;
+	if (cudaHostAlloc (&g->astatus, sizeof(int) * RC_ASYNC_DEPTH, cudaHostAllocDefault) != cudaSuccess || !g->astatus)
+	{
+		snprintf (err, errlen, "cudaHostAlloc (status words) failed: %s", cudaGetErrorString (cudaGetLastError ()));
+		delete g;
+		return NULL;
+	}
 	g->ahead = 0; g->ainflight = 0; g->amode = 0;
 	{ const char *e = getenv ("RC_ASYNC_GROUPS"); g->agroups = e && atoi (e) >= 1 && atoi (e) <= 8 ? atoi (e) : 4; }
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
@@ -1562,6 +1579,11 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
 	g->mirrorgroups = 0;
+	/* Environment knobs, all read ONCE here; they select measured-and-rejected variants for A/B runs and are not part of
+	 * the API: RC_ASYNC_GROUPS=1..8 groups of a pipelined call (default 4), RC_SLOW_IN_ENDS k_ends finds the
+	 * general cells itself, RC_SCAN_LARGE start with the large scan instance, RC_NO_GRAPH no CUDA-graph replay,
+	 * RC_FRONT_512 512-thread front-end CTAs on many-view batches */
+	g->front_512 = getenv ("RC_FRONT_512") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
 	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
@@ -1626,7 +1648,15 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_d2blob); cudaFree (g->d_d2pics); cudaFree (g->d_d2cmds); cudaFree (g->d_d2first);
 	cudaFreeHost (g->h_pal32[0]); cudaFreeHost (g->h_pal32[1]); cudaEventDestroy (g->evpal[0]); cudaEventDestroy (g->evpal[1]);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
+	cudaFree (g->d_bents); cudaFree (g->d_alias); cudaFree (g->d_finalverts); cudaFree (g->d_particles);
+	cudaFree (g->d_colormaps); cudaFree (g->d_zres); cudaFree (g->d_zscratch);
+	cudaFree (g->d_amodels); cudaFree (g->d_stverts); cudaFree (g->d_atris); cudaFree (g->d_poseverts);
+	cudaFree (g->d_skinpixels); cudaFree (g->d_anormdots);
+	if (g->graph_exec) cudaGraphExecDestroy (g->graph_exec);
 	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
+	for (int i = 0; i < 8; i++) cudaEventDestroy (g->evgroup[i]);
+	cudaEventDestroy (g->evcopy); cudaEventDestroy (g->evfork); cudaEventDestroy (g->evjoin);
+	cudaStreamDestroy (g->copystream); cudaStreamDestroy (g->sidestream);
 	cudaStreamDestroy (g->stream);
 	delete g;
 }
@@ -1804,6 +1834,9 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 {
 	const rc_world_t *w = &g->w;
 	int facecap = (w->numworldfaces < 65000 ? w->numworldfaces : 65000) + 6;	/* + the six sky-box faces */
+	/* brush-entity surf_t slots, once allocated, are kept: batches that alternate between having brush entities and not
+	 * must not free and reallocate every chunk buffer (and re-instantiate the graph) each time */
+	if (g->d_views && g->bsurfcap > want_bsurfs) want_bsurfs = g->bsurfcap;
 	int edgecap = g->maxedges, surfcap = facecap + 2 + want_bsurfs;
 	size_t freeb = 0, totalb = 0;
 	if (g->d_views && g->facecap == facecap && g->edgecap == edgecap && g->bsurfcap == want_bsurfs && (g->chunkcap >= n || g->chunkcap == g->maxchunk))
@@ -1881,7 +1914,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	/* The plain device path (no entities, no warp views, no per-group consumers, no profiling) is a fixed sequence of
 	 * memsets and kernels on two streams whose parameters only change with the world or the buffers: it is captured
 	 * into a CUDA graph once and relaunched, which removes the launch gaps and the event round trips of the forks. */
-	const bool capturable = g->use_graphs && !timed && !g->host_fb && !g->groupfn && !anywarp &&
+	const bool capturable = g->use_graphs && !timed && s != cudaStreamLegacy && !g->host_fb && !g->groupfn && !anywarp &&
 		!(g->cur_batch && (g->cur_batch->nzres || g->cur_batch->nbents));
 	rc_frame_t f0;
 	memcpy (&f0, &f, sizeof(f));
@@ -1912,7 +1945,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaLaunchConfig_t cfg;
 		cudaLaunchAttribute attr[1];
 		memset (&cfg, 0, sizeof(cfg));
-		const bool manyviews = n > g->numsms && !getenv ("RC_FRONT_512");	/* more views than SMs: several waves */
+		const bool manyviews = n > g->numsms && !g->front_512;	/* more views than SMs: several waves */
 		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? FRONT_MANY : FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -2182,7 +2215,9 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 {
 	const rc_view_t *views = batch->views;
 	const int n = batch->n;
-	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	/* NULL is the legacy default stream (include/ref_cuda.h): a caller on the default stream is ordered with its own
+	 * producers and consumers.  The host-output paths pass the renderer's own stream explicitly. */
+	cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
 	const bool mirrored = !g->host_fb && g->mirror_fb;
 	if (mirrored) { g->host_fb = g->mirror_fb; g->host_z = z_dev ? g->mirror_z : NULL; }
 	struct unmirror_t { rc_gpu_t *g; bool on; ~unmirror_t () { if (on) { g->host_fb = NULL; g->host_z = NULL; } } } unmirror = { g, mirrored };
@@ -2294,8 +2329,11 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 			CK (cudaEventRecord (g->adone_s[g->amode - 1], s));
 			break;
 		}
-		CK (cudaMemcpyAsync (&st, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+		int stw[2] = { 0, 0 };
+		CK (cudaMemcpyAsync (stw, g->d_status, sizeof(stw), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
+		st = stw[0];
+		g->stats.alias_range_events = stw[1];
 #ifdef RC_FRONT_TIMING
 		{
 			int tq[16];
@@ -2351,7 +2389,7 @@ int rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, i
 	/* the device->host copies are issued by run_chunk (overlapped with the draw kernel where possible);
 	 * rc_gpu_render returns when the stream, copies included, has drained */
 	g->host_fb = fb_out; g->host_z = z_out;
-	int r = rc_gpu_render (g, batch, g->d_fb, g->d_zb, NULL, status, err, errlen);
+	int r = rc_gpu_render (g, batch, g->d_fb, g->d_zb, g->stream, status, err, errlen);
 	g->host_fb = NULL; g->host_z = NULL;
 	return r;
 }
@@ -2382,7 +2420,7 @@ int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_
 	CK (cudaEventRecord (g->adone_copy[slot], g->copystream));	/* paths that copy on the main stream leave this one as "done" */
 	g->host_fb = fb_out; g->host_z = z_out; g->amode = slot + 1;
 	int st = 0;
-	int r = rc_gpu_render (g, batch, g->d_afb[slot], g->d_azb[slot], NULL, &st, err, errlen);
+	int r = rc_gpu_render (g, batch, g->d_afb[slot], g->d_azb[slot], g->stream, &st, err, errlen);
 	g->host_fb = NULL; g->host_z = NULL; g->amode = 0;
 	if (r == RC_OK) g->ainflight++;
 	return r;
@@ -2397,6 +2435,11 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 	CK (cudaEventSynchronize (g->adone_s[slot]));
 	CK (cudaEventSynchronize (g->adone_copy[slot]));
 	if (status) *status = g->astatus[slot];
+	/* a pool overflow leaves keys without blocks behind (and the allocation pointer past the end): the next render
+	 * starts with D_FlushCaches, so the blocking re-render the caller owes this batch -- and every later batch -- is clean;
+	 * batches already queued behind this one report RC_STAT_CACHE_POOL themselves (rc_span_seg) */
+	if (g->astatus[slot] & (RC_STAT_CACHE_POOL | RC_STAT_SPAN_POOL))
+		g->flush_pending = 1;
 	g->ahead = (g->ahead + 1) % RC_ASYNC_DEPTH; g->ainflight--;
 	return RC_OK;
 }
@@ -2404,7 +2447,7 @@ int rc_gpu_wait_host (rc_gpu_t *g, int *status, char *err, size_t errlen)
 int rc_gpu_present (rc_gpu_t *g, const uint32_t *pal32, int n, const void *fb, void *rgbx, void *stream, int host, char *err, size_t errlen)
 {
 	cudaSetDevice (g->device);
-	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	cudaStream_t s = host ? g->stream : (stream ? (cudaStream_t)stream : cudaStreamLegacy);	/* NULL: the legacy default stream */
 	const size_t px = (size_t)g->width * g->height;
 	if (n > g->palcap)
 	{
@@ -2475,7 +2518,7 @@ int rc_gpu_upload_draw2d (rc_gpu_t *g, const uint8_t *blob, size_t len, const vo
 int rc_gpu_draw2d (rc_gpu_t *g, const rc_draw2d_t *cmds, int ncmds, const int *first, int n, void *fb, void *stream, int host, char *err, size_t errlen)
 {
 	cudaSetDevice (g->device);
-	cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+	cudaStream_t s = host ? g->stream : (stream ? (cudaStream_t)stream : cudaStreamLegacy);	/* NULL: the legacy default stream */
 	const size_t px = (size_t)g->width * g->height;
 	if (!g->d_d2blob) { snprintf (err, errlen, "2D assets not uploaded"); return RC_ERR_ARG; }
 	if (ncmds > g->d2cmdcap || n + 1 > g->d2firstcap)

@@ -213,6 +213,9 @@ fail:
 }
 
 /* ------------------------------------------------------------------ light sampling ---- */
+/* a + (b - a) * frac / 16 with the reference's arithmetic shift */
+static int lerp16 (int a, int b, int frac) { return (((b - a) * frac) >> 4) + a; }
+
 /* RecursiveLightPoint, r_light.c:156-245 */
 static int light_point_r (const rc_world_t *w, const int *lsv, int node, const float *start, const float *end)
 {
@@ -263,22 +266,23 @@ static int light_point_r (const rc_world_t *w, const int *lsv, int node, const f
 		r = 0;
 		if (surf->lightofs != -1)
 		{
-			int maps, line, dsfrac = ds & 15, dtfrac = dt & 15, r00 = 0, r01 = 0, r10 = 0, r11 = 0;
-			float scale;
-			const unsigned char *lightmap;
-			line = (surf->extents[0] >> 4) + 1;
-			lightmap = w->lightdata + surf->lightofs + (dt>>4) * line + (ds>>4);
-			for (maps = 0; maps < RC_MAXLIGHTMAPS && surf->styles[maps] != 255; maps++)
+			/* the four luxels around (ds, dt), each the sum over the face's light styles (accumulated the way the
+			 * reference does: an int that takes a float product per style, truncating every time), then a bilinear
+			 * blend in 4-bit fixed point: along s on both rows, then along t (r_light.c:213-236) */
+			const int luxw = (surf->extents[0] >> 4) + 1, luxh = (surf->extents[1] >> 4) + 1;
+			const int corner[4] = { 0, 1, luxw, luxw + 1 };
+			const unsigned char *lm = w->lightdata + surf->lightofs + (dt >> 4) * luxw + (ds >> 4);
+			int acc[4] = { 0, 0, 0, 0 }, m, c, top, bottom;
+			for (m = 0; m < RC_MAXLIGHTMAPS && surf->styles[m] != 255; m++, lm += luxw * luxh)
 			{
-				int st = surf->styles[maps];
-				scale = (st < RC_MAX_LIGHTSTYLES ? lsv[st] : 0) * (1.0 / 256.0);
-				r00 += (float)lightmap[     0] * scale;
-				r01 += (float)lightmap[     1] * scale;
-				r10 += (float)lightmap[line+0] * scale;
-				r11 += (float)lightmap[line+1] * scale;
-				lightmap += line * ((surf->extents[1]>>4)+1);
+				const int style = surf->styles[m];
+				const float scale = (style < RC_MAX_LIGHTSTYLES ? lsv[style] : 0) * (1.0 / 256.0);
+				for (c = 0; c < 4; c++)
+					acc[c] += (float)lm[corner[c]] * scale;
 			}
-			r = ((int) ((((((((r11-r10) * dsfrac) >> 4) + r10)-((((r01-r00) * dsfrac) >> 4) + r00)) * dtfrac) >> 4) + ((((r01-r00) * dsfrac) >> 4) + r00)));
+			top = lerp16 (acc[0], acc[1], ds & 15);
+			bottom = lerp16 (acc[2], acc[3], ds & 15);
+			r = lerp16 (top, bottom, dt & 15);
 		}
 		return r;
 	}

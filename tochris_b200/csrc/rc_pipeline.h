@@ -53,6 +53,10 @@ static inline unsigned long long rc_host_cas_ull (unsigned long long *p, unsigne
 #define RC_ATOMIC_CAS_ULL(p, c, v) rc_host_cas_ull ((p), (c), (v))
 #endif
 
+/* a place where the reference itself reads or loops out of range (RC_STAT_ALIAS_RANGE): the status bit, and a count of
+ * the events in status word 1 so that tests can pin how often it happens */
+#define RC_ALIAS_RANGE_HIT(f) do { RC_ATOMIC_OR_I ((f)->status, RC_STAT_ALIAS_RANGE); RC_ATOMIC_ADD_I ((f)->status + 1, 1); } while (0)
+
 #define RC_FACEPOS_NONE    0xFFFFu   /* face not marked by any visited leaf */
 #define RC_FACEPOS_MARKED  0xFFFEu   /* marked (surf->visframe == r_framecount), not rendered */
 #define RC_MAX_FACE_EDGES  30        /* per face; slot 31 is the synthetic left-clip edge */
@@ -1467,6 +1471,16 @@ RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t 
 RC_HD void rc_scan_line (const rc_world_t *w, const rc_frame_t *f, int vi, int line)
 {
 	const rc_view_t *vw = &f->views[vi];
+	if (vw->rdflags & 1 /* RDF_NOWORLDMODEL */)
+	{
+		/* R_EdgeDrawing returns at once (r_main.c:889): no span, not even the background, is drawn; D_ViewChanged
+		 * has set the WHOLE z-buffer to 0xFFFF for the entities to test against (d_modech.c:103-106) */
+		rc_line_clear (f, vi, line);
+		if (f->zb)
+			for (int x = 0; x < f->width; x++)
+				f->zb[((size_t)vi * f->height + line) * f->width + x] = (int16_t)-1;
+		return;
+	}
 	if (line < vw->vrect_y || line >= vw->vrectbottom)
 	{
 		rc_line_clear (f, vi, line);
@@ -1752,7 +1766,11 @@ RC_HD void rc_surf_resolve (const rc_frame_t *f, int vi, int si)
 	if (!s->hasspans || s->flags == -1)
 		return;
 	if (s->pad == RC_SRC_POOL && s->miplevel >= 0)
+	{
 		s->cacheofs = f->cachevals[s->miplevel];
+		if (s->cacheofs == 0)
+			RC_ATOMIC_OR_I (f->status, RC_STAT_CACHE_POOL);
+	}
 }
 
 /* ------------------------------------------------------------- stage 5: cache build ---- */
@@ -1987,7 +2005,14 @@ RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_sub
 		 * stage, every other user of the same (face, mip, texture, light) key looks it up now */
 		int cacheofs = s.cacheofs;
 		if (s.srckind == RC_SRC_POOL && sfp->miplevel >= 0)
+		{
 			cacheofs = f->cachevals[sfp->miplevel];
+			/* 0 is never a valid block (the pool starts after the sky-box pictures): the block's creator -- in this
+			 * batch or an earlier one -- ran out of pool.  Every batch that meets such a key reports it, so the host
+			 * flushes the cache (D_FlushCaches) and the batch is drawn again */
+			if (cacheofs == 0)
+				RC_ATOMIC_OR_I (f->status, RC_STAT_CACHE_POOL);
+		}
 		uint32_t kind = RC_KIND_POOL;
 		if (s.srckind == RC_SRC_TEXELS) kind = (s.drawflags & RC_SURF_DRAWTURB) ? RC_KIND_TURB : RC_KIND_TEXELS;
 		else if (s.srckind == RC_SRC_SKY) kind = RC_KIND_SKY;
@@ -2683,7 +2708,7 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 	r_countextrastep = r_ubasestep + 1;
 	if (initialleftheight <= 0 || initialrightheight <= 0)
 	{
-		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		RC_ALIAS_RANGE_HIT (f);
 		return;
 	}
 	const int W = f->width, H = f->height;
@@ -2727,14 +2752,14 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 				l_segment = 2;
 				if (l_remaining <= 0)
 				{
-					RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+					RC_ALIAS_RANGE_HIT (f);
 					break;
 				}
 			}
 			else
 			{
 				/* the reference would read span packages left over from an earlier triangle */
-				RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+				RC_ALIAS_RANGE_HIT (f);
 				break;
 			}
 		}
@@ -2763,14 +2788,14 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 					int ti = lptex;
 					if ((unsigned)ti >= (unsigned)c->skinsize)
 					{
-						RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+						RC_ALIAS_RANGE_HIT (f);
 						RC_DEBUG_PRINT ("skin index %d out of %d (sub %d, x %d y %d)\n", ti, c->skinsize, sub, x, y);
 						ti = 0;
 					}
 					int ci = c->skin[ti] + (llight & 0xFF00);
 					if (ci >= 64 * 256)
 					{
-						RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+						RC_ALIAS_RANGE_HIT (f);
 						RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, llight);
 						ci &= 0x3FFF;
 					}
@@ -2779,7 +2804,7 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 					RC_ATOMIC_MAX_ULL (&c->zplane[(size_t)y * W + x], key);
 				}
 				else
-					RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+					RC_ALIAS_RANGE_HIT (f);
 				lzi = rc_addw (lzi, r_zistepx);
 				llight = rc_addw (llight, r_lstepx);
 				lptex += a_ststepxwhole;
@@ -2795,7 +2820,7 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 			}
 		}
 		else if (lcount < 0)
-			RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+			RC_ALIAS_RANGE_HIT (f);
 		/* D_PolysetScanLeftEdge step */
 		l_remaining--;
 		if (l_stepping)
@@ -3024,7 +3049,7 @@ RC_HD void rc_particle (const rc_frame_t *f, int pi)
 	const unsigned long long key = ((unsigned long long)(unsigned)(izi + 32768) << 48) |
 		((((unsigned long long)1 << 39) | (unsigned long long)p->order) << 8) | (unsigned long long)(p->color & 0xFF);
 	if (izi > 32767 || izi < -32768)
-		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		RC_ALIAS_RANGE_HIT (f);
 	for (int r = 0; r < rows; r++)
 		for (int i = 0; i < pix; i++)
 		{
@@ -3214,7 +3239,7 @@ RC_HD void rc_sprite_span (const rc_frame_t *f, int si, int k)
 	if (!haveleft)
 	{
 		/* the reference would read a span the left scan never wrote (stack garbage) */
-		RC_ATOMIC_OR_I (f->status, RC_STAT_ALIAS_RANGE);
+		RC_ALIAS_RANGE_HIT (f);
 		return;
 	}
 	if (span_count <= 0)

@@ -382,9 +382,11 @@ typedef struct {            /* one drawn brush entity of one view (R_DrawBEntiti
 #define RC_STAT_CACHE_POOL       32  /* surface cache pool too small (retried by the host) */
 #define RC_STAT_STALE_CLIPVERT   64  /* reference would read r_rightenter/r_rightexit left over from an earlier face */
 #define RC_STAT_FACELIST         128 /* face list capacity exceeded */
-#define RC_STAT_UNSUPPORTED_ENT   256 /* a sprite / brush entity was skipped (not built yet) */
-#define RC_STAT_ALIAS_RANGE       512
-#define RC_STAT_BMODEL_OVERFLOW   1024 /* brush entity clipping ran out of vertices/edges (reference: MAX_BMODEL_VERTS/EDGES) */ /* alias rasteriser hit a case where the reference reads/loops out of range */
+/* bit 256 is not used (it flagged entity kinds that were skipped before sprites and brush entities were built) */
+#define RC_STAT_ALIAS_RANGE       512  /* the entity rasterisers hit a case where the reference itself reads or loops out of range (clipped
+                                        * triangles stepping off the skin, d_polyse.c:385-447; span packages left by an earlier triangle;
+                                        * a particle 1/z outside 16 bits): those pixels are undefined in the reference.  rc_stats_t.alias_range_events counts them */
+#define RC_STAT_BMODEL_OVERFLOW   1024 /* brush entity clipping ran out of vertices/edges (reference: MAX_BMODEL_VERTS/EDGES) */
 
 #ifdef __cplusplus
 }
