@@ -276,6 +276,11 @@ void RC_SetProfiling (int on);
  * Returns the number of records written (<= cap) or a negative error. */
 int  RC_DebugRead (int kind, int view, void *dst, int cap);
 
+/* Test hook: the byte image ref_cuda keeps of a loaded alias model -- the block Mod_LoadAliasModel assembles
+ * (ref_soft/r_model.c:1349-1572) from `pheader` on, which the polygon rasteriser reads around the skin when clipped
+ * triangles step off the picture.  Returns its length and copies min (length, cap) bytes. */
+int  RC_DebugAliasImage (struct model_s *model, void *dst, int cap);
+
 /* north_star naming: a refexport_t-style table over the same functions. */
 typedef struct {
     int   api_version;

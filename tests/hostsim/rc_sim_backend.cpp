@@ -89,7 +89,8 @@ int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const floa
 		g->stverts.insert (g->stverts.end (), a->stverts, a->stverts + 4 * a->numverts);
 		g->atris.insert (g->atris.end (), a->tris, a->tris + 4 * a->numtris);
 		g->poseverts.insert (g->poseverts.end (), a->poseverts, a->poseverts + 4 * (size_t)a->numposes * a->numverts);
-		g->skinpixels.insert (g->skinpixels.end (), a->skinpixels, a->skinpixels + (size_t)a->numskinpics * a->skinwidth * a->skinheight);
+		m.skins_len = a->skinimagelen; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+		g->skinpixels.insert (g->skinpixels.end (), a->skinpixels, a->skinpixels + (size_t)a->skinimagelen);
 		g->amodels.push_back (m);
 		a->device_index = i;
 		if (a->numverts > g->maxverts) g->maxverts = a->numverts;

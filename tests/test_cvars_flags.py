@@ -27,7 +27,7 @@ def _run(case, lib, assets_dir, sim):
             assert np.array_equal(o["z"][i], r["z"][i]), (i, int((o["z"][i] != r["z"][i]).sum()))
         assert any(r["fb"][i].any() for i in range(len(specs))), "no entity pixel was drawn"
     else:
-        rcutil.assert_parity(o, r, specs, w, h)
+        rcutil.assert_parity(o, r, specs, w, h, allow_alias_range=False)
     return o, r, specs
 
 

@@ -51,7 +51,7 @@ def test_matches_oracle(assets_dir, oracle_available, scene, w, h, n, t0, dt, ex
     o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs, cvars=cvars)
     assert r["stats"]["kernel_launches"] > 0
-    rcutil.assert_parity(o, r, specs, w, h)
+    rcutil.assert_parity(o, r, specs, w, h, allow_alias_range=False)
 
 
 def test_golden_fixtures(assets_dir):
@@ -178,7 +178,7 @@ def test_sub_rectangles_match_oracle_gpu(assets_dir, oracle_available):
     specs = rcutil.scene_views("multi", 6, time=0.3, time_step=0.2)          # 324 is not a multiple of 8
     o = run_oracle.render(assets_dir, "maps/multi.bsp", 324, 202, specs)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, "maps/multi.bsp", 324, 202, specs)
-    rcutil.assert_parity(o, r, specs, 324, 202)
+    rcutil.assert_parity(o, r, specs, 324, 202, allow_alias_range=False)
 
 
 FUZZ = [
@@ -201,7 +201,7 @@ def test_fuzz_shapes_match_oracle(assets_dir, oracle_available, scene, w, h, n, 
     specs = rcutil.scene_views(scene, n, time=t0, time_step=dt)
     o = run_oracle.render(assets_dir, f"maps/{scene}.bsp", w, h, specs)
     r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
-    rcutil.assert_parity(o, r, specs, w, h)
+    rcutil.assert_parity(o, r, specs, w, h, allow_alias_range=False)
 
 
 @pytest.mark.parametrize("scene,w,h,n,kw", [("multi", 320, 240, 6, {}), ("multi", 640, 480, 4, dict(dlights=3)), ("full", 400, 300, 6, {})])

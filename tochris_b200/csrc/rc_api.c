@@ -258,7 +258,7 @@ static struct model_s *rc_load_model (const char *name)
 	}
 	if (len >= 4 && !memcmp (buf, "IDPO", 4))
 	{
-		rc_hostalias_t *a = RC_LoadAliasModel (buf, len, rc.err, sizeof(rc.err));
+		rc_hostalias_t *a = RC_LoadAliasModel (buf, len, name, rc.err, sizeof(rc.err));
 		free (buf);
 		if (!a) return NULL;
 		m = rc_new_model (name);
@@ -669,6 +669,15 @@ int RC_SetSkybox (const char *name)
 void RC_FlushCaches (void) { if (rc.gpu) rc_gpu_flush_caches (rc.gpu); }
 void RC_GetStats (rc_stats_t *out) { if (rc.gpu) rc_gpu_get_stats (rc.gpu, out); else memset (out, 0, sizeof(*out)); }
 void RC_SetProfiling (int on) { if (rc.gpu) rc_gpu_set_profiling (rc.gpu, on); }
+/* test hook: the memory image of a loaded alias model (the reference's cache block from `pheader` on, see
+ * rc_host_alias.c) -> its length; copies min (length, cap) bytes */
+int RC_DebugAliasImage (struct model_s *model, void *dst, int cap)
+{
+	if (!model || model->type != rc_mod_alias || !model->alias) return RC_ERR_ARG;
+	if (dst && cap > 0)
+		memcpy (dst, model->alias->skinpixels, (size_t)(cap < model->alias->skinimagelen ? cap : model->alias->skinimagelen));
+	return model->alias->skinimagelen;
+}
 int  RC_DebugRead (int kind, int view, void *dst, int cap) { return rc.gpu ? rc_gpu_debug_read (rc.gpu, kind, view, dst, cap) : RC_ERR_ARG; }
 
 /* R_BuildGammaTable, ref_soft/r_main.c:794-817 (libm pow on the host, as the reference) */

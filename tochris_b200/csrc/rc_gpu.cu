@@ -1679,7 +1679,8 @@ int rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const floa
 		stv.insert (stv.end (), a->stverts, a->stverts + 4 * a->numverts);
 		tri.insert (tri.end (), a->tris, a->tris + 4 * a->numtris);
 		pose.insert (pose.end (), a->poseverts, a->poseverts + 4 * (size_t)a->numposes * a->numverts);
-		skin.insert (skin.end (), a->skinpixels, a->skinpixels + (size_t)a->numskinpics * a->skinwidth * a->skinheight);
+		m.skins_len = a->skinimagelen; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+		skin.insert (skin.end (), a->skinpixels, a->skinpixels + (size_t)a->skinimagelen);
 		am.push_back (m);
 		a->device_index = i;
 		if (a->numverts > g->maxverts) g->maxverts = a->numverts;

@@ -64,7 +64,9 @@ typedef struct rc_hostalias_s {  /* aliashdr_t + mdl_t, flattened */
     int  *tris;                /* [numtris][4]: facesfront, v0, v1, v2 */
     unsigned char *poseverts;  /* [numposes][numverts] trivertx_t */
     unsigned char *posebbox;   /* [numposes][8] */
-    unsigned char *skinpixels; /* [numskinpics][skinwidth*skinheight] */
+    unsigned char *skinpixels; /* the reference's memory image of the loaded model, from `pheader` on (rc_alias_build_image) */
+    int   skinimagelen;        /* its length */
+    int  *skinpicofs;          /* [numskinpics]: offset of every skin picture inside the image */
     rc_aliasframe_t *frames, *skins;
     float *intervals;
     int   device_index;        /* slot in the device model table, -1 until uploaded */
@@ -112,7 +114,7 @@ rc_hostworld_t *RC_LoadBrushModel (const void *data, size_t len, const uint8_t *
 int  RC_ApplyLit (rc_hostworld_t *hw, const uint8_t *lit, size_t litlen);
 void RC_FreeHostWorld (rc_hostworld_t *hw);
 
-rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, char *err, size_t errlen);
+rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, const char *modelname, char *err, size_t errlen);
 void RC_FreeHostAlias (rc_hostalias_t *a);
 int  RC_LightPoint (const rc_hostworld_t *hw, const int *lightstylevalue, const float *p);
 int  RC_VisCullEntity (const rc_hostworld_t *hw, const float *vieworg, const float *mins, const float *maxs);

@@ -33,15 +33,17 @@
 typedef struct { int ident, version; float scale[3], scale_origin[3], boundingradius, eyeposition[3];
                  int numskins, skinwidth, skinheight, numverts, numtris, numframes, synctype, flags; float size; } mdl_t;
 
+static int rc_alias_build_image (rc_hostalias_t *a, const unsigned char *base, const char *modelname);
+
 void RC_FreeHostAlias (rc_hostalias_t *a)
 {
 	if (!a) return;
 	free (a->stverts); free (a->tris); free (a->poseverts); free (a->posebbox); free (a->skinpixels);
-	free (a->frames); free (a->skins); free (a->intervals);
+	free (a->frames); free (a->skins); free (a->intervals); free (a->skinpicofs);
 	free (a);
 }
 
-rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, char *err, size_t errlen)
+rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, const char *modelname, char *err, size_t errlen)
 {
 	const unsigned char *base = (const unsigned char *)data, *p, *end = base + len;
 	const mdl_t *in = (const mdl_t *)data;
@@ -206,6 +208,8 @@ rc_hostalias_t *RC_LoadAliasModel (const void *data, size_t len, char *err, size
 		}
 	}
 	a->device_index = -1;
+	if (!rc_alias_build_image (a, base, modelname ? modelname : "?"))
+		FAIL ("out of memory (model image)");
 	return a;
 fail:
 	RC_FreeHostAlias (a);
@@ -213,6 +217,185 @@ fail:
 }
 
 /* ------------------------------------------------------------------ light sampling ---- */
+/* ---- the reference's in-memory image of a loaded model -------------------------------------------
+ * D_PolysetDrawSpans8 indexes the skin with whatever the edge stepping produced: clipped triangles step up to a few
+ * texel rows off the picture (d_polyse.c:385-447), and the reference then reads its OWN model memory around the skin --
+ * the hunk header in front of it, the skin descriptors, the triangle and st-vertex arrays before that; the next
+ * allocation's header and the frame vertices behind it.  Those bytes decide pixels, so the device keeps, per model, the
+ * byte image of the block Mod_LoadAliasModel assembles (r_model.c:1349-1572): every Hunk_AllocName (common/zone.c:404:
+ * a 16-byte header {0x1df001ed, size, name[8]} + the size rounded up to 16, zero filled) in the reference's order,
+ * from `pheader` on, with the LP64 struct layouts of r_model.h:214-264 / modelgen.h:40-100.  Skin reads inside the image
+ * are then exact; only reads that leave the model's block altogether are still reported (RC_STAT_ALIAS_RANGE). */
+typedef struct { unsigned char *p; size_t len, cap; char name[8]; } rc_img_t;
+
+static size_t img_alloc (rc_img_t *im, size_t size)
+{
+	/* returns the offset of the block's payload relative to pheader (the first payload is offset 0) */
+	const size_t total = 16 + ((size + 15) & ~(size_t)15), at = im->len;
+	if (im->len + total > im->cap)
+	{
+		size_t ncap = (im->len + total) * 2 + 4096;
+		unsigned char *np = (unsigned char *)realloc (im->p, ncap);
+		if (!np) return (size_t)-1;
+		im->p = np; im->cap = ncap;
+	}
+	memset (im->p + at, 0, total);
+	{
+		const int sentinal = 0x1df001ed, sz = (int)total;
+		memcpy (im->p + at, &sentinal, 4); memcpy (im->p + at + 4, &sz, 4); memcpy (im->p + at + 8, im->name, 8);
+	}
+	im->len += total;
+	return at + 16 - 16;	/* the image starts at pheader = 16 bytes into the first block: offsets are (at + 16) - 16 */
+}
+#define IMG(im, ofs) ((im)->p + 16 + (ofs))		/* payload byte `ofs` (relative to pheader) */
+static void img_i32 (rc_img_t *im, size_t ofs, int v) { memcpy (IMG (im, ofs), &v, 4); }
+static void img_f32 (rc_img_t *im, size_t ofs, float v) { memcpy (IMG (im, ofs), &v, 4); }
+
+static int rc_alias_build_image (rc_hostalias_t *a, const unsigned char *base, const char *modelname)
+{
+	const mdl_t *in = (const mdl_t *)base;
+	const unsigned char *p = base + sizeof(mdl_t);
+	const int skinsize = a->skinwidth * a->skinheight;
+	const size_t FRAMEDESC = 32, SKINDESC = 24, GROUPFRAMEDESC = 16;	/* maliasframedesc_t, maliasskindesc_t (a pointer inside), maliasgroupframedesc_t */
+	rc_img_t im;
+	size_t hdr, pmodel, stv, tri, sd;
+	int i, j, pic = 0;
+
+	memset (&im, 0, sizeof(im));
+	{
+		/* loadname = COM_FileBase (mod->name), common/common.c:583-603; strncpy (h->name, name, 8) */
+		const char *s = modelname + strlen (modelname) - 1, *s2;
+		char basename[64];
+		while (s != modelname && *s != '.') s--;
+		for (s2 = s; s2 > modelname && *s2 != '/'; s2--) ;
+		if (*s2 != '/') s2 = modelname - 1;
+		if (s - s2 < 2) strcpy (basename, "?model?");
+		else { size_t n = (size_t)(s - 1 - s2); if (n > 63) n = 63; memcpy (basename, s2 + 1, n); basename[n] = 0; }
+		strncpy (im.name, basename, 8);
+	}
+	a->skinpicofs = (int *)calloc ((size_t)a->numskinpics + 1, sizeof(int));
+	if (!a->skinpicofs) return 0;
+	/* the header block: aliashdr_t + frames[numframes] + mdl_t + stverts + triangles */
+	hdr = img_alloc (&im, 16 + FRAMEDESC * a->numframes + sizeof(mdl_t) + 12 * (size_t)a->numverts + 16 * (size_t)a->numtris);
+	if (hdr == (size_t)-1) return 0;
+	pmodel = 16 + FRAMEDESC * a->numframes; stv = pmodel + sizeof(mdl_t); tri = stv + 12 * (size_t)a->numverts;
+	img_i32 (&im, 0, (int)pmodel); img_i32 (&im, 4, (int)stv); img_i32 (&im, 12, (int)tri);
+	{
+		/* the mdl_t fields the loader sets (r_model.c:1392-1426); ident, version, synctype and flags stay 0 */
+		mdl_t m;
+		memset (&m, 0, sizeof(m));
+		m.boundingradius = in->boundingradius; m.numskins = in->numskins; m.skinwidth = in->skinwidth; m.skinheight = in->skinheight;
+		m.numverts = in->numverts; m.numtris = in->numtris; m.numframes = in->numframes;
+		m.size = in->size * (1.0 / 11.0);		/* ALIAS_BASE_SIZE_RATIO, modelgen.h:34 */
+		for (i = 0; i < 3; i++) { m.scale[i] = in->scale[i]; m.scale_origin[i] = in->scale_origin[i]; m.eyeposition[i] = in->eyeposition[i]; }
+		memcpy (IMG (&im, pmodel), &m, sizeof(m));
+	}
+	/* skins: the descriptor array, then per skin its pixels (a group: group struct, intervals, pictures) */
+	sd = img_alloc (&im, SKINDESC * a->numskins);
+	if (sd == (size_t)-1) return 0;
+	img_i32 (&im, 8, (int)sd);
+	for (i = 0; i < a->numskins; i++)
+	{
+		const int type = *(const int *)p; p += 4;
+		img_i32 (&im, sd + SKINDESC * i, type);
+		if (type == 0)
+		{
+			const size_t o = img_alloc (&im, skinsize);
+			if (o == (size_t)-1) return 0;
+			memcpy (IMG (&im, o), p, skinsize); p += skinsize;
+			img_i32 (&im, sd + SKINDESC * i + 16, (int)o);
+			a->skinpicofs[pic++] = (int)o;
+		}
+		else
+		{
+			const int n = *(const int *)p;
+			size_t g, iv;
+			p += 4;
+			g = img_alloc (&im, 8 + SKINDESC * n);		/* maliasskingroup_t + (n - 1) skindescs */
+			iv = g == (size_t)-1 ? g : img_alloc (&im, 4 * (size_t)n);
+			if (iv == (size_t)-1) return 0;
+			img_i32 (&im, sd + SKINDESC * i + 16, (int)g);
+			img_i32 (&im, g, n); img_i32 (&im, g + 4, (int)iv);
+			for (j = 0; j < n; j++) img_f32 (&im, iv + 4 * j, *(const float *)(p + 4 * j));
+			p += 4 * (size_t)n;
+			for (j = 0; j < n; j++)
+			{
+				const size_t o = img_alloc (&im, skinsize);
+				if (o == (size_t)-1) return 0;
+				memcpy (IMG (&im, o), p, skinsize); p += skinsize;
+				img_i32 (&im, g + 8 + SKINDESC * j + 16, (int)o);
+				a->skinpicofs[pic++] = (int)o;
+			}
+		}
+	}
+	/* st vertices (s and t in 16.16) and triangles */
+	for (i = 0; i < a->numverts; i++)
+	{
+		const int *sv = (const int *)p + 3 * i;
+		img_i32 (&im, stv + 12 * i, sv[0]); img_i32 (&im, stv + 12 * i + 4, sv[1] << 16); img_i32 (&im, stv + 12 * i + 8, sv[2] << 16);
+	}
+	p += 12 * (size_t)a->numverts;
+	memcpy (IMG (&im, tri), p, 16 * (size_t)a->numtris);
+	p += 16 * (size_t)a->numtris;
+	/* frames: descriptor in the header block; vertices (a group: group struct, intervals, vertices per pose) in their own blocks */
+	for (i = 0; i < a->numframes; i++)
+	{
+		const size_t fd = 16 + FRAMEDESC * i;
+		const int type = *(const int *)p; p += 4;
+		img_i32 (&im, fd, type);
+		if (type == 0)
+		{
+			size_t o;
+			strcpy ((char *)IMG (&im, fd + 16), (const char *)(p + 8));	/* strcpy (name, pdaliasframe->name) */
+			memcpy (IMG (&im, fd + 4), p, 3); memcpy (IMG (&im, fd + 8), p + 4, 3);	/* bboxmin.v, bboxmax.v (not lightnormalindex) */
+			o = img_alloc (&im, 4 * (size_t)a->numverts);
+			if (o == (size_t)-1) return 0;
+			memcpy (IMG (&im, o), p + 24, 4 * (size_t)a->numverts);
+			img_i32 (&im, fd + 12, (int)o);
+			p += 24 + 4 * (size_t)a->numverts;
+		}
+		else
+		{
+			const int n = *(const int *)p;
+			size_t g, iv;
+			g = img_alloc (&im, 8 + GROUPFRAMEDESC * n);	/* maliasgroup_t + (n - 1) frames */
+			if (g == (size_t)-1) return 0;
+			img_i32 (&im, g, n);
+			memcpy (IMG (&im, fd + 4), p + 4, 3); memcpy (IMG (&im, fd + 8), p + 8, 3);
+			img_i32 (&im, fd + 12, (int)g);
+			p += 12;
+			iv = img_alloc (&im, 4 * (size_t)n);
+			if (iv == (size_t)-1) return 0;
+			img_i32 (&im, g + 4, (int)iv);
+			for (j = 0; j < n; j++) img_f32 (&im, iv + 4 * j, *(const float *)(p + 4 * j));
+			p += 4 * (size_t)n;
+			for (j = 0; j < n; j++)
+			{
+				const size_t gf = g + 8 + GROUPFRAMEDESC * j;
+				size_t o;
+				img_i32 (&im, gf + 12, n);
+				strcpy ((char *)IMG (&im, fd + 16), (const char *)(p + 8));	/* every pose's name lands in the frame's name field */
+				memcpy (IMG (&im, gf), p, 3); memcpy (IMG (&im, gf + 4), p + 4, 3);
+				o = img_alloc (&im, 4 * (size_t)a->numverts);
+				if (o == (size_t)-1) return 0;
+				memcpy (IMG (&im, o), p + 24, 4 * (size_t)a->numverts);
+				img_i32 (&im, gf + 8, (int)o);
+				p += 24 + 4 * (size_t)a->numverts;
+			}
+		}
+	}
+	/* the image handed to the device starts at pheader and ends with the last block (the cache copy takes 16 bytes more,
+	 * whatever the hunk held behind the model: not part of it) */
+	free (a->skinpixels);
+	a->skinpixels = (unsigned char *)malloc (im.len - 16 + 16);
+	if (!a->skinpixels) { free (im.p); return 0; }
+	memcpy (a->skinpixels, im.p + 16, im.len - 16);
+	memset (a->skinpixels + im.len - 16, 0, 16);
+	a->skinimagelen = (int)(im.len - 16);
+	free (im.p);
+	return 1;
+}
+
 /* a + (b - a) * frac / 16 with the reference's arithmetic shift */
 static int lerp16 (int a, int b, int frac) { return (((b - a) * frac) >> 4) + a; }
 
@@ -561,7 +744,7 @@ int RC_AliasSetup (const rc_hostalias_t *a, const rc_hostworld_t *hw, const enti
 					break;
 			pic = sk->first + i;
 		}
-		out->skin = pic;	/* relative to the model's first skin; made absolute at upload */
+		out->skin = a->skinpicofs[pic];	/* offset of the picture inside the model's image (the device adds the image's base) */
 	}
 	alias_transform (a, e, v, modelorg, trivial_accept, xf);
 	memcpy (out->xf, xf, sizeof(xf));

@@ -2525,7 +2525,7 @@ typedef struct {
 	const uint8_t *skin;
 	const uint8_t *colormap;
 	unsigned long long *zplane;
-	int skinwidth, skinsize, seamfixupX16;
+	int skinwidth, skinlo, skinhi, seamfixupX16;	/* texel indices skinlo .. skinhi-1 (relative to the picture) lie inside the model's image */
 	unsigned long long orderbits;	/* (order << 8), OR-ed under the z and over the colour */
 } rc_polyctx_t;
 
@@ -2786,10 +2786,11 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 				if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
 				{
 					int ti = lptex;
-					if ((unsigned)ti >= (unsigned)c->skinsize)
+					if (ti < c->skinlo || ti >= c->skinhi)
 					{
+						/* outside the model's whole memory block: the reference reads a neighbour on its heap */
 						RC_ALIAS_RANGE_HIT (f);
-						RC_DEBUG_PRINT ("skin index %d out of %d (sub %d, x %d y %d)\n", ti, c->skinsize, sub, x, y);
+						RC_DEBUG_PRINT ("skin index %d outside the model image %d .. %d (sub %d, x %d y %d)\n", ti, c->skinlo, c->skinhi, sub, x, y);
 						ti = 0;
 					}
 					int ci = c->skin[ti] + (llight & 0xFF00);
@@ -2950,10 +2951,10 @@ RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti)
 	const rc_finalvert_t *pfv = f->finalverts + in->vertbase;
 	rc_polyctx_t c;
 	c.f = f; c.vw = vw;
-	c.skin = f->skinpixels + m->skins_ofs + (size_t)in->skin * m->skinwidth * m->skinheight;
+	c.skin = f->skinpixels + m->skins_ofs + in->skin;
 	c.colormap = f->colormaps + (size_t)in->colormap * 16384;
 	c.zplane = f->zres + (size_t)vw->zres_index * f->width * f->height;
-	c.skinwidth = m->skinwidth; c.skinsize = m->skinwidth * m->skinheight;
+	c.skinwidth = m->skinwidth; c.skinlo = -in->skin; c.skinhi = m->skins_len - in->skin;
 	c.seamfixupX16 = (m->skinwidth >> 1) << 16;
 	c.orderbits = (((unsigned long long)in->order << 24) | ((unsigned long long)ti << 8)) << 8;
 	const rc_finalvert_t *a = &pfv[tri[1]], *b = &pfv[tri[2]], *d = &pfv[tri[3]];

@@ -294,8 +294,11 @@ typedef struct {            /* one loaded model's slices of the shared device bl
     int stverts_ofs;        /* into stverts[] (int4: onseam, s<<16, t<<16, 0) */
     int tris_ofs;           /* into tris[] (int4: facesfront, v0, v1, v2) */
     int poses_ofs;          /* into poseverts[] (trivertx_t, 4 B each); pose p at poses_ofs + p*numverts */
-    int skins_ofs;          /* into skinpixels[]; skin k at skins_ofs + k*skinwidth*skinheight */
-} rc_aliasmodel_t;          /* 32 B */
+    int skins_ofs;          /* into skinpixels[]: start of the model's memory image (the reference's cache block from `pheader` on,
+                             * rc_host_alias.c rc_alias_build_image); rc_aliasinst_t.skin is the picture's offset inside it */
+    int skins_len;          /* length of that image: skin reads that stay inside it are the reference's own out-of-picture reads */
+    int pad[3];
+} rc_aliasmodel_t;          /* 48 B */
 
 typedef struct {            /* one drawn alias entity of one view (host-prepared: R_DrawAliasModel, r_alias.c:734-788) */
     int   view;
@@ -308,7 +311,7 @@ typedef struct {            /* one drawn alias entity of one view (host-prepared
     int   shadequant;       /* row of r_avertexnormal_dots */
     float framelerp;
     int   pose_old, pose_new;
-    int   skin;             /* absolute offset of the skin in skinpixels[] */
+    int   skin;             /* offset of the skin picture inside the model's image (rc_aliasmodel_t.skins_ofs) */
     float ziscale;
     int   colormap;         /* index of the entity colormap in the batch's colormap table (0 = vid.colormap) */
     int   vertbase;         /* first finalvert of this instance in the batch pool */
