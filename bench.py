@@ -206,7 +206,10 @@ def run_ours(args):
                 dist.gather(fb[first:first + num], gbufs.get(first), dst=0)
         r.set_group_callback(on_group, side.cuda_stream, 4)
     l2flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # an explicit non-default stream carries the L2 flush, the timing events and the render, in that order (a NULL stream
+    # means the legacy default stream to RC_RenderViewsDevice, and CUDA graphs cannot be captured there)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     px = n * W * H
 
     def step(timed_events=None):

@@ -329,7 +329,7 @@ int RC_LoadWorld (const char *name)
 /* ---- rendering --------------------------------------------------------------------------- */
 static int rc_prepare_views (const refdef_t *views, int n)
 {
-	int i, j, rcode, ndl, nwarp = 0, nbent_total = 0, nbents = 0, maxbfaces = 0;
+	int i, j, ndl, nwarp = 0, nbent_total = 0, nbents = 0, maxbfaces = 0;
 	if (!rc.inited) return rc_fail (RC_ERR_ARG, "RC_Init first");
 	if (!views || n <= 0) return rc_fail (RC_ERR_ARG, "no views");
 	if (n > rc.viewscratchcap)
@@ -363,15 +363,32 @@ static int rc_prepare_views (const refdef_t *views, int n)
 		rc.dlscratchcap = rc.dlscratch ? ndl : 0;
 		if (!rc.dlscratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
 	}
+	/* per-view constants (R_SetupFrame / R_ViewChanged: libm, the view leaf's BSP descent): views are independent, so
+	 * large batches (BASELINE config C4: 65,536 views per call) are set up by all the host threads -- same arithmetic per
+	 * view, any order */
+	{
+		int bad = -1, badcode = RC_OK;
+		#pragma omp parallel for schedule(static) if (n >= 512)
+		for (i = 0; i < n; i++)
+		{
+			rc_view_t *v = &rc.viewscratch[i];
+			int code = RC_SetupView (&views[i], &rc.vid, &rc.cvars, v);
+			if (code != RC_OK)
+			{
+				#pragma omp critical
+				{ if (bad < 0 || i < bad) { bad = i; badcode = code; } }
+				continue;
+			}
+			v->viewleaf = (rc.world && !(views[i].flags & RDF_NOWORLDMODEL)) ? RC_PointInLeaf (rc.world->world, views[i].vieworg) : -1;
+		}
+		if (bad >= 0) return rc_fail (badcode, "view %d: bad refdef rectangle", bad);
+	}
 	ndl = 0;
 	for (i = 0; i < n; i++)
 	{
 		rc_view_t *v = &rc.viewscratch[i];
 		if (!rc.world && !(views[i].flags & RDF_NOWORLDMODEL))
 			return rc_fail (RC_ERR_NOWORLD, "R_RenderView: NULL worldmodel");	/* r_main.c:1003 */
-		rcode = RC_SetupView (&views[i], &rc.vid, &rc.cvars, v);
-		if (rcode != RC_OK) return rc_fail (rcode, "view %d: bad refdef rectangle", i);
-		v->viewleaf = (rc.world && !(views[i].flags & RDF_NOWORLDMODEL)) ? RC_PointInLeaf (rc.world->world, views[i].vieworg) : -1;
 		if (views[i].num_dlights > MAX_DLIGHTS)
 			return rc_fail (RC_ERR_ARG, "view %d: more than %d dlights", i, MAX_DLIGHTS);
 		if (v->dowarp)

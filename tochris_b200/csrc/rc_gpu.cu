@@ -95,6 +95,7 @@ struct rc_gpu_s {
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
 	int slow_in_ends;
+	int scan_serial;
 	int front_512;			/* RC_FRONT_512: keep 512-thread front-end CTAs on many-view batches (experiment knob) */
 	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
 	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
@@ -452,6 +453,7 @@ struct scan_warp_t {			/* per-warp shared memory */
 		struct { unsigned long long ku[AET]; uint16_t kidx[AET]; } k;	/* B1/B2: unsorted keys: u (biased) << 32 | step code */
 		struct { int16_t x0[SPANS], x1[SPANS]; uint16_t sf[SPANS]; } sp;	/* B3/C: change points, spans */
 	} a;
+	unsigned long long klo[32];	/* B1/B2, lines with <= 32 active edges: the low half of the 128-bit order key (rc_aet_make) */
 	int      su[SPANS];		/* sorted: u (12.20); at publish time: first segment of every span */
 	uint32_t ss[AET];		/* sorted: surfs[0] | surfs[1] << 16 */
 	int      lkey[SCAN_LEADS], tcount[SCAN_LEADS];
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	{
 		const int c = base + lane;
 		bool act = false;
-		unsigned long long key = 0ull;
+		unsigned long long key = 0ull, klo = 0ull;
 		if (c < ncand)
 		{
 			const uint32_t vv = sh->c_vv[c];
@@ -569,6 +571,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 				}
 				act = true;
 				key = ((unsigned long long)(((uint32_t)sh->c_u[c] + (uint32_t)(line - v) * step) ^ 0x80000000u) << 32) | code;
+				/* the low half (rc_aet_make): later start line first, then the newedges[] order */
+				const uint32_t rk = sh->c_rank[c];
+				klo = ((unsigned long long)((uint32_t)(~v) & 0xFFFFu) << 32) | ((rk >> 31) ? rk : (~rk & 0x7FFFFFFFu));
 			}
 		}
 		const unsigned m = __ballot_sync (0xFFFFFFFFu, act);
@@ -576,6 +581,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		if (act && pos < AET)
 		{
 			sw->a.k.ku[pos] = key; sw->a.k.kidx[pos] = (uint16_t)c;
+			if (pos < 32) sw->klo[pos] = klo;
 		}
 		n += __popc (m);
 	}
@@ -586,157 +592,280 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	}
 	__syncwarp ();
 
-	/* ---- B2: rank sort (keys are unique) ---- */
-	for (int i = lane; i < n; i += 32)
-	{
-		const unsigned long long ui = sw->a.k.ku[i];
-		int rank = 0;
-		for (int j = 0; j < n; j++)
-		{
-			const unsigned long long uj = sw->a.k.ku[j];
-			rank += (uj < ui) ? 1 : 0;
-			if (uj == ui && j != i)
-			{
-				/* same u and step: start line and emission order decide (rare) */
-				unsigned long long hi_i, lo_i, hi_j, lo_j;
-				scan_full_key (sh, sw->a.k.kidx[i], line, &hi_i, &lo_i);
-				scan_full_key (sh, sw->a.k.kidx[j], line, &hi_j, &lo_j);
-				rank += (lo_j < lo_i) ? 1 : 0;
-			}
-		}
-		sw->su[rank] = (int)((uint32_t)(ui >> 32) ^ 0x80000000u);
-		sw->ss[rank] = sh->c_sf[sw->a.k.kidx[i]];
-	}
-	__syncwarp ();
-
-	/* ---- B3: spans ---- */
 	rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
 	const int head_u = vw->vrect_x, tail_u = vw->vrectright;
 	bool fallback = false;
-	int m = 0, nsp = 0;
-	for (int base = 0; base < n; base += 32)
+	int nsp = 0;
+	if (n <= 32)
 	{
-		const int k = base + lane;
-		int s1 = 0, key = 0, insub = 0;
-		if (k < n)
+		/* ---- the common case, one edge per lane, everything after the sort in registers ----
+		 * B2  rank sort on the 64-bit key (uniform shared-memory reads of the other keys); exact ties take the full key
+		 * B3  pairing: every trailing edge finds the lane of its surface's leading edge by a bit-sliced comparison of
+		 *     the 16-bit surface numbers (one ballot per bit); duplicates by match.any.  Lead k toggles bit k, its
+		 *     trailing edge toggles the same bit; the inclusive XOR scan is the set of active leads after every edge,
+		 *     the top of the reference's stack is the member with the smallest BSP key (unique for world surfaces).
+		 *     Change points -> runs -> spans as below.  Anything the model does not cover (brush-entity surfaces, a
+		 *     surface with two leading or two trailing edges, a trailing edge before / without its leading edge) is
+		 *     walked by lane 0 with the reference's own algorithm. */
+		const unsigned long long ui = lane < n ? sw->a.k.ku[lane] : ~0ull;
+		const int myc = lane < n ? (int)sw->a.k.kidx[lane] : 0;
+		/* rank by u alone (32-bit compares), then the edges that share their u -- twin edges are common: a clipped
+		 * shared edge is emitted once per face -- order themselves inside their group by the rest of the key
+		 * (step code, start line, emission order: unique per edge) */
+		const uint32_t u32 = (uint32_t)(ui >> 32);
+		const uint32_t *ku32 = reinterpret_cast<const uint32_t *>(sw->a.k.ku);
+		int rank = 0;
+		for (int j = 0; j < n; j++)
+			rank += (ku32[2 * j + 1] < u32) ? 1 : 0;
 		{
-			s1 = (int)(sw->ss[k] >> 16);
-			if (s1)
+			unsigned grp = 0u;
+			if (lane < n)
+				grp = __match_any_sync (n == 32 ? 0xFFFFFFFFu : (1u << n) - 1u, u32) & ~(1u << lane);
+			if (grp)
 			{
-				const int4 g = *reinterpret_cast<const int4 *>(&surfs[s1]);	/* key, flags, face, insubmodel */
-				key = g.x; insub = g.w;
-			}
-		}
-		if (insub) fallback = true;
-		const unsigned mask = __ballot_sync (0xFFFFFFFFu, s1 != 0);
-		const int pos = m + __popc (mask & lt);
-		if (s1)
-		{
-			if (pos < SCAN_LEADS)
-			{
-				sw->lkey[pos] = key; sw->lsurf[pos] = (uint16_t)s1; sw->lk[pos] = (uint8_t)k;
-			}
-			sw->lidx[k] = (uint8_t)(pos < SCAN_LEADS ? pos : 0);
-		}
-		m += __popc (mask);
-	}
-	if (m > SCAN_LEADS) fallback = true;
-	fallback = __any_sync (0xFFFFFFFFu, fallback);
-	__syncwarp ();
-	if (!fallback)
-	{
-		/* rank of every leading surface by key */
-		for (int i = lane; i < m; i += 32)
-		{
-			const int ki = sw->lkey[i];
-			int r = 0;
-			for (int j = 0; j < m; j++)
-			{
-				const int kj = sw->lkey[j];
-				r += (kj < ki) ? 1 : 0;
-				if (kj == ki && j != i) fallback = true;	/* a second leading edge of the same surface */
-			}
-			sw->lrank[i] = (uint8_t)r;
-			sw->rsurf[r] = sw->lsurf[i];
-			sw->tcount[i] = 0;
-		}
-		fallback = __any_sync (0xFFFFFFFFu, fallback);
-		__syncwarp ();
-	}
-	if (!fallback)
-	{
-		/* toggles, XOR scan, top surface after every edge, change points (x0 / sf reuse the key area) */
-		unsigned long long carry = 0ull;
-		int prevtop = 1, nc = 1;
-		if (lane == 0) { sw->a.sp.x0[0] = (int16_t)head_u; sw->a.sp.sf[0] = 1; }
-		for (int base = 0; base < n; base += 32)
-		{
-			const int k = base + lane;
-			unsigned long long tog = 0ull;
-			int iu = 0;
-			if (k < n)
-			{
-				const uint32_t sfk = sw->ss[k];
-				const int s0 = (int)(sfk & 0xFFFF), s1 = (int)(sfk >> 16);
-				iu = sw->su[k] >> 20;
-				if (s1)
-					tog ^= 1ull << sw->lrank[sw->lidx[k]];
-				if (s0)
+				const uint32_t ci = (uint32_t)ui;
+				const unsigned long long li = sw->klo[lane];
+				for (; grp; grp &= grp - 1u)
 				{
-					int found = -1;
-					for (int j = 0; j < m; j++)
-						if (sw->lsurf[j] == s0) found = j;
-					if (found < 0 || (int)sw->lk[found] >= k)
-						fallback = true;		/* trailing edge without / before its leading edge */
-					else
-					{
-						tog ^= 1ull << sw->lrank[found];
-						atomicAdd (&sw->tcount[found], 1);
-					}
+					const int j = __ffs (grp) - 1;
+					const uint32_t cj = ku32[2 * j];
+					rank += (cj < ci || (cj == ci && sw->klo[j] < li)) ? 1 : 0;
 				}
 			}
-			unsigned long long v = tog;
-			#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const unsigned long long t = __shfl_up_sync (0xFFFFFFFFu, v, o);
-				if (lane >= o) v ^= t;
-			}
-			v ^= carry;
-			carry = __shfl_sync (0xFFFFFFFFu, v, 31);
-			const int top = v ? (int)sw->rsurf[__ffsll ((long long)v) - 1] : 1;
-			int pt = __shfl_up_sync (0xFFFFFFFFu, top, 1);
-			if (lane == 0) pt = prevtop;
-			prevtop = __shfl_sync (0xFFFFFFFFu, top, 31);
-			const bool chg = k < n && top != pt;
-			const unsigned mask = __ballot_sync (0xFFFFFFFFu, chg);
-			const int pos = nc + __popc (mask & lt);
-			if (chg) { sw->a.sp.x0[pos] = (int16_t)iu; sw->a.sp.sf[pos] = (uint16_t)top; }
-			nc += __popc (mask);
+		}
+		if (lane < n)
+		{
+			sw->su[rank] = (int)((uint32_t)(ui >> 32) ^ 0x80000000u);
+			sw->ss[rank] = sh->c_sf[myc];
 		}
 		__syncwarp ();
-		for (int i = lane; i < m; i += 32)
-			if (sw->tcount[i] > 1) fallback = true;			/* two trailing edges of one surface */
+		const int uk = lane < n ? sw->su[lane] : 0;
+		const uint32_t sfk = lane < n ? sw->ss[lane] : 0u;
+		const uint32_t s0 = sfk & 0xFFFFu, s1 = sfk >> 16;
+		int key = 0x7FFFFFFF;
+		if (s1)
+		{
+			const int4 g = *reinterpret_cast<const int4 *>(&surfs[s1]);	/* key, flags, face, insubmodel */
+			key = g.x;
+			fallback = g.w != 0;
+		}
+		sw->lkey[lane] = key;
+		/* duplicates: two leading (trailing) edges of one surface */
+		const unsigned dl = __match_any_sync (0xFFFFFFFFu, s1 ? s1 : 0x10000u + lane);
+		const unsigned dt = __match_any_sync (0xFFFFFFFFu, s0 ? s0 : 0x10000u + lane);
+		if ((dl & (dl - 1)) | (dt & (dt - 1)))
+			fallback = true;
+		/* lanes whose leading surface is my trailing surface */
+		unsigned eq = __ballot_sync (0xFFFFFFFFu, s1 != 0);
+		const unsigned anyid = __reduce_or_sync (0xFFFFFFFFu, s0 | s1);
+		for (unsigned b = 0; (anyid >> b) != 0; b++)
+		{
+			const unsigned lb = __ballot_sync (0xFFFFFFFFu, (s1 >> b) & 1u);
+			eq &= lb ^ (((s0 >> b) & 1u) - 1u);
+		}
+		int lpos = 0;
+		if (s0)
+		{
+			if (eq == 0u || (int)(__ffs (eq) - 1) >= lane)
+				fallback = true;		/* a trailing edge without / before its leading edge */
+			lpos = eq ? __ffs (eq) - 1 : 0;
+		}
 		fallback = __any_sync (0xFFFFFFFFu, fallback);
 		if (!fallback)
 		{
-			/* runs between change points -> spans, empty runs dropped (in place: writes never pass reads) */
-			for (int base = 0; base < nc; base += 32)
+			unsigned v = (s1 ? 1u << lane : 0u) ^ (s0 ? 1u << lpos : 0u);
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
 			{
-				const int j = base + lane;
-				int st = 0, en = 0, sf = 0;
-				bool valid = false;
-				if (j < nc)
+				const unsigned t = __shfl_up_sync (0xFFFFFFFFu, v, o);
+				if (lane >= o) v ^= t;
+			}
+			/* the active lead with the smallest key (the stack is a few surfaces deep) */
+			int best = 0x7FFFFFFF, bl = -1;
+			for (unsigned bits = v; bits; bits &= bits - 1u)
+			{
+				const int j = __ffs (bits) - 1;
+				const int kj = sw->lkey[j];
+				if (kj < best) { best = kj; bl = j; }
+			}
+			const int top = bl < 0 ? 1 : (int)(sw->ss[bl] >> 16);
+			int pt = __shfl_up_sync (0xFFFFFFFFu, top, 1);
+			if (lane == 0) pt = 1;
+			const bool chg = lane < n && top != pt;
+			const unsigned cm = __ballot_sync (0xFFFFFFFFu, chg);
+			/* a change point starts a run that ends at the next change point (the line's end after the last one); the
+			 * head run starts at the left edge of the view with the background on top; empty runs are dropped */
+			const int iu = uk >> 20;
+			const unsigned above = lane == 31 ? 0u : cm & ~((2u << lane) - 1u);
+			const int nxt = above ? __ffs (above) - 1 : 0, first = cm ? __ffs (cm) - 1 : 0;
+			int en = __shfl_sync (0xFFFFFFFFu, iu, nxt), hen = __shfl_sync (0xFFFFFFFFu, iu, first);
+			if (!above) en = tail_u;
+			if (!cm) hen = tail_u;
+			const bool valid = chg && en > iu;
+			const int hvalid = hen > head_u ? 1 : 0;
+			const unsigned vm = __ballot_sync (0xFFFFFFFFu, valid);
+			nsp = hvalid + __popc (vm);
+			__syncwarp ();		/* a.sp shares its memory with the key arrays read above */
+			if (valid)
+			{
+				const int pos = hvalid + __popc (vm & lt);
+				sw->a.sp.x0[pos] = (int16_t)iu; sw->a.sp.x1[pos] = (int16_t)en; sw->a.sp.sf[pos] = (uint16_t)top;
+			}
+			if (lane == 0 && hvalid) { sw->a.sp.x0[0] = (int16_t)head_u; sw->a.sp.x1[0] = (int16_t)hen; sw->a.sp.sf[0] = 1; }
+			__syncwarp ();
+		}
+	}
+	else
+	{
+		/* ---- B2: rank sort (keys are unique) ---- */
+		for (int i = lane; i < n; i += 32)
+		{
+			const unsigned long long ui = sw->a.k.ku[i];
+			int rank = 0;
+			for (int j = 0; j < n; j++)
+			{
+				const unsigned long long uj = sw->a.k.ku[j];
+				rank += (uj < ui) ? 1 : 0;
+				if (uj == ui && j != i)
 				{
-					st = sw->a.sp.x0[j]; en = (j + 1 < nc) ? (int)sw->a.sp.x0[j + 1] : tail_u; sf = sw->a.sp.sf[j];
-					valid = en > st;
+					/* same u and step: start line and emission order decide (rare) */
+					unsigned long long hi_i, lo_i, hi_j, lo_j;
+					scan_full_key (sh, sw->a.k.kidx[i], line, &hi_i, &lo_i);
+					scan_full_key (sh, sw->a.k.kidx[j], line, &hi_j, &lo_j);
+					rank += (lo_j < lo_i) ? 1 : 0;
 				}
-				__syncwarp ();
-				const unsigned mask = __ballot_sync (0xFFFFFFFFu, valid);
-				const int pos = nsp + __popc (mask & lt);
-				if (valid) { sw->a.sp.x0[pos] = (int16_t)st; sw->a.sp.x1[pos] = (int16_t)en; sw->a.sp.sf[pos] = (uint16_t)sf; }
-				nsp += __popc (mask);
-				__syncwarp ();
+			}
+			sw->su[rank] = (int)((uint32_t)(ui >> 32) ^ 0x80000000u);
+			sw->ss[rank] = sh->c_sf[sw->a.k.kidx[i]];
+		}
+		__syncwarp ();
+
+		/* ---- B3: spans ---- */
+		int m = 0;
+		for (int base = 0; base < n; base += 32)
+		{
+			const int k = base + lane;
+			int s1 = 0, key = 0, insub = 0;
+			if (k < n)
+			{
+				s1 = (int)(sw->ss[k] >> 16);
+				if (s1)
+				{
+					const int4 g = *reinterpret_cast<const int4 *>(&surfs[s1]);	/* key, flags, face, insubmodel */
+					key = g.x; insub = g.w;
+				}
+			}
+			if (insub) fallback = true;
+			const unsigned mask = __ballot_sync (0xFFFFFFFFu, s1 != 0);
+			const int pos = m + __popc (mask & lt);
+			if (s1)
+			{
+				if (pos < SCAN_LEADS)
+				{
+					sw->lkey[pos] = key; sw->lsurf[pos] = (uint16_t)s1; sw->lk[pos] = (uint8_t)k;
+				}
+				sw->lidx[k] = (uint8_t)(pos < SCAN_LEADS ? pos : 0);
+			}
+			m += __popc (mask);
+		}
+		if (m > SCAN_LEADS) fallback = true;
+		fallback = __any_sync (0xFFFFFFFFu, fallback);
+		__syncwarp ();
+		if (!fallback)
+		{
+			/* rank of every leading surface by key */
+			for (int i = lane; i < m; i += 32)
+			{
+				const int ki = sw->lkey[i];
+				int r = 0;
+				for (int j = 0; j < m; j++)
+				{
+					const int kj = sw->lkey[j];
+					r += (kj < ki) ? 1 : 0;
+					if (kj == ki && j != i) fallback = true;	/* a second leading edge of the same surface */
+				}
+				sw->lrank[i] = (uint8_t)r;
+				sw->rsurf[r] = sw->lsurf[i];
+				sw->tcount[i] = 0;
+			}
+			fallback = __any_sync (0xFFFFFFFFu, fallback);
+			__syncwarp ();
+		}
+		if (!fallback)
+		{
+			/* toggles, XOR scan, top surface after every edge, change points (x0 / sf reuse the key area) */
+			unsigned long long carry = 0ull;
+			int prevtop = 1, nc = 1;
+			if (lane == 0) { sw->a.sp.x0[0] = (int16_t)head_u; sw->a.sp.sf[0] = 1; }
+			for (int base = 0; base < n; base += 32)
+			{
+				const int k = base + lane;
+				unsigned long long tog = 0ull;
+				int iu = 0;
+				if (k < n)
+				{
+					const uint32_t sfk = sw->ss[k];
+					const int s0 = (int)(sfk & 0xFFFF), s1 = (int)(sfk >> 16);
+					iu = sw->su[k] >> 20;
+					if (s1)
+						tog ^= 1ull << sw->lrank[sw->lidx[k]];
+					if (s0)
+					{
+						int found = -1;
+						for (int j = 0; j < m; j++)
+							if (sw->lsurf[j] == s0) found = j;
+						if (found < 0 || (int)sw->lk[found] >= k)
+							fallback = true;		/* trailing edge without / before its leading edge */
+						else
+						{
+							tog ^= 1ull << sw->lrank[found];
+							atomicAdd (&sw->tcount[found], 1);
+						}
+					}
+				}
+				unsigned long long v = tog;
+				#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const unsigned long long t = __shfl_up_sync (0xFFFFFFFFu, v, o);
+					if (lane >= o) v ^= t;
+				}
+				v ^= carry;
+				carry = __shfl_sync (0xFFFFFFFFu, v, 31);
+				const int top = v ? (int)sw->rsurf[__ffsll ((long long)v) - 1] : 1;
+				int pt = __shfl_up_sync (0xFFFFFFFFu, top, 1);
+				if (lane == 0) pt = prevtop;
+				prevtop = __shfl_sync (0xFFFFFFFFu, top, 31);
+				const bool chg = k < n && top != pt;
+				const unsigned mask = __ballot_sync (0xFFFFFFFFu, chg);
+				const int pos = nc + __popc (mask & lt);
+				if (chg) { sw->a.sp.x0[pos] = (int16_t)iu; sw->a.sp.sf[pos] = (uint16_t)top; }
+				nc += __popc (mask);
+			}
+			__syncwarp ();
+			for (int i = lane; i < m; i += 32)
+				if (sw->tcount[i] > 1) fallback = true;			/* two trailing edges of one surface */
+			fallback = __any_sync (0xFFFFFFFFu, fallback);
+			if (!fallback)
+			{
+				/* runs between change points -> spans, empty runs dropped (in place: writes never pass reads) */
+				for (int base = 0; base < nc; base += 32)
+				{
+					const int j = base + lane;
+					int st = 0, en = 0, sf = 0;
+					bool valid = false;
+					if (j < nc)
+					{
+						st = sw->a.sp.x0[j]; en = (j + 1 < nc) ? (int)sw->a.sp.x0[j + 1] : tail_u; sf = sw->a.sp.sf[j];
+						valid = en > st;
+					}
+					__syncwarp ();
+					const unsigned mask = __ballot_sync (0xFFFFFFFFu, valid);
+					const int pos = nsp + __popc (mask & lt);
+					if (valid) { sw->a.sp.x0[pos] = (int16_t)st; sw->a.sp.x1[pos] = (int16_t)en; sw->a.sp.sf[pos] = (uint16_t)sf; }
+					nsp += __popc (mask);
+					__syncwarp ();
+				}
 			}
 		}
 	}
@@ -755,6 +884,78 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 	__syncwarp ();
 
 	/* ---- C: publish ---- */
+	if (nsp <= 32)
+	{
+		/* the common case: one span per lane.  One scan gives the segment offsets and their total, one atomicAdd
+		 * reserves the span and segment records; every span lane writes its record and the owners of its segments.
+		 * Cell map: the spans that cover at least one whole cell are compacted; a bit per cell marks where such a
+		 * span's first whole cell is (one REDUX.OR per 32 cells), so a cell finds its span by a population count
+		 * instead of a search. */
+		const bool have = lane < nsp;
+		const int u0 = have ? (int)sw->a.sp.x0[lane] : 0, x1 = have ? (int)sw->a.sp.x1[lane] : 0, sf = have ? (int)sw->a.sp.sf[lane] : 0;
+		const int cnt = x1 - u0, c = have ? rc_span_seg_count (cnt) : 0;
+		int incl = c;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int t = __shfl_up_sync (0xFFFFFFFFu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		const int nseg = __shfl_sync (0xFFFFFFFFu, incl, 31);
+		unsigned long long old = 0ull;
+		if (lane == 0)
+			old = atomicAdd (&f.alloc[0], (unsigned long long)nsp | ((unsigned long long)nseg << 32));
+		old = __shfl_sync (0xFFFFFFFFu, old, 0);
+		const int spanbase = (int)(old & 0xFFFFFFFFu), segbase = (int)(old >> 32);
+		if (spanbase + nsp > f.spancap || segbase + nseg > f.segcap)
+		{
+			if (lane == 0) atomicOr (f.status, RC_STAT_SPAN_POOL);
+			for (int cc = lane; cc < cw; cc += 32)
+				cells[cc] = make_int2 (-1, 0);
+			return;
+		}
+		const int myseg = segbase + incl - c;
+		const int cs = (u0 + 7) >> 3, ce = x1 >> 3;		/* whole cells cs .. ce-1 */
+		const bool full = have && ce > cs;
+		const unsigned fm = __ballot_sync (0xFFFFFFFFu, full);
+		__syncwarp ();		/* the span arrays were read above: su / ss are reused for the compacted list */
+		if (have)
+		{
+			uint4 *dst = reinterpret_cast<uint4 *>(&f.spans[spanbase + lane]);
+			dst[0] = make_uint4 ((uint32_t)(uint16_t)u0 | ((uint32_t)cnt << 16), (uint32_t)((vi * f.height + line) * f.width + u0), (uint32_t)myseg, (uint32_t)(vi * f.surfcap + sf));
+			dst[1] = make_uint4 (0u, 0u, 0u, ((uint32_t)line << 20) | (vw->warp_index >= 0 ? RC_SPAN_WARPBIT : 0u));
+			surfs[sf].hasspans = 1;
+			for (int q = 0; q < c; q++)
+				f.segspan[myseg + q] = spanbase + lane;
+			if (full)
+			{
+				const int r = __popc (fm & lt);
+				sw->su[r] = myseg;						/* < 2^26 */
+				sw->ss[r] = (uint32_t)u0 | ((uint32_t)ce << 11) | ((uint32_t)lane << 21);	/* u0 < 2^11, ce <= 256, lane < 32 */
+			}
+		}
+		__syncwarp ();
+		int before = 0;
+		for (int base = 0; base < cw; base += 32)
+		{
+			const unsigned wbits = __reduce_or_sync (0xFFFFFFFFu, (full && (cs >> 5) == (base >> 5)) ? 1u << (cs & 31) : 0u);
+			const int cc = base + lane;
+			const int k = before + __popc (wbits & (lane == 31 ? 0xFFFFFFFFu : (2u << lane) - 1u)) - 1;
+			before += __popc (wbits);
+			if (cc < cw)
+			{
+				int2 cell = make_int2 (-1, 0);
+				if (k >= 0)
+				{
+					const uint32_t pk = sw->ss[k];
+					if (cc < (int)((pk >> 11) & 0x3FFu))
+						cell = make_int2 (spanbase + (int)(pk >> 21), (int)((uint32_t)sw->su[k] * 64u + (uint32_t)((cc << 3) - (int)(pk & 0x7FFu))));
+				}
+				cells[cc] = cell;
+			}
+		}
+		return;
+	}
 	int nseg = 0;
 	if (nsp <= SPANS)
 		for (int j = lane; j < nsp; j += 32)
@@ -838,6 +1039,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			cell = make_int2 (spanbase + idx, (int)((uint32_t)sw->su[idx] * 64u + (uint32_t)(x - sw->a.sp.x0[idx])));
 		cells[c] = cell;
 	}
+}
+
+/* experiment: one THREAD per (view, scanline), the serial scan of the host simulator (rc_scan_line) */
+__global__ void __launch_bounds__(64) k_scan_serial (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+{
+	const int line = blockIdx.y * blockDim.x + threadIdx.x;
+	if (line < f.height)
+		rc_scan_line (&w, &f, blockIdx.x, line);
 }
 
 __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
@@ -1584,6 +1793,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	 * general cells itself, RC_SCAN_LARGE start with the large scan instance, RC_NO_GRAPH no CUDA-graph replay,
 	 * RC_FRONT_512 512-thread front-end CTAs on many-view batches */
 	g->front_512 = getenv ("RC_FRONT_512") ? 1 : 0;
+	g->scan_serial = getenv ("RC_SCAN_SERIAL") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
 	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
@@ -1974,7 +2184,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	}
 	if (timed) cudaEventRecord (g->ev[2], s);
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
-	if (g->scan_large) k_scan<256, SCAN_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<256, SCAN_CAND>), s>>> (w, f);
+	if (g->scan_serial) { dim3 gss (n, (g->height + 63) / 64); k_scan_serial<<<gss, 64, 0, s>>> (w, f); }
+	else if (g->scan_large) k_scan<256, SCAN_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<256, SCAN_CAND>), s>>> (w, f);
 	else k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>), s>>> (w, f);
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
