@@ -123,6 +123,8 @@ typedef struct {
           r_fastsky, r_skycolor, r_lerpmodels, d_mipcap, d_mipscale, r_maxsurfs, r_maxedges;
     size_t surfcache_bytes;   /* device surface-cache pool (0: default) */
     int   max_views_in_flight;/* views processed per pipeline pass (0: derived from memory) */
+    int   host_threads;       /* host threads that set up the views of a large batch (0: min (8, online CPUs); one process
+                               * per GPU shares the host: give each rank its share) */
 } rc_config_t;
 
 void RC_DefaultConfig (rc_config_t *cfg);
@@ -265,6 +267,8 @@ typedef struct {
     float  ms_cells;          /* part of ms_draw spent in k_draw proper (full cells, straight-line code) */
     long long fullcells;      /* screen cells covered by one span (k_draw items) */
     long long slowcells;      /* of those, cells k_draw queued for the general code (turbulent, sky, solid, warp views, negative 1/z) */
+    float  ms_alias, ms_particles, ms_zresolve;   /* entity stage (profiling mode): alias models + sprites, particles, the ordered z resolve */
+    float  pad_;
     long long alias_range_events; /* how often the entity rasterisers met a case the reference itself handles out of range
                                * (status bit 512, RC_STAT_ALIAS_RANGE); blocking calls only */
 } rc_stats_t;

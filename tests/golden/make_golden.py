@@ -21,17 +21,26 @@ CASES = [
     ("full_320x240", "full", 320, 240, 32, 0.37, 0.173, 2),
     ("multi_c2_640x480", "multi", 640, 480, 64, 1.0, 0.0, 0),
     ("multi_c4_160x120", "multi", 160, 120, 256, 0.0, 0.01, 4),
+    # bench.py extras: the first views of its 320x240 line, and BASELINE config C3 at full size (hashes only)
+    ("multi_320x240", "multi", 320, 240, 64, 0.0, 0.01, 0),
+    ("full_c3_1280x720", "full", 1280, 720, 32, 2.5, 0.5, 0, dict(entities=256, particles=8192)),
 ]
 
 
 def main():
     base = tempfile.mkdtemp(prefix="rc_golden_")
     rcutil.make_assets(base)
-    for name, scene, w, h, n, t0, dt, keep in CASES:
-        specs = rcutil.scene_views(scene, n, time=t0, time_step=dt) if scene != "box" else rcutil.scene_views(scene, n)
+    only = set(sys.argv[1:])
+    for case in CASES:
+        name, scene, w, h, n, t0, dt, keep = case[:8]
+        extra = case[8] if len(case) > 8 else {}
+        if only and name not in only:
+            continue
+        specs = rcutil.scene_views(scene, n, time=t0, time_step=dt, **extra) if scene != "box" else rcutil.scene_views(scene, n)
         o = run_oracle.render(base, f"maps/{scene}.bsp", w, h, specs)
         d = dict(scene=scene, w=w, h=h, n=n, t0=t0, dt=dt, fb_sha=rcutil.sha(o["fb"]), z_sha=rcutil.sha(o["z"]),
                  bsp_sha=rcutil.sha(np.frombuffer(open(os.path.join(base, "id1", "maps", scene + ".bsp"), "rb").read(), dtype=np.uint8)))
+        d.update({k: int(v) for k, v in extra.items()})
         if keep:
             d["fb"] = o["fb"][:keep]; d["z"] = o["z"][:keep]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)

@@ -62,7 +62,8 @@ def test_golden_fixtures(assets_dir):
             continue
         g = np.load(os.path.join(gdir, fn), allow_pickle=False)
         scene = str(g["scene"]); w, h, n = int(g["w"]), int(g["h"]), int(g["n"])
-        specs = rcutil.scene_views(scene, n, time=float(g["t0"]), time_step=float(g["dt"])) if scene != "box" else rcutil.scene_views(scene, n)
+        extra = {k: int(g[k]) for k in ("entities", "particles") if k in g}
+        specs = rcutil.scene_views(scene, n, time=float(g["t0"]), time_step=float(g["dt"]), **extra) if scene != "box" else rcutil.scene_views(scene, n)
         r = rcutil.render_rc(api.LIBPATH, assets_dir, f"maps/{scene}.bsp", w, h, specs)
         assert rcutil.sha(r["fb"]) == str(g["fb_sha"]), fn
         assert rcutil.sha(r["z"]) == str(g["z_sha"]), fn

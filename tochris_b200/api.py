@@ -27,7 +27,7 @@ class rc_config_t(C.Structure):
                 ("r_fastsky", C.c_float), ("r_skycolor", C.c_float), ("r_lerpmodels", C.c_float),
                 ("d_mipcap", C.c_float), ("d_mipscale", C.c_float), ("r_maxsurfs", C.c_float),
                 ("r_maxedges", C.c_float),
-                ("surfcache_bytes", C.c_size_t), ("max_views_in_flight", C.c_int)]
+                ("surfcache_bytes", C.c_size_t), ("max_views_in_flight", C.c_int), ("host_threads", C.c_int)]
 
 
 class rc_stats_t(C.Structure):
@@ -37,7 +37,9 @@ class rc_stats_t(C.Structure):
                 ("ms_walk", C.c_float), ("ms_faces", C.c_float), ("ms_scan", C.c_float), ("ms_surfprep", C.c_float),
                 ("ms_cache", C.c_float), ("ms_draw", C.c_float), ("ms_total", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float), ("ms_cells", C.c_float),
-                ("fullcells", C.c_longlong), ("slowcells", C.c_longlong), ("alias_range_events", C.c_longlong)]
+                ("fullcells", C.c_longlong), ("slowcells", C.c_longlong),
+                ("ms_alias", C.c_float), ("ms_particles", C.c_float), ("ms_zresolve", C.c_float), ("pad_", C.c_float),
+                ("alias_range_events", C.c_longlong)]
 
 
 class rc_edge_t(C.Structure):

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <math.h>
 #include <time.h>
@@ -32,6 +33,7 @@ static struct {
 	struct model_s *world;
 	char         err[1024];
 	int          loadlits;		/* r_loadlits (r_main.c:130) */
+	int          host_threads;	/* threads that set up the views of a large batch */
 	/* 2D overlay (r_draw.c): conchars + pictures + translation tables in one blob, mirrored on the device */
 	uint8_t     *d2blob; size_t d2len, d2cap;
 	rc_pic_t     d2pics[RC_MAX_PICS]; char d2names[RC_MAX_PICS][64]; int d2npics;
@@ -153,6 +155,11 @@ int RC_Init (const rc_config_t *cfg)
 			return rc_fail (RC_ERR_FILE, "Couldn't load data/anorm_dots.f32 (alias shading table)");
 		}
 		fclose (f);
+	}
+	{
+		long ncpu = sysconf (_SC_NPROCESSORS_ONLN);
+		rc.host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)(ncpu > 8 ? 8 : (ncpu < 1 ? 1 : ncpu));
+		if (rc.host_threads > 64) rc.host_threads = 64;
 	}
 	rc.gpu = rc_gpu_create (cfg->device, cfg->width, cfg->height, cfg->surfcache_bytes, cfg->max_views_in_flight,
 				rc.err, sizeof(rc.err));
@@ -368,7 +375,7 @@ static int rc_prepare_views (const refdef_t *views, int n)
 	 * view, any order */
 	{
 		int bad = -1, badcode = RC_OK;
-		#pragma omp parallel for schedule(static) if (n >= 512)
+		#pragma omp parallel for schedule(static) num_threads(rc.host_threads) if (n >= 512 && rc.host_threads > 1)
 		for (i = 0; i < n; i++)
 		{
 			rc_view_t *v = &rc.viewscratch[i];

@@ -106,7 +106,7 @@ struct rc_gpu_s {
 	int profiling;
 	int flush_pending;		/* D_FlushCaches requested: done on the stream of the next render */
 	long long launches_total;
-	cudaEvent_t ev[10];
+	cudaEvent_t ev[16];
 	int last_n;
 	const rc_batch_t *cur_batch;
 };
@@ -1798,7 +1798,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
 	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
-	for (int i = 0; i < 10; i++) cudaEventCreate (&g->ev[i]);
+	for (int i = 0; i < 16; i++) cudaEventCreate (&g->ev[i]);
 
 	std::vector<int> st (RC_SIN_BUFFER_SIZE), ist (RC_SIN_BUFFER_SIZE);
 	RC_BuildTurbTables (st.data (), ist.data (), RC_SIN_BUFFER_SIZE);
@@ -1863,7 +1863,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_amodels); cudaFree (g->d_stverts); cudaFree (g->d_atris); cudaFree (g->d_poseverts);
 	cudaFree (g->d_skinpixels); cudaFree (g->d_anormdots);
 	if (g->graph_exec) cudaGraphExecDestroy (g->graph_exec);
-	for (int i = 0; i < 10; i++) cudaEventDestroy (g->ev[i]);
+	for (int i = 0; i < 16; i++) cudaEventDestroy (g->ev[i]);
 	for (int i = 0; i < 8; i++) cudaEventDestroy (g->evgroup[i]);
 	cudaEventDestroy (g->evcopy); cudaEventDestroy (g->evfork); cudaEventDestroy (g->evjoin);
 	cudaStreamDestroy (g->copystream); cudaStreamDestroy (g->sidestream);
@@ -2295,6 +2295,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			f.slowmode = 0;
 		}
 	}
+	if (timed) cudaEventRecord (g->ev[10], s);		/* end of the world's draw stage */
 	if (g->cur_batch && g->cur_batch->nzres)
 	{
 		const rc_batch_t *b = g->cur_batch;
@@ -2337,6 +2338,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 				g->stats.kernel_launches++;
 			}
 		}
+		if (timed) cudaEventRecord (g->ev[11], s);	/* alias models + sprites */
 		if (phi > plo)
 		{
 			rc_frame_t f3 = f;
@@ -2344,9 +2346,11 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			k_particles<<<(phi - plo + 127) / 128, 128, 0, s>>> (f3);
 			g->stats.kernel_launches++;
 		}
+		if (timed) cudaEventRecord (g->ev[12], s);	/* particles */
 		dim3 gz ((g->width + 127) / 128, g->height, n);
 		k_zresolve<<<gz, 128, 0, s>>> (f);
 		g->stats.kernel_launches++;
+		if (timed) cudaEventRecord (g->ev[13], s);	/* z resolve */
 	}
 	if (anywarp)
 	{
@@ -2419,6 +2423,12 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 		if (cudaEventElapsedTime (&ms, g->ev[7], g->ev[8]) == cudaSuccess) g->stats.ms_cells += ms;
 		else cudaGetLastError ();
 		cudaEventElapsedTime (&ms, g->ev[0], g->ev[6]); g->stats.ms_total += ms;
+		if (g->cur_batch && g->cur_batch->nzres)
+		{
+			cudaEventElapsedTime (&ms, g->ev[10], g->ev[11]); g->stats.ms_alias += ms;
+			cudaEventElapsedTime (&ms, g->ev[11], g->ev[12]); g->stats.ms_particles += ms;
+			cudaEventElapsedTime (&ms, g->ev[12], g->ev[13]); g->stats.ms_zresolve += ms;
+		}
 	}
 }
 
