@@ -211,25 +211,33 @@ def run_extra(kind, args, rank, world, local):
         if rank != 0:
             root_ptr = r.ipc_import(bytes(hbuf.cpu().numpy().tobytes()))
         r.set_mirror_output(root_ptr + lo * px1)
+        r.set_mirror_deferred(True)          # the copy of step k beside the kernels of step k+1; fence before the clock stops
+        fb_alt = torch.empty_like(fb)
     l2flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(dev)          # the L2 flush, the events and the render on one explicit stream
     torch.cuda.set_stream(stream)
     status = 0
+    stepno = [0]
 
-    def step():
+    def step(last=False):
         r.flush_caches()
         l2flush.zero_()
-        return r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        stepno[0] += 1
+        target = fb_alt if (world > 1 and stepno[0] & 1) else fb
+        st = r.render_device(rds, n, target.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        if world > 1 and last:
+            r.mirror_fence(stream.cuda_stream)
+        return st
     for _ in range(3):
-        status |= step()
+        status |= step(last=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     t_w0 = time.perf_counter()
-    for a, b in evs:
+    for k, (a, b) in enumerate(evs):
         a.record(stream)
-        status |= step()
+        status |= step(last=(k == steps - 1))
         b.record(stream)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_w0) * 1e3
@@ -254,7 +262,10 @@ def run_extra(kind, args, rank, world, local):
     # every other rank's shard (outside the timed region)
     verified, how = None, []
     if world > 1:
+        r.set_mirror_deferred(False)
         r.set_mirror_output(0)
+        if stepno[0] & 1:                     # the last timed step drew into the alternate buffer
+            fb.copy_(fb_alt)
     if rank == 0:
         import ctypes as C
         g = golden(gname)
@@ -299,7 +310,7 @@ def run_extra(kind, args, rank, world, local):
            "value": round(total * steps / (dev_ms / 1e3), 1), "unit": "views/s" if kind != "c3" else "frames/s", "n_gpus": world,
            "views_total": total, "views_per_gpu": n, "steps": steps, "ms_per_step": round(dev_ms / steps, 4),
            "wall_ms_per_step": round(wall_ms / steps, 4), "mpixel_per_s": round(total * steps * px1 / (dev_ms / 1e3) / 1e6, 1),
-           "gather": ("CUDA-IPC mirror into rank 0's buffer inside the timed region" if world > 1 else "none (one GPU)"),
+           "gather": ("CUDA-IPC mirror into rank 0's buffer inside the timed region (deferred: the copy of step k runs beside step k+1, fence before the clock stops)" if world > 1 else "none (one GPU)"),
            "verified": verified, "verified_how": how, "status": status_names(status),
            "timing": "CUDA events per step on the launching stream, max over ranks; surface cache and L2 flushed before every step"}
     if prof:
@@ -358,7 +369,11 @@ def run_ours(args):
         if args.gather == "peer":
             fb_target = root_ptr + rank * n * px1
         else:
+            # deferred mirror: the copy of step k into rank 0's buffer runs beside the kernels of step k+1 (two frame
+            # buffers in rotation); RC_MirrorFence before the end of the timed region
             r.set_mirror_output(root_ptr + rank * n * px1)
+            r.set_mirror_deferred(True)
+            fb_alt = torch.empty_like(fb)
     elif world > 1 and args.gather == "nccl":
         gather = [torch.empty_like(fb) for _ in range(world)] if rank == 0 else None
     elif world > 1:
@@ -375,13 +390,20 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     px = n * W * H
 
-    def step(timed_events=None):
+    deferred = world > 1 and args.gather == "peer-copy"
+    stepno = [0]
+
+    def step(timed_events=None, last=False):
         if not args.keep_cache:
             r.flush_caches()               # D_FlushCaches: every step rebuilds its surface blocks
         l2flush.zero_()                    # evict the previous step's data from the 126 MB L2
         if timed_events is not None:
             timed_events[0].record(stream)
-        st = r.render_device(rds, n, fb_target, zb.data_ptr(), stream.cuda_stream)
+        stepno[0] += 1
+        target = (fb_alt.data_ptr() if stepno[0] & 1 else fb.data_ptr()) if deferred else fb_target
+        st = r.render_device(rds, n, target, zb.data_ptr(), stream.cuda_stream)
+        if deferred and last:
+            r.mirror_fence(stream.cuda_stream)     # every frame of every step has arrived on rank 0 before the clock stops
         if world > 1 and args.gather == "nccl":
             shard.gather_frames(fb, n * world, rank, world, dst=0, bufs=gather, concat=False)
         elif world > 1 and args.gather == "nccl-groups":
@@ -392,7 +414,7 @@ def run_ours(args):
 
     status = 0
     for _ in range(max(args.warmup, 3)):
-        status |= step()
+        status |= step(last=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -404,7 +426,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        status |= step(evs[k])
+        status |= step(evs[k], last=(k == args.steps - 1))
         launches += r.stats()["kernel_launches"]
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
@@ -416,6 +438,7 @@ def run_ours(args):
         r.set_group_callback(None)
     gather_check = None
     if world > 1 and args.gather in ("peer", "peer-copy"):
+        r.set_mirror_deferred(False)
         r.set_mirror_output(0)
         # once, outside the timed region: what arrived on rank 0 over NVLink equals what each rank renders locally
         r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
@@ -608,7 +631,7 @@ def run_ours(args):
                    "width": W, "height": H, "views_per_gpu": n, "global_batch": n * world},
         "method": {"parallelism": f"dp{world} by view", "l2": "flushed between steps (256 MiB write)",
                    "surface_cache": "kept across steps" if args.keep_cache else "flushed before every step (all visible blocks rebuilt inside the timed region)",
-                   "gather_verified": gather_check, "collective": ({"peer-copy": "none: rank 0 exports its gather buffer (CUDA IPC peer memory); every rank copies each finished group of 16 views into its slice over NVLink on a second stream while the next group is drawn; NCCL only for the handle broadcast and the closing barrier", "peer": "none: every rank renders straight into rank 0's gather buffer (CUDA IPC peer memory), the draw kernel's stores cross NVLink as they are produced; NCCL only for the handle broadcast and the closing barrier", "nccl": "NCCL gather of framebuffers to rank 0 inside the timed region", "nccl-groups": "NCCL gather per group of 16 views, overlapped with the draw of the next group"}[args.gather] if world > 1 else "none")},
+                   "gather_verified": gather_check, "collective": ({"peer-copy": "none: rank 0 exports its gather buffer (CUDA IPC peer memory); every rank copies each finished batch into its slice over NVLink on a copy stream while the next step is rendered (deferred mirror, two frame buffers in rotation), RC_MirrorFence before the end of the timed region; NCCL only for the handle broadcast and the closing barrier", "peer": "none: every rank renders straight into rank 0's gather buffer (CUDA IPC peer memory), the draw kernel's stores cross NVLink as they are produced; NCCL only for the handle broadcast and the closing barrier", "nccl": "NCCL gather of framebuffers to rank 0 inside the timed region", "nccl-groups": "NCCL gather per group of 16 views, overlapped with the draw of the next group"}[args.gather] if world > 1 else "none")},
         "mpixel_per_s": round(value * W * H / 1e6, 1),
         "warm_surface_cache": ({"value": round(n / (warm_ms / 1e3), 1), "ms_per_step": round(warm_ms, 4),
                                 "note": "same steps without the per-step D_FlushCaches (the reference's and the CPU arm's steady state); informational"}

@@ -244,6 +244,15 @@ void RC_SetMirrorOutput (void *fb, void *z);
  * worth it when the destination's ingress is the bound (many ranks mirroring into one root) -- at the cost of one
  * more draw launch per group. */
 void RC_SetMirrorGroups (int ngroups);
+/* Deferred mirror: for a STREAM of batches (one RC_RenderViewsDevice per step) the copy to the mirror need not finish
+ * inside the call.  With RC_SetMirrorDeferred (1) a call enqueues its kernels on `stream`, then the copy of the whole
+ * batch on the renderer's copy stream, and returns; `stream` does not wait for the copy, so it runs beside the next
+ * batch's kernels (the root's NVLink ingress -- (N-1) x the bytes of one rank per step -- is then busy during the whole
+ * step instead of after it).  Ordering: a call that draws into a frame buffer whose copy is still in flight waits for
+ * that copy first (alternate two frame buffers to keep the overlap); RC_MirrorFence (stream) makes `stream` wait for
+ * every copy enqueued so far -- call it before the mirror's contents are read, e.g. at the end of a timed region. */
+void RC_SetMirrorDeferred (int on);
+int  RC_MirrorFence (void *stream);
 
 /* The `loadsky <name>` command / r_skyname cvar (ref_soft/r_main.c:169-177, r_sky.c:138-194):
  * loads <basedir>/id1/env/<name>{rt,bk,lf,ft,up,dn}.pcx (six 256x256 8-bit PCX pictures); from then on

@@ -123,6 +123,8 @@ int rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle) { (void)g;
 int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr) { (void)g; (void)handle; (void)ptr; return RC_ERR_CUDA; }
 void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { (void)g; (void)ptr; }
 void rc_gpu_set_mirror_groups (rc_gpu_t *g, int ngroups) { (void)g; (void)ngroups; }
+void rc_gpu_set_mirror_deferred (rc_gpu_t *g, int on) { (void)g; (void)on; }
+int rc_gpu_mirror_fence (rc_gpu_t *g, void *stream, char *err, size_t errlen) { (void)g; (void)stream; (void)err; (void)errlen; return RC_OK; }
 void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { (void)g; (void)fb; (void)z; }
 
 void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)

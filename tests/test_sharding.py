@@ -101,6 +101,19 @@ def _gpu_worker(rank, world, base, outdir, qs):
                 st = r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
                 assert st == 0
             stream.synchronize()
+        # deferred mirror (RC_SetMirrorDeferred / RC_MirrorFence): the copy of a batch overlaps the next batch; two frame
+        # buffers in rotation, then one more call into a buffer whose copy is still in flight (it must wait for it)
+        fb2 = torch.zeros_like(fb)
+        r.set_mirror_deferred(True)
+        for k in range(5):
+            st = r.render_device(rds, n, (fb2 if k & 1 else fb).data_ptr(), zb.data_ptr(), stream.cuda_stream)
+            assert st == 0
+        st = r.render_device(rds, n, fb.data_ptr(), zb.data_ptr(), stream.cuda_stream)
+        assert st == 0
+        r.mirror_fence(stream.cuda_stream)
+        stream.synchronize()
+        assert torch.equal(fb, fb2)
+        r.set_mirror_deferred(False)
         r.set_mirror_output(0)
         np.save(os.path.join(outdir, f"local{rank}.npy"), fb.cpu().numpy())
         qs[0].put(("done", rank)) if rank else None

@@ -326,6 +326,14 @@ class RefCuda:
     def set_mirror_groups(self, ngroups: int):
         self.lib.RC_SetMirrorGroups(ngroups)
 
+    def set_mirror_deferred(self, on: bool):
+        """RC_SetMirrorDeferred: the mirror copy of a batch overlaps the next batch; mirror_fence() before reading the mirror."""
+        self.lib.RC_SetMirrorDeferred(int(on))
+
+    def mirror_fence(self, stream: int = 0):
+        if self.lib.RC_MirrorFence(C.c_void_p(stream or None)) != 0:
+            raise RuntimeError(f"RC_MirrorFence failed: {self.err()}")
+
     def flush_caches(self):
         self.lib.RC_FlushCaches()
 

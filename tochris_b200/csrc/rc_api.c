@@ -651,6 +651,8 @@ int  RC_IpcImport (const unsigned char handle[64], void **ptr) { return rc.gpu ?
 void RC_IpcClose (void *ptr) { if (rc.gpu) rc_gpu_ipc_close (rc.gpu, ptr); }
 void RC_SetMirrorOutput (void *fb, void *z) { if (rc.gpu) rc_gpu_set_mirror (rc.gpu, fb, z); }
 void RC_SetMirrorGroups (int ngroups) { if (rc.gpu) rc_gpu_set_mirror_groups (rc.gpu, ngroups); }
+void RC_SetMirrorDeferred (int on) { if (rc.gpu) rc_gpu_set_mirror_deferred (rc.gpu, on); }
+int  RC_MirrorFence (void *stream) { return rc.gpu ? rc_gpu_mirror_fence (rc.gpu, stream, rc.err, sizeof(rc.err)) : RC_ERR_ARG; }
 
 int RC_SetSkybox (const char *name)
 {

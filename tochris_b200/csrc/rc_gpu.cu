@@ -37,6 +37,8 @@
 	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
 
 
+#define RC_GRAPHS 4
+
 struct rc_gpu_s {
 	int device, width, height, numsms;
 	cudaStream_t stream;
@@ -94,12 +96,21 @@ struct rc_gpu_s {
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
+	/* deferred mirror (RC_SetMirrorDeferred): the copy of a batch to the mirror runs on the copy stream AFTER the call's
+	 * kernels and the caller's stream does not wait for it -- it overlaps the next batch; a frame buffer that still has a
+	 * copy in flight makes the next call that draws into it wait, RC_MirrorFence makes a stream wait for all of them */
+	int mirror_deferred;
+	struct { const void *fb; cudaEvent_t ev; int valid; } mpend[4];
+	cudaEvent_t evrender;
 	int slow_in_ends;
 	int scan_serial;
 	int front_512;			/* RC_FRONT_512: keep 512-thread front-end CTAs on many-view batches (experiment knob) */
 	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
 	/* the plain device path as a CUDA graph: captured once per (world, frame) parameter set, relaunched while they stay the same */
-	cudaGraphExec_t graph_exec; rc_world_t graph_w; rc_frame_t graph_f; int use_graphs;
+	/* a few graphs are kept: callers rotate frame buffers (double buffering, the deferred mirror) and every buffer set is
+	 * its own graph */
+	struct { cudaGraphExec_t exec; rc_world_t w; rc_frame_t f; unsigned long long used; } graphs[RC_GRAPHS];
+	unsigned long long graph_clock; int use_graphs;
 	uint8_t *host_fb; int16_t *host_z;	/* set by rc_gpu_render_host: finished view groups are copied out while the next ones are drawn */
 	/* stats */
 	rc_stats_t stats;
@@ -1787,7 +1798,9 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaStreamCreateWithFlags (&g->sidestream, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
-	g->mirrorgroups = 0;
+	g->mirrorgroups = 0; g->mirror_deferred = 0;
+	for (int i = 0; i < 4; i++) { g->mpend[i].fb = NULL; g->mpend[i].valid = 0; cudaEventCreateWithFlags (&g->mpend[i].ev, cudaEventDisableTiming); }
+	cudaEventCreateWithFlags (&g->evrender, cudaEventDisableTiming);
 	/* Environment knobs, all read ONCE here; they select measured-and-rejected variants for A/B runs and are not part of
 	 * the API: RC_ASYNC_GROUPS=1..8 groups of a pipelined call (default 4), RC_SLOW_IN_ENDS k_ends finds the
 	 * general cells itself, RC_SCAN_LARGE start with the large scan instance, RC_NO_GRAPH no CUDA-graph replay,
@@ -1796,7 +1809,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->scan_serial = getenv ("RC_SCAN_SERIAL") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
-	g->graph_exec = NULL; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
+	for (int i = 0; i < RC_GRAPHS; i++) { g->graphs[i].exec = NULL; g->graphs[i].used = 0; }
+	g->graph_clock = 0; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
 	for (int i = 0; i < 16; i++) cudaEventCreate (&g->ev[i]);
 
@@ -1862,10 +1876,12 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFree (g->d_colormaps); cudaFree (g->d_zres); cudaFree (g->d_zscratch);
 	cudaFree (g->d_amodels); cudaFree (g->d_stverts); cudaFree (g->d_atris); cudaFree (g->d_poseverts);
 	cudaFree (g->d_skinpixels); cudaFree (g->d_anormdots);
-	if (g->graph_exec) cudaGraphExecDestroy (g->graph_exec);
+	for (int i = 0; i < RC_GRAPHS; i++) if (g->graphs[i].exec) cudaGraphExecDestroy (g->graphs[i].exec);
 	for (int i = 0; i < 16; i++) cudaEventDestroy (g->ev[i]);
 	for (int i = 0; i < 8; i++) cudaEventDestroy (g->evgroup[i]);
 	cudaEventDestroy (g->evcopy); cudaEventDestroy (g->evfork); cudaEventDestroy (g->evjoin);
+	for (int i = 0; i < 4; i++) cudaEventDestroy (g->mpend[i].ev);
+	cudaEventDestroy (g->evrender);
 	cudaStreamDestroy (g->copystream); cudaStreamDestroy (g->sidestream);
 	cudaStreamDestroy (g->stream);
 	delete g;
@@ -2006,6 +2022,16 @@ int rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr)
 void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr) { cudaSetDevice (g->device); cudaIpcCloseMemHandle (ptr); }
 void rc_gpu_set_mirror_groups (rc_gpu_t *g, int ngroups) { g->mirrorgroups = ngroups; }
 void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z) { g->mirror_fb = (uint8_t *)fb; g->mirror_z = (int16_t *)z; }
+void rc_gpu_set_mirror_deferred (rc_gpu_t *g, int on) { g->mirror_deferred = on != 0; }
+int rc_gpu_mirror_fence (rc_gpu_t *g, void *stream, char *err, size_t errlen)
+{
+	cudaSetDevice (g->device);
+	cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+	for (int i = 0; i < 4; i++)
+		if (g->mpend[i].valid)
+			CK (cudaStreamWaitEvent (s, g->mpend[i].ev, 0));
+	return RC_OK;
+}
 
 void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups)
 {
@@ -2133,17 +2159,24 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaStream_t s; bool on;
 		~capture_guard_t () { if (on) { cudaGraph_t gr = NULL; cudaStreamEndCapture (s, &gr); if (gr) cudaGraphDestroy (gr); } }
 	} capture = { s, false };
+	int gslot = 0;
 	if (timed) cudaEventRecord (g->ev[0], s);
 	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
 	if (capturable)
 	{
-		if (g->graph_exec && !memcmp (&g->graph_w, &w, sizeof(w)) && !memcmp (&g->graph_f, &f0, sizeof(f0)))
+		gslot = 0;
+		for (int i = 0; i < RC_GRAPHS; i++)
 		{
-			CK (cudaGraphLaunch (g->graph_exec, s));
-			g->stats.kernel_launches += 9;	/* the eight pipeline kernels + k_reset_chunk */
-			return RC_OK;
+			if (g->graphs[i].exec && !memcmp (&g->graphs[i].w, &w, sizeof(w)) && !memcmp (&g->graphs[i].f, &f0, sizeof(f0)))
+			{
+				g->graphs[i].used = ++g->graph_clock;
+				CK (cudaGraphLaunch (g->graphs[i].exec, s));
+				g->stats.kernel_launches += 9;	/* the eight pipeline kernels + k_reset_chunk */
+				return RC_OK;
+			}
+			if (g->graphs[i].used < g->graphs[gslot].used) gslot = i;	/* least recently used (an empty slot has 0) */
 		}
-		if (g->graph_exec) { cudaGraphExecDestroy (g->graph_exec); g->graph_exec = NULL; }
+		if (g->graphs[gslot].exec) { cudaGraphExecDestroy (g->graphs[gslot].exec); g->graphs[gslot].exec = NULL; g->graphs[gslot].used = 0; }
 		CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
 		capture.on = true;
 	}
@@ -2380,11 +2413,12 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaGraph_t graph = NULL;
 		capture.on = false;
 		CK (cudaStreamEndCapture (s, &graph));
-		cudaError_t ge = cudaGraphInstantiate (&g->graph_exec, graph, 0);
+		cudaError_t ge = cudaGraphInstantiate (&g->graphs[gslot].exec, graph, 0);
 		cudaGraphDestroy (graph);
-		if (ge != cudaSuccess) { g->graph_exec = NULL; snprintf (err, errlen, "cudaGraphInstantiate: %s", cudaGetErrorString (ge)); return RC_ERR_CUDA; }
-		memcpy (&g->graph_w, &w, sizeof(w)); memcpy (&g->graph_f, &f0, sizeof(f0));
-		CK (cudaGraphLaunch (g->graph_exec, s));
+		if (ge != cudaSuccess) { g->graphs[gslot].exec = NULL; snprintf (err, errlen, "cudaGraphInstantiate: %s", cudaGetErrorString (ge)); return RC_ERR_CUDA; }
+		memcpy (&g->graphs[gslot].w, &w, sizeof(w)); memcpy (&g->graphs[gslot].f, &f0, sizeof(f0));
+		g->graphs[gslot].used = ++g->graph_clock;
+		CK (cudaGraphLaunch (g->graphs[gslot].exec, s));
 	}
 	CK (cudaGetLastError ());
 	return RC_OK;
@@ -2440,8 +2474,16 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	/* NULL is the legacy default stream (include/ref_cuda.h): a caller on the default stream is ordered with its own
 	 * producers and consumers.  The host-output paths pass the renderer's own stream explicitly. */
 	cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
-	const bool mirrored = !g->host_fb && g->mirror_fb;
+	const bool deferred = !g->host_fb && g->mirror_fb && g->mirror_deferred;
+	const bool mirrored = !g->host_fb && g->mirror_fb && !deferred;
 	if (mirrored) { g->host_fb = g->mirror_fb; g->host_z = z_dev ? g->mirror_z : NULL; }
+	if (deferred)
+	{
+		/* a copy of an earlier batch may still be reading this frame buffer */
+		for (int i = 0; i < 4; i++)
+			if (g->mpend[i].valid && g->mpend[i].fb == fb_dev)
+				CK (cudaStreamWaitEvent (s, g->mpend[i].ev, 0));
+	}
 	struct unmirror_t { rc_gpu_t *g; bool on; ~unmirror_t () { if (on) { g->host_fb = NULL; g->host_z = NULL; } } } unmirror = { g, mirrored };
 	size_t px = (size_t)g->width * g->height;
 	int st = 0;
@@ -2569,7 +2611,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 			/* more active edges on a scanline (or candidates in an 8-line band) than the small instance of the scan
 			 * kernel holds: the large one from now on, and this batch again */
 			g->scan_large = 1;
-			if (g->graph_exec) { cudaGraphExecDestroy (g->graph_exec); g->graph_exec = NULL; }
+			for (int i = 0; i < RC_GRAPHS; i++) if (g->graphs[i].exec) { cudaGraphExecDestroy (g->graphs[i].exec); g->graphs[i].exec = NULL; g->graphs[i].used = 0; }
 			memset (&g->stats, 0, sizeof(g->stats));
 			continue;
 		}
@@ -2584,6 +2626,26 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		/* surface-cache pool (or table) exhausted, or entries left half-built: D_FlushCaches and redo */
 		memset (&g->stats, 0, sizeof(g->stats));
 		do_flush (g, s);
+	}
+	if (deferred)
+	{
+		/* the whole batch goes to the mirror on the copy stream; nothing on `s` waits for it */
+		int slot = -1;
+		for (int i = 0; i < 4 && slot < 0; i++) if (g->mpend[i].valid && g->mpend[i].fb == fb_dev) slot = i;
+		for (int i = 0; i < 4 && slot < 0; i++) if (!g->mpend[i].valid) slot = i;
+		if (slot < 0)
+		{
+			/* more than four frame buffers in rotation: the oldest entry is waited for and reused */
+			slot = 0;
+			CK (cudaEventSynchronize (g->mpend[0].ev));
+		}
+		CK (cudaEventRecord (g->evrender, s));
+		CK (cudaStreamWaitEvent (g->copystream, g->evrender, 0));
+		CK (cudaMemcpyAsync (g->mirror_fb, fb_dev, px * n, cudaMemcpyDefault, g->copystream));
+		if (g->mirror_z && z_dev)
+			CK (cudaMemcpyAsync (g->mirror_z, z_dev, px * n * sizeof(int16_t), cudaMemcpyDefault, g->copystream));
+		CK (cudaEventRecord (g->mpend[slot].ev, g->copystream));
+		g->mpend[slot].fb = fb_dev; g->mpend[slot].valid = 1;
 	}
 	g->launches_total += g->stats.kernel_launches;
 	g->last_n = n < g->chunkcap ? n : g->chunkcap;

@@ -171,6 +171,8 @@ int  rc_gpu_ipc_import (rc_gpu_t *g, const unsigned char *handle, void **ptr);
 void rc_gpu_ipc_close (rc_gpu_t *g, void *ptr);
 void rc_gpu_set_mirror (rc_gpu_t *g, void *fb, void *z);
 void rc_gpu_set_mirror_groups (rc_gpu_t *g, int ngroups);
+void rc_gpu_set_mirror_deferred (rc_gpu_t *g, int on);
+int  rc_gpu_mirror_fence (rc_gpu_t *g, void *stream, char *err, size_t errlen);
 void rc_gpu_set_group_callback (rc_gpu_t *g, rc_group_fn fn, void *user, void *side_stream, int ngroups);
 /* pixels: six 256x256 pictures in r_skysideimage order, or NULL to switch the sky box off */
 int  rc_gpu_set_skybox (rc_gpu_t *g, const uint8_t *pixels, char *err, size_t errlen);
