@@ -505,6 +505,19 @@ def run_ours(args):
         a.record(); fb_host.copy_(fb.view(n, H, W), non_blocking=True); b.record()
     torch.cuda.synchronize()
     d2h_ms = sorted(a.elapsed_time(b) for a, b in cevs[2:])[len(cevs[2:]) // 2]
+    # N>1: the same copy by ALL ranks at once -- what the host takes in when every GPU delivers its frame buffers at the same
+    # time (one VM, one NUMA node: profiles/r02o_d2h_probe_8gpu.json); the floor of an e2e step at N GPUs
+    d2h_all_ms = None
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0c = time.perf_counter()
+        for _ in range(8):
+            fb_host.copy_(fb.view(n, H, W), non_blocking=True)
+        torch.cuda.synchronize()
+        tc = torch.tensor([(time.perf_counter() - t0c) / 8 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        d2h_all_ms = float(tc[0])
     # ---- extra: the same steps with the surface cache KEPT across steps, which is how ref_soft (and the CPU arm
     # below, after its warm-up pass) normally runs: D_CacheSurface hits.  Reported beside `value`, not as it.
     warm_ms = None
@@ -646,6 +659,10 @@ def run_ours(args):
                 "verified": bool(e2e_ok),
                 "d2h_copy_alone": {"ms": round(d2h_ms, 4), "gbs": round(px / d2h_ms / 1e6, 1),
                                    "note": "median of 6 plain device->pinned-host copies of one step's frame buffers, measured here with nothing else running: the floor of any e2e step on this box"},
+                "d2h_copy_all_ranks_at_once": ({"ms": round(d2h_all_ms, 4), "aggregate_gbs": round(world * px / d2h_all_ms / 1e6, 1),
+                                                "floor_frames_per_s": round(n * world / (d2h_all_ms / 1e3), 1),
+                                                "note": "every rank copying one step's frame buffers to its own pinned buffer at the same time: the host's aggregate ingest (one VM, one NUMA node) bounds e2e at N GPUs, not the GPUs or their PCIe links"}
+                                               if d2h_all_ms else None),
                 "blocking_call": {"value": round(n * world * args.steps / e2e_sync_s, 1), "ms_per_step": round(e2e_sync_s / args.steps * 1e3, 4),
                                   "note": "RC_RenderViews, one blocking call per step, timed call by call"}},
         "value_verified": value_check, "gather_verified": gather_check,
