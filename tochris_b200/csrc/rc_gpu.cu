@@ -76,6 +76,8 @@ struct rc_gpu_s {
 	rc_spriteinst_t *d_sprites; int spritecap; uint8_t *d_spritepixels;
 	uint8_t *d_colormaps; int colormapcap;
 	unsigned long long *d_zres; size_t zrescap;
+	rc_aspan_t *d_aspans; long long aspancap; rc_aspantri_t *d_aspantris; int aspantricap;
+	long long aspan_need; int aspantri_need;	/* what the last entity batch asked of the span queue */
 	int16_t *d_zscratch; size_t zscratchcap;
 	rc_bent_t *d_bents; int bentcap; int *d_leafkey; int *d_nbsurfs; int bsurfcap;
 	rc_cachejob_t *d_jobs;
@@ -1615,9 +1617,64 @@ __global__ void k_alias_verts (const __grid_constant__ rc_frame_t f)
 	rc_alias_vertex (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void k_alias_tris (const __grid_constant__ rc_frame_t f)
+/* One thread per (instance, triangle) walks the triangle's edges; the spans go to the queue (rc_pipeline.h "Span queue").
+ * The slots of the unclipped triangles of a warp are reserved with ONE atomic: a triangle knows its scanline count before
+ * it is walked, and 1.3 M triangles adding to one counter one by one would be the longest thing in the kernel. */
+__global__ void __launch_bounds__(64) k_alias_tris (const __grid_constant__ rc_frame_t f)
 {
-	rc_alias_triangle (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+	const int ii = blockIdx.y, ti = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned lane = threadIdx.x & 31;
+	const int rows = f.aspancap > 0 ? rc_alias_triangle_rows (&f, ii, ti) : 0;
+	/* inclusive prefix sum of the rows, count of the triangles */
+	int pre = rows;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const int v = __shfl_up_sync (0xFFFFFFFFu, pre, o);
+		if (lane >= (unsigned)o) pre += v;
+	}
+	const unsigned wants = __ballot_sync (0xFFFFFFFFu, rows > 0);
+	const int total = __shfl_sync (0xFFFFFFFFu, pre, 31);
+	unsigned long long base = 0ull;
+	if (lane == 0 && wants)
+		base = atomicAdd (&f.alloc[5], ((unsigned long long)__popc (wants) << RC_AQ_SHIFT) | (unsigned long long)total);
+	base = __shfl_sync (0xFFFFFFFFu, base, 0);
+	const long long span0 = (long long)(base & ((1ull << RC_AQ_SHIFT) - 1)) + (pre - rows);
+	const int tri = (int)(base >> RC_AQ_SHIFT) + __popc (wants & ((1u << lane) - 1u));
+	rc_alias_triangle (&f, ii, ti, f.aspancap > 0 ? 1 : 0, rows, span0, tri);
+}
+
+/* one thread per queued span: D_PolysetDrawSpans8 */
+__global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc_frame_t f)
+{
+	const unsigned long long a = f.alloc[5];
+	long long n = (long long)(a & ((1ull << RC_AQ_SHIFT) - 1));
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		/* what this batch asked of the queue: the host sizes it for the next one */
+		atomicMax (&f.alloc[6], (unsigned long long)n); atomicMax (&f.alloc[7], a >> RC_AQ_SHIFT);
+	}
+	if (n > f.aspancap) n = f.aspancap;
+	const uint4 *sp4 = reinterpret_cast<const uint4 *>(f.aspans);
+	const uint4 *tr4 = reinterpret_cast<const uint4 *>(f.aspantris);
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+	{
+		const uint4 s0 = __ldcs (&sp4[2 * i]);
+		if ((int)s0.y <= 0)
+			continue;
+		const uint4 s1 = __ldcs (&sp4[2 * i + 1]);
+		rc_aspan_t sp;
+		sp.xy = (int)s0.x; sp.count = (int)s0.y; sp.ptex = (int)s0.z; sp.stfrac = (int)s0.w;
+		sp.light = (int)s1.x; sp.zi = (int)s1.y; sp.tri = (int)s1.z; sp.pad = 0;
+		const uint4 t0 = __ldg (&tr4[4 * (size_t)sp.tri]), t1 = __ldg (&tr4[4 * (size_t)sp.tri + 1]),
+			    t2 = __ldg (&tr4[4 * (size_t)sp.tri + 2]), t3 = __ldg (&tr4[4 * (size_t)sp.tri + 3]);
+		rc_aspantri_t t;
+		t.zistepx = (int)t0.x; t.lstepx = (int)t0.y; t.ststepxwhole = (int)t0.z; t.stfracstep = (int)t0.w;
+		t.orderbits = (unsigned long long)t1.x | ((unsigned long long)t1.y << 32); t.skinofs = (int)t1.z; t.skinwidth = (int)t1.w;
+		t.skinlo = (int)t2.x; t.skinhi = (int)t2.y; t.cmapidx = (int)t2.z; t.viewidx = (int)t2.w;
+		t.zresidx = (int)t3.x; t.zwidth = (int)t3.y; t.pad[0] = t.pad[1] = 0;
+		rc_alias_queued_span (&f, sp, t);
+	}
 }
 
 __global__ void k_sprites (const __grid_constant__ rc_frame_t f)
@@ -1713,10 +1770,12 @@ __global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long
 __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
 {
 	const unsigned t = threadIdx.x;
-	if (t == 0 || (t >= 2 && t <= 4))
+	if (t == 0 || (t >= 2 && t <= 5))
 		alloc[t] = 0ull;
 	if (status && t < 16)
 		status[t] = 0;
+	if (status && (t == 6 || t == 7))
+		alloc[t] = 0ull;		/* first chunk of a batch: the span queue's high-water marks */
 }
 
 /* status word of a pipelined call, stored straight into pinned host memory: a device->host cudaMemcpyAsync would
@@ -1782,7 +1841,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->d_views = NULL; g->d_fb = NULL; g->d_zb = NULL; g->outcap = 0; g->profiling = 0; g->last_n = 0; g->flush_pending = 0; g->launches_total = 0; g->d_dlights = NULL; g->dlightcap = 0; g->d_warpbuf = NULL; g->warpcap = 0;
 	g->d_amodels = NULL; g->d_stverts = g->d_atris = NULL; g->d_poseverts = g->d_skinpixels = NULL; g->d_anormdots = NULL;
 	g->maxverts = g->maxtris = 0; g->d_alias = NULL; g->aliascap = 0; g->d_finalverts = NULL; g->finalvertcap = 0;
-	g->d_particles = NULL; g->particlecap = 0; g->d_sprites = NULL; g->spritecap = 0; g->d_spritepixels = NULL; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
+	g->d_particles = NULL; g->particlecap = 0; g->d_sprites = NULL; g->spritecap = 0; g->d_spritepixels = NULL; g->d_colormaps = NULL; g->colormapcap = 0; g->d_zres = NULL; g->zrescap = 0; g->d_aspans = NULL; g->aspancap = 0; g->d_aspantris = NULL; g->aspantricap = 0; g->aspan_need = 0; g->aspantri_need = 0; g->d_zscratch = NULL; g->zscratchcap = 0; g->cur_batch = NULL;
 	g->d_bents = NULL; g->bentcap = 0; g->d_leafkey = NULL; g->d_nbsurfs = NULL; g->bsurfcap = 0;
 	cudaFuncSetAttribute (k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>));
 	cudaFuncSetAttribute (k_scan<256, SCAN_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(scan_cta_t<256, SCAN_CAND>));
@@ -1873,7 +1932,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	cudaFreeHost (g->h_pal32[0]); cudaFreeHost (g->h_pal32[1]); cudaEventDestroy (g->evpal[0]); cudaEventDestroy (g->evpal[1]);
 	cudaFree (g->d_sprites); cudaFree (g->d_spritepixels);
 	cudaFree (g->d_bents); cudaFree (g->d_alias); cudaFree (g->d_finalverts); cudaFree (g->d_particles);
-	cudaFree (g->d_colormaps); cudaFree (g->d_zres); cudaFree (g->d_zscratch);
+	cudaFree (g->d_colormaps); cudaFree (g->d_zres); cudaFree (g->d_zscratch); cudaFree (g->d_aspans); cudaFree (g->d_aspantris);
 	cudaFree (g->d_amodels); cudaFree (g->d_stverts); cudaFree (g->d_atris); cudaFree (g->d_poseverts);
 	cudaFree (g->d_skinpixels); cudaFree (g->d_anormdots);
 	for (int i = 0; i < RC_GRAPHS; i++) if (g->graphs[i].exec) cudaGraphExecDestroy (g->graphs[i].exec);
@@ -2344,16 +2403,21 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		while (plo < b->nparticles && b->particles[plo].view < first_view) plo++;
 		phi = plo;
 		while (phi < b->nparticles && b->particles[phi].view < first_view + n) phi++;
-		for (int first = alo; first < ahi; first += 32768)
+		/* instances per launch: grid.y (at most 65535), and the 28 bits the queue's counter has for triangle records */
+		int astep = 32768;
+		while (astep > 1 && (long long)astep * (g->maxtris > 0 ? g->maxtris : 1) * 8 > (1ll << 28)) astep >>= 1;
+		for (int first = alo; first < ahi; first += astep)
 		{
-			/* grid.y = instance: at most 65535 per launch */
-			int cnt = ahi - first < 32768 ? ahi - first : 32768;
+			int cnt = ahi - first < astep ? ahi - first : astep;
 			rc_frame_t f2 = f;
 			f2.alias = g->d_alias + first;
 			dim3 ga ((g->maxverts + 127) / 128, cnt), gt ((g->maxtris + 63) / 64, cnt);
+			f2.aspans = g->d_aspans; f2.aspancap = g->aspancap; f2.aspantris = g->d_aspantris; f2.aspantricap = g->aspantricap;
+			CK (cudaMemsetAsync (g->d_alloc + 5, 0, sizeof(unsigned long long), s));
 			k_alias_verts<<<ga, 128, 0, s>>> (f2);
 			k_alias_tris<<<gt, 64, 0, s>>> (f2);
-			g->stats.kernel_launches += 2;
+			k_alias_spans<<<g->numsms * 8, 256, 0, s>>> (f2);
+			g->stats.kernel_launches += 3;
 		}
 		{
 			/* sprite entities of this chunk's views (ordered by view) */
@@ -2547,6 +2611,34 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		CK (cudaMalloc (&g->d_zres, sizeof(unsigned long long) * g->zrescap));
 	}
 	if (batch->nalias)
+	{
+		/* span queue of the alias rasteriser: sized from what the previous entity batch asked for (a first guess before
+		 * that); triangles that find it full are drawn by their own thread, so the size is never a matter of correctness */
+		long long want = g->aspan_need + g->aspan_need / 4;
+		const long long guess = (long long)(batch->nalias < 32768 ? batch->nalias : 32768) * g->maxtris * 4;
+		if (want < guess) want = guess;
+		if (want < (1 << 20)) want = 1 << 20;
+		if (want > (256ll << 20)) want = 256ll << 20;
+		if (want > g->aspancap)
+		{
+			CK (cudaStreamSynchronize (s));
+			cudaFree (g->d_aspans); g->d_aspans = NULL; g->aspancap = 0;
+			if (cudaMalloc (&g->d_aspans, sizeof(rc_aspan_t) * (size_t)want) == cudaSuccess) g->aspancap = want;
+			else cudaGetLastError ();		/* no queue: direct drawing */
+		}
+		long long wt = (long long)g->aspantri_need + g->aspantri_need / 4;
+		const long long guesst = (long long)(batch->nalias < 32768 ? batch->nalias : 32768) * g->maxtris;
+		if (wt < guesst) wt = guesst;
+		if (wt > (1ll << 28) - 1) wt = (1ll << 28) - 1;	/* the counter has 28 bits for triangles */
+		if (wt > g->aspantricap)
+		{
+			CK (cudaStreamSynchronize (s));
+			cudaFree (g->d_aspantris); g->d_aspantris = NULL; g->aspantricap = 0;
+			if (cudaMalloc (&g->d_aspantris, sizeof(rc_aspantri_t) * (size_t)wt) == cudaSuccess) g->aspantricap = (int)wt;
+			else cudaGetLastError ();
+		}
+	}
+	if (batch->nalias)
 		CK (cudaMemcpyAsync (g->d_alias, batch->alias, sizeof(rc_aliasinst_t) * batch->nalias, cudaMemcpyHostToDevice, s));
 	if (batch->nparticles)
 		CK (cudaMemcpyAsync (g->d_particles, batch->particles, sizeof(rc_particle_t) * batch->nparticles, cudaMemcpyHostToDevice, s));
@@ -2594,8 +2686,12 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 			break;
 		}
 		int stw[2] = { 0, 0 };
+		unsigned long long qneed[2] = { 0ull, 0ull };
 		CK (cudaMemcpyAsync (stw, g->d_status, sizeof(stw), cudaMemcpyDeviceToHost, s));
+		if (batch->nalias)
+			CK (cudaMemcpyAsync (qneed, g->d_alloc + 6, sizeof(qneed), cudaMemcpyDeviceToHost, s));
 		CK (cudaStreamSynchronize (s));
+		if (batch->nalias) { g->aspan_need = (long long)qneed[0]; g->aspantri_need = (int)(qneed[1] < (1ull << 28) ? qneed[1] : (1ull << 28) - 1); }
 		st = stw[0];
 		g->stats.alias_range_events = stw[1];
 #ifdef RC_FRONT_TIMING

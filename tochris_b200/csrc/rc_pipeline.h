@@ -27,7 +27,9 @@
 #define RC_ATOMIC_ADD_ULL(p, v) atomicAdd ((p), (v))
 #define RC_ATOMIC_OR_I(p, v)    atomicOr ((p), (v))
 #define RC_ATOMIC_MIN_I(p, v)   atomicMin ((p), (v))
-#define RC_ATOMIC_MAX_ULL(p, v) atomicMax ((p), (v))
+/* the resolve planes only ever grow: a fragment that does not beat the value read from L2 cannot beat the final one either,
+ * so most of an overdrawn view's fragments cost one read instead of one atomic */
+#define RC_ATOMIC_MAX_ULL(p, v) do { unsigned long long *p_ = (p); const unsigned long long v_ = (v); if (v_ > __ldcg (p_)) atomicMax (p_, v_); } while (0)
 #define RC_ATOMIC_CAS_ULL(p, c, v) atomicCAS ((p), (c), (v))
 #else
 #define RC_HD static inline
@@ -127,6 +129,8 @@ typedef struct {
     int *nbsurfs;                 /* [nviews]: surf_t slots handed to brush-entity fragments */
     int bsurfcap;                 /* per view; their slots start at facecap + 2 */
     unsigned long long *zres;     /* [nzres][height*width]: max over fragments of (z, draw order, colour) */
+    struct rc_aspan_s *aspans; long long aspancap;   /* GPU: queued spans of alias triangles (k_alias_tris -> k_alias_spans); alloc[5] = triangles << RC_AQ_SHIFT | spans */
+    struct rc_aspantri_s *aspantris; int aspantricap;   /* the constants their triangles share */
     int *status;
 } rc_frame_t;
 
@@ -2525,9 +2529,103 @@ typedef struct {
 	const uint8_t *skin;
 	const uint8_t *colormap;
 	unsigned long long *zplane;
+	const int16_t *zworld; int zwidth;	/* the view's z-buffer as the world pass left it */
 	int skinwidth, skinlo, skinhi, seamfixupX16;	/* texel indices skinlo .. skinhi-1 (relative to the picture) lie inside the model's image */
 	unsigned long long orderbits;	/* (order << 8), OR-ed under the z and over the colour */
+	int skinofs, cmapidx, viewidx, zresidx;	/* the same as indices, for the queued form */
+	/* GPU: 0 = the thread draws its spans itself; 1 = they go to the span queue, `qrows` slots from `qspan0` and triangle
+	 * record `qtri` reserved by the caller; 2 = queue, the triangle reserves for itself (clipped triangles) */
+	int qmode, qtri, qrows; long long qspan0;
 } rc_polyctx_t;
+
+RC_HD int rc_min3i (int a, int b, int c) { int m = a < b ? a : b; return m < c ? m : c; }
+RC_HD int rc_max3i (int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
+
+/* Span queue of the alias rasteriser (GPU).  A triangle is walked edge by edge by ONE thread (the DDA of
+ * D_PolysetScanLeftEdge is serial and cheap), but its pixels -- two dependent loads and one atomic each -- are not drawn
+ * there: every scanline's span goes to a queue with the stepping state at its first pixel, and k_alias_spans gives each
+ * queued span a thread of its own.  (One thread per triangle doing everything took 9 ms at C3, one warp per large triangle
+ * sharing each span's pixels 8.5 ms: 2.5 G warp instructions at 24 % issue rate, the rows of a triangle being walked by
+ * 32 lanes that had 10 - 20 pixels to share.) */
+#define RC_AQ_SHIFT 36		/* alloc[5]: spans reserved in the low 36 bits, triangle records above (28 bits) */
+typedef struct rc_aspantri_s {	/* 64 B: what the spans of one rasterised (sub)triangle share */
+	int zistepx, lstepx, ststepxwhole, stfracstep;	/* r_zistepx, r_lstepx, a_ststepxwhole, a_sstepxfrac | a_tstepxfrac << 16 */
+	unsigned long long orderbits;			/* draw order, triangle, fan index: under the z and over the colour */
+	int skinofs, skinwidth, skinlo, skinhi;
+	int cmapidx, viewidx, zresidx, zwidth;
+	int pad[2];
+} rc_aspantri_t;
+typedef struct rc_aspan_s {	/* 32 B */
+	int xy;			/* x & 0xFFFF | y << 16 */
+	int count;		/* <= 0: reserved but not used */
+	int ptex, stfrac;	/* l_ptex, l_sfrac | l_tfrac << 16 at the first pixel */
+	int light, zi;
+	int tri, pad;
+} rc_aspan_t;
+
+/* D_PolysetDrawSpans8 (d_polyse.c:385-447), one span: every pixel the reference would z-test becomes one atomicMax of
+ * (z, draw order, colour) into the view's resolve plane */
+RC_HD void rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint8_t *colormap, unsigned long long *zplane,
+	const int16_t *zworld, int zwidth, int skinwidth, int skinlo, int skinhi, unsigned long long orderbits,
+	int r_zistepx, int r_lstepx, int a_ststepxwhole, int a_sstepxfrac, int a_tstepxfrac,
+	int x, const int y, int lcount, int lptex, int lsfrac, int ltfrac, int llight, int lzi)
+{
+	const int W = f->width, H = f->height;
+	for (; lcount > 0; lcount--, x++)
+	{
+		if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
+		{
+			/* d_polyse.c:422 tests the fragment against the z-buffer before it reads the skin; what the world pass left
+			 * there is a lower bound of what the reference finds: a fragment behind it never lands */
+			if ((lzi >> 16) >= zworld[(size_t)y * zwidth + x])
+			{
+				int ti = lptex;
+				if (ti < skinlo || ti >= skinhi)
+				{
+					/* outside the model's whole memory block: the reference reads a neighbour on its heap */
+					RC_ALIAS_RANGE_HIT (f);
+					RC_DEBUG_PRINT ("skin index %d outside the model image %d .. %d (x %d y %d)\n", ti, skinlo, skinhi, x, y);
+					ti = 0;
+				}
+				int ci = skin[ti] + (llight & 0xFF00);
+				if (ci >= 64 * 256)
+				{
+					RC_ALIAS_RANGE_HIT (f);
+					RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, llight);
+					ci &= 0x3FFF;
+				}
+				const unsigned long long key = ((unsigned long long)(unsigned)((lzi >> 16) + 32768) << 48) | orderbits | colormap[ci];
+				RC_ATOMIC_MAX_ULL (&zplane[(size_t)y * W + x], key);
+			}
+		}
+		else
+			RC_ALIAS_RANGE_HIT (f);
+		lzi = rc_addw (lzi, r_zistepx);
+		llight = rc_addw (llight, r_lstepx);
+		lptex += a_ststepxwhole;
+		lsfrac += a_sstepxfrac;
+		lptex += lsfrac >> 16;
+		lsfrac &= 0xFFFF;
+		ltfrac += a_tstepxfrac;
+		if (ltfrac & 0x10000)
+		{
+			lptex += skinwidth;
+			ltfrac &= 0xFFFF;
+		}
+	}
+}
+
+/* one queued span (k_alias_spans) */
+RC_HD void rc_alias_queued_span (const rc_frame_t *f, const rc_aspan_t &sp, const rc_aspantri_t &t)
+{
+	const size_t viewpix = (size_t)f->width * f->height;
+	rc_polyset_span (f, f->skinpixels + t.skinofs, f->colormaps + (size_t)t.cmapidx * 16384, f->zres + (size_t)t.zresidx * viewpix,
+		f->zb + viewpix * t.viewidx, t.zwidth, t.skinwidth, t.skinlo, t.skinhi, t.orderbits,
+		t.zistepx, t.lstepx, t.ststepxwhole, t.stfracstep & 0xFFFF, (int)((unsigned)t.stfracstep >> 16),
+		(int)(int16_t)(sp.xy & 0xFFFF), sp.xy >> 16, sp.count, sp.ptex, sp.stfrac & 0xFFFF, (int)((unsigned)sp.stfrac >> 16), sp.light, sp.zi);
+}
+
+typedef struct { int mode, tri, rows, n, reserved; long long span0; } rc_aqueue_t;
 
 /* D_PolysetSetUpForLineScan, d_polyse.c:279-310.  adivtab (ref_soft/adivtab.h) is the table of
  * floor quotients / remainders for numerators and denominators in [-15,16] ({0,0} for a zero
@@ -2591,8 +2689,8 @@ RC_HD void rc_edge_table (int idx, int *t)
  * packages and then walks the right side; the two sides are independent, so here they are
  * stepped together scanline by scanline.  Each pixel that the reference would z-test becomes
  * one atomicMax of (z, draw order, colour) into the view's resolve plane. */
-RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, const int *fv1, int fl1,
-				const int *fv2, int fl2, int facesfront, int sub)
+RC_HD void rc_polyset_triangle_body (const rc_polyctx_t *c, const int *fv0, int fl0, const int *fv1, int fl1,
+				const int *fv2, int fl2, int facesfront, int sub, rc_aqueue_t *q)
 {
 	const rc_frame_t *f = c->f;
 	const int d_xdenom = (fv0[1]-fv1[1]) * (fv0[0]-fv2[0]) - (fv0[0]-fv1[0])*(fv0[1]-fv2[1]);
@@ -2711,7 +2809,30 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 		RC_ALIAS_RANGE_HIT (f);
 		return;
 	}
-	const int W = f->width, H = f->height;
+	const unsigned long long orderbits = c->orderbits | ((unsigned long long)sub << 8);
+#ifdef __CUDACC__
+	if (q->mode == 2)
+	{
+		/* one slot per scanline between the highest and the lowest vertex, one triangle record */
+		const int h = rc_max3i (P[0][1], P[1][1], P[2][1]) - rc_min3i (P[0][1], P[1][1], P[2][1]);
+		const unsigned long long a = RC_ATOMIC_ADD_ULL (&f->alloc[5], (1ull << RC_AQ_SHIFT) | (unsigned long long)h);
+		q->span0 = (long long)(a & ((1ull << RC_AQ_SHIFT) - 1)); q->tri = (int)(a >> RC_AQ_SHIFT); q->rows = h; q->reserved = 1;
+	}
+	if (q->mode)
+	{
+		if (q->span0 + q->rows > f->aspancap || q->tri >= f->aspantricap)
+			q->mode = 0;		/* queue full: this triangle is drawn here (the host grows the queue for the next batch) */
+		else
+		{
+			rc_aspantri_t *t = &f->aspantris[q->tri];
+			uint4 *t4 = reinterpret_cast<uint4 *>(t);
+			t4[0] = make_uint4 ((unsigned)r_zistepx, (unsigned)r_lstepx, (unsigned)a_ststepxwhole, (unsigned)a_sstepxfrac | ((unsigned)a_tstepxfrac << 16));
+			t4[1] = make_uint4 ((unsigned)orderbits, (unsigned)(orderbits >> 32), (unsigned)c->skinofs, (unsigned)skinwidth);
+			t4[2] = make_uint4 ((unsigned)c->skinlo, (unsigned)c->skinhi, (unsigned)c->cmapidx, (unsigned)c->viewidx);
+			t4[3] = make_uint4 ((unsigned)c->zresidx, (unsigned)c->zwidth, 0u, 0u);
+		}
+	}
+#endif
 	int guard = 0;
 	for (;;)
 	{
@@ -2778,47 +2899,18 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 		r_remaining--;
 		if (lcount > 0)
 		{
-			int lptex = l_ptex, lsfrac = l_sfrac, ltfrac = l_tfrac, llight = l_light, lzi = l_zi;
-			int x = lx;
-			const int y = ly;
-			for (int n = lcount; n; n--, x++)
+#ifdef __CUDACC__
+			if (q->mode && q->n < q->rows)
 			{
-				if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
-				{
-					int ti = lptex;
-					if (ti < c->skinlo || ti >= c->skinhi)
-					{
-						/* outside the model's whole memory block: the reference reads a neighbour on its heap */
-						RC_ALIAS_RANGE_HIT (f);
-						RC_DEBUG_PRINT ("skin index %d outside the model image %d .. %d (sub %d, x %d y %d)\n", ti, c->skinlo, c->skinhi, sub, x, y);
-						ti = 0;
-					}
-					int ci = c->skin[ti] + (llight & 0xFF00);
-					if (ci >= 64 * 256)
-					{
-						RC_ALIAS_RANGE_HIT (f);
-						RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, llight);
-						ci &= 0x3FFF;
-					}
-					const unsigned long long key = ((unsigned long long)(unsigned)((lzi >> 16) + 32768) << 48) |
-						c->orderbits | ((unsigned long long)sub << 8) | c->colormap[ci];
-					RC_ATOMIC_MAX_ULL (&c->zplane[(size_t)y * W + x], key);
-				}
-				else
-					RC_ALIAS_RANGE_HIT (f);
-				lzi = rc_addw (lzi, r_zistepx);
-				llight = rc_addw (llight, r_lstepx);
-				lptex += a_ststepxwhole;
-				lsfrac += a_sstepxfrac;
-				lptex += lsfrac >> 16;
-				lsfrac &= 0xFFFF;
-				ltfrac += a_tstepxfrac;
-				if (ltfrac & 0x10000)
-				{
-					lptex += skinwidth;
-					ltfrac &= 0xFFFF;
-				}
+				uint4 *s4 = reinterpret_cast<uint4 *>(&f->aspans[q->span0 + q->n]);
+				s4[0] = make_uint4 (((unsigned)lx & 0xFFFFu) | ((unsigned)ly << 16), (unsigned)lcount, (unsigned)l_ptex, (unsigned)l_sfrac | ((unsigned)l_tfrac << 16));
+				s4[1] = make_uint4 ((unsigned)l_light, (unsigned)l_zi, (unsigned)q->tri, 0u);
+				q->n++;
 			}
+			else
+#endif
+			rc_polyset_span (f, c->skin, c->colormap, c->zplane, c->zworld, c->zwidth, skinwidth, c->skinlo, c->skinhi, orderbits,
+				r_zistepx, r_lstepx, a_ststepxwhole, a_sstepxfrac, a_tstepxfrac, lx, ly, lcount, l_ptex, l_sfrac, l_tfrac, l_light, l_zi);
 		}
 		else if (lcount < 0)
 			RC_ALIAS_RANGE_HIT (f);
@@ -2865,6 +2957,25 @@ RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, 
 		}
 	}
 #undef RC_LEFT_SETUP
+}
+
+RC_HD void rc_polyset_triangle (const rc_polyctx_t *c, const int *fv0, int fl0, const int *fv1, int fl1,
+				const int *fv2, int fl2, int facesfront, int sub)
+{
+	rc_aqueue_t q;
+	q.mode = c->qmode; q.tri = c->qtri; q.rows = c->qrows; q.span0 = c->qspan0; q.n = 0; q.reserved = c->qmode == 1;
+	rc_polyset_triangle_body (c, fv0, fl0, fv1, fl1, fv2, fl2, facesfront, sub, &q);
+#ifdef __CUDACC__
+	if (q.reserved)
+	{
+		/* reserved slots the triangle did not use (or could not: queue full) */
+		const rc_frame_t *f = c->f;
+		long long lim = q.span0 + q.rows;
+		if (lim > f->aspancap) lim = f->aspancap;
+		for (long long i = q.span0 + (q.mode ? q.n : 0); i < lim; i++)
+			f->aspans[i].count = 0;
+	}
+#endif
 }
 
 /* R_Alias_clip_{left,right,top,bottom} (r_aclip.c:96-185): edge 0 = left, 1 = right, 2 = top, 3 = bottom */
@@ -2940,7 +3051,36 @@ RC_HD int rc_alias_clip (const rc_view_t *vw, float ziscale, const rc_finalvert_
 
 /* One thread per (alias instance, triangle): the triangle loops of R_AliasPreparePoints
  * (r_alias.c:340-362) / D_DrawNonSubdiv, including R_AliasClipTriangle (r_aclip.c:235-349). */
-RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti)
+/* Triangles whose screen box holds more pixels than this go through the span queue (GPU); smaller ones are drawn by the
+ * thread that walks them */
+#define RC_QUEUE_MIN_PIXELS 16
+
+/* GPU, before the triangle is walked: the number of span slots an unclipped, front-facing triangle wants from the queue
+ * (0: culled, clipped -- those reserve for themselves --, or small enough to be drawn directly) */
+RC_HD int rc_alias_triangle_rows (const rc_frame_t *f, int ii, int ti)
+{
+	const rc_aliasinst_t *in = &f->alias[ii];
+	const rc_aliasmodel_t *m = &f->amodels[in->model];
+	if (ti >= m->numtris)
+		return 0;
+	const int *tri = f->atris + 4 * ((size_t)m->tris_ofs + ti);
+	const rc_finalvert_t *pfv = f->finalverts + in->vertbase;
+	const rc_finalvert_t *a = &pfv[tri[1]], *b = &pfv[tri[2]], *d = &pfv[tri[3]];
+	if (!in->trivial_accept && ((a->flags | b->flags | d->flags) & (RC_ALIAS_XY_CLIP_MASK | RC_ALIAS_Z_CLIP)))
+		return 0;
+	if ((a->v[1] - b->v[1]) * (a->v[0] - d->v[0]) - (a->v[0] - b->v[0]) * (a->v[1] - d->v[1]) >= 0)
+		return 0;		/* d_xdenom: faces away */
+	const int x0 = rc_min3i (a->v[0], b->v[0], d->v[0]), x1 = rc_max3i (a->v[0], b->v[0], d->v[0]);
+	const int y0 = rc_min3i (a->v[1], b->v[1], d->v[1]), y1 = rc_max3i (a->v[1], b->v[1], d->v[1]);
+	if ((long long)(x1 - x0 + 1) * (y1 - y0 + 1) <= RC_QUEUE_MIN_PIXELS)
+		return 0;
+	return y1 - y0;
+}
+
+/* qrows > 0 (GPU): the caller reserved that many span slots from qspan0 and the triangle record qtri; qrows = 0 with
+ * queue = 1: clipped triangles reserve for themselves, others are drawn directly; queue = 0 (the host simulator, and the
+ * reference's own order of work): everything is drawn by this thread */
+RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti, int queue = 0, int qrows = 0, long long qspan0 = 0, int qtri = 0)
 {
 	const rc_aliasinst_t *in = &f->alias[ii];
 	const rc_aliasmodel_t *m = &f->amodels[in->model];
@@ -2951,9 +3091,12 @@ RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti)
 	const rc_finalvert_t *pfv = f->finalverts + in->vertbase;
 	rc_polyctx_t c;
 	c.f = f; c.vw = vw;
+	c.qmode = qrows > 0 ? 1 : 0; c.qrows = qrows; c.qspan0 = qspan0; c.qtri = qtri;
+	c.skinofs = m->skins_ofs + in->skin; c.cmapidx = in->colormap; c.viewidx = in->view - f->viewbase; c.zresidx = vw->zres_index;
 	c.skin = f->skinpixels + m->skins_ofs + in->skin;
 	c.colormap = f->colormaps + (size_t)in->colormap * 16384;
 	c.zplane = f->zres + (size_t)vw->zres_index * f->width * f->height;
+	c.zworld = f->zb + (size_t)f->width * f->height * (in->view - f->viewbase); c.zwidth = vw->zwidth;
 	c.skinwidth = m->skinwidth; c.skinlo = -in->skin; c.skinhi = m->skins_len - in->skin;
 	c.seamfixupX16 = (m->skinwidth >> 1) << 16;
 	c.orderbits = (((unsigned long long)in->order << 24) | ((unsigned long long)ti << 8)) << 8;
@@ -3014,6 +3157,7 @@ RC_HD void rc_alias_triangle (const rc_frame_t *f, int ii, int ti)
 		else if (p->v[1] > vw->vrectbottom) p->v[1] = vw->vrectbottom;
 		p->flags = 0;
 	}
+	c.qmode = queue ? 2 : 0;
 	for (int i = 1; i < k - 1; i++)
 		rc_polyset_triangle (&c, fv[pingpong][0].v, 0, fv[pingpong][i].v, 0, fv[pingpong][i+1].v, 0, facesfront, i);
 }
@@ -3047,6 +3191,7 @@ RC_HD void rc_particle (const rc_frame_t *f, int pi)
 	else if (pix > vw->d_pix_max) pix = vw->d_pix_max;
 	const int rows = pix << vw->d_y_aspect_shift;
 	unsigned long long *zplane = f->zres + (size_t)vw->zres_index * f->width * f->height;
+	const int16_t *zworld = f->zb + (size_t)f->width * f->height * (p->view - f->viewbase);
 	const unsigned long long key = ((unsigned long long)(unsigned)(izi + 32768) << 48) |
 		((((unsigned long long)1 << 39) | (unsigned long long)p->order) << 8) | (unsigned long long)(p->color & 0xFF);
 	if (izi > 32767 || izi < -32768)
@@ -3055,7 +3200,8 @@ RC_HD void rc_particle (const rc_frame_t *f, int pi)
 		for (int i = 0; i < pix; i++)
 		{
 			const int x = u + i, y = v + r;
-			if ((unsigned)x < (unsigned)f->width && (unsigned)y < (unsigned)f->height)
+			/* d_part.c:82 (`*pz <= izi`) against what the world pass left: a lower bound of what the reference finds */
+			if ((unsigned)x < (unsigned)f->width && (unsigned)y < (unsigned)f->height && zworld[(size_t)y * vw->zwidth + x] <= izi)
 				RC_ATOMIC_MAX_ULL (&zplane[(size_t)y * f->width + x], key);
 		}
 }
