@@ -81,6 +81,7 @@ struct rc_gpu_s {
 	int16_t *d_zscratch; size_t zscratchcap;
 	rc_bent_t *d_bents; int bentcap; int *d_leafkey; int *d_nbsurfs; int bsurfcap;
 	rc_cachejob_t *d_jobs;
+	int2 *d_cacheunits; int cacheunitcap;	/* (job, first row) of the row bands k_cache works on; count in alloc[8] */
 	unsigned long long *d_alloc;	/* [0] spans|segments<<32, [1] cache cursor, [2] jobs, [3] cells queued for k_slowcells, [4] full cells */
 	int *d_status;
 	/* host-output path */
@@ -1075,85 +1076,161 @@ __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_c
 		rc_surf_prep (&w, &f, vi, si);
 }
 
-/* Surface-cache build: R_BuildLightmap + R_DrawSurfaceBlock8_mip0..3 (r_light.c:372,
- * r_surf.c:187-375).  Persistent CTAs stride over the job list the prep kernel produced.
- *   - vid.colormap (16 KB) is staged in shared memory once per CTA
- *   - per job, blocklights (<= 17x17 luxels) are built in shared memory
- *   - each thread then shades one row segment of one light block (16>>mip texels): one
- *     vector load of source texels, light stepped right->left with the reference's wrapping
- *     32-bit adds, one vector store.  1 B in, 1 B out per texel. */
-__global__ void __launch_bounds__(256) k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+/* Surface-cache build: R_BuildLightmap + R_DrawSurfaceBlock8_mip0..3 (r_light.c:372, r_surf.c:187-375).
+ * Work unit = a band of rows of one job holding about RC_CACHE_UNIT_TEXELS texels (the prep kernel lists them: blocks
+ * differ 256-fold in size), one WARP per unit, the warps of the grid striding over the list.  What a unit costs is a
+ * chain of dependent loads, not arithmetic -- unit -> job -> lightmap samples and source texels -> colormap -> store --
+ * so the kernel is built to keep many short chains in flight: everything a unit needs of the face and the texture sits
+ * in the job record (rc_surf_prep looked it up), no CTA-wide barrier, no staging of the 16 KB colormap (it is read
+ * through L1; staging it per CTA capped the CTAs per SM and cost 16 KB of L2 reads for units of a few KB).
+ *   - the rows of blocklights the band needs (17 x 17 luxels at most) are built in the warp's slice of shared memory
+ *   - a lane shades 16 consecutive texels of a row: 32-bit loads of source texels, the light of each texel in the
+ *     reference's wrapping 32-bit arithmetic in closed form (rc_cache_texel), colormap look-ups, 32-bit stores.
+ *     1 B in, 1 B out per texel.  (mip 3 rows, 2-texel blocks, go texel by texel.)
+ * History (C2, 6.7 M texels, events): CTA per job with the colormap in shared memory 22 us; CTA per 4096-texel band
+ * 27 us (more units, each with a CTA's worth of set-up); the same without the staging, 4 texels per thread 22 us, 16
+ * texels per thread 20 us -- a quarter of the instructions and no faster, which is what pointed at the chains. */
+#ifndef CACHE_THREADS
+#define CACHE_THREADS 256
+#endif
+#ifndef CACHE_MINB
+#define CACHE_MINB 4
+#endif
+__global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	__shared__ __align__(16) uint8_t s_cmap[256 * 64];
-	__shared__ unsigned bl[18 * 18];
-	const unsigned long long nj = f.alloc[2];
+	__shared__ unsigned s_bl[CACHE_THREADS / 32][18 * 18];
+	const uint8_t * __restrict__ cmap = w.colormap;
+	const unsigned long long nj = f.alloc[2], nu = f.alloc[8];
 	const int njobs = nj > (unsigned long long)f.jobcap ? f.jobcap : (int)nj;
-	if ((int)blockIdx.x >= njobs)
-		return;
-	for (int i = threadIdx.x; i < 256 * 64 / 16; i += blockDim.x)
-		reinterpret_cast<uint4 *>(s_cmap)[i] = reinterpret_cast<const uint4 *>(w.colormap)[i];
-	for (int j = blockIdx.x; j < njobs; j += gridDim.x)
+	/* a unit list that overflowed (or jobs that did): whole jobs as units */
+	const bool byunit = f.cacheunits != NULL && nu <= (unsigned long long)f.cacheunitcap && nj <= (unsigned long long)f.jobcap;
+	const int total = byunit ? (int)nu : njobs;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	unsigned *bl = s_bl[wib];
+	const int nwarps = gridDim.x * (CACHE_THREADS / 32);
+	for (int un = blockIdx.x * (CACHE_THREADS / 32) + wib; un < total; un += nwarps)
 	{
-		const rc_cachejob_t job = f.jobs[j];
-		const rc_face_t *fa = &w.faces[job.face];
-		const rc_texture_t *mt = &w.textures[job.texture];
-		const int lw = (fa->extents[0] >> 4) + 1;
-		const int size = lw * ((fa->extents[1] >> 4) + 1);
-		__syncthreads ();
-		for (int i = threadIdx.x; i < size; i += blockDim.x)
-			bl[i] = rc_cache_luxel (&w, &f, &job, i);
-		__syncthreads ();
-		const int mip = job.mip, shift = 4 - mip, bs = 16 >> mip;
-		const int nu = job.width >> shift;		/* light blocks per row */
-		const int nseg = nu * job.height;
-		const int tw = mt->width >> mip, th = mt->height >> mip;
-		const int soffset = ((fa->texturemins[0] >> mip) + (tw << 16)) % tw;
-		const int toffset = ((fa->texturemins[1] >> mip) + (th << 16)) % th;
-		const uint8_t *src = w.texels + mt->offsets[mip];
-		uint8_t *dst = f.cachepool + job.dstofs;
-		for (int seg = threadIdx.x; seg < nseg; seg += blockDim.x)
+		int j = un, y0 = 0;
+		if (byunit)
 		{
-			const int y = seg / nu, u = seg - y * nu;
-			const int vb = y >> shift, i = y & (bs - 1);
-			const unsigned l00 = bl[vb * lw + u], l01 = bl[vb * lw + u + 1];
-			const unsigned l10 = bl[(vb + 1) * lw + u], l11 = bl[(vb + 1) * lw + u + 1];
-			const int lightleftstep = (int)((l10 - l00) >> shift);
-			const int lightrightstep = (int)((l11 - l01) >> shift);
-			const unsigned lightleft = l00 + (unsigned)i * (unsigned)lightleftstep;
-			const unsigned lightright = l01 + (unsigned)i * (unsigned)lightrightstep;
-			const int lightstep = (int)(lightleft - lightright) >> shift;
-			const int sx = (soffset + u * bs) % tw;
-			const int sy = (toffset + y) % th;
-			const uint8_t *ps = src + sy * tw + sx;
-			uint8_t *pd = dst + y * job.width + u * bs;
-			unsigned light = lightright;		/* column b = bs-1 first */
-			if (mip == 0 && ((((size_t)ps) | ((size_t)pd)) & 15) == 0)
+			const int2 u2 = __ldg (reinterpret_cast<const int2 *>(f.cacheunits) + un);
+			j = u2.x; y0 = u2.y;
+		}
+		const rc_cachejob_t *job = &f.jobs[j];
+		const int mip = job->mip, width = job->width, height = job->height, dstofs = job->dstofs;
+		const int lw = job->smax, tw = job->tw, th = job->th, soffset = job->soffset, toffset = job->toffset, srcofs = job->srcofs;
+		const int rb = job->bandrows;
+		const int y1 = byunit ? (y0 + rb < height ? y0 + rb : height) : height;
+		const int shift = 4 - mip, bs = 16 >> mip;
+		const int lux0 = (y0 >> shift) * lw, lux1 = (((y1 - 1) >> shift) + 2) * lw;	/* luxel rows vb .. vb + 1 of the band's rows */
+		const uint8_t *src = w.texels + srcofs;
+		uint8_t *dst = f.cachepool + dstofs;
+		/* work item: 16 consecutive texels of a row (1, 2 or 4 light blocks at mip 0, 1, 2) */
+		const int G = job->items;
+		const int nitems = G * (y1 - y0);
+		const int qG = job->qG, rG = job->rG;
+		const bool words = mip <= 2 && (width & 3) == 0 && (tw & 3) == 0 && (soffset & 3) == 0 && ((((size_t)src) | ((size_t)dst)) & 3) == 0;
+		/* source column / row of an item, kept incrementally (no modulo per item): sx = (soffset + 16 cg) % tw, sy = (toffset + y) % th */
+		const int dsx = job->dsx, wsx = job->wsx, dsy = job->dsy;
+		struct item_t { int row, cg, sx, sy; };
+		auto advance = [&] (item_t &t)		/* the item 32 further on */
+		{
+			t.row += qG; t.cg += rG; t.sx += dsx; t.sy += dsy;
+			if (t.cg >= G) { t.cg -= G; t.row++; t.sx -= wsx; if (t.sx < 0) t.sx += tw; if (++t.sy >= th) t.sy -= th; }
+			if (t.sx >= tw) t.sx -= tw;
+			if (t.sy >= th) t.sy -= th;
+		};
+		auto fetch = [&] (const item_t &t, bool valid, unsigned (&in)[4])	/* the item's source texels */
+		{
+			const uint8_t *srow = src + t.sy * tw;
+			const int nx = width - (t.cg << 4);
+			in[0] = in[1] = in[2] = in[3] = 0;
+			if (!(valid && words))
+				return;
+			if (nx >= 16 && t.sx + 16 <= tw)
 			{
-				const uint4 sv = *reinterpret_cast<const uint4 *>(ps);
-				const unsigned in[4] = { sv.x, sv.y, sv.z, sv.w };
-				unsigned out[4];
+				/* the common case: 16 texels that do not wrap */
 				#pragma unroll
-				for (int q = 3; q >= 0; q--)
+				for (int wd = 0; wd < 4; wd++)
+					in[wd] = __ldg (reinterpret_cast<const unsigned *>(srow + t.sx) + wd);
+				return;
+			}
+			int sxw = t.sx;
+			#pragma unroll
+			for (int wd = 0; wd < 4; wd++)
+				if (wd * 4 < nx)
 				{
-					unsigned o = 0;
-					#pragma unroll
-					for (int b = 3; b >= 0; b--)
-					{
-						o |= (unsigned)s_cmap[(light & 0xFF00) + ((in[q] >> (8 * b)) & 0xFF)] << (8 * b);
-						light += (unsigned)lightstep;
-					}
-					out[q] = o;
+					while (sxw >= tw) sxw -= tw;
+					in[wd] = __ldg (reinterpret_cast<const unsigned *>(srow + sxw));
+					sxw += 4;
 				}
-				*reinterpret_cast<uint4 *>(pd) = make_uint4 (out[0], out[1], out[2], out[3]);
+		};
+		auto shade = [&] (const item_t &t, const unsigned (&in)[4])
+		{
+			const int x0 = t.cg << 4, y = y0 + t.row;
+			const int nx = width - x0 < 16 ? width - x0 : 16;
+			if (words)
+			{
+				const int vb = y >> shift, i = y & (bs - 1);
+				uint8_t *drow = dst + y * width + x0;
+				unsigned light = 0; int lightstep = 0;
+				#pragma unroll
+				for (int wd = 0; wd < 4; wd++)
+				{
+					if (wd * 4 < nx)
+					{
+						const int x = x0 + wd * 4, b = x & (bs - 1);
+						if (wd == 0 || b == 0)
+						{
+							/* a new light block: its row i, stepped right to left (r_surf.c:187-227) */
+							const int u = x >> shift;
+							const unsigned l00 = bl[vb * lw + u], l01 = bl[vb * lw + u + 1];
+							const unsigned l10 = bl[(vb + 1) * lw + u], l11 = bl[(vb + 1) * lw + u + 1];
+							const int lightleftstep = (int)((l10 - l00) >> shift);		/* unsigned >>: r_surf.c:202 */
+							const int lightrightstep = (int)((l11 - l01) >> shift);
+							const unsigned lightleft = l00 + (unsigned)i * (unsigned)lightleftstep;
+							const unsigned lightright = l01 + (unsigned)i * (unsigned)lightrightstep;
+							lightstep = (int)(lightleft - lightright) >> shift;
+							light = lightright + (unsigned)(bs - 1 - b) * (unsigned)lightstep;	/* light of texel x; its right neighbours are one step less each */
+						}
+						unsigned o = 0;
+						#pragma unroll
+						for (int k = 0; k < 4; k++)
+						{
+							o |= (unsigned)__ldg (&cmap[(light & 0xFF00) + ((in[wd] >> (8 * k)) & 0xFF)]) << (8 * k);
+							light -= (unsigned)lightstep;
+						}
+						*reinterpret_cast<unsigned *>(drow + wd * 4) = o;
+					}
+				}
 			}
 			else
 			{
-				for (int b = bs - 1; b >= 0; b--)
-				{
-					pd[b] = s_cmap[(light & 0xFF00) + ps[b]];
-					light += (unsigned)lightstep;
-				}
+				for (int k = 0; k < nx; k++)
+					dst[y * width + x0 + k] = rc_cache_texel (&w, job, bl, x0 + k, y);
 			}
+		};
+		/* items lane, lane + 32 (a 1024-texel unit has 64): their source texels are requested BEFORE the luxels are built,
+		 * so that the two cold reads of a unit -- lightmap samples and texels -- wait side by side */
+		item_t ta, tb;
+		ta.row = lane / G; ta.cg = lane - ta.row * G;
+		ta.sx = (soffset + (ta.cg << 4)) % tw; ta.sy = (toffset + y0 + ta.row) % th;
+		tb = ta; advance (tb);
+		unsigned ina[4], inb[4];
+		fetch (ta, lane < nitems, ina);
+		fetch (tb, lane + 32 < nitems, inb);
+		__syncwarp ();
+		for (int i = lux0 + lane; i < lux1; i += 32)
+			bl[i] = rc_cache_luxel (&w, &f, job, i);
+		__syncwarp ();
+		for (int it = lane; it < nitems; it += 64)
+		{
+			shade (ta, ina);
+			if (it + 32 < nitems)
+				shade (tb, inb);
+			ta = tb; advance (ta); tb = ta; advance (tb);
+			fetch (ta, it + 64 < nitems, ina);
+			fetch (tb, it + 96 < nitems, inb);
 		}
 	}
 }
@@ -1770,7 +1847,7 @@ __global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long
 __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
 {
 	const unsigned t = threadIdx.x;
-	if (t == 0 || (t >= 2 && t <= 5))
+	if (t == 0 || (t >= 2 && t <= 5) || t == 8)
 		alloc[t] = 0ull;
 	if (status && t < 16)
 		status[t] = 0;
@@ -1886,14 +1963,14 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	if (cudaMalloc (&g->d_cachepool, g->cachecap) != cudaSuccess ||
 	    cudaMalloc (&g->d_cachekeys, sizeof(unsigned long long) * g->cacheslots) != cudaSuccess ||
 	    cudaMalloc (&g->d_cachevals, sizeof(int) * g->cacheslots) != cudaSuccess ||
-	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 8) != cudaSuccess ||
+	    cudaMalloc (&g->d_alloc, sizeof(unsigned long long) * 16) != cudaSuccess ||
 	    cudaMalloc (&g->d_status, sizeof(int) * 16) != cudaSuccess)
 	{
 		snprintf (err, errlen, "cudaMalloc (surface cache) failed: %s", cudaGetErrorString (cudaGetLastError ()));
 		delete g;
 		return NULL;
 	}
-	cudaMemset (g->d_alloc, 0, sizeof(unsigned long long) * 8);
+	cudaMemset (g->d_alloc, 0, sizeof(unsigned long long) * 16);
 	cudaMemset (g->d_cachekeys, 0xFF, sizeof(unsigned long long) * g->cacheslots);
 	cudaDeviceSynchronize ();
 	return g;
@@ -1905,7 +1982,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_cellspan); cudaFree (g->d_slowcells); cudaFree (g->d_jobs); cudaFree (g->d_segspan); cudaFree (g->d_sub);
+	cudaFree (g->d_cellspan); cudaFree (g->d_slowcells); cudaFree (g->d_jobs); cudaFree (g->d_cacheunits); g->d_cacheunits = NULL; cudaFree (g->d_segspan); cudaFree (g->d_sub);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -2178,6 +2255,8 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_segspan, sizeof(int) * (size_t)g->segcap));
 	CK (cudaMalloc (&g->d_sub, sizeof(rc_sub_t) * (8 * (size_t)g->segcap + 8)));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
+	g->cacheunitcap = g->jobcap * 8 + 65536;
+	CK (cudaMalloc (&g->d_cacheunits, sizeof(int2) * (size_t)g->cacheunitcap));
 	g->chunkcap = want;
 	return RC_OK;
 }
@@ -2204,7 +2283,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
-	f.jobs = g->d_jobs; f.jobcap = g->jobcap;
+	f.jobs = g->d_jobs; f.jobcap = g->jobcap; f.cacheunits = reinterpret_cast<int *>(g->d_cacheunits); f.cacheunitcap = g->cacheunitcap;
 	f.fb = fb; f.zb = zb; f.status = g->d_status; f.warpbuf = g->d_warpbuf;
 
 	/* The plain device path (no entities, no warp views, no per-group consumers, no profiling) is a fixed sequence of
@@ -2285,7 +2364,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	if (timed) cudaEventRecord (g->ev[4], s);
 	if (timed)
 	{
-		k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
+		k_cache<<<g->numsms * CACHE_MINB, CACHE_THREADS, 0, s>>> (w, f);
 		cudaEventRecord (g->ev[5], s);
 		k_spanseg<<<g->numsms * 8, 128, 0, s>>> (w, f);
 		cudaEventRecord (g->ev[7], s);
@@ -2298,7 +2377,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
 		k_spanseg<<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
 		cudaEventRecord (g->evjoin, g->sidestream);
-		k_cache<<<g->numsms * 8, 256, 0, s>>> (w, f);
+		k_cache<<<g->numsms * CACHE_MINB, CACHE_THREADS, 0, s>>> (w, f);
 		cudaStreamWaitEvent (s, g->evjoin, 0);
 	}
 	const bool entities = g->cur_batch && g->cur_batch->nzres;

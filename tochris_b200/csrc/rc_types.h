@@ -285,8 +285,20 @@ typedef struct {
     int view;               /* for dynamic lights (-1: none) */
     int pad;                /* bit 0: r_fullbright */
     int dlightbits;
-    int pad2[3];
-} rc_cachejob_t;            /* 64 B */
+    int pad2[3];            /* [0] first dlight, [1] how many */
+    /* what the build needs of the face and the texture, looked up once by the prep kernel (the build kernel's units
+     * are short chains of dependent loads: every level taken out of them counts) */
+    int lightofs;           /* face lightofs (-1: none) */
+    uint8_t styles[4];
+    int smax, tmax;         /* luxels per row / rows: (extents >> 4) + 1 */
+    int tw, th;             /* texture size at this mip */
+    int soffset, toffset;   /* ((texturemins >> mip) + (tw << 16)) % tw: r_surf.c:130-140 */
+    int srcofs;             /* first texel of the mip in the texel blob */
+    int bandrows;           /* rows per work unit of the build kernel (rc_cache_band_rows) */
+    int items;              /* 16-texel items per row: (width + 15) >> 4 */
+    int qG, rG;             /* 32 / items, 32 % items: how a warp's lanes step through the items */
+    int dsx, wsx, dsy;      /* (16 rG) % tw, (16 items) % tw, qG % th: the source position's steps */
+} rc_cachejob_t;            /* 128 B */
 
 /* ---- alias models (MDL): ref_soft/r_alias.c, r_aclip.c, d_polyse.c ------------------------ */
 typedef struct {            /* one loaded model's slices of the shared device blobs */

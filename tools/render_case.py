@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--async-calls", type=int, default=0, help="also run this many pipelined RC_RenderViewsAsync calls")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--flush", action="store_true", help="D_FlushCaches before every repetition (every render rebuilds its surface cache blocks)")
     for k in ("entities", "particles", "sprites", "doors", "dlights", "underwater_every"):
         ap.add_argument("--" + k, type=int, default=0)
     a = ap.parse_args()
@@ -36,6 +37,8 @@ def main():
     r.load_world(f"maps/{a.scene}.bsp")
     rds = views.build_refdefs(specs, a.w, a.h, model_resolver=r.model)
     for _ in range(a.reps):
+        if a.flush:
+            r.flush_caches()
         fb, z, st = r.render(rds)
     print("render_case: status", status_names(st), "launches", r.stats()["kernel_launches"])
     if a.async_calls:
