@@ -258,6 +258,7 @@ def run_extra(kind, args, rank, world, local):
                 acc[k] = acc.get(k, 0) + v
         r.set_profiling(False)
         prof = {k[3:]: round(v / steps, 4) for k, v in acc.items() if k.startswith("ms_") and k not in ("ms_h2d", "ms_d2h")}
+        frag = {k: int(acc.get(k, 0) / steps) for k in ("alias_fragments", "alias_fragments_front", "alias_spans")}
     # ---- what arrived on rank 0 against (a) the committed golden hash of the first views, (b) rank 0's own render of
     # every other rank's shard (outside the timed region)
     verified, how = None, []
@@ -316,8 +317,19 @@ def run_extra(kind, args, rank, world, local):
     if prof:
         ent_px = None
         out["kernel_ms_per_step"] = prof
+        # alias / particle pixels cost 6 B when they pass the z test (2 B z read, 1 B texel, 1 B colour, 2 B z
+        # write) and 2 B when they fail; "pass" is counted against the world's z-buffer (what the span kernel tests first)
+        model_bytes = 6 * frag["alias_fragments_front"] + 2 * (frag["alias_fragments"] - frag["alias_fragments_front"])
+        alias_ms = prof.get("alias") or 0.0
         out["entity_stage"] = {"alias_ms": prof.get("alias"), "particles_ms": prof.get("particles"), "zresolve_ms": prof.get("zresolve"),
-                               "note": "k_alias_verts + k_alias_tris + k_sprites | k_particles | k_zresolve, serialised by the profiling events"}
+                               "alias_spans_per_step": frag["alias_spans"], "alias_fragments_per_step": frag["alias_fragments"],
+                               "alias_fragments_in_front_of_world": frag["alias_fragments_front"],
+                               "alias_fragments_per_view_pixel": round(frag["alias_fragments"] / float(total * px1), 2),
+                               "alias_model_bytes_per_step": int(model_bytes),
+                               "alias_model_gbs": round(model_bytes / (alias_ms * 1e-3) / 1e9, 1) if alias_ms else None,
+                               "note": "k_alias_verts + k_alias_tris + k_alias_spans + k_sprites | k_particles | k_zresolve, serialised by the profiling events; "
+                                       "fragments = pixels of alias spans the rasteriser looked at (overdraw included: the C3 scene stacks 256 models, many of them "
+                                       "near the camera, in front of every view), bytes by SURVEY.md 8(d)'s 6 B / 2 B model"}
     return out
 
 
@@ -677,6 +689,14 @@ def run_ours(args):
                      "draw_stage_ms": round(stage_ms, 4),
                      "draw_stage_note": "k_draw + k_ends (cells that hold a span boundary) + k_slowcells (turbulent / sky / solid cells), serialised by the profiling events; they overlap on two streams in the timed steps",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+        "surface_cache_kernel": {"kernel": "k_cache (R_BuildLightMap + R_DrawSurfaceBlock8_mip0..3 of every block the step's views need; the cache is flushed before each step)",
+                                 "texels_per_launch": int(prof["cache_texels"] / args.steps), "alg_bytes_per_launch": int(2 * prof["cache_texels"] / args.steps),
+                                 "kernel_ms": round(prof["ms_cache"] / args.steps, 4),
+                                 "achieved_gbs": round(2 * prof["cache_texels"] / (prof["ms_cache"] * 1e-3) / 1e9, 1) if prof["ms_cache"] else None,
+                                 "frac": round(2 * prof["cache_texels"] / (prof["ms_cache"] * 1e-3) / 1e9 / peak, 4) if prof["ms_cache"] else None,
+                                 "note": "2 B per rebuilt texel (SURVEY.md 8d); event-timed alone; in the timed steps it runs beside k_spanseg on a second stream. "
+                                         "13 MB of algorithmic bytes per launch: the kernel is far too short to approach the HBM roofline -- an empty launch "
+                                         "of it measures 5 us, and its work is chains of dependent loads (DESIGN.md section 3)"},
         "kernel_ms_per_step": {k[3:]: round(v / args.steps, 4) for k, v in prof.items() if k.startswith("ms_") and k not in ("ms_h2d", "ms_d2h")},
         "per_step_counts": {k: int(prof[k] / args.steps) for k in ("faces", "edges", "spans", "blocks", "cache_jobs", "cache_texels")},
     }

@@ -280,6 +280,9 @@ typedef struct {
     float  pad_;
     long long alias_range_events; /* how often the entity rasterisers met a case the reference itself handles out of range
                                * (status bit 512, RC_STAT_ALIAS_RANGE); blocking calls only */
+    long long alias_fragments;    /* profiling mode: pixels of alias-model spans the rasteriser looked at (d_polyse.c:422's z test) */
+    long long alias_fragments_front; /* of those, the ones in front of the world's z-buffer (skin and colormap read, resolve plane updated) */
+    long long alias_spans;        /* spans that went through the span queue */
 } rc_stats_t;
 void RC_GetStats (rc_stats_t *out);
 void RC_SetProfiling (int on);

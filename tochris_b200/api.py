@@ -39,7 +39,8 @@ class rc_stats_t(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_spanseg", C.c_float), ("ms_cells", C.c_float),
                 ("fullcells", C.c_longlong), ("slowcells", C.c_longlong),
                 ("ms_alias", C.c_float), ("ms_particles", C.c_float), ("ms_zresolve", C.c_float), ("pad_", C.c_float),
-                ("alias_range_events", C.c_longlong)]
+                ("alias_range_events", C.c_longlong), ("alias_fragments", C.c_longlong),
+                ("alias_fragments_front", C.c_longlong), ("alias_spans", C.c_longlong)]
 
 
 class rc_edge_t(C.Structure):

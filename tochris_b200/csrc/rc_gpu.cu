@@ -1733,6 +1733,7 @@ __global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc
 	}
 	if (n > f.aspancap) n = f.aspancap;
 	const uint4 *sp4 = reinterpret_cast<const uint4 *>(f.aspans);
+	long long tested = 0; int front = 0, nsp = 0;
 	const uint4 *tr4 = reinterpret_cast<const uint4 *>(f.aspantris);
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
 	{
@@ -1750,7 +1751,24 @@ __global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc
 		t.orderbits = (unsigned long long)t1.x | ((unsigned long long)t1.y << 32); t.skinofs = (int)t1.z; t.skinwidth = (int)t1.w;
 		t.skinlo = (int)t2.x; t.skinhi = (int)t2.y; t.cmapidx = (int)t2.z; t.viewidx = (int)t2.w;
 		t.zresidx = (int)t3.x; t.zwidth = (int)t3.y; t.pad[0] = t.pad[1] = 0;
-		rc_alias_queued_span (&f, sp, t);
+		front += rc_alias_queued_span (&f, sp, t);
+		tested += sp.count; nsp++;
+	}
+	if (f.countfrags)
+	{
+		/* profiling mode: fragments looked at / in front of the world (alloc[9], alloc[10]), spans (alloc[11]) */
+		#pragma unroll
+		for (int o = 16; o; o >>= 1)
+		{
+			tested += __shfl_xor_sync (0xFFFFFFFFu, tested, o);
+			front += __shfl_xor_sync (0xFFFFFFFFu, front, o);
+			nsp += __shfl_xor_sync (0xFFFFFFFFu, nsp, o);
+		}
+		if ((threadIdx.x & 31) == 0 && nsp)
+		{
+			atomicAdd (&f.alloc[9], (unsigned long long)tested); atomicAdd (&f.alloc[10], (unsigned long long)front);
+			atomicAdd (&f.alloc[11], (unsigned long long)nsp);
+		}
 	}
 }
 
@@ -1851,7 +1869,7 @@ __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
 		alloc[t] = 0ull;
 	if (status && t < 16)
 		status[t] = 0;
-	if (status && (t == 6 || t == 7))
+	if (status && (t == 6 || t == 7 || (t >= 9 && t <= 11)))
 		alloc[t] = 0ull;		/* first chunk of a batch: the span queue's high-water marks */
 }
 
@@ -2285,6 +2303,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;
 	f.jobs = g->d_jobs; f.jobcap = g->jobcap; f.cacheunits = reinterpret_cast<int *>(g->d_cacheunits); f.cacheunitcap = g->cacheunitcap;
 	f.fb = fb; f.zb = zb; f.status = g->d_status; f.warpbuf = g->d_warpbuf;
+	f.countfrags = g->profiling ? 1 : 0;
 
 	/* The plain device path (no entities, no warp views, no per-group consumers, no profiling) is a fixed sequence of
 	 * memsets and kernels on two streams whose parameters only change with the world or the buffers: it is captured
@@ -2569,8 +2588,9 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 
 static void collect_stats (rc_gpu_t *g, int n, bool timed)
 {
-	unsigned long long a[8];
+	unsigned long long a[16];
 	cudaMemcpy (a, g->d_alloc, sizeof(a), cudaMemcpyDeviceToHost);
+	g->stats.alias_fragments = (long long)a[9]; g->stats.alias_fragments_front = (long long)a[10]; g->stats.alias_spans = (long long)a[11];
 	g->stats.fullcells += (long long)a[4];
 	g->stats.slowcells += (long long)a[3];
 	g->stats.spans += (long long)(a[0] & 0xFFFFFFFFu);

@@ -133,6 +133,7 @@ typedef struct {
     unsigned long long *zres;     /* [nzres][height*width]: max over fragments of (z, draw order, colour) */
     struct rc_aspan_s *aspans; long long aspancap;   /* GPU: queued spans of alias triangles (k_alias_tris -> k_alias_spans); alloc[5] = triangles << RC_AQ_SHIFT | spans */
     struct rc_aspantri_s *aspantris; int aspantricap;   /* the constants their triangles share */
+    int countfrags;               /* GPU, profiling mode: the alias span kernel counts its fragments (alloc[9..11]) */
     int *cacheunits; int cacheunitcap;   /* GPU: {job, first row} of the row bands the cache build works on; count in alloc[8] */
     int *status;
 } rc_frame_t;
@@ -2592,12 +2593,14 @@ typedef struct rc_aspan_s {	/* 32 B */
 
 /* D_PolysetDrawSpans8 (d_polyse.c:385-447), one span: every pixel the reference would z-test becomes one atomicMax of
  * (z, draw order, colour) into the view's resolve plane */
-RC_HD void rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint8_t *colormap, unsigned long long *zplane,
+/* returns the number of fragments in front of the world's z-buffer */
+RC_HD int rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint8_t *colormap, unsigned long long *zplane,
 	const int16_t *zworld, int zwidth, int skinwidth, int skinlo, int skinhi, unsigned long long orderbits,
 	int r_zistepx, int r_lstepx, int a_ststepxwhole, int a_sstepxfrac, int a_tstepxfrac,
 	int x, const int y, int lcount, int lptex, int lsfrac, int ltfrac, int llight, int lzi)
 {
 	const int W = f->width, H = f->height;
+	int front = 0;
 	for (; lcount > 0; lcount--, x++)
 	{
 		if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
@@ -2606,6 +2609,7 @@ RC_HD void rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint
 			 * there is a lower bound of what the reference finds: a fragment behind it never lands */
 			if ((lzi >> 16) >= zworld[(size_t)y * zwidth + x])
 			{
+				front++;
 				int ti = lptex;
 				if (ti < skinlo || ti >= skinhi)
 				{
@@ -2640,13 +2644,14 @@ RC_HD void rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint
 			ltfrac &= 0xFFFF;
 		}
 	}
+	return front;
 }
 
 /* one queued span (k_alias_spans) */
-RC_HD void rc_alias_queued_span (const rc_frame_t *f, const rc_aspan_t &sp, const rc_aspantri_t &t)
+RC_HD int rc_alias_queued_span (const rc_frame_t *f, const rc_aspan_t &sp, const rc_aspantri_t &t)
 {
 	const size_t viewpix = (size_t)f->width * f->height;
-	rc_polyset_span (f, f->skinpixels + t.skinofs, f->colormaps + (size_t)t.cmapidx * 16384, f->zres + (size_t)t.zresidx * viewpix,
+	return rc_polyset_span (f, f->skinpixels + t.skinofs, f->colormaps + (size_t)t.cmapidx * 16384, f->zres + (size_t)t.zresidx * viewpix,
 		f->zb + viewpix * t.viewidx, t.zwidth, t.skinwidth, t.skinlo, t.skinhi, t.orderbits,
 		t.zistepx, t.lstepx, t.ststepxwhole, t.stfracstep & 0xFFFF, (int)((unsigned)t.stfracstep >> 16),
 		(int)(int16_t)(sp.xy & 0xFFFF), sp.xy >> 16, sp.count, sp.ptex, sp.stfrac & 0xFFFF, (int)((unsigned)sp.stfrac >> 16), sp.light, sp.zi);
