@@ -128,6 +128,29 @@ typedef struct {
 } rc_config_t;
 
 void RC_DefaultConfig (rc_config_t *cfg);
+/* the configuration of the running renderer (zeroes before RC_Init) */
+void RC_GetConfig (rc_config_t *cfg);
+
+/* return codes and RC_STAT_* status bits (rc_types.h holds the same values for the library's own files) */
+#ifndef RC_OK
+#define RC_OK                    0
+#define RC_ERR_CUDA              (-1)
+#define RC_ERR_ARG               (-2)
+#define RC_ERR_NOWORLD           (-3)
+#define RC_ERR_FILE              (-4)
+#define RC_ERR_FORMAT            (-5)
+#define RC_ERR_NOMEM             (-6)
+#define RC_STAT_EDGE_OVERFLOW    1    /* a view produced more edges than r_maxedges: the reference drops faces (r_rast.c:544) */
+#define RC_STAT_SURF_OVERFLOW    2    /* ditto r_maxsurfs (r_rast.c:537) */
+#define RC_STAT_SPAN_POOL        4    /* internal span pool was too small (the blocking calls retry by themselves) */
+#define RC_STAT_AET_OVERFLOW     8    /* more active edges on one scanline than the scan kernel holds (ditto) */
+#define RC_STAT_STACK_OVERFLOW   16   /* active surface stack deeper than the scan kernel holds */
+#define RC_STAT_CACHE_POOL       32   /* surface cache pool too small (ditto) */
+#define RC_STAT_STALE_CLIPVERT   64   /* the reference would read r_rightenter / r_rightexit left over from the previous frame */
+#define RC_STAT_FACELIST         128  /* face list capacity exceeded */
+#define RC_STAT_ALIAS_RANGE      512  /* the entity rasterisers met a case where the reference itself reads or loops out of range */
+#define RC_STAT_BMODEL_OVERFLOW  1024 /* brush entity clipping ran out of vertices / edges (MAX_BMODEL_VERTS / EDGES) */
+#endif
 
 /* Creates the renderer (CUDA context, tables, palette/colormap from <basedir>/id1/gfx).
  * Replaces VID_Init + R_Init (common/host.c:837-841).  Returns RC_OK or a negative RC_ERR_*. */
@@ -149,6 +172,35 @@ void RC_SetLoadLits (int on);
 int  RC_TimeRefresh (const refdef_t *base, uint8_t *fb_out, double *seconds, int *status);
 int  RC_PointContents (const float *org);
 int  RC_ViewFlagsForOrigin (const float *org);
+
+/* ---- the client's scene lists and `timedemo` in batched form (rc_scene.c) ----
+ * rc_scene_t keeps the four per-frame lists of client/cl_view.c:67-78 with the reference's limits (256 entities, 2048
+ * particles, 32 dlights, 16 colour shifts; what is added to a full list is dropped: the Add calls return 0) and, unlike
+ * the reference's globals, keeps every finished frame, so that a demo or a roll-out becomes one refdef_t array:
+ *   RC_SceneClear = V_ClearScene, RC_SceneAdd* = V_AddEntity / V_AddParticle / V_AddDlight / V_AddCshift (cl_view.c:85-148),
+ *   RC_SceneEndFrame = the assembly in V_RenderView (cl_view.c:915-940; add[4] = cl_add_entities / _particles / _lights /
+ *   _cshifts, NULL = all on), RC_SceneFrames = the frames so far, RC_CalcFov = CalcFov (cl_view.c:629; 0 for a bad fov_x),
+ *   RC_TimeDemo = timedemo (cl_demo.c:324-365): frame 0 does not count, the rest is rendered `batch` views per call;
+ *   fb_out NULL keeps the frames on the device, else n * height * width bytes through the pipelined host path. */
+typedef struct rc_scene_s rc_scene_t;
+typedef struct {
+    int    frames;            /* n - 1: "the first frame didn't count" */
+    double seconds, fps;
+    int    status;            /* RC_STAT_* bits of all batches */
+    char   text[64];          /* "%i frames %5.1f seconds %5.1f fps\n", CL_FinishTimeDemo's line */
+} rc_timedemo_t;
+rc_scene_t *RC_SceneNew (void);
+void  RC_SceneFree (rc_scene_t *s);
+void  RC_SceneClear (rc_scene_t *s);
+void  RC_SceneReset (rc_scene_t *s);
+int   RC_SceneAddEntity (rc_scene_t *s, const entity_t *ent);
+int   RC_SceneAddParticle (rc_scene_t *s, const float *org, int color);
+int   RC_SceneAddDlight (rc_scene_t *s, const float *org, float radius);
+int   RC_SceneAddCshift (rc_scene_t *s, int r, int g, int b, int percent);
+int   RC_SceneEndFrame (rc_scene_t *s, const refdef_t *view, const int *add);
+const refdef_t *RC_SceneFrames (rc_scene_t *s, int *n);
+float RC_CalcFov (float fov_x, float width, float height);
+int   RC_TimeDemo (const refdef_t *frames, int n, int batch, uint8_t *fb_out, rc_timedemo_t *out);
 
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)

@@ -153,6 +153,8 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	rc_frame_t f;
 	memset (&f, 0, sizeof(f));
 	if (!g->haveworld) { snprintf (err, errlen, "no world"); return RC_ERR_NOWORLD; }
+	std::vector<int16_t> zscratch;		/* a caller that does not want z (z_dev NULL, as the device path allows) */
+	if (!z_dev) { zscratch.assign ((size_t)n * g->width * g->height, 0); z_dev = zscratch.data (); }
 	f.nviews = n; f.width = g->width; f.height = g->height; f.views = views; f.dlights = batch->dlights; f.viewbase = 0;
 	f.facecap = (w->numworldfaces < 65000 ? w->numworldfaces : 65000) + 6;
 	std::vector<rc_facerec_t> facelist ((size_t)n * f.facecap);

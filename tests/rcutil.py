@@ -175,11 +175,23 @@ def _rc_worker(q, libpath, basedir, mapname, width, height, specs, cvars, want_d
         from tochris_b200.api import RefCuda
         cvars = dict(cvars or {})
         skyname = cvars.pop("r_skyname", None)
+        demo_batch = cvars.pop("_timedemo_batch", 0)
         r = RefCuda(basedir, width, height, libpath=libpath, **cvars)
         r.load_world(mapname)
         if skyname:
             r.set_skybox(skyname)
         rds = views.build_refdefs(specs, width, height, model_resolver=r.model)
+        if demo_batch:
+            # the frames go through the client's scene lists (RC_Scene*) and are rendered by RC_TimeDemo
+            scene, frames, nfr, dropped = r.record_scene(rds)
+            fb = np.zeros((nfr, height, width), dtype=np.uint8)
+            td = r.timedemo(frames, nfr, demo_batch, fb)
+            td_dev = r.timedemo(frames, nfr, demo_batch, None)       # frames stay on the device
+            r.scene_free(scene)
+            out = dict(fb=fb, z=None, status=td["status"], stats=r.stats(), timedemo=td, timedemo_device=td_dev, dropped=dropped)
+            r.shutdown()
+            q.put(("ok", out))
+            return
         fb, z, st = r.render(rds)
         out = dict(fb=fb, z=z, status=st, stats=r.stats())
         if want_debug:

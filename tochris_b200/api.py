@@ -43,6 +43,10 @@ class rc_stats_t(C.Structure):
                 ("alias_fragments_front", C.c_longlong), ("alias_spans", C.c_longlong)]
 
 
+class rc_timedemo_t(C.Structure):    # include/ref_cuda.h rc_timedemo_t
+    _fields_ = [("frames", C.c_int), ("seconds", C.c_double), ("fps", C.c_double), ("status", C.c_int), ("text", C.c_char * 64)]
+
+
 class rc_edge_t(C.Structure):
     _fields_ = [("u", C.c_int), ("u_step", C.c_int), ("v", C.c_short), ("v2", C.c_short),
                 ("surfs", C.c_ushort * 2), ("rank", C.c_uint), ("pad", C.c_int * 3)]
@@ -125,6 +129,23 @@ class RefCuda:
         L.RC_SetMirrorGroups.argtypes = [C.c_int]
         L.RC_SetGroupCallback.argtypes = [GROUPFN, C.c_void_p, C.c_void_p, C.c_int]
         L.RC_SetGroupCallback.restype = None
+        L.RC_SceneNew.restype = C.c_void_p
+        L.RC_SceneFree.argtypes = [C.c_void_p]
+        L.RC_SceneFree.restype = None
+        L.RC_SceneClear.argtypes = [C.c_void_p]
+        L.RC_SceneClear.restype = None
+        L.RC_SceneReset.argtypes = [C.c_void_p]
+        L.RC_SceneReset.restype = None
+        L.RC_SceneAddEntity.argtypes = [C.c_void_p, C.c_void_p]
+        L.RC_SceneAddParticle.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+        L.RC_SceneAddDlight.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float]
+        L.RC_SceneAddCshift.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.RC_SceneEndFrame.argtypes = [C.c_void_p, C.POINTER(refdef_t), C.POINTER(C.c_int)]
+        L.RC_SceneFrames.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.RC_SceneFrames.restype = C.POINTER(refdef_t)
+        L.RC_CalcFov.argtypes = [C.c_float, C.c_float, C.c_float]
+        L.RC_CalcFov.restype = C.c_float
+        L.RC_TimeDemo.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_int, C.c_void_p, C.POINTER(rc_timedemo_t)]
         L.Mod_ForName.restype = C.c_void_p
         L.Mod_ForName.argtypes = [C.c_char_p, C.c_int]
         cfg = rc_config_t()
@@ -225,6 +246,50 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"RC_TimeRefresh failed ({rc}): {self.err()}")
         return fb, secs.value, st.value
+
+    # ---- the client's scene lists and timedemo (rc_scene.c; cl_view.c:67-148,889-943, cl_demo.c:324-365) ----
+    def calc_fov(self, fov_x: float, width: float, height: float) -> float:
+        return float(self.lib.RC_CalcFov(fov_x, width, height))
+
+    def record_scene(self, rds, n: int | None = None, add=None):
+        """Feeds every refdef_t of `rds` to the scene recorder the way the client would -- V_ClearScene, then one V_Add*
+        call per entity, particle, dlight and colour shift, then the frame's refdef_t -- and returns (scene handle,
+        refdef_t pointer, number of frames, [per frame: how many Add calls the full lists dropped])."""
+        L = self.lib
+        n = len(rds) if n is None else n
+        s = L.RC_SceneNew()
+        addv = (C.c_int * 4)(*add) if add is not None else None
+        dropped = []
+        for i in range(n):
+            rd = rds[i]
+            L.RC_SceneClear(s)
+            d = 0
+            for j in range(rd.num_entities):
+                d += 1 - L.RC_SceneAddEntity(s, C.byref(rd.entities[j]))
+            for j in range(rd.num_particles):
+                d += 1 - L.RC_SceneAddParticle(s, rd.particles[j].org, rd.particles[j].color)
+            for j in range(rd.num_dlights):
+                d += 1 - L.RC_SceneAddDlight(s, rd.dlights[j].origin, rd.dlights[j].radius)
+            for j in range(rd.num_cshifts):
+                c = rd.cshifts[j]
+                d += 1 - L.RC_SceneAddCshift(s, c.destcolor[0], c.destcolor[1], c.destcolor[2], c.percent)
+            dropped.append(d)
+            if L.RC_SceneEndFrame(s, C.byref(rd), addv) != i:
+                raise RuntimeError("RC_SceneEndFrame failed")
+        cnt = C.c_int(0)
+        frames = L.RC_SceneFrames(s, C.byref(cnt))
+        return s, frames, cnt.value, dropped
+
+    def scene_free(self, s):
+        self.lib.RC_SceneFree(s)
+
+    def timedemo(self, frames, n: int, batch: int = 64, fb=None) -> dict:
+        """RC_TimeDemo over a refdef_t array; fb: optional (n, h, w) uint8 array that receives every frame."""
+        out = rc_timedemo_t()
+        rc = self.lib.RC_TimeDemo(frames, n, batch, fb.ctypes.data if fb is not None else None, C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"RC_TimeDemo failed ({rc}): {self.err()}")
+        return dict(frames=out.frames, seconds=out.seconds, fps=out.fps, status=out.status, text=out.text.decode())
 
     def point_contents(self, org) -> int:
         a = (C.c_float * 3)(*org)

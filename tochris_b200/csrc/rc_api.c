@@ -82,6 +82,17 @@ void RC_DefaultConfig (rc_config_t *c)
 	c->r_maxsurfs = 1000; c->r_maxedges = 2000;
 }
 
+void RC_GetConfig (rc_config_t *c)
+{
+	if (!c) return;
+	memset (c, 0, sizeof(*c));
+	if (!rc.inited) return;
+	*c = rc.cfg;
+	c->basedir = rc.basedir;
+	c->width = rc.vid.width; c->height = rc.vid.height;
+	c->host_threads = rc.host_threads;
+}
+
 static void *rc_read_file (const char *name, size_t *len)
 {
 	char path[1024];

@@ -382,6 +382,7 @@ typedef struct {            /* one drawn brush entity of one view (R_DrawBEntiti
 } rc_bent_t;                /* 220 B */
 
 /* error / status bits returned through the C-ABI */
+#ifndef RC_OK
 #define RC_OK                    0
 #define RC_ERR_CUDA              (-1)
 #define RC_ERR_ARG               (-2)
@@ -402,6 +403,7 @@ typedef struct {            /* one drawn brush entity of one view (R_DrawBEntiti
                                         * triangles stepping off the skin, d_polyse.c:385-447; span packages left by an earlier triangle;
                                         * a particle 1/z outside 16 bits): those pixels are undefined in the reference.  rc_stats_t.alias_range_events counts them */
 #define RC_STAT_BMODEL_OVERFLOW   1024 /* brush entity clipping ran out of vertices/edges (reference: MAX_BMODEL_VERTS/EDGES) */
+#endif
 
 #ifdef __cplusplus
 }
