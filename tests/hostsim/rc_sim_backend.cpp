@@ -179,8 +179,8 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	std::vector<rc_cell_t> cellspan ((size_t)n * g->height * cw, nocell);
 	f.spans = g->spans.data (); f.cellspan = cellspan.data ();
 	std::vector<int> segspan ((size_t)f.segcap, -1);
-	std::vector<rc_sub_t> sub ((size_t)f.segcap * 8 + 8, rc_sub_t ());
-	f.segspan = segspan.data (); f.sub = sub.data ();
+	std::vector<rc_bnd_t> bnd ((size_t)f.segcap * 8 + 16, rc_bnd_t ());
+	f.segspan = segspan.data (); f.bnd = bnd.data ();
 	g->alloc[0] = 0; g->alloc[2] = 0;
 	f.alloc = g->alloc;
 	f.cachekeys = g->cachekeys.data (); f.cachevals = g->cachevals.data (); f.cachemask = (int)g->cachekeys.size () - 1;

@@ -64,7 +64,7 @@ struct rc_gpu_s {
 	rc_edge_t *d_edges; int *d_nedges;
 	rc_surf_t *d_surfs;
 	rc_span_t *d_spans; rc_cell_t *d_cellspan; int2 *d_slowcells;
-	int *d_segspan; rc_sub_t *d_sub;
+	int *d_segspan; rc_bnd_t *d_bnd;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 			{
 				const int r = __popc (fm & lt);
 				sw->su[r] = myseg;						/* < 2^26 */
-				sw->ss[r] = (uint32_t)u0 | ((uint32_t)ce << 11) | ((uint32_t)lane << 21);	/* u0 < 2^11, ce <= 256, lane < 32 */
+				sw->ss[r] = (uint32_t)u0 | ((uint32_t)ce << 11) | ((uint32_t)lane << 21) | ((uint32_t)(x1 & 7) << 26);	/* u0 < 2^11, ce <= 256, lane < 32 */
 			}
 		}
 		__syncwarp ();
@@ -963,7 +963,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 				{
 					const uint32_t pk = sw->ss[k];
 					if (cc < (int)((pk >> 11) & 0x3FFu))
-						cell = make_int2 (spanbase + (int)(pk >> 21), (int)((uint32_t)sw->su[k] * 64u + (uint32_t)((cc << 3) - (int)(pk & 0x7FFu))));
+					{
+						const int pu0 = (int)(pk & 0x7FFu), px1 = (int)(((pk >> 11) & 0x3FFu) << 3) + (int)(pk >> 26);
+						cell = make_int2 (rc_cell_si (spanbase + (int)((pk >> 21) & 31u), (cc << 3) - pu0, px1 - pu0),
+								  (int)((uint32_t)sw->su[k] * 64u + (uint32_t)((cc << 3) - pu0)));
+					}
 				}
 				cells[cc] = cell;
 			}
@@ -1050,7 +1054,8 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant
 		}
 		int2 cell = make_int2 (-1, 0);
 		if (idx >= 0 && x + 8 <= sw->a.sp.x1[idx])
-			cell = make_int2 (spanbase + idx, (int)((uint32_t)sw->su[idx] * 64u + (uint32_t)(x - sw->a.sp.x0[idx])));
+			cell = make_int2 (rc_cell_si (spanbase + idx, x - sw->a.sp.x0[idx], sw->a.sp.x1[idx] - sw->a.sp.x0[idx]),
+					  (int)((uint32_t)sw->su[idx] * 64u + (uint32_t)(x - sw->a.sp.x0[idx])));
 		cells[c] = cell;
 	}
 }
@@ -1235,36 +1240,37 @@ __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __gr
 	}
 }
 
-/* Span-segment kernel: one thread per 64-pixel segment (rc_span_seg).  A thread's eight subdivision
- * records are 128 contiguous bytes, a warp's 4 KB: they are staged in shared memory (swizzled, conflict
- * free) and written out by the whole warp, 512 contiguous bytes per store instruction instead of 32
- * scattered 16-byte pieces. */
+/* Span-segment kernel: one thread per segment of a span (rc_span_seg): eight boundary records, 64 contiguous
+ * bytes per thread, 2 KB per warp.  They are staged in shared memory (swizzled, conflict free) and written out by
+ * the whole warp, 256 contiguous bytes per store instruction instead of 32 scattered 8-byte pieces; a segment's
+ * records past the span's last subdivision are not written (the two that follow it come from the thread that holds
+ * the last subdivision, straight to global memory). */
 #ifndef SEG_MINB
 #define SEG_MINB 8	/* 64 registers: 24.5 us instead of 30 (measured 1 / 6 / 8 / 10 CTAs per SM) */
 #endif
 __global__ void __launch_bounds__(128, SEG_MINB) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	__shared__ uint4 stage[128 * 8];
+	__shared__ uint2 stage[128 * 8];
 	unsigned long long a = f.alloc[0];
 	int nsegs = (int)(a >> 32);
 	if (nsegs > f.segcap) nsegs = f.segcap;
 	const int lane = threadIdx.x & 31;
-	uint4 *wst = stage + (threadIdx.x & ~31) * 8;
-	uint4 *sub4 = reinterpret_cast<uint4 *>(f.sub);
+	uint2 *wst = stage + (threadIdx.x & ~31) * 8;
+	uint2 *bnd2 = reinterpret_cast<uint2 *>(f.bnd);
 	for (int t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); t0 < nsegs; t0 += gridDim.x * blockDim.x)
 	{
 		const int t = t0 + lane;
-		int wrote = 0;
+		int nvalid = 0;
 		if (t < nsegs)
-			wrote = rc_span_seg (&w, &f, t, reinterpret_cast<rc_sub_t *>(wst + lane * 8), lane & 7);
-		const unsigned m = __ballot_sync (0xFFFFFFFFu, wrote);
+			nvalid = rc_span_seg (&w, &f, t, reinterpret_cast<rc_bnd_t *>(wst + lane * 8), lane & 7);
 		__syncwarp ();
 		#pragma unroll
 		for (int r = 0; r < 8; r++)
 		{
 			const int seg = r * 4 + (lane >> 3), rec = lane & 7;
-			if (m & (1u << seg))
-				sub4[(size_t)(t0 + seg) * 8 + rec] = wst[seg * 8 + (rec ^ (seg & 7))];
+			const int nv = __shfl_sync (0xFFFFFFFFu, nvalid, seg);
+			if (rec < nv)
+				bnd2[(size_t)(t0 + seg) * 8 + rec] = wst[seg * 8 + (rec ^ (seg & 7))];
 		}
 		__syncwarp ();
 	}
@@ -1292,12 +1298,25 @@ __device__ __noinline__ void draw_general (const rc_world_t *w, const rc_frame_t
 }
 
 struct draw_item_t {
-	int   si;		/* span, -1: nothing to draw */
-	uint32_t sub;		/* cell record: subdivision record << 3 | position in it */
+	int   si;		/* cell record: span | RC_CELL_L0 | RC_CELL_L1, -1: nothing to draw */
+	uint32_t sub;		/* cell record: boundary record of the cell's first pixel's subdivision << 3 | position in it */
 	uint32_t pix;		/* first pixel of the cell in the colour / z planes */
 	uint4 sb;		/* second half of the span record: iziorg, izistep, cacheofs, cwk */
-	uint4 r0, r1;		/* subdivision records k, k+1 */
+	uint2 b0, b1, b2, b3;	/* boundary records k .. k+3: B[k], B[k+1], then B[k+2] or subdivision k's own step when it is
+				 * the span's last, then subdivision k+1's step when that one is */
 };
+
+/* subdivisions k and k+1 of a full cell as {s, t, sstep, tstep}, from its four boundary records (rc_sub_of) */
+__device__ __forceinline__ void draw_item_subs (const draw_item_t &it, uint4 &r0, uint4 &r1)
+{
+	const bool l0 = (it.si & RC_CELL_L0) != 0, l1 = ((unsigned)it.si & RC_CELL_L1) != 0;
+	r0.x = it.b0.x; r0.y = it.b0.y;
+	r0.z = l0 ? it.b2.x : (uint32_t)((int)(it.b1.x - it.b0.x) >> 3);
+	r0.w = l0 ? it.b2.y : (uint32_t)((int)(it.b1.y - it.b0.y) >> 3);
+	r1.x = it.b1.x; r1.y = it.b1.y;
+	r1.z = l1 ? it.b3.x : (uint32_t)((int)(it.b2.x - it.b1.x) >> 3);
+	r1.w = l1 ? it.b3.y : (uint32_t)((int)(it.b2.y - it.b1.y) >> 3);
+}
 
 #ifndef DRAW_TW
 #define DRAW_TW 8		/* tile = DRAW_TW cells x 32 / DRAW_TW rows per warp */
@@ -1383,7 +1402,7 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 	const unsigned wstride = gridDim.x * (blockDim.x >> 5);
 	const bool fast_ok = f.zb != NULL && (f.width & 7) == 0;
 	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
-	const uint4 *sub4 = reinterpret_cast<const uint4 *>(f.sub);
+	const uint2 *bnd2 = reinterpret_cast<const uint2 *>(f.bnd);
 	const int2 *cells = reinterpret_cast<const int2 *>(f.cellspan);
 	/* tile -> (tx, ty), kept incrementally (no divide per item) */
 	unsigned tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1404,10 +1423,13 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 	auto issue = [&] (draw_item_t &it, const int2 cell, const uint32_t pix)
 	{
 		it.si = cell.x; it.sub = (uint32_t)cell.y; it.pix = pix;
-		const unsigned s = cell.x < 0 ? 0u : (unsigned)cell.x;
+		const unsigned s = cell.x == -1 ? 0u : (unsigned)RC_CELL_SPAN (cell.x);
 		it.sb = __ldg (&spans4[2 * (size_t)s + 1]);
 		const unsigned k = it.sub >> 3;
-		it.r0 = __ldg (&sub4[k]); it.r1 = __ldg (&sub4[k + 1]);
+		it.b0 = __ldg (&bnd2[k]); it.b1 = __ldg (&bnd2[k + 1]); it.b2 = __ldg (&bnd2[k + 2]);
+		it.b3 = make_uint2 (0u, 0u);
+		if ((unsigned)cell.x & RC_CELL_L1)		/* (-1 has the bit too: record 3, harmless) */
+			it.b3 = __ldg (&bnd2[k + 3]);
 	};
 
 	unsigned t0 = tile;
@@ -1437,18 +1459,20 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 		if (c1.x >= 0)
 		{
 			draw_prefetch_l1 (&spans4[2 * (size_t)c1.x + 1]);
-			draw_prefetch_l1 (&sub4[(uint32_t)c1.y >> 3]);
-			draw_prefetch_l1 (&sub4[((uint32_t)c1.y >> 3) + 1]);
+			draw_prefetch_l1 (&bnd2[(uint32_t)c1.y >> 3]);
+			draw_prefetch_l1 (&bnd2[((uint32_t)c1.y >> 3) + 3]);
 		}
 		draw_item_t cur;
 		issue (cur, c0, p0);
 #endif
 		/* cells the straight-line code does not handle are queued for the general kernel (k_ends):
 		 * one atomicAdd per warp */
-		nfull += cur.si >= 0;
+		nfull += cur.si != -1;
 		uint32_t pxn[8];
-		const bool fast = cur.si >= 0 && draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, cur.r0, cur.r1, fast_ok, pxn);
-		const bool slow = cur.si >= 0 && !fast;
+		uint4 r0, r1;
+		draw_item_subs (cur, r0, r1);
+		const bool fast = cur.si != -1 && draw_cell_fast (w, f, cur.sub, cur.pix, cur.sb, r0, r1, fast_ok, pxn);
+		const bool slow = cur.si != -1 && !fast;
 		/* colour of the PREVIOUS tile's cell: its gathers were issued one iteration ago */
 		if (pend)
 			draw_cell_store (f, pendpix, pxo);
@@ -1464,7 +1488,7 @@ __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant_
 				base = atomicAdd (&f.alloc[3], (unsigned long long)__popc (sm));
 			base = __shfl_sync (0xFFFFFFFFu, base, __ffs (sm) - 1);
 			if (slow)
-				f.slowcells[base + __popc (sm & ((1u << lane) - 1u))] = make_int2 (cur.si, (int)cur.pix);
+				f.slowcells[base + __popc (sm & ((1u << lane) - 1u))] = make_int2 (RC_CELL_SPAN (cur.si), (int)cur.pix);
 		}
 #if DRAW_PF == 0
 		cur = nxt;
@@ -1502,7 +1526,7 @@ template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
-	const uint4 *sub4 = reinterpret_cast<const uint4 *>(f.sub);
+	const uint2 *bnd2 = reinterpret_cast<const uint2 *>(f.bnd);
 	unsigned long long al = f.alloc[0];
 	int nspans = (int)(al & 0xFFFFFFFFu);
 	if (nspans > f.spancap) nspans = f.spancap;
@@ -1559,14 +1583,18 @@ __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant_
 			act[q] = q >= firstq && row[q] && uq[q] < cellx + 8;
 			rel[q] = cellx - uq[q];
 		}
-		/* level 1: subdivision records of every share */
+		/* level 1: subdivisions k, k + 1 of every share from its boundary records (rc_sub_of) */
 		uint4 R0[3], R1[3];
 		#pragma unroll
 		for (int q = 0; q < 3; q++)
 		{
 			const int k = rel[q] < 0 ? 0 : rel[q] >> 3;
-			const uint4 *rp = sub4 + (act[q] ? (size_t)A[q].z * 8 + k : 0);
-			R0[q] = __ldg (rp); R1[q] = __ldg (rp + 1);
+			const int lastsub = (((int16_t)(A[q].x >> 16) + 7) >> 3) - 1;
+			const uint2 *rp = bnd2 + (act[q] ? (size_t)A[q].z * 8 + k : 0);
+			const uint2 b0 = __ldg (rp), b1 = __ldg (rp + 1), b2 = __ldg (rp + 2), b3 = __ldg (rp + 3);
+			const bool l0 = k == lastsub, l1 = k + 1 == lastsub;
+			R0[q] = make_uint4 (b0.x, b0.y, l0 ? b2.x : (uint32_t)((int)(b1.x - b0.x) >> 3), l0 ? b2.y : (uint32_t)((int)(b1.y - b0.y) >> 3));
+			R1[q] = make_uint4 (b1.x, b1.y, l1 ? b3.x : (uint32_t)((int)(b2.x - b1.x) >> 3), l1 ? b3.y : (uint32_t)((int)(b2.y - b1.y) >> 3));
 		}
 		uint32_t px[8], zq[8];
 		#pragma unroll
@@ -1657,9 +1685,10 @@ __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant_
 		const int2 *cells = reinterpret_cast<const int2 *>(f.cellspan);
 		for (unsigned t = (unsigned)(f.drawview0 * f.height) * cw + blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += gridDim.x * blockDim.x)
 		{
-			const int2 cell = __ldg (&cells[t]);
-			if (cell.x < 0)
+			int2 cell = __ldg (&cells[t]);
+			if (cell.x == -1)
 				continue;
+			cell.x = RC_CELL_SPAN (cell.x);
 			const uint4 sb = __ldg (&spans4[2 * (size_t)cell.x + 1]);
 			const unsigned row = t / cw, c = t - row * cw;
 			const uint32_t pix = row * (unsigned)f.width + (c << 3);
@@ -2000,7 +2029,7 @@ static void free_chunk (rc_gpu_t *g)
 	cudaFree (g->d_facemark); cudaFree (g->d_nodevisit); cudaFree (g->d_viewleaf);
 	cudaFree (g->d_nbsurfs); cudaFree (g->d_leafkey); g->d_nbsurfs = NULL; g->d_leafkey = NULL;
 	cudaFree (g->d_edges); cudaFree (g->d_nedges); cudaFree (g->d_surfs); cudaFree (g->d_spans);
-	cudaFree (g->d_cellspan); cudaFree (g->d_slowcells); cudaFree (g->d_jobs); cudaFree (g->d_cacheunits); g->d_cacheunits = NULL; cudaFree (g->d_segspan); cudaFree (g->d_sub);
+	cudaFree (g->d_cellspan); cudaFree (g->d_slowcells); cudaFree (g->d_jobs); cudaFree (g->d_cacheunits); g->d_cacheunits = NULL; cudaFree (g->d_segspan); cudaFree (g->d_bnd);
 	g->d_views = NULL; g->chunkcap = 0;
 }
 
@@ -2216,9 +2245,9 @@ static size_t per_view_bytes (const rc_gpu_t *g, int facecap, int edgecap, int s
 {
 	size_t lines = g->height;
 	size_t cw = (g->width + 7) / 8;
-	size_t spans = lines * g->spans_per_line, segs = spans + lines * (cw / 8 + 1);
+	size_t spans = lines * g->spans_per_line, segs = spans + spans / 4 + lines * (cw / 8 + 1);
 	return sizeof(rc_view_t) + sizeof(rc_facerec_t) * facecap + 6 * (size_t)numfaces + 8 * (size_t)g->w.numnodes + sizeof(rc_edge_t) * edgecap +
-	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + (4 + 8 * sizeof(rc_sub_t)) * segs + (sizeof(rc_cell_t) + 8) * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
+	       sizeof(rc_surf_t) * surfcap + sizeof(rc_span_t) * spans + (4 + 8 * sizeof(rc_bnd_t)) * segs + (sizeof(rc_cell_t) + 8) * cw * lines + sizeof(rc_cachejob_t) * 8 + 16;
 }
 
 static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t errlen)
@@ -2251,7 +2280,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	size_t lines = (size_t)g->height * want;
 	g->spancap = (int)(lines * g->spans_per_line < 0x7FFFFFFF ? lines * g->spans_per_line : 0x7FFFFFFF);
 	const size_t cw = (g->width + 7) / 8;
-	size_t segs = (size_t)g->spancap + lines * (cw / 8 + 1);
+	size_t segs = (size_t)g->spancap + (size_t)g->spancap / 4 + lines * (cw / 8 + 1);	/* a span needs ((nsub + 2) + 7) / 8 segments (rc_span_seg_count) */
 	g->segcap = (int)(segs < (1 << 26) - 2 ? segs : (1 << 26) - 2);	/* rc_cell_t.sub holds segment * 64 + pixel in 32 bits */
 	g->jobcap = want * 8 + 4096;
 	if (g->jobcap > want * surfcap) g->jobcap = want * surfcap;
@@ -2271,7 +2300,7 @@ static int ensure_chunk (rc_gpu_t *g, int n, int want_bsurfs, char *err, size_t 
 	CK (cudaMalloc (&g->d_cellspan, sizeof(rc_cell_t) * lines * cw));
 	CK (cudaMalloc (&g->d_slowcells, sizeof(int2) * lines * cw));
 	CK (cudaMalloc (&g->d_segspan, sizeof(int) * (size_t)g->segcap));
-	CK (cudaMalloc (&g->d_sub, sizeof(rc_sub_t) * (8 * (size_t)g->segcap + 8)));
+	CK (cudaMalloc (&g->d_bnd, sizeof(rc_bnd_t) * (8 * (size_t)g->segcap + 16)));
 	CK (cudaMalloc (&g->d_jobs, sizeof(rc_cachejob_t) * (size_t)g->jobcap));
 	g->cacheunitcap = g->jobcap * 8 + 65536;
 	CK (cudaMalloc (&g->d_cacheunits, sizeof(int2) * (size_t)g->cacheunitcap));
@@ -2297,7 +2326,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	f.edges = g->d_edges; f.edgecap = g->edgecap; f.nedges = g->d_nedges;
 	f.surfs = g->d_surfs; f.surfcap = g->surfcap; f.maxedges = g->maxedges; f.maxsurfs = g->maxsurfs;
 	f.spans = g->d_spans; f.spancap = g->spancap; f.cellspan = g->d_cellspan; f.slowcells = g->d_slowcells;
-	f.segspan = g->d_segspan; f.sub = g->d_sub; f.segcap = g->segcap;
+	f.segspan = g->d_segspan; f.bnd = g->d_bnd; f.segcap = g->segcap;
 	f.alloc = g->d_alloc;
 	f.cachekeys = g->d_cachekeys; f.cachevals = g->d_cachevals; f.cachemask = g->cacheslots - 1;
 	f.cachepool = g->d_cachepool; f.cachecap = g->cachecap;

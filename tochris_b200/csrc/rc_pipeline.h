@@ -94,7 +94,7 @@ typedef struct {
     rc_span_t *spans; int spancap;
     rc_cell_t *cellspan;          /* [nviews][height][(width+7)/8]: the span that covers ALL eight pixels of a screen cell, si -1: none */
     int *segspan; int segcap;     /* [segcap]: owning span of every 64-pixel span segment (8 subdivisions) */
-    rc_sub_t *sub;                /* [segcap * 8 + 8]: subdivision k of a span is record segbase * 8 + k */
+    rc_bnd_t *bnd;                /* [segcap * 8 + 8]: boundary b of a span is record segbase * 8 + b (rc_types.h rc_bnd_t) */
 #ifdef __CUDACC__
     int2 *slowcells;              /* GPU only: {span, first pixel} of the full cells k_draw queues for the general code; count in alloc[3] */
 #else
@@ -1420,7 +1420,15 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
  * boundary are drawn whole by one owner from the shares of their spans (rc_mixed_owner).
  * cellspan[(view, line, cell)] = {span, subdivision record of the cell's first pixel * 8 + its
  * position inside that subdivision}; si = -1 where no span covers the whole cell. */
-RC_HD int rc_span_seg_count (int count) { return (((count + 7) >> 3) + 7) >> 3; }	/* segments of 8 subdivisions = 64 pixels */
+/* segments of a span: units of 8 boundary records (and one thread of the segment kernel); nsub + 2 records are needed
+ * (B[0] .. B[nsub], the last subdivision's step) */
+RC_HD int rc_span_seg_count (int count) { return (((count + 7) >> 3) + 2 + 7) >> 3; }
+/* the span field of a cell record: the span, and where the cell (first pixel at span pixel `rel`) meets the last subdivision */
+RC_HD int rc_cell_si (int si, int rel, int count)
+{
+	const int k = rel >> 3, last = ((count + 7) >> 3) - 1;
+	return (int)((unsigned)si | (k == last ? (unsigned)RC_CELL_L0 : 0u) | (k + 1 == last ? RC_CELL_L1 : 0u));
+}
 
 RC_HD void rc_write_span (const rc_frame_t *f, const rc_view_t *vw, int vi, int line, int si, int surf, int u0, int count, int segbase)
 {
@@ -1465,7 +1473,7 @@ RC_HD void rc_line_publish (const rc_frame_t *f, const rc_view_t *vw, rc_surf_t 
 		rc_write_span (f, vw, vi, line, spanbase + i, ls->surf[i], u0, cnt, segbase);
 		for (int c = (u0 + 7) >> 3; (c << 3) + 8 <= u0 + cnt; c++)
 		{
-			cells[c].si = spanbase + i;
+			cells[c].si = rc_cell_si (spanbase + i, (c << 3) - u0, cnt);
 			cells[c].sub = (uint32_t)(segbase * 8) * 8u + (uint32_t)((c << 3) - u0);
 		}
 		for (int q = rc_span_seg_count (cnt); q > 0; q--)
@@ -1954,19 +1962,37 @@ RC_HD rc_span_t rc_load_span (const rc_span_t *p)
 	s.iziorg = (int)b.x; s.izistep = (int)b.y; s.cacheofs = (int)b.z; s.cwk = b.w;
 	return s;
 }
-RC_HD rc_sub_t rc_load_sub (const rc_sub_t *p)
+RC_HD rc_bnd_t rc_load_bnd (const rc_bnd_t *p)
 {
-	const uint4 a = __ldg (reinterpret_cast<const uint4 *>(p));
-	rc_sub_t r;
-	r.s = (int)a.x; r.t = (int)a.y; r.sstep = (int)a.z; r.tstep = (int)a.w;
+	const uint2 a = __ldg (reinterpret_cast<const uint2 *>(p));
+	rc_bnd_t r;
+	r.s = (int)a.x; r.t = (int)a.y;
 	return r;
 }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return __byte_perm (a, b, 0x5410); }
 #else
 RC_HD rc_span_t rc_load_span (const rc_span_t *p) { return *p; }
-RC_HD rc_sub_t rc_load_sub (const rc_sub_t *p) { return *p; }
+RC_HD rc_bnd_t rc_load_bnd (const rc_bnd_t *p) { return *p; }
 RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 16); }
 #endif
+
+/* subdivision k of a span from its boundary records (rp = the span's record k; last: k is the span's last subdivision) */
+RC_HD rc_sub_t rc_sub_of (const rc_bnd_t *rp, int last)
+{
+	const rc_bnd_t b0 = rc_load_bnd (rp), b1 = rc_load_bnd (rp + 1);
+	rc_sub_t r;
+	r.s = b0.s; r.t = b0.t;
+	if (last)
+	{
+		const rc_bnd_t st = rc_load_bnd (rp + 2);
+		r.sstep = st.s; r.tstep = st.t;
+	}
+	else
+	{
+		r.sstep = (b1.s - b0.s) >> 3; r.tstep = (b1.t - b0.t) >> 3;
+	}
+	return r;
+}
 
 /* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
  * D_DrawSpans8 (d_scan.c:278-365) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
@@ -1974,10 +2000,11 @@ RC_HD uint32_t rc_zpair (uint32_t a, uint32_t b) { return (a & 0xFFFFu) | (b << 
  *        b = 0              span start, clamped to [0, bbextent]
  *        0 < b < nsub       after b steps of 8 pixels, clamped to [8, bbextent]   (`snext` of subdivision b-1)
  *        b = nsub           the span's last pixel: nsub-1 steps of 8, then left-1 single steps
- * the record of subdivision k is {B[k], step}: step = (B[k+1] - B[k]) >> 3 (d_scan.c:334-335), and for the
- * last subdivision (B[nsub] - B[nsub-1]) / (left - 1) truncated (d_scan.c:364-365) -- the draw kernel
- * never divides.  Segment 0 also completes the span record with what the draw kernel needs of the
- * surface: 1/z start and step, texel block and pitch, kind.
+ * subdivision k is {B[k], step}: step = (B[k+1] - B[k]) >> 3 (d_scan.c:334-335), and for the last subdivision
+ * (B[nsub] - B[nsub-1]) / (left - 1) truncated (d_scan.c:364-365).  What is stored per span is B[0] .. B[nsub] and
+ * that one divided step (rc_bnd_t, 8 B each: 1 B per pixel where records of {B[k], step} were 2): the draw kernels
+ * take the other steps from two neighbouring records and never divide.  Segment 0 also completes the span record with
+ * what the draw kernel needs of the surface: 1/z start and step, texel block and pitch, kind.
  * The accumulators of D_DrawSpans8 are sequentially rounded float sums, so boundary b costs b
  * adds: the segment replays the cheap adds from the span start and does the divide / convert /
  * clamp only for its own boundaries. */
@@ -2011,8 +2038,9 @@ RC_HD rc_segsurf_t rc_load_segsurf (const rc_surf_t *s)
 }
 
 /* `stage` (GPU): the thread's eight records go to this (shared-memory) slot, record i at index i ^ swz, and the
- * caller copies them out; returns 1 when records were produced */
-RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_sub_t *stage = 0, int swz = 0)
+ * caller copies the first `return value` of them out (0: none -- not a textured span, or a segment past the last
+ * subdivision) */
+RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_bnd_t *stage = 0, int swz = 0)
 {
 	const int si = f->segspan[seg];
 	rc_span_t *spp = &f->spans[si];
@@ -2108,49 +2136,52 @@ RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_sub
 		if (tt > bbextentt) tt = bbextentt; else if (tt < lo) tt = lo;
 		st[2 * i] = ss; st[2 * i + 1] = tt;
 	}
-	/* per-pixel steps; the one truncating division of the span is done once, outside the unrolled loop */
-	int stp[16];
-	#pragma unroll
-	for (int i = 0; i < 8; i++)
+	/* this segment's own records: boundaries 8 sidx .. that are subdivision starts (b < nsub) */
+	int nvalid = nsub - (sidx << 3);
+	if (nvalid > 8) nvalid = 8;
+	if (nvalid < 0) nvalid = 0;
+	rc_bnd_t *out = f->bnd + (size_t)seg * 8;
 	{
-		stp[2 * i] = (st[2 * i + 2] - st[2 * i]) >> 3;
-		stp[2 * i + 1] = (st[2 * i + 3] - st[2 * i + 1]) >> 3;
-	}
-	{
+		/* the segment that holds the LAST subdivision also writes what follows it: B[nsub] (the last pixel's
+		 * coordinates) and the subdivision's per-pixel step -- the one truncating division of a span (d_scan.c:364-365).
+		 * These two records may lie in the next segment's block; its thread leaves them alone (b >= nsub) */
 		const int il = nsub - 1 - (sidx << 3);			/* the last subdivision's place in this segment */
 		if (il >= 0 && il < 8)
 		{
 			const int lastn = count - ((nsub - 1) << 3);		/* its pixels */
-			int ds_ = 0, dt_ = 0;
+			int ds_ = 0, dt_ = 0, es_ = 0, et_ = 0;
 			#pragma unroll
 			for (int i = 0; i < 8; i++)
-				if (i == il) { ds_ = st[2 * i + 2] - st[2 * i]; dt_ = st[2 * i + 3] - st[2 * i + 1]; }
+				if (i == il) { es_ = st[2 * i + 2]; et_ = st[2 * i + 3]; ds_ = es_ - st[2 * i]; dt_ = et_ - st[2 * i + 1]; }
 			const int sstep = lastn > 1 ? ds_ / (lastn - 1) : 0, tstep = lastn > 1 ? dt_ / (lastn - 1) : 0;
-			#pragma unroll
-			for (int i = 0; i < 8; i++)
-				if (i == il) { stp[2 * i] = sstep; stp[2 * i + 1] = tstep; }
+#ifdef __CUDACC__
+			reinterpret_cast<uint2 *>(out)[il + 1] = make_uint2 ((uint32_t)es_, (uint32_t)et_);
+			reinterpret_cast<uint2 *>(out)[il + 2] = make_uint2 ((uint32_t)sstep, (uint32_t)tstep);
+#else
+			out[il + 1].s = es_; out[il + 1].t = et_; out[il + 2].s = sstep; out[il + 2].t = tstep;
+#endif
 		}
 	}
-	/* records past the last subdivision are never used: all eight are written, one 16-byte store each */
-	rc_sub_t *out = f->sub + (size_t)seg * 8;
 #ifdef __CUDACC__
 	if (stage)
 	{
+		/* (all eight slots are staged; the caller copies the first nvalid out) */
 		#pragma unroll
 		for (int i = 0; i < 8; i++)
-			reinterpret_cast<uint4 *>(stage)[i ^ swz] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)stp[2*i], (uint32_t)stp[2*i+1]);
-		return 1;
+			reinterpret_cast<uint2 *>(stage)[i ^ swz] = make_uint2 ((uint32_t)st[2*i], (uint32_t)st[2*i+1]);
+		return nvalid;
 	}
 	#pragma unroll
 	for (int i = 0; i < 8; i++)
-		reinterpret_cast<uint4 *>(out)[i] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)stp[2*i], (uint32_t)stp[2*i+1]);
+		if (i < nvalid)
+			reinterpret_cast<uint2 *>(out)[i] = make_uint2 ((uint32_t)st[2*i], (uint32_t)st[2*i+1]);
 #else
-	for (int i = 0; i < 8; i++)
+	for (int i = 0; i < nvalid; i++)
 	{
-		out[i].s = st[2*i]; out[i].t = st[2*i+1]; out[i].sstep = stp[2*i]; out[i].tstep = stp[2*i+1];
+		out[i].s = st[2*i]; out[i].t = st[2*i+1];
 	}
 #endif
-	return 1;
+	return nvalid;
 }
 
 /* The part of span `sp` that lies inside one 8-pixel window, general form (D_DrawSpans8 d_scan.c:254-386 /
@@ -2274,11 +2305,12 @@ RC_HD unsigned rc_cell_part (const rc_world_t *w, const rc_frame_t *f, const rc_
 		const uint8_t *pbase = (kind == RC_KIND_POOL ? f->cachepool : w->texels) + sp.cacheofs;
 		/* a span that starts inside the window: subdivision 0 from window pixel -rel on (a < 0, no crossing) */
 		const int k = rel < 0 ? 0 : rel >> 3, a = rel < 0 ? rel : rel & 7;
-		const rc_sub_t *rp = f->sub + (size_t)sp.segbase * 8 + k;
-		const rc_sub_t r0 = rc_load_sub (rp);
+		const rc_bnd_t *rp = f->bnd + (size_t)sp.segbase * 8 + k;
+		const int lastsub = ((sp.count + 7) >> 3) - 1;
+		const rc_sub_t r0 = rc_sub_of (rp, k == lastsub);
 		rc_sub_t r1 = r0;
 		if (a + hi > 8)		/* the window runs on into subdivision k+1 */
-			r1 = rc_load_sub (rp + 1);
+			r1 = rc_sub_of (rp + 1, k + 1 == lastsub);
 		int sstep = r0.sstep, tstep = r0.tstep;
 		int ss = rc_addw (r0.s, rc_mulw (a, sstep)), tt = rc_addw (r0.t, rc_mulw (a, tstep));
 		const int *turbtab = w->sintable;
@@ -2380,9 +2412,10 @@ RC_HD void rc_draw_pixels (const rc_world_t *w, const rc_frame_t *f, const rc_sp
 RC_HD void rc_draw_cell (const rc_world_t *w, const rc_frame_t *f, int row, int c)
 {
 	const int cw = (f->width + 7) >> 3;
-	const int si = f->cellspan[(size_t)row * cw + c].si;
-	if (si < 0)
+	const int cs = f->cellspan[(size_t)row * cw + c].si;
+	if (cs == -1)
 		return;
+	const int si = RC_CELL_SPAN (cs);
 	const rc_span_t sp = rc_load_span (&f->spans[si]);
 	rc_draw_pixels (w, f, sp, (c << 3) - sp.u, true);
 }

@@ -266,12 +266,27 @@ typedef struct {            /* espan_t replacement (r_shared.h:117-121) + everyt
 #define RC_SPAN_WARPBIT 0x80000u
 
 typedef struct {            /* one 8-pixel subdivision of a span (d_scan.c:278-365): 16.16 texture coordinates of its
-                             * first pixel and the per-pixel step the reference uses inside it */
+                             * first pixel and the per-pixel step the reference uses inside it (in registers; what is
+                             * stored are the boundary records below) */
     int s, t, sstep, tstep;
 } rc_sub_t;
 
+typedef struct {            /* 8 B: the 16.16 (s, t) at one subdivision boundary of a span.  A span with nsub subdivisions
+                             * owns records [segbase * 8 .. + nsub + 1]: B[0] .. B[nsub] (B[nsub] = the last pixel's
+                             * coordinates), then one record holding the per-pixel step of the LAST subdivision (the one
+                             * step that is a truncating division, d_scan.c:364-365; every other step is
+                             * (B[k+1] - B[k]) >> 3, :334-335, which the draw kernels take from two neighbouring records) */
+    int s, t;
+} rc_bnd_t;
+
+/* cell records flag where a cell touches the span's last subdivision, so that the draw kernel knows which of its two
+ * steps to read instead of derive */
+#define RC_CELL_L0     0x40000000          /* the subdivision of the cell's first pixel is the span's last */
+#define RC_CELL_L1     0x80000000u         /* the following one is */
+#define RC_CELL_SPAN(x) ((int)((x) & 0x3FFFFFFF))
+
 typedef struct {            /* draw work item: a screen-aligned 8-pixel cell covered by one span */
-    int      si;            /* span, -1: none (the cell is drawn by span heads / tails, or lies outside the view rectangle) */
+    int      si;            /* span (| RC_CELL_L0 | RC_CELL_L1), -1: none (the cell is drawn by span heads / tails, or lies outside the view rectangle) */
     uint32_t sub;           /* (segbase * 8 + k) << 3 | a: the subdivision record of the cell's first pixel and its position in it */
 } rc_cell_t;
 

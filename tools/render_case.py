@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--async-calls", type=int, default=0, help="also run this many pipelined RC_RenderViewsAsync calls")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--device", action="store_true", help="outputs stay on the device (RC_RenderViewsDevice on a torch stream): the plain path, one k_draw launch over all views")
     ap.add_argument("--flush", action="store_true", help="D_FlushCaches before every repetition (every render rebuilds its surface cache blocks)")
     for k in ("entities", "particles", "sprites", "doors", "dlights", "underwater_every"):
         ap.add_argument("--" + k, type=int, default=0)
@@ -36,10 +37,21 @@ def main():
     r = RefCuda(base, a.w, a.h)
     r.load_world(f"maps/{a.scene}.bsp")
     rds = views.build_refdefs(specs, a.w, a.h, model_resolver=r.model)
+    if a.device:
+        import torch
+        dfb = torch.empty((a.n, a.h, a.w), dtype=torch.uint8, device="cuda")
+        dz = torch.empty((a.n, a.h, a.w), dtype=torch.int16, device="cuda")
+        stream = torch.cuda.Stream()
     for _ in range(a.reps):
         if a.flush:
             r.flush_caches()
-        fb, z, st = r.render(rds)
+        if a.device:
+            with torch.cuda.stream(stream):
+                st = r.render_device(rds, a.n, dfb.data_ptr(), dz.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            fb, z = dfb.cpu().numpy(), dz.cpu().numpy()
+        else:
+            fb, z, st = r.render(rds)
     print("render_case: status", status_names(st), "launches", r.stats()["kernel_launches"])
     if a.async_calls:
         import numpy as np
