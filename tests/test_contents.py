@@ -5,10 +5,24 @@ import numpy as np
 import rcutil
 
 
+import pytest
+
+
 def test_point_contents_match_reference(assets_dir, sim_lib, oracle_available):
-    import pytest
     if not oracle_available:
         pytest.skip("oracle/_ref not built")
+    _contents_case(assets_dir, sim_lib)
+
+
+@pytest.mark.gpu
+def test_point_contents_match_reference_gpu(assets_dir, oracle_available):
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from tochris_b200 import api
+    _contents_case(assets_dir, api.LIBPATH)
+
+
+def _contents_case(assets_dir, sim_lib):
     from oracle.refsoft import RefSoft
     from tochris_b200.api import RefCuda
     import multiprocessing as mp

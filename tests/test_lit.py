@@ -36,6 +36,20 @@ def write_lit(assets_dir, mapname, version=1, magic=b"QLIT", seed=7):
 def test_lit_lighting(assets_dir, sim_lib, oracle_available, version, magic, used):
     if not oracle_available:
         pytest.skip("oracle/_ref not built")
+    _lit_case(assets_dir, sim_lib, version, magic, used)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version,magic,used", [(1, b"QLIT", True), (2, b"QLIT", False)])
+def test_lit_lighting_gpu(assets_dir, oracle_available, version, magic, used):
+    """the same through libref_cuda.so: the loader is host code, the samples end up in the device's lightdata"""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from tochris_b200 import api
+    _lit_case(assets_dir, api.LIBPATH, version, magic, used)
+
+
+def _lit_case(assets_dir, sim_lib, version, magic, used):
     from oracle import run_oracle
     assert write_lit(assets_dir, "small", version, magic) > 0
     mdir = os.path.join(assets_dir, "id1", "maps")
