@@ -65,6 +65,7 @@ struct rc_gpu_s {
 	rc_surf_t *d_surfs;
 	rc_span_t *d_spans; rc_cell_t *d_cellspan; int2 *d_slowcells;
 	int *d_segspan; rc_bnd_t *d_bnd;
+	int front_256, front_csize;
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -1989,6 +1990,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	 * general cells itself, RC_SCAN_LARGE start with the large scan instance, RC_NO_GRAPH no CUDA-graph replay,
 	 * RC_FRONT_512 512-thread front-end CTAs on many-view batches */
 	g->front_512 = getenv ("RC_FRONT_512") ? 1 : 0;
+	g->front_256 = getenv ("RC_FRONT_256") ? 1 : 0;
+	{ const char *e = getenv ("RC_FRONT_CSIZE"); g->front_csize = e ? atoi (e) : 0; if (g->front_csize != 1 && g->front_csize != 2 && g->front_csize != 4 && g->front_csize != 8) g->front_csize = 0; }
 	g->scan_serial = getenv ("RC_SCAN_SERIAL") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
@@ -2375,7 +2378,9 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaLaunchConfig_t cfg;
 		cudaLaunchAttribute attr[1];
 		memset (&cfg, 0, sizeof(cfg));
-		const bool manyviews = n > g->numsms && !g->front_512;	/* more views than SMs: several waves */
+		bool manyviews = n > g->numsms && !g->front_512;	/* more views than SMs: several waves */
+		if (g->front_csize > 0) csize = g->front_csize;		/* experiments: RC_FRONT_CSIZE / RC_FRONT_256 */
+		if (g->front_256) manyviews = true;
 		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? FRONT_MANY : FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
