@@ -117,6 +117,13 @@ void rc_gpu_flush_caches (rc_gpu_t *g)
 	g->alloc[1] = RC_SKYBOX_BYTES;		/* the pool starts after the sky-box pictures */
 }
 
+/* large batches in parts: a device matter (the host's set-up overlapping the device's work); the simulator never splits */
+int rc_gpu_can_split (const rc_gpu_t *g) { (void)g; return 0; }
+int rc_gpu_render_begin (rc_gpu_t *g, void *fb_dev, void *stream) { (void)g; (void)fb_dev; (void)stream; return RC_OK; }
+int rc_gpu_render_part (rc_gpu_t *g, const rc_batch_t *part, void *fb_part, void *z_part, void *stream, int first_part, char *err, size_t errlen)
+{ (void)g; (void)part; (void)fb_part; (void)z_part; (void)stream; (void)first_part; snprintf (err, errlen, "the simulator does not split batches"); return RC_ERR_ARG; }
+int rc_gpu_render_finish (rc_gpu_t *g, void *fb_dev, void *z_dev, int n, void *stream, int *status, char *err, size_t errlen)
+{ (void)g; (void)fb_dev; (void)z_dev; (void)n; (void)stream; (void)status; (void)err; (void)errlen; return RC_ERR_ARG; }
 int rc_gpu_device_alloc (rc_gpu_t *g, size_t bytes, void **ptr) { (void)g; *ptr = malloc (bytes); return *ptr ? RC_OK : RC_ERR_NOMEM; }
 void rc_gpu_device_free (rc_gpu_t *g, void *ptr) { (void)g; free (ptr); }
 int rc_gpu_ipc_export (rc_gpu_t *g, void *ptr, unsigned char *handle) { (void)g; (void)ptr; (void)handle; return RC_ERR_CUDA; }

@@ -125,6 +125,54 @@ def test_c4_full_batch_properties(assets_dir, oracle_available):
     assert r["same"]
 
 
+def _parts_worker(q, libpath, basedir, reps):
+    try:
+        import torch
+        from tochris_b200.api import RefCuda
+        from tochris_b200.scenes import views
+        base = rcutil.scene_views("full", 256, time=0.3, time_step=0.02, entities=3, particles=40, underwater_every=37)
+        r = RefCuda(basedir, 160, 120, libpath=libpath)
+        r.load_world("maps/full.bsp")
+        rds = views.build_refdefs(base * reps, 160, 120, model_resolver=r.model)
+        n = len(rds)
+        fb = torch.zeros((n, 120, 160), dtype=torch.uint8, device="cuda")
+        z = torch.zeros((n, 120, 160), dtype=torch.int16, device="cuda")
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            st = r.render_device(rds, n, fb.data_ptr(), z.data_ptr(), stream.cuda_stream)      # n >= 2048: drawn in parts
+        torch.cuda.synchronize()
+        launches_parts = r.stats()["kernel_launches"]
+        fbh = fb.cpu().numpy().reshape(reps, 256, 120, 160); zh = z.cpu().numpy().reshape(reps, 256, 120, 160)
+        same = bool((fbh == fbh[0:1]).all() and (zh == zh[0:1]).all())
+        q.put(("ok", dict(status=st, same=same, fb=fbh[0].copy(), z=zh[0].copy(), n=n, launches=launches_parts)))
+        r.shutdown()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put(("err", traceback.format_exc()))
+
+
+def test_large_device_batches_drawn_in_parts(assets_dir, oracle_available):
+    """RC_RenderViewsDevice draws a batch of 2048 views or more in parts (the host sets up part k+1 while the device draws
+    part k; status words accumulate, one wait at the end): 9 x 256 cameras with entities, particles and
+    under-water views -- every repetition byte-identical to the first, the first equal to the reference."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    import multiprocessing as mp
+    from oracle import run_oracle
+    base = rcutil.scene_views("full", 256, time=0.3, time_step=0.02, entities=3, particles=40, underwater_every=37)
+    o = run_oracle.render(assets_dir, "maps/full.bsp", 160, 120, base)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_parts_worker, args=(q, api.LIBPATH, assets_dir, 9))
+    p.start()
+    kind, r = q.get(timeout=1800)
+    p.join(timeout=60)
+    assert kind == "ok", r
+    assert r["n"] == 2304 and r["status"] & ~rcutil.RC_STAT_ALIAS_RANGE == 0, api.status_names(r["status"])
+    rcutil.assert_parity(o, dict(fb=r["fb"], z=r["z"], status=r["status"]), base, 160, 120)
+    assert r["same"]
+
+
 @pytest.mark.gpu
 def test_async_pipeline_matches_blocking_call(assets_dir):
     """RC_RenderViewsAsync / RC_WaitViews (up to three batches outstanding, copies overlapping the next batches' kernels)

@@ -695,9 +695,53 @@ int RC_WaitViews (int *status)
 	return rc_gpu_wait_host (rc.gpu, status, rc.err, sizeof(rc.err));
 }
 
+/* a large batch is drawn in about eight parts of at least RC_PART_MIN views (below) */
+#define RC_PART_MIN 1024
+
 int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
 {
-	int r = rc_prepare_views (views, n);
+	int r;
+	if (rc.inited && views && fb_dev && n >= 2 * RC_PART_MIN && rc_gpu_can_split (rc.gpu))
+	{
+		const int part = ((n + 7) / 8 + 255) / 256 * 256 > RC_PART_MIN ? ((n + 7) / 8 + 255) / 256 * 256 : RC_PART_MIN;
+		/* a large batch (BASELINE config C4: 65,536 views per call) in parts: the set-up of part k+1 -- 5 ms of host
+		 * work and 47 MB of view records for the whole of C4 -- runs while the device draws part k */
+		const size_t px = (size_t)rc.vid.width * rc.vid.height;
+		int first, st = 0;
+		r = rc_gpu_render_begin (rc.gpu, fb_dev, stream);
+		for (first = 0; r == RC_OK && first < n; first += part)
+		{
+			const int cnt = n - first < part ? n - first : part;
+			r = rc_prepare_views (views + first, cnt);
+			if (r == RC_OK)
+				r = rc_gpu_render_part (rc.gpu, &rc.batch, (uint8_t *)fb_dev + px * (size_t)first,
+							z_dev ? (void *)((int16_t *)z_dev + px * (size_t)first) : NULL, stream, first == 0, rc.err, sizeof(rc.err));
+		}
+		if (r == RC_OK)
+			r = rc_gpu_render_finish (rc.gpu, fb_dev, z_dev, n, stream, &st, rc.err, sizeof(rc.err));
+		if (r != RC_OK)
+		{
+			int dummy;
+			rc_gpu_render_finish (rc.gpu, fb_dev, z_dev, 0, stream, &dummy, rc.err, sizeof(rc.err));	/* drain what was enqueued */
+			return r;
+		}
+		if (!(st & (RC_STAT_SPAN_POOL | RC_STAT_CACHE_POOL | RC_STAT_AET_OVERFLOW)))
+		{
+			if (status) *status = st;
+			return RC_OK;
+		}
+		/* a pool ran out in one of the parts: the whole batch again in one piece, which grows the pools and retries */
+	}
+	if (getenv ("RC_PREP_TIMING"))
+	{
+		struct timespec t0, t1;
+		clock_gettime (CLOCK_MONOTONIC, &t0);
+		r = rc_prepare_views (views, n);
+		clock_gettime (CLOCK_MONOTONIC, &t1);
+		fprintf (stderr, "rc_prepare_views: %d views %.3f ms (%d threads)\n", n, 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec), rc.host_threads);
+	}
+	else
+	r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
 	r = rc_gpu_render (rc.gpu, &rc.batch, fb_dev, z_dev, stream, status, rc.err, sizeof(rc.err));

@@ -38,6 +38,9 @@
 
 
 #define RC_GRAPHS 4
+#define RC_RF_KEEP_STATUS 1	/* rc_gpu_render_part: the status words are not cleared */
+#define RC_RF_DEFER       2	/* nothing waits, no CUDA graph */
+#define RC_RF_NO_MIRROR   4	/* the mirror copy is the caller's */
 
 struct rc_gpu_s {
 	int device, width, height, numsms;
@@ -66,6 +69,7 @@ struct rc_gpu_s {
 	rc_span_t *d_spans; rc_cell_t *d_cellspan; int2 *d_slowcells;
 	int *d_segspan; rc_bnd_t *d_bnd;
 	int front_256, front_csize;
+	int rflags;			/* RC_RF_* of the call being enqueued (rc_gpu_render_part) */
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -150,6 +154,9 @@ struct rc_gpu_s {
 #ifndef FRONT_MANY
 #define FRONT_MANY 256
 #endif
+#ifndef FRONT_MANY_MINB
+#define FRONT_MANY_MINB 3	/* CTAs per SM of the 256-thread instance (many-view batches): 85 registers */
+#endif
 #define FRONT_EDGE_SLOTS 1024
 #define FRONT_FIXLIST 1024
 #define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
@@ -173,7 +180,7 @@ __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
  * two CTAs per SM -- when there are more views than SMs: the phases are latency bound, so two views per SM nearly
  * double the front end's throughput on many-view batches (160x120 x 4096: 1.03 -> 0.6 ms) */
 template <int FT>
-__global__ void __launch_bounds__(FT) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+__global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster ();
@@ -2340,7 +2347,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	/* The plain device path (no entities, no warp views, no per-group consumers, no profiling) is a fixed sequence of
 	 * memsets and kernels on two streams whose parameters only change with the world or the buffers: it is captured
 	 * into a CUDA graph once and relaunched, which removes the launch gaps and the event round trips of the forks. */
-	const bool capturable = g->use_graphs && !timed && s != cudaStreamLegacy && !g->host_fb && !g->groupfn && !anywarp &&
+	const bool capturable = g->use_graphs && !(g->rflags & RC_RF_DEFER) && !timed && s != cudaStreamLegacy && !g->host_fb && !g->groupfn && !anywarp &&
 		!(g->cur_batch && (g->cur_batch->nzres || g->cur_batch->nbents));
 	rc_frame_t f0;
 	memcpy (&f0, &f, sizeof(f));
@@ -2369,7 +2376,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		CK (cudaStreamBeginCapture (s, cudaStreamCaptureModeThreadLocal));
 		capture.on = true;
 	}
-	k_reset_chunk<<<1, 32, 0, s>>> (g->d_alloc, first_view == 0 ? g->d_status : NULL);
+	k_reset_chunk<<<1, 32, 0, s>>> (g->d_alloc, (first_view == 0 && !(g->rflags & RC_RF_KEEP_STATUS)) ? g->d_status : NULL);
 
 	{
 		/* cluster size: as many CTAs per view as fit the machine in one wave, at most 8 */
@@ -2663,6 +2670,37 @@ static void collect_stats (rc_gpu_t *g, int n, bool timed)
 	}
 }
 
+/* deferred mirror: a copy of an earlier batch may still be reading this frame buffer */
+static void mirror_wait_pending (rc_gpu_t *g, const void *fb_dev, cudaStream_t s)
+{
+	for (int i = 0; i < 4; i++)
+		if (g->mpend[i].valid && g->mpend[i].fb == fb_dev)
+			cudaStreamWaitEvent (s, g->mpend[i].ev, 0);
+}
+
+/* deferred mirror: the whole batch goes to the mirror on the copy stream; nothing on `s` waits for it */
+static int mirror_enqueue (rc_gpu_t *g, void *fb_dev, void *z_dev, int n, cudaStream_t s, char *err, size_t errlen)
+{
+	const size_t px = (size_t)g->width * g->height;
+	int slot = -1;
+	for (int i = 0; i < 4 && slot < 0; i++) if (g->mpend[i].valid && g->mpend[i].fb == fb_dev) slot = i;
+	for (int i = 0; i < 4 && slot < 0; i++) if (!g->mpend[i].valid) slot = i;
+	if (slot < 0)
+	{
+		/* more than four frame buffers in rotation: the oldest entry is waited for and reused */
+		slot = 0;
+		CK (cudaEventSynchronize (g->mpend[0].ev));
+	}
+	CK (cudaEventRecord (g->evrender, s));
+	CK (cudaStreamWaitEvent (g->copystream, g->evrender, 0));
+	CK (cudaMemcpyAsync (g->mirror_fb, fb_dev, px * n, cudaMemcpyDefault, g->copystream));
+	if (g->mirror_z && z_dev)
+		CK (cudaMemcpyAsync (g->mirror_z, z_dev, px * n * sizeof(int16_t), cudaMemcpyDefault, g->copystream));
+	CK (cudaEventRecord (g->mpend[slot].ev, g->copystream));
+	g->mpend[slot].fb = fb_dev; g->mpend[slot].valid = 1;
+	return RC_OK;
+}
+
 int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
 		   int *status, char *err, size_t errlen)
 {
@@ -2671,16 +2709,11 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	/* NULL is the legacy default stream (include/ref_cuda.h): a caller on the default stream is ordered with its own
 	 * producers and consumers.  The host-output paths pass the renderer's own stream explicitly. */
 	cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
-	const bool deferred = !g->host_fb && g->mirror_fb && g->mirror_deferred;
-	const bool mirrored = !g->host_fb && g->mirror_fb && !deferred;
+	const bool deferred = !(g->rflags & RC_RF_NO_MIRROR) && !g->host_fb && g->mirror_fb && g->mirror_deferred;
+	const bool mirrored = !(g->rflags & RC_RF_NO_MIRROR) && !g->host_fb && g->mirror_fb && !deferred;
 	if (mirrored) { g->host_fb = g->mirror_fb; g->host_z = z_dev ? g->mirror_z : NULL; }
 	if (deferred)
-	{
-		/* a copy of an earlier batch may still be reading this frame buffer */
-		for (int i = 0; i < 4; i++)
-			if (g->mpend[i].valid && g->mpend[i].fb == fb_dev)
-				CK (cudaStreamWaitEvent (s, g->mpend[i].ev, 0));
-	}
+		mirror_wait_pending (g, fb_dev, s);
 	struct unmirror_t { rc_gpu_t *g; bool on; ~unmirror_t () { if (on) { g->host_fb = NULL; g->host_z = NULL; } } } unmirror = { g, mirrored };
 	size_t px = (size_t)g->width * g->height;
 	int st = 0;
@@ -2810,6 +2843,8 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 				if (g->profiling) collect_stats (g, cn, true);
 			}
 		}
+		if (g->rflags & RC_RF_DEFER)
+			break;		/* one part of a large batch: nothing waits here, rc_gpu_render_finish reads the status */
 		if (g->amode)
 		{
 			/* pipelined call: the status lands in pinned memory, nothing waits here; a pool overflow is
@@ -2858,27 +2893,60 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 	}
 	if (deferred)
 	{
-		/* the whole batch goes to the mirror on the copy stream; nothing on `s` waits for it */
-		int slot = -1;
-		for (int i = 0; i < 4 && slot < 0; i++) if (g->mpend[i].valid && g->mpend[i].fb == fb_dev) slot = i;
-		for (int i = 0; i < 4 && slot < 0; i++) if (!g->mpend[i].valid) slot = i;
-		if (slot < 0)
-		{
-			/* more than four frame buffers in rotation: the oldest entry is waited for and reused */
-			slot = 0;
-			CK (cudaEventSynchronize (g->mpend[0].ev));
-		}
-		CK (cudaEventRecord (g->evrender, s));
-		CK (cudaStreamWaitEvent (g->copystream, g->evrender, 0));
-		CK (cudaMemcpyAsync (g->mirror_fb, fb_dev, px * n, cudaMemcpyDefault, g->copystream));
-		if (g->mirror_z && z_dev)
-			CK (cudaMemcpyAsync (g->mirror_z, z_dev, px * n * sizeof(int16_t), cudaMemcpyDefault, g->copystream));
-		CK (cudaEventRecord (g->mpend[slot].ev, g->copystream));
-		g->mpend[slot].fb = fb_dev; g->mpend[slot].valid = 1;
+		const int mr = mirror_enqueue (g, fb_dev, z_dev, n, s, err, errlen);
+		if (mr != RC_OK) return mr;
 	}
 	g->launches_total += g->stats.kernel_launches;
 	g->last_n = n < g->chunkcap ? n : g->chunkcap;
 	if (status) *status = st;
+	return RC_OK;
+}
+
+/* Large batches in parts (RC_RenderViewsDevice): the host sets up part k+1 -- per-view constants on all its threads, the
+ * upload of the view records -- while the device draws part k.  A part is enqueued like a call of its own but nothing
+ * waits for it, the status words accumulate over the parts, the CUDA-graph cache is left alone (every part has its own
+ * output pointer) and the mirror copy is left to the end of the whole batch. */
+int rc_gpu_can_split (const rc_gpu_t *g)
+{
+	return !g->profiling && !g->host_fb && !g->groupfn && !g->amode;
+}
+
+int rc_gpu_render_begin (rc_gpu_t *g, void *fb_dev, void *stream)
+{
+	if (g->mirror_fb && g->mirror_deferred)
+		mirror_wait_pending (g, fb_dev, stream ? (cudaStream_t)stream : cudaStreamLegacy);
+	return RC_OK;
+}
+
+int rc_gpu_render_part (rc_gpu_t *g, const rc_batch_t *part, void *fb_part, void *z_part, void *stream, int first_part, char *err, size_t errlen)
+{
+	g->rflags = RC_RF_DEFER | RC_RF_NO_MIRROR | (first_part ? 0 : RC_RF_KEEP_STATUS);
+	const int r = rc_gpu_render (g, part, fb_part, z_part, stream, NULL, err, errlen);
+	g->rflags = 0;
+	return r;
+}
+
+/* the end of a batch drawn in parts: the mirror copy of the whole batch, then the status of all parts (this waits) */
+int rc_gpu_render_finish (rc_gpu_t *g, void *fb_dev, void *z_dev, int n, void *stream, int *status, char *err, size_t errlen)
+{
+	cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+	const size_t px = (size_t)g->width * g->height;
+	if (g->mirror_fb && g->mirror_deferred)
+	{
+		const int mr = mirror_enqueue (g, fb_dev, z_dev, n, s, err, errlen);
+		if (mr != RC_OK) return mr;
+	}
+	else if (g->mirror_fb)
+	{
+		CK (cudaMemcpyAsync (g->mirror_fb, fb_dev, px * n, cudaMemcpyDefault, s));
+		if (g->mirror_z && z_dev)
+			CK (cudaMemcpyAsync (g->mirror_z, z_dev, px * n * sizeof(int16_t), cudaMemcpyDefault, s));
+	}
+	int stw[2] = { 0, 0 };
+	CK (cudaMemcpyAsync (stw, g->d_status, sizeof(stw), cudaMemcpyDeviceToHost, s));
+	CK (cudaStreamSynchronize (s));
+	g->stats.alias_range_events = stw[1];
+	if (status) *status = stw[0];
 	return RC_OK;
 }
 

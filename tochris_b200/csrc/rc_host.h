@@ -158,6 +158,10 @@ int  rc_gpu_upload_world (rc_gpu_t *g, const rc_hostworld_t *hw, int maxedges, i
 /* renders n prepared views; fb_dev/z_dev are device pointers (z may be NULL) */
 int  rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_dev, void *stream,
                     int *status, char *err, size_t errlen);
+int  rc_gpu_can_split (const rc_gpu_t *g);
+int  rc_gpu_render_begin (rc_gpu_t *g, void *fb_dev, void *stream);
+int  rc_gpu_render_part (rc_gpu_t *g, const rc_batch_t *part, void *fb_part, void *z_part, void *stream, int first_part, char *err, size_t errlen);
+int  rc_gpu_render_finish (rc_gpu_t *g, void *fb_dev, void *z_dev, int n, void *stream, int *status, char *err, size_t errlen);
 int  rc_gpu_render_host (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_out, int16_t *z_out,
                          int *status, char *err, size_t errlen);
 #define RC_ASYNC_DEPTH 3	/* RC_RenderViewsAsync calls that may be outstanding: one being copied out, one drawn, one queued behind it */
