@@ -732,15 +732,6 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 		}
 		/* a pool ran out in one of the parts: the whole batch again in one piece, which grows the pools and retries */
 	}
-	if (getenv ("RC_PREP_TIMING"))
-	{
-		struct timespec t0, t1;
-		clock_gettime (CLOCK_MONOTONIC, &t0);
-		r = rc_prepare_views (views, n);
-		clock_gettime (CLOCK_MONOTONIC, &t1);
-		fprintf (stderr, "rc_prepare_views: %d views %.3f ms (%d threads)\n", n, 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec), rc.host_threads);
-	}
-	else
 	r = rc_prepare_views (views, n);
 	if (r != RC_OK) return r;
 	if (!fb_dev) return rc_fail (RC_ERR_ARG, "fb_dev is NULL");
