@@ -1249,36 +1249,35 @@ __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __gr
 }
 
 /* Span-segment kernel: one thread per segment of a span (rc_span_seg): eight boundary records, 64 contiguous
- * bytes per thread, 2 KB per warp.  They are staged in shared memory (swizzled, conflict free) and written out by
- * the whole warp, 256 contiguous bytes per store instruction instead of 32 scattered 8-byte pieces; a segment's
- * records past the span's last subdivision are not written (the two that follow it come from the thread that holds
- * the last subdivision, straight to global memory). */
+ * bytes per thread, 2 KB per warp.  They are staged in shared memory (swizzled) and written out by the whole warp, 512
+ * contiguous bytes per store instruction instead of 32 scattered pieces; segments that lie past their span's last
+ * subdivision write nothing (rc_span_seg). */
 #ifndef SEG_MINB
 #define SEG_MINB 8	/* 64 registers: 24.5 us instead of 30 (measured 1 / 6 / 8 / 10 CTAs per SM) */
 #endif
 __global__ void __launch_bounds__(128, SEG_MINB) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
-	__shared__ uint2 stage[128 * 8];
+	__shared__ uint4 stage[128 * 4];
 	unsigned long long a = f.alloc[0];
 	int nsegs = (int)(a >> 32);
 	if (nsegs > f.segcap) nsegs = f.segcap;
 	const int lane = threadIdx.x & 31;
-	uint2 *wst = stage + (threadIdx.x & ~31) * 8;
-	uint2 *bnd2 = reinterpret_cast<uint2 *>(f.bnd);
+	uint4 *wst = stage + (threadIdx.x & ~31) * 4;
+	uint4 *bnd4 = reinterpret_cast<uint4 *>(f.bnd);
 	for (int t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); t0 < nsegs; t0 += gridDim.x * blockDim.x)
 	{
 		const int t = t0 + lane;
-		int nvalid = 0;
+		int wrote = 0;
 		if (t < nsegs)
-			nvalid = rc_span_seg (&w, &f, t, reinterpret_cast<rc_bnd_t *>(wst + lane * 8), lane & 7);
+			wrote = rc_span_seg (&w, &f, t, reinterpret_cast<rc_bnd_t *>(wst + lane * 4), lane & 3);
+		const unsigned m = __ballot_sync (0xFFFFFFFFu, wrote);
 		__syncwarp ();
 		#pragma unroll
-		for (int r = 0; r < 8; r++)
+		for (int r = 0; r < 4; r++)
 		{
-			const int seg = r * 4 + (lane >> 3), rec = lane & 7;
-			const int nv = __shfl_sync (0xFFFFFFFFu, nvalid, seg);
-			if (rec < nv)
-				bnd2[(size_t)(t0 + seg) * 8 + rec] = wst[seg * 8 + (rec ^ (seg & 7))];
+			const int seg = r * 8 + (lane >> 2), pair = lane & 3;
+			if (m & (1u << seg))
+				bnd4[(size_t)(t0 + seg) * 4 + pair] = wst[seg * 4 + (pair ^ (seg & 3))];
 		}
 		__syncwarp ();
 	}

@@ -1994,6 +1994,20 @@ RC_HD rc_sub_t rc_sub_of (const rc_bnd_t *rp, int last)
 	return r;
 }
 
+/* a / d truncated toward zero as C's `/` does, for d in 0 .. 7 (0 and negative: 0 -- the reference does not divide when the
+ * last subdivision has one pixel) and any 32-bit a, without a division: |a| * ceil (2^34 / d) >> 34 is exact while
+ * |a| * (d - 1) < 2^34, i.e. for every |a| <= 2^31 */
+RC_HD int rc_div_small (int a, int d)
+{
+	if (d <= 1)
+		return d == 1 ? a : 0;
+	const unsigned long long m = d == 2 ? 0x200000000ull : d == 3 ? 0x155555556ull : d == 4 ? 0x100000000ull :
+				     d == 5 ? 0xCCCCCCCDull : d == 6 ? 0xAAAAAAABull : 0x92492493ull;
+	const unsigned ua = a < 0 ? 0u - (unsigned)a : (unsigned)a;
+	const unsigned q = (unsigned)(((unsigned long long)ua * m) >> 34);
+	return a < 0 ? -(int)q : (int)q;
+}
+
 /* One thread per span SEGMENT (8 subdivisions = 64 pixels), before drawing: the float side of
  * D_DrawSpans8 (d_scan.c:278-365) and the set-up of D_DrawZSpans (d_scan.c:399-413), once per
  * subdivision instead of once per pixel block.  With B[b] = the 16.16 (s, t) at subdivision boundary b,
@@ -2037,9 +2051,9 @@ RC_HD rc_segsurf_t rc_load_segsurf (const rc_surf_t *s)
 	return d;
 }
 
-/* `stage` (GPU): the thread's eight records go to this (shared-memory) slot, record i at index i ^ swz, and the
- * caller copies the first `return value` of them out (0: none -- not a textured span, or a segment past the last
- * subdivision) */
+/* `stage` (GPU): the thread's eight records go to this (shared-memory) slot as four 16-byte pairs, pair i at index
+ * i ^ swz, and the caller copies them out when the function returns 1 (0: nothing to write -- not a textured span, or a
+ * segment past the last subdivision) */
 RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_bnd_t *stage = 0, int swz = 0)
 {
 	const int si = f->segspan[seg];
@@ -2087,6 +2101,8 @@ RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_bnd
 	}
 	if (!texels)
 		return 0;
+	if ((sidx << 3) >= ((count + 7) >> 3))
+		return 0;		/* the segment only holds records that follow the last subdivision: its neighbour writes them */
 	const float sstepu = s.d_sdivzstepu, tstepu = s.d_tdivzstepu;
 	const float sdivz8stepu = sstepu * 8, tdivz8stepu = tstepu * 8, zi8stepu = zistepu * 8;
 	float sdivz = s.d_sdivzorigin + dv*s.d_sdivzstepv + du*sstepu;
@@ -2136,15 +2152,13 @@ RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_bnd
 		if (tt > bbextentt) tt = bbextentt; else if (tt < lo) tt = lo;
 		st[2 * i] = ss; st[2 * i + 1] = tt;
 	}
-	/* this segment's own records: boundaries 8 sidx .. that are subdivision starts (b < nsub) */
-	int nvalid = nsub - (sidx << 3);
-	if (nvalid > 8) nvalid = 8;
-	if (nvalid < 0) nvalid = 0;
+	/* this segment's records: boundaries 8 sidx .. 8 sidx + 7 that are subdivision starts (b < nsub); the segment that
+	 * holds the LAST subdivision also writes what follows it -- B[nsub] (the last pixel's coordinates) and that
+	 * subdivision's per-pixel step, the one truncating division of a span (d_scan.c:364-365) -- into its own block where
+	 * they fit (slots il + 1, il + 2) and into the next segment's otherwise (that segment, all of whose boundaries are
+	 * >= nsub, returned above and writes nothing).  A segment that writes at all writes its eight slots. */
 	rc_bnd_t *out = f->bnd + (size_t)seg * 8;
 	{
-		/* the segment that holds the LAST subdivision also writes what follows it: B[nsub] (the last pixel's
-		 * coordinates) and the subdivision's per-pixel step -- the one truncating division of a span (d_scan.c:364-365).
-		 * These two records may lie in the next segment's block; its thread leaves them alone (b >= nsub) */
 		const int il = nsub - 1 - (sidx << 3);			/* the last subdivision's place in this segment */
 		if (il >= 0 && il < 8)
 		{
@@ -2153,35 +2167,44 @@ RC_HD int rc_span_seg (const rc_world_t *w, const rc_frame_t *f, int seg, rc_bnd
 			#pragma unroll
 			for (int i = 0; i < 8; i++)
 				if (i == il) { es_ = st[2 * i + 2]; et_ = st[2 * i + 3]; ds_ = es_ - st[2 * i]; dt_ = et_ - st[2 * i + 1]; }
-			const int sstep = lastn > 1 ? ds_ / (lastn - 1) : 0, tstep = lastn > 1 ? dt_ / (lastn - 1) : 0;
+			const int sstep = rc_div_small (ds_, lastn - 1), tstep = rc_div_small (dt_, lastn - 1);
+			#pragma unroll
+			for (int i = 1; i < 8; i++)
+			{
+				if (i == il + 1) { st[2 * i] = es_; st[2 * i + 1] = et_; }
+				if (i == il + 2) { st[2 * i] = sstep; st[2 * i + 1] = tstep; }
+			}
+			if (il >= 6)
+			{
+				/* (record 8 is the next block's slot 0) */
 #ifdef __CUDACC__
-			reinterpret_cast<uint2 *>(out)[il + 1] = make_uint2 ((uint32_t)es_, (uint32_t)et_);
-			reinterpret_cast<uint2 *>(out)[il + 2] = make_uint2 ((uint32_t)sstep, (uint32_t)tstep);
+				if (il == 7) reinterpret_cast<uint2 *>(out)[8] = make_uint2 ((uint32_t)es_, (uint32_t)et_);
+				reinterpret_cast<uint2 *>(out)[il + 2] = make_uint2 ((uint32_t)sstep, (uint32_t)tstep);
 #else
-			out[il + 1].s = es_; out[il + 1].t = et_; out[il + 2].s = sstep; out[il + 2].t = tstep;
+				if (il == 7) { out[8].s = es_; out[8].t = et_; }
+				out[il + 2].s = sstep; out[il + 2].t = tstep;
 #endif
+			}
 		}
 	}
 #ifdef __CUDACC__
 	if (stage)
 	{
-		/* (all eight slots are staged; the caller copies the first nvalid out) */
 		#pragma unroll
-		for (int i = 0; i < 8; i++)
-			reinterpret_cast<uint2 *>(stage)[i ^ swz] = make_uint2 ((uint32_t)st[2*i], (uint32_t)st[2*i+1]);
-		return nvalid;
+		for (int i = 0; i < 8; i += 2)
+			reinterpret_cast<uint4 *>(stage)[(i >> 1) ^ swz] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)st[2*i+2], (uint32_t)st[2*i+3]);
+		return 1;
 	}
 	#pragma unroll
-	for (int i = 0; i < 8; i++)
-		if (i < nvalid)
-			reinterpret_cast<uint2 *>(out)[i] = make_uint2 ((uint32_t)st[2*i], (uint32_t)st[2*i+1]);
+	for (int i = 0; i < 8; i += 2)
+		reinterpret_cast<uint4 *>(out)[i >> 1] = make_uint4 ((uint32_t)st[2*i], (uint32_t)st[2*i+1], (uint32_t)st[2*i+2], (uint32_t)st[2*i+3]);
 #else
-	for (int i = 0; i < nvalid; i++)
+	for (int i = 0; i < 8; i++)
 	{
 		out[i].s = st[2*i]; out[i].t = st[2*i+1];
 	}
 #endif
-	return nvalid;
+	return 1;
 }
 
 /* The part of span `sp` that lies inside one 8-pixel window, general form (D_DrawSpans8 d_scan.c:254-386 /
