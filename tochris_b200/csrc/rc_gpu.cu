@@ -37,6 +37,25 @@
 	snprintf (err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); return RC_ERR_CUDA; } } while (0)
 
 
+/* Programmatic dependent launch: a kernel launched with launch_k (..., pdl = true) may be brought onto the SMs while the
+ * kernel before it on the stream is still draining; it must not touch anything that kernel (or an earlier one) wrote before
+ * RC_GRID_DEP_WAIT (), which returns when the preceding grid has completed and its memory is visible.  The wait is a
+ * no-op in a kernel launched the ordinary way, so every kernel of the pipeline carries it. */
+#define RC_GRID_DEP_WAIT() asm volatile ("griddepcontrol.wait;" ::: "memory")
+
+template <typename... KA, typename... A>
+static cudaError_t launch_k (void (*kern) (KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, A &&... args)
+{
+	cudaLaunchConfig_t cfg;
+	cudaLaunchAttribute at[1];
+	memset (&cfg, 0, sizeof(cfg));
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx (&cfg, kern, static_cast<KA> (args)...);
+}
+
 #define RC_GRAPHS 4
 #define RC_RF_KEEP_STATUS 1	/* rc_gpu_render_part: the status words are not cleared */
 #define RC_RF_DEFER       2	/* nothing waits, no CUDA graph */
@@ -70,6 +89,7 @@ struct rc_gpu_s {
 	int *d_segspan; rc_bnd_t *d_bnd;
 	int front_256, front_csize;
 	int rflags;			/* RC_RF_* of the call being enqueued (rc_gpu_render_part) */
+	int use_pdl;			/* programmatic dependent launch along the main stream's chain of kernels (RC_NO_PDL switches it off) */
 	rc_dlight_t *d_dlights; int dlightcap;
 	uint8_t *d_warpbuf; int warpcap;
 	/* alias models (uploaded blobs) and per-batch entity buffers */
@@ -182,6 +202,7 @@ __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
 template <int FT>
 __global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster ();
 	extern __shared__ __align__(16) unsigned char front_smem[];
@@ -508,6 +529,7 @@ __device__ __forceinline__ void scan_full_key (const scan_cta_t<AET, CAND> *sh, 
 template <int AET, int CAND>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	extern __shared__ __align__(16) unsigned char scan_smem[];
 	constexpr int SPANS = AET + 2;
 	scan_cta_t<AET, CAND> *sh = reinterpret_cast<scan_cta_t<AET, CAND> *>(scan_smem);
@@ -1078,11 +1100,13 @@ __global__ void __launch_bounds__(64) k_scan_serial (const __grid_constant__ rc_
 
 __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	rc_bmodel_face (&w, &f, f.bentbase + blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	int vi = blockIdx.x;
 	int si = rc_surf_slot (&f, vi, blockIdx.y * blockDim.x + threadIdx.x);
 	if (si >= 0)
@@ -1111,6 +1135,7 @@ __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_c
 #endif
 __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	__shared__ unsigned s_bl[CACHE_THREADS / 32][18 * 18];
 	const uint8_t * __restrict__ cmap = w.colormap;
 	const unsigned long long nj = f.alloc[2], nu = f.alloc[8];
@@ -1257,6 +1282,7 @@ __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __gr
 #endif
 __global__ void __launch_bounds__(128, SEG_MINB) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	__shared__ uint4 stage[128 * 4];
 	unsigned long long a = f.alloc[0];
 	int nsegs = (int)(a >> 32);
@@ -1402,6 +1428,7 @@ __device__ __forceinline__ void draw_cell_store (const rc_frame_t &f, const uint
 template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	const unsigned cw = (unsigned)((f.width + 7) >> 3), tilesx = (cw + DRAW_TW - 1) / DRAW_TW;
 	const unsigned row0 = (unsigned)(f.drawview0 * f.height), nrows = (unsigned)((f.drawview1 - f.drawview0) * f.height);
 	const unsigned ntiles = tilesx * ((nrows + DRAW_TH - 1) / DRAW_TH);
@@ -1532,6 +1559,7 @@ __device__ __noinline__ void draw_mixed_general (const rc_world_t *w, const rc_f
 template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
 	const uint2 *bnd2 = reinterpret_cast<const uint2 *>(f.bnd);
 	unsigned long long al = f.alloc[0];
@@ -1710,6 +1738,7 @@ __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant_
 template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128) k_slowcells (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
+	RC_GRID_DEP_WAIT ();
 	const unsigned nslow = (unsigned)f.alloc[3];
 	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nslow; t += gridDim.x * blockDim.x)
 	{
@@ -1884,12 +1913,14 @@ __global__ void __launch_bounds__(256) k_draw2d (const rc_d2ctx_t x, const rc_dr
 
 __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 {
+	RC_GRID_DEP_WAIT ();
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		p[i] = v;
 }
 
 __global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long long *poolptr, unsigned long long first)
 {
+	RC_GRID_DEP_WAIT ();
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		keys[i] = RC_CACHE_EMPTY;
 	if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -1900,6 +1931,7 @@ __global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long
  * cache's) and, for the first chunk of a batch, the status words -- one launch instead of three memsets */
 __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
 {
+	RC_GRID_DEP_WAIT ();
 	const unsigned t = threadIdx.x;
 	if (t == 0 || (t >= 2 && t <= 5) || t == 8)
 		alloc[t] = 0ull;
@@ -1914,6 +1946,7 @@ __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
  * next batch's kernels back until those copies are through */
 __global__ void k_status_out (const int *d_status, int *host_status)
 {
+	RC_GRID_DEP_WAIT ();
 	*host_status = *d_status;
 	__threadfence_system ();
 }
@@ -1997,6 +2030,7 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	 * RC_FRONT_512 512-thread front-end CTAs on many-view batches */
 	g->front_512 = getenv ("RC_FRONT_512") ? 1 : 0;
 	g->front_256 = getenv ("RC_FRONT_256") ? 1 : 0;
+	g->use_pdl = getenv ("RC_NO_PDL") ? 0 : 1;
 	{ const char *e = getenv ("RC_FRONT_CSIZE"); g->front_csize = e ? atoi (e) : 0; if (g->front_csize != 1 && g->front_csize != 2 && g->front_csize != 4 && g->front_csize != 8) g->front_csize = 0; }
 	g->scan_serial = getenv ("RC_SCAN_SERIAL") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
@@ -2391,6 +2425,10 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
+		cudaLaunchAttribute attr2[2];
+		attr2[0] = attr[0];
+		attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr2[1].val.programmaticStreamSerializationAllowed = 1;
+		if (g->use_pdl && !timed) { cfg.attrs = attr2; cfg.numAttrs = 2; }
 		if (manyviews) CK (cudaLaunchKernelEx (&cfg, k_front<FRONT_MANY>, w, f));
 		else CK (cudaLaunchKernelEx (&cfg, k_front<FRONT_THREADS>, w, f));
 	}
@@ -2416,10 +2454,10 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	dim3 gs (n, (g->height + SCAN_WARPS - 1) / SCAN_WARPS);
 	if (g->scan_serial) { dim3 gss (n, (g->height + 63) / 64); k_scan_serial<<<gss, 64, 0, s>>> (w, f); }
 	else if (g->scan_large) k_scan<256, SCAN_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<256, SCAN_CAND>), s>>> (w, f);
-	else k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND><<<gs, SCAN_WARPS * 32, sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>), s>>> (w, f);
+	else CK (launch_k (k_scan<SCAN_SMALL_AET, SCAN_SMALL_CAND>, gs, dim3 (SCAN_WARPS * 32), sizeof(scan_cta_t<SCAN_SMALL_AET, SCAN_SMALL_CAND>), s, g->use_pdl && !timed, w, f));
 	if (timed) cudaEventRecord (g->ev[3], s);
 	dim3 gp (n, (g->surfcap + 63) / 64);
-	k_surfprep<<<gp, 64, 0, s>>> (w, f);
+	CK (launch_k (k_surfprep, gp, dim3 (64), 0, s, g->use_pdl && !timed, w, f));
 	if (timed) cudaEventRecord (g->ev[4], s);
 	if (timed)
 	{
@@ -2436,7 +2474,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
 		k_spanseg<<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
 		cudaEventRecord (g->evjoin, g->sidestream);
-		k_cache<<<g->numsms * CACHE_MINB, CACHE_THREADS, 0, s>>> (w, f);
+		CK (launch_k (k_cache, dim3 (g->numsms * CACHE_MINB), dim3 (CACHE_THREADS), 0, s, g->use_pdl, w, f));
 		cudaStreamWaitEvent (s, g->evjoin, 0);
 	}
 	const bool entities = g->cur_batch && g->cur_batch->nzres;
@@ -2466,7 +2504,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			const int nv = f.drawview1 - f.drawview0;
 			int ctas = (int)(((size_t)nv * g->height * ((g->width + 7) / 8) + 127) / 128);
 			if (ctas > g->numsms * 16) ctas = g->numsms * 16;
-			k_draw<false><<<ctas, 128, 0, s>>> (w, f);
+			CK (launch_k (k_draw<false>, dim3 (ctas), dim3 (128), 0, s, g->use_pdl && !timed && gi > 0, w, f));	/* (group 0 follows a fork) */
 			if (timed) cudaEventRecord (g->ev[8], s);
 			if (gi == 0) cudaStreamWaitEvent (s, g->evjoin, 0);
 			cudaEventRecord (g->evgroup[gi], s);
@@ -2518,8 +2556,8 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
 			if (!f.slowmode)
 			{
-				if (anywarp) k_slowcells<true><<<g->numsms * 8, 128, 0, s>>> (w, f);
-				else k_slowcells<false><<<g->numsms * 8, 128, 0, s>>> (w, f);
+				if (anywarp) CK (launch_k (k_slowcells<true>, dim3 (g->numsms * 8), dim3 (128), 0, s, g->use_pdl, w, f));
+				else CK (launch_k (k_slowcells<false>, dim3 (g->numsms * 8), dim3 (128), 0, s, g->use_pdl, w, f));
 			}
 			cudaStreamWaitEvent (s, g->evjoin, 0);
 			f.slowmode = 0;
@@ -2848,7 +2886,7 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		{
 			/* pipelined call: the status lands in pinned memory, nothing waits here; a pool overflow is
 			 * reported by rc_gpu_wait_host and the caller renders that batch again with the blocking call */
-			k_status_out<<<1, 1, 0, s>>> (g->d_status, &g->astatus[g->amode - 1]);
+			CK (launch_k (k_status_out, dim3 (1), dim3 (1), 0, s, false, (const int *)g->d_status, &g->astatus[g->amode - 1]));
 			CK (cudaEventRecord (g->adone_s[g->amode - 1], s));
 			break;
 		}
@@ -2995,7 +3033,7 @@ int rc_gpu_render_host_async (rc_gpu_t *g, const rc_batch_t *batch, uint8_t *fb_
 	}
 	/* cleared by a kernel, not cudaMemsetAsync: nothing of this call may queue on a copy engine ahead of its own
 	 * frame-buffer copies (the engine would be busy with the previous call's) */
-	k_fill64<<<g->numsms * 4, 256, 0, g->stream>>> ((unsigned long long *)g->d_afb[slot], 0ull, (px * n + 7) / 8);
+	CK (launch_k (k_fill64, dim3 (g->numsms * 4), dim3 (256), 0, g->stream, g->use_pdl != 0, (unsigned long long *)g->d_afb[slot], 0ull, (size_t)((px * n + 7) / 8)));
 	g->astatus[slot] = 0;
 	CK (cudaEventRecord (g->adone_copy[slot], g->copystream));	/* paths that copy on the main stream leave this one as "done" */
 	g->host_fb = fb_out; g->host_z = z_out; g->amode = slot + 1;
