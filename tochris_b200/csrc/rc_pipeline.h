@@ -2657,47 +2657,91 @@ RC_HD int rc_polyset_span (const rc_frame_t *f, const uint8_t *skin, const uint8
 {
 	const int W = f->width, H = f->height;
 	int front = 0;
-	for (; lcount > 0; lcount--, x++)
+	const bool yin = (unsigned)y < (unsigned)H;
+	const int16_t *zwrow = zworld + (size_t)(yin ? y : 0) * zwidth;
+	unsigned long long *zprow = zplane + (size_t)(yin ? y : 0) * W;
+	/* four pixels per round, so that their four chains of dependent reads -- world z, skin, colormap, the plane's current
+	 * value -- wait side by side (one pixel per round, the thread sat out every chain in turn: 2.4 ms at C3).  The stepping
+	 * between the pixels is the reference's, in its order. */
+	while (lcount > 0)
 	{
-		if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
+		const int nb = lcount < 4 ? lcount : 4;
+		int px[4], pzi[4], pti[4], plight[4];
+		bool in[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++)
 		{
-			/* d_polyse.c:422 tests the fragment against the z-buffer before it reads the skin; what the world pass left
-			 * there is a lower bound of what the reference finds: a fragment behind it never lands */
-			if ((lzi >> 16) >= zworld[(size_t)y * zwidth + x])
+			px[j] = x; pzi[j] = lzi >> 16; pti[j] = lptex; plight[j] = llight;
+			in[j] = j < nb && yin && (unsigned)x < (unsigned)W;
+			if (j < nb)
 			{
-				front++;
-				int ti = lptex;
-				if (ti < skinlo || ti >= skinhi)
+				if (!in[j])
+					RC_ALIAS_RANGE_HIT (f);
+				x++;
+				lzi = rc_addw (lzi, r_zistepx);
+				llight = rc_addw (llight, r_lstepx);
+				lptex += a_ststepxwhole;
+				lsfrac += a_sstepxfrac;
+				lptex += lsfrac >> 16;
+				lsfrac &= 0xFFFF;
+				ltfrac += a_tstepxfrac;
+				if (ltfrac & 0x10000)
+				{
+					lptex += skinwidth;
+					ltfrac &= 0xFFFF;
+				}
+			}
+		}
+		lcount -= nb;
+		/* d_polyse.c:422 tests the fragment against the z-buffer before it reads the skin; what the world pass left
+		 * there is a lower bound of what the reference finds: a fragment behind it never lands */
+		int zw[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++)
+			zw[j] = in[j] ? (int)zwrow[px[j]] : 0x7FFFFFFF;
+		bool pass[4];
+		int sk[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			pass[j] = in[j] && pzi[j] >= zw[j];
+			int ti = pti[j];
+			if (ti < skinlo || ti >= skinhi)
+			{
+				if (pass[j])
 				{
 					/* outside the model's whole memory block: the reference reads a neighbour on its heap */
 					RC_ALIAS_RANGE_HIT (f);
-					RC_DEBUG_PRINT ("skin index %d outside the model image %d .. %d (x %d y %d)\n", ti, skinlo, skinhi, x, y);
-					ti = 0;
+					RC_DEBUG_PRINT ("skin index %d outside the model image %d .. %d (x %d y %d)\n", ti, skinlo, skinhi, px[j], y);
 				}
-				int ci = skin[ti] + (llight & 0xFF00);
-				if (ci >= 64 * 256)
+				ti = 0;
+			}
+			sk[j] = pass[j] ? (int)skin[ti] : 0;
+		}
+		unsigned long long key[4], cur[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			int ci = sk[j] + (plight[j] & 0xFF00);
+			if (ci >= 64 * 256)
+			{
+				if (pass[j])
 				{
 					RC_ALIAS_RANGE_HIT (f);
-					RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, llight);
-					ci &= 0x3FFF;
+					RC_DEBUG_PRINT ("colormap index %d (light %d)\n", ci, plight[j]);
 				}
-				const unsigned long long key = ((unsigned long long)(unsigned)((lzi >> 16) + 32768) << 48) | orderbits | colormap[ci];
-				RC_ATOMIC_MAX_ULL (&zplane[(size_t)y * W + x], key);
+				ci &= 0x3FFF;
 			}
+			key[j] = pass[j] ? (((unsigned long long)(unsigned)(pzi[j] + 32768) << 48) | orderbits | colormap[ci]) : 0ull;
+			/* the planes only grow: a fragment that does not beat the value read now cannot beat the final one */
+			cur[j] = pass[j] ? RC_LDCG (&zprow[px[j]]) : ~0ull;
 		}
-		else
-			RC_ALIAS_RANGE_HIT (f);
-		lzi = rc_addw (lzi, r_zistepx);
-		llight = rc_addw (llight, r_lstepx);
-		lptex += a_ststepxwhole;
-		lsfrac += a_sstepxfrac;
-		lptex += lsfrac >> 16;
-		lsfrac &= 0xFFFF;
-		ltfrac += a_tstepxfrac;
-		if (ltfrac & 0x10000)
+		#pragma unroll
+		for (int j = 0; j < 4; j++)
 		{
-			lptex += skinwidth;
-			ltfrac &= 0xFFFF;
+			front += pass[j];
+			if (key[j] > cur[j])
+				RC_ATOMIC_MAX_ULL_BLIND (&zprow[px[j]], key[j]);
 		}
 	}
 	return front;
