@@ -125,6 +125,8 @@ typedef struct {
     int   max_views_in_flight;/* views processed per pipeline pass (0: derived from memory) */
     int   host_threads;       /* host threads that set up the views of a large batch (0: min (8, online CPUs); one process
                                * per GPU shares the host: give each rank its share) */
+    float r_draworder;        /* r_main.c:108: non-zero draws the FARTHEST surface of every pixel (R_GenerateSpansBackward,
+                               * r_edge.c:573; the reference honours it only while a local server runs, r_misc.c:420) */
 } rc_config_t;
 
 void RC_DefaultConfig (rc_config_t *cfg);

@@ -95,7 +95,7 @@ void VID_Update (vrect_t *r) { (void)r; }
 void Sys_mkdir (char *path) { (void)path; }
 void Sys_Quit (void) { exit (0); }
 /* Com_ClientMaxclients/Com_ServerState come from common/common.c (state 0:
- * no local server => r_misc.c:420 forces r_draworder to 0 every frame). */
+ * no local server => r_misc.c:420 forces r_draworder to 0 every frame; orc_set_cvar ("r_draworder") switches the state). */
 
 double Sys_FloatTime (void)
 {
@@ -240,6 +240,10 @@ int orc_set_cvar (const char *name, float value)
 	cvar_t *v = Cvar_FindVar ((char *)name);
 	if (!v) return -1;
 	Cvar_SetValue (v, value);		/* common/cvar.h:74 takes the cvar_t */
+	/* r_draworder is only honoured while a local server runs (r_misc.c:420 resets it every frame otherwise): the shim
+	 * says one does, as the engine would after `map` */
+	if (!strcmp (name, "r_draworder"))
+		Com_SetServerState (value ? 1 : 0);
 	return 0;
 }
 

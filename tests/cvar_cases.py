@@ -91,6 +91,8 @@ CVAR_CASES = [
     ("r_clearcolor", "multi", 320, 240, 32, 8, 0.0, 0.0, {}, dict(r_clearcolor=251.0), "outside"),
     ("r_clearcolor_default", "full", 320, 240, 16, 4, 0.0, 0.0, dict(entities=4), {}, "outside"),
     ("r_lerpmodels0", "multi", 320, 240, 32, 8, 0.6, 0.09, dict(entities=8), dict(r_lerpmodels=0.0), None),
+    ("r_draworder", "multi", 320, 240, 32, 8, 0.3, 0.11, {}, dict(r_draworder=1.0), None),        # the farthest surface wins (R_GenerateSpansBackward)
+    ("r_draworder_full", "full", 400, 300, 24, 6, 0.37, 0.173, dict(doors=2, entities=4, particles=40, dlights=1), dict(r_draworder=1.0), None),
     ("RDF_NOWORLDMODEL", "multi", 320, 200, 24, 8, 0.6, 0.09, {}, {}, "noworld"),
     ("RDF_NOWORLDMODEL_particles", "multi", 320, 200, 8, 4, 0.6, 0.09, dict(particles=50), dict(r_fullbright=0.0), "noworld"),
 ]

@@ -27,7 +27,8 @@ class rc_config_t(C.Structure):
                 ("r_fastsky", C.c_float), ("r_skycolor", C.c_float), ("r_lerpmodels", C.c_float),
                 ("d_mipcap", C.c_float), ("d_mipscale", C.c_float), ("r_maxsurfs", C.c_float),
                 ("r_maxedges", C.c_float),
-                ("surfcache_bytes", C.c_size_t), ("max_views_in_flight", C.c_int), ("host_threads", C.c_int)]
+                ("surfcache_bytes", C.c_size_t), ("max_views_in_flight", C.c_int), ("host_threads", C.c_int),
+                ("r_draworder", C.c_float)]
 
 
 class rc_stats_t(C.Structure):

@@ -136,6 +136,7 @@ int RC_Init (const rc_config_t *cfg)
 	rc.cvars.r_fastsky = cfg->r_fastsky; rc.cvars.r_skycolor = cfg->r_skycolor;
 	rc.cvars.r_lerpmodels = cfg->r_lerpmodels; rc.cvars.d_mipcap = cfg->d_mipcap;
 	rc.cvars.d_mipscale = cfg->d_mipscale;
+	rc.cvars.r_draworder = cfg->r_draworder;
 	rc.cvars.r_maxsurfs = cfg->r_maxsurfs < 1000 ? 1000 : cfg->r_maxsurfs;	/* MINSURFACES, r_main.c:267 */
 	rc.cvars.r_maxedges = cfg->r_maxedges < 2000 ? 2000 : cfg->r_maxedges;	/* MINEDGES, r_main.c:293 */
 	{

@@ -24,7 +24,7 @@ typedef struct { int width, height, rowbytes; float aspect; } rc_vidinfo_t;
 
 typedef struct {
     float r_clearcolor, r_fullbright, r_ambient, r_drawentities, r_drawviewmodel, r_waterwarp,
-          r_fastsky, r_skycolor, r_lerpmodels, d_mipcap, d_mipscale, r_maxsurfs, r_maxedges;
+          r_fastsky, r_skycolor, r_lerpmodels, d_mipcap, d_mipscale, r_maxsurfs, r_maxedges, r_draworder;
 } rc_cvars_t;
 
 /* ---- models ------------------------------------------------------------------------- */

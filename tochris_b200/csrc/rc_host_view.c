@@ -110,7 +110,9 @@ int RC_SetupView (const rc_refdef_t *rd, const rc_vidinfo_t *vid, const rc_cvars
 	rc_view_t *v = out;
 
 	memset (v, 0, sizeof(*v));
-	v->rdflags = rd->flags;
+	v->rdflags = rd->flags & 0xFF;
+	if (cv->r_draworder)
+		v->rdflags |= RC_VIEW_DRAWORDER;		/* r_edge.c:94-105 */
 	v->ambientlight = (int)cv->r_ambient;			/* r_misc.c:415 */
 	if (v->ambientlight < 0)
 		v->ambientlight = 0;

@@ -811,7 +811,10 @@ RC_HD void rc_face_emit (const rc_world_t *w, const rc_frame_t *f, int vi, int p
 	if (isbox)
 		planedist = vw->origin[pplane->type] + pplane->dist;	/* r_rast.c:183-187: r_origin[axis] +- 128 */
 	float distinv = 1.0 / (planedist - rc_dot3 (vw->origin, pplane->normal));
-	surf->key = rec.key;
+	/* r_draworder (R_BeginEdgeFrame, r_edge.c:94-105 / R_LeadingEdgeBackwards :290-366): the background gets the SMALLEST
+	 * key and the surface with the LARGEST key is on top of the stack.  Negated keys under the same rule -- smallest on
+	 * top, background 0x7FFFFFFF -- give the same order, so the scan stage is shared */
+	surf->key = (vw->rdflags & RC_VIEW_DRAWORDER) ? -rec.key : rec.key;
 	surf->flags = fa->flags;
 	surf->face = rec.face;
 	surf->insubmodel = 0;
@@ -1025,7 +1028,7 @@ RC_HD void rc_bmodel_emit (rc_bctx_t *c, const int *ev0, const int *ev1, int n, 
 	p_normal[1] = rc_dot3 (pplane->normal, xf->vup);
 	p_normal[2] = rc_dot3 (pplane->normal, xf->vpn);
 	float distinv = 1.0 / (pplane->dist - rc_dot3 (xf->origin, pplane->normal));
-	surf->key = key;
+	surf->key = (vw->rdflags & RC_VIEW_DRAWORDER) ? -key : key;
 	surf->flags = fa->flags;
 	surf->face = c->face;
 	surf->insubmodel = 1;
@@ -1272,6 +1275,9 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
 	const int edge_tail_u = vw->vrectright;		/* ((vrectright<<20)+0xFFFFF) >> 20 */
 	stk[0].surf = 1; stk[0].key = 0x7FFFFFFF; stk[0].state = 1; stk[0].last_u = edge_head_u; stk[0].insub = 0;
 	const float fv = (float)line;
+	/* R_LeadingEdgeBackwards has no 1/z test between two brush-model surfaces of one leaf: the new one goes in front
+	 * ("they'll never be farthest anyway", r_edge.c:312-343) */
+	const int backward = (vw->rdflags & RC_VIEW_DRAWORDER) != 0;
 
 	for (int k = 0; k < n; k++)
 	{
@@ -1353,7 +1359,7 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
 				double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
 				double newzibottom = newzi * 0.99;
 				double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
-				if (newzibottom >= testzi)
+				if (backward || newzibottom >= testzi)
 					newtop = 1;
 				else
 				{
@@ -1383,7 +1389,7 @@ RC_HD int rc_span_walk (const rc_frame_t *f, const rc_view_t *vw, const rc_surf_
 						double newzi = sf->d_ziorigin + fv*sf->d_zistepv + fu*sf->d_zistepu;
 						double newzibottom = newzi * 0.99;
 						double testzi = s2->d_ziorigin + fv*s2->d_zistepv + fu*s2->d_zistepu;
-						if (newzibottom >= testzi)
+						if (backward || newzibottom >= testzi)
 							break;
 						double newzitop = newzi * 1.01;
 						if (newzitop >= testzi && sf->d_zistepu >= s2->d_zistepu)

@@ -175,7 +175,7 @@ typedef struct {
     int   ambientlight;
     int   animtime;                /* (int)(time*10)   r_surf.c:72 */
     int   turbphase;               /* (int)(time*SPEED)&(CYCLE-1)  d_scan.c:128 */
-    int   rdflags;
+    int   rdflags;          /* refdef_t.flags (RDF_*) | RC_VIEW_DRAWORDER */
     int   dowarp;
     int   clearcolor;              /* (int)r_clearcolor.value & 0xFF */
     int   fullbright;              /* r_fullbright.value != 0 */
@@ -281,6 +281,7 @@ typedef struct {            /* 8 B: the 16.16 (s, t) at one subdivision boundary
 
 /* cell records flag where a cell touches the span's last subdivision, so that the draw kernel knows which of its two
  * steps to read instead of derive */
+#define RC_VIEW_DRAWORDER 0x100        /* rc_view_t.rdflags: r_draworder is set (the farthest surface wins: R_GenerateSpansBackward) */
 #define RC_CELL_L0     0x40000000          /* the subdivision of the cell's first pixel is the span's last */
 #define RC_CELL_L1     0x80000000u         /* the following one is */
 #define RC_CELL_SPAN(x) ((int)((x) & 0x3FFFFFFF))
