@@ -41,7 +41,33 @@
  * kernel before it on the stream is still draining; it must not touch anything that kernel (or an earlier one) wrote before
  * RC_GRID_DEP_WAIT (), which returns when the preceding grid has completed and its memory is visible.  The wait is a
  * no-op in a kernel launched the ordinary way, so every kernel of the pipeline carries it. */
+#ifdef RC_PDL_EARLY
+/* the dependents may be brought onto the SMs as soon as every CTA of this grid has started (they still wait, in their own
+ * RC_GRID_DEP_WAIT, for this grid to complete) */
+#define RC_GRID_DEP_WAIT() asm volatile ("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+#else
 #define RC_GRID_DEP_WAIT() asm volatile ("griddepcontrol.wait;" ::: "memory")
+#endif
+
+#ifdef RC_TRACE
+/* debug build: first start / last end of every pipeline kernel on the device's global timer (ns), printed per step by
+ * rc_gpu_render_chunk's caller -- the time line inside a CUDA graph, which events cannot see */
+__device__ unsigned long long g_trace[32];
+struct rc_trace_scope {
+	int k;
+	__device__ __forceinline__ rc_trace_scope (int kk) : k (kk)
+	{
+		if (threadIdx.x == 0) { unsigned long long t; asm volatile ("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin (&g_trace[2 * k], t); }
+	}
+	__device__ __forceinline__ ~rc_trace_scope ()
+	{
+		if (threadIdx.x == 0) { unsigned long long t; asm volatile ("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMax (&g_trace[2 * k + 1], t); }
+	}
+};
+#define RC_TRACE_SCOPE(k) rc_trace_scope trace_scope_ (k)
+#else
+#define RC_TRACE_SCOPE(k) do { } while (0)
+#endif
 
 template <typename... KA, typename... A>
 static cudaError_t launch_k (void (*kern) (KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, A &&... args)
@@ -131,6 +157,7 @@ struct rc_gpu_s {
 	struct { const void *fb; cudaEvent_t ev; int valid; } mpend[4];
 	cudaEvent_t evrender;
 	int slow_in_ends;
+	int draw_first, draw_ctas, ends_ctas;	/* experiments: RC_DRAW_FIRST, RC_DRAW_CTAS, RC_ENDS_CTAS (CTAs per SM) */
 	int scan_serial;
 	int front_512;			/* RC_FRONT_512: keep 512-thread front-end CTAs on many-view batches (experiment knob) */
 	int scan_large;			/* the scan kernel's large instance (256 active edges per line) after an overflow of the small one */
@@ -203,6 +230,7 @@ template <int FT>
 __global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (1);
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster ();
 	extern __shared__ __align__(16) unsigned char front_smem[];
@@ -530,6 +558,7 @@ template <int AET, int CAND>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) k_scan (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (2);
 	extern __shared__ __align__(16) unsigned char scan_smem[];
 	constexpr int SPANS = AET + 2;
 	scan_cta_t<AET, CAND> *sh = reinterpret_cast<scan_cta_t<AET, CAND> *>(scan_smem);
@@ -1107,6 +1136,7 @@ __global__ void k_bmodel (const __grid_constant__ rc_world_t w, const __grid_con
 __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (3);
 	int vi = blockIdx.x;
 	int si = rc_surf_slot (&f, vi, blockIdx.y * blockDim.x + threadIdx.x);
 	if (si >= 0)
@@ -1136,6 +1166,7 @@ __global__ void k_surfprep (const __grid_constant__ rc_world_t w, const __grid_c
 __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (4);
 	__shared__ unsigned s_bl[CACHE_THREADS / 32][18 * 18];
 	const uint8_t * __restrict__ cmap = w.colormap;
 	const unsigned long long nj = f.alloc[2], nu = f.alloc[8];
@@ -1283,6 +1314,7 @@ __global__ void __launch_bounds__(CACHE_THREADS, CACHE_MINB) k_cache (const __gr
 __global__ void __launch_bounds__(128, SEG_MINB) k_spanseg (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (5);
 	__shared__ uint4 stage[128 * 4];
 	unsigned long long a = f.alloc[0];
 	int nsegs = (int)(a >> 32);
@@ -1429,6 +1461,7 @@ template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, DRAW_MINB) k_draw (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (6);
 	const unsigned cw = (unsigned)((f.width + 7) >> 3), tilesx = (cw + DRAW_TW - 1) / DRAW_TW;
 	const unsigned row0 = (unsigned)(f.drawview0 * f.height), nrows = (unsigned)((f.drawview1 - f.drawview0) * f.height);
 	const unsigned ntiles = tilesx * ((nrows + DRAW_TH - 1) / DRAW_TH);
@@ -1560,6 +1593,7 @@ template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128, ENDS_MINB) k_ends (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (7);
 	const uint4 *spans4 = reinterpret_cast<const uint4 *>(f.spans);
 	const uint2 *bnd2 = reinterpret_cast<const uint2 *>(f.bnd);
 	unsigned long long al = f.alloc[0];
@@ -1739,6 +1773,7 @@ template <bool WARPVIEWS>
 __global__ void __launch_bounds__(128) k_slowcells (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (8);
 	const unsigned nslow = (unsigned)f.alloc[3];
 	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nslow; t += gridDim.x * blockDim.x)
 	{
@@ -1921,6 +1956,7 @@ __global__ void k_fill64 (unsigned long long *p, unsigned long long v, size_t n)
 __global__ void k_flush_cache (unsigned long long *keys, size_t n, unsigned long long *poolptr, unsigned long long first)
 {
 	RC_GRID_DEP_WAIT ();
+	RC_TRACE_SCOPE (9);
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
 		keys[i] = RC_CACHE_EMPTY;
 	if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -1933,6 +1969,11 @@ __global__ void k_reset_chunk (unsigned long long *alloc, int *status)
 {
 	RC_GRID_DEP_WAIT ();
 	const unsigned t = threadIdx.x;
+#ifdef RC_TRACE
+	g_trace[t] = (t & 1) ? 0ull : ~0ull;
+	__syncwarp ();
+	{ RC_TRACE_SCOPE (0); }
+#endif
 	if (t == 0 || (t >= 2 && t <= 5) || t == 8)
 		alloc[t] = 0ull;
 	if (status && t < 16)
@@ -2035,6 +2076,9 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	g->scan_serial = getenv ("RC_SCAN_SERIAL") ? 1 : 0;
 	g->slow_in_ends = getenv ("RC_SLOW_IN_ENDS") ? 1 : 0;	/* measured: 14 us slower than the queue + k_slowcells at C2 */
 	g->scan_large = getenv ("RC_SCAN_LARGE") ? 1 : 0;
+	g->draw_first = getenv ("RC_DRAW_FIRST") ? 1 : 0;
+	{ const char *e = getenv ("RC_DRAW_CTAS"); g->draw_ctas = e && atoi (e) >= 1 && atoi (e) <= 32 ? atoi (e) : 16; }
+	{ const char *e = getenv ("RC_ENDS_CTAS"); g->ends_ctas = e && atoi (e) >= 1 && atoi (e) <= 32 ? atoi (e) : 16; }
 	for (int i = 0; i < RC_GRAPHS; i++) { g->graphs[i].exec = NULL; g->graphs[i].used = 0; }
 	g->graph_clock = 0; g->use_graphs = getenv ("RC_NO_GRAPH") ? 0 : 1;
 	g->host_fb = NULL; g->host_z = NULL; g->mirror_fb = NULL; g->mirror_z = NULL; g->groupfn = NULL; g->groupuser = NULL; g->groupstream = NULL; g->ngroups = 0;
@@ -2469,7 +2513,11 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	else
 	{
 		/* the surface-cache build and the span-segment kernel only depend on the prep kernel: they run
-		 * side by side (second stream forked and joined with events) */
+		 * side by side (second stream forked and joined with events)
+		 * (k_cache first: its one wave of CTAs thins out as the warps run out of units and k_spanseg's CTAs move in, 6 us
+		 * after it on the device's clock; the other way round -- the longer kernel on the main stream, programmatically
+		 * dependent -- k_spanseg's eight CTAs per SM keep k_cache out until they drain and the pair ends at the same
+		 * time: RC_TRACE build, tools/variant.sh) */
 		cudaEventRecord (g->evfork, s);
 		cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
 		k_spanseg<<<g->numsms * 8, 128, 0, g->sidestream>>> (w, f);
@@ -2549,11 +2597,19 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			f.slowmode = g->slow_in_ends;
 			cudaEventRecord (g->evfork, s);
 			cudaStreamWaitEvent (g->sidestream, g->evfork, 0);
-			if (anywarp) k_ends<true><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
-			else k_ends<false><<<g->numsms * 16, 128, 0, g->sidestream>>> (w, f);
+			if (g->draw_first)
+			{
+				if (anywarp) k_draw<true><<<g->numsms * g->draw_ctas, 128, 0, s>>> (w, f);
+				else k_draw<false><<<g->numsms * g->draw_ctas, 128, 0, s>>> (w, f);
+			}
+			if (anywarp) k_ends<true><<<g->numsms * g->ends_ctas, 128, 0, g->sidestream>>> (w, f);
+			else k_ends<false><<<g->numsms * g->ends_ctas, 128, 0, g->sidestream>>> (w, f);
 			cudaEventRecord (g->evjoin, g->sidestream);
-			if (anywarp) k_draw<true><<<g->numsms * 16, 128, 0, s>>> (w, f);
-			else k_draw<false><<<g->numsms * 16, 128, 0, s>>> (w, f);
+			if (!g->draw_first)
+			{
+				if (anywarp) k_draw<true><<<g->numsms * g->draw_ctas, 128, 0, s>>> (w, f);
+				else k_draw<false><<<g->numsms * g->draw_ctas, 128, 0, s>>> (w, f);
+			}
 			if (!f.slowmode)
 			{
 				if (anywarp) CK (launch_k (k_slowcells<true>, dim3 (g->numsms * 8), dim3 (128), 0, s, g->use_pdl, w, f));
@@ -2899,6 +2955,18 @@ int rc_gpu_render (rc_gpu_t *g, const rc_batch_t *batch, void *fb_dev, void *z_d
 		if (batch->nalias) { g->aspan_need = (long long)qneed[0]; g->aspantri_need = (int)(qneed[1] < (1ull << 28) ? qneed[1] : (1ull << 28) - 1); }
 		st = stw[0];
 		g->stats.alias_range_events = stw[1];
+#ifdef RC_TRACE
+		{
+			unsigned long long tr[32];
+			static const char *nm[10] = { "reset", "front", "scan", "prep", "cache", "spanseg", "draw", "ends", "slow", "flush" };
+			cudaMemcpyFromSymbol (tr, g_trace, sizeof(tr));
+			const unsigned long long t0 = tr[0];
+			fprintf (stderr, "trace(us)");
+			for (int k = 0; k < 9; k++)
+				if (tr[2 * k + 1]) fprintf (stderr, " %s %.1f-%.1f", nm[k], (double)(long long)(tr[2 * k] - t0) * 1e-3, (double)(long long)(tr[2 * k + 1] - t0) * 1e-3);
+			fprintf (stderr, "\n");
+		}
+#endif
 #ifdef RC_FRONT_TIMING
 		{
 			int tq[16];
