@@ -204,6 +204,79 @@ const refdef_t *RC_SceneFrames (rc_scene_t *s, int *n);
 float RC_CalcFov (float fov_x, float width, float height);
 int   RC_TimeDemo (const refdef_t *frames, int n, int batch, uint8_t *fb_out, rc_timedemo_t *out);
 
+/* ---- what FILLS those lists: the client's particle system, dynamic lights and entity interpolation (rc_client.c) ----
+ * rc_fx_t owns what client/cl_effects.c keeps in globals (particles[], the active / free lists, cl_dlights[], the spark
+ * field's avelocities, the tracer counter); one per client, any number of clients.
+ *   RC_FxNew (n)           CL_InitParticles + CL_ClearParticles: n = the `-particles` argument (0: MAX_PARTICLES; floor 512)
+ *   RC_FxClear             CL_ClearParticles (cl_effects.c:147) and the light array zeroed as at a map change
+ *   RC_FxEffect            every spawner of cl_effects.c behind one call; rand () is drawn in the reference's order.
+ *                          Returns the particles made (the reference stops silently at an empty free list), -1: bad argument
+ *        effect                     a            b      i0          i1           reference
+ *        RC_FX_ENTITY_PARTICLES     ent origin   -      -           -            CL_EntityParticles    :98
+ *        RC_FX_POINT                org          -      count c     -            a line of CL_ReadPointFile_f :159
+ *        RC_FX_EXPLOSION            org          -      -           -            CL_ParticleExplosion  :233
+ *        RC_FX_EXPLOSION2           org          -      colorStart  colorLength  CL_ParticleExplosion2 :274
+ *        RC_FX_BLOB_EXPLOSION       org          -      -           -            CL_BlobExplosion      :304
+ *        RC_FX_RUN_EFFECT           org          dir    color       count        CL_RunParticleEffect  :348
+ *        RC_FX_ROCKET_SPLASH        org          -      -           -            CL_RocketSplash       :372
+ *        RC_FX_LAVA_SPLASH          org          -      -           -            CL_LavaSplash         :411
+ *        RC_FX_TELEPORT_SPLASH      org          -      -           -            CL_TeleportSplash     :517
+ *        RC_FX_RAIL_TRAIL           start        end    -           -            CL_RailTrail          :446
+ *        RC_FX_ROCKET_TRAIL .. RC_FX_VOOR_TRAIL  start  end  (tracer: color)     CL_RocketTrail :548 .. CL_VoorTrail :747
+ *   RC_FxAddParticles      CL_AddParticles (:784): dead particles leave, the living go to the scene (newest first, as the
+ *                          reference's list runs) and are moved on by time - oldtime; returns how many went to the scene
+ *   RC_FxAllocDlight       CL_AllocDlight (:915): same key, else first dead, else light 0; zeroed, the caller fills it
+ *   RC_FxAddDlights        CL_AddDlights (:959): live lights to the scene, then radius -= dt * decay
+ *   RC_ClientAddEntities   the loop body of CL_AddEntities (cl_main.c:320-470) over rc_cent_t[]: interpolation of origin,
+ *                          angles (the short way round) and frame, RF_MINLIGHT for players, rotating / bobbing items,
+ *                          EF_* effects (spark field, muzzle flash, glow lights), MF_* trails, the viewer's own model only
+ *                          from the chase camera (RF_VIEWERMODEL); writes lerp_origin back.  Returns the entities added. */
+typedef struct rc_fx_s rc_fx_t;
+typedef struct { vec3_t origin; float radius; float die; float decay; int key; } rc_fxlight_t;   /* cdlight_t, client.h:91-98 */
+enum { RC_FX_ENTITY_PARTICLES, RC_FX_POINT, RC_FX_EXPLOSION, RC_FX_EXPLOSION2, RC_FX_BLOB_EXPLOSION, RC_FX_RUN_EFFECT,
+       RC_FX_ROCKET_SPLASH, RC_FX_LAVA_SPLASH, RC_FX_TELEPORT_SPLASH, RC_FX_RAIL_TRAIL, RC_FX_ROCKET_TRAIL,
+       RC_FX_GRENADE_TRAIL, RC_FX_BLOOD_TRAIL, RC_FX_SLIGHT_BLOOD_TRAIL, RC_FX_TRACER_TRAIL, RC_FX_VOOR_TRAIL };
+#define RC_EF_BRIGHTFIELD 1          /* common/quakedef.h:210-213 */
+#define RC_EF_MUZZLEFLASH 2
+#define RC_EF_BRIGHTLIGHT 4
+#define RC_EF_DIMLIGHT    8
+#define RC_MF_ROCKET   1             /* model flags (Mod_Flags), common/quakedef.h:217-224 */
+#define RC_MF_GRENADE  2
+#define RC_MF_GIB      4
+#define RC_MF_ROTATE   8
+#define RC_MF_TRACER   16
+#define RC_MF_ZOMGIB   32
+#define RC_MF_TRACER2  64
+#define RC_MF_TRACER3  128
+typedef struct {                     /* what CL_AddEntities reads of a centity_t (client.h:62-78), its model and colormap */
+    int    number;                   /* index into cl_entities[] */
+    struct model_s *model;           /* cl.model_precache[current.modelindex]; NULL: skipped */
+    int    modelflags;               /* Mod_Flags (model) */
+    byte  *colormap;                 /* vid.colormap, or the player's translation table */
+    vec3_t prev_origin, prev_angles; int prev_frame;                     /* centity_t.prev */
+    vec3_t cur_origin, cur_angles;   int cur_frame, effects, skin;       /* centity_t.current */
+    float  startlerp, deltalerp, frametime, syncbase;
+    vec3_t lerp_origin;              /* in: where the entity was drawn last frame (the trail's start); out: this frame's */
+} rc_cent_t;
+typedef struct {                     /* the globals CL_AddEntities reads */
+    double time;                     /* cl.time */
+    int    maxclients;               /* Com_ClientMaxclients () */
+    int    viewentity;               /* cl.viewentity */
+    int    chase_active, bobbingitems;   /* the cvars, as booleans */
+    vec3_t viewangles;               /* cl.viewangles */
+} rc_clframe_t;
+rc_fx_t *RC_FxNew (int max_particles);
+void  RC_FxFree (rc_fx_t *fx);
+void  RC_FxClear (rc_fx_t *fx);
+int   RC_FxEffect (rc_fx_t *fx, int effect, const float *a, const float *b, int i0, int i1, double time);
+int   RC_FxAddParticles (rc_fx_t *fx, rc_scene_t *scene, double time, double oldtime);
+int   RC_FxParticleCount (const rc_fx_t *fx);
+int   RC_FxParticles (const rc_fx_t *fx, int max, float *org3, float *vel3, float *ramp, float *die, int *color, int *kind);
+rc_fxlight_t *RC_FxAllocDlight (rc_fx_t *fx, int key, double time);
+rc_fxlight_t *RC_FxLights (rc_fx_t *fx);                /* the MAX_DLIGHTS lights */
+int   RC_FxAddDlights (rc_fx_t *fx, rc_scene_t *scene, double time, double oldtime);
+int   RC_ClientAddEntities (rc_fx_t *fx, rc_scene_t *scene, rc_cent_t *cents, int n, const rc_clframe_t *frame);
+
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)
  * n*height*width int16.  Host<->device copies happen inside the call.

@@ -1,0 +1,53 @@
+"""ctypes mirrors of the client-side producer API (include/ref_cuda.h, tochris_b200/csrc/rc_client.c): the structs
+CL_AddEntities reads (rc_cent_t / rc_clframe_t), the dynamic-light record and the effect numbers; `bind(lib)` declares
+the RC_Fx* / RC_ClientAddEntities prototypes on a loaded library (product or host simulator)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from .refdef import vec3
+
+(FX_ENTITY_PARTICLES, FX_POINT, FX_EXPLOSION, FX_EXPLOSION2, FX_BLOB_EXPLOSION, FX_RUN_EFFECT, FX_ROCKET_SPLASH,
+ FX_LAVA_SPLASH, FX_TELEPORT_SPLASH, FX_RAIL_TRAIL, FX_ROCKET_TRAIL, FX_GRENADE_TRAIL, FX_BLOOD_TRAIL,
+ FX_SLIGHT_BLOOD_TRAIL, FX_TRACER_TRAIL, FX_VOOR_TRAIL) = range(16)
+EF_BRIGHTFIELD, EF_MUZZLEFLASH, EF_BRIGHTLIGHT, EF_DIMLIGHT = 1, 2, 4, 8                  # common/quakedef.h:210-213
+MF_ROCKET, MF_GRENADE, MF_GIB, MF_ROTATE, MF_TRACER, MF_ZOMGIB, MF_TRACER2, MF_TRACER3 = 1, 2, 4, 8, 16, 32, 64, 128
+MAX_DLIGHTS = 32
+
+
+class rc_fxlight_t(C.Structure):      # cdlight_t, client/client.h:91-98
+    _fields_ = [("origin", vec3), ("radius", C.c_float), ("die", C.c_float), ("decay", C.c_float), ("key", C.c_int)]
+
+
+class rc_cent_t(C.Structure):
+    _fields_ = [("number", C.c_int), ("model", C.c_void_p), ("modelflags", C.c_int), ("colormap", C.c_void_p),
+                ("prev_origin", vec3), ("prev_angles", vec3), ("prev_frame", C.c_int),
+                ("cur_origin", vec3), ("cur_angles", vec3), ("cur_frame", C.c_int), ("effects", C.c_int), ("skin", C.c_int),
+                ("startlerp", C.c_float), ("deltalerp", C.c_float), ("frametime", C.c_float), ("syncbase", C.c_float),
+                ("lerp_origin", vec3)]
+
+
+class rc_clframe_t(C.Structure):
+    _fields_ = [("time", C.c_double), ("maxclients", C.c_int), ("viewentity", C.c_int), ("chase_active", C.c_int),
+                ("bobbingitems", C.c_int), ("viewangles", vec3)]
+
+
+def bind(L):
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    L.RC_FxNew.argtypes = [C.c_int]
+    L.RC_FxNew.restype = C.c_void_p
+    L.RC_FxFree.argtypes = [C.c_void_p]
+    L.RC_FxFree.restype = None
+    L.RC_FxClear.argtypes = [C.c_void_p]
+    L.RC_FxClear.restype = None
+    L.RC_FxEffect.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, C.c_int, C.c_double]
+    L.RC_FxAddParticles.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    L.RC_FxParticleCount.argtypes = [C.c_void_p]
+    L.RC_FxParticles.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp, ip, ip]
+    L.RC_FxAllocDlight.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.RC_FxAllocDlight.restype = C.POINTER(rc_fxlight_t)
+    L.RC_FxLights.argtypes = [C.c_void_p]
+    L.RC_FxLights.restype = C.POINTER(rc_fxlight_t)
+    L.RC_FxAddDlights.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    L.RC_ClientAddEntities.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(rc_cent_t), C.c_int, C.POINTER(rc_clframe_t)]
+    return L
