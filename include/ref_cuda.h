@@ -175,6 +175,22 @@ int  RC_TimeRefresh (const refdef_t *base, uint8_t *fb_out, double *seconds, int
 int  RC_PointContents (const float *org);
 int  RC_ViewFlagsForOrigin (const float *org);
 
+/* ---- device lifetimes of the alias models (ref_soft/r_model.c:95-130, 247-258, common/zone.c) ----
+ * The reference keeps alias models in the Cache_Alloc heap: the least recently used ones are thrown out when it is short
+ * of room, reloaded when asked for again, and Mod_TouchModel refreshes a model's place in that order.  The device copy
+ * follows the same rules under RC_SetModelCacheBytes (0, the default: everything loaded stays resident): the models a
+ * batch draws are resident while it is drawn (even above the budget); when one of them is not, the resident set is
+ * rebuilt -- the batch's models, then the rest from the most to the least recently used while they fit -- from the
+ * host copy.  Pixels never depend on it. */
+typedef struct {
+    int    loaded, resident;          /* alias models loaded on the host / resident on the device */
+    size_t resident_bytes, budget_bytes;
+    int    uploads, evictions;        /* models that came onto / left the device since RC_Init */
+    int    rebuilds;                  /* times the resident set was re-packed */
+} rc_modelcache_t;
+void RC_SetModelCacheBytes (size_t bytes);
+void RC_ModelCacheInfo (rc_modelcache_t *out);
+
 /* ---- the client's scene lists and `timedemo` in batched form (rc_scene.c) ----
  * rc_scene_t keeps the four per-frame lists of client/cl_view.c:67-78 with the reference's limits (256 entities, 2048
  * particles, 32 dlights, 16 colour shifts; what is added to a full list is dropped: the Add calls return 0) and, unlike

@@ -48,6 +48,11 @@ class rc_timedemo_t(C.Structure):    # include/ref_cuda.h rc_timedemo_t
     _fields_ = [("frames", C.c_int), ("seconds", C.c_double), ("fps", C.c_double), ("status", C.c_int), ("text", C.c_char * 64)]
 
 
+class rc_modelcache_t(C.Structure):   # include/ref_cuda.h rc_modelcache_t
+    _fields_ = [("loaded", C.c_int), ("resident", C.c_int), ("resident_bytes", C.c_size_t), ("budget_bytes", C.c_size_t),
+                ("uploads", C.c_int), ("evictions", C.c_int), ("rebuilds", C.c_int)]
+
+
 class rc_edge_t(C.Structure):
     _fields_ = [("u", C.c_int), ("u_step", C.c_int), ("v", C.c_short), ("v2", C.c_short),
                 ("surfs", C.c_ushort * 2), ("rank", C.c_uint), ("pad", C.c_int * 3)]
@@ -147,6 +152,12 @@ class RefCuda:
         L.RC_CalcFov.argtypes = [C.c_float, C.c_float, C.c_float]
         L.RC_CalcFov.restype = C.c_float
         L.RC_TimeDemo.argtypes = [C.POINTER(refdef_t), C.c_int, C.c_int, C.c_void_p, C.POINTER(rc_timedemo_t)]
+        L.RC_SetModelCacheBytes.argtypes = [C.c_size_t]
+        L.RC_SetModelCacheBytes.restype = None
+        L.RC_ModelCacheInfo.argtypes = [C.POINTER(rc_modelcache_t)]
+        L.RC_ModelCacheInfo.restype = None
+        L.Mod_TouchModel.argtypes = [C.c_char_p]
+        L.Mod_TouchModel.restype = None
         L.Mod_ForName.restype = C.c_void_p
         L.Mod_ForName.argtypes = [C.c_char_p, C.c_int]
         cfg = rc_config_t()
@@ -403,6 +414,18 @@ class RefCuda:
 
     def flush_caches(self):
         self.lib.RC_FlushCaches()
+
+    def set_model_cache_bytes(self, nbytes: int):
+        """device budget of the alias models (0: everything loaded stays resident); least recently used leave first"""
+        self.lib.RC_SetModelCacheBytes(nbytes)
+
+    def touch_model(self, name: str):
+        self.lib.Mod_TouchModel(name.encode())
+
+    def model_cache_info(self) -> dict:
+        s = rc_modelcache_t()
+        self.lib.RC_ModelCacheInfo(C.byref(s))
+        return {k: getattr(s, k) for k, _ in rc_modelcache_t._fields_}
 
     def set_profiling(self, on: bool):
         self.lib.RC_SetProfiling(int(on))

@@ -55,6 +55,10 @@ static struct {
 	uint8_t     *cmapscratch; int cmapscratchcap;
 	float        anorm_dots[16 * 256];
 	int          alias_dirty;		/* alias models loaded since the last device upload */
+	/* device residency of the alias models (the reference's Cache_Alloc lifetimes, r_model.c:95-130 / zone.c) */
+	size_t       modelcache_bytes;		/* budget, 0: every loaded model stays resident */
+	long long    model_clock;
+	rc_modelcache_t modelcache;
 	int          sprite_dirty;		/* ditto sprite models */
 	rc_spriteinst_t *spritescratch; int spritescratchcap;
 	rc_batch_t   batch;
@@ -318,7 +322,90 @@ struct model_s *Mod_ForName (char *name, qboolean crash)
 	return m;
 }
 
-void Mod_TouchModel (char *name) { (void)name; }
+/* Mod_TouchModel, r_model.c:247-258: a loaded alias model becomes the most recently used one (Cache_Check), so that it is
+ * the last to leave the device when the model cache is short of room; never loads anything */
+void Mod_TouchModel (char *name)
+{
+	struct model_s *m = name ? rc_find_model (name) : NULL;
+	if (m && m->type == rc_mod_alias && m->alias)
+		m->alias->last_used = ++rc.model_clock;
+}
+
+static size_t rc_alias_device_bytes (const rc_hostalias_t *a)
+{
+	return 16 * (size_t)a->numverts + 16 * (size_t)a->numtris + 4 * (size_t)a->numposes * a->numverts + (size_t)a->skinimagelen;
+}
+
+/* The device copy of the alias models has the lifetimes of the reference's model cache: the reference keeps alias models
+ * in the Cache_Alloc heap, which throws out the least recently used ones when it is short of room (zone.c), reloads a
+ * model when something asks for it again (Mod_Extradata -> Mod_LoadModel, r_model.c:95-130) and lets Mod_TouchModel
+ * refresh a model's place in that order.  Here the budget is RC_SetModelCacheBytes: a batch's models are always
+ * resident while it is drawn; when one of them is not, the resident set is rebuilt -- the batch's models first, then
+ * the others from the most to the least recently used while they fit -- and uploaded from the host copy. */
+static int rc_alias_make_resident (const refdef_t *views, int n)
+{
+	int i, j, need = rc.alias_dirty, nloaded = 0, nres = 0;
+	rc_hostalias_t *loaded[RC_MAX_MODELS], *res[RC_MAX_MODELS];
+	size_t bytes = 0;
+	const long long now = ++rc.model_clock;
+	for (i = 0; i < n; i++)
+		for (j = 0; j < views[i].num_entities; j++)
+		{
+			const struct model_s *mod = views[i].entities[j].model;
+			if (mod && mod->type == rc_mod_alias && mod->alias && mod->alias->last_used != now)
+			{
+				mod->alias->last_used = now;
+				if (mod->alias->device_index < 0) need = 1;
+			}
+		}
+	if (!need)
+		return RC_OK;
+	for (i = 0; i < rc.nummodels; i++)
+		if (rc.models[i]->type == rc_mod_alias && rc.models[i]->alias)
+			loaded[nloaded++] = rc.models[i]->alias;
+	/* most recently used first (insertion sort: a few dozen models; stable, so equal stamps keep load order) */
+	for (i = 1; i < nloaded; i++)
+	{
+		rc_hostalias_t *a = loaded[i];
+		for (j = i; j > 0 && loaded[j - 1]->last_used < a->last_used; j--) loaded[j] = loaded[j - 1];
+		loaded[j] = a;
+	}
+	for (i = 0; i < nloaded; i++)
+	{
+		rc_hostalias_t *a = loaded[i];
+		const size_t b = rc_alias_device_bytes (a);
+		const int wanted = a->last_used == now;
+		if (wanted || !rc.modelcache_bytes || bytes + b <= rc.modelcache_bytes)
+		{
+			if (a->device_index < 0) rc.modelcache.uploads++;
+			res[nres++] = a;
+			bytes += b;
+		}
+		else
+		{
+			if (a->device_index >= 0) rc.modelcache.evictions++;
+			a->device_index = -1;
+		}
+	}
+	if (rc_gpu_upload_alias (rc.gpu, res, nres, rc.anorm_dots, rc.err, sizeof(rc.err)) != RC_OK)
+		return RC_ERR_CUDA;
+	rc.modelcache.rebuilds++;
+	rc.modelcache.resident = nres; rc.modelcache.loaded = nloaded;
+	rc.modelcache.resident_bytes = bytes; rc.modelcache.budget_bytes = rc.modelcache_bytes;
+	rc.alias_dirty = 0;
+	return RC_OK;
+}
+
+void RC_SetModelCacheBytes (size_t bytes)
+{
+	if (bytes != rc.modelcache_bytes) rc.alias_dirty = 1;	/* the next batch with entities re-packs the resident set */
+	rc.modelcache_bytes = bytes;
+}
+
+void RC_ModelCacheInfo (rc_modelcache_t *out)
+{
+	if (out) { *out = rc.modelcache; out->budget_bytes = rc.modelcache_bytes; }
+}
 int  Mod_Flags (struct model_s *model) { return model ? model->flags : 0; }
 void R_TranslatePlayerSkin (int playernum, struct model_s *model, int skinnum, int top, int bottom)
 { (void)playernum; (void)model; (void)skinnum; (void)top; (void)bottom; }
@@ -470,8 +557,6 @@ static int rc_prepare_views (const refdef_t *views, int n)
 	{
 		int nent = 0, npart = 0, nalias = 0, nverts = 0, ncmap = 1, nzres = 0, maxcmaps = 1, nsprites = 0;
 		const byte *cmaps[64];
-		rc_hostalias_t *amodels[RC_MAX_MODELS];
-		int namodels = 0;
 		for (i = 0; i < n; i++)
 		{
 			nent += views[i].num_entities > 0 ? views[i].num_entities : 0;
@@ -495,15 +580,8 @@ static int rc_prepare_views (const refdef_t *views, int n)
 			rc.spritescratchcap = rc.spritescratch ? nent : 0;
 			if (!rc.spritescratch) return rc_fail (RC_ERR_NOMEM, "out of memory");
 		}
-		if (rc.alias_dirty && nent)
-		{
-			for (i = 0; i < rc.nummodels; i++)
-				if (rc.models[i]->type == rc_mod_alias)
-					amodels[namodels++] = rc.models[i]->alias;
-			if (rc_gpu_upload_alias (rc.gpu, amodels, namodels, rc.anorm_dots, rc.err, sizeof(rc.err)) != RC_OK)
-				return RC_ERR_CUDA;
-			rc.alias_dirty = 0;
-		}
+		if (nent && rc_alias_make_resident (views, n) != RC_OK)
+			return RC_ERR_CUDA;
 		if (nent > rc.aliasscratchcap)
 		{
 			free (rc.aliasscratch);

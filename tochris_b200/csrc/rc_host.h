@@ -69,7 +69,8 @@ typedef struct rc_hostalias_s {  /* aliashdr_t + mdl_t, flattened */
     int  *skinpicofs;          /* [numskinpics]: offset of every skin picture inside the image */
     rc_aliasframe_t *frames, *skins;
     float *intervals;
-    int   device_index;        /* slot in the device model table, -1 until uploaded */
+    int   device_index;        /* slot in the device model table, -1 while not resident on the device */
+    long long last_used;       /* the library's model clock when a batch last drew it / Mod_TouchModel named it (LRU order) */
 } rc_hostalias_t;
 
 typedef struct { int type; int first, count; int intervals; } rc_spriteframe_t;   /* mspriteframedesc_t: single (0) or group */
@@ -150,7 +151,7 @@ typedef struct {
 
 rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, int max_views, char *err, size_t errlen);
 void rc_gpu_destroy (rc_gpu_t *g);
-/* (re)uploads every loaded alias model; models[i]->device_index = i */
+/* (re)uploads the given alias models (the resident set of rc_api.c's model cache); models[i]->device_index = i */
 int  rc_gpu_upload_alias (rc_gpu_t *g, rc_hostalias_t **models, int n, const float *anorm_dots, char *err, size_t errlen);
 /* (re)uploads the pixels of every loaded sprite model; models[i]->device_ofs is set */
 int  rc_gpu_upload_sprites (rc_gpu_t *g, rc_hostsprite_t **models, int n, char *err, size_t errlen);
