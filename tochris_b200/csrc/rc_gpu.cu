@@ -1794,14 +1794,48 @@ __global__ void k_alias_verts (const __grid_constant__ rc_frame_t f)
 	rc_alias_vertex (&f, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-/* One thread per (instance, triangle) walks the triangle's edges; the spans go to the queue (rc_pipeline.h "Span queue").
- * The slots of the unclipped triangles of a warp are reserved with ONE atomic: a triangle knows its scanline count before
- * it is walked, and 1.3 M triangles adding to one counter one by one would be the longest thing in the kernel. */
-__global__ void __launch_bounds__(64) k_alias_tris (const __grid_constant__ rc_frame_t f)
+/* The triangles of the batch's alias instances: a thread looks at one (instance, triangle), and the triangles that
+ * survive -- about four in ten at C3: half face away, some are clipped off -- are walked (their edges stepped scanline
+ * by scanline, the spans going to the queue: rc_pipeline.h "Span queue").
+ *   - The slots of the unclipped triangles of a warp are reserved with ONE atomic: a triangle knows its scanline count
+ *     before it is walked, and 1.3 M triangles adding to one counter one by one would be the longest thing in the kernel.
+ *   - The walk is long, branchy code; with a thread per triangle walking its own, the culled lanes idled through it
+ *     (7.4 of 32 lanes active at C3).  So the CTA first COMPACTS its surviving triangles into shared memory and then
+ *     walks them with as few, full warps as they need; the index space is (instance, triangle) flattened, so a CTA's
+ *     256 candidates do not stop at a model's last triangle. */
+#define ATRI_THREADS 256
+__device__ __forceinline__ bool alias_triangle_alive (const rc_frame_t &f, int ii, int ti)
 {
-	const int ii = blockIdx.y, ti = blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned lane = threadIdx.x & 31;
-	const int rows = f.aspancap > 0 ? rc_alias_triangle_rows (&f, ii, ti) : 0;
+	/* what rc_alias_triangle would return from at once: past the model's last triangle, facing away (unclipped:
+	 * d_xdenom >= 0, d_polyse.c:150-156), or every vertex beyond the same edge of the view */
+	const rc_aliasinst_t *in = &f.alias[ii];
+	const rc_aliasmodel_t *m = &f.amodels[in->model];
+	if (ti >= m->numtris)
+		return false;
+	const int *tri = f.atris + 4 * ((size_t)m->tris_ofs + ti);
+	const rc_finalvert_t *pfv = f.finalverts + in->vertbase;
+	const rc_finalvert_t *a = &pfv[tri[1]], *b = &pfv[tri[2]], *d = &pfv[tri[3]];
+	const int clipmask = RC_ALIAS_XY_CLIP_MASK | RC_ALIAS_Z_CLIP;
+	if (!in->trivial_accept)
+	{
+		if (a->flags & b->flags & d->flags & clipmask)
+			return false;
+		if ((a->flags | b->flags | d->flags) & clipmask)
+			return true;		/* clipped: the fan's triangles are tested one by one */
+	}
+	return (a->v[1] - b->v[1]) * (a->v[0] - d->v[0]) - (a->v[0] - b->v[0]) * (a->v[1] - d->v[1]) < 0;
+}
+
+__global__ void __launch_bounds__(ATRI_THREADS) k_alias_tris (const __grid_constant__ rc_frame_t f, const int ninst, const int maxtris)
+{
+	__shared__ int s_ii[ATRI_THREADS], s_ti[ATRI_THREADS], s_rows[ATRI_THREADS], s_tri[ATRI_THREADS], s_wcount[ATRI_THREADS / 32];
+	__shared__ long long s_span0[ATRI_THREADS];
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const long long gidx = (long long)blockIdx.x * ATRI_THREADS + threadIdx.x;
+	const int ii = (int)(gidx / maxtris), ti = (int)(gidx - (long long)ii * maxtris);
+	const bool valid = ii < ninst;
+	const int rows = valid && f.aspancap > 0 ? rc_alias_triangle_rows (&f, ii, ti) : 0;
+	const bool alive = valid && (rows > 0 || alias_triangle_alive (f, ii, ti));
 	/* inclusive prefix sum of the rows, count of the triangles */
 	int pre = rows;
 	#pragma unroll
@@ -1818,11 +1852,36 @@ __global__ void __launch_bounds__(64) k_alias_tris (const __grid_constant__ rc_f
 	base = __shfl_sync (0xFFFFFFFFu, base, 0);
 	const long long span0 = (long long)(base & ((1ull << RC_AQ_SHIFT) - 1)) + (pre - rows);
 	const int tri = (int)(base >> RC_AQ_SHIFT) + __popc (wants & ((1u << lane) - 1u));
-	rc_alias_triangle (&f, ii, ti, f.aspancap > 0 ? 1 : 0, rows, span0, tri);
+	/* the survivors, in order, into shared memory (binning them by scanline count, so that a warp's triangles are of a
+	 * height, was measured and changes nothing: 2.87-2.95 against 2.87-3.00 ms alias stage at C3) */
+	const unsigned am = __ballot_sync (0xFFFFFFFFu, alive);
+	if (lane == 0) s_wcount[wid] = __popc (am);
+	__syncthreads ();
+	int off = 0, nitems = 0;
+	#pragma unroll
+	for (int q = 0; q < ATRI_THREADS / 32; q++)
+	{
+		if (q < (int)wid) off += s_wcount[q];
+		nitems += s_wcount[q];
+	}
+	if (alive)
+	{
+		const int k = off + __popc (am & ((1u << lane) - 1u));
+		s_ii[k] = ii; s_ti[k] = ti; s_rows[k] = rows; s_tri[k] = tri; s_span0[k] = span0;
+	}
+	__syncthreads ();
+	if ((int)threadIdx.x < nitems)
+	{
+		const int k = threadIdx.x;
+		rc_alias_triangle (&f, s_ii[k], s_ti[k], f.aspancap > 0 ? 1 : 0, s_rows[k], s_span0[k], s_tri[k]);
+	}
 }
 
 /* one thread per queued span: D_PolysetDrawSpans8 */
-__global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc_frame_t f)
+#ifndef ALIAS_SPANS_MINB
+#define ALIAS_SPANS_MINB 4	/* 64 registers: 3.26 -> 3.08 ms alias stage at C3 against 76 registers (three CTAs per SM); 5 CTAs (48 registers, spills): 3.37 */
+#endif
+__global__ void __launch_bounds__(256, ALIAS_SPANS_MINB) k_alias_spans (const __grid_constant__ rc_frame_t f)
 {
 	const unsigned long long a = f.alloc[5];
 	long long n = (long long)(a & ((1ull << RC_AQ_SHIFT) - 1));
@@ -1835,6 +1894,83 @@ __global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc
 	const uint4 *sp4 = reinterpret_cast<const uint4 *>(f.aspans);
 	long long tested = 0; int front = 0, nsp = 0;
 	const uint4 *tr4 = reinterpret_cast<const uint4 *>(f.aspantris);
+#ifndef ALIAS_SPAN_PER_THREAD
+	/* A thread per span leaves half the lanes idle (15.6 of 32 at C3): a warp's 32 spans run from 1 to 60 pixels and the
+	 * warp loops for the longest.  Here the unit of work is a CHUNK of four consecutive pixels (one round of
+	 * rc_polyset_span): the warp loads 32 spans, scans their chunk counts, and deals the chunks out one per lane -- the
+	 * lane finds its span by a binary search over the scan (shuffles), takes the span's fields from the lane that
+	 * loaded it, steps the span's state to the chunk's first pixel in closed form, and runs the reference's stepping
+	 * from there.  The closed form is exact: 1/z and light are wrapping 32-bit sums, the skin pointer gains
+	 * a_ststepxwhole per pixel plus one carry out of 16 bits of s fraction and one skin row per carry out of 16 bits of
+	 * t fraction (d_polyse.c:431-441), and the carries of k steps telescope to floor ((frac + k * step) / 65536) because
+	 * both fractions and both steps are below 65536 (k * step < 2^27). */
+	const unsigned lane = threadIdx.x & 31u;
+	const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * 32;
+	for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n; base += wstride)
+	{
+		const long long i = base + lane;
+		uint4 s0 = make_uint4 (0u, 0u, 0u, 0u), s1 = make_uint4 (0u, 0u, 0u, 0u);
+		if (i < n)
+		{
+			s0 = __ldcs (&sp4[2 * i]);
+			if ((int)s0.y > 0) s1 = __ldcs (&sp4[2 * i + 1]);
+		}
+		const int mycount = (int)s0.y > 0 ? (int)s0.y : 0;
+		const int mychunks = (mycount + 3) >> 2;
+		int incl = mychunks;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int v = __shfl_up_sync (0xFFFFFFFFu, incl, o);
+			if (lane >= (unsigned)o) incl += v;
+		}
+		const int total = __shfl_sync (0xFFFFFFFFu, incl, 31);
+		const int excl = incl - mychunks;
+		tested += mycount; nsp += mycount > 0;
+		for (int q0 = 0; q0 < total; q0 += 32)
+		{
+			const int q = q0 + (int)lane;
+			const bool act = q < total;
+			const int qq = act ? q : total - 1;
+			/* the span whose chunks include qq: the first lane whose inclusive count is above it */
+			int lo = 0, hi = 31;
+			#pragma unroll
+			for (int it = 0; it < 5; it++)
+			{
+				const int mid = (lo + hi) >> 1;
+				const int v = __shfl_sync (0xFFFFFFFFu, incl, mid);
+				if (v > qq) hi = mid; else lo = mid + 1;
+			}
+			const int src = lo;
+			const int k0 = (qq - __shfl_sync (0xFFFFFFFFu, excl, src)) << 2;
+			rc_aspan_t sp;
+			sp.xy = (int)__shfl_sync (0xFFFFFFFFu, s0.x, src); sp.count = (int)__shfl_sync (0xFFFFFFFFu, s0.y, src);
+			sp.ptex = (int)__shfl_sync (0xFFFFFFFFu, s0.z, src); sp.stfrac = (int)__shfl_sync (0xFFFFFFFFu, s0.w, src);
+			sp.light = (int)__shfl_sync (0xFFFFFFFFu, s1.x, src); sp.zi = (int)__shfl_sync (0xFFFFFFFFu, s1.y, src);
+			sp.tri = (int)__shfl_sync (0xFFFFFFFFu, s1.z, src); sp.pad = 0;
+			if (!act)
+				continue;
+			const uint4 t0 = __ldg (&tr4[4 * (size_t)sp.tri]), t1 = __ldg (&tr4[4 * (size_t)sp.tri + 1]),
+				    t2 = __ldg (&tr4[4 * (size_t)sp.tri + 2]), t3 = __ldg (&tr4[4 * (size_t)sp.tri + 3]);
+			rc_aspantri_t t;
+			t.zistepx = (int)t0.x; t.lstepx = (int)t0.y; t.ststepxwhole = (int)t0.z; t.stfracstep = (int)t0.w;
+			t.orderbits = (unsigned long long)t1.x | ((unsigned long long)t1.y << 32); t.skinofs = (int)t1.z; t.skinwidth = (int)t1.w;
+			t.skinlo = (int)t2.x; t.skinhi = (int)t2.y; t.cmapidx = (int)t2.z; t.viewidx = (int)t2.w;
+			t.zresidx = (int)t3.x; t.zwidth = (int)t3.y; t.pad[0] = t.pad[1] = 0;
+			/* the span from its pixel k0 on, four pixels at most */
+			const int sstep = t.stfracstep & 0xFFFF, tstep = (int)((unsigned)t.stfracstep >> 16);
+			const int S = (sp.stfrac & 0xFFFF) + k0 * sstep, T = (int)((unsigned)sp.stfrac >> 16) + k0 * tstep;
+			const int left = sp.count - k0;
+			sp.xy = (int)(((unsigned)sp.xy & 0xFFFF0000u) | (((unsigned)sp.xy + (unsigned)k0) & 0xFFFFu));
+			sp.count = left < 4 ? left : 4;
+			sp.ptex += k0 * t.ststepxwhole + (S >> 16) + t.skinwidth * (T >> 16);
+			sp.stfrac = (S & 0xFFFF) | ((T & 0xFFFF) << 16);
+			sp.light = (int)((unsigned)sp.light + (unsigned)k0 * (unsigned)t.lstepx);
+			sp.zi = (int)((unsigned)sp.zi + (unsigned)k0 * (unsigned)t.zistepx);
+			front += rc_alias_queued_span (&f, sp, t);
+		}
+	}
+#else
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
 	{
 		const uint4 s0 = __ldcs (&sp4[2 * i]);
@@ -1854,6 +1990,7 @@ __global__ void __launch_bounds__(256) k_alias_spans (const __grid_constant__ rc
 		front += rc_alias_queued_span (&f, sp, t);
 		tested += sp.count; nsp++;
 	}
+#endif
 	if (f.countfrags)
 	{
 		/* profiling mode: fragments looked at / in front of the world (alloc[9], alloc[10]), spans (alloc[11]) */
@@ -2643,11 +2780,12 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			int cnt = ahi - first < astep ? ahi - first : astep;
 			rc_frame_t f2 = f;
 			f2.alias = g->d_alias + first;
-			dim3 ga ((g->maxverts + 127) / 128, cnt), gt ((g->maxtris + 63) / 64, cnt);
+			dim3 ga ((g->maxverts + 127) / 128, cnt);
+			const unsigned gt = (unsigned)(((long long)cnt * (g->maxtris > 0 ? g->maxtris : 1) + ATRI_THREADS - 1) / ATRI_THREADS);
 			f2.aspans = g->d_aspans; f2.aspancap = g->aspancap; f2.aspantris = g->d_aspantris; f2.aspantricap = g->aspantricap;
 			CK (cudaMemsetAsync (g->d_alloc + 5, 0, sizeof(unsigned long long), s));
 			k_alias_verts<<<ga, 128, 0, s>>> (f2);
-			k_alias_tris<<<gt, 64, 0, s>>> (f2);
+			k_alias_tris<<<gt, ATRI_THREADS, 0, s>>> (f2, cnt, g->maxtris > 0 ? g->maxtris : 1);
 			k_alias_spans<<<g->numsms * 8, 256, 0, s>>> (f2);
 			g->stats.kernel_launches += 3;
 		}
