@@ -1804,6 +1804,9 @@ __global__ void k_alias_verts (const __grid_constant__ rc_frame_t f)
  *     walks them with as few, full warps as they need; the index space is (instance, triangle) flattened, so a CTA's
  *     256 candidates do not stop at a model's last triangle. */
 #define ATRI_THREADS 256
+#ifndef ATRI_CAND
+#define ATRI_CAND 1	/* candidates per thread: 2 (the survivors then fill seven of the CTA's eight warps) measured the same, 3 slower */
+#endif
 __device__ __forceinline__ bool alias_triangle_alive (const rc_frame_t &f, int ii, int ti)
 {
 	/* what rc_alias_triangle would return from at once: past the model's last triangle, facing away (unclipped:
@@ -1828,53 +1831,67 @@ __device__ __forceinline__ bool alias_triangle_alive (const rc_frame_t &f, int i
 
 __global__ void __launch_bounds__(ATRI_THREADS) k_alias_tris (const __grid_constant__ rc_frame_t f, const int ninst, const int maxtris)
 {
-	__shared__ int s_ii[ATRI_THREADS], s_ti[ATRI_THREADS], s_rows[ATRI_THREADS], s_tri[ATRI_THREADS], s_wcount[ATRI_THREADS / 32];
-	__shared__ long long s_span0[ATRI_THREADS];
+	/* ATRI_CAND candidates per thread: with one, the CTA's survivors fill three or four of its eight warps and the rest
+	 * of its register allocation idles through the walk (12 % of the SM's warp slots active at C3) -- which is not what
+	 * bounds it: two candidates per thread, seven busy warps, 2.90 against 2.83-2.92 ms alias stage */
+	constexpr int NC = ATRI_THREADS * ATRI_CAND;
+	__shared__ int s_ii[NC], s_ti[NC], s_rows[NC], s_tri[NC], s_wcount[ATRI_CAND][ATRI_THREADS / 32];
+	__shared__ long long s_span0[NC];
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const long long gidx = (long long)blockIdx.x * ATRI_THREADS + threadIdx.x;
-	const int ii = (int)(gidx / maxtris), ti = (int)(gidx - (long long)ii * maxtris);
-	const bool valid = ii < ninst;
-	const int rows = valid && f.aspancap > 0 ? rc_alias_triangle_rows (&f, ii, ti) : 0;
-	const bool alive = valid && (rows > 0 || alias_triangle_alive (f, ii, ti));
-	/* inclusive prefix sum of the rows, count of the triangles */
-	int pre = rows;
+	int ii[ATRI_CAND], ti[ATRI_CAND], rows[ATRI_CAND], tri[ATRI_CAND];
+	long long span0[ATRI_CAND];
+	bool alive[ATRI_CAND];
+	unsigned am[ATRI_CAND];
 	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
+	for (int c = 0; c < ATRI_CAND; c++)
 	{
-		const int v = __shfl_up_sync (0xFFFFFFFFu, pre, o);
-		if (lane >= (unsigned)o) pre += v;
+		const long long gidx = ((long long)blockIdx.x * ATRI_CAND + c) * ATRI_THREADS + threadIdx.x;
+		ii[c] = (int)(gidx / maxtris); ti[c] = (int)(gidx - (long long)ii[c] * maxtris);
+		const bool valid = ii[c] < ninst;
+		rows[c] = valid && f.aspancap > 0 ? rc_alias_triangle_rows (&f, ii[c], ti[c]) : 0;
+		alive[c] = valid && (rows[c] > 0 || alias_triangle_alive (f, ii[c], ti[c]));
+		/* inclusive prefix sum of the rows, count of the triangles */
+		int pre = rows[c];
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int v = __shfl_up_sync (0xFFFFFFFFu, pre, o);
+			if (lane >= (unsigned)o) pre += v;
+		}
+		const unsigned wants = __ballot_sync (0xFFFFFFFFu, rows[c] > 0);
+		const int total = __shfl_sync (0xFFFFFFFFu, pre, 31);
+		unsigned long long base = 0ull;
+		if (lane == 0 && wants)
+			base = atomicAdd (&f.alloc[5], ((unsigned long long)__popc (wants) << RC_AQ_SHIFT) | (unsigned long long)total);
+		base = __shfl_sync (0xFFFFFFFFu, base, 0);
+		span0[c] = (long long)(base & ((1ull << RC_AQ_SHIFT) - 1)) + (pre - rows[c]);
+		tri[c] = (int)(base >> RC_AQ_SHIFT) + __popc (wants & ((1u << lane) - 1u));
+		am[c] = __ballot_sync (0xFFFFFFFFu, alive[c]);
+		if (lane == 0) s_wcount[c][wid] = __popc (am[c]);
 	}
-	const unsigned wants = __ballot_sync (0xFFFFFFFFu, rows > 0);
-	const int total = __shfl_sync (0xFFFFFFFFu, pre, 31);
-	unsigned long long base = 0ull;
-	if (lane == 0 && wants)
-		base = atomicAdd (&f.alloc[5], ((unsigned long long)__popc (wants) << RC_AQ_SHIFT) | (unsigned long long)total);
-	base = __shfl_sync (0xFFFFFFFFu, base, 0);
-	const long long span0 = (long long)(base & ((1ull << RC_AQ_SHIFT) - 1)) + (pre - rows);
-	const int tri = (int)(base >> RC_AQ_SHIFT) + __popc (wants & ((1u << lane) - 1u));
 	/* the survivors, in order, into shared memory (binning them by scanline count, so that a warp's triangles are of a
 	 * height, was measured and changes nothing: 2.87-2.95 against 2.87-3.00 ms alias stage at C3) */
-	const unsigned am = __ballot_sync (0xFFFFFFFFu, alive);
-	if (lane == 0) s_wcount[wid] = __popc (am);
 	__syncthreads ();
-	int off = 0, nitems = 0;
+	int nitems = 0;
 	#pragma unroll
-	for (int q = 0; q < ATRI_THREADS / 32; q++)
+	for (int c = 0; c < ATRI_CAND; c++)
 	{
-		if (q < (int)wid) off += s_wcount[q];
-		nitems += s_wcount[q];
-	}
-	if (alive)
-	{
-		const int k = off + __popc (am & ((1u << lane) - 1u));
-		s_ii[k] = ii; s_ti[k] = ti; s_rows[k] = rows; s_tri[k] = tri; s_span0[k] = span0;
+		int off = nitems;
+		#pragma unroll
+		for (int q = 0; q < ATRI_THREADS / 32; q++)
+		{
+			if (q < (int)wid) off += s_wcount[c][q];
+			nitems += s_wcount[c][q];
+		}
+		if (alive[c])
+		{
+			const int k = off + __popc (am[c] & ((1u << lane) - 1u));
+			s_ii[k] = ii[c]; s_ti[k] = ti[c]; s_rows[k] = rows[c]; s_tri[k] = tri[c]; s_span0[k] = span0[c];
+		}
 	}
 	__syncthreads ();
-	if ((int)threadIdx.x < nitems)
-	{
-		const int k = threadIdx.x;
+	for (int k = threadIdx.x; k < nitems; k += ATRI_THREADS)
 		rc_alias_triangle (&f, s_ii[k], s_ti[k], f.aspancap > 0 ? 1 : 0, s_rows[k], s_span0[k], s_tri[k]);
-	}
 }
 
 /* one thread per queued span: D_PolysetDrawSpans8 */
@@ -2781,7 +2798,7 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 			rc_frame_t f2 = f;
 			f2.alias = g->d_alias + first;
 			dim3 ga ((g->maxverts + 127) / 128, cnt);
-			const unsigned gt = (unsigned)(((long long)cnt * (g->maxtris > 0 ? g->maxtris : 1) + ATRI_THREADS - 1) / ATRI_THREADS);
+			const unsigned gt = (unsigned)(((long long)cnt * (g->maxtris > 0 ? g->maxtris : 1) + ATRI_THREADS * ATRI_CAND - 1) / (ATRI_THREADS * ATRI_CAND));
 			f2.aspans = g->d_aspans; f2.aspancap = g->aspancap; f2.aspantris = g->d_aspantris; f2.aspantricap = g->aspantricap;
 			CK (cudaMemsetAsync (g->d_alloc + 5, 0, sizeof(unsigned long long), s));
 			k_alias_verts<<<ga, 128, 0, s>>> (f2);
