@@ -55,6 +55,7 @@ static struct {
 	uint8_t     *cmapscratch; int cmapscratchcap;
 	float        anorm_dots[16 * 256];
 	int          alias_dirty;		/* alias models loaded since the last device upload */
+	int          ent_parts;			/* entity-heavy device batches are drawn in this many parts (RC_ENT_PARTS, experiment) */
 	/* device residency of the alias models (the reference's Cache_Alloc lifetimes, r_model.c:95-130 / zone.c) */
 	size_t       modelcache_bytes;		/* budget, 0: every loaded model stays resident */
 	long long    model_clock;
@@ -175,6 +176,7 @@ int RC_Init (const rc_config_t *cfg)
 	}
 	{
 		long ncpu = sysconf (_SC_NPROCESSORS_ONLN);
+		{ const char *e = getenv ("RC_ENT_PARTS"); rc.ent_parts = e ? atoi (e) : 0; }
 		rc.host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)(ncpu > 8 ? 8 : (ncpu < 1 ? 1 : ncpu));
 		if (rc.host_threads > 64) rc.host_threads = 64;
 	}
@@ -780,9 +782,19 @@ int RC_WaitViews (int *status)
 int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_dev, void *stream, int *status)
 {
 	int r;
-	if (rc.inited && views && fb_dev && n >= 2 * RC_PART_MIN && rc_gpu_can_split (rc.gpu))
+	int entparts = 0;
+	if (rc.inited && views && fb_dev && n >= 8 && n < 2 * RC_PART_MIN && rc.ent_parts > 1)
 	{
-		const int part = ((n + 7) / 8 + 255) / 256 * 256 > RC_PART_MIN ? ((n + 7) / 8 + 255) / 256 * 256 : RC_PART_MIN;
+		/* a batch whose host set-up is entity work (R_AliasCheckBBox, R_LightPoint, the transform ... per entity;
+		 * BASELINE config C3: 8,192 entities and 262,144 particles per 32-view call) is drawn in parts as well */
+		long long nent = 0;
+		int i;
+		for (i = 0; i < n; i++) nent += views[i].num_entities + (views[i].num_particles >> 5);
+		if (nent >= 4096) entparts = rc.ent_parts;
+	}
+	if (rc.inited && views && fb_dev && (n >= 2 * RC_PART_MIN || entparts) && rc_gpu_can_split (rc.gpu))
+	{
+		const int part = entparts ? (n + entparts - 1) / entparts : (((n + 7) / 8 + 255) / 256 * 256 > RC_PART_MIN ? ((n + 7) / 8 + 255) / 256 * 256 : RC_PART_MIN);
 		/* a large batch (BASELINE config C4: 65,536 views per call) in parts: the set-up of part k+1 -- 5 ms of host
 		 * work and 47 MB of view records for the whole of C4 -- runs while the device draws part k */
 		const size_t px = (size_t)rc.vid.width * rc.vid.height;

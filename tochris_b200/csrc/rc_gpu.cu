@@ -1895,6 +1895,9 @@ __global__ void __launch_bounds__(ATRI_THREADS) k_alias_tris (const __grid_const
 }
 
 /* one thread per queued span: D_PolysetDrawSpans8 */
+#ifndef ALIAS_CHUNK
+#define ALIAS_CHUNK 4		/* pixels per unit of work of k_alias_spans (a multiple of rc_polyset_span's round of four) */
+#endif
 #ifndef ALIAS_SPANS_MINB
 #define ALIAS_SPANS_MINB 4	/* 64 registers: 3.26 -> 3.08 ms alias stage at C3 against 76 registers (three CTAs per SM); 5 CTAs (48 registers, spills): 3.37 */
 #endif
@@ -1933,7 +1936,7 @@ __global__ void __launch_bounds__(256, ALIAS_SPANS_MINB) k_alias_spans (const __
 			if ((int)s0.y > 0) s1 = __ldcs (&sp4[2 * i + 1]);
 		}
 		const int mycount = (int)s0.y > 0 ? (int)s0.y : 0;
-		const int mychunks = (mycount + 3) >> 2;
+		const int mychunks = (mycount + ALIAS_CHUNK - 1) / ALIAS_CHUNK;
 		int incl = mychunks;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -1959,7 +1962,7 @@ __global__ void __launch_bounds__(256, ALIAS_SPANS_MINB) k_alias_spans (const __
 				if (v > qq) hi = mid; else lo = mid + 1;
 			}
 			const int src = lo;
-			const int k0 = (qq - __shfl_sync (0xFFFFFFFFu, excl, src)) << 2;
+			const int k0 = (qq - __shfl_sync (0xFFFFFFFFu, excl, src)) * ALIAS_CHUNK;
 			rc_aspan_t sp;
 			sp.xy = (int)__shfl_sync (0xFFFFFFFFu, s0.x, src); sp.count = (int)__shfl_sync (0xFFFFFFFFu, s0.y, src);
 			sp.ptex = (int)__shfl_sync (0xFFFFFFFFu, s0.z, src); sp.stfrac = (int)__shfl_sync (0xFFFFFFFFu, s0.w, src);
@@ -1979,7 +1982,7 @@ __global__ void __launch_bounds__(256, ALIAS_SPANS_MINB) k_alias_spans (const __
 			const int S = (sp.stfrac & 0xFFFF) + k0 * sstep, T = (int)((unsigned)sp.stfrac >> 16) + k0 * tstep;
 			const int left = sp.count - k0;
 			sp.xy = (int)(((unsigned)sp.xy & 0xFFFF0000u) | (((unsigned)sp.xy + (unsigned)k0) & 0xFFFFu));
-			sp.count = left < 4 ? left : 4;
+			sp.count = left < ALIAS_CHUNK ? left : ALIAS_CHUNK;
 			sp.ptex += k0 * t.ststepxwhole + (S >> 16) + t.skinwidth * (T >> 16);
 			sp.stfrac = (S & 0xFFFF) | ((T & 0xFFFF) << 16);
 			sp.light = (int)((unsigned)sp.light + (unsigned)k0 * (unsigned)t.lstepx);
@@ -3203,8 +3206,11 @@ int rc_gpu_render_finish (rc_gpu_t *g, void *fb_dev, void *z_dev, int n, void *s
 			CK (cudaMemcpyAsync (g->mirror_z, z_dev, px * n * sizeof(int16_t), cudaMemcpyDefault, s));
 	}
 	int stw[2] = { 0, 0 };
+	unsigned long long qneed[2] = { 0ull, 0ull };
 	CK (cudaMemcpyAsync (stw, g->d_status, sizeof(stw), cudaMemcpyDeviceToHost, s));
+	CK (cudaMemcpyAsync (qneed, g->d_alloc + 6, sizeof(qneed), cudaMemcpyDeviceToHost, s));	/* what the parts asked of the alias span queue */
 	CK (cudaStreamSynchronize (s));
+	if (qneed[0] || qneed[1]) { g->aspan_need = (long long)qneed[0]; g->aspantri_need = (int)(qneed[1] < (1ull << 28) ? qneed[1] : (1ull << 28) - 1); }
 	g->stats.alias_range_events = stw[1];
 	if (status) *status = stw[0];
 	return RC_OK;
