@@ -799,17 +799,29 @@ int RC_RenderViewsDevice (const refdef_t *views, int n, void *fb_dev, void *z_de
 		 * work and 47 MB of view records for the whole of C4 -- runs while the device draws part k */
 		const size_t px = (size_t)rc.vid.width * rc.vid.height;
 		int first, st = 0;
+		double t_prep = 0, t_enq = 0, t_fin = 0;
+		struct timespec ta, tb;
 		r = rc_gpu_render_begin (rc.gpu, fb_dev, stream);
 		for (first = 0; r == RC_OK && first < n; first += part)
 		{
 			const int cnt = n - first < part ? n - first : part;
+			clock_gettime (CLOCK_MONOTONIC, &ta);
 			r = rc_prepare_views (views + first, cnt);
+			clock_gettime (CLOCK_MONOTONIC, &tb);
+			t_prep += (tb.tv_sec - ta.tv_sec) * 1e3 + (tb.tv_nsec - ta.tv_nsec) * 1e-6;
 			if (r == RC_OK)
 				r = rc_gpu_render_part (rc.gpu, &rc.batch, (uint8_t *)fb_dev + px * (size_t)first,
 							z_dev ? (void *)((int16_t *)z_dev + px * (size_t)first) : NULL, stream, first == 0, rc.err, sizeof(rc.err));
+			clock_gettime (CLOCK_MONOTONIC, &ta);
+			t_enq += (ta.tv_sec - tb.tv_sec) * 1e3 + (ta.tv_nsec - tb.tv_nsec) * 1e-6;
 		}
+		clock_gettime (CLOCK_MONOTONIC, &ta);
 		if (r == RC_OK)
 			r = rc_gpu_render_finish (rc.gpu, fb_dev, z_dev, n, stream, &st, rc.err, sizeof(rc.err));
+		clock_gettime (CLOCK_MONOTONIC, &tb);
+		t_fin = (tb.tv_sec - ta.tv_sec) * 1e3 + (tb.tv_nsec - ta.tv_nsec) * 1e-6;
+		if (getenv ("RC_TIMING"))
+			fprintf (stderr, "RC_RenderViewsDevice in parts of %d: host set-up %.2f ms, enqueue (with uploads) %.2f ms, wait at the end %.2f ms\n", part, t_prep, t_enq, t_fin);
 		if (r != RC_OK)
 		{
 			int dummy;

@@ -147,6 +147,9 @@ struct rc_gpu_s {
 	int agroups;	/* groups of a pipelined call (RC_ASYNC_GROUPS) */
 	int ahead, ainflight, amode;	/* amode: slot + 1 while an asynchronous call is being enqueued */
 	cudaStream_t copystream, sidestream; cudaEvent_t evgroup[8], evcopy, evfork, evjoin;
+	/* batches drawn in parts: the view records of a part go through one of two pinned staging buffers, so that their
+	 * upload is asynchronous and the host can set up the next part while the device draws this one */
+	rc_view_t *h_viewstage[2]; size_t viewstagecap[2]; cudaEvent_t ev_viewstage[2]; int viewstage_used[2], viewstage_idx;
 	rc_group_fn groupfn; void *groupuser; cudaStream_t groupstream; int ngroups;	/* RC_SetGroupCallback */
 	uint8_t *mirror_fb; int16_t *mirror_z;	/* RC_SetMirrorOutput */
 	int mirrorgroups;
@@ -204,9 +207,11 @@ struct rc_gpu_s {
 #ifndef FRONT_MANY_MINB
 #define FRONT_MANY_MINB 3	/* CTAs per SM of the 256-thread instance (many-view batches): 85 registers */
 #endif
-#define FRONT_EDGE_SLOTS 1024
-#define FRONT_FIXLIST 1024
-#define FRONT_SMEM (sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS + sizeof(uint32_t) * FRONT_EDGE_SLOTS)
+/* edge results a CTA holds per batch of faces, and its fix-up list: sized by the CTA (shared memory per CTA bounds how many
+ * views an SM has in flight in the many-view instance) */
+#define FRONT_EDGE_SLOTS_OF(ft) ((ft) >= 256 ? 1024 : 384)
+#define FRONT_FIXLIST_OF(ft) ((ft) >= 256 ? 1024 : 256)
+#define FRONT_SMEM_OF(ft) ((sizeof(rc_edgeres_t) + sizeof(uint32_t)) * FRONT_EDGE_SLOTS_OF (ft))
 
 /* L2 prefetch of a slice of a read-only array: the front end chases pointers through the BSP
  * (node -> plane -> child ...), and after a cold start (the bench flushes L2 between steps) every
@@ -227,7 +232,7 @@ __device__ __forceinline__ void front_prefetch (const void *p, size_t bytes)
  * two CTAs per SM -- when there are more views than SMs: the phases are latency bound, so two views per SM nearly
  * double the front end's throughput on many-view batches (160x120 x 4096: 1.03 -> 0.6 ms) */
 template <int FT>
-__global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
+__global__ void __launch_bounds__(FT, FT == FRONT_MANY ? FRONT_MANY_MINB : 1) k_front (const __grid_constant__ rc_world_t w, const __grid_constant__ rc_frame_t f)
 {
 	RC_GRID_DEP_WAIT ();
 	RC_TRACE_SCOPE (1);
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (
 		 * A face is a serial chain of 4-8 edges in the reference; giving every edge its own thread cuts the
 		 * phase's critical path by that factor.  Edge results live in shared memory. */
 		rc_edgeres_t *s_res = reinterpret_cast<rc_edgeres_t *>(front_smem);
+		constexpr int FRONT_EDGE_SLOTS = FRONT_EDGE_SLOTS_OF (FT);
 		uint32_t *s_owner = reinterpret_cast<uint32_t *>(front_smem + sizeof(rc_edgeres_t) * FRONT_EDGE_SLOTS);
 		__shared__ int s_wsum[(FT / 32)], s_included, s_total;
 		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
@@ -420,6 +426,7 @@ __global__ void __launch_bounds__(FT, FT == 256 ? FRONT_MANY_MINB : 1) k_front (
 		const int lane = tid & 31, wid = tid >> 5;
 		const rc_surf_t *surfs = f.surfs + (size_t)vi * f.surfcap;
 		const rc_facerec_t *list = f.facelist + (size_t)vi * f.facecap;
+		constexpr int FRONT_FIXLIST = FRONT_FIXLIST_OF (FT);
 		__shared__ int s_nfix, s_fix[FRONT_FIXLIST];
 		if (tid == 0) s_nfix = 0;
 		__syncthreads ();
@@ -2219,6 +2226,8 @@ rc_gpu_t *rc_gpu_create (int device, int width, int height, size_t cache_bytes, 
 	cudaStreamCreateWithFlags (&g->sidestream, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags (&g->evfork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&g->evjoin, cudaEventDisableTiming);
+	for (int i = 0; i < 2; i++) { g->h_viewstage[i] = NULL; g->viewstagecap[i] = 0; g->viewstage_used[i] = 0; cudaEventCreateWithFlags (&g->ev_viewstage[i], cudaEventDisableTiming); }
+	g->viewstage_idx = 0;
 	g->mirrorgroups = 0; g->mirror_deferred = 0;
 	for (int i = 0; i < 4; i++) { g->mpend[i].fb = NULL; g->mpend[i].valid = 0; cudaEventCreateWithFlags (&g->mpend[i].ev, cudaEventDisableTiming); }
 	cudaEventCreateWithFlags (&g->evrender, cudaEventDisableTiming);
@@ -2307,6 +2316,7 @@ void rc_gpu_destroy (rc_gpu_t *g)
 	for (int i = 0; i < 16; i++) cudaEventDestroy (g->ev[i]);
 	for (int i = 0; i < 8; i++) cudaEventDestroy (g->evgroup[i]);
 	cudaEventDestroy (g->evcopy); cudaEventDestroy (g->evfork); cudaEventDestroy (g->evjoin);
+	for (int i = 0; i < 2; i++) { cudaEventDestroy (g->ev_viewstage[i]); if (g->h_viewstage[i]) cudaFreeHost (g->h_viewstage[i]); }
 	for (int i = 0; i < 4; i++) cudaEventDestroy (g->mpend[i].ev);
 	cudaEventDestroy (g->evrender);
 	cudaStreamDestroy (g->copystream); cudaStreamDestroy (g->sidestream);
@@ -2591,7 +2601,27 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 	} capture = { s, false };
 	int gslot = 0;
 	if (timed) cudaEventRecord (g->ev[0], s);
-	CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
+	if (g->rflags & RC_RF_DEFER)
+	{
+		/* a copy from pageable memory holds the calling thread until the stream has reached it, i.e. until the previous
+		 * part is drawn (C4, eight parts: 22.7 of the call's 29.7 ms were spent inside these calls) */
+		const int b = (g->viewstage_idx ^= 1);
+		const size_t bytes = sizeof(rc_view_t) * (size_t)n;
+		if (g->viewstage_used[b]) CK (cudaEventSynchronize (g->ev_viewstage[b]));
+		if (g->viewstagecap[b] < bytes)
+		{
+			if (g->h_viewstage[b]) cudaFreeHost (g->h_viewstage[b]);
+			g->h_viewstage[b] = NULL; g->viewstagecap[b] = 0;
+			CK (cudaHostAlloc ((void **)&g->h_viewstage[b], bytes, cudaHostAllocDefault));
+			g->viewstagecap[b] = bytes;
+		}
+		memcpy (g->h_viewstage[b], hviews, bytes);
+		CK (cudaMemcpyAsync (g->d_views, g->h_viewstage[b], bytes, cudaMemcpyHostToDevice, s));
+		CK (cudaEventRecord (g->ev_viewstage[b], s));
+		g->viewstage_used[b] = 1;
+	}
+	else
+		CK (cudaMemcpyAsync (g->d_views, hviews, sizeof(rc_view_t) * n, cudaMemcpyHostToDevice, s));
 	if (capturable)
 	{
 		gslot = 0;
@@ -2622,7 +2652,11 @@ static int run_chunk (rc_gpu_t *g, const rc_view_t *hviews, int first_view, int 
 		bool manyviews = n > g->numsms && !g->front_512;	/* more views than SMs: several waves */
 		if (g->front_csize > 0) csize = g->front_csize;		/* experiments: RC_FRONT_CSIZE / RC_FRONT_256 */
 		if (g->front_256) manyviews = true;
-		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? FRONT_MANY : FRONT_THREADS); cfg.dynamicSmemBytes = FRONT_SMEM > 2 * (size_t)w.numnodes + 16 ? FRONT_SMEM : 2 * (size_t)w.numnodes + 16; cfg.stream = s;
+		cfg.gridDim = dim3 (n * csize); cfg.blockDim = dim3 (manyviews ? FRONT_MANY : FRONT_THREADS); cfg.stream = s;
+		{
+			const size_t fs = manyviews ? FRONT_SMEM_OF (FRONT_MANY) : FRONT_SMEM_OF (FRONT_THREADS);
+			cfg.dynamicSmemBytes = fs > 2 * (size_t)w.numnodes + 16 ? fs : 2 * (size_t)w.numnodes + 16;
+		}
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
