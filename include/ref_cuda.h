@@ -292,6 +292,20 @@ rc_fxlight_t *RC_FxAllocDlight (rc_fx_t *fx, int key, double time);
 rc_fxlight_t *RC_FxLights (rc_fx_t *fx);                /* the MAX_DLIGHTS lights */
 int   RC_FxAddDlights (rc_fx_t *fx, rc_scene_t *scene, double time, double oldtime);
 int   RC_ClientAddEntities (rc_fx_t *fx, rc_scene_t *scene, rc_cent_t *cents, int n, const rc_clframe_t *frame);
+/* The other two producers V_RenderView calls (cl_view.c:903-914).  Colour shifts (cl_view.c:321-550): four per client --
+ * medium, damage, bonus, power-up -- sent to the scene only in frames in which one of them changed since the last call,
+ * damage and bonus fading by the frame time.  Beams (cl_tent.c:60-105, 303-356): up to 24 bolts, each drawn as a chain of
+ * model segments every 30 units, at most 128 segments a frame. */
+void  RC_FxSetContentsColor (rc_fx_t *fx, int contents);             /* V_SetContentsColor (RC_PointContents' value) */
+void  RC_FxSetEmptyColor (rc_fx_t *fx, int r, int g, int b, int percent);   /* the v_cshift command */
+void  RC_FxDamage (rc_fx_t *fx, int armor, int blood);               /* the colour half of CL_ParseDamage */
+void  RC_FxBonusFlash (rc_fx_t *fx);                                 /* V_BonusFlash_f */
+void  RC_FxClearCshifts (rc_fx_t *fx);                               /* CL_ClearCshifts */
+int   RC_FxAddCshifts (rc_fx_t *fx, rc_scene_t *scene, int items, double host_frametime);   /* CL_AddCshifts + V_CalcPowerupCshift */
+const cshift_t *RC_FxCshifts (const rc_fx_t *fx);                    /* the four shifts (test / HUD access) */
+int   RC_FxBeam (rc_fx_t *fx, int entity, struct model_s *model, const float *start, const float *end, double time);   /* CL_ParseBeam */
+int   RC_ClientAddTempEntities (rc_fx_t *fx, rc_scene_t *scene, double time, int viewentity, const float *view_lerp_origin,
+                                byte *colormap, struct model_s *const *bolts /* cl_bolt1..3_mod or NULL */);
 
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)

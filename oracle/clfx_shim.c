@@ -1,5 +1,5 @@
 /* TEST INFRASTRUCTURE ONLY.
- * Platform shim around the UNMODIFIED client/cl_effects.c + client/cl_main.c + common/mathlib.c of the reference, compiled
+ * Platform shim around the UNMODIFIED client/cl_effects.c + cl_main.c + cl_tent.c + cl_view.c + common/mathlib.c of the reference, compiled
  * from where they lie into oracle/_ref/libclfx.so (oracle/Makefile, target `clfx`): the particle system, the dynamic
  * lights and CL_AddEntities, i.e. what tochris_b200/csrc/rc_client.c restates.  Nothing of the product links or loads
  * this; tests/test_client_fx.py drives both sides with the same calls and the same srand () seed.
@@ -7,9 +7,10 @@
 #include "client.h"
 
 /* ---- data the two client files expect from the rest of the engine ---- */
-cvar_t      chase_active = { "chase_active", "0" };
-beam_t      cl_beams[MAX_BEAMS];
-entity_t    cl_temp_entities[MAX_TEMP_ENTITIES];
+extern cvar_t chase_active;	/* (cl_view.c) */
+cvar_t      cl_forwardspeed = { "cl_forwardspeed", "200" }, scr_fov = { "fov", "90" };
+qboolean    con_forcedup;
+vrect_t     scr_vrect;
 double      host_frametime, realtime;
 float       scr_centertime_off;
 viddef_t    vid;
@@ -29,6 +30,14 @@ void Cmd_AddCommand (char *name, xcommand_t fn) { (void)name; (void)fn; }
 void Con_Printf (char *fmt, ...) { (void)fmt; }
 void Con_DPrintf (char *fmt, ...) { (void)fmt; }
 int  Mod_Flags (struct model_s *m) { return *(int *)m; }		/* the tests' "models" are ints holding the flags */
+void Sys_Error (char *error, ...) { fprintf (stderr, "libclfx: Sys_Error: %s\n", error); abort (); }
+/* the server message the parsers read (CL_ParseDamage, CL_ParseBeam): numbers queued by the test */
+static float clfx_msg[64]; static int clfx_msgn, clfx_msgpos;
+void  clfx_msg_set (const float *v, int n) { memcpy (clfx_msg, v, sizeof(float) * (n < 64 ? n : 64)); clfx_msgn = n; clfx_msgpos = 0; }
+static float clfx_msg_next (void) { return clfx_msgpos < clfx_msgn ? clfx_msg[clfx_msgpos++] : 0; }
+int   MSG_ReadByte (void) { return (int)clfx_msg_next (); }
+int   MSG_ReadShort (void) { return (int)clfx_msg_next (); }
+float MSG_ReadCoord (void) { return clfx_msg_next (); }
 void clfx_unexpected (const char *name) { fprintf (stderr, "libclfx: %s called (not part of the path under test)\n", name); abort (); }
 
 /* ---- recorders in place of client/cl_view.c's lists ---- */
@@ -48,7 +57,22 @@ void V_AddEntity (entity_t *ent)
 {
 	if (rec_nentities < REC_MAX) rec_entities[rec_nentities++] = *ent;
 }
-void clfx_rec_clear (void) { rec_nparticles = rec_ndlights = rec_nentities = 0; }
+extern int r_numcshifts; extern cshift_t r_cshifts[];	/* cl_view.c's own list (its V_AddCshift is left in place) */
+void clfx_rec_clear (void) { rec_nparticles = rec_ndlights = rec_nentities = 0; r_numcshifts = 0; }
+int  clfx_rec_cshifts (cshift_t *out, int max)
+{
+	int i;
+	for (i = 0; i < r_numcshifts && i < max; i++) out[i] = r_cshifts[i];
+	return r_numcshifts;
+}
+void clfx_cshifts (cshift_t *out) { memcpy (out, cl.cshifts, sizeof(cshift_t) * NUM_CSHIFTS); }
+extern struct model_s *cl_bolt1_mod, *cl_bolt2_mod, *cl_bolt3_mod;
+void clfx_set_bolts (struct model_s *a, struct model_s *b, struct model_s *c) { cl_bolt1_mod = a; cl_bolt2_mod = b; cl_bolt3_mod = c; }
+void clfx_set_frame (double time, double oldtime, double frametime, int items, int viewentity, const float *view_lerp_origin)
+{
+	cl.time = time; cl.oldtime = oldtime; host_frametime = frametime; cl.items = items; cl.viewentity = viewentity;
+	if (view_lerp_origin) VectorCopy (view_lerp_origin, cl_entities[viewentity].lerp_origin);
+}
 int  clfx_rec_particles (float *org3, int *color, int max)
 {
 	int i;
@@ -84,6 +108,7 @@ void clfx_init (unsigned seed, int numparticles)
 	memset (&cl, 0, sizeof(cl));
 	memset (&cls, 0, sizeof(cls));
 	memset (cl_dlights, 0, sizeof(cl_dlights));
+	memset (cl_beams, 0, sizeof(cl_beams));
 	memset (particles, 0, sizeof(particles));
 	memset (avelocities, 0, 162 * sizeof(vec3_t));
 	CL_InitParticles ();

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from tochris_b200 import api, client
-from tochris_b200.refdef import entity_t, refdef_t, vec3
+from tochris_b200.refdef import cshift_t, entity_t, refdef_t, vec3
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLFX = os.path.join(ROOT, "oracle", "_ref", "libclfx.so")
@@ -56,6 +56,13 @@ def ref(tmp_path):
         getattr(L, name).argtypes = [fp, fp]
     L.CL_TracerTrail.argtypes = [fp, fp, C.c_int]
     L.CL_EntityParticles.argtypes = [C.POINTER(entity_t)]
+    L.clfx_msg_set.argtypes = [fp, C.c_int]
+    L.clfx_rec_cshifts.argtypes = [C.POINTER(cshift_t), C.c_int]
+    L.clfx_cshifts.argtypes = [C.POINTER(cshift_t)]
+    L.clfx_set_bolts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.clfx_set_frame.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, fp]
+    L.V_SetContentsColor.argtypes = [C.c_int]
+    L.CL_ParseBeam.argtypes = [C.c_void_p]
     return L
 
 
@@ -342,3 +349,152 @@ def test_fx_argument_errors(sim_lib):
     assert L.RC_FxEffect(fx, 99, a, None, 0, 0, 1.0) == -1
     assert L.RC_FxAddParticles(fx, None, 7.0, 6.9) == 0 and L.RC_FxParticleCount(fx) == 0   # all dead at t = 7
     L.RC_FxFree(fx)
+
+
+def test_colour_shifts_match_the_reference(ref, sim_lib):
+    """V_SetContentsColor, CL_ParseDamage's colour half, V_BonusFlash_f, V_CalcPowerupCshift and CL_AddCshifts
+    (cl_view.c:321-550): the shifts reach the scene only in frames in which one changed; damage and bonus fade by the
+    frame time (an int minus a double, truncated)"""
+    rnd = random.Random(5)
+    F = client
+    script = []
+    for k in range(120):
+        ev = []
+        if rnd.random() < 0.25: ev.append(("contents", rnd.choice([-1, -2, -3, -4, -5, -6])))
+        if rnd.random() < 0.2: ev.append(("damage", rnd.choice([0, 0, 5, 40, 100]), rnd.choice([0, 3, 20, 90])))
+        if rnd.random() < 0.15: ev.append(("bonus",))
+        if k == 70: ev.append(("clear",))
+        items = rnd.choice([0, 0, 0, F.IT_QUAD, F.IT_SUIT, F.IT_INVISIBILITY, F.IT_INVULNERABILITY, F.IT_QUAD | F.IT_SUIT]) if k % 7 == 0 else None
+        script.append((ev, items, rnd.choice([0.0, 0.001, 0.013, 0.02, 0.05, 0.1])))
+
+    def run_ref():
+        L = ref
+        L.clfx_init(1, 0)
+        out, items = [], 0
+        for ev, it, dt in script:
+            if it is not None: items = it
+            L.clfx_set_frame(1.0, 1.0, dt, items, 1, None)
+            for e in ev:
+                if e[0] == "contents": L.V_SetContentsColor(e[1])
+                elif e[0] == "damage":
+                    L.clfx_msg_set((C.c_float * 5)(e[1], e[2], 10.0, 20.0, 30.0), 5)
+                    L.CL_ParseDamage()
+                elif e[0] == "bonus": L.V_BonusFlash_f()
+                else: L.CL_ClearCshifts()
+            L.clfx_rec_clear()
+            L.CL_AddCshifts()
+            sent = (cshift_t * 16)()
+            n = L.clfx_rec_cshifts(sent, 16)
+            state = (cshift_t * 4)()
+            L.clfx_cshifts(state)
+            out.append((n, bytes(sent)[: n * 16], bytes(state)))
+        return out
+
+    def run_ours(lib):
+        L = client.bind(C.CDLL(lib))
+        L.RC_SceneNew.restype = C.c_void_p
+        for nm in ("RC_SceneFree", "RC_SceneClear", "RC_SceneReset"): getattr(L, nm).argtypes = [C.c_void_p]
+        L.RC_SceneEndFrame.argtypes = [C.c_void_p, C.POINTER(refdef_t), ip]
+        L.RC_SceneFrames.argtypes = [C.c_void_p, ip]
+        L.RC_SceneFrames.restype = C.POINTER(refdef_t)
+        fx, sc = L.RC_FxNew(0), L.RC_SceneNew()
+        out, items = [], 0
+        for ev, it, dt in script:
+            if it is not None: items = it
+            for e in ev:
+                if e[0] == "contents": L.RC_FxSetContentsColor(fx, e[1])
+                elif e[0] == "damage": L.RC_FxDamage(fx, e[1], e[2])
+                elif e[0] == "bonus": L.RC_FxBonusFlash(fx)
+                else: L.RC_FxClearCshifts(fx)
+            L.RC_SceneReset(sc)
+            n = L.RC_FxAddCshifts(fx, sc, items, dt)
+            rd = refdef_t()
+            k = L.RC_SceneEndFrame(sc, C.byref(rd), None)
+            cnt = C.c_int()
+            fr = L.RC_SceneFrames(sc, C.byref(cnt))[k]
+            assert fr.num_cshifts == n
+            sent = b"".join(bytes(fr.cshifts[i]) for i in range(n))
+            state = bytes((cshift_t * 4).from_address(C.addressof(L.RC_FxCshifts(fx).contents)))
+            out.append((n, sent, state))
+        L.RC_FxFree(fx); L.RC_SceneFree(sc)
+        return out
+
+    want = run_ref()
+    assert 10 < sum(1 for w in want if w[0] == 0) < 110 and any(w[0] == 4 for w in want)      # frames with and without a change
+    for name, lib in _libs(sim_lib):
+        got = run_ours(lib)
+        for k, (a, b) in enumerate(zip(want, got)):
+            assert a == b, f"{name} frame {k}: {a[0]} / {b[0]} shifts sent"
+
+
+def test_beams_match_the_reference(ref, sim_lib):
+    """CL_ParseBeam + CL_AddTempEntities (cl_tent.c:60-105, 303-356): replaced / new / expired beams, the viewer's own beam
+    starting at the viewer's drawn position, full-bright bolt models, the 128-entity limit, straight-up beams
+    (Vector2Angles' special case) and the reference's shared loop counter"""
+    rnd = random.Random(9)
+    models = (C.c_int * 4)(0, 0, 0, 0)
+    mp = [C.addressof(models) + 4 * i for i in range(4)]
+    frames = []
+    t = 1.0
+    for k in range(40):
+        # (at most four beams alive, in slots 0-3: with a drawn beam in a higher slot the reference's shared loop counter
+        # walks it past the end of cl_beams[] -- undefined there, not reproduced)
+        t += 1.0 if k in (25, 26) else rnd.choice([0.02, 0.05, 0.15, 0.3])
+        beams = []
+        for _ in range(rnd.choice([0, 1, 1, 2, 3])):
+            a = [rnd.uniform(-300, 300) for _ in range(3)]
+            b = [a[0], a[1], a[2] + rnd.choice([-200.0, 150.0])] if rnd.random() < 0.15 else [a[j] + rnd.uniform(-400, 400) for j in range(3)]
+            beams.append((rnd.choice([1, 1, 2, 5, 9]), rnd.randrange(4), a, b))
+        if k == 25:
+            beams = [(100 + j, 0, [0.0, 0.0, 0.0], [3000.0, 100.0 * j, 50.0]) for j in range(3)]     # 100 segments each: the limit
+        frames.append((t, beams, [rnd.uniform(-50, 50) for _ in range(3)]))
+
+    def run_ref():
+        L = ref
+        L.clfx_init(77, 0)
+        L.clfx_set_bolts(mp[0], mp[1], mp[2])
+        out = []
+        for t, beams, vorg in frames:
+            L.clfx_set_frame(t, t, 0.0, 0, 1, V(*vorg))
+            for ent, mi, a, b in beams:
+                L.clfx_msg_set((C.c_float * 7)(ent, *a, *b), 7)
+                L.CL_ParseBeam(mp[mi])
+            L.clfx_rec_clear()
+            L.CL_AddTempEntities()
+            ents = (entity_t * 256)()
+            n = L.clfx_rec_entities(ents, 256)
+            out.append((n, bytes(ents)[: n * C.sizeof(entity_t)]))
+        return out, L.clfx_vid_colormap()
+
+    def run_ours(lib, cmap):
+        L = client.bind(C.CDLL(lib))
+        L.RC_SceneNew.restype = C.c_void_p
+        for nm in ("RC_SceneFree", "RC_SceneClear", "RC_SceneReset"): getattr(L, nm).argtypes = [C.c_void_p]
+        L.RC_SceneEndFrame.argtypes = [C.c_void_p, C.POINTER(refdef_t), ip]
+        L.RC_SceneFrames.argtypes = [C.c_void_p, ip]
+        L.RC_SceneFrames.restype = C.POINTER(refdef_t)
+        libc.srand(77)
+        fx, sc = L.RC_FxNew(0), L.RC_SceneNew()
+        bolts = (C.c_void_p * 3)(mp[0], mp[1], mp[2])
+        out = []
+        for t, beams, vorg in frames:
+            for ent, mi, a, b in beams:
+                assert L.RC_FxBeam(fx, ent, mp[mi], V(*a), V(*b), t) in (0, 1)
+            L.RC_SceneReset(sc)
+            n = L.RC_ClientAddTempEntities(fx, sc, t, 1, V(*vorg), cmap, bolts)
+            rd = refdef_t()
+            k = L.RC_SceneEndFrame(sc, C.byref(rd), None)
+            cnt = C.c_int()
+            fr = L.RC_SceneFrames(sc, C.byref(cnt))[k]
+            assert fr.num_entities == n
+            out.append((n, b"".join(bytes(fr.entities[i]) for i in range(n))))
+        L.RC_FxFree(fx); L.RC_SceneFree(sc)
+        return out
+
+    want, cmap = run_ref()
+    assert max(w[0] for w in want) == 128 and sum(w[0] for w in want) > 600
+    for name, lib in _libs(sim_lib):
+        got = run_ours(lib, cmap)
+        for k, (a, b) in enumerate(zip(want, got)):
+            assert a[0] == b[0], f"{name} frame {k}: {a[0]} / {b[0]} beam segments"
+            assert a[1] == b[1], f"{name} frame {k}: segment entities differ"

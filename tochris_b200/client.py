@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-from .refdef import vec3
+from .refdef import cshift_t, vec3
 
 (FX_ENTITY_PARTICLES, FX_POINT, FX_EXPLOSION, FX_EXPLOSION2, FX_BLOB_EXPLOSION, FX_RUN_EFFECT, FX_ROCKET_SPLASH,
  FX_LAVA_SPLASH, FX_TELEPORT_SPLASH, FX_RAIL_TRAIL, FX_ROCKET_TRAIL, FX_GRENADE_TRAIL, FX_BLOOD_TRAIL,
@@ -13,6 +13,7 @@ from .refdef import vec3
 EF_BRIGHTFIELD, EF_MUZZLEFLASH, EF_BRIGHTLIGHT, EF_DIMLIGHT = 1, 2, 4, 8                  # common/quakedef.h:210-213
 MF_ROCKET, MF_GRENADE, MF_GIB, MF_ROTATE, MF_TRACER, MF_ZOMGIB, MF_TRACER2, MF_TRACER3 = 1, 2, 4, 8, 16, 32, 64, 128
 MAX_DLIGHTS = 32
+IT_INVISIBILITY, IT_INVULNERABILITY, IT_SUIT, IT_QUAD = 524288, 1048576, 2097152, 4194304     # common/quakedef.h:154-157
 
 
 class rc_fxlight_t(C.Structure):      # cdlight_t, client/client.h:91-98
@@ -50,4 +51,19 @@ def bind(L):
     L.RC_FxLights.restype = C.POINTER(rc_fxlight_t)
     L.RC_FxAddDlights.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
     L.RC_ClientAddEntities.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(rc_cent_t), C.c_int, C.POINTER(rc_clframe_t)]
+    L.RC_FxSetContentsColor.argtypes = [C.c_void_p, C.c_int]
+    L.RC_FxSetContentsColor.restype = None
+    L.RC_FxSetEmptyColor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.RC_FxSetEmptyColor.restype = None
+    L.RC_FxDamage.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.RC_FxDamage.restype = None
+    L.RC_FxBonusFlash.argtypes = [C.c_void_p]
+    L.RC_FxBonusFlash.restype = None
+    L.RC_FxClearCshifts.argtypes = [C.c_void_p]
+    L.RC_FxClearCshifts.restype = None
+    L.RC_FxAddCshifts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    L.RC_FxCshifts.argtypes = [C.c_void_p]
+    L.RC_FxCshifts.restype = C.POINTER(cshift_t)
+    L.RC_FxBeam.argtypes = [C.c_void_p, C.c_int, C.c_void_p, fp, fp, C.c_double]
+    L.RC_ClientAddTempEntities.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, fp, C.c_void_p, C.POINTER(C.c_void_p)]
     return L

@@ -32,6 +32,8 @@ void RC_AngleVectors (const float *angles, float *forward, float *right, float *
 #define FX_MIN_PARTICLES 512	/* ABSOLUTE_MIN_PARTICLES, cl_effects.c:23 */
 #define FX_MAX_PARTICLES 2048	/* MAX_PARTICLES, client/ref.h:33 */
 #define FX_NORMALS 162
+#define FX_MAX_BEAMS 24		/* MAX_BEAMS, client.h:101 */
+#define FX_MAX_TEMP_ENTITIES 128	/* client.h:286 */
 
 enum { PK_STATIC, PK_GRAV, PK_SLOWGRAV, PK_FIRE, PK_EXPLODE, PK_EXPLODE2, PK_BLOB, PK_BLOB2, PK_RAILTRAIL };	/* ptype_t */
 
@@ -54,6 +56,9 @@ struct rc_fx_s {
 	float  avel[FX_NORMALS][3]; 	/* avelocities, cl_effects.c:92 */
 	float  normals[FX_NORMALS][3]; int have_normals;
 	int    tracercount;
+	cshift_t cshifts[4], prev_cshifts[4];	/* cl.cshifts / cl.prev_cshifts: contents, damage, bonus, powerup (client.h:48-56) */
+	cshift_t cshift_empty;			/* the `v_cshift` command's colour for air (cl_view.c:321, 401-407) */
+	struct { int entity; struct model_s *model; float endtime; float start[3], end[3]; } beams[FX_MAX_BEAMS];	/* cl_beams, cl_tent.c:26 */
 };
 
 static int fx_load_normals (rc_fx_t *x)
@@ -125,6 +130,9 @@ void RC_FxClear (rc_fx_t *x)
 	x->nfree = x->cap;
 	x->n = 0;
 	memset (x->lights, 0, sizeof(x->lights));
+	memset (x->beams, 0, sizeof(x->beams));			/* CL_ClearState, cl_main.c:81-82 */
+	memset (x->cshifts, 0, sizeof(x->cshifts)); memset (x->prev_cshifts, 0, sizeof(x->prev_cshifts));
+	x->cshift_empty.destcolor[0] = 130; x->cshift_empty.destcolor[1] = 80; x->cshift_empty.destcolor[2] = 50; x->cshift_empty.percent = 0;
 }
 
 int RC_FxParticleCount (const rc_fx_t *x) { return x->n; }
@@ -726,6 +734,181 @@ int RC_ClientAddEntities (rc_fx_t *x, rc_scene_t *scene, rc_cent_t *cents, int n
 		if (scene)
 			RC_SceneAddEntity (scene, &ent);
 		added++;
+	}
+	return added;
+}
+
+/* ---- colour shifts: what CL_AddCshifts hands to the scene (cl_view.c:321-550) ------------------------------------------
+ * Four shifts per client -- the medium the eye is in, damage, item pick-up, power-up -- are blended into the palette by
+ * R_UpdatePalette (a20).  The reference sends them to the scene only in frames in which one of them CHANGED since the
+ * last call (the palette of the previous frame stays otherwise), and lets damage and bonus fade by the frame time. */
+enum { CS_CONTENTS, CS_DAMAGE, CS_BONUS, CS_POWERUP, CS_COUNT };
+
+void RC_FxSetContentsColor (rc_fx_t *x, int contents)	/* V_SetContentsColor, cl_view.c:432-455 */
+{
+	static const cshift_t lava = { { 255, 80, 0 }, 150 }, slime = { { 0, 25, 5 }, 150 }, water = { { 130, 80, 50 }, 128 };
+	switch (contents)
+	{
+	case -1: case -2: x->cshifts[CS_CONTENTS] = x->cshift_empty; break;	/* CONTENTS_EMPTY, CONTENTS_SOLID */
+	case -5: x->cshifts[CS_CONTENTS] = lava; break;
+	case -4: x->cshifts[CS_CONTENTS] = slime; break;
+	default: x->cshifts[CS_CONTENTS] = water; break;
+	}
+}
+
+void RC_FxSetEmptyColor (rc_fx_t *x, int r, int g, int b, int percent)	/* the `v_cshift` command, cl_view.c:401-407 */
+{
+	x->cshift_empty.destcolor[0] = r; x->cshift_empty.destcolor[1] = g; x->cshift_empty.destcolor[2] = b; x->cshift_empty.percent = percent;
+}
+
+void RC_FxDamage (rc_fx_t *x, int armor, int blood)	/* the colour half of CL_ParseDamage, cl_view.c:331-376 */
+{
+	float count = (blood + armor) * 0.5;
+	cshift_t *cs = &x->cshifts[CS_DAMAGE];
+	if (count < 10)
+		count = 10;
+	if (armor > blood) { cs->destcolor[0] = 200; cs->destcolor[1] = 100; cs->destcolor[2] = 100; }
+	else if (armor) { cs->destcolor[0] = 220; cs->destcolor[1] = 50; cs->destcolor[2] = 50; }
+	else { cs->destcolor[0] = 255; cs->destcolor[1] = 0; cs->destcolor[2] = 0; }
+	cs->percent += 3*count;
+	if (cs->percent < 0) cs->percent = 0;
+	if (cs->percent > 150) cs->percent = 150;
+}
+
+void RC_FxBonusFlash (rc_fx_t *x)	/* V_BonusFlash_f, cl_view.c:417-423 */
+{
+	cshift_t *cs = &x->cshifts[CS_BONUS];
+	cs->destcolor[0] = 215; cs->destcolor[1] = 186; cs->destcolor[2] = 69; cs->percent = 50;
+}
+
+void RC_FxClearCshifts (rc_fx_t *x)	/* CL_ClearCshifts, cl_view.c:500-506 */
+{
+	for (int i = 0; i < CS_COUNT; i++)
+		x->cshifts[i].percent = 0;
+}
+
+/* CL_AddCshifts, cl_view.c:513-550 (with V_CalcPowerupCshift, :460-498: `items` = cl.items).  Returns the number of shifts
+ * handed to the scene: 0 in a frame in which nothing changed. */
+int RC_FxAddCshifts (rc_fx_t *x, rc_scene_t *scene, int items, double host_frametime)
+{
+	static const struct { int bit; cshift_t cs; } powerups[4] = {		/* IT_QUAD, IT_SUIT, IT_INVISIBILITY, IT_INVULNERABILITY (quakedef.h:154-157) */
+		{ 4194304, { { 0, 0, 255 }, 30 } }, { 2097152, { { 0, 255, 0 }, 20 } }, { 524288, { { 100, 100, 100 }, 100 } }, { 1048576, { { 255, 255, 100 }, 30 } } };
+	int changed = 0, n = 0, k;
+	for (k = 0; k < 4; k++)
+		if (items & powerups[k].bit)
+		{
+			x->cshifts[CS_POWERUP] = powerups[k].cs;
+			break;
+		}
+	if (k == 4)
+		x->cshifts[CS_POWERUP].percent = 0;		/* (the colour stays) */
+	for (int i = 0; i < CS_COUNT; i++)
+	{
+		if (x->cshifts[i].percent != x->prev_cshifts[i].percent) changed = 1;
+		for (int j = 0; j < 3; j++)
+			if (x->cshifts[i].destcolor[j] != x->prev_cshifts[i].destcolor[j]) changed = 1;
+		x->prev_cshifts[i] = x->cshifts[i];
+	}
+	x->cshifts[CS_DAMAGE].percent -= host_frametime*150;
+	if (x->cshifts[CS_DAMAGE].percent <= 0)
+		x->cshifts[CS_DAMAGE].percent = 0;
+	x->cshifts[CS_BONUS].percent -= host_frametime*100;
+	if (x->cshifts[CS_BONUS].percent <= 0)
+		x->cshifts[CS_BONUS].percent = 0;
+	if (!changed)
+		return 0;
+	for (int i = 0; i < CS_COUNT; i++)
+		if (x->cshifts[i].percent >= 0)
+		{
+			if (scene)
+				RC_SceneAddCshift (scene, x->cshifts[i].destcolor[0], x->cshifts[i].destcolor[1], x->cshifts[i].destcolor[2], x->cshifts[i].percent);
+			n++;
+		}
+	return n;
+}
+
+const cshift_t *RC_FxCshifts (const rc_fx_t *x) { return x->cshifts; }
+
+/* ---- beams: the lightning bolts of cl_tent.c, a chain of model segments every 30 units -------------------------------- */
+/* CL_ParseBeam, cl_tent.c:60-105: the beam of this entity is replaced, else the first free one is taken; 0: "beam list
+ * overflow" */
+int RC_FxBeam (rc_fx_t *x, int entity, struct model_s *model, const float *start, const float *end, double time)
+{
+	int i;
+	for (i = 0; i < FX_MAX_BEAMS; i++)
+		if (x->beams[i].entity == entity)
+			break;
+	if (i == FX_MAX_BEAMS)
+	{
+		for (i = 0; i < FX_MAX_BEAMS; i++)
+			if (!x->beams[i].model || x->beams[i].endtime < time)
+				break;
+		if (i == FX_MAX_BEAMS)
+			return 0;
+		x->beams[i].entity = entity;
+	}
+	x->beams[i].model = model;
+	x->beams[i].endtime = time + 0.2;
+	memcpy (x->beams[i].start, start, sizeof(x->beams[i].start));
+	memcpy (x->beams[i].end, end, sizeof(x->beams[i].end));
+	return 1;
+}
+
+/* CL_AddTempEntities, cl_tent.c:303-356: every live beam becomes a chain of entities from its start (the viewer's
+ * drawn position for the viewer's own beam) towards its end, rolled at random, full bright for the three bolt models; at
+ * most 128 a frame.  The reference's segment loop reuses the beam loop's counter (it leaves it at 3), so a drawn beam in
+ * slot k makes the loop look at slots k+1 .. k+20 only -- reproduced, short of reading past the array as the reference
+ * does for k > 3.  Returns the entities added. */
+int RC_ClientAddTempEntities (rc_fx_t *x, rc_scene_t *scene, double time, int viewentity, const float *view_lerp_origin,
+			      byte *colormap, struct model_s *const *bolts)
+{
+	int i, b, added = 0;
+	for (i = 0, b = 0; i < FX_MAX_BEAMS && b < FX_MAX_BEAMS; i++, b++)
+	{
+		float dist[3], org[3], ang[3], d;
+		if (!x->beams[b].model || x->beams[b].endtime < time)
+			continue;
+		if (x->beams[b].entity == viewentity && view_lerp_origin)
+			memcpy (x->beams[b].start, view_lerp_origin, sizeof(org));
+		for (int j = 0; j < 3; j++)
+			dist[j] = x->beams[b].end[j] - x->beams[b].start[j];
+		/* Vector2Angles, mathlib.c:505 */
+		if (!dist[0] && !dist[1])
+		{
+			ang[1] = 0;
+			ang[0] = (dist[2] > 0) ? 90 : 270;
+		}
+		else
+		{
+			float y = atan2 (dist[1], dist[0]) * 180 / M_PI;
+			if (y < 0) y += 360;
+			float p = atan2 (dist[2], sqrt (dist[0]*dist[0]+dist[1]*dist[1])) * 180 / M_PI;
+			if (p < 0) p += 360;
+			ang[0] = p; ang[1] = y;
+		}
+		memcpy (org, x->beams[b].start, sizeof(org));
+		d = fx_normalize (dist);
+		while (d > 0)
+		{
+			entity_t ent;
+			if (added == FX_MAX_TEMP_ENTITIES)
+				return added;		/* CL_NewTempEntity: none left */
+			memset (&ent, 0, sizeof(ent));
+			memcpy (ent.origin, org, sizeof(org));
+			ent.model = x->beams[b].model;
+			ent.angles[0] = ang[0];
+			ent.angles[1] = ang[1];
+			ent.angles[2] = rand ()%360;
+			ent.colormap = colormap;
+			if (bolts && (ent.model == bolts[0] || ent.model == bolts[1] || ent.model == bolts[2]))
+				ent.flags = RF_FULLBRIGHT|RF_NOSHADOW;
+			if (scene)
+				RC_SceneAddEntity (scene, &ent);
+			added++;
+			for (i = 0; i < 3; i++)
+				org[i] += dist[i]*30;
+			d -= 30;
+		}
 	}
 	return added;
 }
