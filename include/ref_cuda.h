@@ -306,6 +306,30 @@ const cshift_t *RC_FxCshifts (const rc_fx_t *fx);                    /* the four
 int   RC_FxBeam (rc_fx_t *fx, int entity, struct model_s *model, const float *start, const float *end, double time);   /* CL_ParseBeam */
 int   RC_ClientAddTempEntities (rc_fx_t *fx, rc_scene_t *scene, double time, int viewentity, const float *view_lerp_origin,
                                 byte *colormap, struct model_s *const *bolts /* cl_bolt1..3_mod or NULL */);
+/* The view itself: V_CalcRefdef / V_CalcIntermissionRefdef (cl_view.c:758-886) -- eye position (view height, bob, hull
+ * bound, smoothed stair steps), view angles (movement roll, damage kick, idle sway, punch angle), rectangle and fov into
+ * *rd, and the gun (V_AddGun) into the scene; returns the entities added (0 / 1), -1 for a bad argument (fov outside
+ * 1..179: Sys_Error there).  The caller then samples the world where the eye is: RC_ClientSetViewContents (fx, rd,
+ * RC_PointContents (rd->vieworg)) sets RDF_UNDERWATER and the medium's colour shift.  CL_DriftPitch (input state) and the
+ * chase camera (collision traces) are the engine's. */
+typedef struct {
+    double time, oldtime, host_frametime;                 /* cl.time, cl.oldtime, host_frametime */
+    vec3_t lerp_origin;                                   /* cl_entities[cl.viewentity].lerp_origin */
+    vec3_t current_origin, current_angles;                /* ... .current (intermission only) */
+    vec3_t velocity, viewangles, punchangle;              /* cl.velocity, cl.viewangles, cl.punchangle */
+    float  viewheight;                                    /* cl.viewheight */
+    int    onground, health, items, intermission, chase_active;   /* cl.onground, cl.stats[STAT_HEALTH], cl.items, ... */
+    int    vrect[4];                                      /* scr_vrect: x, y, width, height */
+    float  fov_x;                                         /* scr_fov */
+    float  cl_rollangle, cl_rollspeed, cl_bob, cl_bobcycle, cl_bobup, v_kicktime;    /* the cvars (cl_view.c:33-57) */
+    float  v_idlescale, v_iyaw_cycle, v_iroll_cycle, v_ipitch_cycle, v_iyaw_level, v_iroll_level, v_ipitch_level;
+    struct model_s *gun_model; int gun_frame, gun_oldframe; float gun_frametime;    /* cl.viewent */
+    byte  *colormap;                                      /* vid.colormap */
+} rc_viewstate_t;
+void  RC_FxDamageKick (rc_fx_t *fx, int armor, int blood, const float *from, const float *viewer_lerp_origin, const float *viewangles,
+                       float v_kickroll, float v_kickpitch, float v_kicktime);      /* the kick half of CL_ParseDamage */
+int   RC_ClientCalcRefdef (rc_fx_t *fx, rc_scene_t *scene, const rc_viewstate_t *in, refdef_t *rd);
+void  RC_ClientSetViewContents (rc_fx_t *fx, refdef_t *rd, int contents);
 
 /* Renders `n` independent views (R_RenderView semantics each, r_main.c:988-1062) into
  * packed HOST buffers: fb_out n*height*width bytes (8-bit palettised), z_out (may be NULL)

@@ -174,3 +174,60 @@ int clfx_add_entities (clfx_cent_t *in, int n, const clfx_frame_t *fr)
 	return rec_nentities;
 }
 void *clfx_vid_colormap (void) { return vid.colormap; }
+
+/* ---- V_CalcRefdef / V_CalcIntermissionRefdef over the test's view state (the layout of rc_viewstate_t) ---- */
+typedef struct {
+	double time, oldtime, host_frametime;
+	vec3_t lerp_origin, current_origin, current_angles, velocity, viewangles, punchangle;
+	float viewheight;
+	int onground, health, items, intermission, chase_active;
+	int vrect[4];
+	float fov_x;
+	float cl_rollangle, cl_rollspeed, cl_bob, cl_bobcycle, cl_bobup, v_kicktime;
+	float v_idlescale, v_iyaw_cycle, v_iroll_cycle, v_ipitch_cycle, v_iyaw_level, v_iroll_level, v_ipitch_level;
+	struct model_s *gun_model; int gun_frame, gun_oldframe; float gun_frametime;
+	byte *colormap;
+} clfx_viewstate_t;
+extern cvar_t cl_rollangle, cl_rollspeed, cl_bob, cl_bobcycle, cl_bobup, v_kicktime, v_kickroll, v_kickpitch, v_idlescale,
+	v_iyaw_cycle, v_iroll_cycle, v_ipitch_cycle, v_iyaw_level, v_iroll_level, v_ipitch_level;
+extern void V_CalcRefdef (void);
+extern void V_CalcIntermissionRefdef (void);
+extern int r_numentities; extern entity_t r_entities[];
+static int clfx_contents = -1;
+int  CM_PointContents (vec3_t p) { (void)p; return clfx_contents; }
+void clfx_set_contents (int c) { clfx_contents = c; }
+void clfx_set_kick (float roll, float pitch) { v_kickroll.value = roll; v_kickpitch.value = pitch; }
+void clfx_set_viewer (int viewentity, const float *lerp_origin, const float *viewangles, float kicktime)
+{
+	cl.viewentity = viewentity; v_kicktime.value = kicktime;
+	VectorCopy (lerp_origin, cl_entities[viewentity].lerp_origin);
+	VectorCopy (viewangles, cl.viewangles);
+}
+/* returns the entities the view code added (the gun), copied to *gun */
+int clfx_calc_refdef (const clfx_viewstate_t *in, refdef_t *out, entity_t *gun)
+{
+	centity_t *cent;
+	cls.demoplayback = true;		/* no pitch drift: input state */
+	cl.viewentity = 1; cent = &cl_entities[1];
+	cl.time = in->time; cl.oldtime = in->oldtime; host_frametime = in->host_frametime;
+	VectorCopy (in->lerp_origin, cent->lerp_origin);
+	VectorCopy (in->current_origin, cent->current.origin); VectorCopy (in->current_angles, cent->current.angles);
+	VectorCopy (in->velocity, cl.velocity); VectorCopy (in->viewangles, cl.viewangles); VectorCopy (in->punchangle, cl.punchangle);
+	cl.viewheight = in->viewheight; cl.onground = in->onground; cl.stats[STAT_HEALTH] = in->health; cl.items = in->items;
+	chase_active.value = in->chase_active;
+	scr_vrect.x = in->vrect[0]; scr_vrect.y = in->vrect[1]; scr_vrect.width = in->vrect[2]; scr_vrect.height = in->vrect[3];
+	scr_fov.value = in->fov_x;
+	cl_rollangle.value = in->cl_rollangle; cl_rollspeed.value = in->cl_rollspeed; cl_bob.value = in->cl_bob;
+	cl_bobcycle.value = in->cl_bobcycle; cl_bobup.value = in->cl_bobup; v_kicktime.value = in->v_kicktime;
+	v_idlescale.value = in->v_idlescale; v_iyaw_cycle.value = in->v_iyaw_cycle; v_iroll_cycle.value = in->v_iroll_cycle;
+	v_ipitch_cycle.value = in->v_ipitch_cycle; v_iyaw_level.value = in->v_iyaw_level; v_iroll_level.value = in->v_iroll_level;
+	v_ipitch_level.value = in->v_ipitch_level;
+	memset (&cl.viewent, 0, sizeof(cl.viewent));
+	cl.viewent.current.modelindex = in->gun_model ? 7 : 0; cl.model_precache[7] = in->gun_model;
+	cl.viewent.current.frame = in->gun_frame; cl.viewent.prev.frame = in->gun_oldframe; cl.viewent.frametime = in->gun_frametime;
+	r_numentities = 0;
+	if (in->intermission) V_CalcIntermissionRefdef (); else V_CalcRefdef ();
+	*out = cl.refdef;
+	if (r_numentities) *gun = r_entities[0];
+	return r_numentities;
+}

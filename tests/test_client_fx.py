@@ -62,6 +62,10 @@ def ref(tmp_path):
     L.clfx_set_bolts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.clfx_set_frame.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, fp]
     L.V_SetContentsColor.argtypes = [C.c_int]
+    L.clfx_set_contents.argtypes = [C.c_int]
+    L.clfx_set_kick.argtypes = [C.c_float, C.c_float]
+    L.clfx_set_viewer.argtypes = [C.c_int, fp, fp, C.c_float]
+    L.clfx_calc_refdef.argtypes = [C.POINTER(client.rc_viewstate_t), C.POINTER(refdef_t), C.POINTER(entity_t)]
     L.CL_ParseBeam.argtypes = [C.c_void_p]
     return L
 
@@ -498,3 +502,96 @@ def test_beams_match_the_reference(ref, sim_lib):
         for k, (a, b) in enumerate(zip(want, got)):
             assert a[0] == b[0], f"{name} frame {k}: {a[0]} / {b[0]} beam segments"
             assert a[1] == b[1], f"{name} frame {k}: segment entities differ"
+
+
+def test_calc_refdef_matches_the_reference(ref, sim_lib):
+    """V_CalcRefdef / V_CalcIntermissionRefdef with V_CalcBob, V_CalcRoll, V_CalcViewRoll (damage kicks from
+    CL_ParseDamage), V_AddIdle, V_BoundOffsets, the stair smoothing, V_AddGun and the contents at the eye
+    (cl_view.c:159-210, 331-391, 646-886): a 200-frame walk with steps up and down, strafing, damage from all sides, idle
+    sway on and off, death, invisibility, an intermission -- refdef_t, the gun entity and the medium's colour shift bit for bit"""
+    rnd = random.Random(21)
+    gun = (C.c_int * 1)(0)
+    cmap = ref.clfx_vid_colormap()
+    frames = []
+    t, z = 5.0, 24.0
+    for k in range(200):
+        dt = rnd.choice([0.0, 0.008, 0.013, 0.02, 0.05, 0.1])
+        old, t = t, t + dt
+        if rnd.random() < 0.2: z += rnd.choice([16.0, 18.0, 8.0, -16.0, 30.0])        # stairs, drops
+        v = client.default_viewstate()
+        v.time, v.oldtime, v.host_frametime = t, old, dt
+        v.lerp_origin = V(10.0 * k, -3.0 * k, z)
+        v.current_origin = V(10.0 * k + 1, -3.0 * k, z); v.current_angles = V(5.0, 90.0 + k, 0.0)
+        v.velocity = V(rnd.uniform(-400, 400), rnd.uniform(-400, 400), rnd.uniform(-100, 100)) if k % 9 else V(0, 0, 0)
+        v.viewangles = V(rnd.uniform(-60, 60), rnd.uniform(0, 360), rnd.uniform(-5, 5))
+        v.punchangle = V(rnd.uniform(-4, 0), 0.0, 0.0) if k % 5 == 0 else V(0, 0, 0)
+        v.onground = int(k % 4 != 3)
+        v.health = -5 if 120 <= k < 130 else 100
+        v.items = client.IT_INVISIBILITY if 60 <= k < 70 else 0
+        v.intermission = int(150 <= k < 160)
+        v.vrect[:] = [0, 0, 320, 200] if k % 2 else [16, 8, 288, 160]
+        v.fov_x = rnd.choice([90.0, 110.0, 45.0])
+        v.v_idlescale = 1.5 if 80 <= k < 110 else 0.0
+        v.viewheight = rnd.choice([22.0, 22.0, 12.0])
+        v.gun_model = C.addressof(gun) if k % 11 else None
+        v.gun_frame, v.gun_oldframe, v.gun_frametime = k % 6, (k + 5) % 6, t - rnd.choice([0.0, 0.03, 0.07, 0.2])
+        v.colormap = cmap
+        dmg = (rnd.choice([0, 30, 80]), rnd.choice([5, 25, 90]), [10.0 * k + rnd.uniform(-100, 100), -3.0 * k + rnd.uniform(-100, 100), z + 20]) if rnd.random() < 0.15 else None
+        frames.append((v, dmg, rnd.choice([-1, -1, -2, -3, -4, -5])))
+
+    def run_ref():
+        L = ref
+        L.clfx_init(3, 0)
+        L.clfx_set_kick(0.6, 0.6)
+        out = []
+        for v, dmg, contents in frames:
+            if dmg:
+                L.clfx_set_viewer(1, v.lerp_origin, v.viewangles, v.v_kicktime)
+                L.clfx_msg_set((C.c_float * 5)(dmg[0], dmg[1], *dmg[2]), 5)
+                L.CL_ParseDamage()
+            L.clfx_set_contents(contents)
+            rd, g = refdef_t(), entity_t()
+            n = L.clfx_calc_refdef(C.byref(v), C.byref(rd), C.byref(g))
+            cs = (cshift_t * 4)()
+            L.clfx_cshifts(cs)
+            out.append((n, [rd.x, rd.y, rd.width, rd.height, rd.flags], bytes(rd)[28:60], bytes(g) if n else b"", bytes(cs)[:16]))
+        return out
+
+    def run_ours(lib):
+        L = client.bind(C.CDLL(lib))
+        L.RC_SceneNew.restype = C.c_void_p
+        for nm in ("RC_SceneFree", "RC_SceneClear", "RC_SceneReset"): getattr(L, nm).argtypes = [C.c_void_p]
+        L.RC_SceneEndFrame.argtypes = [C.c_void_p, C.POINTER(refdef_t), ip]
+        L.RC_SceneFrames.argtypes = [C.c_void_p, ip]
+        L.RC_SceneFrames.restype = C.POINTER(refdef_t)
+        fx, sc = L.RC_FxNew(0), L.RC_SceneNew()
+        out = []
+        for v, dmg, contents in frames:
+            if dmg:
+                L.RC_FxDamage(fx, dmg[0], dmg[1])
+                L.RC_FxDamageKick(fx, dmg[0], dmg[1], V(*dmg[2]), v.lerp_origin, v.viewangles, 0.6, 0.6, v.v_kicktime)
+            L.RC_SceneReset(sc)
+            rd = refdef_t()
+            n = L.RC_ClientCalcRefdef(fx, sc, C.byref(v), C.byref(rd))
+            assert n in (0, 1)
+            L.RC_ClientSetViewContents(fx, C.byref(rd), contents)
+            k = L.RC_SceneEndFrame(sc, C.byref(refdef_t()), None)
+            cnt = C.c_int()
+            fr = L.RC_SceneFrames(sc, C.byref(cnt))[k]
+            assert fr.num_entities == n
+            g = bytes(fr.entities[0]) if n else b""
+            cs = bytes((cshift_t * 4).from_address(C.addressof(L.RC_FxCshifts(fx).contents)))
+            out.append((n, [rd.x, rd.y, rd.width, rd.height, rd.flags], bytes(rd)[28:60], g, cs[:16]))
+        L.RC_FxFree(fx); L.RC_SceneFree(sc)
+        return out
+
+    want = run_ref()
+    assert {w[0] for w in want} == {0, 1} and {w[1][4] for w in want} == {0, 2}
+    for name, lib in _libs(sim_lib):
+        got = run_ours(lib)
+        for k, (a, b) in enumerate(zip(want, got)):
+            assert a[1] == b[1], f"{name} frame {k}: rectangle / flags {a[1]} {b[1]}"
+            assert a[2] == b[2], (f"{name} frame {k}: fov / vieworg / viewangles " +
+                                  f"{np.frombuffer(a[2], np.float32)} {np.frombuffer(b[2], np.float32)}")
+            assert a[0] == b[0] and a[3] == b[3], f"{name} frame {k}: the gun entity differs"
+            assert a[4] == b[4], f"{name} frame {k}: contents colour"

@@ -33,6 +33,31 @@ class rc_clframe_t(C.Structure):
                 ("bobbingitems", C.c_int), ("viewangles", vec3)]
 
 
+class rc_viewstate_t(C.Structure):
+    _fields_ = [("time", C.c_double), ("oldtime", C.c_double), ("host_frametime", C.c_double),
+                ("lerp_origin", vec3), ("current_origin", vec3), ("current_angles", vec3),
+                ("velocity", vec3), ("viewangles", vec3), ("punchangle", vec3),
+                ("viewheight", C.c_float),
+                ("onground", C.c_int), ("health", C.c_int), ("items", C.c_int), ("intermission", C.c_int), ("chase_active", C.c_int),
+                ("vrect", C.c_int * 4), ("fov_x", C.c_float),
+                ("cl_rollangle", C.c_float), ("cl_rollspeed", C.c_float), ("cl_bob", C.c_float), ("cl_bobcycle", C.c_float),
+                ("cl_bobup", C.c_float), ("v_kicktime", C.c_float),
+                ("v_idlescale", C.c_float), ("v_iyaw_cycle", C.c_float), ("v_iroll_cycle", C.c_float), ("v_ipitch_cycle", C.c_float),
+                ("v_iyaw_level", C.c_float), ("v_iroll_level", C.c_float), ("v_ipitch_level", C.c_float),
+                ("gun_model", C.c_void_p), ("gun_frame", C.c_int), ("gun_oldframe", C.c_int), ("gun_frametime", C.c_float),
+                ("colormap", C.c_void_p)]
+
+
+def default_viewstate():
+    """the cvar defaults of cl_view.c:33-57"""
+    v = rc_viewstate_t()
+    v.cl_rollangle, v.cl_rollspeed, v.cl_bob, v.cl_bobcycle, v.cl_bobup, v.v_kicktime = 2.0, 200.0, 0.02, 0.6, 0.5, 0.5
+    v.v_idlescale, v.v_iyaw_cycle, v.v_iroll_cycle, v.v_ipitch_cycle = 0.0, 2.0, 0.5, 1.0
+    v.v_iyaw_level, v.v_iroll_level, v.v_ipitch_level = 0.3, 0.1, 0.3
+    v.fov_x, v.viewheight, v.health = 90.0, 22.0, 100
+    return v
+
+
 def bind(L):
     fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
     L.RC_FxNew.argtypes = [C.c_int]
@@ -64,6 +89,11 @@ def bind(L):
     L.RC_FxAddCshifts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
     L.RC_FxCshifts.argtypes = [C.c_void_p]
     L.RC_FxCshifts.restype = C.POINTER(cshift_t)
+    L.RC_FxDamageKick.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, C.c_float, C.c_float, C.c_float]
+    L.RC_FxDamageKick.restype = None
+    L.RC_ClientCalcRefdef.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(rc_viewstate_t), C.c_void_p]
+    L.RC_ClientSetViewContents.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.RC_ClientSetViewContents.restype = None
     L.RC_FxBeam.argtypes = [C.c_void_p, C.c_int, C.c_void_p, fp, fp, C.c_double]
     L.RC_ClientAddTempEntities.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, fp, C.c_void_p, C.POINTER(C.c_void_p)]
     return L

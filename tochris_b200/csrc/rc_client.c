@@ -58,6 +58,8 @@ struct rc_fx_s {
 	int    tracercount;
 	cshift_t cshifts[4], prev_cshifts[4];	/* cl.cshifts / cl.prev_cshifts: contents, damage, bonus, powerup (client.h:48-56) */
 	cshift_t cshift_empty;			/* the `v_cshift` command's colour for air (cl_view.c:321, 401-407) */
+	float  dmg_time, dmg_roll, dmg_pitch;	/* v_dmg_time / _roll / _pitch: the view kick of the last damage (cl_view.c:64) */
+	float  oldz;				/* V_CalcRefdef's static: the eye height the stair smoothing has reached */
 	struct { int entity; struct model_s *model; float endtime; float start[3], end[3]; } beams[FX_MAX_BEAMS];	/* cl_beams, cl_tent.c:26 */
 };
 
@@ -911,4 +913,156 @@ int RC_ClientAddTempEntities (rc_fx_t *x, rc_scene_t *scene, double time, int vi
 		}
 	}
 	return added;
+}
+
+/* ---- the view itself: V_CalcRefdef / V_CalcIntermissionRefdef (cl_view.c:159-210, 646-886) ---------------------------------
+ * From the viewer's interpolated state to the frame's refdef_t: eye position (view height, bob, 1/32 off any node plane,
+ * bounded to the player's hull, stair steps smoothed), view angles (movement roll, damage kick, idle sway, punch angle,
+ * the dead player's 80 degree roll), rectangle and field of view, RDF_UNDERWATER and the medium's colour shift from the
+ * contents at the eye, and the gun model as an entity.  Not here: CL_DriftPitch (input state; a demo does not drift:
+ * pass the angles as they are) and the chase camera (it traces against the collision hulls: pass chase_active = 0). */
+static float fx_calc_roll (const rc_viewstate_t *in)		/* V_CalcRoll, cl_view.c:159-180 */
+{
+	float forward[3], right[3], up[3], sign, side, value;
+	RC_AngleVectors (in->viewangles, forward, right, up);
+	side = in->velocity[0]*right[0] + in->velocity[1]*right[1] + in->velocity[2]*right[2];
+	sign = side < 0 ? -1 : 1;
+	side = fabs (side);
+	value = in->cl_rollangle;
+	if (side < in->cl_rollspeed)
+		side = side * value / in->cl_rollspeed;
+	else
+		side = value;
+	return side*sign;
+}
+
+static float fx_calc_bob (const rc_viewstate_t *in)		/* V_CalcBob, cl_view.c:189-210 */
+{
+	float bob, cycle;
+	cycle = in->time - (int)(in->time/in->cl_bobcycle)*in->cl_bobcycle;
+	cycle /= in->cl_bobcycle;
+	if (cycle < in->cl_bobup)
+		cycle = M_PI * cycle / in->cl_bobup;
+	else
+		cycle = M_PI + M_PI*(cycle-in->cl_bobup)/(1.0 - in->cl_bobup);
+	bob = sqrt (in->velocity[0]*in->velocity[0] + in->velocity[1]*in->velocity[1]) * in->cl_bob;
+	bob = bob * (0.3 + 0.7*sin (cycle));
+	bob = bob < 4 ? bob : 4;		/* bound (-7, bob, 4) */
+	return -7 > bob ? -7 : bob;
+}
+
+/* the view-kick half of CL_ParseDamage (cl_view.c:378-391); RC_FxDamage is the colour half */
+void RC_FxDamageKick (rc_fx_t *x, int armor, int blood, const float *from_in, const float *viewer_lerp_origin, const float *viewangles,
+		      float v_kickroll, float v_kickpitch, float v_kicktime)
+{
+	float count = (blood + armor) * 0.5, from[3], forward[3], right[3], up[3], side;
+	if (count < 10)
+		count = 10;
+	for (int i = 0; i < 3; i++) from[i] = from_in[i] - viewer_lerp_origin[i];
+	fx_normalize (from);
+	RC_AngleVectors (viewangles, forward, right, up);
+	side = from[0]*right[0] + from[1]*right[1] + from[2]*right[2];
+	x->dmg_roll = count*side*v_kickroll;
+	side = from[0]*forward[0] + from[1]*forward[1] + from[2]*forward[2];
+	x->dmg_pitch = count*side*v_kickpitch;
+	x->dmg_time = v_kicktime;
+}
+
+int RC_ClientCalcRefdef (rc_fx_t *x, rc_scene_t *scene, const rc_viewstate_t *in, refdef_t *rd)
+{
+	if (!x || !in || !rd)
+		return -1;
+	if (in->fov_x < 1 || in->fov_x > 179)
+		return -1;			/* CalcFov: Sys_Error ("Bad fov") there */
+	rd->x = in->vrect[0]; rd->y = in->vrect[1]; rd->width = in->vrect[2]; rd->height = in->vrect[3];
+	rd->fov_x = in->fov_x;
+	rd->fov_y = RC_CalcFov (rd->fov_x, rd->width, rd->height);
+	if (in->intermission)
+	{
+		/* V_CalcIntermissionRefdef, cl_view.c:758-795: the player entity's own origin and angles, always swaying */
+		for (int i = 0; i < 3; i++) { rd->vieworg[i] = in->current_origin[i]; rd->viewangles[i] = in->current_angles[i]; }
+		rd->viewangles[2] += 1 * sin (in->time*in->v_iroll_cycle) * in->v_iroll_level;
+		rd->viewangles[0] += 1 * sin (in->time*in->v_ipitch_cycle) * in->v_ipitch_level;
+		rd->viewangles[1] += 1 * sin (in->time*in->v_iyaw_cycle) * in->v_iyaw_level;
+		rd->vieworg[0] += 1.0/32; rd->vieworg[1] += 1.0/32; rd->vieworg[2] += 1.0/32;
+		return 0;
+	}
+	const float bob = fx_calc_bob (in);
+	rd->vieworg[0] = in->lerp_origin[0]; rd->vieworg[1] = in->lerp_origin[1];
+	rd->vieworg[2] = in->lerp_origin[2] + in->viewheight + bob;
+	rd->vieworg[0] += 1.0/32; rd->vieworg[1] += 1.0/32; rd->vieworg[2] += 1.0/32;
+	for (int i = 0; i < 3; i++) rd->viewangles[i] = in->viewangles[i];
+	/* V_CalcViewRoll, :734-751 */
+	rd->viewangles[2] += fx_calc_roll (in);
+	if (x->dmg_time > 0)
+	{
+		rd->viewangles[2] += x->dmg_time/in->v_kicktime*x->dmg_roll;
+		rd->viewangles[0] += x->dmg_time/in->v_kicktime*x->dmg_pitch;
+		x->dmg_time -= in->host_frametime;
+	}
+	if (in->health <= 0)
+		rd->viewangles[2] = 80;
+	/* V_AddIdle (v_idlescale), :674-679 */
+	rd->viewangles[2] += in->v_idlescale * sin (in->time*in->v_iroll_cycle) * in->v_iroll_level;
+	rd->viewangles[0] += in->v_idlescale * sin (in->time*in->v_ipitch_cycle) * in->v_ipitch_level;
+	rd->viewangles[1] += in->v_idlescale * sin (in->time*in->v_iyaw_cycle) * in->v_iyaw_level;
+	/* V_BoundOffsets, :646-666: never outside the player's clipping hull */
+	{
+		static const float lo[3] = { 14, 14, 22 }, hi[3] = { 14, 14, 30 };
+		for (int i = 0; i < 3; i++)
+		{
+			if (rd->vieworg[i] < in->lerp_origin[i] - lo[i]) rd->vieworg[i] = in->lerp_origin[i] - lo[i];
+			else if (rd->vieworg[i] > in->lerp_origin[i] + hi[i]) rd->vieworg[i] = in->lerp_origin[i] + hi[i];
+		}
+	}
+	for (int i = 0; i < 3; i++) rd->viewangles[i] = rd->viewangles[i] + in->punchangle[i];
+	/* stair steps, :839-858: the eye follows a step up at 80 units a second, at most 12 behind */
+	if (in->onground && in->lerp_origin[2] - x->oldz > 0)
+	{
+		float steptime = in->time - in->oldtime;
+		if (steptime < 0)
+			steptime = 0;
+		x->oldz += steptime * 80;
+		if (x->oldz > in->lerp_origin[2])
+			x->oldz = in->lerp_origin[2];
+		if (in->lerp_origin[2] - x->oldz > 12)
+			x->oldz = in->lerp_origin[2] - 12;
+		rd->vieworg[2] += x->oldz - in->lerp_origin[2];
+	}
+	else
+		x->oldz = in->lerp_origin[2];
+	/* V_AddGun, :687-726 */
+	if (!in->chase_active && !(in->items & 524288 /* IT_INVISIBILITY */) && in->health > 0 && in->gun_model)
+	{
+		entity_t gun;
+		float forward[3], right[3], up[3];
+		memset (&gun, 0, sizeof(gun));
+		gun.model = in->gun_model;
+		gun.frame = in->gun_frame;
+		gun.oldframe = in->gun_oldframe;
+		gun.flags = RF_WEAPONMODEL|RF_DEPTHSCALE|RF_MINLIGHT|RF_NOSHADOW;
+		gun.framelerp = (in->time - in->gun_frametime) * 10;
+		gun.framelerp = gun.framelerp < 1 ? gun.framelerp : 1;
+		gun.framelerp = 0 > gun.framelerp ? 0 : gun.framelerp;
+		gun.colormap = in->colormap;
+		for (int i = 0; i < 3; i++) gun.origin[i] = rd->vieworg[i];
+		gun.angles[0] = -rd->viewangles[0]; gun.angles[1] = rd->viewangles[1]; gun.angles[2] = in->viewangles[2];
+		gun.angles[2] -= in->v_idlescale * sin (in->time*in->v_iroll_cycle) * in->v_iroll_level;
+		gun.angles[0] -= in->v_idlescale * sin (in->time*in->v_ipitch_cycle) * in->v_ipitch_level;
+		gun.angles[1] -= in->v_idlescale * sin (in->time*in->v_iyaw_cycle) * in->v_iyaw_level;
+		RC_AngleVectors (gun.angles, forward, right, up);
+		for (int i = 0; i < 3; i++) gun.origin[i] = gun.origin[i] + (bob * 0.4)*forward[i];
+		if (scene)
+			RC_SceneAddEntity (scene, &gun);
+		return 1;
+	}
+	return 0;
+}
+
+/* what both view functions do once the eye is placed (cl_view.c:783-794, 865-873): RDF_UNDERWATER and the colour of the
+ * medium from the contents at the eye (RC_PointContents (rd->vieworg)) */
+void RC_ClientSetViewContents (rc_fx_t *x, refdef_t *rd, int contents)
+{
+	rd->flags = contents <= -3 /* CONTENTS_WATER */ ? RDF_UNDERWATER : 0;
+	RC_FxSetContentsColor (x, contents);
 }
