@@ -37,6 +37,7 @@ class ViewSpec:
     dlights: List[Tuple[float, float, float, float]] = field(default_factory=list)   # x, y, z, radius
     particles: List[Tuple[float, float, float, int]] = field(default_factory=list)   # x, y, z, colour
     cshifts: List[Tuple[int, int, int, int]] = field(default_factory=list)           # r, g, b, percent (ref.h:49-53)
+    fov_y: Optional[float] = None                        # default: CalcFov (fov_x, w, h); a replayed frame brings its own
 
 
 def write_base_assets(basedir: str):
@@ -98,7 +99,7 @@ def build_refdefs(specs: Sequence[ViewSpec], width: int, height: int,
         rd.oldtime = float(sp.time)
         rd.flags = sp.flags
         rd.fov_x = sp.fov_x
-        rd.fov_y = calc_fov_y(sp.fov_x, w, h)
+        rd.fov_y = calc_fov_y(sp.fov_x, w, h) if sp.fov_y is None else sp.fov_y
         for k in range(3):
             rd.vieworg[k] = float(sp.origin[k])
             rd.viewangles[k] = float(sp.angles[k])
