@@ -17,6 +17,7 @@ roofline / cpu_baseline: see DESIGN.md "Measurement".
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import multiprocessing as mp
 import os
@@ -124,22 +125,51 @@ def run_reference_cpu(basedir, mapname, w, h, specs, seconds=8.0, passes=0):
 
 # ------------------------------------------------------------------------------ clocks ----
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU while the timed steps run.  In-process NVML (what nvidia-smi itself asks,
+    the recipe's clocks line field for field), initialised BEFORE the clock starts: an `nvidia-smi` child per sample took
+    tens of milliseconds to start -- on every rank, inside a timed region of a few milliseconds, with the driver locks
+    NVML's start-up takes -- and left one sample.  Falls back to the nvidia-smi child when pynvml is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop = index, [], False
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.sample()              # (also pages in what the calls need)
+            self.rows.clear()
+        except Exception:  # noqa: BLE001
+            self.nv = self.h = None
+
+    def sample(self):
+        nv, h = self.nv, self.h
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:  # noqa: BLE001
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda m: "Active" if bits & m else "Not Active"   # noqa: E731
+        self.rows.append([str(self.index), str(sm), str(mx), "", act(nv.nvmlClocksThrottleReasonHwSlowdown), act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          act(nv.nvmlClocksThrottleReasonSwThermalSlowdown), act(nv.nvmlClocksThrottleReasonSwPowerCap)])
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    self.sample()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nv is not None else 0.1)
 
     def summary(self):
         sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
@@ -234,6 +264,8 @@ def run_extra(kind, args, rank, world, local):
     if world > 1:
         dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    gc.collect()
+    gc.disable()
     t_w0 = time.perf_counter()
     for k, (a, b) in enumerate(evs):
         a.record(stream)
@@ -241,6 +273,7 @@ def run_extra(kind, args, rank, world, local):
         b.record(stream)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_w0) * 1e3
+    gc.enable()
     if world > 1:
         dist.barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -428,24 +461,32 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         status |= step(last=True)
     torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None       # (rank 0 prints the line: its GPU's clocks; NVML starts before the barrier)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = r.stats()["kernel_launches"]
     launches = 0
     torch.cuda.synchronize()
+    # (a step is 0.2 ms of device work and the host enqueues it while the L2 flush runs: a collection of the interpreter's
+    # garbage inside the K steps would leave the device idle between a step's two events -- on one of N ranks, which the
+    # max over ranks then reports for all)
+    gc.collect()
+    gc.disable()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         status |= step(evs[k], last=(k == args.steps - 1))
         launches += r.stats()["kernel_launches"]
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    gc.enable()
     if world > 1:
         dist.barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    sampler.stop = True
+    if sampler is not None:
+        sampler.stop = True
     if world > 1 and args.gather == "nccl-groups":
         r.set_group_callback(None)
     gather_check = None
@@ -506,10 +547,13 @@ def run_ours(args):
             status |= r.wait()
     pipelined(3)
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()
     t0 = time.perf_counter()
     pipelined(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
     e2e_ok &= all(int(b.astype(np.uint64).sum()) == ref_sum for b in fb_np2)
     # ---- the PCIe floor under e2e: the same bytes, device plane -> the same pinned buffer, nothing else running
     cevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
